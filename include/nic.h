@@ -1,0 +1,222 @@
+/*
+ * nic.h - C ABI of libnic_b200.so: hand-written sm_100a kernels for the forward pass
+ * (+ likelihood / rate-distortion terms) of the hyperprior / autoregressive-context
+ * image codec of achraf-15/neural_image_compression.
+ *
+ * The reference has no FFI of its own (it is pure PyTorch); each entry below names the
+ * reference Python call (file:line under /root/reference) whose arithmetic it replaces.
+ * The Python host in neural_image_compression_b200/ binds these with ctypes
+ * (see INTEGRATION.md for the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *     the caller owns every buffer, the library allocates and frees nothing
+ *     (except small immutable tables created once per process).
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronises the device.
+ *   - every entry returns 0 on success or a negative NIC_E_* code; nic_last_error()
+ *     then holds a thread-local description.  Nothing throws or aborts.
+ *   - reductions are deterministic (fixed-order trees, no floating-point atomics).
+ *   - the library is compiled for sm_100a only; on any other device entries return
+ *     NIC_E_UNSUPPORTED_ARCH.  There is no CPU or multi-architecture fallback.
+ */
+#ifndef NIC_B200_H
+#define NIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NIC_ABI_VERSION 1
+
+enum {
+  NIC_OK = 0,
+  NIC_E_BADSHAPE = -1,
+  NIC_E_BADALIGN = -2,
+  NIC_E_UNSUPPORTED_ARCH = -3,
+  NIC_E_CUDA = -4,
+  NIC_E_UNSUPPORTED = -5,
+  NIC_E_WORKSPACE = -6
+};
+
+/* tensor layouts / element types understood by the conv engine */
+enum { NIC_LAYOUT_NCHW = 0, NIC_LAYOUT_NHWC = 1 };
+enum { NIC_DT_F32 = 0, NIC_DT_BF16 = 1 };
+
+/* arithmetic of the contraction */
+enum {
+  NIC_PREC_FP32 = 0,   /* CUDA-core FFMA, fp32 operands and accumulation (parity grade)           */
+  NIC_PREC_BF16 = 1,   /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulation in TMEM          */
+  NIC_PREC_BF16X3 = 2  /* tcgen05, operands split hi+lo in bf16, 3 MMAs per product (fp32 grade)   */
+};
+
+/* fused epilogues */
+enum {
+  NIC_EPI_BIAS = 0,    /* y = acc + b                                   Components.py:16,73,103  */
+  NIC_EPI_LRELU = 1,   /* y = leaky_relu(acc + b, 0.01)                 Components.py:70,72,100,102; ParametersModels.py:30,32 */
+  NIC_EPI_GDN = 2,     /* v = acc + b; y = v * rsqrt(beta + gamma.v^2)  Components.py:11,13,15 (compressai GDN) */
+  NIC_EPI_IGDN = 3     /* v = acc + b; y = v *  sqrt(beta + gamma.v^2)  Components.py:40,42,44 */
+};
+
+/* quantisation mode of the likelihood kernels, Models.py:55-66 */
+enum {
+  NIC_Q_ROUND = 0,     /* x_in = rint(x)   (eval, Models.py:63-64; round-half-even, sign kept)   */
+  NIC_Q_NOISE = 1,     /* x_in = x + noise (training, Models.py:57-58; noise injected by caller) */
+  NIC_Q_PASSTHRU = 2   /* x_in = x         (caller already quantised)                            */
+};
+
+/*
+ * One 2-D convolution or transposed convolution, PyTorch semantics
+ * (torch.nn.Conv2d / ConvTranspose2d with dilation 1, groups 1).
+ * Replaces the nn.Conv2d / nn.ConvTranspose2d (+ GDN / LeakyReLU) pairs of
+ * Components.py:9-17, 38-46, 68-74, 98-104, ContextModels.py:18-20 and
+ * ParametersModels.py:29-35.
+ */
+typedef struct nic_conv_desc {
+  int32_t n, c_in, h_in, w_in;      /* input  [n, c_in, h_in, w_in] (logical NCHW extents)      */
+  int32_t c_out, h_out, w_out;      /* output [n, c_out, h_out, w_out]                          */
+  int32_t kh, kw, stride, pad;      /* kernel, stride (1|2), padding                            */
+  int32_t transposed;               /* 0: Conv2d, 1: ConvTranspose2d                            */
+  int32_t output_padding;           /* ConvTranspose2d only                                     */
+  int32_t mask_a;                   /* 1: PixelCNN mask 'A' (ContextModels.py:13-16)            */
+  int32_t epilogue;                 /* NIC_EPI_*                                                */
+  int32_t precision;                /* NIC_PREC_*                                               */
+  int32_t in_layout, out_layout;    /* NIC_LAYOUT_*                                             */
+  int32_t in_dtype, out_dtype;      /* NIC_DT_*                                                 */
+  int32_t out_c_total, out_c_offset;/* output tensor has out_c_total channels; this conv writes
+                                       channels [out_c_offset, out_c_offset + c_out) (makes the
+                                       torch.cat of Models.py:73 free); 0,0 = plain             */
+} nic_conv_desc;
+
+int nic_version(void);
+const char* nic_last_error(void);
+/* 0 when the current device is sm_100 (B200), NIC_E_UNSUPPORTED_ARCH otherwise */
+int nic_check_device(void);
+
+/* ---- weight preparation (once per load_state_dict; derived caches, never saved) ---------- */
+
+/* elements (of the packed dtype) the packed weight of `d` occupies */
+size_t nic_packed_weight_elems(const nic_conv_desc* d);
+/*
+ * Re-layout a reference-format weight for the engine: Conv2d [c_out, c_in, kh, kw]
+ * (Components.py:10-16), ConvTranspose2d [c_in, c_out, kh, kw] (Components.py:39-45),
+ * masked taps dropped when d->mask_a (the reference zeroes them in place, ContextModels.py:19).
+ * fp32: [tap][c_in][c_out] f32.  bf16: [tap][c_out][c_in] bf16 (K-major B operand);
+ * bf16x3: hi block followed by lo block.
+ */
+int nic_pack_conv_weight(const nic_conv_desc* d, const float* w_ref, void* w_packed, void* stream);
+/*
+ * compressai GDN reparametrisation (oracle/gdn.py):
+ *   beta_eff = max(beta, sqrt(beta_min + 2^-36))^2 - 2^-36,  gamma_eff = max(gamma, 2^-18)^2 - 2^-36.
+ * gamma_packed: fp32 -> [c_in(j)][c_out(i)] f32; bf16 -> [i][j] bf16 (hi, then lo when bf16x3).
+ */
+int nic_pack_gdn(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw,
+                 float* beta_eff, void* gamma_packed, int32_t precision, void* stream);
+
+/* ---- transforms ---------------------------------------------------------------------------- */
+
+size_t nic_conv_workspace_bytes(const nic_conv_desc* d);
+/*
+ * y = epilogue(conv(x, w) + bias).  gdn_gamma / gdn_beta are the nic_pack_gdn outputs and are
+ * only read for NIC_EPI_GDN / NIC_EPI_IGDN.
+ */
+int nic_conv_fwd(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                 const void* gdn_gamma, const float* gdn_beta, void* y,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Stand-alone GDN / IGDN (compressai.layers.gdn.GDN.forward; call sites Components.py:11-15, 40-44) for
+ * callers that invoke the layer on its own: y = x * rsqrt(beta + gamma . x^2) (inverse: * sqrt).
+ * x, y: f32 in `layout`; gamma_packed / beta_eff from nic_pack_gdn(NIC_PREC_FP32).
+ */
+int nic_gdn_fwd(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, int32_t layout, int32_t inverse,
+                const float* gamma_packed, const float* beta_eff, float* y, void* stream);
+
+/*
+ * Latent hand-off after the last g_a / h_a conv (Models.py:52-66): reads v (NHWC f32, the
+ * engine's layout), writes the reference-layout copy `v_nchw` (dict entries 'y' / 'z'),
+ * the quantised / noised tensor `v_in_nchw` ('y_in' / 'z_in') and the engine-layout copy
+ * `v_in_nhwc` (dtype out_dtype) that h_s / the context model / g_s consume.
+ * noise_nchw is read only for NIC_Q_NOISE.
+ */
+int nic_latent_handoff(const float* v_nhwc, int32_t n, int32_t c, int32_t h, int32_t w, int32_t qmode,
+                       const float* noise_nchw, float* v_nchw, float* v_in_nchw, void* v_in_nhwc,
+                       int32_t out_dtype, void* stream);
+
+/* ---- likelihoods --------------------------------------------------------------------------- */
+
+/* number of float partial sums per image the likelihood / sse kernels write */
+int32_t nic_partials_per_image(void);
+
+/*
+ * K-component Gaussian-mixture likelihood (K = 1: mean-scale Gaussian), NCHW f32 throughout.
+ * Replaces ParametersModels.py:43-64 (chunk / view / softmax / softplus + 1e-6),
+ * EntropyModels.py:192-233 (+ utils.py:6-8, clamp at :31) and the torch.log of Models.py:87,
+ * and accumulates sum(logp) per image for RateDistortionLoss.py:13.
+ *   y          [b, m, hw]          input latent (quantised here according to qmode)
+ *   raw        [b, 3*k*m, hw]      (k = 1: [b, 2*m, hw]) entropy-parameter net output
+ *   y_in, p, logp  [b, m, hw]      outputs ('y_in', 'p_y', 'logp_y'); y_in may be NULL
+ *   weights, mus, sigmas [b, k, m, hw]  outputs, all three NULL for the lean variant
+ *                                   (k = 1: weights must be NULL, mus/sigmas are mu/sigma)
+ *   logp_partials [b, nic_partials_per_image()]  per-image partial sums of logp (fixed order)
+ */
+int nic_gm_likelihood_fwd(const float* y, const float* raw, const float* noise,
+                          int32_t b, int32_t m, int32_t hw, int32_t k, int32_t qmode,
+                          float* y_in, float* p, float* logp,
+                          float* weights, float* mus, float* sigmas,
+                          float* logp_partials, void* stream);
+
+/*
+ * The reference's conditional-model call on ALREADY-activated parameters, for callers that use
+ * GaussianConditional / GaussianMixtureConditional on their own (EntropyModels.py:192-233, clamp :31):
+ *   p = max(sum_k w_k * (Phi((x+.5-mu_k)/s_k) - Phi((x-.5-mu_k)/s_k)), 1e-9)
+ * x, p [b, m, hw]; weights / mus / sigmas [b, k, m, hw] (k = 1: weights NULL).
+ */
+int nic_gm_pmf_fwd(const float* x, const float* weights, const float* mus, const float* sigmas,
+                   int32_t b, int32_t m, int32_t hw, int32_t k, float* p, void* stream);
+
+/*
+ * Factorized prior likelihood (per-channel 1-3-3-3-1 MLP), NCHW f32.
+ * Replaces EntropyModels.py:88-151 (+ clamp :31) and the torch.log of Models.py:84.
+ *   fparams [c, 43]: per channel, the reference parameters after their fixed transforms:
+ *     softplus(matrices.0)[3] bias0[3] tanh(factors.0)[3] softplus(matrices.1)[9] bias1[3]
+ *     tanh(factors.1)[3] softplus(matrices.2)[9] bias2[3] tanh(factors.2)[3]
+ *     softplus(matrices.3)[3] bias3[1]   (see nic_pack_factorized)
+ */
+int nic_pack_factorized(int32_t c, const float* m0, const float* b0, const float* f0,
+                        const float* m1, const float* b1, const float* f1,
+                        const float* m2, const float* b2, const float* f2,
+                        const float* m3, const float* b3, float* fparams, void* stream);
+int nic_factorized_likelihood_fwd(const float* z, const float* fparams, const float* noise,
+                                  int32_t b, int32_t c, int32_t hw, int32_t qmode,
+                                  float* z_in, float* p, float* logp,
+                                  float* logp_partials, void* stream);
+
+/* ---- distortion + rate-distortion terms ----------------------------------------------------- */
+
+/* per-image partial sums of (x_hat - x)^2, NCHW f32, chw = 3*h*w (RateDistortionLoss.py:26) */
+int nic_sse_fwd(const float* x_hat, const float* x, int32_t b, int64_t chw,
+                float* sse_partials, void* stream);
+
+/* per-image partial sums of v [b, per_image] f32 (the torch.sum of RateDistortionLoss.py:13-14 when a
+ * caller hands rd_loss tensors this library did not produce) */
+int nic_sum_fwd(const float* v, int32_t b, int64_t per_image, float* partials, void* stream);
+
+/*
+ * Folds the three partial-sum arrays into the rd_loss terms (RateDistortionLoss.py:13-34):
+ *   per_image [3][b]: bits_y, bits_z, mse_per_image
+ *   scalars   [8]   : bpp_y, bpp_z, bpp_total, mse, psnr, loss, bits_y_mean, bits_z_mean
+ * (psnr = -10 log10(mean_b mse + 1e-8); loss = bpp_total + lambda * 255^2 * mse).
+ * One launch, one block, fixed summation order.
+ */
+int nic_rd_finalize(const float* logp_y_partials, const float* logp_z_partials,
+                    const float* sse_partials, int32_t b, int32_t num_pixels, int64_t chw,
+                    float lambda_rd, float* per_image, float* scalars, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIC_B200_H */

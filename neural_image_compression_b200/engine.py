@@ -1,0 +1,157 @@
+"""Host-side glue between the nn.Module mirror of the reference and the C ABI (include/nic.h).
+
+Everything here is plumbing: it owns no arithmetic.  Tensors are allocated by PyTorch and passed to
+the library as raw device pointers on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import (ConvDesc, DT_BF16, DT_F32, EPI_BIAS, EPI_GDN, EPI_IGDN, EPI_LRELU, LAYOUT_NCHW, LAYOUT_NHWC,
+                   PRECISIONS, PREC_FP32, check, current_stream, ptr)
+
+DEFAULT_PRECISION = os.environ.get("NIC_PRECISION", "fp32")
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.NicError(f"{what}: expected a CUDA tensor on a B200; this package has no CPU path")
+
+
+def act_dtype(precision: str):
+    return torch.float32 if precision == "fp32" else torch.bfloat16
+
+
+def conv_out_hw(conv: nn.Module, h: int, w: int):
+    k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+    if isinstance(conv, nn.ConvTranspose2d):
+        op = conv.output_padding[0]
+        return (h - 1) * s - 2 * p + k + op, (w - 1) * s - 2 * p + k + op
+    return (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+
+
+class ConvOp:
+    """One reference conv layer (+ the GDN / LeakyReLU that follows it) bound to nic_conv_fwd.
+
+    Holds packed-weight caches keyed by precision; a cache entry is rebuilt when the parameter
+    storage or its in-place version counter changes (load_state_dict, optimizer step, .to()).
+    """
+
+    def __init__(self, conv: nn.Module, epilogue: int = EPI_BIAS, gdn: Optional[nn.Module] = None, mask_a: bool = False):
+        self.conv, self.epilogue, self.gdn, self.mask_a = conv, epilogue, gdn, mask_a
+        self.transposed = isinstance(conv, nn.ConvTranspose2d)
+        self._cache = {}
+
+    def desc(self, n, h, w, precision, in_layout, out_layout, in_dtype, out_dtype, out_c_total=0, out_c_offset=0) -> ConvDesc:
+        cv = self.conv
+        ho, wo = conv_out_hw(cv, h, w)
+        d = ConvDesc()
+        d.n, d.c_in, d.h_in, d.w_in = n, cv.in_channels, h, w
+        d.c_out, d.h_out, d.w_out = cv.out_channels, ho, wo
+        d.kh, d.kw, d.stride, d.pad = cv.kernel_size[0], cv.kernel_size[1], cv.stride[0], cv.padding[0]
+        d.transposed = int(self.transposed)
+        d.output_padding = cv.output_padding[0] if self.transposed else 0
+        d.mask_a = int(self.mask_a)
+        d.epilogue, d.precision = self.epilogue, PRECISIONS[precision]
+        d.in_layout, d.out_layout, d.in_dtype, d.out_dtype = in_layout, out_layout, in_dtype, out_dtype
+        d.out_c_total, d.out_c_offset = out_c_total, out_c_offset
+        return d
+
+    def _key(self):
+        ts = [self.conv.weight, self.conv.bias]
+        if self.gdn is not None:
+            ts += [self.gdn.beta, self.gdn.gamma]
+        return tuple((t.data_ptr(), t._version, str(t.device)) for t in ts)
+
+    def packed(self, precision: str):
+        key = self._key()
+        ent = self._cache.get(precision)
+        if ent is not None and ent[0] == key:
+            return ent[1]
+        lib = _lib.load()
+        cv = self.conv
+        require_cuda(cv.weight, "conv weight")
+        dev = cv.weight.device
+        d = self.desc(1, 64, 64, precision, LAYOUT_NHWC, LAYOUT_NHWC, DT_F32, DT_F32)
+        elems = lib.nic_packed_weight_elems(C.byref(d))
+        if elems == 0:
+            check(-1, "nic_packed_weight_elems")
+        wp = torch.empty(elems, dtype=act_dtype(precision), device=dev)
+        with torch.cuda.device(dev):
+            w32 = cv.weight.detach().float().contiguous()
+            check(lib.nic_pack_conv_weight(C.byref(d), ptr(w32), ptr(wp), current_stream()), "nic_pack_conv_weight")
+            bias = cv.bias.detach().float().contiguous()
+            gamma = beta = None
+            if self.gdn is not None:
+                c = cv.out_channels
+                mult = 2 if precision == "bf16x3" else 1
+                gamma = torch.empty(c * c * mult, dtype=act_dtype(precision), device=dev)
+                beta = torch.empty(c, dtype=torch.float32, device=dev)
+                check(lib.nic_pack_gdn(c, float(self.gdn.beta_min), ptr(self.gdn.beta.detach().float().contiguous()),
+                                       ptr(self.gdn.gamma.detach().float().contiguous()), ptr(beta), ptr(gamma),
+                                       PRECISIONS[precision], current_stream()), "nic_pack_gdn")
+        out = (wp, bias, gamma, beta)
+        self._cache[precision] = (key, out)
+        return out
+
+    def run(self, x: torch.Tensor, n: int, h: int, w: int, precision: str, in_layout=LAYOUT_NHWC, out_layout=LAYOUT_NHWC,
+            out: Optional[torch.Tensor] = None, out_c_total: int = 0, out_c_offset: int = 0,
+            out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """x: contiguous tensor in `in_layout`; returns (or fills) the output in `out_layout`."""
+        lib = _lib.load()
+        require_cuda(x, "conv input")
+        in_dt = DT_BF16 if x.dtype == torch.bfloat16 else DT_F32
+        if out_dtype is None:
+            out_dtype = act_dtype(precision)
+        out_dt = DT_BF16 if out_dtype == torch.bfloat16 else DT_F32
+        d = self.desc(n, h, w, precision, in_layout, out_layout, in_dt, out_dt, out_c_total, out_c_offset)
+        ctot = out_c_total or d.c_out
+        if out is None:
+            shape = (n, d.h_out, d.w_out, ctot) if out_layout == LAYOUT_NHWC else (n, ctot, d.h_out, d.w_out)
+            out = torch.empty(shape, dtype=out_dtype, device=x.device)
+        wp, bias, gamma, beta = self.packed(precision)
+        ws_bytes = lib.nic_conv_workspace_bytes(C.byref(d))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+        check(lib.nic_conv_fwd(C.byref(d), ptr(x), ptr(wp), ptr(bias), ptr(gamma), ptr(beta), ptr(out), ptr(ws), ws_bytes,
+                               current_stream()), "nic_conv_fwd")
+        return out
+
+
+def run_sequential_nchw(ops, x: torch.Tensor, precision: str) -> torch.Tensor:
+    """A chain of ConvOps with reference (NCHW f32) tensors at both ends; NHWC inside."""
+    require_cuda(x, "input")
+    x = x.contiguous().float()
+    n, _, h, w = x.shape
+    cur, layout = x, LAYOUT_NCHW
+    with torch.cuda.device(x.device):
+        for i, op in enumerate(ops):
+            last = i == len(ops) - 1
+            cur = op.run(cur, n, h, w, precision, in_layout=layout, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC,
+                         out_dtype=torch.float32 if last else None)
+            h, w = conv_out_hw(op.conv, h, w)
+            layout = LAYOUT_NHWC
+    return cur
+
+
+def latent_handoff(v_nhwc: torch.Tensor, qmode: int, noise: Optional[torch.Tensor], in_dtype: torch.dtype):
+    """Models.py:52-66.  Returns (v_nchw, v_in_nchw, v_in_nhwc)."""
+    lib = _lib.load()
+    n, h, w, c = v_nhwc.shape
+    v = torch.empty((n, c, h, w), dtype=torch.float32, device=v_nhwc.device)
+    v_in = torch.empty_like(v)
+    v_in_nhwc = torch.empty((n, h, w, c), dtype=in_dtype, device=v_nhwc.device)
+    if noise is not None:
+        noise = noise.contiguous().float()
+    check(lib.nic_latent_handoff(ptr(v_nhwc), n, c, h, w, qmode, ptr(noise), ptr(v), ptr(v_in), ptr(v_in_nhwc),
+                                 DT_BF16 if in_dtype == torch.bfloat16 else DT_F32, current_stream()), "nic_latent_handoff")
+    return v, v_in, v_in_nhwc
+
+
+def partials(b: int, device) -> torch.Tensor:
+    return torch.empty((b, _lib.load().nic_partials_per_image()), dtype=torch.float32, device=device)

@@ -1,0 +1,64 @@
+"""CPU: the oracle restatement against the vectors the REAL reference produced (tests/golden, made by
+oracle/make_golden.py from /root/reference).  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import forward as O
+from tests import helpers as H
+
+
+@pytest.mark.parametrize("case", H.golden_cases())
+def test_oracle_matches_reference_vectors(case):
+    g = H.load_golden(case)
+    M, K, gain = int(g["M"]), int(g["K"]), bool(g["gain"])
+    model = H.seeded_model(M, K, gain)
+    assert H.state_digest(model.state_dict()) == str(g["state_digest"]), "seeded weights differ from the reference's"
+    x = torch.from_numpy(g["x"])
+    out = O.forward(model.state_dict(), x, M, K, training=False)
+    for key in g.files:
+        if not key.startswith("out_"):
+            continue
+        ref = g[key]
+        got = out[key[4:]].numpy()
+        assert got.shape == ref.shape, key
+        if key in ("out_y_in", "out_z_in"):
+            assert np.array_equal(got, ref), key
+        else:
+            np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-7, err_msg=key)
+    rd = O.rd_loss(out, x, 0.005)
+    for key in ("bpp_y", "bpp_z", "bpp_total", "mse", "psnr", "bits_y", "bits_z", "bits_total"):
+        assert abs(rd[key] - float(g["rd_" + key])) <= 1e-6 * max(1.0, abs(float(g["rd_" + key]))), key
+    assert abs(float(rd["loss"]) - float(g["rd_loss"])) <= 1e-5 * abs(float(g["rd_loss"]))
+    np.testing.assert_allclose(rd["mse_per_image"].numpy(), g["rd_mse_per_image"], rtol=1e-6)
+    np.testing.assert_allclose(rd["psnr_per_image"].numpy(), g["rd_psnr_per_image"], rtol=1e-6)
+
+
+def test_gain_cases_have_nontrivial_symbols():
+    g = H.load_golden("c2_k3_128x192_gain")
+    assert (g["out_y_in"] != 0).mean() > 0.5 and (g["out_z_in"] != 0).mean() > 0.2
+
+
+def test_fp64_shadow_is_close_to_fp32():
+    g = H.load_golden("c1_k1_128_gain")
+    model = H.seeded_model(128, 1, True)
+    x = torch.from_numpy(g["x"])
+    o32 = O.forward(model.state_dict(), x, 128, 1)
+    o64 = O.forward(model.state_dict(), x, 128, 1, dtype=torch.float64)
+    assert (o32["y"].double() - o64["y"]).abs().max() < 1e-3
+    real, _ = H.symbol_mismatches(o32["y_in"].numpy(), o64["y_in"].numpy(), o64["y"].numpy(), tau=1e-3)
+    assert real == 0
+
+
+def test_mask_a_has_12_live_taps():
+    m = O.mask_a(torch.zeros(2, 3, 5, 5))
+    assert int(m[0, 0].sum()) == 12
+    assert m[0, 0, 2, 2] == 0 and m[0, 0, 2, 1] == 1 and m[0, 0, 3].sum() == 0
+
+
+def test_training_mode_uses_injected_noise():
+    model = H.seeded_model(128, 1, False)
+    x = H.seeded_input((1, 3, 64, 64))
+    nz, ny = torch.rand(1, 128, 1, 1) - 0.5, torch.rand(1, 128, 4, 4) - 0.5
+    out = O.forward(model.state_dict(), x, 128, 1, training=True, noise_z=nz, noise_y=ny)
+    assert torch.equal(out["y_in"], out["y"] + ny) and torch.equal(out["z_in"], out["z"] + nz)
