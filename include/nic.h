@@ -95,6 +95,8 @@ int nic_version(void);
 const char* nic_last_error(void);
 /* 0 when the current device is sm_100 (B200), NIC_E_UNSUPPORTED_ARCH otherwise */
 int nic_check_device(void);
+/* number of CUDA kernels this library has launched in this process (all threads) */
+uint64_t nic_launch_count(void);
 
 /* ---- weight preparation (once per load_state_dict; derived caches, never saved) ---------- */
 

@@ -1,6 +1,6 @@
 // Error plumbing + device check for the C ABI (include/nic.h).
 #include <stdarg.h>
-#include <mutex>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -28,7 +28,13 @@ int check_cuda(cudaError_t e, const char* what) {
   return fail(NIC_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
-int check_launch(const char* what) { return check_cuda(cudaGetLastError(), what); }
+static std::atomic<uint64_t> g_launches{0};
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(cudaGetLastError(), what);
+}
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 }  // namespace nic
 
@@ -50,6 +56,8 @@ int nic_check_device(void) {
                      "libnic_b200 is built for sm_100a only; device %d is sm_%d%d (no fallback)", dev, major, minor);
   return NIC_OK;
 }
+
+uint64_t nic_launch_count(void) { return nic::launch_count(); }
 
 int32_t nic_partials_per_image(void) { return nic::kPartials; }
 

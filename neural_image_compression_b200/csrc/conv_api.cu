@@ -71,8 +71,8 @@ int nic_conv_fwd(const nic_conv_desc* d, const void* x, const void* w_packed, co
                  void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = nic_check_device()) return rc;
   if (int rc = validate_conv_desc(d)) return rc;
-  if (!x || !w_packed || !bias || !y) return fail(NIC_E_BADSHAPE, "conv: null pointer");
   if (d->n == 0) return NIC_OK;
+  if (!x || !w_packed || !bias || !y) return fail(NIC_E_BADSHAPE, "conv: null pointer");
   switch (d->precision) {
     case NIC_PREC_FP32:
       return conv_fwd_fp32(d, x, w_packed, bias, gdn_gamma, gdn_beta, y, workspace, workspace_bytes, as_stream(stream));

@@ -11,7 +11,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-GAIN_Y, GAIN_Z = 136.2, 3.86          # frozen gain-init constants (oracle/make_golden.py)
+# seeded weight sets, see oracle/make_golden.py: (gain on last g_a conv, gain on last h_a conv, + on sigma biases)
+INITS = {"plain": (1.0, 1.0, 0.0), "gain": (136.2, 3.86, 0.0), "calib": (34.0, 3.86, 3.0)}
 
 
 def golden_cases():
@@ -29,18 +30,30 @@ def state_digest(sd) -> str:
     return h.hexdigest()
 
 
-def seeded_model(M, K, gain, precision="fp32"):
-    """Product model with the weights the reference draws under torch.manual_seed(0)."""
+def apply_init(sd, init):
+    gy, gz, sigma_bias = INITS[init]
+    for k in ("encoder.net.6.weight", "encoder.net.6.bias"):
+        sd[k] = sd[k] * gy
+    for k in ("hyper_encoder.net.4.weight", "hyper_encoder.net.4.bias"):
+        sd[k] = sd[k] * gz
+    if sigma_bias:
+        b = sd["entropy_parameters.net.4.bias"].clone()
+        n = b.numel()
+        start = n // 2 if n % 3 else 2 * n // 3          # [mu | sigma] (K = 1) or [w | mu | sigma]
+        b[start:] += sigma_bias
+        sd["entropy_parameters.net.4.bias"] = b
+    return sd
+
+
+def seeded_model(M, K, init="plain", precision="fp32"):
+    """Product model with the weights the reference draws under torch.manual_seed(0), re-scaled per `init`."""
     from neural_image_compression_b200.Models import JointAutoregressiveHierarchical
+    if isinstance(init, bool):
+        init = "gain" if init else "plain"
     torch.manual_seed(0)
     model = JointAutoregressiveHierarchical(M, K=K, precision=precision)
-    if gain:
-        sd = {k: v.clone() for k, v in model.state_dict().items()}
-        for k in ("encoder.net.6.weight", "encoder.net.6.bias"):
-            sd[k] = sd[k] * GAIN_Y
-        for k in ("hyper_encoder.net.4.weight", "hyper_encoder.net.4.bias"):
-            sd[k] = sd[k] * GAIN_Z
-        model.load_state_dict(sd)
+    if init != "plain":
+        model.load_state_dict(apply_init({k: v.clone() for k, v in model.state_dict().items()}, init))
     return model
 
 

@@ -17,7 +17,11 @@ DICT_KEYS_KN = (DICT_KEYS_K1 - {"mu", "sigma"}) | {"weights", "mus", "sigmas"}
 TAU = {"fp32": 2e-3, "bf16x3": 5e-3}
 
 
-def check_against(out, rd, ref, ref_rd, K, precision="fp32", x_hat_tol=1e-4):
+def check_against(out, rd, ref, ref_rd, K, precision="fp32", x_hat_tol=1e-4, bpp_band=0.0):
+    """bpp_band: |bpp(reference fp32) - bpp(reference arithmetic in fp64)| of the case.  Where it exceeds the 1e-3
+    criterion (gain-init: most likelihoods sit at the 1e-9 clamp and are erf-difference rounding noise) the total is
+    required to land within that band of the reference instead, and bits are additionally compared on the
+    well-conditioned elements (p_ref >= 1e-6) at the strict tolerance."""
     report = {}
     assert set(out) == (DICT_KEYS_K1 if K == 1 else DICT_KEYS_KN)
     for k, v in out.items():
@@ -35,8 +39,17 @@ def check_against(out, rd, ref, ref_rd, K, precision="fp32", x_hat_tol=1e-4):
             bad, worst = H.likelihood_close(out[name].cpu().numpy(), ref[name])
             report[name] = (bad, worst)
             assert bad <= 1e-5 * ref[name].size, f"{name}: {bad} outside tolerance (max abs err {worst:.2e})"
-    assert abs(rd["bpp_total"] - ref_rd["bpp_total"]) <= H.BPP_TOL, (rd["bpp_total"], ref_rd["bpp_total"])
-    assert abs(rd["bpp_y"] - ref_rd["bpp_y"]) <= H.BPP_TOL and abs(rd["bpp_z"] - ref_rd["bpp_z"]) <= H.BPP_TOL
+    tol = max(H.BPP_TOL, bpp_band)
+    report["bpp"] = (rd["bpp_total"], ref_rd["bpp_total"])
+    assert abs(rd["bpp_total"] - ref_rd["bpp_total"]) <= tol, (rd["bpp_total"], ref_rd["bpp_total"], tol)
+    assert abs(rd["bpp_y"] - ref_rd["bpp_y"]) <= tol and abs(rd["bpp_z"] - ref_rd["bpp_z"]) <= H.BPP_TOL
+    if same.all():
+        good = ref["p_y"] >= 1e-6
+        npix = ref["x_hat"].shape[0] * ref["x_hat"].shape[2] * ref["x_hat"].shape[3]
+        ours = -(out["logp_y"].cpu().numpy().astype(np.float64)[good]).sum() / np.log(2.0) / npix
+        theirs = -(ref["logp_y"].astype(np.float64)[good]).sum() / np.log(2.0) / npix
+        report["bpp_y_conditioned"] = (ours, theirs)
+        assert abs(ours - theirs) <= H.BPP_TOL, (ours, theirs)
     assert abs(rd["psnr"] - ref_rd["psnr"]) <= H.PSNR_TOL, (rd["psnr"], ref_rd["psnr"])
     xe = float(np.abs(out["x_hat"].cpu().numpy() - ref["x_hat"]).max() / np.abs(ref["x_hat"]).max())
     report["x_hat_rel"] = xe
@@ -49,35 +62,40 @@ def check_against(out, rd, ref, ref_rd, K, precision="fp32", x_hat_tol=1e-4):
 def test_model_matches_reference_vectors_fp32(case):
     from neural_image_compression_b200.RateDistortionLoss import rd_loss
     g = H.load_golden(case)
-    M, K, gain = int(g["M"]), int(g["K"]), bool(g["gain"])
-    model = H.seeded_model(M, K, gain, precision="fp32").cuda()
+    M, K, init = int(g["M"]), int(g["K"]), str(g["init"])
+    band = abs(float(g["rd_bpp_total"]) - float(g["fp64_bpp_total"])) if init == "gain" else 0.0
+    model = H.seeded_model(M, K, init, precision="fp32").cuda()
     x = torch.from_numpy(g["x"]).cuda()
     out = model(x, training=False)
     rd = rd_loss(out, x, 0.005)
     ref = {k[4:]: g[k] for k in g.files if k.startswith("out_")}
     ref_rd = {k[3:]: float(g[k]) for k in g.files if k.startswith("rd_") and g[k].ndim == 0}
-    rep = check_against(out, rd, ref, ref_rd, K)
+    rep = check_against(out, rd, ref, ref_rd, K, bpp_band=band)
     print(case, rep)
     assert out["training"] is False
 
 
-def test_model_matches_oracle_at_kodak_shape_fp32():
-    """One 768x512 image (BASELINE configs[1] shape at batch 1), gain-init, oracle run live."""
+@pytest.mark.parametrize("init", ["calib", "gain"])
+def test_model_matches_oracle_at_kodak_shape_fp32(init):
+    """One 768x512 image (BASELINE configs[1] shape at batch 1), oracle run live (fp32, and fp64 for the band)."""
     from neural_image_compression_b200.RateDistortionLoss import rd_loss
-    model = H.seeded_model(128, 3, True, precision="fp32")
+    model = H.seeded_model(128, 3, init, precision="fp32")
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     x = H.seeded_input((1, 3, 512, 768))
     ref_t = O.forward(sd, x, 128, 3)
     ref_rd = O.rd_loss(ref_t, x, 0.005)
+    band = 0.0
+    if init == "gain":
+        band = abs(O.rd_loss(O.forward(sd, x, 128, 3, dtype=torch.float64), x, 0.005)["bpp_total"] - ref_rd["bpp_total"])
     ref = {k: v.numpy() for k, v in ref_t.items() if torch.is_tensor(v) and not k.startswith("_")}
     model = model.cuda()
     out = model(x.cuda(), training=False)
     rd = rd_loss(out, x.cuda(), 0.005)
-    print(check_against(out, rd, ref, ref_rd, 3))
+    print(init, check_against(out, rd, ref, ref_rd, 3, bpp_band=band))
 
 
 def test_training_forward_with_injected_noise_fp32():
-    model = H.seeded_model(128, 3, True, precision="fp32")
+    model = H.seeded_model(128, 3, "calib", precision="fp32")
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     x = H.seeded_input((2, 3, 64, 128))
     torch.manual_seed(12)
@@ -96,7 +114,7 @@ def test_training_forward_with_injected_noise_fp32():
 
 
 def test_lean_forward_skips_parameter_tensors():
-    model = H.seeded_model(128, 3, False, precision="fp32").cuda()
+    model = H.seeded_model(128, 3, "plain", precision="fp32").cuda()
     x = H.seeded_input((1, 3, 64, 64)).cuda()
     full, lean = model(x, training=False), model(x, training=False, lean=True)
     assert "weights" not in lean and torch.equal(full["p_y"], lean["p_y"]) and torch.equal(full["x_hat"], lean["x_hat"])
@@ -105,7 +123,7 @@ def test_lean_forward_skips_parameter_tensors():
 def test_full_size_batch_properties_fp32():
     """BASELINE configs[1] at full size (16 x 3 x 512 x 768): size-independent properties instead of an oracle run."""
     from neural_image_compression_b200.RateDistortionLoss import rd_loss
-    model = H.seeded_model(128, 3, True, precision="fp32").cuda()
+    model = H.seeded_model(128, 3, "calib", precision="fp32").cuda()
     x = H.seeded_input((16, 3, 512, 768)).cuda()
     out = model(x, training=False)
     rd = rd_loss(out, x, 0.005)
@@ -116,7 +134,7 @@ def test_full_size_batch_properties_fp32():
     # (2) quantisation is idempotent and integral; likelihoods are probabilities; logp = log p
     assert torch.equal(torch.round(out["y_in"]), out["y_in"]) and torch.equal(torch.round(out["y"]), out["y_in"])
     for k in ("p_y", "p_z"):
-        assert float(out[k].min()) >= 1e-9 and float(out[k].max()) <= 1 + 1e-6
+        assert float(out[k].min()) >= float(np.float32(1e-9)) and float(out[k].max()) <= 1 + 1e-6
     assert torch.allclose(out["logp_y"], torch.log(out["p_y"]), atol=1e-6)
     assert torch.allclose(out["weights"].sum(1), torch.ones_like(out["y"]), atol=1e-5)
     # (3) rate/distortion terms are the means of the per-image terms

@@ -6,7 +6,7 @@ from tests import helpers as H
 
 
 def test_state_dict_layout_matches_reference():
-    m = H.seeded_model(128, 3, False)
+    m = H.seeded_model(128, 3)
     sd = m.state_dict()
     assert len(sd) == 84 and sum(p.numel() for p in m.parameters()) == 7312707
     assert tuple(sd["decoder.net.6.weight"].shape) == (128, 3, 5, 5)
@@ -23,10 +23,10 @@ def test_state_dict_layout_matches_reference():
 
 def test_k1_variant_and_attributes():
     from neural_image_compression_b200.EntropyModels import GaussianConditional, GaussianMixtureConditional
-    m1 = H.seeded_model(128, 1, False)
+    m1 = H.seeded_model(128, 1)
     assert sum(p.numel() for p in m1.parameters()) == 6738371
     assert isinstance(m1.conditional, GaussianConditional) and m1.distribution == "Mean-Scale Gaussian"
-    m3 = H.seeded_model(128, 3, False)
+    m3 = H.seeded_model(128, 3)
     assert isinstance(m3.conditional, GaussianMixtureConditional) and m3.distribution == "Mixture of Gaussians"
     for attr in ("encoder", "decoder", "hyper_encoder", "hyper_decoder", "factorized_entropy_model", "context_model",
                  "entropy_parameters", "conditional", "M", "K", "H"):
@@ -47,7 +47,7 @@ def test_constructor_errors_match_reference():
 
 
 def test_channel_cdf_pmf_diagnostics_run_on_cpu():
-    m = H.seeded_model(128, 1, False)
+    m = H.seeded_model(128, 1)
     x = torch.arange(-5, 6, dtype=torch.float32)
     cdf = m.factorized_entropy_model.channel_cdf(3, x)
     pmf = m.factorized_entropy_model.channel_pmf(3, x)

@@ -11,8 +11,8 @@ from tests import helpers as H
 @pytest.mark.parametrize("case", H.golden_cases())
 def test_oracle_matches_reference_vectors(case):
     g = H.load_golden(case)
-    M, K, gain = int(g["M"]), int(g["K"]), bool(g["gain"])
-    model = H.seeded_model(M, K, gain)
+    M, K, init = int(g["M"]), int(g["K"]), str(g["init"])
+    model = H.seeded_model(M, K, init)
     assert H.state_digest(model.state_dict()) == str(g["state_digest"]), "seeded weights differ from the reference's"
     x = torch.from_numpy(g["x"])
     out = O.forward(model.state_dict(), x, M, K, training=False)
@@ -39,9 +39,21 @@ def test_gain_cases_have_nontrivial_symbols():
     assert (g["out_y_in"] != 0).mean() > 0.5 and (g["out_z_in"] != 0).mean() > 0.2
 
 
+def test_calib_cases_are_well_conditioned_and_gain_cases_are_not():
+    """The reference's own fp32-vs-fp64 spread: < 1e-5 bpp on calib (the 1e-3 criterion is meaningful there), > 1e-3 on
+    gain (likelihoods at the clamp are erf-difference rounding noise)."""
+    for case in H.golden_cases():
+        g = H.load_golden(case)
+        band = abs(float(g["rd_bpp_total"]) - float(g["fp64_bpp_total"]))
+        if str(g["init"]) == "calib":
+            assert band < 1e-5 and (g["out_y_in"] != 0).mean() > 0.5 and float(g["out_p_y"].min()) > 1e-6, (case, band)
+        if str(g["init"]) == "gain":
+            assert band > 1e-3, (case, band)
+
+
 def test_fp64_shadow_is_close_to_fp32():
     g = H.load_golden("c1_k1_128_gain")
-    model = H.seeded_model(128, 1, True)
+    model = H.seeded_model(128, 1, 'gain')
     x = torch.from_numpy(g["x"])
     o32 = O.forward(model.state_dict(), x, 128, 1)
     o64 = O.forward(model.state_dict(), x, 128, 1, dtype=torch.float64)
@@ -57,7 +69,7 @@ def test_mask_a_has_12_live_taps():
 
 
 def test_training_mode_uses_injected_noise():
-    model = H.seeded_model(128, 1, False)
+    model = H.seeded_model(128, 1, 'plain')
     x = H.seeded_input((1, 3, 64, 64))
     nz, ny = torch.rand(1, 128, 1, 1) - 0.5, torch.rand(1, 128, 4, 4) - 0.5
     out = O.forward(model.state_dict(), x, 128, 1, training=True, noise_z=nz, noise_y=ny)
