@@ -43,11 +43,11 @@ static float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 // one thread issues 4 MMAs (K = 64) reading A from row offset r0; all 4 warps read TMEM back to D[128][128].
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) mma_probe_kernel(const __nv_bfloat16* A, const __nv_bfloat16* B, float* D, int rows_total, int r0,
-                                                        int base_offset, int* status) {
+                                                        int base_offset, int* status, int sbo_rows = 8) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                       // rows_total * 128 B (<= 160 rows -> 20 KB)
-  uint8_t* sB = smem + 24 * 1024;           // 128 * 128 B
+  uint8_t* sB = smem + 48 * 1024;           // 128 * 128 B
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) mma_probe_kernel(const __nv_bfloat16* A, 
     const uint32_t a0 = smem_u32(sA) + r0 * 128, b0 = smem_u32(sB);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      umma_bf16(tm, umma_desc_sw128(a0 + k * 32, 1024, base_offset), umma_desc_sw128(b0 + k * 32, 1024, 0), idesc, k > 0);
+      umma_bf16(tm, umma_desc_sw128(a0 + k * 32, sbo_rows * 128, base_offset), umma_desc_sw128(b0 + k * 32, 1024, 0), idesc, k > 0);
     umma_commit(&bar);
   }
   __syncwarp();
@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(128) mma_probe_kernel(const __nv_bfloat16* A, 
   if (warp == 0) tmem_dealloc(tm, 128);
 }
 
-static int run_mma_probe(int r0, int base_offset, bool verbose) {
-  const int rows_total = 160;
+static int run_mma_probe(int r0, int base_offset, bool verbose, int sbo_rows = 8) {
+  const int rows_total = 16 * sbo_rows + 40 > 384 ? 384 : 16 * sbo_rows + 40;
   std::vector<__nv_bfloat16> hA(rows_total * 64), hB(128 * 64);
   srand(1234);
   for (auto& v : hA) v = __float2bfloat16((rand() % 17 - 8) / 8.0f);
@@ -102,9 +102,9 @@ static int run_mma_probe(int r0, int base_offset, bool verbose) {
   CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0, 128 * 128 * 4)); CK(cudaMemset(dS, 0, 4));
-  const int smem = 24 * 1024 + 16 * 1024 + 1024;
+  const int smem = 48 * 1024 + 16 * 1024 + 1024;
   CK(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  mma_probe_kernel<<<1, 128, smem>>>(dA, dB, dD, rows_total, r0, base_offset, dS);
+  mma_probe_kernel<<<1, 128, smem>>>(dA, dB, dD, rows_total, r0, base_offset, dS, sbo_rows);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("  r0=%d base_offset=%d: CUDA error %s\n", r0, base_offset, cudaGetErrorString(e)); exit(3); }
   std::vector<float> hD(128 * 128); int st;
@@ -113,12 +113,12 @@ static int run_mma_probe(int r0, int base_offset, bool verbose) {
   for (int m = 0; m < 128; ++m)
     for (int n = 0; n < 128; ++n) {
       double ref = 0;
-      for (int k = 0; k < 64; ++k) ref += bf2f(hA[(m + r0) * 64 + k]) * bf2f(hB[n * 64 + k]);
+      for (int k = 0; k < 64; ++k) ref += bf2f(hA[((m / 8) * sbo_rows + (m % 8) + r0) * 64 + k]) * bf2f(hB[n * 64 + k]);
       const double err = fabs(ref - hD[m * 128 + n]);
       if (err > maxerr) maxerr = err;
       if (err > 1e-3) ++bad;
     }
-  if (verbose || bad) printf("  r0=%d base_offset=%d: status=%d bad=%d/16384 maxerr=%.4g  %s\n", r0, base_offset, st, bad, maxerr, (bad == 0 && st == 0) ? "OK" : "MISMATCH");
+  if (verbose || bad) printf("  sbo_rows=%d r0=%d base_offset=%d: status=%d bad=%d/16384 maxerr=%.4g  %s\n", sbo_rows, r0, base_offset, st, bad, maxerr, (bad == 0 && st == 0) ? "OK" : "MISMATCH");
   cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dS);
   return bad == 0 && st == 0;
 }
@@ -359,6 +359,11 @@ int main(int argc, char** argv) {
     ok2b &= run_mma_probe(r0, r0 & 7, true);
   }
   printf("  -> row offsets with base_offset=0: %s; with base_offset=r0%%8: %s\n", ok2a ? "ALL OK" : "some mismatch", ok2b ? "ALL OK" : "some mismatch");
+  printf("T2b 8-row groups at a stride that is not a multiple of 1024 B (8-pixel-wide tiles inside a wider patch)\n");
+  int ok2c = 1;
+  for (int sbo_rows : {10, 12, 9, 16, 18})
+    for (int r0 : {0, 1, 3, 13}) ok2c &= run_mma_probe(r0, 0, true, sbo_rows);
+  printf("  -> %s\n", ok2c ? "ALL OK" : "some mismatch");
   printf("T3 TMA tiled 4-D loads (NHWC, SW128, OOB zero fill)\n");
   int ok3 = run_tma_probe(enc, 1, -2, -1, 16, 8);
   ok3 &= run_tma_probe(enc, 1, 12, 15, 16, 8);
@@ -372,6 +377,7 @@ int main(int argc, char** argv) {
   run_tma_bw(enc, 128, 64);
   run_tma_bw(enc, 256, 64);
   run_tma_bw(enc, 128, 1024);
+  printf("SUMMARY T2b=%d\n", ok2c);
   printf("SUMMARY T1=%d T2(base0)=%d T2(baseR)=%d T3=%d T3(stride2)=%d T4=%d T4(stride2)=%d\n", ok1, ok2a, ok2b, ok3, ok3s, ok4, ok4s);
   return 0;
 }
