@@ -142,11 +142,12 @@ int nic_gdn_fwd(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, int3
  * engine's layout), writes the reference-layout copy `v_nchw` (dict entries 'y' / 'z'),
  * the quantised / noised tensor `v_in_nchw` ('y_in' / 'z_in') and the engine-layout copy
  * `v_in_nhwc` (dtype out_dtype) that h_s / the context model / g_s consume.
- * noise_nchw is read only for NIC_Q_NOISE.
+ * v_nhwc_bf16 (optional) receives a bf16 NHWC copy of the UNquantised v (h_a reads y, Models.py:53).
+ * noise_nchw is read only for NIC_Q_NOISE.  Any output pointer may be NULL.
  */
 int nic_latent_handoff(const float* v_nhwc, int32_t n, int32_t c, int32_t h, int32_t w, int32_t qmode,
                        const float* noise_nchw, float* v_nchw, float* v_in_nchw, void* v_in_nhwc,
-                       int32_t out_dtype, void* stream);
+                       int32_t out_dtype, void* v_nhwc_bf16, void* stream);
 
 /* ---- likelihoods --------------------------------------------------------------------------- */
 

@@ -100,15 +100,16 @@ class JointAutoregressiveHierarchical(nn.Module):
                 h, w = engine.conv_out_hw(op.conv, h, w)
                 layout = LAYOUT_NHWC
             y_nhwc = a                                                     # f32 [B, hy, wy, M]
-            y, y_in, y_in_nhwc = engine.latent_handoff(y_nhwc, qmode, noise_y, adt)
+            lowp = adt != torch.float32
+            y, y_in, y_in_nhwc, y_lowp = engine.latent_handoff(y_nhwc, qmode, noise_y, adt, want_lowp=lowp)
 
             # ---- h_a (reads the unquantised y, Models.py:53) ------------------------------------
-            a, h, w = (y_nhwc if adt == torch.float32 else y_nhwc.to(adt)), hy, wy
+            a, h, w = (y_lowp if lowp else y_nhwc), hy, wy
             ha = self.hyper_encoder.ops
             for i, op in enumerate(ha):
                 a = op.run(a, B, h, w, prec, out_dtype=torch.float32 if i == len(ha) - 1 else None)
                 h, w = engine.conv_out_hw(op.conv, h, w)
-            z, z_in, z_in_nhwc = engine.latent_handoff(a, qmode, noise_z, adt)
+            z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, qmode, noise_z, adt)
 
             # ---- h_s -> psi = combined[..., 2M:4M];  context -> phi = combined[..., 0:2M] -------
             combined = torch.empty((B, hy, wy, 4 * M), dtype=adt, device=x.device)

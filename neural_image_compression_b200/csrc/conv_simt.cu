@@ -120,6 +120,7 @@ struct SimtParams {
   long ys_n, ys_c, ys_h, ys_w;
   int epilogue;       // NIC_EPI_*; GDN / IGDN here mean "x * rsqrt/sqrt(acc + bias)" with x read back from the input
   int a_square;       // square the A operand on load (GDN's x^2)
+  int out_bf16;       // store the result as bf16 (hand-off to the tensor-core arm); strides are still in elements
   TapTable tt;
 };
 
@@ -291,7 +292,9 @@ conv_simt_kernel(const SimtParams p) {
     if (m >= P) continue;
     const int ox = static_cast<int>(m % wp), oy = static_cast<int>((m / wp) % hp);
     const int img = static_cast<int>(m / (static_cast<long>(wp) * hp));
-    float* yrow = p.y + img * p.ys_n + static_cast<long>(oy * os + py) * p.ys_h + static_cast<long>(ox * os + px) * p.ys_w;
+    const long yoff = img * p.ys_n + static_cast<long>(oy * os + py) * p.ys_h + static_cast<long>(ox * os + px) * p.ys_w;
+    float* yrow = p.y + yoff;
+    __nv_bfloat16* yrow_b = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff;
     const float* xrow = p.x + img * p.xs_n + static_cast<long>(oy) * p.xs_h + static_cast<long>(ox) * p.xs_w;  // GDN: same pixel
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -309,7 +312,10 @@ conv_simt_kernel(const SimtParams p) {
         }
         v[j] = t;
       }
-      if (HN == 4 && p.ys_c == 1 && cbase + 3 < p.cout && ((reinterpret_cast<uintptr_t>(yrow + cbase) & 15) == 0)) {
+      if (p.out_bf16) {
+#pragma unroll
+        for (int j = 0; j < HN; ++j) if (cbase + j < p.cout) yrow_b[(cbase + j) * p.ys_c] = __float2bfloat16_rn(v[j]);
+      } else if (HN == 4 && p.ys_c == 1 && cbase + 3 < p.cout && ((reinterpret_cast<uintptr_t>(yrow + cbase) & 15) == 0)) {
         *reinterpret_cast<float4*>(yrow + cbase) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
 #pragma unroll
@@ -319,6 +325,7 @@ conv_simt_kernel(const SimtParams p) {
   }
 }
 
+static int launch_simt(const SimtParams& p, cudaStream_t st);
 static void set_strides(int layout, long c, long h, long w, long* sn, long* sc, long* sh, long* sw) {
   if (layout == NIC_LAYOUT_NCHW) { *sn = c * h * w; *sc = h * w; *sh = w; *sw = 1; }
   else { *sn = h * w * c; *sh = w * c; *sw = c; *sc = 1; }
@@ -349,6 +356,19 @@ static int launch_simt(const SimtParams& p, cudaStream_t st) {
     else conv_simt_kernel<128, 128, 8, 8, false><<<grid, block, 0, st>>>(p);
   }
   return check_launch("conv_simt_kernel");
+}
+
+// conv + bias (+ LeakyReLU) with f32 input, optional bf16 NHWC output: used by the tensor-core arm for the 3-channel first layer
+int conv_fwd_fp32_ex(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y, int out_bf16_nhwc,
+                     cudaStream_t st) {
+  SimtParams p{};
+  if (int rc = build_tap_table(d, &p.tt)) return rc;
+  p.n = d->n; p.cin = d->c_in; p.hin = d->h_in; p.win = d->w_in; p.cout = d->c_out; p.hout = d->h_out; p.wout = d->w_out;
+  p.x = static_cast<const float*>(x); p.w = static_cast<const float*>(w_packed); p.bias = bias; p.y = static_cast<float*>(y);
+  set_strides(d->in_layout, d->c_in, d->h_in, d->w_in, &p.xs_n, &p.xs_c, &p.xs_h, &p.xs_w);
+  set_strides(out_bf16_nhwc ? NIC_LAYOUT_NHWC : d->out_layout, d->c_out, d->h_out, d->w_out, &p.ys_n, &p.ys_c, &p.ys_h, &p.ys_w);
+  p.epilogue = d->epilogue; p.a_square = 0; p.out_bf16 = out_bf16_nhwc;
+  return launch_simt(p, st);
 }
 
 // fp32 arm of nic_conv_fwd
@@ -411,7 +431,8 @@ int gdn_fwd_fp32(const float* x, int n, int c, int h, int w, int layout, int inv
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 latent_handoff_kernel(const float* __restrict__ v, int n, int c, int h, int w, int qmode, const float* __restrict__ noise,
-                      float* __restrict__ v_nchw, float* __restrict__ vin_nchw, void* __restrict__ vin_nhwc, int out_dtype) {
+                      float* __restrict__ v_nchw, float* __restrict__ vin_nchw, void* __restrict__ vin_nhwc, int out_dtype,
+                      __nv_bfloat16* __restrict__ v_lowp) {
   // 32 x 32 (pixel x channel) transpose tiles through shared memory: coalesced on both layouts
   __shared__ float tile[32][33];
   __shared__ float tile_q[32][33];
@@ -422,7 +443,10 @@ latent_handoff_kernel(const float* __restrict__ v, int n, int c, int h, int w, i
   for (int r = tyy; r < 32; r += 8) {
     const int pix = p0 + r, ch = c0 + tx;
     float val = 0.f;
-    if (pix < hw && ch < c) val = v[(static_cast<long>(img) * hw + pix) * c + ch];
+    if (pix < hw && ch < c) {
+      val = v[(static_cast<long>(img) * hw + pix) * c + ch];
+      if (v_lowp) v_lowp[(static_cast<long>(img) * hw + pix) * c + ch] = __float2bfloat16_rn(val);
+    }
     tile[r][tx] = val;
   }
   __syncthreads();
@@ -468,14 +492,15 @@ int nic_gdn_fwd(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, int3
 
 int nic_latent_handoff(const float* v_nhwc, int32_t n, int32_t c, int32_t h, int32_t w, int32_t qmode,
                        const float* noise_nchw, float* v_nchw, float* v_in_nchw, void* v_in_nhwc,
-                       int32_t out_dtype, void* stream) {
+                       int32_t out_dtype, void* v_nhwc_bf16, void* stream) {
   if (int rc = nic_check_device()) return rc;
   if (n < 0 || c < 1 || h < 1 || w < 1) return fail(NIC_E_BADSHAPE, "latent_handoff: n=%d c=%d h=%d w=%d", n, c, h, w);
   if (qmode == NIC_Q_NOISE && !noise_nchw) return fail(NIC_E_BADSHAPE, "latent_handoff: NIC_Q_NOISE needs noise");
   if (n == 0) return NIC_OK;
   if (n > 65535) return fail(NIC_E_BADSHAPE, "latent_handoff: n=%d > 65535", n);
   dim3 grid((h * w + 31) / 32, (c + 31) / 32, n);
-  latent_handoff_kernel<<<grid, 256, 0, as_stream(stream)>>>(v_nhwc, n, c, h, w, qmode, noise_nchw, v_nchw, v_in_nchw, v_in_nhwc, out_dtype);
+  latent_handoff_kernel<<<grid, 256, 0, as_stream(stream)>>>(v_nhwc, n, c, h, w, qmode, noise_nchw, v_nchw, v_in_nchw, v_in_nhwc, out_dtype,
+                                                                   static_cast<__nv_bfloat16*>(v_nhwc_bf16));
   return check_launch("latent_handoff_kernel");
 }
 

@@ -1,18 +1,617 @@
-// tcgen05 / TMEM / TMA arm of the conv engine (NIC_PREC_BF16, NIC_PREC_BF16X3) - under construction.
+// tcgen05 / TMEM / TMA arm of the conv engine (NIC_PREC_BF16): implicit-GEMM convolution on the 5th-gen
+// tensor cores of sm_100a, bf16 operands, fp32 accumulation in tensor memory.
+//
+// Formulation (conv_common.cuh): out[pixels, c_out] = sum over taps, c_in of shifted-input . W_tap.
+//
+// One persistent CTA per SM, 7 warps:
+//   warp 0   A producer   TMA (cp.async.bulk.tensor.4d) loads of input PATCHES: for an output tile of 16 rows x 8
+//                         pixels the (16 + halo) x (8 + halo) input pixels of one 64-channel chunk land ONCE in shared
+//                         memory (128-byte swizzle, one 128 B row per pixel); stride-2 convs load the four
+//                         even/odd "planes" of the input with TMA element strides of 2.  Conv zero padding is the
+//                         TMA out-of-bounds fill.
+//   warp 1   B producer   TMA loads of the [c_out tile x 64] weight slab of each (tap, chunk) into a ring.
+//   warp 2   MMA issuer   one thread issues tcgen05.mma (M = 128, N = c_out tile, K = 16) for every tap straight
+//                         from the patch: the A descriptor of tap (dy, dx) starts at patch pixel (dy, dx) and walks
+//                         16 groups of 8 consecutive pixels with a stride of one patch row - no im2col copy,
+//                         every input byte is read from L2 once per chunk instead of once per tap
+//                         (measured basis: tools/tc_probe.cu T2/T2b, profiles/r1_tc_probe.txt).
+//   warps 3-6 epilogue    tcgen05.ld the accumulator (double-buffered in TMEM so the next tile's MMAs overlap),
+//                         add bias, LeakyReLU, or GDN / IGDN: the squares go back to shared memory as a bf16
+//                         K-major tile, a second tcgen05.mma contracts them with gamma into another TMEM region and
+//                         the epilogue applies x * rsqrt(beta + .) (or sqrt) - the GDN of Components.py:11-15, 40-44
+//                         never touches HBM.
+//
+// Activations are NHWC bf16 between layers (c_in a multiple of 64).  The 3-channel first layer runs its
+// 75-deep contraction on the CUDA cores (conv_simt.cu) and only its GDN comes here (1x1 identity slab).
+#include <cuda.h>
+
 #include "conv_common.cuh"
+#include "tc_primitives.cuh"
 
 namespace nic {
 
-int conv_fwd_tc(const nic_conv_desc*, const void*, const void*, const float*, const void*, const float*, void*, void*, size_t, cudaStream_t) {
-  return fail(NIC_E_UNSUPPORTED, "conv: tcgen05 arm not built yet");
+using namespace tc;
+
+// conv_simt.cu
+int conv_fwd_fp32_ex(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y, int out_bf16_nhwc,
+                     cudaStream_t st);
+
+namespace {
+
+constexpr int kTileH = 16, kTileW = 8;          // output pixels per M = 128 block: 16 groups of 8
+constexpr int kMaxSlots = 4;
+constexpr int kThreads = 224;
+
+struct TcTap { int8_t plane, roff, coff, slab; };
+struct TcPhase {
+  int8_t py, px, nplanes, pad0;
+  int8_t plane_ph[4], plane_pw[4], plane_dymin[4], plane_dxmin[4];
+  int8_t plane_tap_begin[5];                   // taps of plane p: [plane_tap_begin[p], plane_tap_begin[p+1]) into taps[]
+};
+
+struct TcParams {
+  TcPhase phases[kMaxPhases];
+  TcTap taps[kMaxTaps];
+  int nphases, in_stride, out_stride;
+  int n, hin, win, cin, cout, hout, wout;
+  int hp, wp;                                  // per-phase output grid
+  int tiles_x, tiles_y, n_ntiles, total_tiles;
+  int nchunks;                                 // cin / 64
+  int ph_rows, pw_cols;                        // patch rows / cols (pixels)
+  int slot_bytes, nsa, nsb;
+  int nb, cout_pad;                            // N of the MMA (c_out tile), padded c_out of the packed weights
+  int epilogue;
+  int out_dtype;                               // NIC_DT_*
+  long ys_n, ys_c, ys_h, ys_w;                 // output strides (elements), channel offset already applied to y
+  int flat_hw;                                 // > 0: 1x1 conv over a flattened pixel list; pixel p -> image p / flat_hw
+  const float* bias;
+  const float* beta;
+  void* y;
+  int* status;
+  // shared-memory carve-up (byte offsets from the 1024-aligned base)
+  int off_a, off_b, off_gamma, off_sq, smem_bytes;
+};
+
+struct __align__(8) TcBarriers {
+  uint64_t a_full[kMaxSlots], a_empty[kMaxSlots], b_full[kMaxSlots], b_empty[kMaxSlots];
+  uint64_t acc_full[2], acc_empty[2], gdn_full, gamma_full;
+  uint32_t tmem_base;
+  volatile int abort_flag;
+};
+
+__device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, TcBarriers* sb, int* status) {
+  for (uint32_t i = 0; i < (1u << 22); ++i) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((i & 255u) == 255u && sb->abort_flag) return false;
+  }
+  sb->abort_flag = 1;
+  atomicExch(status, 1);
+  return false;
 }
-int pack_weight_tc(const nic_conv_desc*, const TapTable&, const float*, void*, cudaStream_t) {
-  return fail(NIC_E_UNSUPPORTED, "pack_conv_weight: tcgen05 arm not built yet");
+
+__device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& ntile, int& phase, int& img, int& ty, int& tx) {
+  tx = tile % p.tiles_x; tile /= p.tiles_x;
+  ty = tile % p.tiles_y; tile /= p.tiles_y;
+  img = tile % p.n; tile /= p.n;
+  phase = tile % p.nphases; tile /= p.nphases;
+  ntile = tile;
 }
-int pack_gdn_tc(int32_t, float, const float*, const float*, float*, void*, int32_t, cudaStream_t) {
-  return fail(NIC_E_UNSUPPORTED, "pack_gdn: tcgen05 arm not built yet");
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
 }
-size_t packed_weight_elems_tc(const nic_conv_desc*, const TapTable&) { return 0; }
-size_t conv_workspace_bytes_tc(const nic_conv_desc*) { return 0; }
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_g, const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ TcBarriers sb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool gdn = p.epilogue == NIC_EPI_GDN || p.epilogue == NIC_EPI_IGDN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sb.a_full[i], 1); mbar_init(&sb.a_empty[i], 1); mbar_init(&sb.b_full[i], 1); mbar_init(&sb.b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], 4); }
+    mbar_init(&sb.gdn_full, 1); mbar_init(&sb.gamma_full, 1);
+    sb.abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(&sb.tmem_base, 512); tmem_relinquish(); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); if (gdn) tma_prefetch_desc(&map_g); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = sb.tmem_base;
+
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+
+  if (warp == 0) {
+    // ===================== A producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      bool ok = true;
+      for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step) {
+        int ntile, phase, img, ty, tx;
+        decode_tile(p, tile, ntile, phase, img, ty, tx);
+        const TcPhase& ph = p.phases[phase];
+        for (int chunk = 0; chunk < p.nchunks && ok; ++chunk) {
+          for (int pl = 0; pl < ph.nplanes; ++pl, ++it) {
+            const int s = it % p.nsa;
+            if (!wait_or_abort(&sb.a_empty[s], ((it / p.nsa) & 1) ^ 1, &sb, p.status)) { ok = false; break; }
+            mbar_expect_tx(&sb.a_full[s], p.ph_rows * p.pw_cols * 128);
+            const int w0 = p.in_stride * (tx * kTileW + ph.plane_dxmin[pl]) + ph.plane_pw[pl];
+            const int h0 = p.in_stride * (ty * kTileH + ph.plane_dymin[pl]) + ph.plane_ph[pl];
+            tma_load_4d(smem + p.off_a + s * p.slot_bytes, &map_a, &sb.a_full[s], chunk * 64, w0, h0, img);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== B producer =====================
+    if (lane == 0) {
+      if (gdn) {   // gamma [c][c] bf16, K-major: two 64-column halves, resident for the whole kernel
+        mbar_expect_tx(&sb.gamma_full, 2 * 128 * 128);
+        tma_load_2d(smem + p.off_gamma, &map_g, &sb.gamma_full, 0, 0);
+        tma_load_2d(smem + p.off_gamma + 128 * 128, &map_g, &sb.gamma_full, 64, 0);
+      }
+      uint32_t it = 0;
+      bool ok = true;
+      const uint32_t bytes = p.nb * 128;
+      for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step) {
+        int ntile, phase, img, ty, tx;
+        decode_tile(p, tile, ntile, phase, img, ty, tx);
+        const TcPhase& ph = p.phases[phase];
+        const int t0 = ph.plane_tap_begin[0], t1 = ph.plane_tap_begin[ph.nplanes];
+        for (int chunk = 0; chunk < p.nchunks && ok; ++chunk) {
+          for (int t = t0; t < t1; ++t, ++it) {
+            const int s = it % p.nsb;
+            if (!wait_or_abort(&sb.b_empty[s], ((it / p.nsb) & 1) ^ 1, &sb, p.status)) { ok = false; break; }
+            mbar_expect_tx(&sb.b_full[s], bytes);
+            tma_load_2d(smem + p.off_b + s * (128 * 128), &map_w, &sb.b_full[s], chunk * 64, p.taps[t].slab * p.cout_pad + ntile * p.nb);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.nb);
+      const uint32_t a_base = smem_u32(smem + p.off_a), b_base = smem_u32(smem + p.off_b);
+      const uint32_t sbo = p.pw_cols * 128;
+      uint32_t ita = 0, itb = 0, tcount = 0;
+      bool ok = true;
+      for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step, ++tcount) {
+        int ntile, phase, img, ty, tx;
+        decode_tile(p, tile, ntile, phase, img, ty, tx);
+        const TcPhase& ph = p.phases[phase];
+        const uint32_t buf = tcount & 1;
+        if (!wait_or_abort(&sb.acc_empty[buf], ((tcount >> 1) & 1) ^ 1, &sb, p.status)) break;
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem + buf * 128;
+        uint32_t accumulate = 0;
+        for (int chunk = 0; chunk < p.nchunks && ok; ++chunk) {
+          for (int pl = 0; pl < ph.nplanes && ok; ++pl, ++ita) {
+            const int sa = ita % p.nsa;
+            if (!wait_or_abort(&sb.a_full[sa], (ita / p.nsa) & 1, &sb, p.status)) { ok = false; break; }
+            tcgen05_fence_after();
+            const uint32_t a_slot = a_base + sa * p.slot_bytes;
+            for (int t = ph.plane_tap_begin[pl]; t < ph.plane_tap_begin[pl + 1]; ++t, ++itb) {
+              const int sbi = itb % p.nsb;
+              if (!wait_or_abort(&sb.b_full[sbi], (itb / p.nsb) & 1, &sb, p.status)) { ok = false; break; }
+              tcgen05_fence_after();
+              const uint32_t a_tap = a_slot + (p.taps[t].roff * p.pw_cols + p.taps[t].coff) * 128;
+              const uint32_t b_tap = b_base + sbi * (128 * 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d_tmem, umma_desc_sw128(a_tap + k * 32, sbo), umma_desc_sw128(b_tap + k * 32, 1024), idesc, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(&sb.b_empty[sbi]);
+            }
+            umma_commit(&sb.a_empty[sa]);
+          }
+        }
+        umma_commit(&sb.acc_full[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 3..6) =====================
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;                // accumulator row = pixel of the tile
+    const int g = row >> 3, c8 = row & 7;
+    uint8_t* sq = smem + p.off_sq;
+    uint32_t tcount = 0;
+    bool ok = true;
+    for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step, ++tcount) {
+      int ntile, phase, img, ty, tx;
+      decode_tile(p, tile, ntile, phase, img, ty, tx);
+      const TcPhase& ph = p.phases[phase];
+      const uint32_t buf = tcount & 1;
+      if (!__all_sync(0xffffffffu, wait_or_abort(&sb.acc_full[buf], (tcount >> 1) & 1, &sb, p.status))) break;
+      tcgen05_fence_after();
+      const uint32_t acc_addr = tmem + buf * 128 + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t gdn_addr = tmem + 256 + (static_cast<uint32_t>(q * 32) << 16);
+      const int oy = ty * kTileH + g, ox = tx * kTileW + c8;
+      const int out_y = oy * p.out_stride + ph.py, out_x = ox * p.out_stride + ph.px;
+      const bool valid = out_y < p.hout && out_x < p.wout;
+      long obase;
+      if (p.flat_hw > 0) {
+        const long pix = static_cast<long>(oy) * kTileW + ox;
+        obase = (pix / p.flat_hw) * p.ys_n + (pix % p.flat_hw) * p.ys_w;
+      } else {
+        obase = img * p.ys_n + static_cast<long>(out_y) * p.ys_h + static_cast<long>(out_x) * p.ys_w;
+      }
+      const int ncg = (p.nb + 31) / 32;
+      const int cbase = ntile * p.nb;
+
+      if (gdn) {
+        // squares -> bf16 K-major swizzled tile in shared memory (A operand of the gamma contraction)
+        for (int cg = 0; cg < 4; ++cg) {
+          float v[32];
+          tmem_ld_32x32(acc_addr + cg * 32, v);
+          tmem_ld_wait();
+          uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c0 = cg * 32 + j * 8 + e * 2;
+              const float a = v[j * 8 + e * 2] + __ldg(p.bias + c0), b = v[j * 8 + e * 2 + 1] + __ldg(p.bias + c0 + 1);
+              w[e] = pack_bf16x2(a * a, b * b);
+            }
+            const int chunk = ((cg & 1) * 4 + j) ^ (row & 7);
+            *reinterpret_cast<uint4*>(half + chunk * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 3 && lane == 0) {
+          ok = wait_or_abort(&sb.gamma_full, 0, &sb, p.status);
+          tcgen05_fence_after();
+          const uint32_t idg = umma_idesc_bf16(128, 128);
+          const uint32_t sq_base = smem_u32(sq), g_base = smem_u32(smem + p.off_gamma);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem + 256, umma_desc_sw128(sq_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024),
+                      umma_desc_sw128(g_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024), idg, k > 0);
+          umma_commit(&sb.gdn_full);
+        }
+        if (!__all_sync(0xffffffffu, wait_or_abort(&sb.gdn_full, tcount & 1, &sb, p.status))) break;
+        tcgen05_fence_after();
+      }
+
+      for (int cg = 0; cg < ncg; ++cg) {
+        float v[32];
+        tmem_ld_32x32(acc_addr + cg * 32, v);
+        if (gdn) {
+          float nrm[32];
+          tmem_ld_32x32(gdn_addr + cg * 32, nrm);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = cg * 32 + j;
+            const float x = v[j] + __ldg(p.bias + c);
+            const float t = nrm[j] + __ldg(p.beta + c);
+            v[j] = (p.epilogue == NIC_EPI_GDN) ? x * rsqrtf(t) : x * sqrtf(t);
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = cbase + cg * 32 + j;
+            float x = v[j] + (c < p.cout ? __ldg(p.bias + c) : 0.f);
+            if (p.epilogue == NIC_EPI_LRELU) x = x > 0.f ? x : 0.01f * x;
+            v[j] = x;
+          }
+        }
+        if (valid) {
+          const int c0 = cbase + cg * 32;
+          if (p.ys_c == 1 && c0 + 32 <= p.cout) {
+            if (p.out_dtype == NIC_DT_BF16) {
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + obase + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst[j] = make_uint4(pack_bf16x2(v[j * 8], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                                    pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+            } else {
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.y) + obase + c0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int c = c0 + j;
+              if (c < p.cout) {
+                if (p.out_dtype == NIC_DT_BF16) static_cast<__nv_bfloat16*>(p.y)[obase + c * p.ys_c] = __float2bfloat16_rn(v[j]);
+                else static_cast<float*>(p.y)[obase + c * p.ys_c] = v[j];
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb.acc_empty[buf]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int* status_word() {       // one device int per process: the kernels' "a bounded wait expired" flag
+  static int* d = nullptr;
+  if (!d) { if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return nullptr; cudaMemset(d, 0, sizeof(int)); }
+  return d;
+}
+
+int encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled(2d %llu x %llu, box %u x %u) failed: %d", (unsigned long long)inner,
+                                     (unsigned long long)rows, box_inner, box_rows, (int)r);
+  return NIC_OK;
+}
+
+int encode_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, int c, int box_w, int box_h, int stride) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled(nhwc %dx%dx%dx%d, box %dx%d stride %d) failed: %d", n, h, w, c, box_w,
+                                     box_h, stride, (int)r);
+  return NIC_OK;
+}
+
+// Builds phases / planes / taps of the kernel from the generic tap table.
+int build_tc_geometry(const nic_conv_desc* d, const TapTable& tt, TcParams* p) {
+  p->nphases = tt.nphases; p->in_stride = tt.in_stride; p->out_stride = tt.out_stride;
+  int q = 0, ph_rows = 0, pw_cols = 0;
+  const int s = tt.in_stride;
+  for (int ph = 0; ph < tt.nphases; ++ph) {
+    TcPhase& P = p->phases[ph];
+    P.py = tt.py[ph]; P.px = tt.px[ph]; P.nplanes = 0;
+    for (int a = 0; a < s; ++a)
+      for (int b = 0; b < s; ++b) {
+        int dymin = 127, dymax = -127, dxmin = 127, dxmax = -127, cnt = 0;
+        for (int t = tt.phase_begin[ph]; t < tt.phase_begin[ph + 1]; ++t) {
+          // input offset (dy, dx) in full-resolution pixels -> plane (dy mod s, dx mod s), plane offset floor(dy / s)
+          const int pa = ((tt.dy[t] % s) + s) % s, pb = ((tt.dx[t] % s) + s) % s;
+          if (pa != a || pb != b) continue;
+          const int ry = (tt.dy[t] - pa) / s, rx = (tt.dx[t] - pb) / s;
+          dymin = ry < dymin ? ry : dymin; dymax = ry > dymax ? ry : dymax;
+          dxmin = rx < dxmin ? rx : dxmin; dxmax = rx > dxmax ? rx : dxmax;
+          ++cnt;
+        }
+        if (!cnt) continue;
+        const int pl = P.nplanes++;
+        P.plane_ph[pl] = a; P.plane_pw[pl] = b; P.plane_dymin[pl] = dymin; P.plane_dxmin[pl] = dxmin;
+        P.plane_tap_begin[pl] = q;
+        for (int t = tt.phase_begin[ph]; t < tt.phase_begin[ph + 1]; ++t) {
+          const int pa = ((tt.dy[t] % s) + s) % s, pb = ((tt.dx[t] % s) + s) % s;
+          if (pa != a || pb != b) continue;
+          const int ry = (tt.dy[t] - pa) / s, rx = (tt.dx[t] - pb) / s;
+          p->taps[q].plane = pl; p->taps[q].roff = ry - dymin; p->taps[q].coff = rx - dxmin; p->taps[q].slab = t; ++q;
+        }
+        P.plane_tap_begin[pl + 1] = q;
+        const int rows = kTileH + (dymax - dymin), cols = kTileW + (dxmax - dxmin);
+        ph_rows = rows > ph_rows ? rows : ph_rows; pw_cols = cols > pw_cols ? cols : pw_cols;
+      }
+  }
+  p->ph_rows = ph_rows; p->pw_cols = pw_cols;
+  return NIC_OK;
+}
+
+__global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin, int cout, int cout_pad,
+                                        int kh, int kw, int transposed, TapTable tt) {
+  const long total = static_cast<long>(tt.ntaps) * cout_pad * cin;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % cin);
+    const int co = static_cast<int>((i / cin) % cout_pad);
+    const int t = static_cast<int>(i / (static_cast<long>(cin) * cout_pad));
+    float v = 0.f;
+    if (co < cout) {
+      const int a = tt.kh[t], b = tt.kw[t];
+      const long src = transposed ? ((static_cast<long>(ci) * cout + co) * kh + a) * kw + b
+                                  : ((static_cast<long>(co) * cin + ci) * kh + a) * kw + b;
+      v = w[src];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void pack_identity_bf16_kernel(__nv_bfloat16* out, int c) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c * c; i += gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn((i / c) == (i % c) ? 1.f : 0.f);
+}
+
+__global__ void pack_gdn_bf16_kernel(int c, float beta_bound, float gamma_bound, float pedestal, const float* __restrict__ beta,
+                                     const float* __restrict__ gamma, float* __restrict__ beta_eff, __nv_bfloat16* __restrict__ gamma_out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c * c; i += gridDim.x * blockDim.x) {
+    const float g = fmaxf(gamma[i], gamma_bound);
+    gamma_out[i] = __float2bfloat16_rn(g * g - pedestal);          // [i (out)][j (in)]: K-major B operand
+    if (i < c) { const float b = fmaxf(beta[i], beta_bound); beta_eff[i] = b * b - pedestal; }
+  }
+}
+
+inline int nb_for(int cout) { return cout <= 16 ? 16 : 128; }
+inline bool small_cin(const nic_conv_desc* d) { return d->c_in < 64; }
+
+}  // namespace
+
+// Packed layout (bf16 elements):
+//   c_in >= 64 : [tap][c_out padded to a multiple of nb][c_in]
+//   c_in  < 64 : the fp32 [tap][c_in][c_out] pack of conv_simt.cu (as raw bytes) followed by a c_out x c_out identity
+size_t packed_weight_elems_tc(const nic_conv_desc* d, const TapTable& tt) {
+  if (small_cin(d)) return static_cast<size_t>(tt.ntaps) * d->c_in * d->c_out * 2 + static_cast<size_t>(d->c_out) * d->c_out;
+  const int nb = nb_for(d->c_out);
+  const int cout_pad = (d->c_out + nb - 1) / nb * nb;
+  return static_cast<size_t>(tt.ntaps) * cout_pad * d->c_in;
+}
+
+__global__ void pack_weight_f32_kernel(const float*, float*, int, int, int, int, int, TapTable);
+
+int pack_weight_tc(const nic_conv_desc* d, const TapTable& tt, const float* w_ref, void* w_packed, cudaStream_t st) {
+  if (d->precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "pack_conv_weight: precision %d is not built (fp32 and bf16 are)", d->precision);
+  if (small_cin(d)) {
+    const long total = static_cast<long>(tt.ntaps) * d->c_in * d->c_out;
+    pack_weight_f32_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w_ref, static_cast<float*>(w_packed), d->c_in, d->c_out, d->kh,
+                                                                                d->kw, d->transposed, tt);
+    if (int rc = check_launch("pack_weight_f32_kernel")) return rc;
+    pack_identity_bf16_kernel<<<64, 256, 0, st>>>(static_cast<__nv_bfloat16*>(w_packed) + total * 2, d->c_out);
+    return check_launch("pack_identity_bf16_kernel");
+  }
+  if (d->c_in % 64) return fail(NIC_E_UNSUPPORTED, "conv bf16: c_in=%d must be a multiple of 64 (or < 64 for the first layer)", d->c_in);
+  const int nb = nb_for(d->c_out);
+  const int cout_pad = (d->c_out + nb - 1) / nb * nb;
+  const long total = static_cast<long>(tt.ntaps) * cout_pad * d->c_in;
+  const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  pack_weight_bf16_kernel<<<blocks, 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed), d->c_in, d->c_out, cout_pad, d->kh, d->kw,
+                                                  d->transposed, tt);
+  return check_launch("pack_weight_bf16_kernel");
+}
+
+int pack_gdn_tc(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, float* beta_eff, void* gamma_packed,
+                int32_t precision, cudaStream_t st) {
+  if (precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "pack_gdn: precision %d is not built (fp32 and bf16 are)", precision);
+  const float pedestal = static_cast<float>(3.814697265625e-06 * 3.814697265625e-06);
+  const float beta_bound = static_cast<float>(sqrt(static_cast<double>(beta_min) + static_cast<double>(pedestal)));
+  const float gamma_bound = static_cast<float>(sqrt(static_cast<double>(pedestal)));
+  pack_gdn_bf16_kernel<<<(c * c + 255) / 256, 256, 0, st>>>(c, beta_bound, gamma_bound, pedestal, beta_raw, gamma_raw, beta_eff,
+                                                            static_cast<__nv_bfloat16*>(gamma_packed));
+  return check_launch("pack_gdn_bf16_kernel");
+}
+
+size_t conv_workspace_bytes_tc(const nic_conv_desc* d) {
+  if (small_cin(d)) return static_cast<size_t>(d->n) * d->h_out * d->w_out * d->c_out * 2;   // bf16 NHWC pre-activation
+  return 0;
+}
+
+static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, const void* w_packed, const float* bias, const void* gdn_gamma,
+                     const float* gdn_beta, void* y, cudaStream_t st) {
+  TcParams p{};
+  if (int rc = build_tc_geometry(d, tt, &p)) return rc;
+  const bool gdn = d->epilogue == NIC_EPI_GDN || d->epilogue == NIC_EPI_IGDN;
+  if (d->in_layout != NIC_LAYOUT_NHWC || d->in_dtype != NIC_DT_BF16) return fail(NIC_E_UNSUPPORTED, "conv bf16: input must be NHWC bf16");
+  if (d->c_in % 64) return fail(NIC_E_UNSUPPORTED, "conv bf16: c_in=%d must be a multiple of 64", d->c_in);
+  if (gdn && (d->c_out != 128 || !gdn_gamma || !gdn_beta)) return fail(NIC_E_UNSUPPORTED, "conv bf16: the fused GDN epilogue needs c_out = 128 and packed gamma/beta");
+  if ((reinterpret_cast<uintptr_t>(x) & 127) || (reinterpret_cast<uintptr_t>(w_packed) & 127)) return fail(NIC_E_BADALIGN, "conv bf16: tensors must be 128-byte aligned for TMA");
+  p.n = d->n; p.hin = d->h_in; p.win = d->w_in; p.cin = d->c_in; p.cout = d->c_out; p.hout = d->h_out; p.wout = d->w_out;
+  p.nb = nb_for(d->c_out);
+  p.cout_pad = (d->c_out + p.nb - 1) / p.nb * p.nb;
+  p.n_ntiles = p.cout_pad / p.nb;
+  p.nchunks = d->c_in / 64;
+  p.epilogue = d->epilogue; p.out_dtype = d->out_dtype;
+  const int ctot = d->out_c_total ? d->out_c_total : d->c_out;
+  if (d->out_layout == NIC_LAYOUT_NCHW) { p.ys_n = static_cast<long>(ctot) * d->h_out * d->w_out; p.ys_c = static_cast<long>(d->h_out) * d->w_out; p.ys_h = d->w_out; p.ys_w = 1; }
+  else { p.ys_n = static_cast<long>(d->h_out) * d->w_out * ctot; p.ys_h = static_cast<long>(d->w_out) * ctot; p.ys_w = ctot; p.ys_c = 1; }
+  const size_t esz = d->out_dtype == NIC_DT_BF16 ? 2 : 4;
+  p.y = static_cast<uint8_t*>(y) + static_cast<size_t>(d->out_c_offset) * p.ys_c * esz;
+  if (p.ys_c == 1 && ((reinterpret_cast<uintptr_t>(p.y) & 15) || (ctot * esz) % 16)) return fail(NIC_E_BADALIGN, "conv bf16: NHWC output rows must be 16-byte aligned");
+  p.bias = bias; p.beta = gdn_beta;
+  p.status = status_word();
+  if (!p.status) return fail(NIC_E_CUDA, "conv bf16: cannot allocate the status word");
+
+  // geometry of the pixel grid the tiles walk
+  int gn = d->n, gh = d->h_in, gw = d->w_in;
+  const bool pointwise = d->kh == 1 && d->kw == 1 && d->stride == 1 && !d->transposed;
+  const long npix = static_cast<long>(d->n) * d->h_in * d->w_in;
+  if (pointwise && npix % kTileW == 0) {         // 1x1: a flat list of pixels, 8 per row -> every tile is 128 consecutive pixels
+    gn = 1; gh = static_cast<int>(npix / kTileW); gw = kTileW;
+    p.flat_hw = d->h_in * d->w_in;
+    p.n = 1; p.hin = gh; p.win = gw; p.hout = gh; p.wout = gw;
+  }
+  p.hp = (p.hout + tt.out_stride - 1) / tt.out_stride;
+  p.wp = (p.wout + tt.out_stride - 1) / tt.out_stride;
+  p.tiles_x = (p.wp + kTileW - 1) / kTileW;
+  p.tiles_y = (p.hp + kTileH - 1) / kTileH;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.n * p.nphases * p.n_ntiles;
+
+  // shared memory: A slots | B ring | gamma | squares
+  p.slot_bytes = (p.ph_rows * p.pw_cols * 128 + 1023) / 1024 * 1024;
+  p.nsb = 4;
+  const int fixed = p.nsb * 128 * 128 + (gdn ? 4 * 128 * 128 : 0);
+  p.nsa = 4;
+  while (p.nsa > 2 && p.nsa * p.slot_bytes + fixed + 2048 > 227 * 1024) --p.nsa;
+  if (p.nsa * p.slot_bytes + fixed + 2048 > 227 * 1024) return fail(NIC_E_UNSUPPORTED, "conv bf16: patch of %d x %d pixels does not fit shared memory", p.ph_rows, p.pw_cols);
+  p.off_a = 0; p.off_b = p.nsa * p.slot_bytes; p.off_gamma = p.off_b + p.nsb * 128 * 128; p.off_sq = p.off_gamma + (gdn ? 2 * 128 * 128 : 0);
+  p.smem_bytes = p.off_sq + (gdn ? 2 * 128 * 128 : 0) + 1024;
+
+  CUtensorMap map_a, map_w, map_g;
+  if (int rc = encode_nhwc(&map_a, x, gn, gh, gw, d->c_in, p.pw_cols, p.ph_rows, tt.in_stride)) return rc;
+  if (int rc = encode_2d(&map_w, w_packed, d->c_in, static_cast<uint64_t>(tt.ntaps) * p.cout_pad, 64, p.nb)) return rc;
+  if (gdn) { if (int rc = encode_2d(&map_g, gdn_gamma, 128, 128, 64, 128)) return rc; }
+  else map_g = map_w;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute")) return rc;
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  conv_tc_kernel<<<grid, kThreads, p.smem_bytes, st>>>(map_a, map_w, map_g, p);
+  return check_launch("conv_tc_kernel");
+}
+
+int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* gdn_gamma, const float* gdn_beta,
+                void* y, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (d->precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "conv: precision %d is not built (fp32 and bf16 are)", d->precision);
+  TapTable tt;
+  if (int rc = build_tap_table(d, &tt)) return rc;
+  if (!small_cin(d)) return launch_tc(d, tt, x, w_packed, bias, gdn_gamma, gdn_beta, y, st);
+
+  // first layer (c_in = 3): 75-deep contraction on the CUDA cores (fp32, straight from the NCHW image) into a bf16 NHWC
+  // pre-activation, then the activation through the tensor-core kernel as a 1x1 identity slab with the fused epilogue
+  const size_t need = conv_workspace_bytes_tc(d);
+  if (!workspace || workspace_bytes < need) return fail(NIC_E_WORKSPACE, "conv bf16 (first layer): workspace %zu < %zu bytes", workspace_bytes, need);
+  if (d->c_out != 128) return fail(NIC_E_UNSUPPORTED, "conv bf16 (first layer): c_out must be 128");
+  static float* zero_bias = nullptr;
+  if (!zero_bias) { if (cudaMalloc(&zero_bias, 128 * sizeof(float)) != cudaSuccess) return fail(NIC_E_CUDA, "cudaMalloc"); cudaMemset(zero_bias, 0, 128 * sizeof(float)); }
+  nic_conv_desc c1 = *d;
+  c1.epilogue = NIC_EPI_BIAS; c1.precision = NIC_PREC_FP32; c1.out_layout = NIC_LAYOUT_NHWC; c1.out_c_total = 0; c1.out_c_offset = 0;
+  if (int rc = conv_fwd_fp32_ex(&c1, x, w_packed, bias, workspace, 1, st)) return rc;
+  nic_conv_desc c2 = *d;
+  c2.c_in = d->c_out; c2.h_in = d->h_out; c2.w_in = d->w_out; c2.kh = c2.kw = 1; c2.stride = 1; c2.pad = 0; c2.transposed = 0; c2.output_padding = 0;
+  c2.mask_a = 0; c2.in_layout = NIC_LAYOUT_NHWC; c2.in_dtype = NIC_DT_BF16;
+  TapTable t2;
+  if (int rc = build_tap_table(&c2, &t2)) return rc;
+  const size_t simt_bytes = static_cast<size_t>(tt.ntaps) * d->c_in * d->c_out * sizeof(float);
+  const void* ident = static_cast<const uint8_t*>(w_packed) + simt_bytes;
+  return launch_tc(&c2, t2, workspace, ident, zero_bias, gdn_gamma, gdn_beta, y, st);
+}
 
 }  // namespace nic

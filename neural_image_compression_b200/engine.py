@@ -127,8 +127,11 @@ def run_sequential_nchw(ops, x: torch.Tensor, precision: str) -> torch.Tensor:
     """A chain of ConvOps with reference (NCHW f32) tensors at both ends; NHWC inside."""
     require_cuda(x, "input")
     x = x.contiguous().float()
-    n, _, h, w = x.shape
+    n, cin, h, w = x.shape
     cur, layout = x, LAYOUT_NCHW
+    if precision != "fp32" and cin >= 64:
+        # stand-alone call of an inner transform in a tensor-core mode: the engine wants NHWC bf16 (cold path)
+        cur, layout = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), LAYOUT_NHWC
     with torch.cuda.device(x.device):
         for i, op in enumerate(ops):
             last = i == len(ops) - 1
@@ -139,18 +142,21 @@ def run_sequential_nchw(ops, x: torch.Tensor, precision: str) -> torch.Tensor:
     return cur
 
 
-def latent_handoff(v_nhwc: torch.Tensor, qmode: int, noise: Optional[torch.Tensor], in_dtype: torch.dtype):
-    """Models.py:52-66.  Returns (v_nchw, v_in_nchw, v_in_nhwc)."""
+def latent_handoff(v_nhwc: torch.Tensor, qmode: int, noise: Optional[torch.Tensor], in_dtype: torch.dtype,
+                   want_lowp: bool = False):
+    """Models.py:52-66.  Returns (v_nchw, v_in_nchw, v_in_nhwc, v_nhwc_bf16 | None)."""
     lib = _lib.load()
     n, h, w, c = v_nhwc.shape
     v = torch.empty((n, c, h, w), dtype=torch.float32, device=v_nhwc.device)
     v_in = torch.empty_like(v)
     v_in_nhwc = torch.empty((n, h, w, c), dtype=in_dtype, device=v_nhwc.device)
+    v_lowp = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=v_nhwc.device) if want_lowp else None
     if noise is not None:
         noise = noise.contiguous().float()
     check(lib.nic_latent_handoff(ptr(v_nhwc), n, c, h, w, qmode, ptr(noise), ptr(v), ptr(v_in), ptr(v_in_nhwc),
-                                 DT_BF16 if in_dtype == torch.bfloat16 else DT_F32, current_stream()), "nic_latent_handoff")
-    return v, v_in, v_in_nhwc
+                                 DT_BF16 if in_dtype == torch.bfloat16 else DT_F32, ptr(v_lowp), current_stream()),
+          "nic_latent_handoff")
+    return v, v_in, v_in_nhwc, v_lowp
 
 
 def partials(b: int, device) -> torch.Tensor:
