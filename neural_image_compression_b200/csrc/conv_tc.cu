@@ -41,6 +41,7 @@ namespace {
 constexpr int kTileH = 16, kTileW = 8;          // output pixels per M = 128 block: 16 groups of 8
 constexpr int kMaxSlots = 4;
 constexpr int kThreads = 224;
+constexpr int kMaxDynSmem = 232448 - 1024;    // 227 KB opt-in limit minus this kernel's static shared memory
 
 struct TcTap { int8_t plane, roff, coff, slab; };
 struct TcPhase {
@@ -566,8 +567,8 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   p.nsb = 4;
   const int fixed = p.nsb * 128 * 128 + (gdn ? 4 * 128 * 128 : 0);
   p.nsa = 4;
-  while (p.nsa > 2 && p.nsa * p.slot_bytes + fixed + 2048 > 227 * 1024) --p.nsa;
-  if (p.nsa * p.slot_bytes + fixed + 2048 > 227 * 1024) return fail(NIC_E_UNSUPPORTED, "conv bf16: patch of %d x %d pixels does not fit shared memory", p.ph_rows, p.pw_cols);
+  while (p.nsa > 2 && p.nsa * p.slot_bytes + fixed + 1024 > kMaxDynSmem) --p.nsa;
+  if (p.nsa * p.slot_bytes + fixed + 1024 > kMaxDynSmem) return fail(NIC_E_UNSUPPORTED, "conv bf16: patch of %d x %d pixels does not fit shared memory", p.ph_rows, p.pw_cols);
   p.off_a = 0; p.off_b = p.nsa * p.slot_bytes; p.off_gamma = p.off_b + p.nsb * 128 * 128; p.off_sq = p.off_gamma + (gdn ? 2 * 128 * 128 : 0);
   p.smem_bytes = p.off_sq + (gdn ? 2 * 128 * 128 : 0) + 1024;
 
@@ -579,7 +580,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
 
   static bool attr_set = false;
   if (!attr_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute")) return rc;
+    if (int rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), "cudaFuncSetAttribute")) return rc;
     attr_set = true;
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
