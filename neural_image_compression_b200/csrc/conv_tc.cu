@@ -40,8 +40,10 @@ namespace {
 
 constexpr int kTileH = 16, kTileW = 8;          // output pixels per M = 128 block: 16 groups of 8
 constexpr int kMaxSlots = 4;
+constexpr int kMaxBSlots = 8;
 constexpr int kThreads = 224;
-constexpr int kMaxDynSmem = 232448 - 1024;    // 227 KB opt-in limit minus this kernel's static shared memory
+constexpr int kMaxDynSmem = 232448 - 8192;    // 227 KB opt-in limit minus this kernel's static shared memory
+constexpr int kMaxCout = 1280;                // bias table staged in shared memory
 
 struct TcTap { int8_t plane, roff, coff, slab; };
 struct TcPhase {
@@ -56,15 +58,22 @@ struct TcParams {
   int nphases, in_stride, out_stride;
   int n, hin, win, cin, cout, hout, wout;
   int hp, wp;                                  // per-phase output grid
+  int mt;                                      // M = 128 blocks per tile (1 or 2): the blocks share every weight slab
+  int blk_roff[2], blk_coff[2];                // position of block b inside the tile (pixels)
+  int tile_h, tile_w;                          // output pixels per tile
   int tiles_x, tiles_y, n_ntiles, total_tiles;
   int nchunks;                                 // cin / 64
   int ph_rows, pw_cols;                        // patch rows / cols (pixels)
   int slot_bytes, nsa, nsb;
+  int b_resident;                              // all weight slabs of the layer stay in shared memory (small c_out)
+  int nslabs;                                  // taps over all phases
   int nb, cout_pad;                            // N of the MMA (c_out tile), padded c_out of the packed weights
   int epilogue;
   int out_dtype;                               // NIC_DT_*
   long ys_n, ys_c, ys_h, ys_w;                 // output strides (elements), channel offset already applied to y
   int flat_hw;                                 // > 0: 1x1 conv over a flattened pixel list; pixel p -> image p / flat_hw
+  int tma_out;                                 // NHWC bf16 output leaves through shared memory + TMA tensor stores
+  int out_c_offset;                            // channel window start inside the output tensor (TMA coordinates)
   const float* bias;
   const float* beta;
   void* y;
@@ -74,8 +83,8 @@ struct TcParams {
 };
 
 struct __align__(8) TcBarriers {
-  uint64_t a_full[kMaxSlots], a_empty[kMaxSlots], b_full[kMaxSlots], b_empty[kMaxSlots];
-  uint64_t acc_full[2], acc_empty[2], gdn_full, gamma_full;
+  uint64_t a_full[kMaxSlots], a_empty[kMaxSlots], b_full[kMaxBSlots], b_empty[kMaxBSlots];
+  uint64_t acc_full[2], acc_empty[2], gdn_full, gamma_full, bres_full;
   uint32_t tmem_base;
   volatile int abort_flag;
 };
@@ -98,29 +107,82 @@ __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& nt
   ntile = tile;
 }
 
+// number of M blocks of the tile that contain at least one real output pixel
+__device__ __forceinline__ int live_blocks(const TcParams& p, int ty, int tx) {
+  int nblk = 0;
+  for (int b = 0; b < p.mt; ++b)
+    if (ty * p.tile_h + p.blk_roff[b] < p.hp && tx * p.tile_w + p.blk_coff[b] < p.wp) nblk = b + 1;
+  return nblk;
+}
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// one 32-channel group of one pixel to global memory
+__device__ __forceinline__ void store_group(const TcParams& p, long obase, int c0, const float* v) {
+  if (p.ys_c == 1 && c0 + 32 <= p.cout) {
+    if (p.out_dtype == NIC_DT_BF16) {
+      uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + obase + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dst[j] = make_uint4(pack_bf16x2(v[j * 8], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                            pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+    } else {
+      float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.y) + obase + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = c0 + j;
+      if (c < p.cout) {
+        if (p.out_dtype == NIC_DT_BF16) static_cast<__nv_bfloat16*>(p.y)[obase + c * p.ys_c] = __float2bfloat16_rn(v[j]);
+        else static_cast<float*>(p.y)[obase + c * p.ys_c] = v[j];
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_g, const __grid_constant__ TcParams p) {
+               const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ TcBarriers sb;
+  __shared__ float s_bias[kMaxCout];
+  __shared__ float s_beta[128];
+  __shared__ uint32_t s_tap_aoff[kMaxTaps][2];   // (A start of tap t, block b) - (slot base), in 16-byte units
+  __shared__ int s_tap_brow[kMaxTaps];           // weight row of the tap's slab (TMA coordinate / resident tile index)
+  if (threadIdx.x < kMaxTaps) {
+    const int t = threadIdx.x;
+    for (int b = 0; b < 2; ++b)
+      s_tap_aoff[t][b] = static_cast<uint32_t>(((p.taps[t].roff + p.blk_roff[b]) * p.pw_cols + p.taps[t].coff + p.blk_coff[b]) * 128) >> 4;
+    s_tap_brow[t] = p.taps[t].slab;
+  }
+  for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = p.bias[i];
+  if (p.beta) for (int i = threadIdx.x; i < 128; i += kThreads) s_beta[i] = p.beta[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool gdn = p.epilogue == NIC_EPI_GDN || p.epilogue == NIC_EPI_IGDN;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sb.a_full[i], 1); mbar_init(&sb.a_empty[i], 1); mbar_init(&sb.b_full[i], 1); mbar_init(&sb.b_empty[i], 1); }
+    for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sb.a_full[i], 1); mbar_init(&sb.a_empty[i], 1); }
+    for (int i = 0; i < kMaxBSlots; ++i) { mbar_init(&sb.b_full[i], 1); mbar_init(&sb.b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], 4); }
-    mbar_init(&sb.gdn_full, 1); mbar_init(&sb.gamma_full, 1);
+    mbar_init(&sb.gdn_full, 1); mbar_init(&sb.gamma_full, 1); mbar_init(&sb.bres_full, 1);
     sb.abort_flag = 0;
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(&sb.tmem_base, 512); tmem_relinquish(); }
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); if (gdn) tma_prefetch_desc(&map_g); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); if (gdn) tma_prefetch_desc(&map_g); if (p.tma_out) tma_prefetch_desc(&map_o); }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -133,6 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       uint32_t it = 0;
       bool ok = true;
+      const uint32_t bytes = p.ph_rows * p.pw_cols * 128;
       for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step) {
         int ntile, phase, img, ty, tx;
         decode_tile(p, tile, ntile, phase, img, ty, tx);
@@ -141,9 +204,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int pl = 0; pl < ph.nplanes; ++pl, ++it) {
             const int s = it % p.nsa;
             if (!wait_or_abort(&sb.a_empty[s], ((it / p.nsa) & 1) ^ 1, &sb, p.status)) { ok = false; break; }
-            mbar_expect_tx(&sb.a_full[s], p.ph_rows * p.pw_cols * 128);
-            const int w0 = p.in_stride * (tx * kTileW + ph.plane_dxmin[pl]) + ph.plane_pw[pl];
-            const int h0 = p.in_stride * (ty * kTileH + ph.plane_dymin[pl]) + ph.plane_ph[pl];
+            mbar_expect_tx(&sb.a_full[s], bytes);
+            const int w0 = p.in_stride * (tx * p.tile_w + ph.plane_dxmin[pl]) + ph.plane_pw[pl];
+            const int h0 = p.in_stride * (ty * p.tile_h + ph.plane_dymin[pl]) + ph.plane_ph[pl];
             tma_load_4d(smem + p.off_a + s * p.slot_bytes, &map_a, &sb.a_full[s], chunk * 64, w0, h0, img);
           }
         }
@@ -157,20 +220,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tma_load_2d(smem + p.off_gamma, &map_g, &sb.gamma_full, 0, 0);
         tma_load_2d(smem + p.off_gamma + 128 * 128, &map_g, &sb.gamma_full, 64, 0);
       }
-      uint32_t it = 0;
-      bool ok = true;
       const uint32_t bytes = p.nb * 128;
-      for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step) {
-        int ntile, phase, img, ty, tx;
-        decode_tile(p, tile, ntile, phase, img, ty, tx);
-        const TcPhase& ph = p.phases[phase];
-        const int t0 = ph.plane_tap_begin[0], t1 = ph.plane_tap_begin[ph.nplanes];
-        for (int chunk = 0; chunk < p.nchunks && ok; ++chunk) {
-          for (int t = t0; t < t1; ++t, ++it) {
-            const int s = it % p.nsb;
-            if (!wait_or_abort(&sb.b_empty[s], ((it / p.nsb) & 1) ^ 1, &sb, p.status)) { ok = false; break; }
-            mbar_expect_tx(&sb.b_full[s], bytes);
-            tma_load_2d(smem + p.off_b + s * (128 * 128), &map_w, &sb.b_full[s], chunk * 64, p.taps[t].slab * p.cout_pad + ntile * p.nb);
+      if (p.b_resident) {
+        // every (slab, chunk) tile of the layer once: [slab][chunk] tiles of nb x 64
+        mbar_expect_tx(&sb.bres_full, bytes * p.nslabs * p.nchunks);
+        for (int t = 0; t < p.nslabs; ++t)
+          for (int chunk = 0; chunk < p.nchunks; ++chunk)
+            tma_load_2d(smem + p.off_b + (t * p.nchunks + chunk) * bytes, &map_w, &sb.bres_full, chunk * 64, t * p.cout_pad);
+      } else {
+        uint32_t it = 0;
+        bool ok = true;
+        for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step) {
+          int ntile, phase, img, ty, tx;
+          decode_tile(p, tile, ntile, phase, img, ty, tx);
+          const TcPhase& ph = p.phases[phase];
+          const int t0 = ph.plane_tap_begin[0], t1 = ph.plane_tap_begin[ph.nplanes];
+          for (int chunk = 0; chunk < p.nchunks && ok; ++chunk) {
+            for (int t = t0; t < t1; ++t, ++it) {
+              const int s = it % p.nsb;
+              if (!wait_or_abort(&sb.b_empty[s], ((it / p.nsb) & 1) ^ 1, &sb, p.status)) { ok = false; break; }
+              mbar_expect_tx(&sb.b_full[s], bytes);
+              tma_load_2d(smem + p.off_b + s * (128 * 128), &map_w, &sb.b_full[s], chunk * 64, s_tap_brow[t] * p.cout_pad + ntile * p.nb);
+            }
           }
         }
       }
@@ -180,158 +251,196 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, p.nb);
       const uint32_t a_base = smem_u32(smem + p.off_a), b_base = smem_u32(smem + p.off_b);
-      const uint32_t sbo = p.pw_cols * 128;
+      const uint32_t a_hi = umma_desc_hi(p.pw_cols * 128), b_hi = umma_desc_hi(1024);
+      const uint32_t bbytes = p.nb * 128;
+      const int nsa = p.nsa, nsb = p.nsb, nchunks = p.nchunks, b_res = p.b_resident;
       uint32_t ita = 0, itb = 0, tcount = 0;
+      uint32_t sa = 0, pa = 0, sbi = 0, pb = 0;      // ring slot + phase parity of the A and B rings
       bool ok = true;
+      if (b_res) { ok = wait_or_abort(&sb.bres_full, 0, &sb, p.status); tcgen05_fence_after(); }
       for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step, ++tcount) {
         int ntile, phase, img, ty, tx;
         decode_tile(p, tile, ntile, phase, img, ty, tx);
         const TcPhase& ph = p.phases[phase];
+        const int nblk = live_blocks(p, ty, tx);
+        const int nplanes = ph.nplanes;
         const uint32_t buf = tcount & 1;
         if (!wait_or_abort(&sb.acc_empty[buf], ((tcount >> 1) & 1) ^ 1, &sb, p.status)) break;
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem + buf * 128;
+        const uint32_t d_tmem = tmem + buf * 256;
         uint32_t accumulate = 0;
-        for (int chunk = 0; chunk < p.nchunks && ok; ++chunk) {
-          for (int pl = 0; pl < ph.nplanes && ok; ++pl, ++ita) {
-            const int sa = ita % p.nsa;
-            if (!wait_or_abort(&sb.a_full[sa], (ita / p.nsa) & 1, &sb, p.status)) { ok = false; break; }
+        for (int chunk = 0; chunk < nchunks && ok; ++chunk) {
+          for (int pl = 0; pl < nplanes && ok; ++pl) {
+            if (!mbar_try_wait(&sb.a_full[sa], pa) && !wait_or_abort(&sb.a_full[sa], pa, &sb, p.status)) { ok = false; break; }
             tcgen05_fence_after();
-            const uint32_t a_slot = a_base + sa * p.slot_bytes;
-            for (int t = ph.plane_tap_begin[pl]; t < ph.plane_tap_begin[pl + 1]; ++t, ++itb) {
-              const int sbi = itb % p.nsb;
-              if (!wait_or_abort(&sb.b_full[sbi], (itb / p.nsb) & 1, &sb, p.status)) { ok = false; break; }
-              tcgen05_fence_after();
-              const uint32_t a_tap = a_slot + (p.taps[t].roff * p.pw_cols + p.taps[t].coff) * 128;
-              const uint32_t b_tap = b_base + sbi * (128 * 128);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16(d_tmem, umma_desc_sw128(a_tap + k * 32, sbo), umma_desc_sw128(b_tap + k * 32, 1024), idesc, accumulate);
-                accumulate = 1;
+            const uint32_t a_slot_lo = umma_desc_lo(a_base + sa * p.slot_bytes);
+            const int t_end = ph.plane_tap_begin[pl + 1];
+            for (int t = ph.plane_tap_begin[pl]; t < t_end; ++t) {
+              uint32_t b_lo;
+              if (b_res) {
+                b_lo = umma_desc_lo(b_base + (s_tap_brow[t] * nchunks + chunk) * bbytes);
+              } else {
+                if (!mbar_try_wait(&sb.b_full[sbi], pb) && !wait_or_abort(&sb.b_full[sbi], pb, &sb, p.status)) { ok = false; break; }
+                tcgen05_fence_after();
+                b_lo = umma_desc_lo(b_base + sbi * (128 * 128));
               }
-              umma_commit(&sb.b_empty[sbi]);
+              const uint32_t a_lo0 = a_slot_lo + s_tap_aoff[t][0];
+              umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo, b_hi, idesc, accumulate);
+              umma_bf16_lohi(d_tmem, a_lo0 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
+              umma_bf16_lohi(d_tmem, a_lo0 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
+              umma_bf16_lohi(d_tmem, a_lo0 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+              if (nblk > 1) {
+                const uint32_t a_lo1 = a_slot_lo + s_tap_aoff[t][1];
+                umma_bf16_lohi(d_tmem + 128, a_lo1, a_hi, b_lo, b_hi, idesc, accumulate);
+                umma_bf16_lohi(d_tmem + 128, a_lo1 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
+                umma_bf16_lohi(d_tmem + 128, a_lo1 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
+                umma_bf16_lohi(d_tmem + 128, a_lo1 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+              }
+              accumulate = 1;
+              if (!b_res) {
+                umma_commit(&sb.b_empty[sbi]);
+                if (++sbi == static_cast<uint32_t>(nsb)) { sbi = 0; pb ^= 1; }
+              }
             }
             umma_commit(&sb.a_empty[sa]);
+            if (++sa == static_cast<uint32_t>(nsa)) { sa = 0; pa ^= 1; }
           }
         }
         umma_commit(&sb.acc_full[buf]);
       }
+      (void)ita; (void)itb;
     }
   } else {
     // ===================== epilogue (warps 3..6) =====================
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
-    const int row = q * 32 + lane;                // accumulator row = pixel of the tile
+    const int row = q * 32 + lane;                // accumulator row = pixel of the block
     const int g = row >> 3, c8 = row & 7;
     uint8_t* sq = smem + p.off_sq;
-    uint32_t tcount = 0;
+    uint32_t tcount = 0, gdn_count = 0;
     bool ok = true;
+    const int ncg = (p.nb + 31) / 32;
+    const bool igdn = p.epilogue == NIC_EPI_IGDN;
     for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step, ++tcount) {
       int ntile, phase, img, ty, tx;
       decode_tile(p, tile, ntile, phase, img, ty, tx);
       const TcPhase& ph = p.phases[phase];
+      const int nblk = live_blocks(p, ty, tx);
       const uint32_t buf = tcount & 1;
       if (!__all_sync(0xffffffffu, wait_or_abort(&sb.acc_full[buf], (tcount >> 1) & 1, &sb, p.status))) break;
       tcgen05_fence_after();
-      const uint32_t acc_addr = tmem + buf * 128 + (static_cast<uint32_t>(q * 32) << 16);
-      const uint32_t gdn_addr = tmem + 256 + (static_cast<uint32_t>(q * 32) << 16);
-      const int oy = ty * kTileH + g, ox = tx * kTileW + c8;
-      const int out_y = oy * p.out_stride + ph.py, out_x = ox * p.out_stride + ph.px;
-      const bool valid = out_y < p.hout && out_x < p.wout;
-      long obase;
-      if (p.flat_hw > 0) {
-        const long pix = static_cast<long>(oy) * kTileW + ox;
-        obase = (pix / p.flat_hw) * p.ys_n + (pix % p.flat_hw) * p.ys_w;
-      } else {
-        obase = img * p.ys_n + static_cast<long>(out_y) * p.ys_h + static_cast<long>(out_x) * p.ys_w;
-      }
-      const int ncg = (p.nb + 31) / 32;
       const int cbase = ntile * p.nb;
-
-      if (gdn) {
-        // squares -> bf16 K-major swizzled tile in shared memory (A operand of the gamma contraction)
-        for (int cg = 0; cg < 4; ++cg) {
-          float v[32];
-          tmem_ld_32x32(acc_addr + cg * 32, v);
-          tmem_ld_wait();
-          uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c0 = cg * 32 + j * 8 + e * 2;
-              const float a = v[j * 8 + e * 2] + __ldg(p.bias + c0), b = v[j * 8 + e * 2 + 1] + __ldg(p.bias + c0 + 1);
-              w[e] = pack_bf16x2(a * a, b * b);
-            }
-            const int chunk = ((cg & 1) * 4 + j) ^ (row & 7);
-            *reinterpret_cast<uint4*>(half + chunk * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
+      for (int b = 0; b < nblk && ok; ++b) {
+        const uint32_t acc_addr = tmem + buf * 256 + b * 128 + (static_cast<uint32_t>(q * 32) << 16);
+        const int oy0 = ty * p.tile_h + p.blk_roff[b], ox0 = tx * p.tile_w + p.blk_coff[b];
+        const int oy = oy0 + g, ox = ox0 + c8;
+        const int out_y = oy * p.out_stride + ph.py, out_x = ox * p.out_stride + ph.px;
+        const bool valid = oy < p.hp && ox < p.wp && out_y < p.hout && out_x < p.wout;
+        long obase;
+        if (p.flat_hw > 0) {
+          const long pix = static_cast<long>(oy) * kTileW + ox;
+          obase = (pix / p.flat_hw) * p.ys_n + (pix % p.flat_hw) * p.ys_w;
+        } else {
+          obase = img * p.ys_n + static_cast<long>(out_y) * p.ys_h + static_cast<long>(out_x) * p.ys_w;
         }
-        fence_proxy_async_smem();
-        tcgen05_fence_before();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 3 && lane == 0) {
-          ok = wait_or_abort(&sb.gamma_full, 0, &sb, p.status);
-          tcgen05_fence_after();
-          const uint32_t idg = umma_idesc_bf16(128, 128);
-          const uint32_t sq_base = smem_u32(sq), g_base = smem_u32(smem + p.off_gamma);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem + 256, umma_desc_sw128(sq_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024),
-                      umma_desc_sw128(g_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024), idg, k > 0);
-          umma_commit(&sb.gdn_full);
+        if (p.tma_out) {
+          // the staging tile (= the squares tile) may still be read by the previous block's tensor store
+          if (warp == 3 && lane == 0) tma_store_wait_read();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        if (!__all_sync(0xffffffffu, wait_or_abort(&sb.gdn_full, tcount & 1, &sb, p.status))) break;
-        tcgen05_fence_after();
-      }
-
-      for (int cg = 0; cg < ncg; ++cg) {
-        float v[32];
-        tmem_ld_32x32(acc_addr + cg * 32, v);
+        float xr[128];
         if (gdn) {
-          float nrm[32];
-          tmem_ld_32x32(gdn_addr + cg * 32, nrm);
-          tmem_ld_wait();
+          // x (+ bias) stays in registers; its squares go to shared memory as the bf16 K-major A operand of the
+          // gamma contraction, whose result OVERWRITES this accumulator (no extra TMEM); then y = x * rsqrt(beta + .)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = cg * 32 + j;
-            const float x = v[j] + __ldg(p.bias + c);
-            const float t = nrm[j] + __ldg(p.beta + c);
-            v[j] = (p.epilogue == NIC_EPI_GDN) ? x * rsqrtf(t) : x * sqrtf(t);
+          for (int cg = 0; cg < 4; ++cg) {
+            tmem_ld_32x32(acc_addr + cg * 32, xr + cg * 32);
+            tmem_ld_wait();
+            uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c0 = cg * 32 + j * 8 + e * 2;
+                const float a = xr[c0] + s_bias[c0], bb = xr[c0 + 1] + s_bias[c0 + 1];
+                xr[c0] = a; xr[c0 + 1] = bb;
+                w[e] = pack_bf16x2(a * a, bb * bb);
+              }
+              const int chunk = ((cg & 1) * 4 + j) ^ (row & 7);
+              *reinterpret_cast<uint4*>(half + chunk * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+          fence_proxy_async_smem();
+          tcgen05_fence_before();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (warp == 3 && lane == 0) {
+            if (gdn_count == 0) wait_or_abort(&sb.gamma_full, 0, &sb, p.status);
+            tcgen05_fence_after();
+            const uint32_t idg = umma_idesc_bf16(128, 128);
+            const uint32_t sq_base = smem_u32(sq), g_base = smem_u32(smem + p.off_gamma);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem + buf * 256 + b * 128, umma_desc_sw128(sq_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024),
+                        umma_desc_sw128(g_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024), idg, k > 0);
+            umma_commit(&sb.gdn_full);
+          }
+          if (!__all_sync(0xffffffffu, wait_or_abort(&sb.gdn_full, gdn_count & 1, &sb, p.status))) { ok = false; break; }
+          ++gdn_count;
+          tcgen05_fence_after();
+        }
+        const int nvalid_c = p.cout - cbase;                      // channels of this N tile that exist
+        auto emit_group = [&](int cg, const float* v) {             // one pixel x 32 channels: to the staging tile or to HBM
+          if (p.tma_out) {
+            uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int chunk = ((cg & 1) * 4 + j) ^ (row & 7);
+              *reinterpret_cast<uint4*>(half + chunk * 16) =
+                  make_uint4(pack_bf16x2(v[j * 8], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                             pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+            }
+          } else if (valid) {
+            store_group(p, obase, cbase + cg * 32, v);
+          }
+        };
+        if (gdn) {
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg) {
+            float v[32];
+            tmem_ld_32x32(acc_addr + cg * 32, v);
+            tmem_ld_wait();
+            if (igdn) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = xr[cg * 32 + j] * sqrt_approx(v[j] + s_beta[cg * 32 + j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = xr[cg * 32 + j] * rsqrtf(v[j] + s_beta[cg * 32 + j]);
+            }
+            emit_group(cg, v);
           }
         } else {
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = cbase + cg * 32 + j;
-            float x = v[j] + (c < p.cout ? __ldg(p.bias + c) : 0.f);
-            if (p.epilogue == NIC_EPI_LRELU) x = x > 0.f ? x : 0.01f * x;
-            v[j] = x;
-          }
-        }
-        if (valid) {
-          const int c0 = cbase + cg * 32;
-          if (p.ys_c == 1 && c0 + 32 <= p.cout) {
-            if (p.out_dtype == NIC_DT_BF16) {
-              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + obase + c0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                dst[j] = make_uint4(pack_bf16x2(v[j * 8], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
-                                    pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
-            } else {
-              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.y) + obase + c0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
-            }
-          } else {
+          for (int cg = 0; cg < ncg; ++cg) {
+            float v[32];
+            tmem_ld_32x32(acc_addr + cg * 32, v);
+            tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int c = c0 + j;
-              if (c < p.cout) {
-                if (p.out_dtype == NIC_DT_BF16) static_cast<__nv_bfloat16*>(p.y)[obase + c * p.ys_c] = __float2bfloat16_rn(v[j]);
-                else static_cast<float*>(p.y)[obase + c * p.ys_c] = v[j];
-              }
+              const int c = cbase + cg * 32 + j;
+              float x = v[j] + (c < p.cout ? s_bias[c] : 0.f);
+              if (p.epilogue == NIC_EPI_LRELU) x = x > 0.f ? x : 0.01f * x;
+              v[j] = x;
             }
+            emit_group(cg, v);
+          }
+        }
+        if (p.tma_out) {
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (warp == 3 && lane == 0) {
+            const int wc = ox0 * p.out_stride + ph.px, hc = oy0 * p.out_stride + ph.py;
+            for (int h = 0; h < 2; ++h)
+              if (h * 64 < nvalid_c) tma_store_4d(&map_o, sq + h * (128 * 128), p.out_c_offset + cbase + h * 64, wc, hc, img);
+            tma_store_commit();
           }
         }
       }
@@ -339,6 +448,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb.acc_empty[buf]);
     }
+    if (p.tma_out && warp == 3 && lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
@@ -551,32 +661,66 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   int gn = d->n, gh = d->h_in, gw = d->w_in;
   const bool pointwise = d->kh == 1 && d->kw == 1 && d->stride == 1 && !d->transposed;
   const long npix = static_cast<long>(d->n) * d->h_in * d->w_in;
-  if (pointwise && npix % kTileW == 0) {         // 1x1: a flat list of pixels, 8 per row -> every tile is 128 consecutive pixels
+  const bool flat = pointwise && npix % kTileW == 0;
+  if (flat) {                                    // 1x1: a flat list of pixels, 8 per row -> every block is 128 consecutive pixels
     gn = 1; gh = static_cast<int>(npix / kTileW); gw = kTileW;
     p.flat_hw = d->h_in * d->w_in;
     p.n = 1; p.hin = gh; p.win = gw; p.hout = gh; p.wout = gw;
   }
   p.hp = (p.hout + tt.out_stride - 1) / tt.out_stride;
   p.wp = (p.wout + tt.out_stride - 1) / tt.out_stride;
-  p.tiles_x = (p.wp + kTileW - 1) / kTileW;
-  p.tiles_y = (p.hp + kTileH - 1) / kTileH;
+  // two M = 128 blocks per tile share every weight slab (halves the L2 -> shared-memory weight traffic, which is
+  // what bounds M = 128 tiles: profiles/README.md); side by side for images, stacked for the flat 1x1 case
+  p.mt = (flat ? p.hp > kTileH : p.wp > kTileW) ? 2 : 1;
+  p.blk_roff[0] = p.blk_coff[0] = 0;
+  p.blk_roff[1] = flat ? kTileH : 0; p.blk_coff[1] = flat ? 0 : kTileW;
+  p.tile_h = flat ? kTileH * p.mt : kTileH; p.tile_w = flat ? kTileW : kTileW * p.mt;
+  p.ph_rows += p.tile_h - kTileH; p.pw_cols += p.tile_w - kTileW;      // build_tc_geometry sized the patch for one block
+  p.tiles_x = (p.wp + p.tile_w - 1) / p.tile_w;
+  p.tiles_y = (p.hp + p.tile_h - 1) / p.tile_h;
   p.total_tiles = p.tiles_x * p.tiles_y * p.n * p.nphases * p.n_ntiles;
+  p.nslabs = tt.ntaps;
 
-  // shared memory: A slots | B ring | gamma | squares
+  // shared memory: A slots | B ring (or resident weights) | gamma | squares
   p.slot_bytes = (p.ph_rows * p.pw_cols * 128 + 1023) / 1024 * 1024;
-  p.nsb = 4;
-  const int fixed = p.nsb * 128 * 128 + (gdn ? 4 * 128 * 128 : 0);
-  p.nsa = 4;
-  while (p.nsa > 2 && p.nsa * p.slot_bytes + fixed + 1024 > kMaxDynSmem) --p.nsa;
-  if (p.nsa * p.slot_bytes + fixed + 1024 > kMaxDynSmem) return fail(NIC_E_UNSUPPORTED, "conv bf16: patch of %d x %d pixels does not fit shared memory", p.ph_rows, p.pw_cols);
-  p.off_a = 0; p.off_b = p.nsa * p.slot_bytes; p.off_gamma = p.off_b + p.nsb * 128 * 128; p.off_sq = p.off_gamma + (gdn ? 2 * 128 * 128 : 0);
-  p.smem_bytes = p.off_sq + (gdn ? 2 * 128 * 128 : 0) + 1024;
+  p.out_c_offset = d->out_c_offset;
+  p.tma_out = (d->out_layout == NIC_LAYOUT_NHWC && d->out_dtype == NIC_DT_BF16 && p.nb == 128 && d->c_out % 64 == 0 &&
+               ctot % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) ? 1 : 0;
+  // gamma (32 KB, GDN only) + one 32 KB tile that holds the squares for the gamma contraction and then stages the output
+  const int gdn_bytes = (gdn ? 2 * 128 * 128 : 0) + ((gdn || p.tma_out) ? 2 * 128 * 128 : 0);
+  const int bres_bytes = tt.ntaps * p.nchunks * p.nb * 128;
+  p.b_resident = (p.n_ntiles == 1 && p.nb <= 16 && bres_bytes + 2 * p.slot_bytes + gdn_bytes + 1024 <= kMaxDynSmem) ? 1 : 0;
+  int b_bytes;
+  if (p.b_resident) {
+    b_bytes = (bres_bytes + 1023) / 1024 * 1024; p.nsb = 1;
+    p.nsa = 4;
+    while (p.nsa > 2 && p.nsa * p.slot_bytes + b_bytes + gdn_bytes + 1024 > kMaxDynSmem) --p.nsa;
+  } else {
+    // prefer a deep weight ring (TMA latency ~1 us vs ~0.13 us of MMA per slab and block), then A slots
+    p.nsa = 2; p.nsb = 4;
+    if (2 * p.slot_bytes + 4 * 128 * 128 + gdn_bytes + 1024 > kMaxDynSmem)
+      return fail(NIC_E_UNSUPPORTED, "conv bf16: patch of %d x %d pixels does not fit shared memory", p.ph_rows, p.pw_cols);
+    for (;;) {
+      if (p.nsb < kMaxBSlots && p.nsa * p.slot_bytes + (p.nsb + 1) * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem && p.nsb < 2 * p.nsa + 2) ++p.nsb;
+      else if (p.nsa < kMaxSlots && (p.nsa + 1) * p.slot_bytes + p.nsb * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsa;
+      else if (p.nsb < kMaxBSlots && p.nsa * p.slot_bytes + (p.nsb + 1) * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsb;
+      else break;
+    }
+    b_bytes = p.nsb * 128 * 128;
+  }
+  p.off_a = 0; p.off_b = p.nsa * p.slot_bytes; p.off_gamma = p.off_b + b_bytes; p.off_sq = p.off_gamma + (gdn ? 2 * 128 * 128 : 0);
+  p.smem_bytes = p.off_sq + ((gdn || p.tma_out) ? 2 * 128 * 128 : 0) + 1024;
 
-  CUtensorMap map_a, map_w, map_g;
+  CUtensorMap map_a, map_w, map_g, map_o;
   if (int rc = encode_nhwc(&map_a, x, gn, gh, gw, d->c_in, p.pw_cols, p.ph_rows, tt.in_stride)) return rc;
   if (int rc = encode_2d(&map_w, w_packed, d->c_in, static_cast<uint64_t>(tt.ntaps) * p.cout_pad, 64, p.nb)) return rc;
   if (gdn) { if (int rc = encode_2d(&map_g, gdn_gamma, 128, 128, 64, 128)) return rc; }
   else map_g = map_w;
+  if (p.tma_out) {
+    // the output tensor (all ctot channels), walked with the output stride of the phase decomposition
+    const int on = flat ? 1 : d->n, oh = flat ? gh : d->h_out, ow = flat ? gw : d->w_out;
+    if (int rc = encode_nhwc(&map_o, y, on, oh, ow, ctot, kTileW, kTileH, tt.out_stride)) return rc;
+  } else map_o = map_w;
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -584,7 +728,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     attr_set = true;
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  conv_tc_kernel<<<grid, kThreads, p.smem_bytes, st>>>(map_a, map_w, map_g, p);
+  conv_tc_kernel<<<grid, kThreads, p.smem_bytes, st>>>(map_a, map_w, map_g, map_o, p);
   return check_launch("conv_tc_kernel");
 }
 

@@ -344,6 +344,60 @@ static void run_tma_bw(EncodeTiledFn enc, int tile_rows, size_t buf_mb) {
   cudaFree(d); cudaFree(ds);
 }
 
+// -------------------------------------------------------------------------------------------------
+// T6: issue-rate / operand-bandwidth of back-to-back SS-mode MMAs from fixed shared-memory operands
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mma_rate_kernel(int n_dim, int iters, int a_stride_rows, long long* cycles, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 96 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_base, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tm = tmem_base;
+  if (warp == 1 && elect_one()) {
+    const uint32_t idesc = umma_idesc_bf16(128, n_dim);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 48 * 1024);
+    const uint64_t ad = umma_desc_sw128(a0, a_stride_rows * 128), bd = umma_desc_sw128(b0, 1024);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tm + (i & 1) * 256, ad + k * 2, bd + k * 2, idesc, 1);
+    }
+    umma_commit(&bar);
+    const bool ok = mbar_wait(&bar, 0, 1u << 26);
+    const long long t1 = clock64();
+    if (!ok) *status = 1;
+    *cycles = t1 - t0;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+static void run_mma_rate() {
+  long long* dc; int* ds; CK(cudaMalloc(&dc, 8)); CK(cudaMalloc(&ds, 4)); CK(cudaMemset(ds, 0, 4));
+  CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  for (int n : {16, 64, 128, 256}) {
+    for (int stride_rows : {8, 18}) {
+      const int iters = 2000;
+      mma_rate_kernel<<<1, 128, 97 * 1024>>>(n, iters, stride_rows, dc, ds);
+      CK(cudaDeviceSynchronize());
+      long long c; int st; CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, ds, 4, cudaMemcpyDeviceToHost));
+      const double per = (double)c / (iters * 4);
+      printf("  SS MMA M=128 N=%3d K=16, A group stride %2d rows: %.1f clk per MMA -> %.0f MAC/clk/SM (status %d)\n", n, stride_rows, per,
+             128.0 * n * 16 / per, st);
+    }
+  }
+  cudaFree(dc); cudaFree(ds);
+}
+
 int main(int argc, char** argv) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s sm_%d%d, %d SMs, smem/block optin %zu\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount, prop.sharedMemPerBlockOptin);
@@ -373,6 +427,8 @@ int main(int argc, char** argv) {
   printf("T4 TMA-fed MMA\n");
   int ok4 = run_tma_mma(enc, 1);
   int ok4s = run_tma_mma(enc, 2);
+  printf("T6 back-to-back SS-mode MMA rate (one issuing thread, operands resident in shared memory)\n");
+  run_mma_rate();
   printf("T5 L2 -> smem bandwidth\n");
   run_tma_bw(enc, 128, 64);
   run_tma_bw(enc, 256, 64);
