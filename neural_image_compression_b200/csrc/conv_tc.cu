@@ -74,6 +74,9 @@ struct TcParams {
   int flat_hw;                                 // > 0: 1x1 conv over a flattened pixel list; pixel p -> image p / flat_hw
   int tma_out;                                 // NHWC bf16 output leaves through shared memory + TMA tensor stores
   int out_c_offset;                            // channel window start inside the output tensor (TMA coordinates)
+  int shuffle_cout;                            // > 0: sub-pixel (2x2) output: column n = (py * 2 + px) * shuffle_cout + c goes to
+                                               //      pixel (2 oy + py, 2 ox + px), channel c of an fp32 tensor (ConvTranspose2d to RGB)
+  int bias_mod;                                // bias index = column % bias_mod (shuffle) ; 0 = plain
   const float* bias;
   const float* beta;
   void* y;
@@ -152,6 +155,156 @@ __device__ __forceinline__ void store_group(const TcParams& p, long obase, int c
   }
 }
 
+// columns n = (py * 2 + px) * SC + c of one input pixel -> the 2 x 2 output pixels it owns, SC channels, fp32
+template <int SC>
+__device__ __forceinline__ void store_subpixel(const TcParams& p, float* yb, const float* v) {
+#pragma unroll
+  for (int c = 0; c < SC; ++c)
+#pragma unroll
+    for (int yy = 0; yy < 2; ++yy) {
+      float* dst = yb + c * p.ys_c + yy * p.ys_h;
+      const float a = v[(yy * 2) * SC + c], b = v[(yy * 2 + 1) * SC + c];
+      if (p.ys_w == 1 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) *reinterpret_cast<float2*>(dst) = make_float2(a, b);
+      else { dst[0] = a; dst[p.ys_w] = b; }
+    }
+}
+
+// Epilogue of one M = 128 accumulator block (4 warps = 128 threads, thread <-> accumulator row <-> pixel): bias, LeakyReLU or
+// the fused GDN / IGDN, then the store (TMA tensor store of a bf16 NHWC tile staged in shared memory, or direct stores).
+// Returns false when a bounded wait expired.
+__device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb, const float* s_bias, const float* s_beta, uint8_t* sq,
+                                               const uint8_t* gamma_smem, const CUtensorMap* map_o_ptr, uint32_t acc_tmem, int q, int lane,
+                                               bool leader, int img, int oy0, int ox0, int py, int px, int cbase, uint32_t& gdn_count) {
+  const bool gdn = p.epilogue == NIC_EPI_GDN || p.epilogue == NIC_EPI_IGDN;
+  const bool igdn = p.epilogue == NIC_EPI_IGDN;
+  const int ncg = (p.nb + 31) / 32;
+  const int row = q * 32 + lane, g = row >> 3, c8 = row & 7;
+  const uint32_t acc_addr = acc_tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const int oy = oy0 + g, ox = ox0 + c8;
+  const int out_y = oy * p.out_stride + py, out_x = ox * p.out_stride + px;
+  const bool valid = oy < p.hp && ox < p.wp && out_y < p.hout && out_x < p.wout;
+  long obase;
+  if (p.flat_hw > 0) {
+    const long pix = static_cast<long>(oy) * kTileW + ox;
+    obase = (pix / p.flat_hw) * p.ys_n + (pix % p.flat_hw) * p.ys_w;
+  } else {
+    obase = img * p.ys_n + static_cast<long>(out_y) * p.ys_h + static_cast<long>(out_x) * p.ys_w;
+  }
+  if (p.tma_out) {
+    // the staging tile (= the squares tile) may still be read by the previous block's tensor store
+    if (leader) tma_store_wait_read();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+  float xr[128];
+  if (gdn) {
+    // x (+ bias) stays in registers; its squares go to shared memory as the bf16 K-major A operand of the
+    // gamma contraction, whose result OVERWRITES this accumulator (no extra TMEM); then y = x * rsqrt(beta + .)
+#pragma unroll
+    for (int cg = 0; cg < 4; ++cg) {
+      tmem_ld_32x32(acc_addr + cg * 32, xr + cg * 32);
+      tmem_ld_wait();
+      uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c0 = cg * 32 + j * 8 + e * 2;
+          const float a = xr[c0] + s_bias[c0], bb = xr[c0 + 1] + s_bias[c0 + 1];
+          xr[c0] = a; xr[c0 + 1] = bb;
+          w[e] = pack_bf16x2(a * a, bb * bb);
+        }
+        const int chunk = ((cg & 1) * 4 + j) ^ (row & 7);
+        *reinterpret_cast<uint4*>(half + chunk * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (leader) {
+      if (gdn_count == 0) wait_or_abort(&sb->gamma_full, 0, sb, p.status);
+      tcgen05_fence_after();
+      const uint32_t idg = umma_idesc_bf16(128, 128);
+      const uint32_t sq_base = smem_u32(sq), g_base = smem_u32(gamma_smem);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(acc_tmem, umma_desc_sw128(sq_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024),
+                  umma_desc_sw128(g_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024), idg, k > 0);
+      umma_commit(&sb->gdn_full);
+    }
+    if (!__all_sync(0xffffffffu, wait_or_abort(&sb->gdn_full, gdn_count & 1, sb, p.status))) return false;
+    ++gdn_count;
+    tcgen05_fence_after();
+  }
+  const int nvalid_c = p.cout - cbase;                      // channels of this N tile that exist
+  auto emit_group = [&](int cg, const float* v) {             // one pixel x 32 channels: to the staging tile or to HBM
+    if (p.tma_out) {
+      uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int chunk = ((cg & 1) * 4 + j) ^ (row & 7);
+        *reinterpret_cast<uint4*>(half + chunk * 16) =
+            make_uint4(pack_bf16x2(v[j * 8], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                       pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+      }
+    } else if (valid) {
+      if (p.shuffle_cout > 0) {
+        // sub-pixel scatter: this thread's input pixel (oy, ox) owns output pixels (2 oy + {0,1}, 2 ox + {0,1})
+        float* yb = static_cast<float*>(p.y) + img * p.ys_n + static_cast<long>(2 * oy) * p.ys_h + static_cast<long>(2 * ox) * p.ys_w;
+        switch (p.shuffle_cout) {
+          case 1: store_subpixel<1>(p, yb, v); break;
+          case 2: store_subpixel<2>(p, yb, v); break;
+          case 3: store_subpixel<3>(p, yb, v); break;
+          default: store_subpixel<4>(p, yb, v); break;
+        }
+      } else {
+        store_group(p, obase, cbase + cg * 32, v);
+      }
+    }
+  };
+  if (gdn) {
+#pragma unroll
+    for (int cg = 0; cg < 4; ++cg) {
+      float v[32];
+      tmem_ld_32x32(acc_addr + cg * 32, v);
+      tmem_ld_wait();
+      if (igdn) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = xr[cg * 32 + j] * sqrt_approx(v[j] + s_beta[cg * 32 + j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = xr[cg * 32 + j] * rsqrtf(v[j] + s_beta[cg * 32 + j]);
+      }
+      emit_group(cg, v);
+    }
+  } else {
+    for (int cg = 0; cg < ncg; ++cg) {
+      float v[32];
+      tmem_ld_32x32(acc_addr + cg * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = cbase + cg * 32 + j;
+        float x = v[j] + (c < p.cout ? s_bias[c] : 0.f);
+        if (p.epilogue == NIC_EPI_LRELU) x = x > 0.f ? x : 0.01f * x;
+        v[j] = x;
+      }
+      emit_group(cg, v);
+    }
+  }
+  if (p.tma_out) {
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (leader) {
+      const int wc = ox0 * p.out_stride + px, hc = oy0 * p.out_stride + py;
+      for (int h = 0; h < 2; ++h)
+        if (h * 64 < nvalid_c) tma_store_4d(map_o_ptr, sq + h * (128 * 128), p.out_c_offset + cbase + h * 64, wc, hc, img);
+      tma_store_commit();
+    }
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p) {
@@ -168,7 +321,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       s_tap_aoff[t][b] = static_cast<uint32_t>(((p.taps[t].roff + p.blk_roff[b]) * p.pw_cols + p.taps[t].coff + p.blk_coff[b]) * 128) >> 4;
     s_tap_brow[t] = p.taps[t].slab;
   }
-  for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = p.bias[p.bias_mod ? i % p.bias_mod : i];
   if (p.beta) for (int i = threadIdx.x; i < 128; i += kThreads) s_beta[i] = p.beta[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool gdn = p.epilogue == NIC_EPI_GDN || p.epilogue == NIC_EPI_IGDN;
@@ -329,121 +482,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (!__all_sync(0xffffffffu, wait_or_abort(&sb.acc_full[buf], (tcount >> 1) & 1, &sb, p.status))) break;
       tcgen05_fence_after();
       const int cbase = ntile * p.nb;
-      for (int b = 0; b < nblk && ok; ++b) {
-        const uint32_t acc_addr = tmem + buf * 256 + b * 128 + (static_cast<uint32_t>(q * 32) << 16);
-        const int oy0 = ty * p.tile_h + p.blk_roff[b], ox0 = tx * p.tile_w + p.blk_coff[b];
-        const int oy = oy0 + g, ox = ox0 + c8;
-        const int out_y = oy * p.out_stride + ph.py, out_x = ox * p.out_stride + ph.px;
-        const bool valid = oy < p.hp && ox < p.wp && out_y < p.hout && out_x < p.wout;
-        long obase;
-        if (p.flat_hw > 0) {
-          const long pix = static_cast<long>(oy) * kTileW + ox;
-          obase = (pix / p.flat_hw) * p.ys_n + (pix % p.flat_hw) * p.ys_w;
-        } else {
-          obase = img * p.ys_n + static_cast<long>(out_y) * p.ys_h + static_cast<long>(out_x) * p.ys_w;
-        }
-        if (p.tma_out) {
-          // the staging tile (= the squares tile) may still be read by the previous block's tensor store
-          if (warp == 3 && lane == 0) tma_store_wait_read();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        float xr[128];
-        if (gdn) {
-          // x (+ bias) stays in registers; its squares go to shared memory as the bf16 K-major A operand of the
-          // gamma contraction, whose result OVERWRITES this accumulator (no extra TMEM); then y = x * rsqrt(beta + .)
-#pragma unroll
-          for (int cg = 0; cg < 4; ++cg) {
-            tmem_ld_32x32(acc_addr + cg * 32, xr + cg * 32);
-            tmem_ld_wait();
-            uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c0 = cg * 32 + j * 8 + e * 2;
-                const float a = xr[c0] + s_bias[c0], bb = xr[c0 + 1] + s_bias[c0 + 1];
-                xr[c0] = a; xr[c0 + 1] = bb;
-                w[e] = pack_bf16x2(a * a, bb * bb);
-              }
-              const int chunk = ((cg & 1) * 4 + j) ^ (row & 7);
-              *reinterpret_cast<uint4*>(half + chunk * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          }
-          fence_proxy_async_smem();
-          tcgen05_fence_before();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (warp == 3 && lane == 0) {
-            if (gdn_count == 0) wait_or_abort(&sb.gamma_full, 0, &sb, p.status);
-            tcgen05_fence_after();
-            const uint32_t idg = umma_idesc_bf16(128, 128);
-            const uint32_t sq_base = smem_u32(sq), g_base = smem_u32(smem + p.off_gamma);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              umma_bf16(tmem + buf * 256 + b * 128, umma_desc_sw128(sq_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024),
-                        umma_desc_sw128(g_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024), idg, k > 0);
-            umma_commit(&sb.gdn_full);
-          }
-          if (!__all_sync(0xffffffffu, wait_or_abort(&sb.gdn_full, gdn_count & 1, &sb, p.status))) { ok = false; break; }
-          ++gdn_count;
-          tcgen05_fence_after();
-        }
-        const int nvalid_c = p.cout - cbase;                      // channels of this N tile that exist
-        auto emit_group = [&](int cg, const float* v) {             // one pixel x 32 channels: to the staging tile or to HBM
-          if (p.tma_out) {
-            uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int chunk = ((cg & 1) * 4 + j) ^ (row & 7);
-              *reinterpret_cast<uint4*>(half + chunk * 16) =
-                  make_uint4(pack_bf16x2(v[j * 8], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
-                             pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
-            }
-          } else if (valid) {
-            store_group(p, obase, cbase + cg * 32, v);
-          }
-        };
-        if (gdn) {
-#pragma unroll
-          for (int cg = 0; cg < 4; ++cg) {
-            float v[32];
-            tmem_ld_32x32(acc_addr + cg * 32, v);
-            tmem_ld_wait();
-            if (igdn) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = xr[cg * 32 + j] * sqrt_approx(v[j] + s_beta[cg * 32 + j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = xr[cg * 32 + j] * rsqrtf(v[j] + s_beta[cg * 32 + j]);
-            }
-            emit_group(cg, v);
-          }
-        } else {
-          for (int cg = 0; cg < ncg; ++cg) {
-            float v[32];
-            tmem_ld_32x32(acc_addr + cg * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int c = cbase + cg * 32 + j;
-              float x = v[j] + (c < p.cout ? s_bias[c] : 0.f);
-              if (p.epilogue == NIC_EPI_LRELU) x = x > 0.f ? x : 0.01f * x;
-              v[j] = x;
-            }
-            emit_group(cg, v);
-          }
-        }
-        if (p.tma_out) {
-          fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (warp == 3 && lane == 0) {
-            const int wc = ox0 * p.out_stride + ph.px, hc = oy0 * p.out_stride + ph.py;
-            for (int h = 0; h < 2; ++h)
-              if (h * 64 < nvalid_c) tma_store_4d(&map_o, sq + h * (128 * 128), p.out_c_offset + cbase + h * 64, wc, hc, img);
-            tma_store_commit();
-          }
-        }
-      }
+      for (int b = 0; b < nblk && ok; ++b)
+        ok = epilogue_block(p, &sb, s_bias, s_beta, sq, smem + p.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane, warp == 3 && lane == 0,
+                            img, ty * p.tile_h + p.blk_roff[b], tx * p.tile_w + p.blk_coff[b], ph.py, ph.px, ntile * p.nb, gdn_count);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb.acc_empty[buf]);
@@ -454,6 +495,178 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// First layer of g_a: Conv2d(3, 128, 5, stride 2, pad 2) + GDN straight from the NCHW fp32 image (Components.py:10-11).
+// K = 75 is too shallow for a TMA-fed pipeline, so four producer warps build the [128 pixel x 80] bf16 A operand of each
+// block in shared memory (im2col of a 35 x 35 x 3 image patch, k = (kh * 5 + kw) * 3 + c, zero padded to 80), one thread
+// issues 5 tcgen05.mma per block against the resident [128 x 80] weights, and the shared epilogue applies the fused GDN and
+// stores the bf16 NHWC tile with TMA.  9 warps: 0-3 producers, 4 MMA issuer / weight loader, 5-8 epilogue.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFirstThreads = 288;
+constexpr int kPatchW = 36, kPatchH = 35, kPatchPlane = kPatchH * kPatchW;     // fp32 patch rows padded to 36 floats
+
+struct FirstParams {
+  const float* x;                 // [n, 3, hin, win] fp32
+  int n, hin, win, tiles_x, tiles_y, total_tiles;
+  int off_a, off_w, off_gamma, off_sq, off_patch;
+};
+
+struct __align__(8) FirstBarriers {
+  uint64_t a_full, a_empty, w_full;
+  TcBarriers common;              // acc_full / acc_empty / gdn_full / gamma_full + tmem_base + abort flag (epilogue_block uses these)
+};
+
+__global__ void __launch_bounds__(kFirstThreads, 1)
+conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_g,
+                     const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p, const __grid_constant__ FirstParams f) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ FirstBarriers fb;
+  __shared__ float s_bias[128];
+  __shared__ float s_beta[128];
+  TcBarriers& sb = fb.common;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  if (tid < 128) { s_bias[tid] = p.bias[tid]; s_beta[tid] = p.beta[tid]; }
+  if (tid == 0) {
+    mbar_init(&fb.a_full, 128); mbar_init(&fb.a_empty, 1); mbar_init(&fb.w_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], 4); }
+    mbar_init(&sb.gdn_full, 1); mbar_init(&sb.gamma_full, 1);
+    sb.abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == 4) { tmem_alloc(&sb.tmem_base, 512); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = sb.tmem_base;
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  float* patch = reinterpret_cast<float*>(smem + f.off_patch);
+
+  auto tile_coords = [&](int tile, int& img, int& ty, int& tx) {
+    tx = tile % f.tiles_x; tile /= f.tiles_x; ty = tile % f.tiles_y; img = tile / f.tiles_y;
+  };
+
+  if (warp < 4) {
+    // ===================== producers: image patch -> bf16 im2col A operand =====================
+    constexpr int kPerThread = (3 * kPatchH * kPatchH + 127) / 128;     // 29
+    float pre[kPerThread];
+    auto prefetch = [&](int tile) {
+      int img, ty, tx;
+      tile_coords(tile, img, ty, tx);
+      const int y0 = 2 * (ty * 16) - 2, x0 = 2 * (tx * 16) - 2;
+      const float* base = f.x + static_cast<long>(img) * 3 * f.hin * f.win;
+#pragma unroll
+      for (int j = 0; j < kPerThread; ++j) {
+        const int e = tid + 128 * j;
+        float v = 0.f;
+        if (e < 3 * kPatchH * kPatchH) {
+          const int c = e / (kPatchH * kPatchH), rem = e - c * (kPatchH * kPatchH);
+          const int yy = y0 + rem / kPatchH, xx = x0 + rem % kPatchH;
+          if (yy >= 0 && yy < f.hin && xx >= 0 && xx < f.win) v = __ldg(base + (static_cast<long>(c) * f.hin + yy) * f.win + xx);
+        }
+        pre[j] = v;
+      }
+    };
+    if (first_tile < f.total_tiles) prefetch(first_tile);
+    uint32_t it = 0;
+    const int r = tid, g = r >> 3, c8 = r & 7;
+    for (int tile = first_tile; tile < f.total_tiles; tile += tile_step, ++it) {
+#pragma unroll
+      for (int j = 0; j < kPerThread; ++j) {
+        const int e = tid + 128 * j;
+        if (e < 3 * kPatchH * kPatchH) {
+          const int c = e / (kPatchH * kPatchH), rem = e - c * (kPatchH * kPatchH);
+          patch[c * kPatchPlane + (rem / kPatchH) * kPatchW + rem % kPatchH] = pre[j];
+        }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (tile + tile_step < f.total_tiles) prefetch(tile + tile_step);
+      if (!__all_sync(0xffffffffu, wait_or_abort(&fb.a_empty, (it & 1) ^ 1, &sb, p.status))) break;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const float* src = patch + (2 * g) * kPatchW + 2 * (b * 8 + c8);
+        uint8_t* dst = smem + f.off_a + b * (2 * 128 * 128) + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 10; ++ch) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int k = ch * 8 + e * 2 + h;
+              if (k < 75) { const int tap = k / 3, c = k % 3; v2[h] = src[c * kPatchPlane + (tap / 5) * kPatchW + (tap % 5)]; }
+              else v2[h] = 0.f;
+            }
+            w[e] = pack_bf16x2(v2[0], v2[1]);
+          }
+          *reinterpret_cast<uint4*>(dst + (ch >> 3) * (128 * 128) + (((ch & 7) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&fb.a_full);
+      asm volatile("bar.sync 2, 128;" ::: "memory");       // everyone is done reading the patch before it is overwritten
+    }
+  } else if (warp == 4) {
+    // ===================== weight loader + MMA issuer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_g); tma_prefetch_desc(&map_o);
+      mbar_expect_tx(&fb.w_full, 2 * 128 * 128);
+      tma_load_2d(smem + f.off_w, &map_w, &fb.w_full, 0, 0);
+      tma_load_2d(smem + f.off_w + 128 * 128, &map_w, &fb.w_full, 64, 0);
+      mbar_expect_tx(&sb.gamma_full, 2 * 128 * 128);
+      tma_load_2d(smem + f.off_gamma, &map_g, &sb.gamma_full, 0, 0);
+      tma_load_2d(smem + f.off_gamma + 128 * 128, &map_g, &sb.gamma_full, 64, 0);
+      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      const uint32_t hi = umma_desc_hi(1024);
+      const uint32_t a_lo = umma_desc_lo(smem_u32(smem + f.off_a)), w_lo = umma_desc_lo(smem_u32(smem + f.off_w));
+      bool ok = wait_or_abort(&fb.w_full, 0, &sb, p.status);
+      uint32_t it = 0;
+      for (int tile = first_tile; tile < f.total_tiles && ok; tile += tile_step, ++it) {
+        const uint32_t buf = it & 1;
+        if (!wait_or_abort(&sb.acc_empty[buf], ((it >> 1) & 1) ^ 1, &sb, p.status)) break;
+        if (!wait_or_abort(&fb.a_full, it & 1, &sb, p.status)) break;
+        tcgen05_fence_after();
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const uint32_t d = tmem + buf * 256 + b * 128;
+          const uint32_t ab = a_lo + b * ((2 * 128 * 128) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + 2 * k, hi, w_lo + 2 * k, hi, idesc, k);
+          umma_bf16_lohi(d, ab + ((128 * 128) >> 4), hi, w_lo + ((128 * 128) >> 4), hi, idesc, 1);      // k = 64..79
+        }
+        umma_commit(&fb.a_empty);
+        umma_commit(&sb.acc_full[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 5..8) =====================
+    const int q = warp & 3;
+    uint8_t* sq = smem + f.off_sq;
+    uint32_t it = 0, gdn_count = 0;
+    bool ok = true;
+    for (int tile = first_tile; tile < f.total_tiles && ok; tile += tile_step, ++it) {
+      int img, ty, tx;
+      tile_coords(tile, img, ty, tx);
+      const uint32_t buf = it & 1;
+      if (!__all_sync(0xffffffffu, wait_or_abort(&sb.acc_full[buf], (it >> 1) & 1, &sb, p.status))) break;
+      tcgen05_fence_after();
+      for (int b = 0; b < 2 && ok; ++b) {
+        if (tx * 16 + b * 8 >= p.wp) break;
+        ok = epilogue_block(p, &sb, s_bias, s_beta, sq, smem + f.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane, warp == 5 && lane == 0,
+                            img, ty * 16, tx * 16 + b * 8, 0, 0, 0, gdn_count);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb.acc_empty[buf]);
+    }
+    if (warp == 5 && lane == 0) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -565,9 +778,41 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat
   }
 }
 
-__global__ void pack_identity_bf16_kernel(__nv_bfloat16* out, int c) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c * c; i += gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16_rn((i / c) == (i % c) ? 1.f : 0.f);
+// sub-pixel form of ConvTranspose2d(c_in, c_out, 5, stride 2, pad 2, output_padding 1), reference weight [c_in, c_out, 5, 5]:
+//   out[2 oy + py, 2 ox + px, c] = sum_{(dy, dx) in 3x3} in[oy + dy, ox + dx, :] . W'[(dy + 1) * 3 + (dx + 1)][(py * 2 + px) * c_out + c][:]
+// where W' holds w[:, c, kh, kw] of the tap of phase (py, px) that reads offset (dy, dx) and 0 where the phase has no such tap.
+__global__ void pack_weight_subpixel_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin, int cout, TapTable tt) {
+  const long total = 9L * 16 * cin;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % cin);
+    const int n = static_cast<int>((i / cin) % 16);
+    const int slab = static_cast<int>(i / (16L * cin));
+    const int dy = slab / 3 - 1, dx = slab % 3 - 1;
+    float v = 0.f;
+    if (n < 4 * cout) {
+      const int phase = n / cout, c = n % cout;          // tap-table phases are ordered (py, px) = (0,0) (0,1) (1,0) (1,1)
+      for (int t = tt.phase_begin[phase]; t < tt.phase_begin[phase + 1]; ++t)
+        if (tt.dy[t] == dy && tt.dx[t] == dx) v = w[((static_cast<long>(ci) * cout + c) * 5 + tt.kh[t]) * 5 + tt.kw[t]];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// first layer: reference [128, 3, 5, 5] -> [128][128] bf16, k = (kh * 5 + kw) * 3 + c, zero for k >= 75
+__global__ void pack_first_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 128 * 128; i += gridDim.x * blockDim.x) {
+    const int co = i / 128, k = i % 128;
+    float v = 0.f;
+    if (k < 75) { const int tap = k / 3, c = k % 3; v = w[((co * 3 + c) * 5 + tap / 5) * 5 + tap % 5]; }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+int check_first_layer(const nic_conv_desc* d) {
+  if (d->c_in != 3 || d->c_out != 128 || d->kh != 5 || d->kw != 5 || d->stride != 2 || d->pad != 2 || d->transposed || d->mask_a ||
+      d->epilogue != NIC_EPI_GDN)
+    return fail(NIC_E_UNSUPPORTED, "conv bf16: the only c_in < 64 layer built is Conv2d(3, 128, 5, stride 2, pad 2) + GDN (g_a layer 1)");
+  return NIC_OK;
 }
 
 __global__ void pack_gdn_bf16_kernel(int c, float beta_bound, float gamma_bound, float pedestal, const float* __restrict__ beta,
@@ -580,15 +825,27 @@ __global__ void pack_gdn_bf16_kernel(int c, float beta_bound, float gamma_bound,
 }
 
 inline int nb_for(int cout) { return cout <= 16 ? 16 : 128; }
+// stride-2 transposed conv with <= 4 output channels (g_s last layer, 128 -> 3): run as ONE 3x3 stride-1 conv to 4 * c_out
+// "sub-pixel" channels instead of four phase convs with N = 16 each (an N = 16 MMA costs 39 clk, tools/tc_probe T6)
+inline bool subpixel_form(const nic_conv_desc* d) {
+  return d->transposed && d->stride == 2 && d->kh == 5 && d->kw == 5 && d->pad == 2 && d->output_padding == 1 && 4 * d->c_out <= 16 && d->c_in >= 64;
+}
+inline nic_conv_desc subpixel_desc(const nic_conv_desc* d) {
+  nic_conv_desc e = *d;
+  e.transposed = 0; e.output_padding = 0; e.kh = e.kw = 3; e.stride = 1; e.pad = 1;
+  e.c_out = 4 * d->c_out; e.h_out = d->h_in; e.w_out = d->w_in; e.out_c_total = 0; e.out_c_offset = 0;
+  return e;
+}
 inline bool small_cin(const nic_conv_desc* d) { return d->c_in < 64; }
 
 }  // namespace
 
 // Packed layout (bf16 elements):
 //   c_in >= 64 : [tap][c_out padded to a multiple of nb][c_in]
-//   c_in  < 64 : the fp32 [tap][c_in][c_out] pack of conv_simt.cu (as raw bytes) followed by a c_out x c_out identity
+//   c_in  = 3  : [c_out = 128][k padded to 128], k = (kh * kw_size + kw) * 3 + c   (first layer, conv_first_tc_kernel)
 size_t packed_weight_elems_tc(const nic_conv_desc* d, const TapTable& tt) {
-  if (small_cin(d)) return static_cast<size_t>(tt.ntaps) * d->c_in * d->c_out * 2 + static_cast<size_t>(d->c_out) * d->c_out;
+  if (small_cin(d)) return static_cast<size_t>(128) * 128;
+  if (subpixel_form(d)) return static_cast<size_t>(9) * 16 * d->c_in;
   const int nb = nb_for(d->c_out);
   const int cout_pad = (d->c_out + nb - 1) / nb * nb;
   return static_cast<size_t>(tt.ntaps) * cout_pad * d->c_in;
@@ -599,12 +856,16 @@ __global__ void pack_weight_f32_kernel(const float*, float*, int, int, int, int,
 int pack_weight_tc(const nic_conv_desc* d, const TapTable& tt, const float* w_ref, void* w_packed, cudaStream_t st) {
   if (d->precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "pack_conv_weight: precision %d is not built (fp32 and bf16 are)", d->precision);
   if (small_cin(d)) {
-    const long total = static_cast<long>(tt.ntaps) * d->c_in * d->c_out;
-    pack_weight_f32_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w_ref, static_cast<float*>(w_packed), d->c_in, d->c_out, d->kh,
-                                                                                d->kw, d->transposed, tt);
-    if (int rc = check_launch("pack_weight_f32_kernel")) return rc;
-    pack_identity_bf16_kernel<<<64, 256, 0, st>>>(static_cast<__nv_bfloat16*>(w_packed) + total * 2, d->c_out);
-    return check_launch("pack_identity_bf16_kernel");
+    if (int rc = check_first_layer(d)) return rc;
+    pack_first_bf16_kernel<<<64, 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed));
+    return check_launch("pack_first_bf16_kernel");
+  }
+  if (subpixel_form(d)) {
+    if (d->c_in % 64) return fail(NIC_E_UNSUPPORTED, "conv bf16: c_in=%d must be a multiple of 64", d->c_in);
+    const long total = 9L * 16 * d->c_in;
+    pack_weight_subpixel_bf16_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed), d->c_in,
+                                                                                         d->c_out, tt);
+    return check_launch("pack_weight_subpixel_bf16_kernel");
   }
   if (d->c_in % 64) return fail(NIC_E_UNSUPPORTED, "conv bf16: c_in=%d must be a multiple of 64 (or < 64 for the first layer)", d->c_in);
   const int nb = nb_for(d->c_out);
@@ -628,12 +889,14 @@ int pack_gdn_tc(int32_t c, float beta_min, const float* beta_raw, const float* g
 }
 
 size_t conv_workspace_bytes_tc(const nic_conv_desc* d) {
-  if (small_cin(d)) return static_cast<size_t>(d->n) * d->h_out * d->w_out * d->c_out * 2;   // bf16 NHWC pre-activation
+  (void)d;
   return 0;
 }
 
+// `shuffle`: non-null when `d` is the 3x3 stride-1 sub-pixel form of a stride-2 transposed conv (see conv_fwd_tc); it is the
+// ORIGINAL descriptor, whose output tensor the epilogue scatters into.
 static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, const void* w_packed, const float* bias, const void* gdn_gamma,
-                     const float* gdn_beta, void* y, cudaStream_t st) {
+                     const float* gdn_beta, void* y, cudaStream_t st, const nic_conv_desc* shuffle = nullptr) {
   TcParams p{};
   if (int rc = build_tc_geometry(d, tt, &p)) return rc;
   const bool gdn = d->epilogue == NIC_EPI_GDN || d->epilogue == NIC_EPI_IGDN;
@@ -652,8 +915,16 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   else { p.ys_n = static_cast<long>(d->h_out) * d->w_out * ctot; p.ys_h = static_cast<long>(d->w_out) * ctot; p.ys_w = ctot; p.ys_c = 1; }
   const size_t esz = d->out_dtype == NIC_DT_BF16 ? 2 : 4;
   p.y = static_cast<uint8_t*>(y) + static_cast<size_t>(d->out_c_offset) * p.ys_c * esz;
-  if (p.ys_c == 1 && ((reinterpret_cast<uintptr_t>(p.y) & 15) || (ctot * esz) % 16)) return fail(NIC_E_BADALIGN, "conv bf16: NHWC output rows must be 16-byte aligned");
+  if (!shuffle && p.ys_c == 1 && ((reinterpret_cast<uintptr_t>(p.y) & 15) || (ctot * esz) % 16)) return fail(NIC_E_BADALIGN, "conv bf16: NHWC output rows must be 16-byte aligned");
   p.bias = bias; p.beta = gdn_beta;
+  if (shuffle) {
+    if (shuffle->out_dtype != NIC_DT_F32) return fail(NIC_E_UNSUPPORTED, "conv bf16: the sub-pixel output path writes fp32");
+    const int sct = shuffle->out_c_total ? shuffle->out_c_total : shuffle->c_out;
+    p.shuffle_cout = shuffle->c_out; p.bias_mod = shuffle->c_out;
+    if (shuffle->out_layout == NIC_LAYOUT_NCHW) { p.ys_n = static_cast<long>(sct) * shuffle->h_out * shuffle->w_out; p.ys_c = static_cast<long>(shuffle->h_out) * shuffle->w_out; p.ys_h = shuffle->w_out; p.ys_w = 1; }
+    else { p.ys_n = static_cast<long>(shuffle->h_out) * shuffle->w_out * sct; p.ys_h = static_cast<long>(shuffle->w_out) * sct; p.ys_w = sct; p.ys_c = 1; }
+    p.y = static_cast<uint8_t*>(y) + static_cast<size_t>(shuffle->out_c_offset) * p.ys_c * 4;
+  }
   p.status = status_word();
   if (!p.status) return fail(NIC_E_CUDA, "conv bf16: cannot allocate the status word");
 
@@ -684,7 +955,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   // shared memory: A slots | B ring (or resident weights) | gamma | squares
   p.slot_bytes = (p.ph_rows * p.pw_cols * 128 + 1023) / 1024 * 1024;
   p.out_c_offset = d->out_c_offset;
-  p.tma_out = (d->out_layout == NIC_LAYOUT_NHWC && d->out_dtype == NIC_DT_BF16 && p.nb == 128 && d->c_out % 64 == 0 &&
+  p.tma_out = (!shuffle && d->out_layout == NIC_LAYOUT_NHWC && d->out_dtype == NIC_DT_BF16 && p.nb == 128 && d->c_out % 64 == 0 &&
                ctot % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) ? 1 : 0;
   // gamma (32 KB, GDN only) + one 32 KB tile that holds the squares for the gamma contraction and then stages the output
   const int gdn_bytes = (gdn ? 2 * 128 * 128 : 0) + ((gdn || p.tma_out) ? 2 * 128 * 128 : 0);
@@ -732,31 +1003,55 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   return check_launch("conv_tc_kernel");
 }
 
+static int launch_first(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* gdn_gamma,
+                        const float* gdn_beta, void* y, cudaStream_t st) {
+  if (int rc = check_first_layer(d)) return rc;
+  if (d->in_layout != NIC_LAYOUT_NCHW || d->in_dtype != NIC_DT_F32) return fail(NIC_E_UNSUPPORTED, "conv bf16 (first layer): input must be the NCHW fp32 image");
+  if (d->out_layout != NIC_LAYOUT_NHWC || d->out_dtype != NIC_DT_BF16 || d->out_c_total > 128) return fail(NIC_E_UNSUPPORTED, "conv bf16 (first layer): output must be NHWC bf16");
+  if (!gdn_gamma || !gdn_beta) return fail(NIC_E_BADSHAPE, "conv bf16 (first layer): packed gamma / beta missing");
+  if ((reinterpret_cast<uintptr_t>(y) & 127) || (reinterpret_cast<uintptr_t>(w_packed) & 127)) return fail(NIC_E_BADALIGN, "conv bf16: tensors must be 128-byte aligned for TMA");
+  TcParams p{};
+  p.epilogue = NIC_EPI_GDN; p.out_dtype = NIC_DT_BF16; p.nb = 128; p.cout = 128; p.tma_out = 1; p.out_stride = 1;
+  p.n = d->n; p.hout = d->h_out; p.wout = d->w_out; p.hp = d->h_out; p.wp = d->w_out;
+  p.bias = bias; p.beta = gdn_beta; p.y = y;
+  p.ys_n = static_cast<long>(d->h_out) * d->w_out * 128; p.ys_h = static_cast<long>(d->w_out) * 128; p.ys_w = 128; p.ys_c = 1;
+  p.status = status_word();
+  if (!p.status) return fail(NIC_E_CUDA, "conv bf16: cannot allocate the status word");
+  FirstParams f{};
+  f.x = static_cast<const float*>(x); f.n = d->n; f.hin = d->h_in; f.win = d->w_in;
+  f.tiles_x = (d->w_out + 15) / 16; f.tiles_y = (d->h_out + 15) / 16; f.total_tiles = f.tiles_x * f.tiles_y * d->n;
+  f.off_a = 0; f.off_w = 4 * 128 * 128; f.off_gamma = f.off_w + 2 * 128 * 128; f.off_sq = f.off_gamma + 2 * 128 * 128;
+  f.off_patch = f.off_sq + 2 * 128 * 128;
+  const int smem_bytes = f.off_patch + 3 * kPatchPlane * 4 + 1024 + 64;
+  CUtensorMap map_w, map_g, map_o;
+  if (int rc = encode_2d(&map_w, w_packed, 128, 128, 64, 128)) return rc;
+  if (int rc = encode_2d(&map_g, gdn_gamma, 128, 128, 64, 128)) return rc;
+  if (int rc = encode_nhwc(&map_o, y, d->n, d->h_out, d->w_out, 128, kTileW, kTileH, 1)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), "cudaFuncSetAttribute")) return rc;
+    attr_set = true;
+  }
+  const int grid = f.total_tiles < kNumSMs ? f.total_tiles : kNumSMs;
+  conv_first_tc_kernel<<<grid, kFirstThreads, smem_bytes, st>>>(map_w, map_g, map_o, p, f);
+  return check_launch("conv_first_tc_kernel");
+}
+
 int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* gdn_gamma, const float* gdn_beta,
                 void* y, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (d->precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "conv: precision %d is not built (fp32 and bf16 are)", d->precision);
   TapTable tt;
   if (int rc = build_tap_table(d, &tt)) return rc;
+  if (subpixel_form(d)) {
+    if (d->epilogue != NIC_EPI_BIAS) return fail(NIC_E_UNSUPPORTED, "conv bf16: the sub-pixel path has a bias-only epilogue");
+    const nic_conv_desc e = subpixel_desc(d);
+    TapTable te;
+    if (int rc = build_tap_table(&e, &te)) return rc;
+    return launch_tc(&e, te, x, w_packed, bias, nullptr, nullptr, y, st, d);
+  }
   if (!small_cin(d)) return launch_tc(d, tt, x, w_packed, bias, gdn_gamma, gdn_beta, y, st);
 
-  // first layer (c_in = 3): 75-deep contraction on the CUDA cores (fp32, straight from the NCHW image) into a bf16 NHWC
-  // pre-activation, then the activation through the tensor-core kernel as a 1x1 identity slab with the fused epilogue
-  const size_t need = conv_workspace_bytes_tc(d);
-  if (!workspace || workspace_bytes < need) return fail(NIC_E_WORKSPACE, "conv bf16 (first layer): workspace %zu < %zu bytes", workspace_bytes, need);
-  if (d->c_out != 128) return fail(NIC_E_UNSUPPORTED, "conv bf16 (first layer): c_out must be 128");
-  static float* zero_bias = nullptr;
-  if (!zero_bias) { if (cudaMalloc(&zero_bias, 128 * sizeof(float)) != cudaSuccess) return fail(NIC_E_CUDA, "cudaMalloc"); cudaMemset(zero_bias, 0, 128 * sizeof(float)); }
-  nic_conv_desc c1 = *d;
-  c1.epilogue = NIC_EPI_BIAS; c1.precision = NIC_PREC_FP32; c1.out_layout = NIC_LAYOUT_NHWC; c1.out_c_total = 0; c1.out_c_offset = 0;
-  if (int rc = conv_fwd_fp32_ex(&c1, x, w_packed, bias, workspace, 1, st)) return rc;
-  nic_conv_desc c2 = *d;
-  c2.c_in = d->c_out; c2.h_in = d->h_out; c2.w_in = d->w_out; c2.kh = c2.kw = 1; c2.stride = 1; c2.pad = 0; c2.transposed = 0; c2.output_padding = 0;
-  c2.mask_a = 0; c2.in_layout = NIC_LAYOUT_NHWC; c2.in_dtype = NIC_DT_BF16;
-  TapTable t2;
-  if (int rc = build_tap_table(&c2, &t2)) return rc;
-  const size_t simt_bytes = static_cast<size_t>(tt.ntaps) * d->c_in * d->c_out * sizeof(float);
-  const void* ident = static_cast<const uint8_t*>(w_packed) + simt_bytes;
-  return launch_tc(&c2, t2, workspace, ident, zero_bias, gdn_gamma, gdn_beta, y, st);
+  return launch_first(d, x, w_packed, bias, gdn_gamma, gdn_beta, y, st);
 }
 
 }  // namespace nic
