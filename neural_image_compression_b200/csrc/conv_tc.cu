@@ -24,6 +24,7 @@
 // Activations are NHWC bf16 between layers (c_in a multiple of 64).  The 3-channel first layer runs its
 // 75-deep contraction on the CUDA cores (conv_simt.cu) and only its GDN comes here (1x1 identity slab).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "conv_common.cuh"
 #include "tc_primitives.cuh"
@@ -32,6 +33,7 @@ namespace nic {
 
 using namespace tc;
 
+void set_trace_buffer(void* p);
 // conv_simt.cu
 int conv_fwd_fp32_ex(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y, int out_bf16_nhwc,
                      cudaStream_t st);
@@ -77,6 +79,8 @@ struct TcParams {
   int shuffle_cout;                            // > 0: sub-pixel (2x2) output: column n = (py * 2 + px) * shuffle_cout + c goes to
                                                //      pixel (2 oy + py, 2 ox + px), channel c of an fp32 tensor (ConvTranspose2d to RGB)
   int bias_mod;                                // bias index = column % bias_mod (shuffle) ; 0 = plain
+  int dbg;                                     // NIC_TC_DEBUG bits (timing experiments only): 1 skip gamma MMA, 2 skip tensor store
+  long long* dbg_times;                        // NIC_TC_TRACE: [cta][16 tiles][8] clock64 stamps of the pipeline roles (null = off)
   const float* bias;
   const float* beta;
   void* y;
@@ -100,6 +104,10 @@ __device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, Tc
   sb->abort_flag = 1;
   atomicExch(status, 1);
   return false;
+}
+
+__device__ __forceinline__ void trace(const TcParams& p, uint32_t tile_iter, int slot) {
+  if (p.dbg_times && tile_iter < 16) p.dbg_times[(static_cast<long>(blockIdx.x) * 16 + tile_iter) * 8 + slot] = clock64();
 }
 
 __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& ntile, int& phase, int& img, int& ty, int& tx) {
@@ -221,7 +229,7 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
     fence_proxy_async_smem();
     tcgen05_fence_before();
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (leader) {
+    if (leader && !(p.dbg & 1)) {
       if (gdn_count == 0) wait_or_abort(&sb->gamma_full, 0, sb, p.status);
       tcgen05_fence_after();
       const uint32_t idg = umma_idesc_bf16(128, 128);
@@ -232,8 +240,10 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
                   umma_desc_sw128(g_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024), idg, k > 0);
       umma_commit(&sb->gdn_full);
     }
-    if (!__all_sync(0xffffffffu, wait_or_abort(&sb->gdn_full, gdn_count & 1, sb, p.status))) return false;
-    ++gdn_count;
+    if (!(p.dbg & 1)) {
+      if (!__all_sync(0xffffffffu, wait_or_abort(&sb->gdn_full, gdn_count & 1, sb, p.status))) return false;
+      ++gdn_count;
+    }
     tcgen05_fence_after();
   }
   const int nvalid_c = p.cout - cbase;                      // channels of this N tile that exist
@@ -295,7 +305,7 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
   if (p.tma_out) {
     fence_proxy_async_smem();
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (leader) {
+    if (leader && !(p.dbg & 2)) {
       const int wc = ox0 * p.out_stride + px, hc = oy0 * p.out_stride + py;
       for (int h = 0; h < 2; ++h)
         if (h * 64 < nvalid_c) tma_store_4d(map_o_ptr, sq + h * (128 * 128), p.out_c_offset + cbase + h * 64, wc, hc, img);
@@ -357,6 +367,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int pl = 0; pl < ph.nplanes; ++pl, ++it) {
             const int s = it % p.nsa;
             if (!wait_or_abort(&sb.a_empty[s], ((it / p.nsa) & 1) ^ 1, &sb, p.status)) { ok = false; break; }
+            if (chunk == 0 && pl == 0) trace(p, (tile - first_tile) / tile_step, 5);
+            if (chunk == p.nchunks - 1 && pl == ph.nplanes - 1) trace(p, (tile - first_tile) / tile_step, 6);
             mbar_expect_tx(&sb.a_full[s], bytes);
             const int w0 = p.in_stride * (tx * p.tile_w + ph.plane_dxmin[pl]) + ph.plane_pw[pl];
             const int h0 = p.in_stride * (ty * p.tile_h + ph.plane_dymin[pl]) + ph.plane_ph[pl];
@@ -401,13 +413,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 2) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop (so every address below is warp-uniform and lives in uniform registers); only the
+    // tcgen05 instructions themselves are issued by one elected lane.  Per-MMA issue cost must stay under the 64 clk an
+    // M128 N128 K16 MMA occupies the tensor pipe.
+    {
       const uint32_t idesc = umma_idesc_bf16(128, p.nb);
       const uint32_t a_base = smem_u32(smem + p.off_a), b_base = smem_u32(smem + p.off_b);
       const uint32_t a_hi = umma_desc_hi(p.pw_cols * 128), b_hi = umma_desc_hi(1024);
       const uint32_t bbytes = p.nb * 128;
       const int nsa = p.nsa, nsb = p.nsb, nchunks = p.nchunks, b_res = p.b_resident;
-      uint32_t ita = 0, itb = 0, tcount = 0;
+      const uint32_t blk1_off = static_cast<uint32_t>((p.blk_roff[1] * p.pw_cols + p.blk_coff[1]) * 128) >> 4;
+      uint32_t tcount = 0;
       uint32_t sa = 0, pa = 0, sbi = 0, pb = 0;      // ring slot + phase parity of the A and B rings
       bool ok = true;
       if (b_res) { ok = wait_or_abort(&sb.bres_full, 0, &sb, p.status); tcgen05_fence_after(); }
@@ -419,49 +435,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int nplanes = ph.nplanes;
         const uint32_t buf = tcount & 1;
         if (!wait_or_abort(&sb.acc_empty[buf], ((tcount >> 1) & 1) ^ 1, &sb, p.status)) break;
+        if (lane == 0) trace(p, tcount, 0);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem + buf * 256;
         uint32_t accumulate = 0;
         for (int chunk = 0; chunk < nchunks && ok; ++chunk) {
           for (int pl = 0; pl < nplanes && ok; ++pl) {
             if (!mbar_try_wait(&sb.a_full[sa], pa) && !wait_or_abort(&sb.a_full[sa], pa, &sb, p.status)) { ok = false; break; }
+            if (chunk == 0 && pl == 0 && lane == 0) trace(p, tcount, 1);
             tcgen05_fence_after();
             const uint32_t a_slot_lo = umma_desc_lo(a_base + sa * p.slot_bytes);
             const int t_end = ph.plane_tap_begin[pl + 1];
             for (int t = ph.plane_tap_begin[pl]; t < t_end; ++t) {
               uint32_t b_lo;
               if (b_res) {
-                b_lo = umma_desc_lo(b_base + (s_tap_brow[t] * nchunks + chunk) * bbytes);
+                b_lo = umma_desc_lo(b_base + (p.taps[t].slab * nchunks + chunk) * bbytes);
               } else {
                 if (!mbar_try_wait(&sb.b_full[sbi], pb) && !wait_or_abort(&sb.b_full[sbi], pb, &sb, p.status)) { ok = false; break; }
                 tcgen05_fence_after();
                 b_lo = umma_desc_lo(b_base + sbi * (128 * 128));
               }
-              const uint32_t a_lo0 = a_slot_lo + s_tap_aoff[t][0];
-              umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo, b_hi, idesc, accumulate);
-              umma_bf16_lohi(d_tmem, a_lo0 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
-              umma_bf16_lohi(d_tmem, a_lo0 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
-              umma_bf16_lohi(d_tmem, a_lo0 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
-              if (nblk > 1) {
-                const uint32_t a_lo1 = a_slot_lo + s_tap_aoff[t][1];
-                umma_bf16_lohi(d_tmem + 128, a_lo1, a_hi, b_lo, b_hi, idesc, accumulate);
-                umma_bf16_lohi(d_tmem + 128, a_lo1 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
-                umma_bf16_lohi(d_tmem + 128, a_lo1 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
-                umma_bf16_lohi(d_tmem + 128, a_lo1 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+              const uint32_t a_lo0 = a_slot_lo + (static_cast<uint32_t>((p.taps[t].roff * p.pw_cols + p.taps[t].coff) * 128) >> 4);
+              if (elect_one()) {
+                umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo, b_hi, idesc, accumulate);
+                umma_bf16_lohi(d_tmem, a_lo0 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
+                umma_bf16_lohi(d_tmem, a_lo0 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
+                umma_bf16_lohi(d_tmem, a_lo0 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+                if (nblk > 1) {
+                  const uint32_t a_lo1 = a_lo0 + blk1_off;
+                  umma_bf16_lohi(d_tmem + 128, a_lo1, a_hi, b_lo, b_hi, idesc, accumulate);
+                  umma_bf16_lohi(d_tmem + 128, a_lo1 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
+                  umma_bf16_lohi(d_tmem + 128, a_lo1 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
+                  umma_bf16_lohi(d_tmem + 128, a_lo1 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+                }
+                if (!b_res) umma_commit(&sb.b_empty[sbi]);
               }
+              __syncwarp();
               accumulate = 1;
-              if (!b_res) {
-                umma_commit(&sb.b_empty[sbi]);
-                if (++sbi == static_cast<uint32_t>(nsb)) { sbi = 0; pb ^= 1; }
-              }
+              if (!b_res) { if (++sbi == static_cast<uint32_t>(nsb)) { sbi = 0; pb ^= 1; } }
             }
-            umma_commit(&sb.a_empty[sa]);
+            if (elect_one()) umma_commit(&sb.a_empty[sa]);
+            __syncwarp();
             if (++sa == static_cast<uint32_t>(nsa)) { sa = 0; pa ^= 1; }
           }
         }
-        umma_commit(&sb.acc_full[buf]);
+        if (lane == 0) trace(p, tcount, 2);
+        if (elect_one()) umma_commit(&sb.acc_full[buf]);
+        __syncwarp();
       }
-      (void)ita; (void)itb;
     }
   } else {
     // ===================== epilogue (warps 3..6) =====================
@@ -485,6 +506,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int b = 0; b < nblk && ok; ++b)
         ok = epilogue_block(p, &sb, s_bias, s_beta, sq, smem + p.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane, warp == 3 && lane == 0,
                             img, ty * p.tile_h + p.blk_roff[b], tx * p.tile_w + p.blk_coff[b], ph.py, ph.px, ntile * p.nb, gdn_count);
+      if (warp == 3 && lane == 0) trace(p, tcount, 4);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb.acc_empty[buf]);
@@ -687,6 +709,8 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+void* g_trace_buffer = nullptr;   // set through nic_debug_set_trace (timing experiments; not part of the product ABI surface)
+
 int* status_word() {       // one device int per process: the kernels' "a bounded wait expired" flag
   static int* d = nullptr;
   if (!d) { if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return nullptr; cudaMemset(d, 0, sizeof(int)); }
@@ -840,6 +864,8 @@ inline bool small_cin(const nic_conv_desc* d) { return d->c_in < 64; }
 
 }  // namespace
 
+void set_trace_buffer(void* p) { g_trace_buffer = p; }
+
 // Packed layout (bf16 elements):
 //   c_in >= 64 : [tap][c_out padded to a multiple of nb][c_in]
 //   c_in  = 3  : [c_out = 128][k padded to 128], k = (kh * kw_size + kw) * 3 + c   (first layer, conv_first_tc_kernel)
@@ -927,6 +953,8 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   }
   p.status = status_word();
   if (!p.status) return fail(NIC_E_CUDA, "conv bf16: cannot allocate the status word");
+  { const char* e = getenv("NIC_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+  p.dbg_times = reinterpret_cast<long long*>(g_trace_buffer);
 
   // geometry of the pixel grid the tiles walk
   int gn = d->n, gh = d->h_in, gw = d->w_in;
@@ -1017,6 +1045,7 @@ static int launch_first(const nic_conv_desc* d, const void* x, const void* w_pac
   p.ys_n = static_cast<long>(d->h_out) * d->w_out * 128; p.ys_h = static_cast<long>(d->w_out) * 128; p.ys_w = 128; p.ys_c = 1;
   p.status = status_word();
   if (!p.status) return fail(NIC_E_CUDA, "conv bf16: cannot allocate the status word");
+  { const char* e = getenv("NIC_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   FirstParams f{};
   f.x = static_cast<const float*>(x); f.n = d->n; f.hin = d->h_in; f.win = d->w_in;
   f.tiles_x = (d->w_out + 15) / 16; f.tiles_y = (d->h_out + 15) / 16; f.total_tiles = f.tiles_x * f.tiles_y * d->n;
@@ -1055,3 +1084,7 @@ int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, con
 }
 
 }  // namespace nic
+
+// Debug hook for tools/trace_layer.py (not declared in include/nic.h): a device buffer of 148 * 16 * 8 int64 that
+// conv_tc_kernel fills with clock64 stamps of its pipeline roles; NULL switches tracing off.
+extern "C" void nic_debug_set_trace(void* device_buffer) { nic::set_trace_buffer(device_buffer); }

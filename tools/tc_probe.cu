@@ -398,6 +398,70 @@ static void run_mma_rate() {
   cudaFree(dc); cudaFree(ds);
 }
 
+// -------------------------------------------------------------------------------------------------
+// T7: latency and throughput of the 4-D NHWC patch loads the conv kernel issues (box = 64 ch x PW px x PH rows)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tma_patch_kernel(const __grid_constant__ CUtensorMap map, int pw, int ph, int stride, int iters, int depth,
+                                                        int H, int W, int N, long long* lat, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bars[4];
+  if (threadIdx.x == 0) { for (int s = 0; s < 4; ++s) mbar_init(&bars[s], 1); fence_barrier_init(); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = pw * ph * 128;
+    const uint32_t slot = (bytes + 1023) / 1024 * 1024;
+    const int tiles_x = W / (16 * stride), tiles_y = H / (16 * stride);
+    int t = blockIdx.x * 7;
+    long long t0 = clock64();
+    for (int i = 0; i < iters + depth; ++i) {
+      const int s = i % depth;
+      if (i >= depth) {
+        if (!mbar_wait(&bars[s], ((i / depth) - 1) & 1, 1u << 24)) { *status = 1; break; }
+        if (i == depth && blockIdx.x == 0) lat[0] = clock64() - t0;      // completion of the first load(s)
+      }
+      if (i < iters) {
+        const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = (t / (tiles_x * tiles_y)) % N, c = (t / (tiles_x * tiles_y * N)) & 1;
+        mbar_expect_tx(&bars[s], bytes);
+        tma_load_4d(smem + s * slot, &map, &bars[s], c * 64, stride * (tx * 16 - 1), stride * (ty * 16 - 1), n);
+        t += 1;
+      }
+    }
+    if (blockIdx.x == 0) lat[1] = clock64() - t0;
+  }
+}
+
+static void run_tma_patch(EncodeTiledFn enc, int pw, int ph, int stride, int depth) {
+  const int N = 4, H = 256, W = 384, C = 128;
+  const size_t elems = (size_t)N * H * W * C;
+  __nv_bfloat16* d; CK(cudaMalloc(&d, elems * 2)); CK(cudaMemset(d, 0, elems * 2));
+  CUtensorMap map;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(pw * stride), (cuuint32_t)(ph * stride), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { printf("encode patch failed %d\n", (int)r); return; }
+  long long* dl; int* ds; CK(cudaMalloc(&dl, 16)); CK(cudaMalloc(&ds, 4)); CK(cudaMemset(ds, 0, 4));
+  const int slot = (pw * ph * 128 + 1023) / 1024 * 1024;
+  const int smem = depth * slot + 1024;
+  CK(cudaFuncSetAttribute(tma_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int iters = 400;
+  tma_patch_kernel<<<148, 128, smem>>>(map, pw, ph, stride, 50, depth, H, W, N, dl, ds);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  tma_patch_kernel<<<148, 128, smem>>>(map, pw, ph, stride, iters, depth, H, W, N, dl, ds);
+  CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  long long l[2]; int st; CK(cudaMemcpy(l, dl, 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, ds, 4, cudaMemcpyDeviceToHost));
+  const double bytes = 148.0 * iters * pw * ph * 128;
+  printf("  patch %2dx%2d px x 64ch (%5.1f KB) stride %d, %d in flight: %.0f GB/s total, %.1f us per load per SM, first completion %lld clk (status %d)\n",
+         pw, ph, pw * ph * 128 / 1024.0, stride, depth, bytes / ms / 1e6, ms * 1e3 / iters, l[0], st);
+  cudaFree(d); cudaFree(dl); cudaFree(ds);
+}
+
 int main(int argc, char** argv) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s sm_%d%d, %d SMs, smem/block optin %zu\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount, prop.sharedMemPerBlockOptin);
@@ -429,6 +493,14 @@ int main(int argc, char** argv) {
   int ok4s = run_tma_mma(enc, 2);
   printf("T6 back-to-back SS-mode MMA rate (one issuing thread, operands resident in shared memory)\n");
   run_mma_rate();
+  printf("T7 4-D NHWC patch loads (tensor 4 x 256 x 384 x 128 bf16 = 100 MB, L2 resident after warm-up)\n");
+  for (int depth : {1, 2, 4}) {
+    run_tma_patch(enc, 18, 18, 1, depth);
+    run_tma_patch(enc, 18, 18, 2, depth);
+  }
+  run_tma_patch(enc, 10, 18, 1, 4);
+  run_tma_patch(enc, 10, 18, 2, 4);
+  run_tma_patch(enc, 8, 16, 1, 4);
   printf("T5 L2 -> smem bandwidth\n");
   run_tma_bw(enc, 128, 64);
   run_tma_bw(enc, 256, 64);

@@ -1,0 +1,46 @@
+"""Pipeline trace of conv_tc_kernel for one layer (GPU box):  python tools/trace_layer.py k2|d2|d3|k3|ep3"""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch, torch.nn as nn
+from neural_image_compression_b200 import engine, _lib
+from neural_image_compression_b200._lib import EPI_BIAS, EPI_GDN, EPI_IGDN, EPI_LRELU, LAYOUT_NCHW, LAYOUT_NHWC
+from neural_image_compression_b200.gdn import GDN
+
+which = sys.argv[1] if len(sys.argv) > 1 else "k2"
+B = 16
+dev = torch.device("cuda:0")
+cfg = {
+    "k2": (nn.Conv2d(128, 128, 5, 2, 2), EPI_GDN, (256, 384), {}),
+    "k3": (nn.Conv2d(128, 128, 5, 2, 2), EPI_GDN, (128, 192), {}),
+    "d2": (nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1), EPI_IGDN, (128, 192), {}),
+    "d3": (nn.ConvTranspose2d(128, 3, 5, 2, 2, output_padding=1), EPI_BIAS, (256, 384), dict(out_layout=LAYOUT_NCHW, out_dtype=torch.float32)),
+    "ep3": (nn.Conv2d(640, 1152, 1), EPI_BIAS, (32, 48), dict(out_layout=LAYOUT_NCHW, out_dtype=torch.float32)),
+}[which]
+conv, epi, (h, w), kw = cfg
+conv = conv.to(dev)
+g = GDN(128, inverse=(epi == EPI_IGDN)).to(dev) if epi in (EPI_GDN, EPI_IGDN) else None
+op = engine.ConvOp(conv, epi, gdn=g)
+x = torch.randn(B, h, w, conv.in_channels, device=dev).to(torch.bfloat16)
+lib = _lib.load()
+lib.nic_debug_set_trace.argtypes = [C.c_void_p]; lib.nic_debug_set_trace.restype = None
+for _ in range(3):
+    op.run(x, B, h, w, "bf16", **kw)
+torch.cuda.synchronize()
+buf = torch.zeros(148 * 16 * 8, dtype=torch.int64, device=dev)
+lib.nic_debug_set_trace(buf.data_ptr())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); op.run(x, B, h, w, "bf16", **kw); e1.record()
+torch.cuda.synchronize()
+lib.nic_debug_set_trace(None)
+t = buf.cpu().reshape(148, 16, 8)
+print(f"{which}: {e0.elapsed_time(e1)*1000:.1f} us")
+names = ["mma:acc_empty", "mma:first_a", "mma:issued", "epi:acc_full", "epi:done", "A:first_issue", "A:last_issue"]
+for cta in (0, 77):
+    base = int(t[cta, 0][t[cta, 0] > 0].min())
+    print(f"CTA {cta} (clk relative to its first stamp)")
+    for i in range(10):
+        row = t[cta, i]
+        if int(row[0]) == 0:
+            break
+        print("  tile %2d: " % i + "  ".join(f"{n}={int(row[j]) - base:7d}" for j, n in enumerate(names)))
