@@ -219,6 +219,13 @@ int nic_rd_finalize(const float* logp_y_partials, const float* logp_z_partials,
                     const float* sse_partials, int32_t b, int32_t num_pixels, int64_t chw,
                     float lambda_rd, float* per_image, float* scalars, void* stream);
 
+/*
+ * The same terms from already-reduced per-image rows (data-parallel evaluation: every rank all-gathers the
+ * [3][b_local] rows of nic_rd_finalize and folds the global [3][b] array here, in the same fixed order on every rank).
+ *   per_image [3][b]: bits_y, bits_z, mse_per_image   ->   scalars [8] as in nic_rd_finalize
+ */
+int nic_rd_reduce(const float* per_image, int32_t b, int32_t num_pixels, float lambda_rd, float* scalars, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

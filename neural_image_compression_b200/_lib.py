@@ -50,6 +50,7 @@ SIGNATURES = {
     "nic_factorized_likelihood_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "nic_sse_fwd": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "nic_sum_fwd": (C.c_int, [_vp, _i32, _i64, _vp, _vp]),
+    "nic_rd_reduce": (C.c_int, [_vp, _i32, _i32, _f32, _vp, _vp]),
     "nic_rd_finalize": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _f32, _vp, _vp, _vp]),
 }
 

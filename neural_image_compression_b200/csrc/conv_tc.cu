@@ -43,7 +43,8 @@ namespace {
 constexpr int kTileH = 16, kTileW = 8;          // output pixels per M = 128 block: 16 groups of 8
 constexpr int kMaxSlots = 4;
 constexpr int kMaxBSlots = 8;
-constexpr int kThreads = 224;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 96 + kEpiWarps * 32;
 constexpr int kMaxDynSmem = 232448 - 8192;    // 227 KB opt-in limit minus this kernel's static shared memory
 constexpr int kMaxCout = 1280;                // bias table staged in shared memory
 
@@ -177,18 +178,28 @@ __device__ __forceinline__ void store_subpixel(const TcParams& p, float* yb, con
     }
 }
 
-// Epilogue of one M = 128 accumulator block (4 warps = 128 threads, thread <-> accumulator row <-> pixel): bias, LeakyReLU or
-// the fused GDN / IGDN, then the store (TMA tensor store of a bf16 NHWC tile staged in shared memory, or direct stores).
-// Returns false when a bounded wait expired.
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Epilogue of one M = 128 accumulator block: bias, LeakyReLU or the fused GDN / IGDN, then the store (TMA tensor store of a
+// bf16 NHWC tile staged in shared memory, or direct stores).  NW = 4 or 8 epilogue warps; thread <-> accumulator row <->
+// pixel; with 8 warps the second warpgroup (hs = 1) takes channels 64..127 of the same rows, i.e. the other 64-channel half
+// of the squares / staging tile.  Returns false when a bounded wait expired.
+template <int NW>
 __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb, const float* s_bias, const float* s_beta, uint8_t* sq,
                                                const uint8_t* gamma_smem, const CUtensorMap* map_o_ptr, uint32_t acc_tmem, int q, int lane,
-                                               bool leader, int img, int oy0, int ox0, int py, int px, int cbase, uint32_t& gdn_count) {
+                                               int hs, bool leader, int img, int oy0, int ox0, int py, int px, int cbase, uint32_t& gdn_count) {
+  constexpr int NG = (NW == 8) ? 2 : 4;                     // 32-channel groups per thread in the 128-wide paths
   const bool gdn = p.epilogue == NIC_EPI_GDN || p.epilogue == NIC_EPI_IGDN;
   const bool igdn = p.epilogue == NIC_EPI_IGDN;
   const int ncg = (p.nb + 31) / 32;
+  const int cg0 = (NW == 8) ? hs * 2 : 0;                   // first channel group of this thread
   const int row = q * 32 + lane, g = row >> 3, c8 = row & 7;
   const uint32_t acc_addr = acc_tmem + (static_cast<uint32_t>(q * 32) << 16);
-    const int oy = oy0 + g, ox = ox0 + c8;
+  const int oy = oy0 + g, ox = ox0 + c8;
   const int out_y = oy * p.out_stride + py, out_x = ox * p.out_stride + px;
   const bool valid = oy < p.hp && ox < p.wp && out_y < p.hout && out_x < p.wout;
   long obase;
@@ -198,18 +209,23 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
   } else {
     obase = img * p.ys_n + static_cast<long>(out_y) * p.ys_h + static_cast<long>(out_x) * p.ys_w;
   }
+  auto epi_sync = [&]() {
+    if (NW == 8) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else asm volatile("bar.sync 1, 128;" ::: "memory");
+  };
   if (p.tma_out) {
     // the staging tile (= the squares tile) may still be read by the previous block's tensor store
     if (leader) tma_store_wait_read();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    epi_sync();
   }
-  float xr[128];
+  float xr[NG * 32];
   if (gdn) {
     // x (+ bias) stays in registers; its squares go to shared memory as the bf16 K-major A operand of the
     // gamma contraction, whose result OVERWRITES this accumulator (no extra TMEM); then y = x * rsqrt(beta + .)
 #pragma unroll
-    for (int cg = 0; cg < 4; ++cg) {
-      tmem_ld_32x32(acc_addr + cg * 32, xr + cg * 32);
+    for (int i = 0; i < NG; ++i) {
+      const int cg = cg0 + i;
+      tmem_ld_32x32(acc_addr + cg * 32, xr + i * 32);
       tmem_ld_wait();
       uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
 #pragma unroll
@@ -217,9 +233,9 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int c0 = cg * 32 + j * 8 + e * 2;
-          const float a = xr[c0] + s_bias[c0], bb = xr[c0 + 1] + s_bias[c0 + 1];
-          xr[c0] = a; xr[c0 + 1] = bb;
+          const int l = i * 32 + j * 8 + e * 2, c0 = cg * 32 + j * 8 + e * 2;
+          const float a = xr[l] + s_bias[c0], bb = xr[l + 1] + s_bias[c0 + 1];
+          xr[l] = a; xr[l + 1] = bb;
           w[e] = pack_bf16x2(a * a, bb * bb);
         }
         const int chunk = ((cg & 1) * 4 + j) ^ (row & 7);
@@ -228,22 +244,24 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
     }
     fence_proxy_async_smem();
     tcgen05_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    epi_sync();
     if (leader && !(p.dbg & 1)) {
       if (gdn_count == 0) wait_or_abort(&sb->gamma_full, 0, sb, p.status);
       tcgen05_fence_after();
       const uint32_t idg = umma_idesc_bf16(128, 128);
-      const uint32_t sq_base = smem_u32(sq), g_base = smem_u32(gamma_smem);
+      const uint32_t hi = umma_desc_hi(1024);
+      const uint32_t sq_lo = umma_desc_lo(smem_u32(sq)), g_lo = umma_desc_lo(smem_u32(gamma_smem));
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_bf16(acc_tmem, umma_desc_sw128(sq_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024),
-                  umma_desc_sw128(g_base + (k >> 2) * (128 * 128) + (k & 3) * 32, 1024), idg, k > 0);
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t off = ((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4;
+        umma_bf16_lohi(acc_tmem, sq_lo + off, hi, g_lo + off, hi, idg, k);
+      }
       umma_commit(&sb->gdn_full);
     }
     if (!(p.dbg & 1)) {
       if (!__all_sync(0xffffffffu, wait_or_abort(&sb->gdn_full, gdn_count & 1, sb, p.status))) return false;
-      ++gdn_count;
     }
+    ++gdn_count;
     tcgen05_fence_after();
   }
   const int nvalid_c = p.cout - cbase;                      // channels of this N tile that exist
@@ -274,21 +292,26 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
   };
   if (gdn) {
 #pragma unroll
-    for (int cg = 0; cg < 4; ++cg) {
+    for (int i = 0; i < NG; ++i) {
+      const int cg = cg0 + i;
       float v[32];
       tmem_ld_32x32(acc_addr + cg * 32, v);
       tmem_ld_wait();
       if (igdn) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = xr[cg * 32 + j] * sqrt_approx(v[j] + s_beta[cg * 32 + j]);
+        for (int j = 0; j < 32; ++j) v[j] = xr[i * 32 + j] * sqrt_approx(v[j] + s_beta[cg * 32 + j]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = xr[cg * 32 + j] * rsqrtf(v[j] + s_beta[cg * 32 + j]);
+        for (int j = 0; j < 32; ++j) v[j] = xr[i * 32 + j] * rsqrt_approx(v[j] + s_beta[cg * 32 + j]);
       }
       emit_group(cg, v);
     }
   } else {
-    for (int cg = 0; cg < ncg; ++cg) {
+    // channel groups of this warpgroup: with 8 warps the second one takes the upper half of the groups
+    const int per = (NW == 8) ? (ncg + 1) / 2 : ncg;
+    const int first = (NW == 8) ? hs * per : 0;
+    const int last = (first + per < ncg) ? first + per : ncg;
+    for (int cg = first; cg < last; ++cg) {
       float v[32];
       tmem_ld_32x32(acc_addr + cg * 32, v);
       tmem_ld_wait();
@@ -304,7 +327,7 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
   }
   if (p.tma_out) {
     fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    epi_sync();
     if (leader && !(p.dbg & 2)) {
       const int wc = ox0 * p.out_stride + px, hc = oy0 * p.out_stride + py;
       for (int h = 0; h < 2; ++h)
@@ -339,7 +362,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sb.a_full[i], 1); mbar_init(&sb.a_empty[i], 1); }
     for (int i = 0; i < kMaxBSlots; ++i) { mbar_init(&sb.b_full[i], 1); mbar_init(&sb.b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], kEpiWarps); }
     mbar_init(&sb.gdn_full, 1); mbar_init(&sb.gamma_full, 1); mbar_init(&sb.bres_full, 1);
     sb.abort_flag = 0;
     fence_barrier_init();
@@ -485,7 +508,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 3..6) =====================
+    // ===================== epilogue (warps 3..10) =====================
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;                // accumulator row = pixel of the block
     const int g = row >> 3, c8 = row & 7;
@@ -504,8 +527,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tcgen05_fence_after();
       const int cbase = ntile * p.nb;
       for (int b = 0; b < nblk && ok; ++b)
-        ok = epilogue_block(p, &sb, s_bias, s_beta, sq, smem + p.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane, warp == 3 && lane == 0,
-                            img, ty * p.tile_h + p.blk_roff[b], tx * p.tile_w + p.blk_coff[b], ph.py, ph.px, ntile * p.nb, gdn_count);
+        ok = epilogue_block<kEpiWarps>(p, &sb, s_bias, s_beta, sq, smem + p.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane,
+                                       (warp - 3) >> 2, warp == 3 && lane == 0, img, ty * p.tile_h + p.blk_roff[b],
+                                       tx * p.tile_w + p.blk_coff[b], ph.py, ph.px, ntile * p.nb, gdn_count);
       if (warp == 3 && lane == 0) trace(p, tcount, 4);
       tcgen05_fence_before();
       __syncwarp();
@@ -677,8 +701,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       tcgen05_fence_after();
       for (int b = 0; b < 2 && ok; ++b) {
         if (tx * 16 + b * 8 >= p.wp) break;
-        ok = epilogue_block(p, &sb, s_bias, s_beta, sq, smem + f.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane, warp == 5 && lane == 0,
-                            img, ty * 16, tx * 16 + b * 8, 0, 0, 0, gdn_count);
+        ok = epilogue_block<4>(p, &sb, s_bias, s_beta, sq, smem + f.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane, 0,
+                               warp == 5 && lane == 0, img, ty * 16, tx * 16 + b * 8, 0, 0, 0, gdn_count);
       }
       tcgen05_fence_before();
       __syncwarp();
