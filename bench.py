@@ -107,7 +107,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("NIC_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("NIC_PRECISION", "bf16"),
+                    help="bf16 = tcgen05 tensor-core arm (headline); fp32 = CUDA-core parity arm")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
