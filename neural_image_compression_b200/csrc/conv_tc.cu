@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a shared-space pointer
   __shared__ TcBarriers sb;
   __shared__ float s_bias[kMaxCout];
   __shared__ float s_beta[128];
@@ -550,7 +550,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // issues 5 tcgen05.mma per block against the resident [128 x 80] weights, and the shared epilogue applies the fused GDN and
 // stores the bf16 NHWC tile with TMA.  9 warps: 0-3 producers, 4 MMA issuer / weight loader, 5-8 epilogue.
 // ---------------------------------------------------------------------------------------------
-constexpr int kFirstThreads = 288;
+constexpr int kFirstThreads = 160 + kEpiWarps * 32;
 constexpr int kPatchW = 36, kPatchH = 35, kPatchPlane = kPatchH * kPatchW;     // fp32 patch rows padded to 36 floats
 
 struct FirstParams {
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1)
 conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_g,
                      const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p, const __grid_constant__ FirstParams f) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a shared-space pointer
   __shared__ FirstBarriers fb;
   __shared__ float s_bias[128];
   __shared__ float s_beta[128];
@@ -577,7 +577,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   if (tid < 128) { s_bias[tid] = p.bias[tid]; s_beta[tid] = p.beta[tid]; }
   if (tid == 0) {
     mbar_init(&fb.a_full, 128); mbar_init(&fb.a_empty, 1); mbar_init(&fb.w_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], kEpiWarps); }
     mbar_init(&sb.gdn_full, 1); mbar_init(&sb.gamma_full, 1);
     sb.abort_flag = 0;
     fence_barrier_init();
@@ -596,43 +596,45 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 
   if (warp < 4) {
     // ===================== producers: image patch -> bf16 im2col A operand =====================
-    constexpr int kPerThread = (3 * kPatchH * kPatchH + 127) / 128;     // 29
-    float pre[kPerThread];
-    auto prefetch = [&](int tile) {
+    // The fp32 patch of tile i+1 streams into the other half of a double buffer with cp.async (zero fill = conv padding)
+    // while tile i is expanded; warp w copies patch rows w, w+4, ... (coalesced 128 B per row).
+    auto fetch_patch = [&](int tile, int bufi) {
       int img, ty, tx;
       tile_coords(tile, img, ty, tx);
       const int y0 = 2 * (ty * 16) - 2, x0 = 2 * (tx * 16) - 2;
       const float* base = f.x + static_cast<long>(img) * 3 * f.hin * f.win;
+      const uint32_t dst0 = smem_u32(patch + bufi * (3 * kPatchPlane));
+      for (int r = warp; r < 3 * kPatchH; r += 4) {
+        const int c = r / kPatchH, yy = r - c * kPatchH;
+        const int gy = y0 + yy;
+        const bool row_ok = gy >= 0 && gy < f.hin;
+        const float* srow = base + (static_cast<long>(c) * f.hin + (row_ok ? gy : 0)) * f.win;
 #pragma unroll
-      for (int j = 0; j < kPerThread; ++j) {
-        const int e = tid + 128 * j;
-        float v = 0.f;
-        if (e < 3 * kPatchH * kPatchH) {
-          const int c = e / (kPatchH * kPatchH), rem = e - c * (kPatchH * kPatchH);
-          const int yy = y0 + rem / kPatchH, xx = x0 + rem % kPatchH;
-          if (yy >= 0 && yy < f.hin && xx >= 0 && xx < f.win) v = __ldg(base + (static_cast<long>(c) * f.hin + yy) * f.win + xx);
+        for (int h = 0; h < 2; ++h) {
+          const int xx = lane + 32 * h;
+          if (xx < kPatchH) {
+            const int gx = x0 + xx;
+            const bool ok = row_ok && gx >= 0 && gx < f.win;
+            const uint32_t dst = dst0 + (c * kPatchPlane + yy * kPatchW + xx) * 4;
+            const float* src = srow + (ok ? gx : 0);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
+          }
         }
-        pre[j] = v;
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (first_tile < f.total_tiles) prefetch(first_tile);
+    if (first_tile < f.total_tiles) fetch_patch(first_tile, 0);
     uint32_t it = 0;
     const int r = tid, g = r >> 3, c8 = r & 7;
     for (int tile = first_tile; tile < f.total_tiles; tile += tile_step, ++it) {
-#pragma unroll
-      for (int j = 0; j < kPerThread; ++j) {
-        const int e = tid + 128 * j;
-        if (e < 3 * kPatchH * kPatchH) {
-          const int c = e / (kPatchH * kPatchH), rem = e - c * (kPatchH * kPatchH);
-          patch[c * kPatchPlane + (rem / kPatchH) * kPatchW + rem % kPatchH] = pre[j];
-        }
-      }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (tile + tile_step < f.total_tiles) prefetch(tile + tile_step);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 2, 128;" ::: "memory");         // patch(it) visible to all producers; patch(it-1) no longer read
+      if (tile + tile_step < f.total_tiles) fetch_patch(tile + tile_step, (it + 1) & 1);
       if (!__all_sync(0xffffffffu, wait_or_abort(&fb.a_empty, (it & 1) ^ 1, &sb, p.status))) break;
+      const float* pbuf = patch + (it & 1) * (3 * kPatchPlane);
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
-        const float* src = patch + (2 * g) * kPatchW + 2 * (b * 8 + c8);
+        const float* src = pbuf + (2 * g) * kPatchW + 2 * (b * 8 + c8);
         uint8_t* dst = smem + f.off_a + b * (2 * 128 * 128) + r * 128;
 #pragma unroll
         for (int ch = 0; ch < 10; ++ch) {
@@ -653,8 +655,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       }
       fence_proxy_async_smem();
       mbar_arrive(&fb.a_full);
-      asm volatile("bar.sync 2, 128;" ::: "memory");       // everyone is done reading the patch before it is overwritten
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == 4) {
     // ===================== weight loader + MMA issuer =====================
     if (lane == 0) {
@@ -688,7 +690,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       }
     }
   } else {
-    // ===================== epilogue (warps 5..8) =====================
+    // ===================== epilogue (warps 5..12) =====================
     const int q = warp & 3;
     uint8_t* sq = smem + f.off_sq;
     uint32_t it = 0, gdn_count = 0;
@@ -701,8 +703,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       tcgen05_fence_after();
       for (int b = 0; b < 2 && ok; ++b) {
         if (tx * 16 + b * 8 >= p.wp) break;
-        ok = epilogue_block<4>(p, &sb, s_bias, s_beta, sq, smem + f.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane, 0,
-                               warp == 5 && lane == 0, img, ty * 16, tx * 16 + b * 8, 0, 0, 0, gdn_count);
+        ok = epilogue_block<kEpiWarps>(p, &sb, s_bias, s_beta, sq, smem + f.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane,
+                                       (warp - 5) >> 2, warp == 5 && lane == 0, img, ty * 16, tx * 16 + b * 8, 0, 0, 0, gdn_count);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -995,6 +997,12 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   // two M = 128 blocks per tile share every weight slab (halves the L2 -> shared-memory weight traffic, which is
   // what bounds M = 128 tiles: profiles/README.md); side by side for images, stacked for the flat 1x1 case
   p.mt = (flat ? p.hp > kTileH : p.wp > kTileW) ? 2 : 1;
+  {
+    // small layers: one block per tile when two-block tiles would leave SMs idle (fewer than two tiles per SM)
+    const long tiles2 = static_cast<long>((p.wp + (flat ? kTileW : 2 * kTileW) - 1) / (flat ? kTileW : 2 * kTileW)) *
+                        ((p.hp + (flat ? 2 * kTileH : kTileH) - 1) / (flat ? 2 * kTileH : kTileH)) * p.n * tt.nphases * p.n_ntiles;
+    if (tiles2 < 2 * kNumSMs) p.mt = 1;
+  }
   p.blk_roff[0] = p.blk_coff[0] = 0;
   p.blk_roff[1] = flat ? kTileH : 0; p.blk_coff[1] = flat ? 0 : kTileW;
   p.tile_h = flat ? kTileH * p.mt : kTileH; p.tile_w = flat ? kTileW : kTileW * p.mt;
@@ -1075,7 +1083,7 @@ static int launch_first(const nic_conv_desc* d, const void* x, const void* w_pac
   f.tiles_x = (d->w_out + 15) / 16; f.tiles_y = (d->h_out + 15) / 16; f.total_tiles = f.tiles_x * f.tiles_y * d->n;
   f.off_a = 0; f.off_w = 4 * 128 * 128; f.off_gamma = f.off_w + 2 * 128 * 128; f.off_sq = f.off_gamma + 2 * 128 * 128;
   f.off_patch = f.off_sq + 2 * 128 * 128;
-  const int smem_bytes = f.off_patch + 3 * kPatchPlane * 4 + 1024 + 64;
+  const int smem_bytes = f.off_patch + 2 * 3 * kPatchPlane * 4 + 1024 + 64;
   CUtensorMap map_w, map_g, map_o;
   if (int rc = encode_2d(&map_w, w_packed, 128, 128, 64, 128)) return rc;
   if (int rc = encode_2d(&map_g, gdn_gamma, 128, 128, 64, 128)) return rc;

@@ -127,6 +127,40 @@ class ShardedEvaluator:
         return None if ent is None else ent[1]
 
     @torch.no_grad()
+    def evaluate_host_batches(self, host_batches):
+        """Evaluate an iterable of pinned HOST batches [B,3,H,W]; yields the 8 rd scalars (Python floats) per batch.
+
+        The upload of batch i+1 (pinned host -> device, on a copy stream) overlaps the kernels of batch i; every batch
+        still pays its own host->device copy and its own device->host read of the result.
+        """
+        dev = next(self.model.parameters()).device
+        copy_stream = torch.cuda.Stream(device=dev)
+        it = iter(host_batches)
+        staging, ready = [None, None], [torch.cuda.Event(), torch.cuda.Event()]
+
+        def upload(slot, hb):
+            if staging[slot] is None or staging[slot].shape != hb.shape:
+                staging[slot] = torch.empty(hb.shape, dtype=torch.float32, device=dev)
+            with torch.cuda.stream(copy_stream):
+                staging[slot].copy_(hb, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        upload(0, nxt)
+        i = 0
+        while nxt is not None:
+            cur = i & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(cur ^ 1, nxt)                    # overlaps the step below; slot cur^1 was consumed two steps ago
+            torch.cuda.current_stream().wait_event(ready[cur])
+            _, terms = self.step(staging[cur])
+            yield terms["scalars"].tolist()             # device -> host read of this batch's result (synchronises)
+            i += 1
+
+    @torch.no_grad()
     def step(self, x_local: torch.Tensor):
         out, per_image, scalars = self._graphed_local(x_local) if self.graph else self._local(x_local)
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
