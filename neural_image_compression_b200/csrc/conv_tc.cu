@@ -81,7 +81,7 @@ struct TcParams {
                                                //      pixel (2 oy + py, 2 ox + px), channel c of an fp32 tensor (ConvTranspose2d to RGB)
   int bias_mod;                                // bias index = column % bias_mod (shuffle) ; 0 = plain
   int dbg;                                     // NIC_TC_DEBUG bits (timing experiments only): 1 skip gamma MMA, 2 skip tensor store
-  long long* dbg_times;                        // NIC_TC_TRACE: [cta][16 tiles][8] clock64 stamps of the pipeline roles (null = off)
+  long long* dbg_times;                        // NIC_TC_TRACE: [cta][16 tiles][16] clock64 stamps of the pipeline roles (null = off)
   const float* bias;
   const float* beta;
   void* y;
@@ -108,7 +108,7 @@ __device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, Tc
 }
 
 __device__ __forceinline__ void trace(const TcParams& p, uint32_t tile_iter, int slot) {
-  if (p.dbg_times && tile_iter < 16) p.dbg_times[(static_cast<long>(blockIdx.x) * 16 + tile_iter) * 8 + slot] = clock64();
+  if (p.dbg_times && tile_iter < 16) p.dbg_times[(static_cast<long>(blockIdx.x) * 16 + tile_iter) * 16 + slot] = clock64();
 }
 
 __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& ntile, int& phase, int& img, int& ty, int& tx) {
@@ -188,10 +188,17 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 // bf16 NHWC tile staged in shared memory, or direct stores).  NW = 4 or 8 epilogue warps; thread <-> accumulator row <->
 // pixel; with 8 warps the second warpgroup (hs = 1) takes channels 64..127 of the same rows, i.e. the other 64-channel half
 // of the squares / staging tile.  Returns false when a bounded wait expired.
-template <int NW>
+// KEEPX = true: x stays in registers and the gamma contraction overwrites the accumulator in place (no extra TMEM);
+// KEEPX = false: the contraction goes to `gdn_tmem` and x is read from the accumulator a second time (fewer registers).
+template <int NW, bool KEEPX = true>
 __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb, const float* s_bias, const float* s_beta, uint8_t* sq,
                                                const uint8_t* gamma_smem, const CUtensorMap* map_o_ptr, uint32_t acc_tmem, int q, int lane,
-                                               int hs, bool leader, int img, int oy0, int ox0, int py, int px, int cbase, uint32_t& gdn_count) {
+                                               int hs, bool leader, int img, int oy0, int ox0, int py, int px, int cbase, uint32_t& gdn_count,
+                                               uint32_t trace_tile = 0xffffffffu, int trace_base = 8, int bar_id = 1,
+                                               uint64_t* gdn_bar = nullptr, uint32_t gdn_tmem = 0) {
+  if (!gdn_bar) gdn_bar = &sb->gdn_full;
+  if (KEEPX) gdn_tmem = acc_tmem;
+  const uint32_t gdn_addr = gdn_tmem + (static_cast<uint32_t>(q * 32) << 16);
   constexpr int NG = (NW == 8) ? 2 : 4;                     // 32-channel groups per thread in the 128-wide paths
   const bool gdn = p.epilogue == NIC_EPI_GDN || p.epilogue == NIC_EPI_IGDN;
   const bool igdn = p.epilogue == NIC_EPI_IGDN;
@@ -209,23 +216,21 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
   } else {
     obase = img * p.ys_n + static_cast<long>(out_y) * p.ys_h + static_cast<long>(out_x) * p.ys_w;
   }
-  auto epi_sync = [&]() {
-    if (NW == 8) asm volatile("bar.sync 1, 256;" ::: "memory");
-    else asm volatile("bar.sync 1, 128;" ::: "memory");
-  };
+  auto epi_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NW * 32) : "memory"); };
   if (p.tma_out) {
     // the staging tile (= the squares tile) may still be read by the previous block's tensor store
     if (leader) tma_store_wait_read();
     epi_sync();
   }
-  float xr[NG * 32];
+  if (leader) trace(p, trace_tile, trace_base + 0);
+  float xr[KEEPX ? NG * 32 : 32];
   if (gdn) {
     // x (+ bias) stays in registers; its squares go to shared memory as the bf16 K-major A operand of the
     // gamma contraction, whose result OVERWRITES this accumulator (no extra TMEM); then y = x * rsqrt(beta + .)
 #pragma unroll
     for (int i = 0; i < NG; ++i) {
       const int cg = cg0 + i;
-      tmem_ld_32x32(acc_addr + cg * 32, xr + i * 32);
+      tmem_ld_32x32(acc_addr + cg * 32, xr + (KEEPX ? i * 32 : 0));
       tmem_ld_wait();
       uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
 #pragma unroll
@@ -233,7 +238,7 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int l = i * 32 + j * 8 + e * 2, c0 = cg * 32 + j * 8 + e * 2;
+          const int l = (KEEPX ? i * 32 : 0) + j * 8 + e * 2, c0 = cg * 32 + j * 8 + e * 2;
           const float a = xr[l] + s_bias[c0], bb = xr[l + 1] + s_bias[c0 + 1];
           xr[l] = a; xr[l + 1] = bb;
           w[e] = pack_bf16x2(a * a, bb * bb);
@@ -244,7 +249,9 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
     }
     fence_proxy_async_smem();
     tcgen05_fence_before();
+    if (leader) trace(p, trace_tile, trace_base + 1);
     epi_sync();
+    if (leader) trace(p, trace_tile, trace_base + 2);
     if (leader && !(p.dbg & 1)) {
       if (gdn_count == 0) wait_or_abort(&sb->gamma_full, 0, sb, p.status);
       tcgen05_fence_after();
@@ -254,15 +261,16 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const uint32_t off = ((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4;
-        umma_bf16_lohi(acc_tmem, sq_lo + off, hi, g_lo + off, hi, idg, k);
+        umma_bf16_lohi(gdn_tmem, sq_lo + off, hi, g_lo + off, hi, idg, k);
       }
-      umma_commit(&sb->gdn_full);
+      umma_commit(gdn_bar);
     }
     if (!(p.dbg & 1)) {
-      if (!__all_sync(0xffffffffu, wait_or_abort(&sb->gdn_full, gdn_count & 1, sb, p.status))) return false;
+      if (!__all_sync(0xffffffffu, wait_or_abort(gdn_bar, gdn_count & 1, sb, p.status))) return false;
     }
     ++gdn_count;
     tcgen05_fence_after();
+    if (leader) trace(p, trace_tile, trace_base + 3);
   }
   const int nvalid_c = p.cout - cbase;                      // channels of this N tile that exist
   auto emit_group = [&](int cg, const float* v) {             // one pixel x 32 channels: to the staging tile or to HBM
@@ -295,14 +303,22 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
     for (int i = 0; i < NG; ++i) {
       const int cg = cg0 + i;
       float v[32];
-      tmem_ld_32x32(acc_addr + cg * 32, v);
-      tmem_ld_wait();
+      tmem_ld_32x32(gdn_addr + cg * 32, v);
+      if (!KEEPX) {
+        tmem_ld_32x32(acc_addr + cg * 32, xr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xr[j] += s_bias[cg * 32 + j];
+      } else {
+        tmem_ld_wait();
+      }
+      const float* xp = xr + (KEEPX ? i * 32 : 0);
       if (igdn) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = xr[i * 32 + j] * sqrt_approx(v[j] + s_beta[cg * 32 + j]);
+        for (int j = 0; j < 32; ++j) v[j] = xp[j] * sqrt_approx(v[j] + s_beta[cg * 32 + j]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = xr[i * 32 + j] * rsqrt_approx(v[j] + s_beta[cg * 32 + j]);
+        for (int j = 0; j < 32; ++j) v[j] = xp[j] * rsqrt_approx(v[j] + s_beta[cg * 32 + j]);
       }
       emit_group(cg, v);
     }
@@ -325,9 +341,11 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
       emit_group(cg, v);
     }
   }
+  if (leader) trace(p, trace_tile, trace_base + 4);
   if (p.tma_out) {
     fence_proxy_async_smem();
     epi_sync();
+    if (leader) trace(p, trace_tile, trace_base + 5);
     if (leader && !(p.dbg & 2)) {
       const int wc = ox0 * p.out_stride + px, hc = oy0 * p.out_stride + py;
       for (int h = 0; h < 2; ++h)
@@ -529,7 +547,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int b = 0; b < nblk && ok; ++b)
         ok = epilogue_block<kEpiWarps>(p, &sb, s_bias, s_beta, sq, smem + p.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane,
                                        (warp - 3) >> 2, warp == 3 && lane == 0, img, ty * p.tile_h + p.blk_roff[b],
-                                       tx * p.tile_w + p.blk_coff[b], ph.py, ph.px, ntile * p.nb, gdn_count);
+                                       tx * p.tile_w + p.blk_coff[b], ph.py, ph.px, ntile * p.nb, gdn_count, b == 0 ? tcount : 0xffffffffu);
       if (warp == 3 && lane == 0) trace(p, tcount, 4);
       tcgen05_fence_before();
       __syncwarp();
@@ -560,7 +578,7 @@ struct FirstParams {
 };
 
 struct __align__(8) FirstBarriers {
-  uint64_t a_full, a_empty, w_full;
+  uint64_t a_full, a_empty, w_full, gdn_full2;
   TcBarriers common;              // acc_full / acc_empty / gdn_full / gamma_full + tmem_base + abort flag (epilogue_block uses these)
 };
 
@@ -576,7 +594,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   if (tid < 128) { s_bias[tid] = p.bias[tid]; s_beta[tid] = p.beta[tid]; }
   if (tid == 0) {
-    mbar_init(&fb.a_full, 128); mbar_init(&fb.a_empty, 1); mbar_init(&fb.w_full, 1);
+    mbar_init(&fb.a_full, 128); mbar_init(&fb.a_empty, 1); mbar_init(&fb.w_full, 1); mbar_init(&fb.gdn_full2, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], kEpiWarps); }
     mbar_init(&sb.gdn_full, 1); mbar_init(&sb.gamma_full, 1);
     sb.abort_flag = 0;
@@ -673,44 +691,49 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       bool ok = wait_or_abort(&fb.w_full, 0, &sb, p.status);
       uint32_t it = 0;
       for (int tile = first_tile; tile < f.total_tiles && ok; tile += tile_step, ++it) {
-        const uint32_t buf = it & 1;
-        if (!wait_or_abort(&sb.acc_empty[buf], ((it >> 1) & 1) ^ 1, &sb, p.status)) break;
+        // accumulators are single-buffered here (columns 0..255; 256..511 receive the gamma contractions): the 10 MMAs of a
+        // tile are ~0.6k clk against a ~5k clk epilogue, so there is nothing worth overlapping
+        if (!wait_or_abort(&sb.acc_empty[0], (it & 1) ^ 1, &sb, p.status)) break;
         if (!wait_or_abort(&fb.a_full, it & 1, &sb, p.status)) break;
         tcgen05_fence_after();
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-          const uint32_t d = tmem + buf * 256 + b * 128;
+          const uint32_t d = tmem + b * 128;
           const uint32_t ab = a_lo + b * ((2 * 128 * 128) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + 2 * k, hi, w_lo + 2 * k, hi, idesc, k);
           umma_bf16_lohi(d, ab + ((128 * 128) >> 4), hi, w_lo + ((128 * 128) >> 4), hi, idesc, 1);      // k = 64..79
         }
         umma_commit(&fb.a_empty);
-        umma_commit(&sb.acc_full[buf]);
+        umma_commit(&sb.acc_full[0]);
       }
     }
   } else {
     // ===================== epilogue (warps 5..12) =====================
+    // Two independent groups of 4 warps: group 0 takes block 0 of every tile, group 1 block 1, each with its own squares /
+    // staging tile, named barrier and gamma-MMA barrier, so one group computes while the other waits on its gamma MMA or
+    // on its tensor store.
     const int q = warp & 3;
-    uint8_t* sq = smem + f.off_sq;
+    const int grp = (warp - 5) >> 2;
+    uint8_t* sq = smem + f.off_sq + grp * (2 * 128 * 128);
+    uint64_t* gbar = grp ? &fb.gdn_full2 : &sb.gdn_full;
+    const bool leader = ((warp - 5) & 3) == 0 && lane == 0;
     uint32_t it = 0, gdn_count = 0;
     bool ok = true;
     for (int tile = first_tile; tile < f.total_tiles && ok; tile += tile_step, ++it) {
       int img, ty, tx;
       tile_coords(tile, img, ty, tx);
-      const uint32_t buf = it & 1;
-      if (!__all_sync(0xffffffffu, wait_or_abort(&sb.acc_full[buf], (it >> 1) & 1, &sb, p.status))) break;
+      if (!__all_sync(0xffffffffu, wait_or_abort(&sb.acc_full[0], it & 1, &sb, p.status))) break;
       tcgen05_fence_after();
-      for (int b = 0; b < 2 && ok; ++b) {
-        if (tx * 16 + b * 8 >= p.wp) break;
-        ok = epilogue_block<kEpiWarps>(p, &sb, s_bias, s_beta, sq, smem + f.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane,
-                                       (warp - 5) >> 2, warp == 5 && lane == 0, img, ty * 16, tx * 16 + b * 8, 0, 0, 0, gdn_count);
-      }
+      if (tx * 16 + grp * 8 < p.wp)
+        ok = epilogue_block<4, false>(p, &sb, s_bias, s_beta, sq, smem + f.off_gamma, &map_o, tmem + grp * 128, q, lane, 0, leader,
+                                      img, ty * 16, tx * 16 + grp * 8, 0, 0, 0, gdn_count, 0xffffffffu, 8, 1 + grp, gbar,
+                                      tmem + 256 + grp * 128);
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sb.acc_empty[buf]);
+      if (lane == 0) mbar_arrive(&sb.acc_empty[0]);
     }
-    if (warp == 5 && lane == 0) tma_store_wait_all();
+    if (leader) tma_store_wait_all();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -1082,7 +1105,7 @@ static int launch_first(const nic_conv_desc* d, const void* x, const void* w_pac
   f.x = static_cast<const float*>(x); f.n = d->n; f.hin = d->h_in; f.win = d->w_in;
   f.tiles_x = (d->w_out + 15) / 16; f.tiles_y = (d->h_out + 15) / 16; f.total_tiles = f.tiles_x * f.tiles_y * d->n;
   f.off_a = 0; f.off_w = 4 * 128 * 128; f.off_gamma = f.off_w + 2 * 128 * 128; f.off_sq = f.off_gamma + 2 * 128 * 128;
-  f.off_patch = f.off_sq + 2 * 128 * 128;
+  f.off_patch = f.off_sq + 4 * 128 * 128;      // two squares / staging tiles (one per epilogue group)
   const int smem_bytes = f.off_patch + 2 * 3 * kPatchPlane * 4 + 1024 + 64;
   CUtensorMap map_w, map_g, map_o;
   if (int rc = encode_2d(&map_w, w_packed, 128, 128, 64, 128)) return rc;
@@ -1090,7 +1113,7 @@ static int launch_first(const nic_conv_desc* d, const void* x, const void* w_pac
   if (int rc = encode_nhwc(&map_o, y, d->n, d->h_out, d->w_out, 128, kTileW, kTileH, 1)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), "cudaFuncSetAttribute")) return rc;
+    if (int rc = check_cuda(cudaFuncSetAttribute(conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048), "cudaFuncSetAttribute")) return rc;
     attr_set = true;
   }
   const int grid = f.total_tiles < kNumSMs ? f.total_tiles : kNumSMs;

@@ -27,15 +27,16 @@ lib.nic_debug_set_trace.argtypes = [C.c_void_p]; lib.nic_debug_set_trace.restype
 for _ in range(3):
     op.run(x, B, h, w, "bf16", **kw)
 torch.cuda.synchronize()
-buf = torch.zeros(148 * 16 * 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(148 * 16 * 16, dtype=torch.int64, device=dev)
 lib.nic_debug_set_trace(buf.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); op.run(x, B, h, w, "bf16", **kw); e1.record()
 torch.cuda.synchronize()
 lib.nic_debug_set_trace(None)
-t = buf.cpu().reshape(148, 16, 8)
+t = buf.cpu().reshape(148, 16, 16)
 print(f"{which}: {e0.elapsed_time(e1)*1000:.1f} us")
-names = ["mma:acc_empty", "mma:first_a", "mma:issued", "epi:acc_full", "epi:done", "A:first_issue", "A:last_issue"]
+names = ["mma:acc_empty", "mma:first_a", "mma:issued", "epi:acc_full", "epi:done", "A:first", "A:last", "-",
+         "e0:start", "e0:sqdone", "e0:synced", "e0:gdn", "e0:computed", "e0:synced2"]
 for cta in (0, 77):
     base = int(t[cta, 0][t[cta, 0] > 0].min())
     print(f"CTA {cta} (clk relative to its first stamp)")
@@ -43,4 +44,4 @@ for cta in (0, 77):
         row = t[cta, i]
         if int(row[0]) == 0:
             break
-        print("  tile %2d: " % i + "  ".join(f"{n}={int(row[j]) - base:7d}" for j, n in enumerate(names)))
+        print("  tile %2d: " % i + "  ".join(f"{n}={int(row[j]) - base:6d}" for j, n in enumerate(names) if n != "-" and int(row[j]) != 0))
