@@ -240,6 +240,28 @@ def main():
                 "peak_source": f"{peaks['src']} bf16 burst (kernel timed alone)",
                 "whole_step_tflops": FLOPS_PER_IMAGE * B * args.steps / (ms_total / 1e3) / 1e12}
 
+    # ---- the HBM-bound kernel north_star names: quantise + GM-K3 likelihood + log + bit sums, full (dict) variant -------
+    from neural_image_compression_b200.EntropyModels import gm_likelihood
+    from neural_image_compression_b200._lib import Q_ROUND
+    lik = {}
+    for lb in (B, 16 * B):
+        yl = 5 * torch.randn((lb, M, H_IMG // 16, W_IMG // 16), device=dev)
+        rawl = torch.randn((lb, 3 * K * M, H_IMG // 16, W_IMG // 16), device=dev)
+        ld = []
+        for i in range(8):
+            flush.zero_()
+            ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ks.record(); gm_likelihood(yl, rawl, M, K, Q_ROUND, full=True); ke.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ld.append(ks.elapsed_time(ke))
+        lms = statistics.mean(ld)
+        nbytes = yl.numel() * 88                                  # 52 B/elem + 36 B/elem for weights/mus/sigmas
+        lik[f"batch{lb}"] = {"ms": lms, "GB/s": nbytes / (lms / 1e3) / 1e9, "frac_of_hbm_peak": nbytes / (lms / 1e3) / 1e9 / peaks["hbm"]}
+        del yl, rawl
+    roofline_lik = {"bound": "hbm", "kernel": "gm_likelihood_kernel<K=3, full>", "unit": "GB/s", "peak": peaks["hbm"],
+                    "bytes_per_y_element": 88, "peak_source": f"{peaks['src']} copy bandwidth", **lik}
+
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_reference_arm(2, 3)
         line = {
@@ -251,7 +273,7 @@ def main():
                        "l2": "4 rotating input batches (302 MB) + >400 MB of per-step intermediates exceed the 126 MB L2",
                        "launch": "one CUDA-graph replay per step" if use_graph else "per-kernel launches from Python"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_likelihood": roofline_lik,
             "rd": {"bpp_total": float(terms["bpp_total"]), "psnr": float(terms["psnr"]), "e2e_bpp_total": res["bpp_total"]},
         }
         if cpu is not None:

@@ -227,11 +227,18 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
   if (gdn) {
     // x (+ bias) stays in registers; its squares go to shared memory as the bf16 K-major A operand of the
     // gamma contraction, whose result OVERWRITES this accumulator (no extra TMEM); then y = x * rsqrt(beta + .)
+    if (KEEPX) {      // all of this thread's accumulator columns in flight at once, one wait
+#pragma unroll
+      for (int i = 0; i < NG; ++i) tmem_ld_32x32(acc_addr + (cg0 + i) * 32, xr + i * 32);
+      tmem_ld_wait();
+    }
 #pragma unroll
     for (int i = 0; i < NG; ++i) {
       const int cg = cg0 + i;
-      tmem_ld_32x32(acc_addr + cg * 32, xr + (KEEPX ? i * 32 : 0));
-      tmem_ld_wait();
+      if (!KEEPX) {
+        tmem_ld_32x32(acc_addr + cg * 32, xr);
+        tmem_ld_wait();
+      }
       uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -299,28 +306,45 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
     }
   };
   if (gdn) {
-#pragma unroll
-    for (int i = 0; i < NG; ++i) {
-      const int cg = cg0 + i;
-      float v[32];
-      tmem_ld_32x32(gdn_addr + cg * 32, v);
-      if (!KEEPX) {
-        tmem_ld_32x32(acc_addr + cg * 32, xr);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) xr[j] += s_bias[cg * 32 + j];
-      } else {
-        tmem_ld_wait();
-      }
-      const float* xp = xr + (KEEPX ? i * 32 : 0);
+    if (KEEPX && NG == 2) {
+      // both 32-column groups of the contraction in flight at once
+      float v0[32], v1[32];
+      tmem_ld_32x32(gdn_addr + cg0 * 32, v0);
+      tmem_ld_32x32(gdn_addr + (cg0 + 1) * 32, v1);
+      tmem_ld_wait();
       if (igdn) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = xp[j] * sqrt_approx(v[j] + s_beta[cg * 32 + j]);
+        for (int j = 0; j < 32; ++j) { v0[j] = xr[j] * sqrt_approx(v0[j] + s_beta[cg0 * 32 + j]); v1[j] = xr[32 + j] * sqrt_approx(v1[j] + s_beta[cg0 * 32 + 32 + j]); }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = xp[j] * rsqrt_approx(v[j] + s_beta[cg * 32 + j]);
+        for (int j = 0; j < 32; ++j) { v0[j] = xr[j] * rsqrt_approx(v0[j] + s_beta[cg0 * 32 + j]); v1[j] = xr[32 + j] * rsqrt_approx(v1[j] + s_beta[cg0 * 32 + 32 + j]); }
       }
-      emit_group(cg, v);
+      emit_group(cg0, v0);
+      emit_group(cg0 + 1, v1);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NG; ++i) {
+        const int cg = cg0 + i;
+        float v[32];
+        tmem_ld_32x32(gdn_addr + cg * 32, v);
+        if (!KEEPX) {
+          tmem_ld_32x32(acc_addr + cg * 32, xr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) xr[j] += s_bias[cg * 32 + j];
+        } else {
+          tmem_ld_wait();
+        }
+        const float* xp = xr + (KEEPX ? i * 32 : 0);
+        if (igdn) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = xp[j] * sqrt_approx(v[j] + s_beta[cg * 32 + j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = xp[j] * rsqrt_approx(v[j] + s_beta[cg * 32 + j]);
+        }
+        emit_group(cg, v);
+      }
     }
   } else {
     // channel groups of this warpgroup: with 8 warps the second one takes the upper half of the groups
