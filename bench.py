@@ -235,7 +235,10 @@ def main():
     k2_ms = statistics.mean(durs)
     achieved = K2_FLOPS_PER_IMAGE * B / (k2_ms / 1e3) / 1e12
     peak = peaks["bf16_burst"]
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture summarised in
+    # profiles/r1_ncu_full_v3_summary.txt (403.8 MB + 82.0 MB; algorithmic: 402.7 MB in + 100.7 MB out + 0.8 MB weights)
+    k2_traffic = 485.8e6 if B == 16 else None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": k2_traffic,
                 "kernel": "g_a layer 2: conv 128->128 5x5 s2 + GDN, 16x256x384 input", "ms_per_launch": k2_ms,
                 "peak_source": f"{peaks['src']} bf16 burst (kernel timed alone)",
                 "whole_step_tflops": FLOPS_PER_IMAGE * B * args.steps / (ms_total / 1e3) / 1e12}
