@@ -181,3 +181,40 @@ def test_model_bf16_full_size_batch_is_batch_independent():
     one = model(x[3:4], training=False)
     for k in ("y_in", "z_in", "p_y", "x_hat"):
         assert torch.equal(one[k][0], out[k][3]), k
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 64, 64), (3, 3, 192, 320), (2, 3, 128, 448)])
+def test_model_bf16_ragged_sizes_match_fp32_arm(shape):
+    """Sizes whose feature maps do not divide into 16 x 16 tiles (edge tiles, one-block tiles, 1x1 z maps): the
+    tensor-core arm must agree with the fp32 CUDA-core arm (itself checked against the oracle) at bf16 tolerances."""
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    x = H.seeded_input(shape).cuda()
+    ref_model = H.seeded_model(128, 3, "calib", precision="fp32").cuda()
+    model = H.seeded_model(128, 3, "calib", precision="bf16").cuda()
+    ref, out = ref_model(x, training=False), model(x, training=False)
+    r0, r1 = rd_loss(ref, x, 0.005), rd_loss(out, x, 0.005)
+    yerr = float((out["y"] - ref["y"]).abs().max() / ref["y"].abs().max())
+    # x_hat follows the (few) flipped symbols locally, so the max error is a flip's footprint; the RMS is the bf16 noise
+    xerr = float((out["x_hat"] - ref["x_hat"]).pow(2).mean().sqrt() / ref["x_hat"].pow(2).mean().sqrt())
+    xmax = float((out["x_hat"] - ref["x_hat"]).abs().max() / ref["x_hat"].abs().max())
+    flips = float((out["y_in"] != ref["y_in"]).float().mean())
+    print(shape, f"y {yerr:.2e} x_hat {xerr:.2e} flips {flips:.4f} bpp {r1['bpp_total']:.5f}/{r0['bpp_total']:.5f}")
+    assert yerr < 3e-2 and xerr < 2e-2 and xmax < 0.2 and flips < 0.08
+    assert abs(r1["bpp_total"] - r0["bpp_total"]) < 0.05 and abs(r1["psnr"] - r0["psnr"]) < 0.05
+
+
+def test_model_bf16_training_forward_and_k1():
+    """training=True (injected noise) and the K = 1 mean-scale variant through the tensor-core arm."""
+    torch.manual_seed(30)
+    x = H.seeded_input((2, 3, 128, 192))
+    for K in (1, 3):
+        model = H.seeded_model(128, K, "calib", precision="bf16")
+        sd = {k: v.clone() for k, v in model.state_dict().items()}
+        nz, ny = torch.rand(2, 128, 2, 3) - 0.5, torch.rand(2, 128, 8, 12) - 0.5
+        ref = O.forward(sd, x, 128, K, training=True, noise_z=nz, noise_y=ny)
+        out = model.cuda()(x.cuda(), training=True, noise=(nz.cuda(), ny.cuda()))
+        assert out["training"] is True and set(out) >= ({"mu", "sigma"} if K == 1 else {"weights", "mus", "sigmas"})
+        assert float((out["y_in"].cpu() - ref["y_in"]).abs().max() / ref["y_in"].abs().max()) < 3e-2
+        bits = -out["logp_y"].double().sum().item() / np.log(2)
+        ref_bits = -ref["logp_y"].double().sum().item() / np.log(2)
+        assert abs(bits - ref_bits) / ref_bits < 2e-2, (K, bits, ref_bits)
