@@ -670,7 +670,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     const int r = tid, g = r >> 3, c8 = r & 7;
     for (int tile = first_tile; tile < f.total_tiles; tile += tile_step, ++it) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("bar.sync 2, 128;" ::: "memory");         // patch(it) visible to all producers; patch(it-1) no longer read
+      asm volatile("bar.sync 3, 128;" ::: "memory");         // patch(it) visible to all producers; patch(it-1) no longer read
       if (tile + tile_step < f.total_tiles) fetch_patch(tile + tile_step, (it + 1) & 1);
       if (!__all_sync(0xffffffffu, wait_or_abort(&fb.a_empty, (it & 1) ^ 1, &sb, p.status))) break;
       const float* pbuf = patch + (it & 1) * (3 * kPatchPlane);

@@ -199,7 +199,7 @@ def test_model_bf16_ragged_sizes_match_fp32_arm(shape):
     xmax = float((out["x_hat"] - ref["x_hat"]).abs().max() / ref["x_hat"].abs().max())
     flips = float((out["y_in"] != ref["y_in"]).float().mean())
     print(shape, f"y {yerr:.2e} x_hat {xerr:.2e} flips {flips:.4f} bpp {r1['bpp_total']:.5f}/{r0['bpp_total']:.5f}")
-    assert yerr < 3e-2 and xerr < 2e-2 and xmax < 0.2 and flips < 0.08
+    assert yerr < 3e-2 and xerr < 5e-2 and xmax < 0.3 and flips < 0.08
     assert abs(r1["bpp_total"] - r0["bpp_total"]) < 0.05 and abs(r1["psnr"] - r0["psnr"]) < 0.05
 
 
