@@ -592,8 +592,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // issues 5 tcgen05.mma per block against the resident [128 x 80] weights, and the shared epilogue applies the fused GDN and
 // stores the bf16 NHWC tile with TMA.  9 warps: 0-3 producers, 4 MMA issuer / weight loader, 5-8 epilogue.
 // ---------------------------------------------------------------------------------------------
-constexpr int kFirstThreads = 160 + kEpiWarps * 32;
-constexpr int kPatchW = 36, kPatchH = 35, kPatchPlane = kPatchH * kPatchW;     // fp32 patch rows padded to 36 floats
+constexpr int kFirstThreads = 160 + 8 * 32;
+constexpr int kPatchW = 20, kPatchH = 35, kPatchCols = 19, kPatchPlane = kPatchH * kPatchW;   // fp32 patch rows padded to 20 floats
 
 struct FirstParams {
   const float* x;                 // [n, 3, hin, win] fp32
@@ -602,10 +602,14 @@ struct FirstParams {
 };
 
 struct __align__(8) FirstBarriers {
-  uint64_t a_full, a_empty, w_full, gdn_full2;
+  uint64_t a_full[2], a_empty[2], w_full, gdn_full2;
   TcBarriers common;              // acc_full / acc_empty / gdn_full / gamma_full + tmem_base + abort flag (epilogue_block uses these)
 };
 
+// Tile = one M = 128 block (16 rows x 8 output pixels).  Everything is double-buffered by tile parity g = it & 1: A operand
+// stage g, accumulator columns [g*128, +128), gamma-contraction columns [256 + g*128, +128), and epilogue GROUP g (4 warps
+// with their own squares / staging tile, named barrier and gamma barrier) - so the two epilogue groups work on consecutive
+// tiles concurrently while the producers expand the next patch.
 __global__ void __launch_bounds__(kFirstThreads, 1)
 conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_g,
                      const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p, const __grid_constant__ FirstParams f) {
@@ -618,8 +622,11 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   if (tid < 128) { s_bias[tid] = p.bias[tid]; s_beta[tid] = p.beta[tid]; }
   if (tid == 0) {
-    mbar_init(&fb.a_full, 128); mbar_init(&fb.a_empty, 1); mbar_init(&fb.w_full, 1); mbar_init(&fb.gdn_full2, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&fb.a_full[i], 128); mbar_init(&fb.a_empty[i], 1);
+      mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], 4);
+    }
+    mbar_init(&fb.w_full, 1); mbar_init(&fb.gdn_full2, 1);
     mbar_init(&sb.gdn_full, 1); mbar_init(&sb.gamma_full, 1);
     sb.abort_flag = 0;
     fence_barrier_init();
@@ -638,28 +645,31 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 
   if (warp < 4) {
     // ===================== producers: image patch -> bf16 im2col A operand =====================
-    // The fp32 patch of tile i+1 streams into the other half of a double buffer with cp.async (zero fill = conv padding)
-    // while tile i is expanded; warp w copies patch rows w, w+4, ... (coalesced 128 B per row).
+    // The fp32 patch (3 x 35 x 19) of tile i+1 streams into the other half of a double buffer with cp.async (zero fill =
+    // conv padding) while tile i is expanded; warp w copies patch rows w, w+4, ...
     auto fetch_patch = [&](int tile, int bufi) {
       int img, ty, tx;
       tile_coords(tile, img, ty, tx);
-      const int y0 = 2 * (ty * 16) - 2, x0 = 2 * (tx * 16) - 2;
-      const float* base = f.x + static_cast<long>(img) * 3 * f.hin * f.win;
-      const uint32_t dst0 = smem_u32(patch + bufi * (3 * kPatchPlane));
-      for (int r = warp; r < 3 * kPatchH; r += 4) {
-        const int c = r / kPatchH, yy = r - c * kPatchH;
-        const int gy = y0 + yy;
-        const bool row_ok = gy >= 0 && gy < f.hin;
-        const float* srow = base + (static_cast<long>(c) * f.hin + (row_ok ? gy : 0)) * f.win;
+      const int y0 = 2 * (ty * 16) - 2, x0 = 2 * (tx * 8) - 2;
+      const int gx = x0 + lane;
+      const bool col_ok = lane < kPatchCols && gx >= 0 && gx < f.win;
+      const float* base = f.x + static_cast<long>(img) * 3 * f.hin * f.win + (col_ok ? gx : 0);
+      const uint32_t dst0 = smem_u32(patch + bufi * (3 * kPatchPlane)) + lane * 4;
+      if (lane < kPatchCols) {
+        // warp w copies rows w, w + 4, ... of each colour plane; fully unrolled so the 27 copies are independent
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int xx = lane + 32 * h;
-          if (xx < kPatchH) {
-            const int gx = x0 + xx;
-            const bool ok = row_ok && gx >= 0 && gx < f.win;
-            const uint32_t dst = dst0 + (c * kPatchPlane + yy * kPatchW + xx) * 4;
-            const float* src = srow + (ok ? gx : 0);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+          for (int j = 0; j < 9; ++j) {
+            const int yy = warp + 4 * j;
+            if (yy < kPatchH) {
+              const int gy = y0 + yy;
+              const bool ok = col_ok && gy >= 0 && gy < f.hin;
+              const float* src = base + (static_cast<long>(c) * f.hin + (ok ? gy : 0)) * f.win;
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + (c * kPatchPlane + yy * kPatchW) * 4), "l"(src),
+                           "r"(ok ? 4 : 0)
+                           : "memory");
+            }
           }
         }
       }
@@ -669,34 +679,36 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     uint32_t it = 0;
     const int r = tid, g = r >> 3, c8 = r & 7;
     for (int tile = first_tile; tile < f.total_tiles; tile += tile_step, ++it) {
+      const uint32_t st = it & 1;
+      if (tid == 0) trace(p, it, 0);
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("bar.sync 3, 128;" ::: "memory");         // patch(it) visible to all producers; patch(it-1) no longer read
-      if (tile + tile_step < f.total_tiles) fetch_patch(tile + tile_step, (it + 1) & 1);
-      if (!__all_sync(0xffffffffu, wait_or_abort(&fb.a_empty, (it & 1) ^ 1, &sb, p.status))) break;
-      const float* pbuf = patch + (it & 1) * (3 * kPatchPlane);
+      if (tid == 0) trace(p, it, 1);
+      if (tile + tile_step < f.total_tiles) fetch_patch(tile + tile_step, st ^ 1);
+      if (tid == 0) trace(p, it, 2);
+      if (!__all_sync(0xffffffffu, wait_or_abort(&fb.a_empty[st], ((it >> 1) & 1) ^ 1, &sb, p.status))) break;
+      if (tid == 0) trace(p, it, 3);
+      const float* src = patch + st * (3 * kPatchPlane) + (2 * g) * kPatchW + 2 * c8;
+      uint8_t* dst = smem + f.off_a + st * (2 * 128 * 128) + r * 128;
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const float* src = pbuf + (2 * g) * kPatchW + 2 * (b * 8 + c8);
-        uint8_t* dst = smem + f.off_a + b * (2 * 128 * 128) + r * 128;
+      for (int ch = 0; ch < 10; ++ch) {
+        uint32_t w[4];
 #pragma unroll
-        for (int ch = 0; ch < 10; ++ch) {
-          uint32_t w[4];
+        for (int e = 0; e < 4; ++e) {
+          float v2[2];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float v2[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int k = ch * 8 + e * 2 + h;
-              if (k < 75) { const int tap = k / 3, c = k % 3; v2[h] = src[c * kPatchPlane + (tap / 5) * kPatchW + (tap % 5)]; }
-              else v2[h] = 0.f;
-            }
-            w[e] = pack_bf16x2(v2[0], v2[1]);
+          for (int h = 0; h < 2; ++h) {
+            const int k = ch * 8 + e * 2 + h;
+            if (k < 75) { const int tap = k / 3, c = k % 3; v2[h] = src[c * kPatchPlane + (tap / 5) * kPatchW + (tap % 5)]; }
+            else v2[h] = 0.f;
           }
-          *reinterpret_cast<uint4*>(dst + (ch >> 3) * (128 * 128) + (((ch & 7) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          w[e] = pack_bf16x2(v2[0], v2[1]);
         }
+        *reinterpret_cast<uint4*>(dst + (ch >> 3) * (128 * 128) + (((ch & 7) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
       fence_proxy_async_smem();
-      mbar_arrive(&fb.a_full);
+      mbar_arrive(&fb.a_full[st]);
+      if (tid == 0) trace(p, it, 4);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == 4) {
@@ -715,28 +727,23 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       bool ok = wait_or_abort(&fb.w_full, 0, &sb, p.status);
       uint32_t it = 0;
       for (int tile = first_tile; tile < f.total_tiles && ok; tile += tile_step, ++it) {
-        // accumulators are single-buffered here (columns 0..255; 256..511 receive the gamma contractions): the 10 MMAs of a
-        // tile are ~0.6k clk against a ~5k clk epilogue, so there is nothing worth overlapping
-        if (!wait_or_abort(&sb.acc_empty[0], (it & 1) ^ 1, &sb, p.status)) break;
-        if (!wait_or_abort(&fb.a_full, it & 1, &sb, p.status)) break;
+        const uint32_t g = it & 1, par = (it >> 1) & 1;
+        if (!wait_or_abort(&sb.acc_empty[g], par ^ 1, &sb, p.status)) break;
+        trace(p, it, 5);
+        if (!wait_or_abort(&fb.a_full[g], par, &sb, p.status)) break;
+        trace(p, it, 6);
         tcgen05_fence_after();
+        const uint32_t d = tmem + g * 128;
+        const uint32_t ab = a_lo + g * ((2 * 128 * 128) >> 4);
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const uint32_t d = tmem + b * 128;
-          const uint32_t ab = a_lo + b * ((2 * 128 * 128) >> 4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + 2 * k, hi, w_lo + 2 * k, hi, idesc, k);
-          umma_bf16_lohi(d, ab + ((128 * 128) >> 4), hi, w_lo + ((128 * 128) >> 4), hi, idesc, 1);      // k = 64..79
-        }
-        umma_commit(&fb.a_empty);
-        umma_commit(&sb.acc_full[0]);
+        for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + 2 * k, hi, w_lo + 2 * k, hi, idesc, k);
+        umma_bf16_lohi(d, ab + ((128 * 128) >> 4), hi, w_lo + ((128 * 128) >> 4), hi, idesc, 1);      // k = 64..79
+        umma_commit(&fb.a_empty[g]);
+        umma_commit(&sb.acc_full[g]);
       }
     }
   } else {
-    // ===================== epilogue (warps 5..12) =====================
-    // Two independent groups of 4 warps: group 0 takes block 0 of every tile, group 1 block 1, each with its own squares /
-    // staging tile, named barrier and gamma-MMA barrier, so one group computes while the other waits on its gamma MMA or
-    // on its tensor store.
+    // ===================== epilogue (warps 5..12): group g = (warp - 5) / 4 takes the tiles of parity g =====================
     const int q = warp & 3;
     const int grp = (warp - 5) >> 2;
     uint8_t* sq = smem + f.off_sq + grp * (2 * 128 * 128);
@@ -745,17 +752,18 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     uint32_t it = 0, gdn_count = 0;
     bool ok = true;
     for (int tile = first_tile; tile < f.total_tiles && ok; tile += tile_step, ++it) {
+      if ((it & 1) != static_cast<uint32_t>(grp)) continue;
       int img, ty, tx;
       tile_coords(tile, img, ty, tx);
-      if (!__all_sync(0xffffffffu, wait_or_abort(&sb.acc_full[0], it & 1, &sb, p.status))) break;
+      if (!__all_sync(0xffffffffu, wait_or_abort(&sb.acc_full[grp], (it >> 1) & 1, &sb, p.status))) break;
+      if (leader) trace(p, it, 7);
       tcgen05_fence_after();
-      if (tx * 16 + grp * 8 < p.wp)
-        ok = epilogue_block<4, false>(p, &sb, s_bias, s_beta, sq, smem + f.off_gamma, &map_o, tmem + grp * 128, q, lane, 0, leader,
-                                      img, ty * 16, tx * 16 + grp * 8, 0, 0, 0, gdn_count, 0xffffffffu, 8, 1 + grp, gbar,
-                                      tmem + 256 + grp * 128);
+      ok = epilogue_block<4, false>(p, &sb, s_bias, s_beta, sq, smem + f.off_gamma, &map_o, tmem + grp * 128, q, lane, 0, leader,
+                                    img, ty * 16, tx * 8, 0, 0, 0, gdn_count, it, 8, 1 + grp, gbar, tmem + 256 + grp * 128);
+      if (leader) trace(p, it, 14);
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sb.acc_empty[0]);
+      if (lane == 0) mbar_arrive(&sb.acc_empty[grp]);
     }
     if (leader) tma_store_wait_all();
   }
@@ -1125,9 +1133,10 @@ static int launch_first(const nic_conv_desc* d, const void* x, const void* w_pac
   p.status = status_word();
   if (!p.status) return fail(NIC_E_CUDA, "conv bf16: cannot allocate the status word");
   { const char* e = getenv("NIC_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+  p.dbg_times = reinterpret_cast<long long*>(g_trace_buffer);
   FirstParams f{};
   f.x = static_cast<const float*>(x); f.n = d->n; f.hin = d->h_in; f.win = d->w_in;
-  f.tiles_x = (d->w_out + 15) / 16; f.tiles_y = (d->h_out + 15) / 16; f.total_tiles = f.tiles_x * f.tiles_y * d->n;
+  f.tiles_x = (d->w_out + 7) / 8; f.tiles_y = (d->h_out + 15) / 16; f.total_tiles = f.tiles_x * f.tiles_y * d->n;
   f.off_a = 0; f.off_w = 4 * 128 * 128; f.off_gamma = f.off_w + 2 * 128 * 128; f.off_sq = f.off_gamma + 2 * 128 * 128;
   f.off_patch = f.off_sq + 4 * 128 * 128;      // two squares / staging tiles (one per epilogue group)
   const int smem_bytes = f.off_patch + 2 * 3 * kPatchPlane * 4 + 1024 + 64;

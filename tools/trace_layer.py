@@ -16,12 +16,17 @@ cfg = {
     "d2": (nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1), EPI_IGDN, (128, 192), {}),
     "d3": (nn.ConvTranspose2d(128, 3, 5, 2, 2, output_padding=1), EPI_BIAS, (256, 384), dict(out_layout=LAYOUT_NCHW, out_dtype=torch.float32)),
     "ep3": (nn.Conv2d(640, 1152, 1), EPI_BIAS, (32, 48), dict(out_layout=LAYOUT_NCHW, out_dtype=torch.float32)),
+    "l1": (nn.Conv2d(3, 128, 5, 2, 2), EPI_GDN, (512, 768), dict(in_layout=LAYOUT_NCHW)),
 }[which]
 conv, epi, (h, w), kw = cfg
 conv = conv.to(dev)
 g = GDN(128, inverse=(epi == EPI_IGDN)).to(dev) if epi in (EPI_GDN, EPI_IGDN) else None
 op = engine.ConvOp(conv, epi, gdn=g)
 x = torch.randn(B, h, w, conv.in_channels, device=dev).to(torch.bfloat16)
+if which == "l1":
+    x = torch.rand(B, 3, h, w, device=dev)
+    names_l1 = ["P:start", "P:patch_ready", "P:fetched_next", "P:a_empty", "P:built", "M:acc_empty", "M:a_full", "E:acc_full",
+                "e:start", "e:sqdone", "e:synced", "e:gdn", "e:computed", "e:synced2", "E:done"]
 lib = _lib.load()
 lib.nic_debug_set_trace.argtypes = [C.c_void_p]; lib.nic_debug_set_trace.restype = None
 for _ in range(3):
@@ -35,7 +40,7 @@ torch.cuda.synchronize()
 lib.nic_debug_set_trace(None)
 t = buf.cpu().reshape(148, 16, 16)
 print(f"{which}: {e0.elapsed_time(e1)*1000:.1f} us")
-names = ["mma:acc_empty", "mma:first_a", "mma:issued", "epi:acc_full", "epi:done", "A:first", "A:last", "-",
+names = names_l1 if which == "l1" else ["mma:acc_empty", "mma:first_a", "mma:issued", "epi:acc_full", "epi:done", "A:first", "A:last", "-",
          "e0:start", "e0:sqdone", "e0:synced", "e0:gdn", "e0:computed", "e0:synced2"]
 for cta in (0, 77):
     base = int(t[cta, 0][t[cta, 0] > 0].min())
