@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import engine
-from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, PRECISIONS, Q_NOISE, Q_PASSTHRU, Q_ROUND
+from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, MODEL_PRECISIONS, Q_NOISE, Q_PASSTHRU, Q_ROUND
 from .Components import Decoder5x5, Encoder5x5, HyperDecoder5x5, HyperEncoder5x5
 from .ContextModels import ContextModel
 from .EntropyModels import FactorizedEntropyBottleneck, GaussianConditional, GaussianMixtureConditional, gm_likelihood
@@ -35,8 +35,11 @@ class JointAutoregressiveHierarchical(nn.Module):
     """
     latent_channels : int, default=192, number of channels in the bottleneck y (M).
     K : int, default=1.  K == 1 -> mean-scale Gaussian; K > 1 -> mixture of K Gaussians.
-    precision : "fp32" | "bf16x3" | "bf16" arithmetic of the transforms (keyword-only extension; the
-        reference has no such switch).  Defaults to $NIC_PRECISION or "fp32".
+    precision : arithmetic of the transforms (keyword-only extension; the reference has no such switch):
+        "fp32"  CUDA-core FFMA kernels, fp32 operands and accumulation - the parity-grade arm (default, or $NIC_PRECISION);
+        "bf16"  tcgen05 tensor-core kernels, bf16 operands, fp32 accumulation - the throughput arm;
+        "mixed" g_a and h_a (everything upstream of the rounding, i.e. what decides the symbols) in fp32, the entropy
+                path and g_s in bf16: symbols as exact as the fp32 arm at ~3x its speed.
     """
 
     def __init__(self, latent_channels: int = 192, K: int = 1, *, precision: Optional[str] = None):
@@ -59,8 +62,8 @@ class JointAutoregressiveHierarchical(nn.Module):
         self.context_model = ContextModel(latent_channels=self.M)
         self.entropy_parameters = EntropyParameters(latent_channels=self.M, hyper_latent_channels=self.H, K=self.K)
         self.precision = precision or engine.DEFAULT_PRECISION
-        if self.precision not in PRECISIONS:
-            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {self.precision}")
+        if self.precision not in MODEL_PRECISIONS:
+            raise ValueError(f"precision must be one of {MODEL_PRECISIONS}, got {self.precision}")
 
     def forward(self, x: torch.Tensor, training: bool = True, *,
                 noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, lean: bool = False):
@@ -76,7 +79,8 @@ class JointAutoregressiveHierarchical(nn.Module):
         B, _, H, W = x.shape
         if H % 64 or W % 64:
             raise ValueError(f"H and W must be multiples of 64 (four stride-2 stages in g_a, two in h_a); got {H}x{W}")
-        prec = self.precision
+        prec_up = "fp32" if self.precision in ("fp32", "mixed") else "bf16"      # g_a, h_a: upstream of the rounding
+        prec = "fp32" if self.precision == "fp32" else "bf16"                   # h_s, context, entropy parameters, g_s
         adt = engine.act_dtype(prec)
         M, K = self.M, self.K
         x = x.contiguous().float()
@@ -95,19 +99,19 @@ class JointAutoregressiveHierarchical(nn.Module):
             a, h, w, layout = x, H, W, LAYOUT_NCHW
             enc = self.encoder.ops
             for i, op in enumerate(enc):
-                a = op.run(a, B, h, w, prec, in_layout=layout, out_layout=LAYOUT_NHWC,
+                a = op.run(a, B, h, w, prec_up, in_layout=layout, out_layout=LAYOUT_NHWC,
                            out_dtype=torch.float32 if i == len(enc) - 1 else None)
                 h, w = engine.conv_out_hw(op.conv, h, w)
                 layout = LAYOUT_NHWC
             y_nhwc = a                                                     # f32 [B, hy, wy, M]
-            lowp = adt != torch.float32
+            lowp = prec_up != "fp32"
             y, y_in, y_in_nhwc, y_lowp = engine.latent_handoff(y_nhwc, qmode, noise_y, adt, want_lowp=lowp)
 
             # ---- h_a (reads the unquantised y, Models.py:53) ------------------------------------
             a, h, w = (y_lowp if lowp else y_nhwc), hy, wy
             ha = self.hyper_encoder.ops
             for i, op in enumerate(ha):
-                a = op.run(a, B, h, w, prec, out_dtype=torch.float32 if i == len(ha) - 1 else None)
+                a = op.run(a, B, h, w, prec_up, out_dtype=torch.float32 if i == len(ha) - 1 else None)
                 h, w = engine.conv_out_hw(op.conv, h, w)
             z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, qmode, noise_z, adt)
 

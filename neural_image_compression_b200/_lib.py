@@ -20,6 +20,8 @@ PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 EPI_BIAS, EPI_LRELU, EPI_GDN, EPI_IGDN = 0, 1, 2, 3
 Q_ROUND, Q_NOISE, Q_PASSTHRU = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
+# model-level modes: "mixed" = g_a and h_a (everything upstream of the rounding) in fp32, the rest in bf16
+MODEL_PRECISIONS = ("fp32", "bf16", "mixed")
 
 
 class ConvDesc(C.Structure):

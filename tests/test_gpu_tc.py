@@ -218,3 +218,19 @@ def test_model_bf16_training_forward_and_k1():
         bits = -out["logp_y"].double().sum().item() / np.log(2)
         ref_bits = -ref["logp_y"].double().sum().item() / np.log(2)
         assert abs(bits - ref_bits) / ref_bits < 2e-2, (K, bits, ref_bits)
+
+
+def test_model_mixed_precision_symbols_match_fp32_arm_exactly():
+    """precision="mixed": g_a / h_a in fp32 (same kernels as the parity arm) -> y, z and every symbol are bit-identical to
+    the fp32 arm; the bf16 entropy path and g_s then only move likelihoods / x_hat at bf16 tolerances."""
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    x = H.seeded_input((2, 3, 256, 384)).cuda()
+    ref_model = H.seeded_model(128, 3, "calib", precision="fp32").cuda()
+    model = H.seeded_model(128, 3, "calib", precision="mixed").cuda()
+    ref, out = ref_model(x, training=False), model(x, training=False)
+    for k in ("y", "z", "y_in", "z_in"):
+        assert torch.equal(out[k], ref[k]), k
+    r0, r1 = rd_loss(ref, x, 0.005), rd_loss(out, x, 0.005)
+    rel = ((out["p_y"] - ref["p_y"]).abs() / ref["p_y"]).max().item()
+    print(f"mixed: bpp {r1['bpp_total']:.6f} vs {r0['bpp_total']:.6f}, psnr {r1['psnr']:.6f} vs {r0['psnr']:.6f}, max rel p_y err {rel:.2e}")
+    assert abs(r1["bpp_total"] - r0["bpp_total"]) < 1e-3 and abs(r1["psnr"] - r0["psnr"]) < 1e-3
