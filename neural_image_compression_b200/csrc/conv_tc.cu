@@ -3,26 +3,31 @@
 //
 // Formulation (conv_common.cuh): out[pixels, c_out] = sum over taps, c_in of shifted-input . W_tap.
 //
-// One persistent CTA per SM, 7 warps:
-//   warp 0   A producer   TMA (cp.async.bulk.tensor.4d) loads of input PATCHES: for an output tile of 16 rows x 8
-//                         pixels the (16 + halo) x (8 + halo) input pixels of one 64-channel chunk land ONCE in shared
-//                         memory (128-byte swizzle, one 128 B row per pixel); stride-2 convs load the four
-//                         even/odd "planes" of the input with TMA element strides of 2.  Conv zero padding is the
-//                         TMA out-of-bounds fill.
-//   warp 1   B producer   TMA loads of the [c_out tile x 64] weight slab of each (tap, chunk) into a ring.
-//   warp 2   MMA issuer   one thread issues tcgen05.mma (M = 128, N = c_out tile, K = 16) for every tap straight
-//                         from the patch: the A descriptor of tap (dy, dx) starts at patch pixel (dy, dx) and walks
-//                         16 groups of 8 consecutive pixels with a stride of one patch row - no im2col copy,
-//                         every input byte is read from L2 once per chunk instead of once per tap
-//                         (measured basis: tools/tc_probe.cu T2/T2b, profiles/r1_tc_probe.txt).
-//   warps 3-6 epilogue    tcgen05.ld the accumulator (double-buffered in TMEM so the next tile's MMAs overlap),
-//                         add bias, LeakyReLU, or GDN / IGDN: the squares go back to shared memory as a bf16
-//                         K-major tile, a second tcgen05.mma contracts them with gamma into another TMEM region and
-//                         the epilogue applies x * rsqrt(beta + .) (or sqrt) - the GDN of Components.py:11-15, 40-44
-//                         never touches HBM.
+// conv_tc_kernel - one persistent CTA per SM, 11 warps:
+//   warp 0   A producer   TMA (cp.async.bulk.tensor.4d) loads of input PATCHES: for an output tile of 16 x 16 pixels (two
+//                         M = 128 blocks of 16 rows x 8 pixels side by side) the (16 + halo) x (16 + halo) input pixels of
+//                         one 64-channel chunk land ONCE in shared memory (128-byte swizzle, one 128 B row per pixel);
+//                         stride-2 convs load the four even/odd "planes" of the input with TMA element strides of 2.
+//                         Conv zero padding is the TMA out-of-bounds fill.
+//   warp 1   B producer   TMA loads of the [c_out tile x 64] weight slab of each (tap, chunk) into a 4-8 deep ring (both
+//                         blocks of the tile share it); layers with c_out <= 16 keep ALL their slabs resident instead.
+//   warp 2   MMA issuer   the warp walks the loop uniformly (operands in uniform registers), one elected lane issues
+//                         tcgen05.mma (M = 128, N = c_out tile, K = 16) for every tap straight from the patch: the A
+//                         descriptor of tap (dy, dx) starts at patch pixel (dy, dx) and walks 16 groups of 8 consecutive
+//                         pixels with a stride of one patch row - no im2col copy, every input byte is read from L2 once
+//                         per chunk instead of once per tap (basis: tools/tc_probe.cu T2/T2b, profiles/r1_tc_probe.txt).
+//   warps 3-10 epilogue   tcgen05.ld the accumulator (double-buffered in TMEM: 4 x 128 columns, so the next tile's MMAs
+//                         overlap), add bias, LeakyReLU, or GDN / IGDN: x stays in registers, its squares go to shared
+//                         memory as a bf16 K-major tile, a second tcgen05.mma against the resident gamma OVERWRITES the
+//                         accumulator in place and the epilogue applies x * rsqrt(beta + .) (or sqrt) - the GDN of
+//                         Components.py:11-15, 40-44 never touches HBM.  bf16 NHWC outputs are staged in shared memory
+//                         and leave through TMA tensor stores (element strides 2 interleave transposed-conv phases).
+// Special forms: ConvTranspose2d = stride^2 phase convs of a stride-1 kernel; ConvTranspose2d(128 -> 3) = ONE 3x3 conv to
+// 4 x 3 sub-pixel channels (N = 16); 1x1 convs walk a flat pixel list.
 //
-// Activations are NHWC bf16 between layers (c_in a multiple of 64).  The 3-channel first layer runs its
-// 75-deep contraction on the CUDA cores (conv_simt.cu) and only its GDN comes here (1x1 identity slab).
+// conv_first_tc_kernel - Conv2d(3, 128, 5, s2) + GDN from the NCHW fp32 image (K = 75: im2col built by producer warps).
+//
+// Activations are NHWC bf16 between layers (c_in a multiple of 64).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -388,14 +393,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __shared__ TcBarriers sb;
   __shared__ float s_bias[kMaxCout];
   __shared__ float s_beta[128];
-  __shared__ uint32_t s_tap_aoff[kMaxTaps][2];   // (A start of tap t, block b) - (slot base), in 16-byte units
-  __shared__ int s_tap_brow[kMaxTaps];           // weight row of the tap's slab (TMA coordinate / resident tile index)
-  if (threadIdx.x < kMaxTaps) {
-    const int t = threadIdx.x;
-    for (int b = 0; b < 2; ++b)
-      s_tap_aoff[t][b] = static_cast<uint32_t>(((p.taps[t].roff + p.blk_roff[b]) * p.pw_cols + p.taps[t].coff + p.blk_coff[b]) * 128) >> 4;
-    s_tap_brow[t] = p.taps[t].slab;
-  }
+  __shared__ int s_tap_brow[kMaxTaps];           // weight row of the tap's slab (TMA coordinate of the B producer)
+  if (threadIdx.x < kMaxTaps) s_tap_brow[threadIdx.x] = p.taps[threadIdx.x].slab;
   for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = p.bias[p.bias_mod ? i % p.bias_mod : i];
   if (p.beta) for (int i = threadIdx.x; i < 128; i += kThreads) s_beta[i] = p.beta[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -552,13 +551,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ===================== epilogue (warps 3..10) =====================
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
-    const int row = q * 32 + lane;                // accumulator row = pixel of the block
-    const int g = row >> 3, c8 = row & 7;
     uint8_t* sq = smem + p.off_sq;
     uint32_t tcount = 0, gdn_count = 0;
     bool ok = true;
-    const int ncg = (p.nb + 31) / 32;
-    const bool igdn = p.epilogue == NIC_EPI_IGDN;
     for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step, ++tcount) {
       int ntile, phase, img, ty, tx;
       decode_tile(p, tile, ntile, phase, img, ty, tx);
@@ -567,7 +562,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t buf = tcount & 1;
       if (!__all_sync(0xffffffffu, wait_or_abort(&sb.acc_full[buf], (tcount >> 1) & 1, &sb, p.status))) break;
       tcgen05_fence_after();
-      const int cbase = ntile * p.nb;
       for (int b = 0; b < nblk && ok; ++b)
         ok = epilogue_block<kEpiWarps>(p, &sb, s_bias, s_beta, sq, smem + p.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane,
                                        (warp - 3) >> 2, warp == 3 && lane == 0, img, ty * p.tile_h + p.blk_roff[b],
@@ -590,7 +584,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // K = 75 is too shallow for a TMA-fed pipeline, so four producer warps build the [128 pixel x 80] bf16 A operand of each
 // block in shared memory (im2col of a 35 x 35 x 3 image patch, k = (kh * 5 + kw) * 3 + c, zero padded to 80), one thread
 // issues 5 tcgen05.mma per block against the resident [128 x 80] weights, and the shared epilogue applies the fused GDN and
-// stores the bf16 NHWC tile with TMA.  9 warps: 0-3 producers, 4 MMA issuer / weight loader, 5-8 epilogue.
+// stores the bf16 NHWC tile with TMA.  13 warps: 0-3 producers, 4 MMA issuer / weight loader, 5-12 epilogue (two groups).
 // ---------------------------------------------------------------------------------------------
 constexpr int kFirstThreads = 160 + 8 * 32;
 constexpr int kPatchW = 20, kPatchH = 35, kPatchCols = 19, kPatchPlane = kPatchH * kPatchW;   // fp32 patch rows padded to 20 floats
