@@ -288,6 +288,7 @@ def main():
     roofline_lik = {"bound": "hbm", "kernel": "gm_likelihood_kernel<K=3, full>", "unit": "GB/s", "peak": peaks["hbm"],
                     "bytes_per_y_element": 88, "peak_source": f"{peaks['src']} copy bandwidth", **lik}
 
+    assert lib.nic_pipeline_status() == 0, "a tensor-core kernel aborted on an expired pipeline wait: numbers invalid"
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_reference_arm(2, 3)
         line = {

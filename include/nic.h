@@ -97,6 +97,12 @@ const char* nic_last_error(void);
 int nic_check_device(void);
 /* number of CUDA kernels this library has launched in this process (all threads) */
 uint64_t nic_launch_count(void);
+/*
+ * The tensor-core kernels bound every mbarrier wait; if one ever expires (a pipeline bug, never expected) the kernel
+ * gives up instead of hanging the GPU and raises a device flag.  This reads and clears that flag: 0 = every kernel since
+ * the last call ran to completion, 1 = at least one aborted (its output is invalid).  Synchronises the device.
+ */
+int nic_pipeline_status(void);
 
 /* ---- weight preparation (once per load_state_dict; derived caches, never saved) ---------- */
 

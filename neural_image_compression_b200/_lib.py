@@ -38,6 +38,7 @@ SIGNATURES = {
     "nic_last_error": (C.c_char_p, []),
     "nic_check_device": (C.c_int, []),
     "nic_launch_count": (C.c_uint64, []),
+    "nic_pipeline_status": (C.c_int, []),
     "nic_packed_weight_elems": (_sz, [C.POINTER(ConvDesc)]),
     "nic_pack_conv_weight": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
     "nic_pack_gdn": (C.c_int, [_i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp]),

@@ -941,6 +941,16 @@ inline bool small_cin(const nic_conv_desc* d) { return d->c_in < 64; }
 
 void set_trace_buffer(void* p) { g_trace_buffer = p; }
 
+int read_and_clear_status() {
+  int* d = status_word();
+  if (!d) return 0;
+  int h = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  if (cudaMemcpy(&h, d, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+  if (h) cudaMemset(d, 0, sizeof(int));
+  return h ? 1 : 0;
+}
+
 // Packed layout (bf16 elements):
 //   c_in >= 64 : [tap][c_out padded to a multiple of nb][c_in]
 //   c_in  = 3  : [c_out = 128][k padded to 128], k = (kh * kw_size + kw) * 3 + c   (first layer, conv_first_tc_kernel)
@@ -1170,3 +1180,5 @@ int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, con
 // Debug hook for tools/trace_layer.py (not declared in include/nic.h): a device buffer of 148 * 16 * 8 int64 that
 // conv_tc_kernel fills with clock64 stamps of its pipeline roles; NULL switches tracing off.
 extern "C" void nic_debug_set_trace(void* device_buffer) { nic::set_trace_buffer(device_buffer); }
+
+extern "C" int nic_pipeline_status(void) { return nic::read_and_clear_status(); }
