@@ -44,13 +44,20 @@ enum {
 
 /* tensor layouts / element types understood by the conv engine */
 enum { NIC_LAYOUT_NCHW = 0, NIC_LAYOUT_NHWC = 1 };
-enum { NIC_DT_F32 = 0, NIC_DT_BF16 = 1 };
+enum {
+  NIC_DT_F32 = 0,
+  NIC_DT_BF16 = 1,
+  NIC_DT_BF16X2 = 2   /* fp32 value carried as a bf16 pair: an NHWC tensor with 2*c channels, [hi(c) | lo(c)], hi = bf16(v),
+                         lo = bf16(v - hi).  Activation format of the NIC_PREC_BF16X3 arm.                              */
+};
 
 /* arithmetic of the contraction */
 enum {
   NIC_PREC_FP32 = 0,   /* CUDA-core FFMA, fp32 operands and accumulation (parity grade)           */
   NIC_PREC_BF16 = 1,   /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulation in TMEM          */
-  NIC_PREC_BF16X3 = 2  /* tcgen05, operands split hi+lo in bf16, 3 MMAs per product (fp32 grade)   */
+  NIC_PREC_BF16X3 = 2  /* tcgen05, both operands split hi + lo in bf16 and contracted as ONE K-concatenated conv
+                          [A_hi | A_lo | A_hi] . [W_hi | W_hi | W_lo] in a single fp32 TMEM accumulation (fp32 grade,
+                          3x the MMA work); GDN / IGDN and the 3-channel first layer run on the fp32 arm.           */
 };
 
 /* fused epilogues */
@@ -113,13 +120,14 @@ size_t nic_packed_weight_elems(const nic_conv_desc* d);
  * (Components.py:10-16), ConvTranspose2d [c_in, c_out, kh, kw] (Components.py:39-45),
  * masked taps dropped when d->mask_a (the reference zeroes them in place, ContextModels.py:19).
  * fp32: [tap][c_in][c_out] f32.  bf16: [tap][c_out][c_in] bf16 (K-major B operand);
- * bf16x3: hi block followed by lo block.
+ * bf16x3: [tap][c_out][3 c_in] bf16 = [W_hi | W_hi | W_lo] (first layer: the fp32 pack).
+ * nic_packed_weight_elems counts 2-byte elements for the two tensor-core precisions.
  */
 int nic_pack_conv_weight(const nic_conv_desc* d, const float* w_ref, void* w_packed, void* stream);
 /*
  * compressai GDN reparametrisation (oracle/gdn.py):
  *   beta_eff = max(beta, sqrt(beta_min + 2^-36))^2 - 2^-36,  gamma_eff = max(gamma, 2^-18)^2 - 2^-36.
- * gamma_packed: fp32 -> [c_in(j)][c_out(i)] f32; bf16 -> [i][j] bf16 (hi, then lo when bf16x3).
+ * gamma_packed: fp32 and bf16x3 -> [c_in(j)][c_out(i)] f32; bf16 -> [i][j] bf16.
  */
 int nic_pack_gdn(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw,
                  float* beta_eff, void* gamma_packed, int32_t precision, void* stream);
@@ -148,12 +156,13 @@ int nic_gdn_fwd(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, int3
  * engine's layout), writes the reference-layout copy `v_nchw` (dict entries 'y' / 'z'),
  * the quantised / noised tensor `v_in_nchw` ('y_in' / 'z_in') and the engine-layout copy
  * `v_in_nhwc` (dtype out_dtype) that h_s / the context model / g_s consume.
- * v_nhwc_bf16 (optional) receives a bf16 NHWC copy of the UNquantised v (h_a reads y, Models.py:53).
+ * v_nhwc_lowp (optional) receives an NHWC copy of the UNquantised v (h_a reads y, Models.py:53) in lowp_dtype
+ * (NIC_DT_BF16, or NIC_DT_BF16X2 = [hi | lo] with 2c channels).
  * noise_nchw is read only for NIC_Q_NOISE.  Any output pointer may be NULL.
  */
 int nic_latent_handoff(const float* v_nhwc, int32_t n, int32_t c, int32_t h, int32_t w, int32_t qmode,
                        const float* noise_nchw, float* v_nchw, float* v_in_nchw, void* v_in_nhwc,
-                       int32_t out_dtype, void* v_nhwc_bf16, void* stream);
+                       int32_t out_dtype, void* v_nhwc_lowp, int32_t lowp_dtype, void* stream);
 
 /* ---- likelihoods --------------------------------------------------------------------------- */
 

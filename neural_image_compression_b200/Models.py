@@ -39,7 +39,9 @@ class JointAutoregressiveHierarchical(nn.Module):
         "fp32"  CUDA-core FFMA kernels, fp32 operands and accumulation - the parity-grade arm (default, or $NIC_PRECISION);
         "bf16"  tcgen05 tensor-core kernels, bf16 operands, fp32 accumulation - the throughput arm;
         "mixed" g_a and h_a (everything upstream of the rounding, i.e. what decides the symbols) in fp32, the entropy
-                path and g_s in bf16: symbols as exact as the fp32 arm at ~3x its speed.
+                path and g_s in bf16: symbols identical to the fp32 arm at ~2.5x its speed;
+        "bf16x3" g_a and h_a on the tensor cores with both operands split into bf16 hi + lo and contracted as one
+                K-concatenated convolution (fp32 grade: ~1e-5 relative on y), the rest in bf16.
     """
 
     def __init__(self, latent_channels: int = 192, K: int = 1, *, precision: Optional[str] = None):
@@ -79,7 +81,7 @@ class JointAutoregressiveHierarchical(nn.Module):
         B, _, H, W = x.shape
         if H % 64 or W % 64:
             raise ValueError(f"H and W must be multiples of 64 (four stride-2 stages in g_a, two in h_a); got {H}x{W}")
-        prec_up = "fp32" if self.precision in ("fp32", "mixed") else "bf16"      # g_a, h_a: upstream of the rounding
+        prec_up = {"fp32": "fp32", "mixed": "fp32", "bf16x3": "bf16x3", "bf16": "bf16"}[self.precision]   # g_a, h_a
         prec = "fp32" if self.precision == "fp32" else "bf16"                   # h_s, context, entropy parameters, g_s
         adt = engine.act_dtype(prec)
         M, K = self.M, self.K
@@ -105,7 +107,8 @@ class JointAutoregressiveHierarchical(nn.Module):
                 layout = LAYOUT_NHWC
             y_nhwc = a                                                     # f32 [B, hy, wy, M]
             lowp = prec_up != "fp32"
-            y, y_in, y_in_nhwc, y_lowp = engine.latent_handoff(y_nhwc, qmode, noise_y, adt, want_lowp=lowp)
+            y, y_in, y_in_nhwc, y_lowp = engine.latent_handoff(y_nhwc, qmode, noise_y, adt, want_lowp=lowp,
+                                                               lowp_pair=prec_up == "bf16x3")
 
             # ---- h_a (reads the unquantised y, Models.py:53) ------------------------------------
             a, h, w = (y_lowp if lowp else y_nhwc), hy, wy

@@ -15,13 +15,14 @@ _i32, _i64, _f32, _vp, _sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_si
 
 # enums of include/nic.h
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
-DT_F32, DT_BF16 = 0, 1
+DT_F32, DT_BF16, DT_BF16X2 = 0, 1, 2
 PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 EPI_BIAS, EPI_LRELU, EPI_GDN, EPI_IGDN = 0, 1, 2, 3
 Q_ROUND, Q_NOISE, Q_PASSTHRU = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
 # model-level modes: "mixed" = g_a and h_a (everything upstream of the rounding) in fp32, the rest in bf16
-MODEL_PRECISIONS = ("fp32", "bf16", "mixed")
+#                     "bf16x3" = g_a and h_a on the tensor cores with hi/lo-split operands (fp32 grade), the rest in bf16
+MODEL_PRECISIONS = ("fp32", "bf16", "mixed", "bf16x3")
 
 
 class ConvDesc(C.Structure):
@@ -45,7 +46,7 @@ SIGNATURES = {
     "nic_conv_workspace_bytes": (_sz, [C.POINTER(ConvDesc)]),
     "nic_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nic_gdn_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
-    "nic_latent_handoff": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "nic_latent_handoff": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp]),
     "nic_partials_per_image": (_i32, []),
     "nic_gm_likelihood_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nic_gm_pmf_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -120,7 +120,9 @@ struct SimtParams {
   long ys_n, ys_c, ys_h, ys_w;
   int epilogue;       // NIC_EPI_*; GDN / IGDN here mean "x * rsqrt/sqrt(acc + bias)" with x read back from the input
   int a_square;       // square the A operand on load (GDN's x^2)
-  int out_bf16;       // store the result as bf16 (hand-off to the tensor-core arm); strides are still in elements
+  int out_bf16;       // 1: store the result as bf16 (hand-off to the tensor-core arm); strides are still in elements
+                      // 2: store it as a bf16 pair, hi at channel c and lo at channel c + split_off (NIC_DT_BF16X2)
+  long split_off;     // element offset of the lo half (= c_out * ys_c)
   TapTable tt;
 };
 
@@ -314,7 +316,12 @@ conv_simt_kernel(const SimtParams p) {
       }
       if (p.out_bf16) {
 #pragma unroll
-        for (int j = 0; j < HN; ++j) if (cbase + j < p.cout) yrow_b[(cbase + j) * p.ys_c] = __float2bfloat16_rn(v[j]);
+        for (int j = 0; j < HN; ++j)
+          if (cbase + j < p.cout) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+            yrow_b[(cbase + j) * p.ys_c] = hi;
+            if (p.out_bf16 == 2) yrow_b[(cbase + j) * p.ys_c + p.split_off] = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
+          }
       } else if (HN == 4 && p.ys_c == 1 && cbase + 3 < p.cout && ((reinterpret_cast<uintptr_t>(yrow + cbase) & 15) == 0)) {
         *reinterpret_cast<float4*>(yrow + cbase) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
@@ -375,13 +382,15 @@ int conv_fwd_fp32_ex(const nic_conv_desc* d, const void* x, const void* w_packed
 int conv_fwd_fp32(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                   const void* gdn_gamma, const float* gdn_beta, void* y, void* workspace, size_t workspace_bytes,
                   cudaStream_t st) {
-  if (d->in_dtype != NIC_DT_F32 || d->out_dtype != NIC_DT_F32) return fail(NIC_E_UNSUPPORTED, "conv fp32: f32 tensors only");
+  const bool split_out = d->out_dtype == NIC_DT_BF16X2;
+  if (d->in_dtype != NIC_DT_F32 || (d->out_dtype != NIC_DT_F32 && !split_out)) return fail(NIC_E_UNSUPPORTED, "conv fp32: f32 in, f32 or bf16-pair out");
+  if (split_out && (d->out_layout != NIC_LAYOUT_NHWC || d->out_c_total != 0)) return fail(NIC_E_UNSUPPORTED, "conv fp32: bf16-pair output is plain NHWC");
   SimtParams p{};
   if (int rc = build_tap_table(d, &p.tt)) return rc;
   p.n = d->n; p.cin = d->c_in; p.hin = d->h_in; p.win = d->w_in; p.cout = d->c_out; p.hout = d->h_out; p.wout = d->w_out;
   p.x = static_cast<const float*>(x); p.w = static_cast<const float*>(w_packed); p.bias = bias;
   set_strides(d->in_layout, d->c_in, d->h_in, d->w_in, &p.xs_n, &p.xs_c, &p.xs_h, &p.xs_w);
-  const int ctot = d->out_c_total ? d->out_c_total : d->c_out;
+  const int ctot = split_out ? 2 * d->c_out : (d->out_c_total ? d->out_c_total : d->c_out);
   long ys_n, ys_c, ys_h, ys_w;
   set_strides(d->out_layout, ctot, d->h_out, d->w_out, &ys_n, &ys_c, &ys_h, &ys_w);
   float* yout = static_cast<float*>(y) + d->out_c_offset * ys_c;
@@ -389,6 +398,7 @@ int conv_fwd_fp32(const nic_conv_desc* d, const void* x, const void* w_packed, c
   if (!gdn) {
     p.y = yout; p.ys_n = ys_n; p.ys_c = ys_c; p.ys_h = ys_h; p.ys_w = ys_w;
     p.epilogue = d->epilogue; p.a_square = 0;
+    if (split_out) { p.out_bf16 = 2; p.split_off = d->c_out; }
     return launch_simt(p, st);
   }
   // conv + bias into the workspace (NHWC f32), then the GDN contraction as a 1x1 tap over its squares
@@ -409,6 +419,22 @@ int conv_fwd_fp32(const nic_conv_desc* d, const void* x, const void* w_packed, c
   g.xs_n = p.ys_n; g.xs_c = p.ys_c; g.xs_h = p.ys_h; g.xs_w = p.ys_w;
   g.ys_n = ys_n; g.ys_c = ys_c; g.ys_h = ys_h; g.ys_w = ys_w;
   g.epilogue = d->epilogue; g.a_square = 1;
+  if (split_out) { g.out_bf16 = 2; g.split_off = d->c_out; }
+  return launch_simt(g, st);
+}
+
+// GDN / IGDN of an fp32 NHWC tensor into a bf16-pair NHWC tensor (second half of a bf16x3 GDN layer)
+int gdn_fwd_fp32_split(const float* x, int n, int c, int h, int w, int inverse, const float* gamma, const float* beta, void* y,
+                       cudaStream_t st) {
+  SimtParams g{};
+  nic_conv_desc gd{};
+  gd.n = n; gd.c_in = gd.c_out = c; gd.h_in = gd.h_out = h; gd.w_in = gd.w_out = w; gd.kh = gd.kw = 1; gd.stride = 1;
+  if (int rc = build_tap_table(&gd, &g.tt)) return rc;
+  g.n = n; g.cin = g.cout = c; g.hin = g.hout = h; g.win = g.wout = w;
+  g.x = x; g.w = gamma; g.bias = beta; g.y = static_cast<float*>(y);
+  set_strides(NIC_LAYOUT_NHWC, c, h, w, &g.xs_n, &g.xs_c, &g.xs_h, &g.xs_w);
+  set_strides(NIC_LAYOUT_NHWC, 2 * c, h, w, &g.ys_n, &g.ys_c, &g.ys_h, &g.ys_w);
+  g.epilogue = inverse ? NIC_EPI_IGDN : NIC_EPI_GDN; g.a_square = 1; g.out_bf16 = 2; g.split_off = c;
   return launch_simt(g, st);
 }
 
@@ -432,7 +458,7 @@ int gdn_fwd_fp32(const float* x, int n, int c, int h, int w, int layout, int inv
 __global__ void __launch_bounds__(256)
 latent_handoff_kernel(const float* __restrict__ v, int n, int c, int h, int w, int qmode, const float* __restrict__ noise,
                       float* __restrict__ v_nchw, float* __restrict__ vin_nchw, void* __restrict__ vin_nhwc, int out_dtype,
-                      __nv_bfloat16* __restrict__ v_lowp) {
+                      __nv_bfloat16* __restrict__ v_lowp, int lowp_dtype) {
   // 32 x 32 (pixel x channel) transpose tiles through shared memory: coalesced on both layouts
   __shared__ float tile[32][33];
   __shared__ float tile_q[32][33];
@@ -445,7 +471,15 @@ latent_handoff_kernel(const float* __restrict__ v, int n, int c, int h, int w, i
     float val = 0.f;
     if (pix < hw && ch < c) {
       val = v[(static_cast<long>(img) * hw + pix) * c + ch];
-      if (v_lowp) v_lowp[(static_cast<long>(img) * hw + pix) * c + ch] = __float2bfloat16_rn(val);
+      if (v_lowp) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+        if (lowp_dtype == NIC_DT_BF16X2) {
+          v_lowp[(static_cast<long>(img) * hw + pix) * 2 * c + ch] = hi;
+          v_lowp[(static_cast<long>(img) * hw + pix) * 2 * c + c + ch] = __float2bfloat16_rn(val - __bfloat162float(hi));
+        } else {
+          v_lowp[(static_cast<long>(img) * hw + pix) * c + ch] = hi;
+        }
+      }
     }
     tile[r][tx] = val;
   }
@@ -492,7 +526,7 @@ int nic_gdn_fwd(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, int3
 
 int nic_latent_handoff(const float* v_nhwc, int32_t n, int32_t c, int32_t h, int32_t w, int32_t qmode,
                        const float* noise_nchw, float* v_nchw, float* v_in_nchw, void* v_in_nhwc,
-                       int32_t out_dtype, void* v_nhwc_bf16, void* stream) {
+                       int32_t out_dtype, void* v_nhwc_lowp, int32_t lowp_dtype, void* stream) {
   if (int rc = nic_check_device()) return rc;
   if (n < 0 || c < 1 || h < 1 || w < 1) return fail(NIC_E_BADSHAPE, "latent_handoff: n=%d c=%d h=%d w=%d", n, c, h, w);
   if (qmode == NIC_Q_NOISE && !noise_nchw) return fail(NIC_E_BADSHAPE, "latent_handoff: NIC_Q_NOISE needs noise");
@@ -500,7 +534,7 @@ int nic_latent_handoff(const float* v_nhwc, int32_t n, int32_t c, int32_t h, int
   if (n > 65535) return fail(NIC_E_BADSHAPE, "latent_handoff: n=%d > 65535", n);
   dim3 grid((h * w + 31) / 32, (c + 31) / 32, n);
   latent_handoff_kernel<<<grid, 256, 0, as_stream(stream)>>>(v_nhwc, n, c, h, w, qmode, noise_nchw, v_nchw, v_in_nchw, v_in_nhwc, out_dtype,
-                                                                   static_cast<__nv_bfloat16*>(v_nhwc_bf16));
+                                                                   static_cast<__nv_bfloat16*>(v_nhwc_lowp), lowp_dtype);
   return check_launch("latent_handoff_kernel");
 }
 

@@ -40,6 +40,9 @@ using namespace tc;
 
 void set_trace_buffer(void* p);
 // conv_simt.cu
+int conv_fwd_fp32(const nic_conv_desc*, const void*, const void*, const float*, const void*, const float*, void*, void*, size_t, cudaStream_t);
+int gdn_fwd_fp32(const float* x, int n, int c, int h, int w, int layout, int inverse, const float* gamma, const float* beta, float* y, cudaStream_t st);
+int gdn_fwd_fp32_split(const float* x, int n, int c, int h, int w, int inverse, const float* gamma, const float* beta, void* y, cudaStream_t st);
 int conv_fwd_fp32_ex(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y, int out_bf16_nhwc,
                      cudaStream_t st);
 
@@ -70,7 +73,9 @@ struct TcParams {
   int blk_roff[2], blk_coff[2];                // position of block b inside the tile (pixels)
   int tile_h, tile_w;                          // output pixels per tile
   int tiles_x, tiles_y, n_ntiles, total_tiles;
-  int nchunks;                                 // cin / 64
+  int nchunks;                                 // K chunks of 64 (cin / 64; 3 cin / 64 in the bf16x3 arm)
+  int a_chunk_mod;                             // input channel chunk of K chunk c is c % a_chunk_mod (bf16x3: [hi | lo | hi again])
+  int split_out;                               // bf16-pair output: hi to channels [0, cout), lo to [cout, 2 cout)
   int ph_rows, pw_cols;                        // patch rows / cols (pixels)
   int slot_bytes, nsa, nsb;
   int b_resident;                              // all weight slabs of the layer stay in shared memory (small c_out)
@@ -356,18 +361,35 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
     const int per = (NW == 8) ? (ncg + 1) / 2 : ncg;
     const int first = (NW == 8) ? hs * per : 0;
     const int last = (first + per < ncg) ? first + per : ncg;
-    for (int cg = first; cg < last; ++cg) {
-      float v[32];
-      tmem_ld_32x32(acc_addr + cg * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = cbase + cg * 32 + j;
-        float x = v[j] + (c < p.cout ? s_bias[c] : 0.f);
-        if (p.epilogue == NIC_EPI_LRELU) x = x > 0.f ? x : 0.01f * x;
-        v[j] = x;
+    const int npass = p.split_out ? 2 : 1;         // bf16-pair output: one staging + store round for hi, one for lo
+    for (int pass = 0; pass < npass; ++pass) {
+      if (pass == 1) {
+        // hand the staging tile from the hi round to the lo round
+        fence_proxy_async_smem();
+        epi_sync();
+        if (leader) {
+          const int wc = ox0 * p.out_stride + px, hc = oy0 * p.out_stride + py;
+          for (int h = 0; h < 2; ++h)
+            if (h * 64 < nvalid_c) tma_store_4d(map_o_ptr, sq + h * (128 * 128), p.out_c_offset + cbase + h * 64, wc, hc, img);
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+        epi_sync();
       }
-      emit_group(cg, v);
+      for (int cg = first; cg < last; ++cg) {
+        float v[32];
+        tmem_ld_32x32(acc_addr + cg * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = cbase + cg * 32 + j;
+          float x = v[j] + (c < p.cout ? s_bias[c] : 0.f);
+          if (p.epilogue == NIC_EPI_LRELU) x = x > 0.f ? x : 0.01f * x;
+          if (pass == 1) x = x - __bfloat162float(__float2bfloat16_rn(x));
+          v[j] = x;
+        }
+        emit_group(cg, v);
+      }
     }
   }
   if (leader) trace(p, trace_tile, trace_base + 4);
@@ -377,8 +399,9 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
     if (leader) trace(p, trace_tile, trace_base + 5);
     if (leader && !(p.dbg & 2)) {
       const int wc = ox0 * p.out_stride + px, hc = oy0 * p.out_stride + py;
+      const int lo_off = p.split_out ? p.cout : 0;
       for (int h = 0; h < 2; ++h)
-        if (h * 64 < nvalid_c) tma_store_4d(map_o_ptr, sq + h * (128 * 128), p.out_c_offset + cbase + h * 64, wc, hc, img);
+        if (h * 64 < nvalid_c) tma_store_4d(map_o_ptr, sq + h * (128 * 128), p.out_c_offset + lo_off + cbase + h * 64, wc, hc, img);
       tma_store_commit();
     }
   }
@@ -436,7 +459,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_expect_tx(&sb.a_full[s], bytes);
             const int w0 = p.in_stride * (tx * p.tile_w + ph.plane_dxmin[pl]) + ph.plane_pw[pl];
             const int h0 = p.in_stride * (ty * p.tile_h + ph.plane_dymin[pl]) + ph.plane_ph[pl];
-            tma_load_4d(smem + p.off_a + s * p.slot_bytes, &map_a, &sb.a_full[s], chunk * 64, w0, h0, img);
+            tma_load_4d(smem + p.off_a + s * p.slot_bytes, &map_a, &sb.a_full[s], (chunk % p.a_chunk_mod) * 64, w0, h0, img);
           }
         }
       }
@@ -914,6 +937,27 @@ int check_first_layer(const nic_conv_desc* d) {
   return NIC_OK;
 }
 
+// bf16x3: [tap][c_out padded][3 c_in] = [W_hi | W_hi | W_lo], W_hi = bf16(W), W_lo = bf16(W - W_hi)
+__global__ void pack_weight_x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin, int cout, int cout_pad,
+                                      int kh, int kw, int transposed, TapTable tt) {
+  const long total = static_cast<long>(tt.ntaps) * cout_pad * 3 * cin;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % (3 * cin));
+    const int co = static_cast<int>((i / (3 * cin)) % cout_pad);
+    const int t = static_cast<int>(i / (static_cast<long>(3) * cin * cout_pad));
+    const int ci = k % cin, part = k / cin;
+    float v = 0.f;
+    if (co < cout) {
+      const int a = tt.kh[t], b = tt.kw[t];
+      const long src = transposed ? ((static_cast<long>(ci) * cout + co) * kh + a) * kw + b
+                                  : ((static_cast<long>(co) * cin + ci) * kh + a) * kw + b;
+      v = w[src];
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[i] = (part < 2) ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
 __global__ void pack_gdn_bf16_kernel(int c, float beta_bound, float gamma_bound, float pedestal, const float* __restrict__ beta,
                                      const float* __restrict__ gamma, float* __restrict__ beta_eff, __nv_bfloat16* __restrict__ gamma_out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c * c; i += gridDim.x * blockDim.x) {
@@ -955,6 +999,11 @@ int read_and_clear_status() {
 //   c_in >= 64 : [tap][c_out padded to a multiple of nb][c_in]
 //   c_in  = 3  : [c_out = 128][k padded to 128], k = (kh * kw_size + kw) * 3 + c   (first layer, conv_first_tc_kernel)
 size_t packed_weight_elems_tc(const nic_conv_desc* d, const TapTable& tt) {
+  if (d->precision == NIC_PREC_BF16X3) {
+    if (small_cin(d)) return static_cast<size_t>(tt.ntaps) * d->c_in * d->c_out * 2;       // the fp32 pack, counted in 2-byte units
+    const int cp = (d->c_out + 127) / 128 * 128;
+    return static_cast<size_t>(tt.ntaps) * cp * 3 * d->c_in;
+  }
   if (small_cin(d)) return static_cast<size_t>(128) * 128;
   if (subpixel_form(d)) return static_cast<size_t>(9) * 16 * d->c_in;
   const int nb = nb_for(d->c_out);
@@ -965,7 +1014,22 @@ size_t packed_weight_elems_tc(const nic_conv_desc* d, const TapTable& tt) {
 __global__ void pack_weight_f32_kernel(const float*, float*, int, int, int, int, int, TapTable);
 
 int pack_weight_tc(const nic_conv_desc* d, const TapTable& tt, const float* w_ref, void* w_packed, cudaStream_t st) {
-  if (d->precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "pack_conv_weight: precision %d is not built (fp32 and bf16 are)", d->precision);
+  if (d->precision == NIC_PREC_BF16X3) {
+    if (small_cin(d)) {                    // first layer runs on the fp32 arm
+      const long total = static_cast<long>(tt.ntaps) * d->c_in * d->c_out;
+      pack_weight_f32_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w_ref, static_cast<float*>(w_packed), d->c_in, d->c_out,
+                                                                                  d->kh, d->kw, d->transposed, tt);
+      return check_launch("pack_weight_f32_kernel");
+    }
+    if (d->c_in % 64 || d->transposed) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: c_in must be a multiple of 64, Conv2d only (g_a / h_a layers)");
+    const int cp = (d->c_out + 127) / 128 * 128;
+    const long total = static_cast<long>(tt.ntaps) * cp * 3 * d->c_in;
+    const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    pack_weight_x3_kernel<<<blocks, 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed), d->c_in, d->c_out, cp, d->kh, d->kw,
+                                                  d->transposed, tt);
+    return check_launch("pack_weight_x3_kernel");
+  }
+  if (d->precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "pack_conv_weight: precision %d", d->precision);
   if (small_cin(d)) {
     if (int rc = check_first_layer(d)) return rc;
     pack_first_bf16_kernel<<<64, 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed));
@@ -1000,7 +1064,8 @@ int pack_gdn_tc(int32_t c, float beta_min, const float* beta_raw, const float* g
 }
 
 size_t conv_workspace_bytes_tc(const nic_conv_desc* d) {
-  (void)d;
+  const bool gdn = d->epilogue == NIC_EPI_GDN || d->epilogue == NIC_EPI_IGDN;
+  if (d->precision == NIC_PREC_BF16X3 && gdn) return static_cast<size_t>(d->n) * d->h_out * d->w_out * d->c_out * sizeof(float);
   return 0;
 }
 
@@ -1011,7 +1076,10 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   TcParams p{};
   if (int rc = build_tc_geometry(d, tt, &p)) return rc;
   const bool gdn = d->epilogue == NIC_EPI_GDN || d->epilogue == NIC_EPI_IGDN;
-  if (d->in_layout != NIC_LAYOUT_NHWC || d->in_dtype != NIC_DT_BF16) return fail(NIC_E_UNSUPPORTED, "conv bf16: input must be NHWC bf16");
+  const bool x3 = d->precision == NIC_PREC_BF16X3;
+  if (d->in_layout != NIC_LAYOUT_NHWC || d->in_dtype != (x3 ? NIC_DT_BF16X2 : NIC_DT_BF16))
+    return fail(NIC_E_UNSUPPORTED, "conv %s: input must be NHWC %s", x3 ? "bf16x3" : "bf16", x3 ? "bf16 pairs" : "bf16");
+  if (x3 && (gdn || shuffle)) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: bias / LeakyReLU epilogues only");
   if (d->c_in % 64) return fail(NIC_E_UNSUPPORTED, "conv bf16: c_in=%d must be a multiple of 64", d->c_in);
   if (gdn && (d->c_out != 128 || !gdn_gamma || !gdn_beta)) return fail(NIC_E_UNSUPPORTED, "conv bf16: the fused GDN epilogue needs c_out = 128 and packed gamma/beta");
   if ((reinterpret_cast<uintptr_t>(x) & 127) || (reinterpret_cast<uintptr_t>(w_packed) & 127)) return fail(NIC_E_BADALIGN, "conv bf16: tensors must be 128-byte aligned for TMA");
@@ -1019,9 +1087,13 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   p.nb = nb_for(d->c_out);
   p.cout_pad = (d->c_out + p.nb - 1) / p.nb * p.nb;
   p.n_ntiles = p.cout_pad / p.nb;
-  p.nchunks = d->c_in / 64;
-  p.epilogue = d->epilogue; p.out_dtype = d->out_dtype;
-  const int ctot = d->out_c_total ? d->out_c_total : d->c_out;
+  p.nchunks = (x3 ? 3 : 1) * d->c_in / 64;
+  p.a_chunk_mod = (x3 ? 2 : 1) * d->c_in / 64;
+  p.split_out = d->out_dtype == NIC_DT_BF16X2;
+  if (p.split_out && (!x3 || d->out_layout != NIC_LAYOUT_NHWC || d->out_c_total != 0 || d->c_out % 64))
+    return fail(NIC_E_UNSUPPORTED, "conv: bf16-pair output needs the bf16x3 arm, plain NHWC, c_out a multiple of 64");
+  p.epilogue = d->epilogue; p.out_dtype = p.split_out ? NIC_DT_BF16 : d->out_dtype;
+  const int ctot = p.split_out ? 2 * d->c_out : (d->out_c_total ? d->out_c_total : d->c_out);
   if (d->out_layout == NIC_LAYOUT_NCHW) { p.ys_n = static_cast<long>(ctot) * d->h_out * d->w_out; p.ys_c = static_cast<long>(d->h_out) * d->w_out; p.ys_h = d->w_out; p.ys_w = 1; }
   else { p.ys_n = static_cast<long>(d->h_out) * d->w_out * ctot; p.ys_h = static_cast<long>(d->w_out) * ctot; p.ys_w = ctot; p.ys_c = 1; }
   const size_t esz = d->out_dtype == NIC_DT_BF16 ? 2 : 4;
@@ -1074,7 +1146,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   // shared memory: A slots | B ring (or resident weights) | gamma | squares
   p.slot_bytes = (p.ph_rows * p.pw_cols * 128 + 1023) / 1024 * 1024;
   p.out_c_offset = d->out_c_offset;
-  p.tma_out = (!shuffle && d->out_layout == NIC_LAYOUT_NHWC && d->out_dtype == NIC_DT_BF16 && p.nb == 128 && d->c_out % 64 == 0 &&
+  p.tma_out = (!shuffle && d->out_layout == NIC_LAYOUT_NHWC && p.out_dtype == NIC_DT_BF16 && p.nb == 128 && d->c_out % 64 == 0 &&
                ctot % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) ? 1 : 0;
   // gamma (32 KB, GDN only) + one 32 KB tile that holds the squares for the gamma contraction and then stages the output
   const int gdn_bytes = (gdn ? 2 * 128 * 128 : 0) + ((gdn || p.tma_out) ? 2 * 128 * 128 : 0);
@@ -1102,8 +1174,9 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   p.smem_bytes = p.off_sq + ((gdn || p.tma_out) ? 2 * 128 * 128 : 0) + 1024;
 
   CUtensorMap map_a, map_w, map_g, map_o;
-  if (int rc = encode_nhwc(&map_a, x, gn, gh, gw, d->c_in, p.pw_cols, p.ph_rows, tt.in_stride)) return rc;
-  if (int rc = encode_2d(&map_w, w_packed, d->c_in, static_cast<uint64_t>(tt.ntaps) * p.cout_pad, 64, p.nb)) return rc;
+  if (p.split_out && !p.tma_out) return fail(NIC_E_BADALIGN, "conv bf16x3: bf16-pair output must be 16-byte aligned");
+  if (int rc = encode_nhwc(&map_a, x, gn, gh, gw, (x3 ? 2 : 1) * d->c_in, p.pw_cols, p.ph_rows, tt.in_stride)) return rc;
+  if (int rc = encode_2d(&map_w, w_packed, static_cast<uint64_t>(x3 ? 3 : 1) * d->c_in, static_cast<uint64_t>(tt.ntaps) * p.cout_pad, 64, p.nb)) return rc;
   if (gdn) { if (int rc = encode_2d(&map_g, gdn_gamma, 128, 128, 64, 128)) return rc; }
   else map_g = map_w;
   if (p.tma_out) {
@@ -1160,9 +1233,34 @@ static int launch_first(const nic_conv_desc* d, const void* x, const void* w_pac
 
 int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* gdn_gamma, const float* gdn_beta,
                 void* y, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if (d->precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "conv: precision %d is not built (fp32 and bf16 are)", d->precision);
   TapTable tt;
   if (int rc = build_tap_table(d, &tt)) return rc;
+  if (d->precision == NIC_PREC_BF16X3) {
+    const bool gdn = d->epilogue == NIC_EPI_GDN || d->epilogue == NIC_EPI_IGDN;
+    if (small_cin(d)) {
+      // 3-channel first layer: the whole layer (conv + GDN) on the fp32 arm, written as bf16 pairs
+      nic_conv_desc f = *d;
+      f.precision = NIC_PREC_FP32;
+      return conv_fwd_fp32(&f, x, w_packed, bias, gdn_gamma, gdn_beta, y, workspace, workspace_bytes, st);
+    }
+    if (!gdn) return launch_tc(d, tt, x, w_packed, bias, nullptr, nullptr, y, st);
+    // GDN layer: K-concatenated conv on the tensor cores into an fp32 NHWC scratch, then the fp32 GDN contraction
+    const size_t need = conv_workspace_bytes_tc(d);
+    if (!workspace || workspace_bytes < need) return fail(NIC_E_WORKSPACE, "conv bf16x3 + GDN: workspace %zu < %zu bytes", workspace_bytes, need);
+    if (!gdn_gamma || !gdn_beta) return fail(NIC_E_BADSHAPE, "conv: GDN epilogue without gamma/beta");
+    nic_conv_desc c1 = *d;
+    c1.epilogue = NIC_EPI_BIAS; c1.out_dtype = NIC_DT_F32; c1.out_layout = NIC_LAYOUT_NHWC; c1.out_c_total = 0; c1.out_c_offset = 0;
+    if (int rc = launch_tc(&c1, tt, x, w_packed, bias, nullptr, nullptr, workspace, st)) return rc;
+    const int inverse = d->epilogue == NIC_EPI_IGDN;
+    if (d->out_dtype == NIC_DT_BF16X2)
+      return gdn_fwd_fp32_split(static_cast<const float*>(workspace), d->n, d->c_out, d->h_out, d->w_out, inverse,
+                                static_cast<const float*>(gdn_gamma), gdn_beta, y, st);
+    if (d->out_dtype == NIC_DT_F32 && d->out_c_total == 0)
+      return gdn_fwd_fp32(static_cast<const float*>(workspace), d->n, d->c_out, d->h_out, d->w_out, d->out_layout, inverse,
+                          static_cast<const float*>(gdn_gamma), gdn_beta, static_cast<float*>(y), st);
+    return fail(NIC_E_UNSUPPORTED, "conv bf16x3 + GDN: output must be bf16 pairs or plain f32");
+  }
+  if (d->precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "conv: precision %d", d->precision);
   if (subpixel_form(d)) {
     if (d->epilogue != NIC_EPI_BIAS) return fail(NIC_E_UNSUPPORTED, "conv bf16: the sub-pixel path has a bias-only epilogue");
     const nic_conv_desc e = subpixel_desc(d);

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import (ConvDesc, DT_BF16, DT_F32, EPI_BIAS, EPI_GDN, EPI_IGDN, EPI_LRELU, LAYOUT_NCHW, LAYOUT_NHWC,
+from ._lib import (ConvDesc, DT_BF16, DT_BF16X2, DT_F32, EPI_BIAS, EPI_GDN, EPI_IGDN, EPI_LRELU, LAYOUT_NCHW, LAYOUT_NHWC,
                    PRECISIONS, PREC_FP32, check, current_stream, ptr)
 
 DEFAULT_PRECISION = os.environ.get("NIC_PRECISION", "fp32")
@@ -102,16 +102,21 @@ class ConvOp:
 
     def run(self, x: torch.Tensor, n: int, h: int, w: int, precision: str, in_layout=LAYOUT_NHWC, out_layout=LAYOUT_NHWC,
             out: Optional[torch.Tensor] = None, out_c_total: int = 0, out_c_offset: int = 0,
-            out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-        """x: contiguous tensor in `in_layout`; returns (or fills) the output in `out_layout`."""
+            out_dtype=None) -> torch.Tensor:
+        """x: contiguous tensor in `in_layout`; returns (or fills) the output in `out_layout`.
+
+        In the "bf16x3" arm bf16 tensors are hi/lo PAIRS (NIC_DT_BF16X2: NHWC with 2*c channels) and the default output
+        is a pair too; out_dtype=torch.float32 asks for a plain fp32 result."""
         lib = _lib.load()
         require_cuda(x, "conv input")
-        in_dt = DT_BF16 if x.dtype == torch.bfloat16 else DT_F32
+        x3 = precision == "bf16x3"
+        in_dt = (DT_BF16X2 if x3 else DT_BF16) if x.dtype == torch.bfloat16 else DT_F32
         if out_dtype is None:
             out_dtype = act_dtype(precision)
-        out_dt = DT_BF16 if out_dtype == torch.bfloat16 else DT_F32
+        pair_out = x3 and out_dtype == torch.bfloat16
+        out_dt = DT_BF16X2 if pair_out else (DT_BF16 if out_dtype == torch.bfloat16 else DT_F32)
         d = self.desc(n, h, w, precision, in_layout, out_layout, in_dt, out_dt, out_c_total, out_c_offset)
-        ctot = out_c_total or d.c_out
+        ctot = 2 * d.c_out if pair_out else (out_c_total or d.c_out)
         if out is None:
             shape = (n, d.h_out, d.w_out, ctot) if out_layout == LAYOUT_NHWC else (n, ctot, d.h_out, d.w_out)
             out = torch.empty(shape, dtype=out_dtype, device=x.device)
@@ -143,18 +148,19 @@ def run_sequential_nchw(ops, x: torch.Tensor, precision: str) -> torch.Tensor:
 
 
 def latent_handoff(v_nhwc: torch.Tensor, qmode: int, noise: Optional[torch.Tensor], in_dtype: torch.dtype,
-                   want_lowp: bool = False):
-    """Models.py:52-66.  Returns (v_nchw, v_in_nchw, v_in_nhwc, v_nhwc_bf16 | None)."""
+                   want_lowp: bool = False, lowp_pair: bool = False):
+    """Models.py:52-66.  Returns (v_nchw, v_in_nchw, v_in_nhwc, v_nhwc_lowp | None); lowp_pair -> hi/lo pair (2c channels)."""
     lib = _lib.load()
     n, h, w, c = v_nhwc.shape
     v = torch.empty((n, c, h, w), dtype=torch.float32, device=v_nhwc.device)
     v_in = torch.empty_like(v)
     v_in_nhwc = torch.empty((n, h, w, c), dtype=in_dtype, device=v_nhwc.device)
-    v_lowp = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=v_nhwc.device) if want_lowp else None
+    v_lowp = torch.empty((n, h, w, 2 * c if lowp_pair else c), dtype=torch.bfloat16, device=v_nhwc.device) if want_lowp else None
     if noise is not None:
         noise = noise.contiguous().float()
     check(lib.nic_latent_handoff(ptr(v_nhwc), n, c, h, w, qmode, ptr(noise), ptr(v), ptr(v_in), ptr(v_in_nhwc),
-                                 DT_BF16 if in_dtype == torch.bfloat16 else DT_F32, ptr(v_lowp), current_stream()),
+                                 DT_BF16 if in_dtype == torch.bfloat16 else DT_F32, ptr(v_lowp),
+                                 DT_BF16X2 if lowp_pair else DT_BF16, current_stream()),
           "nic_latent_handoff")
     return v, v_in, v_in_nhwc, v_lowp
 

@@ -234,3 +234,24 @@ def test_model_mixed_precision_symbols_match_fp32_arm_exactly():
     rel = ((out["p_y"] - ref["p_y"]).abs() / ref["p_y"]).max().item()
     print(f"mixed: bpp {r1['bpp_total']:.6f} vs {r0['bpp_total']:.6f}, psnr {r1['psnr']:.6f} vs {r0['psnr']:.6f}, max rel p_y err {rel:.2e}")
     assert abs(r1["bpp_total"] - r0["bpp_total"]) < 1e-3 and abs(r1["psnr"] - r0["psnr"]) < 1e-3
+
+
+def test_model_bf16x3_symbols_match_fp32_arm_up_to_ties():
+    """precision="bf16x3": g_a / h_a on the tensor cores with hi/lo-split operands.  y must agree with the fp32 arm to
+    ~1e-5 relative and the symbols must be equal except where the fp32 arm's y sits within 2e-3 of a rounding tie."""
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    for init in ("calib", "gain"):
+        x = H.seeded_input((2, 3, 256, 384)).cuda()
+        ref_model = H.seeded_model(128, 3, init, precision="fp32").cuda()
+        model = H.seeded_model(128, 3, init, precision="bf16x3").cuda()
+        ref, out = ref_model(x, training=False), model(x, training=False)
+        yerr = float((out["y"] - ref["y"]).abs().max() / ref["y"].abs().max())
+        zerr = float((out["z"] - ref["z"]).abs().max() / ref["z"].abs().max())
+        real, ties = H.symbol_mismatches(out["y_in"].cpu().numpy(), ref["y_in"].cpu().numpy(), ref["y"].cpu().numpy(), 2e-3)
+        realz, tiesz = H.symbol_mismatches(out["z_in"].cpu().numpy(), ref["z_in"].cpu().numpy(), ref["z"].cpu().numpy(), 2e-3)
+        r0, r1 = rd_loss(ref, x, 0.005), rd_loss(out, x, 0.005)
+        print(f"bf16x3 {init}: y rel err {yerr:.2e}, z rel err {zerr:.2e}, symbol flips at ties {ties}+{tiesz} (elsewhere {real}+{realz}), "
+              f"bpp {r1['bpp_total']:.6f} vs {r0['bpp_total']:.6f}, psnr {r1['psnr']:.6f} vs {r0['psnr']:.6f}")
+        assert yerr < 1e-4 and zerr < 1e-4 and real == 0 and realz == 0
+        if init == "calib":
+            assert abs(r1["bpp_total"] - r0["bpp_total"]) < 1e-3 and abs(r1["psnr"] - r0["psnr"]) < 1e-3
