@@ -40,8 +40,10 @@ class JointAutoregressiveHierarchical(nn.Module):
         "bf16"  tcgen05 tensor-core kernels, bf16 operands, fp32 accumulation - the throughput arm;
         "mixed" g_a and h_a (everything upstream of the rounding, i.e. what decides the symbols) in fp32, the entropy
                 path and g_s in bf16: symbols identical to the fp32 arm at ~2.5x its speed;
-        "bf16x3" g_a and h_a on the tensor cores with both operands split into bf16 hi + lo and contracted as one
-                K-concatenated convolution (fp32 grade: ~1e-5 relative on y), the rest in bf16.
+        "bf16x3" every transform on the tensor cores at fp32 grade: both operands of every contraction (convs and the GDN
+                channel mixing) split into bf16 hi + lo and contracted as hi.hi + lo.hi + hi.lo in one fp32 TMEM accumulation
+                (~1e-5 relative; 3x the MMA work), activations carried between layers as bf16 hi/lo pairs - the
+                parity-grade tensor-core arm.
     """
 
     def __init__(self, latent_channels: int = 192, K: int = 1, *, precision: Optional[str] = None):
@@ -82,8 +84,10 @@ class JointAutoregressiveHierarchical(nn.Module):
         if H % 64 or W % 64:
             raise ValueError(f"H and W must be multiples of 64 (four stride-2 stages in g_a, two in h_a); got {H}x{W}")
         prec_up = {"fp32": "fp32", "mixed": "fp32", "bf16x3": "bf16x3", "bf16": "bf16"}[self.precision]   # g_a, h_a
-        prec = "fp32" if self.precision == "fp32" else "bf16"                   # h_s, context, entropy parameters, g_s
+        prec = {"fp32": "fp32", "mixed": "bf16", "bf16x3": "bf16x3", "bf16": "bf16"}[self.precision]    # h_s, context, entropy parameters, g_s
         adt = engine.act_dtype(prec)
+        pair = prec == "bf16x3"                      # activations are bf16 hi/lo pairs: [hi(c) | lo(c)] channels
+        cw = 2 if pair else 1
         M, K = self.M, self.K
         x = x.contiguous().float()
         hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
@@ -107,7 +111,7 @@ class JointAutoregressiveHierarchical(nn.Module):
                 layout = LAYOUT_NHWC
             y_nhwc = a                                                     # f32 [B, hy, wy, M]
             lowp = prec_up != "fp32"
-            y, y_in, y_in_nhwc, y_lowp = engine.latent_handoff(y_nhwc, qmode, noise_y, adt, want_lowp=lowp,
+            y, y_in, y_in_nhwc, y_lowp = engine.latent_handoff(y_nhwc, qmode, noise_y, "bf16x2" if pair else adt, want_lowp=lowp,
                                                                lowp_pair=prec_up == "bf16x3")
 
             # ---- h_a (reads the unquantised y, Models.py:53) ------------------------------------
@@ -116,10 +120,10 @@ class JointAutoregressiveHierarchical(nn.Module):
             for i, op in enumerate(ha):
                 a = op.run(a, B, h, w, prec_up, out_dtype=torch.float32 if i == len(ha) - 1 else None)
                 h, w = engine.conv_out_hw(op.conv, h, w)
-            z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, qmode, noise_z, adt)
+            z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, qmode, noise_z, "bf16x2" if pair else adt)
 
             # ---- h_s -> psi = combined[..., 2M:4M];  context -> phi = combined[..., 0:2M] -------
-            combined = torch.empty((B, hy, wy, 4 * M), dtype=adt, device=x.device)
+            combined = torch.empty((B, hy, wy, cw * 4 * M), dtype=adt, device=x.device)
             a, h, w = z_in_nhwc, hz, wz
             hs = self.hyper_decoder.ops
             for i, op in enumerate(hs):

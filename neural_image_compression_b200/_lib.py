@@ -21,7 +21,7 @@ EPI_BIAS, EPI_LRELU, EPI_GDN, EPI_IGDN = 0, 1, 2, 3
 Q_ROUND, Q_NOISE, Q_PASSTHRU = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
 # model-level modes: "mixed" = g_a and h_a (everything upstream of the rounding) in fp32, the rest in bf16
-#                     "bf16x3" = g_a and h_a on the tensor cores with hi/lo-split operands (fp32 grade), the rest in bf16
+#                     "bf16x3" = every transform on the tensor cores with hi/lo-split operands (fp32 grade)
 MODEL_PRECISIONS = ("fp32", "bf16", "mixed", "bf16x3")
 
 

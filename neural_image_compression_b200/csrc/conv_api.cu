@@ -44,7 +44,7 @@ int nic_pack_gdn(int32_t c, float beta_min, const float* beta_raw, const float* 
                  float* beta_eff, void* gamma_packed, int32_t precision, void* stream) {
   if (int rc = nic_check_device()) return rc;
   if (c < 1 || !beta_raw || !gamma_raw || !beta_eff || !gamma_packed) return fail(NIC_E_BADSHAPE, "pack_gdn: bad arguments");
-  if (precision == NIC_PREC_FP32 || precision == NIC_PREC_BF16X3) {   // bf16x3 runs its GDN contraction on the fp32 arm
+  if (precision == NIC_PREC_FP32) {
     // constants of compressai's NonNegativeParametrizer (oracle/gdn.py), evaluated as the fp32 tensors torch holds
     const float pedestal = static_cast<float>(3.814697265625e-06 * 3.814697265625e-06);   // (2^-18)^2
     const float beta_bound = static_cast<float>(sqrt(static_cast<double>(beta_min) + static_cast<double>(pedestal)));

@@ -504,7 +504,12 @@ latent_handoff_kernel(const float* __restrict__ v, int n, int c, int h, int w, i
       if (pix < hw && ch < c) {
         const long o = (static_cast<long>(img) * hw + pix) * c + ch;
         if (out_dtype == NIC_DT_BF16) static_cast<__nv_bfloat16*>(vin_nhwc)[o] = __float2bfloat16_rn(tile_q[r][tx]);
-        else static_cast<float*>(vin_nhwc)[o] = tile_q[r][tx];
+        else if (out_dtype == NIC_DT_BF16X2) {
+          const long o2 = (static_cast<long>(img) * hw + pix) * 2 * c + ch;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(tile_q[r][tx]);
+          static_cast<__nv_bfloat16*>(vin_nhwc)[o2] = hi;
+          static_cast<__nv_bfloat16*>(vin_nhwc)[o2 + c] = __float2bfloat16_rn(tile_q[r][tx] - __bfloat162float(hi));
+        } else static_cast<float*>(vin_nhwc)[o] = tile_q[r][tx];
       }
     }
   }

@@ -32,6 +32,7 @@
 #include <stdlib.h>
 
 #include "conv_common.cuh"
+#include "tc_host.cuh"
 #include "tc_primitives.cuh"
 
 namespace nic {
@@ -45,6 +46,81 @@ int gdn_fwd_fp32(const float* x, int n, int c, int h, int w, int layout, int inv
 int gdn_fwd_fp32_split(const float* x, int n, int c, int h, int w, int inverse, const float* gamma, const float* beta, void* y, cudaStream_t st);
 int conv_fwd_fp32_ex(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y, int out_bf16_nhwc,
                      cudaStream_t st);
+
+// x3_tc.cu
+int pack_gdn_x3(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, float* beta_eff, void* gamma_packed, cudaStream_t st);
+int gdn_fwd_tc_x3(const float* x, long npix, int c, int inverse, const void* gamma_packed, const float* beta_eff, void* y, cudaStream_t st);
+size_t packed_first_x3_elems();
+int pack_first_x3(const float* w_ref, void* w_packed, cudaStream_t st);
+int conv_first_x3(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, float* y, cudaStream_t st);
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+void* g_trace_buffer = nullptr;   // set through nic_debug_set_trace (timing experiments; not part of the product ABI surface)
+
+int* status_word() {       // one device int per process: the kernels' "a bounded wait expired" flag
+  static int* d = nullptr;
+  if (!d) { if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return nullptr; cudaMemset(d, 0, sizeof(int)); }
+  return d;
+}
+
+int encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled(2d %llu x %llu, box %u x %u) failed: %d", (unsigned long long)inner,
+                                     (unsigned long long)rows, box_inner, box_rows, (int)r);
+  return NIC_OK;
+}
+
+// 2-D row-major tensor of 2-byte (bf16) or 4-byte (f32) elements, 128-byte swizzled boxes (box_inner * elem_bytes = 128)
+int encode_2d_ex(CUtensorMap* m, const void* base, int elem_bytes, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * elem_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                   strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled(2d %llu x %llu, box %u x %u, %d B) failed: %d", (unsigned long long)inner,
+                                     (unsigned long long)rows, box_inner, box_rows, elem_bytes, (int)r);
+  return NIC_OK;
+}
+
+int encode_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, int c, int box_w, int box_h, int stride) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled(nhwc %dx%dx%dx%d, box %dx%d stride %d) failed: %d", n, h, w, c, box_w,
+                                     box_h, stride, (int)r);
+  return NIC_OK;
+}
+
 
 namespace {
 
@@ -75,7 +151,8 @@ struct TcParams {
   int tiles_x, tiles_y, n_ntiles, total_tiles;
   int nchunks;                                 // K chunks of 64 (cin / 64; 3 cin / 64 in the bf16x3 arm)
   int a_chunk_mod;                             // input channel chunk of K chunk c is c % a_chunk_mod (bf16x3: [hi | lo | hi again])
-  int split_out;                               // bf16-pair output: hi to channels [0, cout), lo to [cout, 2 cout)
+  int split_out;                               // bf16-pair output: hi to the channel window of the first half of the tensor,
+  int split_lo_off;                            //   lo to the same window shifted by split_lo_off channels (the second half)
   int ph_rows, pw_cols;                        // patch rows / cols (pixels)
   int slot_bytes, nsa, nsb;
   int b_resident;                              // all weight slabs of the layer stay in shared memory (small c_out)
@@ -399,7 +476,7 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
     if (leader) trace(p, trace_tile, trace_base + 5);
     if (leader && !(p.dbg & 2)) {
       const int wc = ox0 * p.out_stride + px, hc = oy0 * p.out_stride + py;
-      const int lo_off = p.split_out ? p.cout : 0;
+      const int lo_off = p.split_out ? p.split_lo_off : 0;
       for (int h = 0; h < 2; ++h)
         if (h * 64 < nvalid_c) tma_store_4d(map_o_ptr, sq + h * (128 * 128), p.out_c_offset + lo_off + cbase + h * 64, wc, hc, img);
       tma_store_commit();
@@ -792,57 +869,6 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-void* g_trace_buffer = nullptr;   // set through nic_debug_set_trace (timing experiments; not part of the product ABI surface)
-
-int* status_word() {       // one device int per process: the kernels' "a bounded wait expired" flag
-  static int* d = nullptr;
-  if (!d) { if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return nullptr; cudaMemset(d, 0, sizeof(int)); }
-  return d;
-}
-
-int encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {inner, rows};
-  cuuint64_t strides[1] = {inner * 2};
-  cuuint32_t box[2] = {box_inner, box_rows};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled(2d %llu x %llu, box %u x %u) failed: %d", (unsigned long long)inner,
-                                     (unsigned long long)rows, box_inner, box_rows, (int)r);
-  return NIC_OK;
-}
-
-int encode_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, int c, int box_w, int box_h, int stride) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
-  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled(nhwc %dx%dx%dx%d, box %dx%d stride %d) failed: %d", n, h, w, c, box_w,
-                                     box_h, stride, (int)r);
-  return NIC_OK;
-}
-
 // Builds phases / planes / taps of the kernel from the generic tap table.
 int build_tc_geometry(const nic_conv_desc* d, const TapTable& tt, TcParams* p) {
   p->nphases = tt.nphases; p->in_stride = tt.in_stride; p->out_stride = tt.out_stride;
@@ -917,6 +943,26 @@ __global__ void pack_weight_subpixel_bf16_kernel(const float* __restrict__ w, __
         if (tt.dy[t] == dy && tt.dx[t] == dx) v = w[((static_cast<long>(ci) * cout + c) * 5 + tt.kh[t]) * 5 + tt.kw[t]];
     }
     out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// the same in the bf16x3 arm: [9][16][3 c_in] = [W_hi | W_hi | W_lo]
+__global__ void pack_weight_subpixel_x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin, int cout, TapTable tt) {
+  const long total = 9L * 16 * 3 * cin;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % (3 * cin));
+    const int n = static_cast<int>((i / (3 * cin)) % 16);
+    const int slab = static_cast<int>(i / (16L * 3 * cin));
+    const int ci = k % cin, part = k / cin;
+    const int dy = slab / 3 - 1, dx = slab % 3 - 1;
+    float v = 0.f;
+    if (n < 4 * cout) {
+      const int phase = n / cout, c = n % cout;
+      for (int t = tt.phase_begin[phase]; t < tt.phase_begin[phase + 1]; ++t)
+        if (tt.dy[t] == dy && tt.dx[t] == dx) v = w[((static_cast<long>(ci) * cout + c) * 5 + tt.kh[t]) * 5 + tt.kw[t]];
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[i] = (part < 2) ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
   }
 }
 
@@ -1000,7 +1046,8 @@ int read_and_clear_status() {
 //   c_in  = 3  : [c_out = 128][k padded to 128], k = (kh * kw_size + kw) * 3 + c   (first layer, conv_first_tc_kernel)
 size_t packed_weight_elems_tc(const nic_conv_desc* d, const TapTable& tt) {
   if (d->precision == NIC_PREC_BF16X3) {
-    if (small_cin(d)) return static_cast<size_t>(tt.ntaps) * d->c_in * d->c_out * 2;       // the fp32 pack, counted in 2-byte units
+    if (small_cin(d)) return packed_first_x3_elems();
+    if (subpixel_form(d)) return static_cast<size_t>(9) * 16 * 3 * d->c_in;
     const int cp = (d->c_out + 127) / 128 * 128;
     return static_cast<size_t>(tt.ntaps) * cp * 3 * d->c_in;
   }
@@ -1015,13 +1062,17 @@ __global__ void pack_weight_f32_kernel(const float*, float*, int, int, int, int,
 
 int pack_weight_tc(const nic_conv_desc* d, const TapTable& tt, const float* w_ref, void* w_packed, cudaStream_t st) {
   if (d->precision == NIC_PREC_BF16X3) {
-    if (small_cin(d)) {                    // first layer runs on the fp32 arm
-      const long total = static_cast<long>(tt.ntaps) * d->c_in * d->c_out;
-      pack_weight_f32_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w_ref, static_cast<float*>(w_packed), d->c_in, d->c_out,
-                                                                                  d->kh, d->kw, d->transposed, tt);
-      return check_launch("pack_weight_f32_kernel");
+    if (small_cin(d)) {
+      if (int rc = check_first_layer(d)) return rc;
+      return pack_first_x3(w_ref, w_packed, st);
     }
-    if (d->c_in % 64 || d->transposed) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: c_in must be a multiple of 64, Conv2d only (g_a / h_a layers)");
+    if (d->c_in % 64) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: c_in=%d must be a multiple of 64 (or 3 for the first layer)", d->c_in);
+    if (subpixel_form(d)) {
+      const long total = 9L * 16 * 3 * d->c_in;
+      pack_weight_subpixel_x3_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed), d->c_in,
+                                                                                         d->c_out, tt);
+      return check_launch("pack_weight_subpixel_x3_kernel");
+    }
     const int cp = (d->c_out + 127) / 128 * 128;
     const long total = static_cast<long>(tt.ntaps) * cp * 3 * d->c_in;
     const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
@@ -1054,7 +1105,8 @@ int pack_weight_tc(const nic_conv_desc* d, const TapTable& tt, const float* w_re
 
 int pack_gdn_tc(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, float* beta_eff, void* gamma_packed,
                 int32_t precision, cudaStream_t st) {
-  if (precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "pack_gdn: precision %d is not built (fp32 and bf16 are)", precision);
+  if (precision == NIC_PREC_BF16X3) return pack_gdn_x3(c, beta_min, beta_raw, gamma_raw, beta_eff, gamma_packed, st);
+  if (precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "pack_gdn: precision %d", precision);
   const float pedestal = static_cast<float>(3.814697265625e-06 * 3.814697265625e-06);
   const float beta_bound = static_cast<float>(sqrt(static_cast<double>(beta_min) + static_cast<double>(pedestal)));
   const float gamma_bound = static_cast<float>(sqrt(static_cast<double>(pedestal)));
@@ -1079,7 +1131,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   const bool x3 = d->precision == NIC_PREC_BF16X3;
   if (d->in_layout != NIC_LAYOUT_NHWC || d->in_dtype != (x3 ? NIC_DT_BF16X2 : NIC_DT_BF16))
     return fail(NIC_E_UNSUPPORTED, "conv %s: input must be NHWC %s", x3 ? "bf16x3" : "bf16", x3 ? "bf16 pairs" : "bf16");
-  if (x3 && (gdn || shuffle)) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: bias / LeakyReLU epilogues only");
+  if (x3 && gdn) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: the conv kernel has bias / LeakyReLU epilogues only (GDN follows as gdn_x3_kernel)");
   if (d->c_in % 64) return fail(NIC_E_UNSUPPORTED, "conv bf16: c_in=%d must be a multiple of 64", d->c_in);
   if (gdn && (d->c_out != 128 || !gdn_gamma || !gdn_beta)) return fail(NIC_E_UNSUPPORTED, "conv bf16: the fused GDN epilogue needs c_out = 128 and packed gamma/beta");
   if ((reinterpret_cast<uintptr_t>(x) & 127) || (reinterpret_cast<uintptr_t>(w_packed) & 127)) return fail(NIC_E_BADALIGN, "conv bf16: tensors must be 128-byte aligned for TMA");
@@ -1090,13 +1142,15 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   p.nchunks = (x3 ? 3 : 1) * d->c_in / 64;
   p.a_chunk_mod = (x3 ? 2 : 1) * d->c_in / 64;
   p.split_out = d->out_dtype == NIC_DT_BF16X2;
-  if (p.split_out && (!x3 || d->out_layout != NIC_LAYOUT_NHWC || d->out_c_total != 0 || d->c_out % 64))
-    return fail(NIC_E_UNSUPPORTED, "conv: bf16-pair output needs the bf16x3 arm, plain NHWC, c_out a multiple of 64");
+  if (p.split_out && (!x3 || d->out_layout != NIC_LAYOUT_NHWC || d->c_out % 64 || d->out_c_total % 64 || d->out_c_offset % 64))
+    return fail(NIC_E_UNSUPPORTED, "conv: bf16-pair output needs the bf16x3 arm, NHWC, channel counts / offsets multiples of 64");
   p.epilogue = d->epilogue; p.out_dtype = p.split_out ? NIC_DT_BF16 : d->out_dtype;
-  const int ctot = p.split_out ? 2 * d->c_out : (d->out_c_total ? d->out_c_total : d->c_out);
+  const int chalf = d->out_c_total ? d->out_c_total : d->c_out;
+  p.split_lo_off = chalf;
+  const int ctot = p.split_out ? 2 * chalf : chalf;
   if (d->out_layout == NIC_LAYOUT_NCHW) { p.ys_n = static_cast<long>(ctot) * d->h_out * d->w_out; p.ys_c = static_cast<long>(d->h_out) * d->w_out; p.ys_h = d->w_out; p.ys_w = 1; }
   else { p.ys_n = static_cast<long>(d->h_out) * d->w_out * ctot; p.ys_h = static_cast<long>(d->w_out) * ctot; p.ys_w = ctot; p.ys_c = 1; }
-  const size_t esz = d->out_dtype == NIC_DT_BF16 ? 2 : 4;
+  const size_t esz = d->out_dtype == NIC_DT_F32 ? 4 : 2;
   p.y = static_cast<uint8_t*>(y) + static_cast<size_t>(d->out_c_offset) * p.ys_c * esz;
   if (!shuffle && p.ys_c == 1 && ((reinterpret_cast<uintptr_t>(p.y) & 15) || (ctot * esz) % 16)) return fail(NIC_E_BADALIGN, "conv bf16: NHWC output rows must be 16-byte aligned");
   p.bias = bias; p.beta = gdn_beta;
@@ -1237,28 +1291,34 @@ int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, con
   if (int rc = build_tap_table(d, &tt)) return rc;
   if (d->precision == NIC_PREC_BF16X3) {
     const bool gdn = d->epilogue == NIC_EPI_GDN || d->epilogue == NIC_EPI_IGDN;
-    if (small_cin(d)) {
-      // 3-channel first layer: the whole layer (conv + GDN) on the fp32 arm, written as bf16 pairs
-      nic_conv_desc f = *d;
-      f.precision = NIC_PREC_FP32;
-      return conv_fwd_fp32(&f, x, w_packed, bias, gdn_gamma, gdn_beta, y, workspace, workspace_bytes, st);
+    if (subpixel_form(d)) {
+      if (d->epilogue != NIC_EPI_BIAS) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: the sub-pixel path has a bias-only epilogue");
+      const nic_conv_desc e = subpixel_desc(d);
+      TapTable te;
+      if (int rc = build_tap_table(&e, &te)) return rc;
+      return launch_tc(&e, te, x, w_packed, bias, nullptr, nullptr, y, st, d);
     }
-    if (!gdn) return launch_tc(d, tt, x, w_packed, bias, nullptr, nullptr, y, st);
-    // GDN layer: K-concatenated conv on the tensor cores into an fp32 NHWC scratch, then the fp32 GDN contraction
+    if (!gdn) {
+      if (small_cin(d)) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: the only c_in < 64 layer built is Conv2d(3, 128, 5, s2, p2) + GDN");
+      return launch_tc(d, tt, x, w_packed, bias, nullptr, nullptr, y, st);
+    }
+    // GDN / IGDN layer: conv + bias on the tensor cores into an fp32 NHWC scratch, then the hi/lo-split gamma contraction
+    // (gdn_x3_kernel) writes the bf16-pair activation
     const size_t need = conv_workspace_bytes_tc(d);
     if (!workspace || workspace_bytes < need) return fail(NIC_E_WORKSPACE, "conv bf16x3 + GDN: workspace %zu < %zu bytes", workspace_bytes, need);
     if (!gdn_gamma || !gdn_beta) return fail(NIC_E_BADSHAPE, "conv: GDN epilogue without gamma/beta");
-    nic_conv_desc c1 = *d;
-    c1.epilogue = NIC_EPI_BIAS; c1.out_dtype = NIC_DT_F32; c1.out_layout = NIC_LAYOUT_NHWC; c1.out_c_total = 0; c1.out_c_offset = 0;
-    if (int rc = launch_tc(&c1, tt, x, w_packed, bias, nullptr, nullptr, workspace, st)) return rc;
-    const int inverse = d->epilogue == NIC_EPI_IGDN;
-    if (d->out_dtype == NIC_DT_BF16X2)
-      return gdn_fwd_fp32_split(static_cast<const float*>(workspace), d->n, d->c_out, d->h_out, d->w_out, inverse,
-                                static_cast<const float*>(gdn_gamma), gdn_beta, y, st);
-    if (d->out_dtype == NIC_DT_F32 && d->out_c_total == 0)
-      return gdn_fwd_fp32(static_cast<const float*>(workspace), d->n, d->c_out, d->h_out, d->w_out, d->out_layout, inverse,
-                          static_cast<const float*>(gdn_gamma), gdn_beta, static_cast<float*>(y), st);
-    return fail(NIC_E_UNSUPPORTED, "conv bf16x3 + GDN: output must be bf16 pairs or plain f32");
+    if (d->out_dtype != NIC_DT_BF16X2 || d->out_layout != NIC_LAYOUT_NHWC || d->out_c_total != 0)
+      return fail(NIC_E_UNSUPPORTED, "conv bf16x3 + GDN: output must be a plain NHWC bf16-pair tensor");
+    if (small_cin(d)) {
+      if (int rc = check_first_layer(d)) return rc;
+      if (int rc = conv_first_x3(d, x, w_packed, bias, static_cast<float*>(workspace), st)) return rc;
+    } else {
+      nic_conv_desc c1 = *d;
+      c1.epilogue = NIC_EPI_BIAS; c1.out_dtype = NIC_DT_F32; c1.out_layout = NIC_LAYOUT_NHWC; c1.out_c_total = 0; c1.out_c_offset = 0;
+      if (int rc = launch_tc(&c1, tt, x, w_packed, bias, nullptr, nullptr, workspace, st)) return rc;
+    }
+    return gdn_fwd_tc_x3(static_cast<const float*>(workspace), static_cast<long>(d->n) * d->h_out * d->w_out, d->c_out,
+                         d->epilogue == NIC_EPI_IGDN, gdn_gamma, gdn_beta, y, st);
   }
   if (d->precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "conv: precision %d", d->precision);
   if (subpixel_form(d)) {

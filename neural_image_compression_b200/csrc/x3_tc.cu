@@ -1,0 +1,528 @@
+// bf16x3 (fp32-grade) tensor-core pieces that do not fit the generic conv kernel of conv_tc.cu:
+//
+//   gdn_x3_kernel        GDN / IGDN (compressai.layers.gdn.GDN; call sites Components.py:11-15, 40-44) of an fp32 NHWC
+//                        tensor on the tensor cores.  The channel-mixing contraction norm = beta + gamma . x^2 runs as
+//                        THREE tcgen05 contractions sq_hi.g_hi + sq_hi.g_lo + sq_lo.g_hi with x^2 and gamma both split into
+//                        bf16 hi + lo (2^-17 relative instead of the 2^-9 of a single bf16 pass), accumulated in one fp32
+//                        TMEM tile; y = x * rsqrt(norm) (or * sqrt) leaves as a bf16 hi/lo PAIR tensor (NIC_DT_BF16X2) through
+//                        TMA stores.  HBM-bound: 8 B per element (4 in, 4 out).
+//   conv_first_x3_kernel Conv2d(3, 128, 5, stride 2, pad 2) (Components.py:10) from the NCHW fp32 image with image patch and
+//                        weights split hi + lo: 15 MMAs of K = 16 per 128-pixel tile
+//                        (A_hi.W_hi + A_lo.W_hi + A_hi.W_lo over K = 80), bias added, fp32 NHWC out (the GDN above follows).
+//
+// Every mbarrier wait is bounded (nic_pipeline_status reports an expiry instead of a hung GPU).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "conv_common.cuh"
+#include "tc_host.cuh"
+#include "tc_primitives.cuh"
+
+namespace nic {
+
+using namespace tc;
+
+namespace {
+
+__device__ __forceinline__ bool wait_abort(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* status) {
+  for (uint32_t i = 0; i < (1u << 22); ++i) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((i & 255u) == 255u && *abort_flag) return false;
+  }
+  *abort_flag = 1;
+  atomicExch(status, 1);
+  return false;
+}
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// v -> (hi, lo) bf16 with hi = bf16(v), lo = bf16(v - hi); two values packed per 32-bit word
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+  hi = static_cast<uint32_t>(__bfloat16_as_ushort(ah)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bh)) << 16);
+  lo = static_cast<uint32_t>(__bfloat16_as_ushort(al)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bl)) << 16);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GDN / IGDN, c = 128, on a flat list of pixels: x [npix][128] f32 -> y [npix][256] bf16 = [hi(128) | lo(128)].
+// One persistent CTA per SM; tile = 128 pixels.  Warp 8 feeds x tiles (4 TMA boxes of 128 px x 32 f32, 128-byte swizzle) into
+// ONE 64 KB slot that is free again as soon as the 8 worker warps hold their 64 values each in registers, so the next
+// tile's load overlaps the contraction and the stores of this one.  Worker thread <-> (pixel row, 64-channel half).
+// ---------------------------------------------------------------------------------------------
+constexpr int kGdnWorkers = 8;
+constexpr int kGdnThreads = kGdnWorkers * 32 + 32;
+constexpr int kPanel = 128 * 128;               // one K-major SWIZZLE_128B panel: 128 rows x 64 bf16 (or 128 rows x 32 f32)
+
+struct GdnX3Params {
+  int ntiles, inverse;
+  const float* beta;
+  int* status;
+};
+
+struct __align__(8) GdnBarriers {
+  uint64_t x_full, x_empty, gamma_full, mma_done;
+  uint32_t tmem_base;
+  volatile int abort_flag;
+};
+
+__global__ void __launch_bounds__(kGdnThreads, 1)
+gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_o,
+              const __grid_constant__ GdnX3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* xs = smem;                              // 4 boxes of [128 px][32 f32]
+  uint8_t* gam = smem + 4 * kPanel;                // g_hi panel 0, 1 | g_lo panel 0, 1   ([128 out][64 in] bf16 each)
+  uint8_t* sqh = smem + 8 * kPanel;                // squares hi (panel 0, 1), later the hi half of the output tile
+  uint8_t* sql = smem + 10 * kPanel;               // squares lo, later the lo half
+  __shared__ GdnBarriers sb;
+  __shared__ float s_beta[128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 128) s_beta[threadIdx.x] = p.beta[threadIdx.x];
+  if (threadIdx.x == 0) {
+    mbar_init(&sb.x_full, 1); mbar_init(&sb.x_empty, kGdnWorkers); mbar_init(&sb.gamma_full, 1); mbar_init(&sb.mma_done, 1);
+    sb.abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == kGdnWorkers) { tmem_alloc(&sb.tmem_base, 128); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = sb.tmem_base;
+
+  if (warp == kGdnWorkers) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_g); tma_prefetch_desc(&map_o);
+      mbar_expect_tx(&sb.gamma_full, 4 * kPanel);
+      tma_load_2d(gam, &map_g, &sb.gamma_full, 0, 0);
+      tma_load_2d(gam + kPanel, &map_g, &sb.gamma_full, 64, 0);
+      tma_load_2d(gam + 2 * kPanel, &map_g, &sb.gamma_full, 0, 128);
+      tma_load_2d(gam + 3 * kPanel, &map_g, &sb.gamma_full, 64, 128);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        if (!wait_abort(&sb.x_empty, (it & 1) ^ 1, &sb.abort_flag, p.status)) break;
+        mbar_expect_tx(&sb.x_full, 4 * kPanel);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tma_load_2d(xs + b * kPanel, &map_x, &sb.x_full, b * 32, tile * 128);
+      }
+    }
+  } else {
+    const int q = warp & 3, hs = warp >> 2;
+    const int row = q * 32 + lane;
+    const bool leader = threadIdx.x == 0;
+    const uint32_t swz = static_cast<uint32_t>(row & 7);
+    uint8_t* my_h = sqh + hs * kPanel + row * 128;
+    uint8_t* my_l = sql + hs * kPanel + row * 128;
+    const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + hs * 64;
+    auto sync_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kGdnWorkers * 32) : "memory"); };
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.x_full, it & 1, &sb.abort_flag, p.status))) break;
+      float xr[64];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const uint8_t* src = xs + (2 * hs + b) * kPanel + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(src + ((static_cast<uint32_t>(j) ^ swz) << 4));
+          xr[b * 32 + j * 4] = v.x; xr[b * 32 + j * 4 + 1] = v.y; xr[b * 32 + j * 4 + 2] = v.z; xr[b * 32 + j * 4 + 3] = v.w;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb.x_empty);                 // the slot may be refilled while this tile is processed
+      if (leader) tma_store_wait_read();                       // previous tile's output has left the staging tiles
+      sync_workers();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = xr[j * 8 + e * 2], b = xr[j * 8 + e * 2 + 1];
+          split2(a * a, b * b, h[e], l[e]);
+        }
+        const uint32_t off = (static_cast<uint32_t>(j) ^ swz) << 4;
+        *reinterpret_cast<uint4*>(my_h + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(my_l + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      sync_workers();
+      if (leader) {
+        if (it == 0) wait_abort(&sb.gamma_full, 0, &sb.abort_flag, p.status);
+        tcgen05_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(128, 128);
+        const uint32_t hi = umma_desc_hi(1024);
+        const uint32_t sh = umma_desc_lo(smem_u32(sqh)), sl = umma_desc_lo(smem_u32(sql));
+        const uint32_t gh = umma_desc_lo(smem_u32(gam)), gl = umma_desc_lo(smem_u32(gam + 2 * kPanel));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = ((k >> 2) * kPanel + (k & 3) * 32) >> 4;
+          umma_bf16_lohi(tmem, sh + off, hi, gh + off, hi, idesc, k);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = ((k >> 2) * kPanel + (k & 3) * 32) >> 4;
+          umma_bf16_lohi(tmem, sh + off, hi, gl + off, hi, idesc, 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = ((k >> 2) * kPanel + (k & 3) * 32) >> 4;
+          umma_bf16_lohi(tmem, sl + off, hi, gh + off, hi, idesc, 1);
+        }
+        umma_commit(&sb.mma_done);
+      }
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.mma_done, it & 1, &sb.abort_flag, p.status))) break;
+      tcgen05_fence_after();
+      float v0[32], v1[32];
+      tmem_ld_32x32(taddr, v0);
+      tmem_ld_32x32(taddr + 32, v1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float n0 = v0[j] + s_beta[hs * 64 + j], n1 = v1[j] + s_beta[hs * 64 + 32 + j];
+        v0[j] = xr[j] * (p.inverse ? sqrt_approx(n0) : rsqrt_approx(n0));
+        v1[j] = xr[32 + j] * (p.inverse ? sqrt_approx(n1) : rsqrt_approx(n1));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t h[4], l[4];
+        const float* src = (j < 4) ? (v0 + j * 8) : (v1 + (j - 4) * 8);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split2(src[e * 2], src[e * 2 + 1], h[e], l[e]);
+        const uint32_t off = (static_cast<uint32_t>(j) ^ swz) << 4;
+        *reinterpret_cast<uint4*>(my_h + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(my_l + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      sync_workers();
+      if (leader) {
+        tma_store_2d(&map_o, sqh, 0, tile * 128);
+        tma_store_2d(&map_o, sqh + kPanel, 64, tile * 128);
+        tma_store_2d(&map_o, sql, 128, tile * 128);
+        tma_store_2d(&map_o, sql + kPanel, 192, tile * 128);
+        tma_store_commit();
+      }
+    }
+    if (leader) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kGdnWorkers) tmem_dealloc(tmem, 128);
+}
+
+// gamma_eff [i (out)][j (in)] split hi | lo: bf16 [2][c][c], K-major B operands; beta_eff f32 [c]
+__global__ void pack_gdn_x3_kernel(int c, float beta_bound, float gamma_bound, float pedestal, const float* __restrict__ beta,
+                                   const float* __restrict__ gamma, float* __restrict__ beta_eff, __nv_bfloat16* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c * c; i += gridDim.x * blockDim.x) {
+    const float g = fmaxf(gamma[i], gamma_bound);
+    const float ge = g * g - pedestal;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(ge);
+    out[i] = hi;
+    out[c * c + i] = __float2bfloat16_rn(ge - __bfloat162float(hi));
+    if (i < c) { const float b = fmaxf(beta[i], beta_bound); beta_eff[i] = b * b - pedestal; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// First layer of g_a in the bf16x3 arm: Conv2d(3, 128, 5, stride 2, pad 2) + bias, NCHW f32 image -> NHWC f32.
+// K = 75 (k = (kh * 5 + kw) * 3 + c, padded to 80).  Operand panels (128 rows x 128 B, 128-byte swizzle):
+//   A: H = hi[k < 64]   L = lo[k < 64]   X = [hi[64..79] | lo[64..79] | unused]     (two stages)
+//   W: same three panels, resident.
+// 13 warps: 0-3 producers (patch fetch with cp.async + im2col expansion), 4 MMA issuer / weight loader, 5-12 two epilogue
+// groups that take alternate tiles: TMEM -> registers -> per-warp shared-memory transpose -> coalesced 128-byte row stores.
+// ---------------------------------------------------------------------------------------------
+constexpr int kF3Threads = 160 + 8 * 32;
+constexpr int kPatchW = 20, kPatchH = 35, kPatchCols = 19, kPatchPlane = kPatchH * kPatchW;
+constexpr int kScratchRow = 144;                 // bytes per transposed row: 32 f32 + 16 B pad (conflict-free float4 access)
+
+struct First3Params {
+  const float* x;                 // [n, 3, hin, win] f32
+  const float* bias;
+  float* y;                       // [n, hout, wout, 128] f32
+  int n, hin, win, hout, wout, tiles_x, tiles_y, total_tiles;
+  int off_a, off_w, off_scratch, off_patch;
+  int* status;
+};
+
+struct __align__(8) First3Barriers {
+  uint64_t a_full[2], a_empty[2], w_full, acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  volatile int abort_flag;
+};
+
+__global__ void __launch_bounds__(kF3Threads, 1)
+conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ First3Params f) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ First3Barriers sb;
+  __shared__ float s_bias[128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  if (tid < 128) s_bias[tid] = f.bias[tid];
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sb.a_full[i], 128); mbar_init(&sb.a_empty[i], 1);
+      mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], 4);
+    }
+    mbar_init(&sb.w_full, 1);
+    sb.abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == 4) { tmem_alloc(&sb.tmem_base, 256); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = sb.tmem_base;
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  float* patch = reinterpret_cast<float*>(smem + f.off_patch);
+
+  auto tile_coords = [&](int tile, int& img, int& ty, int& tx) {
+    tx = tile % f.tiles_x; tile /= f.tiles_x; ty = tile % f.tiles_y; img = tile / f.tiles_y;
+  };
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    auto fetch_patch = [&](int tile, int bufi) {
+      int img, ty, tx;
+      tile_coords(tile, img, ty, tx);
+      const int y0 = 2 * (ty * 16) - 2, x0 = 2 * (tx * 8) - 2;
+      const int gx = x0 + lane;
+      const bool col_ok = lane < kPatchCols && gx >= 0 && gx < f.win;
+      const float* base = f.x + static_cast<long>(img) * 3 * f.hin * f.win + (col_ok ? gx : 0);
+      const uint32_t dst0 = smem_u32(patch + bufi * (3 * kPatchPlane)) + lane * 4;
+      if (lane < kPatchCols) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+          for (int j = 0; j < 9; ++j) {
+            const int yy = warp + 4 * j;
+            if (yy < kPatchH) {
+              const int gy = y0 + yy;
+              const bool ok = col_ok && gy >= 0 && gy < f.hin;
+              const float* src = base + (static_cast<long>(c) * f.hin + (ok ? gy : 0)) * f.win;
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + (c * kPatchPlane + yy * kPatchW) * 4), "l"(src),
+                           "r"(ok ? 4 : 0)
+                           : "memory");
+            }
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (first_tile < f.total_tiles) fetch_patch(first_tile, 0);
+    uint32_t it = 0;
+    const int r = tid, g = r >> 3, c8 = r & 7;
+    const uint32_t swz = static_cast<uint32_t>(r & 7);
+    for (int tile = first_tile; tile < f.total_tiles; tile += tile_step, ++it) {
+      const uint32_t st = it & 1;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 3, 128;" ::: "memory");         // patch(it) visible to all producers; patch(it-1) no longer read
+      if (tile + tile_step < f.total_tiles) fetch_patch(tile + tile_step, st ^ 1);
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.a_empty[st], ((it >> 1) & 1) ^ 1, &sb.abort_flag, f.status))) break;
+      const float* src = patch + st * (3 * kPatchPlane) + (2 * g) * kPatchW + 2 * c8;
+      uint8_t* dst = smem + f.off_a + st * (3 * kPanel) + r * 128;
+#pragma unroll
+      for (int ch = 0; ch < 10; ++ch) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float v2[2];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int k = ch * 8 + e * 2 + hh;
+            if (k < 75) { const int tap = k / 3, c = k % 3; v2[hh] = src[c * kPatchPlane + (tap / 5) * kPatchW + (tap % 5)]; }
+            else v2[hh] = 0.f;
+          }
+          split2(v2[0], v2[1], h[e], l[e]);
+        }
+        if (ch < 8) {
+          const uint32_t off = (static_cast<uint32_t>(ch) ^ swz) << 4;
+          *reinterpret_cast<uint4*>(dst + off) = make_uint4(h[0], h[1], h[2], h[3]);                       // panel H
+          *reinterpret_cast<uint4*>(dst + kPanel + off) = make_uint4(l[0], l[1], l[2], l[3]);              // panel L
+        } else {
+          const uint32_t offh = (static_cast<uint32_t>(ch - 8) ^ swz) << 4, offl = (static_cast<uint32_t>(ch - 6) ^ swz) << 4;
+          *reinterpret_cast<uint4*>(dst + 2 * kPanel + offh) = make_uint4(h[0], h[1], h[2], h[3]);        // panel X, columns 0..15
+          *reinterpret_cast<uint4*>(dst + 2 * kPanel + offl) = make_uint4(l[0], l[1], l[2], l[3]);        // panel X, columns 16..31
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&sb.a_full[st]);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp == 4) {
+    // ===================== weight loader + MMA issuer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&map_w);
+      mbar_expect_tx(&sb.w_full, 3 * kPanel);
+      tma_load_2d(smem + f.off_w, &map_w, &sb.w_full, 0, 0);
+      tma_load_2d(smem + f.off_w + kPanel, &map_w, &sb.w_full, 64, 0);
+      tma_load_2d(smem + f.off_w + 2 * kPanel, &map_w, &sb.w_full, 128, 0);
+      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      const uint32_t hi = umma_desc_hi(1024);
+      const uint32_t a_lo = umma_desc_lo(smem_u32(smem + f.off_a)), w_lo = umma_desc_lo(smem_u32(smem + f.off_w));
+      constexpr uint32_t P = kPanel >> 4;
+      bool ok = wait_abort(&sb.w_full, 0, &sb.abort_flag, f.status);
+      uint32_t it = 0;
+      for (int tile = first_tile; tile < f.total_tiles && ok; tile += tile_step, ++it) {
+        const uint32_t g = it & 1, par = (it >> 1) & 1;
+        if (!wait_abort(&sb.acc_empty[g], par ^ 1, &sb.abort_flag, f.status)) break;
+        if (!wait_abort(&sb.a_full[g], par, &sb.abort_flag, f.status)) break;
+        tcgen05_fence_after();
+        const uint32_t d = tmem + g * 128;
+        const uint32_t ab = a_lo + g * (3 * P);
+        // A_hi . W_hi
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + 2 * k, hi, w_lo + 2 * k, hi, idesc, k);
+        umma_bf16_lohi(d, ab + 2 * P, hi, w_lo + 2 * P, hi, idesc, 1);
+        // A_lo . W_hi
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + P + 2 * k, hi, w_lo + 2 * k, hi, idesc, 1);
+        umma_bf16_lohi(d, ab + 2 * P + 2, hi, w_lo + 2 * P, hi, idesc, 1);
+        // A_hi . W_lo
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + 2 * k, hi, w_lo + P + 2 * k, hi, idesc, 1);
+        umma_bf16_lohi(d, ab + 2 * P, hi, w_lo + 2 * P + 2, hi, idesc, 1);
+        umma_commit(&sb.a_empty[g]);
+        umma_commit(&sb.acc_full[g]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 5..12): group (warp - 5) / 4 takes the tiles of its parity =====================
+    const int q = warp & 3;
+    const int grp = (warp - 5) >> 2;
+    uint8_t* scratch = smem + f.off_scratch + (warp - 5) * (32 * kScratchRow);
+    uint32_t it = 0;
+    for (int tile = first_tile; tile < f.total_tiles; tile += tile_step, ++it) {
+      if ((it & 1) != static_cast<uint32_t>(grp)) continue;
+      int img, ty, tx;
+      tile_coords(tile, img, ty, tx);
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.acc_full[grp], (it >> 1) & 1, &sb.abort_flag, f.status))) break;
+      tcgen05_fence_after();
+      const uint32_t acc = tmem + grp * 128 + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int cg = 0; cg < 4; ++cg) {
+        float v[32];
+        tmem_ld_32x32(acc + cg * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(scratch + lane * kScratchRow + j * 16) =
+              make_float4(v[j * 4] + s_bias[cg * 32 + j * 4], v[j * 4 + 1] + s_bias[cg * 32 + j * 4 + 1],
+                          v[j * 4 + 2] + s_bias[cg * 32 + j * 4 + 2], v[j * 4 + 3] + s_bias[cg * 32 + j * 4 + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3), chunk = lane & 7;
+          const float4 val = *reinterpret_cast<const float4*>(scratch + rr * kScratchRow + chunk * 16);
+          const int row = q * 32 + rr;
+          const int oy = ty * 16 + (row >> 3), ox = tx * 8 + (row & 7);
+          if (oy < f.hout && ox < f.wout)
+            *reinterpret_cast<float4*>(f.y + ((static_cast<long>(img) * f.hout + oy) * f.wout + ox) * 128 + cg * 32 + chunk * 4) = val;
+        }
+        __syncwarp();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb.acc_empty[grp]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
+// reference [128, 3, 5, 5] -> bf16 [128][192]: [hi k<64 | lo k<64 | hi k 64..79 | lo k 64..79 | 0], k = (kh * 5 + kw) * 3 + c
+__global__ void pack_first_x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 128 * 192; i += gridDim.x * blockDim.x) {
+    const int co = i / 192, col = i % 192;
+    int k = -1, lo = 0;
+    if (col < 64) k = col;
+    else if (col < 128) { k = col - 64; lo = 1; }
+    else if (col < 144) k = col - 128 + 64;
+    else if (col < 160) { k = col - 144 + 64; lo = 1; }
+    float v = 0.f;
+    if (k >= 0 && k < 75) { const int tap = k / 3, c = k % 3; v = w[((co * 3 + c) * 5 + tap / 5) * 5 + tap % 5]; }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[i] = lo ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+  }
+}
+
+}  // namespace
+
+// ---- host side ------------------------------------------------------------------------------------
+
+int pack_gdn_x3(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, float* beta_eff, void* gamma_packed, cudaStream_t st) {
+  const float pedestal = static_cast<float>(3.814697265625e-06 * 3.814697265625e-06);
+  const float beta_bound = static_cast<float>(sqrt(static_cast<double>(beta_min) + static_cast<double>(pedestal)));
+  const float gamma_bound = static_cast<float>(sqrt(static_cast<double>(pedestal)));
+  pack_gdn_x3_kernel<<<(c * c + 255) / 256, 256, 0, st>>>(c, beta_bound, gamma_bound, pedestal, beta_raw, gamma_raw, beta_eff,
+                                                          static_cast<__nv_bfloat16*>(gamma_packed));
+  return check_launch("pack_gdn_x3_kernel");
+}
+
+// x [npix][128] f32 -> y [npix][256] bf16 pairs
+int gdn_fwd_tc_x3(const float* x, long npix, int c, int inverse, const void* gamma_packed, const float* beta_eff, void* y, cudaStream_t st) {
+  if (c != 128) return fail(NIC_E_UNSUPPORTED, "gdn bf16x3: built for c = 128 (got %d)", c);
+  if ((reinterpret_cast<uintptr_t>(x) & 127) || (reinterpret_cast<uintptr_t>(y) & 127) || (reinterpret_cast<uintptr_t>(gamma_packed) & 127))
+    return fail(NIC_E_BADALIGN, "gdn bf16x3: tensors must be 128-byte aligned for TMA");
+  if (npix <= 0) return NIC_OK;
+  GdnX3Params p{};
+  p.ntiles = static_cast<int>((npix + 127) / 128); p.inverse = inverse; p.beta = beta_eff;
+  p.status = status_word();
+  if (!p.status) return fail(NIC_E_CUDA, "gdn bf16x3: cannot allocate the status word");
+  CUtensorMap map_x, map_g, map_o;
+  if (int rc = encode_2d_ex(&map_x, x, 4, 128, static_cast<uint64_t>(npix), 32, 128)) return rc;
+  if (int rc = encode_2d(&map_g, gamma_packed, 128, 256, 64, 128)) return rc;
+  if (int rc = encode_2d(&map_o, y, 256, static_cast<uint64_t>(npix), 64, 128)) return rc;
+  const int smem_bytes = 12 * kPanel + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(gdn_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
+    attr_set = true;
+  }
+  const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
+  gdn_x3_kernel<<<grid, kGdnThreads, smem_bytes, st>>>(map_x, map_g, map_o, p);
+  return check_launch("gdn_x3_kernel");
+}
+
+size_t packed_first_x3_elems() { return static_cast<size_t>(128) * 192; }
+
+int pack_first_x3(const float* w_ref, void* w_packed, cudaStream_t st) {
+  pack_first_x3_kernel<<<96, 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed));
+  return check_launch("pack_first_x3_kernel");
+}
+
+// Conv2d(3, 128, 5, s2, p2) + bias: x NCHW f32 -> y NHWC f32
+int conv_first_x3(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, float* y, cudaStream_t st) {
+  if (d->in_layout != NIC_LAYOUT_NCHW || d->in_dtype != NIC_DT_F32) return fail(NIC_E_UNSUPPORTED, "conv bf16x3 (first layer): input must be the NCHW f32 image");
+  if ((reinterpret_cast<uintptr_t>(w_packed) & 127) || (reinterpret_cast<uintptr_t>(y) & 15)) return fail(NIC_E_BADALIGN, "conv bf16x3 (first layer): alignment");
+  First3Params f{};
+  f.x = static_cast<const float*>(x); f.bias = bias; f.y = y;
+  f.n = d->n; f.hin = d->h_in; f.win = d->w_in; f.hout = d->h_out; f.wout = d->w_out;
+  f.tiles_x = (d->w_out + 7) / 8; f.tiles_y = (d->h_out + 15) / 16; f.total_tiles = f.tiles_x * f.tiles_y * d->n;
+  f.off_a = 0; f.off_w = 6 * kPanel; f.off_scratch = 9 * kPanel; f.off_patch = f.off_scratch + 8 * 32 * kScratchRow;
+  f.status = status_word();
+  if (!f.status) return fail(NIC_E_CUDA, "conv bf16x3: cannot allocate the status word");
+  const int smem_bytes = f.off_patch + 2 * 3 * kPatchPlane * 4 + 1024 + 64;
+  CUtensorMap map_w;
+  if (int rc = encode_2d(&map_w, w_packed, 192, 128, 64, 128)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(conv_first_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
+    attr_set = true;
+  }
+  const int grid = f.total_tiles < kNumSMs ? f.total_tiles : kNumSMs;
+  conv_first_x3_kernel<<<grid, kF3Threads, smem_bytes, st>>>(map_w, f);
+  return check_launch("conv_first_x3_kernel");
+}
+
+}  // namespace nic

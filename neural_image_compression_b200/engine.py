@@ -90,7 +90,7 @@ class ConvOp:
             gamma = beta = None
             if self.gdn is not None:
                 c = cv.out_channels
-                mult = 2 if precision == "bf16x3" else 1
+                mult = 2 if precision == "bf16x3" else 1           # bf16x3: gamma as bf16 [hi | lo]
                 gamma = torch.empty(c * c * mult, dtype=act_dtype(precision), device=dev)
                 beta = torch.empty(c, dtype=torch.float32, device=dev)
                 check(lib.nic_pack_gdn(c, float(self.gdn.beta_min), ptr(self.gdn.beta.detach().float().contiguous()),
@@ -116,7 +116,7 @@ class ConvOp:
         pair_out = x3 and out_dtype == torch.bfloat16
         out_dt = DT_BF16X2 if pair_out else (DT_BF16 if out_dtype == torch.bfloat16 else DT_F32)
         d = self.desc(n, h, w, precision, in_layout, out_layout, in_dt, out_dt, out_c_total, out_c_offset)
-        ctot = 2 * d.c_out if pair_out else (out_c_total or d.c_out)
+        ctot = (2 if pair_out else 1) * (out_c_total or d.c_out)       # pair tensors: [hi(c) | lo(c)]
         if out is None:
             shape = (n, d.h_out, d.w_out, ctot) if out_layout == LAYOUT_NHWC else (n, ctot, d.h_out, d.w_out)
             out = torch.empty(shape, dtype=out_dtype, device=x.device)
@@ -128,6 +128,18 @@ class ConvOp:
         return out
 
 
+def to_pair(v: torch.Tensor) -> torch.Tensor:
+    """f32 [..., c] -> bf16 [..., 2c] = [hi | lo], hi = bf16(v), lo = bf16(v - hi): the NIC_DT_BF16X2 activation format."""
+    hi = v.to(torch.bfloat16)
+    lo = (v - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def from_pair(p: torch.Tensor) -> torch.Tensor:
+    c = p.shape[-1] // 2
+    return p[..., :c].float() + p[..., c:].float()
+
+
 def run_sequential_nchw(ops, x: torch.Tensor, precision: str) -> torch.Tensor:
     """A chain of ConvOps with reference (NCHW f32) tensors at both ends; NHWC inside."""
     require_cuda(x, "input")
@@ -136,7 +148,8 @@ def run_sequential_nchw(ops, x: torch.Tensor, precision: str) -> torch.Tensor:
     cur, layout = x, LAYOUT_NCHW
     if precision != "fp32" and cin >= 64:
         # stand-alone call of an inner transform in a tensor-core mode: the engine wants NHWC bf16 (cold path)
-        cur, layout = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), LAYOUT_NHWC
+        cur, layout = x.permute(0, 2, 3, 1).contiguous(), LAYOUT_NHWC
+        cur = to_pair(cur) if precision == "bf16x3" else cur.to(torch.bfloat16)
     with torch.cuda.device(x.device):
         for i, op in enumerate(ops):
             last = i == len(ops) - 1
@@ -154,12 +167,15 @@ def latent_handoff(v_nhwc: torch.Tensor, qmode: int, noise: Optional[torch.Tenso
     n, h, w, c = v_nhwc.shape
     v = torch.empty((n, c, h, w), dtype=torch.float32, device=v_nhwc.device)
     v_in = torch.empty_like(v)
-    v_in_nhwc = torch.empty((n, h, w, c), dtype=in_dtype, device=v_nhwc.device)
+    in_pair = in_dtype == "bf16x2"                      # engine-layout copy as a bf16 hi/lo pair (bf16x3 arm)
+    if in_pair:
+        in_dtype = torch.bfloat16
+    v_in_nhwc = torch.empty((n, h, w, 2 * c if in_pair else c), dtype=in_dtype, device=v_nhwc.device)
     v_lowp = torch.empty((n, h, w, 2 * c if lowp_pair else c), dtype=torch.bfloat16, device=v_nhwc.device) if want_lowp else None
     if noise is not None:
         noise = noise.contiguous().float()
     check(lib.nic_latent_handoff(ptr(v_nhwc), n, c, h, w, qmode, ptr(noise), ptr(v), ptr(v_in), ptr(v_in_nhwc),
-                                 DT_BF16 if in_dtype == torch.bfloat16 else DT_F32, ptr(v_lowp),
+                                 DT_BF16X2 if in_pair else (DT_BF16 if in_dtype == torch.bfloat16 else DT_F32), ptr(v_lowp),
                                  DT_BF16X2 if lowp_pair else DT_BF16, current_stream()),
           "nic_latent_handoff")
     return v, v_in, v_in_nhwc, v_lowp

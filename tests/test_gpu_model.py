@@ -58,28 +58,34 @@ def check_against(out, rd, ref, ref_rd, K, precision="fp32", x_hat_tol=1e-4, bpp
     return report
 
 
+PARITY_ARMS = ["fp32", "bf16x3"]      # CUDA-core fp32 arm and the tensor-core hi/lo-split arm: both must meet the parity bar
+X_HAT_TOL = {"fp32": 1e-4, "bf16x3": 3e-4}
+
+
+@pytest.mark.parametrize("precision", PARITY_ARMS)
 @pytest.mark.parametrize("case", H.golden_cases())
-def test_model_matches_reference_vectors_fp32(case):
+def test_model_matches_reference_vectors(case, precision):
     from neural_image_compression_b200.RateDistortionLoss import rd_loss
     g = H.load_golden(case)
     M, K, init = int(g["M"]), int(g["K"]), str(g["init"])
     band = abs(float(g["rd_bpp_total"]) - float(g["fp64_bpp_total"])) if init == "gain" else 0.0
-    model = H.seeded_model(M, K, init, precision="fp32").cuda()
+    model = H.seeded_model(M, K, init, precision=precision).cuda()
     x = torch.from_numpy(g["x"]).cuda()
     out = model(x, training=False)
     rd = rd_loss(out, x, 0.005)
     ref = {k[4:]: g[k] for k in g.files if k.startswith("out_")}
     ref_rd = {k[3:]: float(g[k]) for k in g.files if k.startswith("rd_") and g[k].ndim == 0}
-    rep = check_against(out, rd, ref, ref_rd, K, bpp_band=band)
-    print(case, rep)
+    rep = check_against(out, rd, ref, ref_rd, K, precision=precision, x_hat_tol=X_HAT_TOL[precision], bpp_band=band)
+    print(case, precision, rep)
     assert out["training"] is False
 
 
+@pytest.mark.parametrize("precision", PARITY_ARMS)
 @pytest.mark.parametrize("init", ["calib", "gain"])
-def test_model_matches_oracle_at_kodak_shape_fp32(init):
+def test_model_matches_oracle_at_kodak_shape(init, precision):
     """One 768x512 image (BASELINE configs[1] shape at batch 1), oracle run live (fp32, and fp64 for the band)."""
     from neural_image_compression_b200.RateDistortionLoss import rd_loss
-    model = H.seeded_model(128, 3, init, precision="fp32")
+    model = H.seeded_model(128, 3, init, precision=precision)
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     x = H.seeded_input((1, 3, 512, 768))
     ref_t = O.forward(sd, x, 128, 3)
@@ -91,11 +97,12 @@ def test_model_matches_oracle_at_kodak_shape_fp32(init):
     model = model.cuda()
     out = model(x.cuda(), training=False)
     rd = rd_loss(out, x.cuda(), 0.005)
-    print(init, check_against(out, rd, ref, ref_rd, 3, bpp_band=band))
+    print(init, precision, check_against(out, rd, ref, ref_rd, 3, precision=precision, x_hat_tol=X_HAT_TOL[precision], bpp_band=band))
 
 
-def test_training_forward_with_injected_noise_fp32():
-    model = H.seeded_model(128, 3, "calib", precision="fp32")
+@pytest.mark.parametrize("precision", PARITY_ARMS)
+def test_training_forward_with_injected_noise(precision):
+    model = H.seeded_model(128, 3, "calib", precision=precision)
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     x = H.seeded_input((2, 3, 64, 128))
     torch.manual_seed(12)
@@ -106,7 +113,9 @@ def test_training_forward_with_injected_noise_fp32():
     np.testing.assert_allclose(out["y_in"].cpu().numpy(), ref["y_in"].numpy(), rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(out["z_in"].cpu().numpy(), ref["z_in"].numpy(), rtol=1e-4, atol=1e-4)
     bad, worst = H.likelihood_close(out["p_y"].cpu().numpy(), ref["p_y"].numpy())
-    assert bad <= 0.002 * ref["p_y"].numel(), (bad, worst)   # y_in differs by fp32 noise here, p follows it
+    # y_in = y + noise is not rounded here, so p follows the arm's own error on y: a few 1e-6 relative (fp32 order of
+    # summation) or ~1e-5 relative (bf16x3: 16-bit operand splits), amplified by |u| = |y - mu| / sigma in the tails
+    assert bad <= {"fp32": 0.002, "bf16x3": 0.02}[precision] * ref["p_y"].numel() and worst < 5e-5, (bad, worst)
     # without injected noise the draw is internal and in U(-.5, .5)
     out2 = model(x.cuda(), training=True)
     d = (out2["y_in"] - out2["y"]).abs().max()
@@ -120,10 +129,11 @@ def test_lean_forward_skips_parameter_tensors():
     assert "weights" not in lean and torch.equal(full["p_y"], lean["p_y"]) and torch.equal(full["x_hat"], lean["x_hat"])
 
 
-def test_full_size_batch_properties_fp32():
+@pytest.mark.parametrize("precision", PARITY_ARMS)
+def test_full_size_batch_properties(precision):
     """BASELINE configs[1] at full size (16 x 3 x 512 x 768): size-independent properties instead of an oracle run."""
     from neural_image_compression_b200.RateDistortionLoss import rd_loss
-    model = H.seeded_model(128, 3, "calib", precision="fp32").cuda()
+    model = H.seeded_model(128, 3, "calib", precision=precision).cuda()
     x = H.seeded_input((16, 3, 512, 768)).cuda()
     out = model(x, training=False)
     rd = rd_loss(out, x, 0.005)

@@ -1,0 +1,154 @@
+"""GPU: the bf16x3 arm (hi/lo-split operands on the tensor cores, fp32 grade) layer by layer against a float64 CPU
+convolution of the SAME fp32 operands.  The split keeps 16 mantissa bits per operand, so every layer must land within
+~1e-5 of the exact result relative to the tensor's scale; the bound asserted is 1e-4."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import forward as O
+from oracle.gdn import gdn_effective
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _run(conv, x_nchw, epilogue, gdn=None, mask_a=False, out_nchw_f32=False, out_f32=False, out_c_total=0, out_c_offset=0,
+         from_image=False):
+    from neural_image_compression_b200 import engine
+    from neural_image_compression_b200._lib import LAYOUT_NCHW, LAYOUT_NHWC
+    dev = torch.device("cuda:0")
+    op = engine.ConvOp(conv.to(dev), epilogue, gdn=None if gdn is None else gdn.to(dev), mask_a=mask_a)
+    n, c, h, w = x_nchw.shape
+    if from_image:
+        x, in_layout = x_nchw.contiguous().to(dev), LAYOUT_NCHW
+    else:
+        x, in_layout = engine.to_pair(x_nchw.permute(0, 2, 3, 1).contiguous().to(dev)), LAYOUT_NHWC
+    out = None
+    if out_c_total:
+        ho, wo = engine.conv_out_hw(conv, h, w)
+        out = torch.zeros((n, ho, wo, 2 * out_c_total), dtype=torch.bfloat16, device=dev)
+    f32 = out_nchw_f32 or out_f32
+    y = op.run(x, n, h, w, "bf16x3", in_layout=in_layout, out_layout=LAYOUT_NCHW if out_nchw_f32 else LAYOUT_NHWC, out=out,
+               out_c_total=out_c_total, out_c_offset=out_c_offset, out_dtype=torch.float32 if f32 else torch.bfloat16)
+    torch.cuda.synchronize()
+    if not f32:
+        y = engine.from_pair(y)
+    y = y.float().cpu()
+    return y if out_nchw_f32 else y.permute(0, 3, 1, 2)
+
+
+def _ref(conv, x, epilogue, gdn=None, mask=None):
+    from neural_image_compression_b200._lib import EPI_GDN, EPI_IGDN, EPI_LRELU
+    w = conv.weight.detach().cpu().double()
+    if mask is not None:
+        w = w * mask.double()
+    b = conv.bias.detach().cpu().double()
+    if isinstance(conv, nn.ConvTranspose2d):
+        v = F.conv_transpose2d(x.double(), w, b, stride=conv.stride, padding=conv.padding, output_padding=conv.output_padding)
+    else:
+        v = F.conv2d(x.double(), w, b, stride=conv.stride, padding=conv.padding)
+    if epilogue == EPI_LRELU:
+        v = F.leaky_relu(v, 0.01)
+    elif epilogue in (EPI_GDN, EPI_IGDN):
+        beta, gamma = gdn_effective(gdn.beta.detach().cpu(), gdn.gamma.detach().cpu())
+        C = beta.numel()
+        norm = F.conv2d(v * v, gamma.double().reshape(C, C, 1, 1), beta.double())
+        v = v * (torch.sqrt(norm) if epilogue == EPI_IGDN else torch.rsqrt(norm))
+    return v.float()
+
+
+def _close(y, ref, tol=TOL):
+    err = float((y - ref).abs().max() / ref.abs().max().clamp_min(1e-9))
+    assert y.shape == ref.shape and err < tol, err
+    return err
+
+
+def _gdn(inverse=False):
+    from neural_image_compression_b200.gdn import GDN
+    g = GDN(128, inverse=inverse)
+    with torch.no_grad():
+        g.gamma.add_(0.02 * torch.rand_like(g.gamma)); g.beta.add_(0.1 * torch.rand_like(g.beta))
+    return g
+
+
+@pytest.mark.parametrize("hw", [(32, 48), (20, 28), (8, 12)])
+def test_x3_conv5x5_s2(hw):
+    from neural_image_compression_b200._lib import EPI_BIAS, EPI_LRELU
+    torch.manual_seed(40)
+    conv = nn.Conv2d(128, 128, 5, 2, 2)
+    x = torch.randn(2, 128, *hw)
+    print(_close(_run(conv, x, EPI_BIAS, out_f32=True), _ref(conv, x, EPI_BIAS)))
+    print(_close(_run(conv, x, EPI_LRELU), _ref(conv, x, EPI_LRELU)))          # pair output
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("hw", [(16, 24), (10, 12)])
+def test_x3_conv_then_gdn_on_tensor_cores(inverse, hw):
+    from neural_image_compression_b200._lib import EPI_GDN, EPI_IGDN
+    torch.manual_seed(41)
+    g = _gdn(inverse)
+    epi = EPI_IGDN if inverse else EPI_GDN
+    conv = nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1) if inverse else nn.Conv2d(128, 128, 5, 2, 2)
+    x = torch.randn(2, 128, *hw)
+    print(_close(_run(conv, x, epi, gdn=g), _ref(conv, x, epi, gdn=g)))
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 96), (1, 3, 80, 48), (3, 3, 32, 32)])
+def test_x3_first_layer_from_nchw_image(shape):
+    from neural_image_compression_b200._lib import EPI_GDN
+    torch.manual_seed(42)
+    conv, g = nn.Conv2d(3, 128, 5, 2, 2), _gdn()
+    x = torch.rand(*shape)
+    print(_close(_run(conv, x, EPI_GDN, gdn=g, from_image=True), _ref(conv, x, EPI_GDN, gdn=g)))
+
+
+def test_x3_transposed_to_192_and_3x3_into_pair_channel_window():
+    from neural_image_compression_b200._lib import EPI_BIAS, EPI_LRELU
+    torch.manual_seed(43)
+    conv = nn.ConvTranspose2d(128, 192, 5, 2, 2, output_padding=1)
+    x = torch.randn(2, 128, 8, 12)
+    print(_close(_run(conv, x, EPI_LRELU), _ref(conv, x, EPI_LRELU)))
+    conv3 = nn.Conv2d(192, 256, 3, 1, 1)
+    x3 = torch.randn(2, 192, 16, 24)
+    y = _run(conv3, x3, EPI_BIAS, out_c_total=512, out_c_offset=256)         # pair tensor [hi(512) | lo(512)], window [256, 512)
+    assert float(y[:, :256].abs().max()) == 0
+    print(_close(y[:, 256:], _ref(conv3, x3, EPI_BIAS)))
+
+
+def test_x3_masked_context_conv_and_pointwise_stack():
+    from neural_image_compression_b200._lib import EPI_BIAS, EPI_LRELU
+    torch.manual_seed(44)
+    conv = nn.Conv2d(128, 256, 5, 1, 2)
+    x = torch.round(4 * torch.randn(2, 128, 16, 24)) + 0.25 * torch.rand(2, 128, 16, 24)
+    mask = O.mask_a(conv.weight.detach())
+    y = _run(conv, x, EPI_BIAS, mask_a=True, out_c_total=512, out_c_offset=0)
+    assert float(y[:, 256:].abs().max()) == 0
+    print(_close(y[:, :256], _ref(conv, x, EPI_BIAS, mask=mask)))
+    c1 = nn.Conv2d(512, 640, 1)
+    x1 = torch.randn(2, 512, 8, 12)
+    print(_close(_run(c1, x1, EPI_LRELU), _ref(c1, x1, EPI_LRELU)))
+    c3 = nn.Conv2d(640, 1152, 1)
+    x3 = torch.randn(2, 640, 8, 12)
+    print(_close(_run(c3, x3, EPI_BIAS, out_nchw_f32=True), _ref(c3, x3, EPI_BIAS)))
+
+
+@pytest.mark.parametrize("hw", [(16, 24), (12, 20)])
+def test_x3_last_layer_to_rgb_nchw(hw):
+    from neural_image_compression_b200._lib import EPI_BIAS
+    torch.manual_seed(45)
+    conv = nn.ConvTranspose2d(128, 3, 5, 2, 2, output_padding=1)
+    x = torch.randn(2, 128, *hw)
+    print(_close(_run(conv, x, EPI_BIAS, out_nchw_f32=True), _ref(conv, x, EPI_BIAS)))
+
+
+def test_x3_h_a_shapes():
+    from neural_image_compression_b200._lib import EPI_BIAS, EPI_LRELU
+    torch.manual_seed(46)
+    c3 = nn.Conv2d(128, 128, 3, 1, 1)
+    x = torch.randn(2, 128, 8, 12)
+    print(_close(_run(c3, x, EPI_LRELU), _ref(c3, x, EPI_LRELU)))
+    c5 = nn.Conv2d(128, 128, 5, 2, 2)
+    x = torch.randn(1, 128, 4, 4)
+    print(_close(_run(c5, x, EPI_BIAS, out_f32=True), _ref(c5, x, EPI_BIAS)))
