@@ -128,7 +128,9 @@ constexpr int kTileH = 16, kTileW = 8;          // output pixels per M = 128 blo
 constexpr int kMaxSlots = 4;
 constexpr int kMaxBSlots = 8;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 96 + kEpiWarps * 32;
+constexpr int kMmaWarps = 2;                    // one MMA-issuing warp per M = 128 block of the tile (see the MMA issuer below)
+constexpr int kFirstEpiWarp = 2 + kMmaWarps;
+constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;
 constexpr int kMaxDynSmem = 232448 - 8192;    // 227 KB opt-in limit minus this kernel's static shared memory
 constexpr int kMaxCout = 1280;                // bias table staged in shared memory
 
@@ -167,7 +169,7 @@ struct TcParams {
   int shuffle_cout;                            // > 0: sub-pixel (2x2) output: column n = (py * 2 + px) * shuffle_cout + c goes to
                                                //      pixel (2 oy + py, 2 ox + px), channel c of an fp32 tensor (ConvTranspose2d to RGB)
   int bias_mod;                                // bias index = column % bias_mod (shuffle) ; 0 = plain
-  int dbg;                                     // NIC_TC_DEBUG bits (timing experiments only): 1 skip gamma MMA, 2 skip tensor store
+  int dbg;                                     // NIC_TC_DEBUG bits (timing experiments only): 1 skip gamma MMA, 2 skip tensor store, 4 skip direct stores
   long long* dbg_times;                        // NIC_TC_TRACE: [cta][16 tiles][16] clock64 stamps of the pipeline roles (null = off)
   const float* bias;
   const float* beta;
@@ -195,7 +197,14 @@ __device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, Tc
 }
 
 __device__ __forceinline__ void trace(const TcParams& p, uint32_t tile_iter, int slot) {
-  if (p.dbg_times && tile_iter < 16) p.dbg_times[(static_cast<long>(blockIdx.x) * 16 + tile_iter) * 16 + slot] = clock64();
+  if (p.dbg_times && tile_iter < 16) {
+    p.dbg_times[(static_cast<long>(blockIdx.x) * 32 + tile_iter) * 16 + slot] = clock64();
+    if (slot == 0) {          // wall-clock ns beside the cycle stamp: their ratio is the SM clock the kernel actually ran at
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      p.dbg_times[(static_cast<long>(blockIdx.x) * 32 + tile_iter) * 16 + 15] = static_cast<long long>(ns);
+    }
+  }
 }
 
 __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& ntile, int& phase, int& img, int& ty, int& tx) {
@@ -377,7 +386,7 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
             make_uint4(pack_bf16x2(v[j * 8], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
                        pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
       }
-    } else if (valid) {
+    } else if (valid && !(p.dbg & 4)) {
       if (p.shuffle_cout > 0) {
         // sub-pixel scatter: this thread's input pixel (oy, ox) owns output pixels (2 oy + {0,1}, 2 ox + {0,1})
         float* yb = static_cast<float*>(p.y) + img * p.ys_n + static_cast<long>(2 * oy) * p.ys_h + static_cast<long>(2 * ox) * p.ys_w;
@@ -462,8 +471,15 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
           const int c = cbase + cg * 32 + j;
           float x = v[j] + (c < p.cout ? s_bias[c] : 0.f);
           if (p.epilogue == NIC_EPI_LRELU) x = x > 0.f ? x : 0.01f * x;
-          if (pass == 1) x = x - __bfloat162float(__float2bfloat16_rn(x));
           v[j] = x;
+        }
+        if (pass == 1) {        // lo = x - bf16(x), through packed conversions (single-value F2F is a 16 / clk / SM instruction)
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const uint32_t h = pack_bf16x2(v[j], v[j + 1]);
+            v[j] -= __uint_as_float(h << 16);
+            v[j + 1] -= __uint_as_float(h & 0xffff0000u);
+          }
         }
         emit_group(cg, v);
       }
@@ -494,16 +510,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __shared__ float s_bias[kMaxCout];
   __shared__ float s_beta[128];
   __shared__ int s_tap_brow[kMaxTaps];           // weight row of the tap's slab (TMA coordinate of the B producer)
-  if (threadIdx.x < kMaxTaps) s_tap_brow[threadIdx.x] = p.taps[threadIdx.x].slab;
+  __shared__ uint32_t s_tap_aoff[kMaxTaps];      // descriptor offset (16-byte units) of the tap's first pixel inside the patch
+  if (threadIdx.x < kMaxTaps) {
+    s_tap_brow[threadIdx.x] = p.taps[threadIdx.x].slab;
+    s_tap_aoff[threadIdx.x] = static_cast<uint32_t>((p.taps[threadIdx.x].roff * p.pw_cols + p.taps[threadIdx.x].coff) * 128) >> 4;
+  }
   for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = p.bias[p.bias_mod ? i % p.bias_mod : i];
   if (p.beta) for (int i = threadIdx.x; i < 128; i += kThreads) s_beta[i] = p.beta[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool gdn = p.epilogue == NIC_EPI_GDN || p.epilogue == NIC_EPI_IGDN;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sb.a_full[i], 1); mbar_init(&sb.a_empty[i], 1); }
-    for (int i = 0; i < kMaxBSlots; ++i) { mbar_init(&sb.b_full[i], 1); mbar_init(&sb.b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], kEpiWarps); }
+    for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sb.a_full[i], 1); mbar_init(&sb.a_empty[i], kMmaWarps); }
+    for (int i = 0; i < kMaxBSlots; ++i) { mbar_init(&sb.b_full[i], 1); mbar_init(&sb.b_empty[i], kMmaWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], kMmaWarps); mbar_init(&sb.acc_empty[i], kEpiWarps); }
     mbar_init(&sb.gdn_full, 1); mbar_init(&sb.gamma_full, 1); mbar_init(&sb.bres_full, 1);
     sb.abort_flag = 0;
     fence_barrier_init();
@@ -575,18 +595,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
-  } else if (warp == 2) {
-    // ===================== MMA issuer =====================
-    // The whole warp walks the loop (so every address below is warp-uniform and lives in uniform registers); only the
-    // tcgen05 instructions themselves are issued by one elected lane.  Per-MMA issue cost must stay under the 64 clk an
-    // M128 N128 K16 MMA occupies the tensor pipe.
+  } else if (warp < kFirstEpiWarp) {
+    // ===================== MMA issuers =====================
+    // Warp 2 + b issues the MMAs of block b of every tile: the address arithmetic, barrier polls and uniform-register moves
+    // between two taps cost one warp ~300-400 clk, about what the 8 MMAs of a two-block tap occupy the tensor pipe at
+    // N = 128 and twice that at N = 16 - two issuers keep the pipe's queue full.  Both walk the same rings; the ring and
+    // accumulator barriers count one tcgen05.commit per issuer.
+    // The whole warp walks the loop (so every address below is warp-uniform); only the tcgen05 instructions themselves are
+    // issued by one elected lane.
     {
+      const int mw = warp - 2;
       const uint32_t idesc = umma_idesc_bf16(128, p.nb);
       const uint32_t a_base = smem_u32(smem + p.off_a), b_base = smem_u32(smem + p.off_b);
       const uint32_t a_hi = umma_desc_hi(p.pw_cols * 128), b_hi = umma_desc_hi(1024);
       const uint32_t bbytes = p.nb * 128;
       const int nsa = p.nsa, nsb = p.nsb, nchunks = p.nchunks, b_res = p.b_resident;
-      const uint32_t blk1_off = static_cast<uint32_t>((p.blk_roff[1] * p.pw_cols + p.blk_coff[1]) * 128) >> 4;
+      const uint32_t blk_off = mw ? static_cast<uint32_t>((p.blk_roff[1] * p.pw_cols + p.blk_coff[1]) * 128) >> 4 : 0u;
       uint32_t tcount = 0;
       uint32_t sa = 0, pa = 0, sbi = 0, pb = 0;      // ring slot + phase parity of the A and B rings
       bool ok = true;
@@ -599,38 +623,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int nplanes = ph.nplanes;
         const uint32_t buf = tcount & 1;
         if (!wait_or_abort(&sb.acc_empty[buf], ((tcount >> 1) & 1) ^ 1, &sb, p.status)) break;
-        if (lane == 0) trace(p, tcount, 0);
+        if (lane == 0 && mw == 0) trace(p, tcount, 0);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem + buf * 256;
+        const uint32_t d_tmem = tmem + buf * 256 + mw * 128;
+        const bool live = mw < nblk;
         uint32_t accumulate = 0;
         for (int chunk = 0; chunk < nchunks && ok; ++chunk) {
           for (int pl = 0; pl < nplanes && ok; ++pl) {
             if (!mbar_try_wait(&sb.a_full[sa], pa) && !wait_or_abort(&sb.a_full[sa], pa, &sb, p.status)) { ok = false; break; }
-            if (chunk == 0 && pl == 0 && lane == 0) trace(p, tcount, 1);
+            if (chunk == 0 && pl == 0 && lane == 0 && mw == 0) trace(p, tcount, 1);
             tcgen05_fence_after();
             const uint32_t a_slot_lo = umma_desc_lo(a_base + sa * p.slot_bytes);
             const int t_end = ph.plane_tap_begin[pl + 1];
             for (int t = ph.plane_tap_begin[pl]; t < t_end; ++t) {
               uint32_t b_lo;
               if (b_res) {
-                b_lo = umma_desc_lo(b_base + (p.taps[t].slab * nchunks + chunk) * bbytes);
+                b_lo = umma_desc_lo(b_base + (s_tap_brow[t] * nchunks + chunk) * bbytes);
               } else {
                 if (!mbar_try_wait(&sb.b_full[sbi], pb) && !wait_or_abort(&sb.b_full[sbi], pb, &sb, p.status)) { ok = false; break; }
                 tcgen05_fence_after();
                 b_lo = umma_desc_lo(b_base + sbi * (128 * 128));
               }
-              const uint32_t a_lo0 = a_slot_lo + (static_cast<uint32_t>((p.taps[t].roff * p.pw_cols + p.taps[t].coff) * 128) >> 4);
+              const uint32_t a_lo0 = a_slot_lo + s_tap_aoff[t] + blk_off;
               if (elect_one()) {
-                umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo, b_hi, idesc, accumulate);
-                umma_bf16_lohi(d_tmem, a_lo0 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
-                umma_bf16_lohi(d_tmem, a_lo0 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
-                umma_bf16_lohi(d_tmem, a_lo0 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
-                if (nblk > 1) {
-                  const uint32_t a_lo1 = a_lo0 + blk1_off;
-                  umma_bf16_lohi(d_tmem + 128, a_lo1, a_hi, b_lo, b_hi, idesc, accumulate);
-                  umma_bf16_lohi(d_tmem + 128, a_lo1 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
-                  umma_bf16_lohi(d_tmem + 128, a_lo1 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
-                  umma_bf16_lohi(d_tmem + 128, a_lo1 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+                if (live) {
+                  umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo, b_hi, idesc, accumulate);
+                  umma_bf16_lohi(d_tmem, a_lo0 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
+                  umma_bf16_lohi(d_tmem, a_lo0 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
+                  umma_bf16_lohi(d_tmem, a_lo0 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
                 }
                 if (!b_res) umma_commit(&sb.b_empty[sbi]);
               }
@@ -643,13 +663,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (++sa == static_cast<uint32_t>(nsa)) { sa = 0; pa ^= 1; }
           }
         }
-        if (lane == 0) trace(p, tcount, 2);
+        if (lane == 0 && mw == 0) trace(p, tcount, 2);
         if (elect_one()) umma_commit(&sb.acc_full[buf]);
         __syncwarp();
       }
     }
   } else {
-    // ===================== epilogue (warps 3..10) =====================
+    // ===================== epilogue (8 warps) =====================
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
     uint8_t* sq = smem + p.off_sq;
     uint32_t tcount = 0, gdn_count = 0;
@@ -664,14 +684,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tcgen05_fence_after();
       for (int b = 0; b < nblk && ok; ++b)
         ok = epilogue_block<kEpiWarps>(p, &sb, s_bias, s_beta, sq, smem + p.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane,
-                                       (warp - 3) >> 2, warp == 3 && lane == 0, img, ty * p.tile_h + p.blk_roff[b],
+                                       (warp - kFirstEpiWarp) >> 2, warp == kFirstEpiWarp && lane == 0, img, ty * p.tile_h + p.blk_roff[b],
                                        tx * p.tile_w + p.blk_coff[b], ph.py, ph.px, ntile * p.nb, gdn_count, b == 0 ? tcount : 0xffffffffu);
-      if (warp == 3 && lane == 0) trace(p, tcount, 4);
+      if (warp == kFirstEpiWarp && lane == 0) trace(p, tcount, 4);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb.acc_empty[buf]);
     }
-    if (p.tma_out && warp == 3 && lane == 0) tma_store_wait_all();
+    if (p.tma_out && warp == kFirstEpiWarp && lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();

@@ -45,12 +45,13 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
   return r;
 }
 
-// v -> (hi, lo) bf16 with hi = bf16(v), lo = bf16(v - hi); two values packed per 32-bit word
+// v -> (hi, lo) bf16 with hi = bf16(v), lo = bf16(v - hi); two values packed per 32-bit word.  Packed conversions only
+// (F2FP, one instruction per two values): single-value F2F runs at 16 / clk / SM and was 40 % of this kernel's time.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-  const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-  hi = static_cast<uint32_t>(__bfloat16_as_ushort(ah)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bh)) << 16);
-  lo = static_cast<uint32_t>(__bfloat16_as_ushort(al)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bl)) << 16);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -67,7 +68,12 @@ struct GdnX3Params {
   int ntiles, inverse;
   const float* beta;
   int* status;
+  long long* dbg_times;          // NIC trace hook (tools/trace_gdn.py): [cta][16 tiles][16] clock64 stamps, null = off
 };
+
+__device__ __forceinline__ void gtrace(const GdnX3Params& p, uint32_t it, int slot) {
+  if (p.dbg_times && it < 16) p.dbg_times[(static_cast<long>(blockIdx.x) * 32 + it) * 16 + slot] = clock64();
+}
 
 struct __align__(8) GdnBarriers {
   uint64_t x_full, x_empty, gamma_full, mma_done;
@@ -126,7 +132,9 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     auto sync_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kGdnWorkers * 32) : "memory"); };
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      if (leader) gtrace(p, it, 0);
       if (!__all_sync(0xffffffffu, wait_abort(&sb.x_full, it & 1, &sb.abort_flag, p.status))) break;
+      if (leader) gtrace(p, it, 1);
       float xr[64];
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
@@ -139,8 +147,10 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb.x_empty);                 // the slot may be refilled while this tile is processed
+      if (leader) gtrace(p, it, 2);
       if (leader) tma_store_wait_read();                       // previous tile's output has left the staging tiles
       sync_workers();
+      if (leader) gtrace(p, it, 3);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         uint32_t h[4], l[4];
@@ -155,8 +165,10 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
+      if (leader) gtrace(p, it, 4);
       sync_workers();
       if (leader) {
+        gtrace(p, it, 5);
         if (it == 0) wait_abort(&sb.gamma_full, 0, &sb.abort_flag, p.status);
         tcgen05_fence_after();
         const uint32_t idesc = umma_idesc_bf16(128, 128);
@@ -179,9 +191,11 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           umma_bf16_lohi(tmem, sl + off, hi, gh + off, hi, idesc, 1);
         }
         umma_commit(&sb.mma_done);
+        gtrace(p, it, 6);
       }
       if (!__all_sync(0xffffffffu, wait_abort(&sb.mma_done, it & 1, &sb.abort_flag, p.status))) break;
       tcgen05_fence_after();
+      if (leader) gtrace(p, it, 7);
       float v0[32], v1[32];
       tmem_ld_32x32(taddr, v0);
       tmem_ld_32x32(taddr + 32, v1);
@@ -204,8 +218,10 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       }
       tcgen05_fence_before();
       fence_proxy_async_smem();
+      if (leader) gtrace(p, it, 8);
       sync_workers();
       if (leader) {
+        gtrace(p, it, 9);
         tma_store_2d(&map_o, sqh, 0, tile * 128);
         tma_store_2d(&map_o, sqh + kPanel, 64, tile * 128);
         tma_store_2d(&map_o, sql, 128, tile * 128);
@@ -479,6 +495,7 @@ int gdn_fwd_tc_x3(const float* x, long npix, int c, int inverse, const void* gam
   p.ntiles = static_cast<int>((npix + 127) / 128); p.inverse = inverse; p.beta = beta_eff;
   p.status = status_word();
   if (!p.status) return fail(NIC_E_CUDA, "gdn bf16x3: cannot allocate the status word");
+  p.dbg_times = reinterpret_cast<long long*>(g_trace_buffer);
   CUtensorMap map_x, map_g, map_o;
   if (int rc = encode_2d_ex(&map_x, x, 4, 128, static_cast<uint64_t>(npix), 32, 128)) return rc;
   if (int rc = encode_2d(&map_g, gamma_packed, 128, 256, 64, 128)) return rc;

@@ -381,6 +381,66 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int n_dim, int iters, int
   if (warp == 0) tmem_dealloc(tm, 512);
 }
 
+// T8: the same with the operand walk of the conv kernel: every group of 4 K-steps starts at a different (unaligned) row
+// offset inside an 18-pixel-wide patch (filter taps), two accumulators alternate (two M blocks), n_b weight tiles rotate
+__global__ void __launch_bounds__(128) mma_walk_kernel(int n_dim, int iters, int two_acc, int walk, long long* cycles, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_base, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tm = tmem_base;
+  if (warp == 1 && elect_one()) {
+    const uint32_t idesc = umma_idesc_bf16(128, n_dim);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 96 * 1024);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const int tap = walk ? (i % 9) : 0;
+      const uint32_t arow = (tap / 3) * 18 + (tap % 3);                  // patch pixel of the tap
+      const uint64_t ad = umma_desc_sw128(a0 + arow * 128, 18 * 128), bd = umma_desc_sw128(b0 + (walk ? (i % 9) * 2048 : 0), 1024);
+      const uint32_t d = tm + (two_acc ? (i & 1) * 128 : 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(d, ad + k * 2, bd + k * 2, idesc, 1);
+    }
+    umma_commit(&bar);
+    const bool ok = mbar_wait(&bar, 0, 1u << 26);
+    const long long t1 = clock64();
+    if (!ok) *status = 1;
+    *cycles = t1 - t0;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+static void run_mma_walk() {
+  long long* dc; int* ds; CK(cudaMalloc(&dc, 8)); CK(cudaMalloc(&ds, 4)); CK(cudaMemset(ds, 0, 4));
+  CK(cudaFuncSetAttribute(mma_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+  printf("T8 SS-mode MMA rate with the conv kernel's operand walk (taps at unaligned patch rows, alternating accumulators)\n");
+  for (int n : {16, 128}) {
+    for (int two_acc : {0, 1}) {
+      for (int walk : {0, 1}) {
+        const int iters = 1800;
+        for (int grid : {1, 148}) {
+          mma_walk_kernel<<<grid, 128, 165 * 1024>>>(n, iters, two_acc, walk, dc, ds);
+          CK(cudaDeviceSynchronize());
+          long long c; int st; CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, ds, 4, cudaMemcpyDeviceToHost));
+          printf("  N=%3d, %s, %s, %3d CTAs: %.1f clk per MMA (status %d)\n", n, two_acc ? "2 accumulators" : "1 accumulator ",
+                 walk ? "9-tap walk" : "fixed operands", grid, (double)c / (iters * 4), st);
+        }
+      }
+    }
+  }
+  cudaFree(dc); cudaFree(ds);
+}
+
 static void run_mma_rate() {
   long long* dc; int* ds; CK(cudaMalloc(&dc, 8)); CK(cudaMalloc(&ds, 4)); CK(cudaMemset(ds, 0, 4));
   CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -463,6 +523,7 @@ static void run_tma_patch(EncodeTiledFn enc, int pw, int ph, int stride, int dep
 }
 
 int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "t8")) { run_mma_walk(); return 0; }
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s sm_%d%d, %d SMs, smem/block optin %zu\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount, prop.sharedMemPerBlockOptin);
   EncodeTiledFn enc = get_encode();
@@ -493,6 +554,7 @@ int main(int argc, char** argv) {
   int ok4s = run_tma_mma(enc, 2);
   printf("T6 back-to-back SS-mode MMA rate (one issuing thread, operands resident in shared memory)\n");
   run_mma_rate();
+  run_mma_walk();
   printf("T7 4-D NHWC patch loads (tensor 4 x 256 x 384 x 128 bf16 = 100 MB, L2 resident after warm-up)\n");
   for (int depth : {1, 2, 4}) {
     run_tma_patch(enc, 18, 18, 1, depth);

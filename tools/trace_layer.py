@@ -32,13 +32,13 @@ lib.nic_debug_set_trace.argtypes = [C.c_void_p]; lib.nic_debug_set_trace.restype
 for _ in range(3):
     op.run(x, B, h, w, "bf16", **kw)
 torch.cuda.synchronize()
-buf = torch.zeros(148 * 16 * 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(148 * 32 * 16, dtype=torch.int64, device=dev)
 lib.nic_debug_set_trace(buf.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); op.run(x, B, h, w, "bf16", **kw); e1.record()
 torch.cuda.synchronize()
 lib.nic_debug_set_trace(None)
-t = buf.cpu().reshape(148, 16, 16)
+t = buf.cpu().reshape(148, 32, 16)
 print(f"{which}: {e0.elapsed_time(e1)*1000:.1f} us")
 names = names_l1 if which == "l1" else ["mma:acc_empty", "mma:first_a", "mma:issued", "epi:acc_full", "epi:done", "A:first", "A:last", "-",
          "e0:start", "e0:sqdone", "e0:synced", "e0:gdn", "e0:computed", "e0:synced2"]
@@ -50,3 +50,8 @@ for cta in (0, 77):
         if int(row[0]) == 0:
             break
         print("  tile %2d: " % i + "  ".join(f"{n}={int(row[j]) - base:6d}" for j, n in enumerate(names) if n != "-" and int(row[j]) != 0))
+    live = [i for i in range(16) if int(t[cta, i][0]) and int(t[cta, i][15])]
+    if len(live) > 2:
+        a, b = live[1], live[-1]
+        dclk, dns = int(t[cta, b][0]) - int(t[cta, a][0]), int(t[cta, b][15]) - int(t[cta, a][15])
+        print(f"  SM clock during the kernel: {dclk / dns * 1000:.0f} MHz ({dclk} clk in {dns} ns, tiles {a}..{b})")
