@@ -611,62 +611,145 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t bbytes = p.nb * 128;
       const int nsa = p.nsa, nsb = p.nsb, nchunks = p.nchunks, b_res = p.b_resident;
       const uint32_t blk_off = mw ? static_cast<uint32_t>((p.blk_roff[1] * p.pw_cols + p.blk_coff[1]) * 128) >> 4 : 0u;
-      uint32_t tcount = 0;
-      uint32_t sa = 0, pa = 0, sbi = 0, pb = 0;      // ring slot + phase parity of the A and B rings
-      bool ok = true;
-      if (b_res) { ok = wait_or_abort(&sb.bres_full, 0, &sb, p.status); tcgen05_fence_after(); }
-      for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step, ++tcount) {
-        int ntile, phase, img, ty, tx;
-        decode_tile(p, tile, ntile, phase, img, ty, tx);
-        const TcPhase& ph = p.phases[phase];
-        const int nblk = live_blocks(p, ty, tx);
-        const int nplanes = ph.nplanes;
-        const uint32_t buf = tcount & 1;
-        if (!wait_or_abort(&sb.acc_empty[buf], ((tcount >> 1) & 1) ^ 1, &sb, p.status)) break;
-        if (lane == 0 && mw == 0) trace(p, tcount, 0);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem + buf * 256 + mw * 128;
-        const bool live = mw < nblk;
-        uint32_t accumulate = 0;
-        for (int chunk = 0; chunk < nchunks && ok; ++chunk) {
-          for (int pl = 0; pl < nplanes && ok; ++pl) {
-            if (!mbar_try_wait(&sb.a_full[sa], pa) && !wait_or_abort(&sb.a_full[sa], pa, &sb, p.status)) { ok = false; break; }
-            if (chunk == 0 && pl == 0 && lane == 0 && mw == 0) trace(p, tcount, 1);
-            tcgen05_fence_after();
-            const uint32_t a_slot_lo = umma_desc_lo(a_base + sa * p.slot_bytes);
-            const int t_end = ph.plane_tap_begin[pl + 1];
-            for (int t = ph.plane_tap_begin[pl]; t < t_end; ++t) {
-              uint32_t b_lo;
+      const uint32_t a_base_lo = umma_desc_lo(a_base), b_base_lo = umma_desc_lo(b_base);
+      const uint32_t slot16 = static_cast<uint32_t>(p.slot_bytes) >> 4, bb16 = bbytes >> 4;
+      // Resident weights (N = 16 layers): ONE thread per issuer walks the loop - no barrier polls inside a plane, so dropping the
+      // per-tap elect / reconvergence / warp barrier matters (per-tap overhead, not the tensor pipe, bounds these layers).
+      // Weight ring (everything else): the warp-uniform loop below is faster (mbarrier polls by the whole warp wake sooner).
+      if (b_res && lane == 0) {
+        uint32_t tcount = 0;
+        uint32_t sa = 0, pa = 0, sbi = 0, pb = 0;      // ring slot + phase parity of the A and B rings
+        bool ok = true;
+        if (b_res) { ok = wait_or_abort(&sb.bres_full, 0, &sb, p.status); tcgen05_fence_after(); }
+        for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step, ++tcount) {
+          int ntile, phase, img, ty, tx;
+          decode_tile(p, tile, ntile, phase, img, ty, tx);
+          const TcPhase& ph = p.phases[phase];
+          const int nblk = live_blocks(p, ty, tx);
+          const int nplanes = ph.nplanes;
+          const uint32_t buf = tcount & 1;
+          if (!wait_or_abort(&sb.acc_empty[buf], ((tcount >> 1) & 1) ^ 1, &sb, p.status)) break;
+          if (mw == 0) trace(p, tcount, 0);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem + buf * 256 + mw * 128;
+          const bool live = mw < nblk;
+          uint32_t accumulate = 0;
+          for (int chunk = 0; chunk < nchunks && ok; ++chunk) {
+            for (int pl = 0; pl < nplanes && ok; ++pl) {
+              if (!mbar_try_wait(&sb.a_full[sa], pa) && !wait_or_abort(&sb.a_full[sa], pa, &sb, p.status)) { ok = false; break; }
+              if (chunk == 0 && pl == 0 && mw == 0) trace(p, tcount, 1);
+              tcgen05_fence_after();
+              const uint32_t a_slot_lo = a_base_lo + sa * slot16 + blk_off;
+              const int t_begin = ph.plane_tap_begin[pl], t_end = ph.plane_tap_begin[pl + 1];
               if (b_res) {
-                b_lo = umma_desc_lo(b_base + (s_tap_brow[t] * nchunks + chunk) * bbytes);
-              } else {
-                if (!mbar_try_wait(&sb.b_full[sbi], pb) && !wait_or_abort(&sb.b_full[sbi], pb, &sb, p.status)) { ok = false; break; }
-                tcgen05_fence_after();
-                b_lo = umma_desc_lo(b_base + sbi * (128 * 128));
-              }
-              const uint32_t a_lo0 = a_slot_lo + s_tap_aoff[t] + blk_off;
-              if (elect_one()) {
                 if (live) {
-                  umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo, b_hi, idesc, accumulate);
-                  umma_bf16_lohi(d_tmem, a_lo0 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
-                  umma_bf16_lohi(d_tmem, a_lo0 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
-                  umma_bf16_lohi(d_tmem, a_lo0 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+                  for (int t = t_begin; t < t_end; ++t) {
+                    const uint32_t b_lo = b_base_lo + (s_tap_brow[t] * nchunks + chunk) * bb16;
+                    const uint32_t a_lo0 = a_slot_lo + s_tap_aoff[t];
+                    umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo, b_hi, idesc, accumulate);
+                    umma_bf16_lohi(d_tmem, a_lo0 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
+                    umma_bf16_lohi(d_tmem, a_lo0 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
+                    umma_bf16_lohi(d_tmem, a_lo0 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+                    accumulate = 1;
+                  }
                 }
-                if (!b_res) umma_commit(&sb.b_empty[sbi]);
+              } else {
+                for (int t = t_begin; t < t_end; ++t) {
+                  if (!mbar_try_wait(&sb.b_full[sbi], pb) && !wait_or_abort(&sb.b_full[sbi], pb, &sb, p.status)) { ok = false; break; }
+                  tcgen05_fence_after();
+                  if (live) {
+                    const uint32_t b_lo = b_base_lo + sbi * ((128 * 128) >> 4);
+                    const uint32_t a_lo0 = a_slot_lo + s_tap_aoff[t];
+                    umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo, b_hi, idesc, accumulate);
+                    umma_bf16_lohi(d_tmem, a_lo0 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
+                    umma_bf16_lohi(d_tmem, a_lo0 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
+                    umma_bf16_lohi(d_tmem, a_lo0 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+                    accumulate = 1;
+                  }
+                  umma_commit(&sb.b_empty[sbi]);
+                  if (++sbi == static_cast<uint32_t>(nsb)) { sbi = 0; pb ^= 1; }
+                }
               }
-              __syncwarp();
-              accumulate = 1;
-              if (!b_res) { if (++sbi == static_cast<uint32_t>(nsb)) { sbi = 0; pb ^= 1; } }
+              umma_commit(&sb.a_empty[sa]);
+              if (++sa == static_cast<uint32_t>(nsa)) { sa = 0; pa ^= 1; }
             }
-            if (elect_one()) umma_commit(&sb.a_empty[sa]);
-            __syncwarp();
-            if (++sa == static_cast<uint32_t>(nsa)) { sa = 0; pa ^= 1; }
           }
+          if (mw == 0) trace(p, tcount, 2);
+          umma_commit(&sb.acc_full[buf]);
         }
-        if (lane == 0 && mw == 0) trace(p, tcount, 2);
-        if (elect_one()) umma_commit(&sb.acc_full[buf]);
-        __syncwarp();
       }
+      if (!b_res) {
+        uint32_t tcount = 0;
+        uint32_t sa = 0, pa = 0, sbi = 0, pb = 0;      // ring slot + phase parity of the A and B rings
+        bool ok = true;
+        if (b_res) { ok = wait_or_abort(&sb.bres_full, 0, &sb, p.status); tcgen05_fence_after(); }
+        for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step, ++tcount) {
+          int ntile, phase, img, ty, tx;
+          decode_tile(p, tile, ntile, phase, img, ty, tx);
+          const TcPhase& ph = p.phases[phase];
+          const int nblk = live_blocks(p, ty, tx);
+          const int nplanes = ph.nplanes;
+          const uint32_t buf = tcount & 1;
+          if (!wait_or_abort(&sb.acc_empty[buf], ((tcount >> 1) & 1) ^ 1, &sb, p.status)) break;
+          if (lane == 0 && mw == 0) trace(p, tcount, 0);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem + buf * 256 + mw * 128;
+          const bool live = mw < nblk;
+          uint32_t accumulate = 0;
+          for (int chunk = 0; chunk < nchunks && ok; ++chunk) {
+            for (int pl = 0; pl < nplanes && ok; ++pl) {
+              if (!mbar_try_wait(&sb.a_full[sa], pa) && !wait_or_abort(&sb.a_full[sa], pa, &sb, p.status)) { ok = false; break; }
+              if (chunk == 0 && pl == 0 && lane == 0 && mw == 0) trace(p, tcount, 1);
+              tcgen05_fence_after();
+              const uint32_t a_slot_lo = umma_desc_lo(a_base + sa * p.slot_bytes);
+              const int t_end = ph.plane_tap_begin[pl + 1];
+              // two taps per iteration: one elect / reconvergence / warp barrier per 8 MMAs of this issuer
+              for (int t = ph.plane_tap_begin[pl]; t < t_end; t += 2) {
+                const bool two = t + 1 < t_end;
+                if (!mbar_try_wait(&sb.b_full[sbi], pb) && !wait_or_abort(&sb.b_full[sbi], pb, &sb, p.status)) { ok = false; break; }
+                const uint32_t s0 = sbi;
+                if (++sbi == static_cast<uint32_t>(nsb)) { sbi = 0; pb ^= 1; }
+                uint32_t s1 = s0;
+                if (two) {
+                  if (!mbar_try_wait(&sb.b_full[sbi], pb) && !wait_or_abort(&sb.b_full[sbi], pb, &sb, p.status)) { ok = false; break; }
+                  s1 = sbi;
+                  if (++sbi == static_cast<uint32_t>(nsb)) { sbi = 0; pb ^= 1; }
+                }
+                tcgen05_fence_after();
+                const uint32_t b_lo0 = b_base_lo + s0 * ((128 * 128) >> 4), b_lo1 = b_base_lo + s1 * ((128 * 128) >> 4);
+                const uint32_t a_lo0 = a_slot_lo + s_tap_aoff[t] + blk_off, a_lo1 = a_slot_lo + s_tap_aoff[two ? t + 1 : t] + blk_off;
+                if (elect_one()) {
+                  if (live) {
+                    umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo0, b_hi, idesc, accumulate);
+                    umma_bf16_lohi(d_tmem, a_lo0 + 2, a_hi, b_lo0 + 2, b_hi, idesc, 1);
+                    umma_bf16_lohi(d_tmem, a_lo0 + 4, a_hi, b_lo0 + 4, b_hi, idesc, 1);
+                    umma_bf16_lohi(d_tmem, a_lo0 + 6, a_hi, b_lo0 + 6, b_hi, idesc, 1);
+                  }
+                  umma_commit(&sb.b_empty[s0]);
+                  if (two) {
+                    if (live) {
+                      umma_bf16_lohi(d_tmem, a_lo1, a_hi, b_lo1, b_hi, idesc, 1);
+                      umma_bf16_lohi(d_tmem, a_lo1 + 2, a_hi, b_lo1 + 2, b_hi, idesc, 1);
+                      umma_bf16_lohi(d_tmem, a_lo1 + 4, a_hi, b_lo1 + 4, b_hi, idesc, 1);
+                      umma_bf16_lohi(d_tmem, a_lo1 + 6, a_hi, b_lo1 + 6, b_hi, idesc, 1);
+                    }
+                    umma_commit(&sb.b_empty[s1]);
+                  }
+                }
+                __syncwarp();
+                accumulate = 1;
+              }
+              if (elect_one()) umma_commit(&sb.a_empty[sa]);
+              __syncwarp();
+              if (++sa == static_cast<uint32_t>(nsa)) { sa = 0; pa ^= 1; }
+            }
+          }
+          if (lane == 0 && mw == 0) trace(p, tcount, 2);
+          if (elect_one()) umma_commit(&sb.acc_full[buf]);
+          __syncwarp();
+        }
+      }
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (8 warps) =====================
