@@ -107,6 +107,21 @@ int encode_2d_ex(CUtensorMap* m, const void* base, int elem_bytes, uint64_t inne
   return NIC_OK;
 }
 
+// NCHW f32 image [n][c][h][w] viewed as a 3-D tensor (w, h, n * c): boxes of box_w x box_h x c floats, no swizzle, zero fill
+// outside the image (the conv padding of the first layer)
+int encode_image_patch(CUtensorMap* m, const void* base, int n, int c, int h, int w, int box_w, int box_h) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n * c};
+  cuuint64_t strides[2] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)c};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled(image %dx%dx%dx%d, box %dx%d) failed: %d", n, c, h, w, box_w, box_h, (int)r);
+  return NIC_OK;
+}
+
 int encode_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, int c, int box_w, int box_h, int stride) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");

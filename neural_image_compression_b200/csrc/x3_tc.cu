@@ -56,9 +56,14 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 
 // ---------------------------------------------------------------------------------------------
 // GDN / IGDN, c = 128, on a flat list of pixels: x [npix][128] f32 -> y [npix][256] bf16 = [hi(128) | lo(128)].
-// One persistent CTA per SM; tile = 128 pixels.  Warp 8 feeds x tiles (4 TMA boxes of 128 px x 32 f32, 128-byte swizzle) into
-// ONE 64 KB slot that is free again as soon as the 8 worker warps hold their 64 values each in registers, so the next
-// tile's load overlaps the contraction and the stores of this one.  Worker thread <-> (pixel row, 64-channel half).
+// One persistent CTA per SM; tile = 128 pixels; worker thread <-> (pixel row, 64-channel half hs).
+// Shared memory: gamma hi / lo (64 KB, resident) + TWO 64 KB tile buffers used in rotation.  A buffer is, in turn,
+//   the fp32 x tile (4 TMA boxes of 128 px x 32 f32, 128-byte swizzle)
+//   -> the bf16 squares, hi and lo (every thread overwrites exactly the two 128-byte rows it has just read into registers:
+//      box 2 hs -> hi panel hs, box 2 hs + 1 -> lo panel hs), the A operand of the 24 MMAs
+//   -> the bf16 hi / lo output tile that four TMA stores drain,
+// so no thread ever waits for a staging tile, and the load of tile t + 1 goes into the other buffer as soon as the stores
+// of tile t - 1 have read it (the store-issuing thread checks that while the MMAs of tile t run).
 // ---------------------------------------------------------------------------------------------
 constexpr int kGdnWorkers = 8;
 constexpr int kGdnThreads = kGdnWorkers * 32 + 32;
@@ -68,7 +73,7 @@ struct GdnX3Params {
   int ntiles, inverse;
   const float* beta;
   int* status;
-  long long* dbg_times;          // NIC trace hook (tools/trace_gdn.py): [cta][16 tiles][16] clock64 stamps, null = off
+  long long* dbg_times;          // NIC trace hook (tools/trace_gdn.py): [cta][32][16] clock64 stamps, null = off
 };
 
 __device__ __forceinline__ void gtrace(const GdnX3Params& p, uint32_t it, int slot) {
@@ -76,7 +81,7 @@ __device__ __forceinline__ void gtrace(const GdnX3Params& p, uint32_t it, int sl
 }
 
 struct __align__(8) GdnBarriers {
-  uint64_t x_full, x_empty, gamma_full, mma_done;
+  uint64_t x_full[2], x_empty[2], gamma_full, mma_done;
   uint32_t tmem_base;
   volatile int abort_flag;
 };
@@ -86,16 +91,15 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
               const __grid_constant__ GdnX3Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* xs = smem;                              // 4 boxes of [128 px][32 f32]
-  uint8_t* gam = smem + 4 * kPanel;                // g_hi panel 0, 1 | g_lo panel 0, 1   ([128 out][64 in] bf16 each)
-  uint8_t* sqh = smem + 8 * kPanel;                // squares hi (panel 0, 1), later the hi half of the output tile
-  uint8_t* sql = smem + 10 * kPanel;               // squares lo, later the lo half
+  uint8_t* gam = smem;                             // g_hi panel 0, 1 | g_lo panel 0, 1   ([128 out][64 in] bf16 each)
+  uint8_t* bufs = smem + 4 * kPanel;               // two tile buffers of 4 panels: [hi 0 | lo 0 | hi 1 | lo 1] once squared
   __shared__ GdnBarriers sb;
-  __shared__ float s_beta[128];
+  __shared__ __align__(16) float s_beta[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < 128) s_beta[threadIdx.x] = p.beta[threadIdx.x];
   if (threadIdx.x == 0) {
-    mbar_init(&sb.x_full, 1); mbar_init(&sb.x_empty, kGdnWorkers); mbar_init(&sb.gamma_full, 1); mbar_init(&sb.mma_done, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sb.x_full[i], 1); mbar_init(&sb.x_empty[i], 1); }
+    mbar_init(&sb.gamma_full, 1); mbar_init(&sb.mma_done, 1);
     sb.abort_flag = 0;
     fence_barrier_init();
   }
@@ -115,10 +119,11 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       tma_load_2d(gam + 3 * kPanel, &map_g, &sb.gamma_full, 64, 128);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        if (!wait_abort(&sb.x_empty, (it & 1) ^ 1, &sb.abort_flag, p.status)) break;
-        mbar_expect_tx(&sb.x_full, 4 * kPanel);
+        const uint32_t b = it & 1;
+        if (!wait_abort(&sb.x_empty[b], ((it >> 1) & 1) ^ 1, &sb.abort_flag, p.status)) break;
+        mbar_expect_tx(&sb.x_full[b], 4 * kPanel);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) tma_load_2d(xs + b * kPanel, &map_x, &sb.x_full, b * 32, tile * 128);
+        for (int k = 0; k < 4; ++k) tma_load_2d(bufs + (b * 4 + k) * kPanel, &map_x, &sb.x_full[b], k * 32, tile * 128);
       }
     }
   } else {
@@ -126,38 +131,33 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     const int row = q * 32 + lane;
     const bool leader = threadIdx.x == 0;
     const uint32_t swz = static_cast<uint32_t>(row & 7);
-    uint8_t* my_h = sqh + hs * kPanel + row * 128;
-    uint8_t* my_l = sql + hs * kPanel + row * 128;
     const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + hs * 64;
     auto sync_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kGdnWorkers * 32) : "memory"); };
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t b = it & 1;
+      uint8_t* my_h = bufs + (b * 4 + 2 * hs) * kPanel + row * 128;      // x box 2 hs, then squares / output hi, panel hs
+      uint8_t* my_l = my_h + kPanel;                                     // x box 2 hs + 1, then squares / output lo, panel hs
       if (leader) gtrace(p, it, 0);
-      if (!__all_sync(0xffffffffu, wait_abort(&sb.x_full, it & 1, &sb.abort_flag, p.status))) break;
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.x_full[b], (it >> 1) & 1, &sb.abort_flag, p.status))) break;
       if (leader) gtrace(p, it, 1);
       float xr[64];
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const uint8_t* src = xs + (2 * hs + b) * kPanel + row * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 v = *reinterpret_cast<const float4*>(src + ((static_cast<uint32_t>(j) ^ swz) << 4));
-          xr[b * 32 + j * 4] = v.x; xr[b * 32 + j * 4 + 1] = v.y; xr[b * 32 + j * 4 + 2] = v.z; xr[b * 32 + j * 4 + 3] = v.w;
-        }
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t off = (static_cast<uint32_t>(j) ^ swz) << 4;
+        const float4 v = *reinterpret_cast<const float4*>(my_h + off), w = *reinterpret_cast<const float4*>(my_l + off);
+        xr[j * 4] = v.x; xr[j * 4 + 1] = v.y; xr[j * 4 + 2] = v.z; xr[j * 4 + 3] = v.w;
+        xr[32 + j * 4] = w.x; xr[32 + j * 4 + 1] = w.y; xr[32 + j * 4 + 2] = w.z; xr[32 + j * 4 + 3] = w.w;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sb.x_empty);                 // the slot may be refilled while this tile is processed
       if (leader) gtrace(p, it, 2);
-      if (leader) tma_store_wait_read();                       // previous tile's output has left the staging tiles
-      sync_workers();
-      if (leader) gtrace(p, it, 3);
+      // squares over the rows just read (this thread is their only reader)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         uint32_t h[4], l[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float a = xr[j * 8 + e * 2], b = xr[j * 8 + e * 2 + 1];
-          split2(a * a, b * b, h[e], l[e]);
+          const float a = xr[j * 8 + e * 2], c = xr[j * 8 + e * 2 + 1];
+          split2(a * a, c * c, h[e], l[e]);
         }
         const uint32_t off = (static_cast<uint32_t>(j) ^ swz) << 4;
         *reinterpret_cast<uint4*>(my_h + off) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -173,25 +173,20 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         tcgen05_fence_after();
         const uint32_t idesc = umma_idesc_bf16(128, 128);
         const uint32_t hi = umma_desc_hi(1024);
-        const uint32_t sh = umma_desc_lo(smem_u32(sqh)), sl = umma_desc_lo(smem_u32(sql));
+        const uint32_t sq = umma_desc_lo(smem_u32(bufs + b * 4 * kPanel));
         const uint32_t gh = umma_desc_lo(smem_u32(gam)), gl = umma_desc_lo(smem_u32(gam + 2 * kPanel));
+        constexpr uint32_t P = kPanel >> 4;
+        // channel half kh of the squares: hi panel at 2 kh, lo panel at 2 kh + 1; of gamma: panel kh of g_hi / g_lo
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t off = ((k >> 2) * kPanel + (k & 3) * 32) >> 4;
-          umma_bf16_lohi(tmem, sh + off, hi, gh + off, hi, idesc, k);
-        }
+        for (int k = 0; k < 8; ++k) umma_bf16_lohi(tmem, sq + (k >> 2) * 2 * P + (k & 3) * 2, hi, gh + (k >> 2) * P + (k & 3) * 2, hi, idesc, k);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t off = ((k >> 2) * kPanel + (k & 3) * 32) >> 4;
-          umma_bf16_lohi(tmem, sh + off, hi, gl + off, hi, idesc, 1);
-        }
+        for (int k = 0; k < 8; ++k) umma_bf16_lohi(tmem, sq + (k >> 2) * 2 * P + (k & 3) * 2, hi, gl + (k >> 2) * P + (k & 3) * 2, hi, idesc, 1);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t off = ((k >> 2) * kPanel + (k & 3) * 32) >> 4;
-          umma_bf16_lohi(tmem, sl + off, hi, gh + off, hi, idesc, 1);
-        }
+        for (int k = 0; k < 8; ++k) umma_bf16_lohi(tmem, sq + ((k >> 2) * 2 + 1) * P + (k & 3) * 2, hi, gh + (k >> 2) * P + (k & 3) * 2, hi, idesc, 1);
         umma_commit(&sb.mma_done);
         gtrace(p, it, 6);
+        // while the MMAs run: once the stores of tile it - 1 have read the other buffer, tile it + 1 may be loaded into it
+        if (it > 0) { tma_store_wait_read(); mbar_arrive(&sb.x_empty[b ^ 1]); }
       }
       if (!__all_sync(0xffffffffu, wait_abort(&sb.mma_done, it & 1, &sb.abort_flag, p.status))) break;
       tcgen05_fence_after();
@@ -200,11 +195,17 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       tmem_ld_32x32(taddr, v0);
       tmem_ld_32x32(taddr + 32, v1);
       tmem_ld_wait();
+      const float4* beta4 = reinterpret_cast<const float4*>(s_beta + hs * 64);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float n0 = v0[j] + s_beta[hs * 64 + j], n1 = v1[j] + s_beta[hs * 64 + 32 + j];
-        v0[j] = xr[j] * (p.inverse ? sqrt_approx(n0) : rsqrt_approx(n0));
-        v1[j] = xr[32 + j] * (p.inverse ? sqrt_approx(n1) : rsqrt_approx(n1));
+      for (int j = 0; j < 8; ++j) {
+        const float4 b0 = beta4[j], b1 = beta4[8 + j];
+        const float n0[4] = {v0[j * 4] + b0.x, v0[j * 4 + 1] + b0.y, v0[j * 4 + 2] + b0.z, v0[j * 4 + 3] + b0.w};
+        const float n1[4] = {v1[j * 4] + b1.x, v1[j * 4 + 1] + b1.y, v1[j * 4 + 2] + b1.z, v1[j * 4 + 3] + b1.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v0[j * 4 + e] = xr[j * 4 + e] * (p.inverse ? sqrt_approx(n0[e]) : rsqrt_approx(n0[e]));
+          v1[j * 4 + e] = xr[32 + j * 4 + e] * (p.inverse ? sqrt_approx(n1[e]) : rsqrt_approx(n1[e]));
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -222,10 +223,11 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       sync_workers();
       if (leader) {
         gtrace(p, it, 9);
-        tma_store_2d(&map_o, sqh, 0, tile * 128);
-        tma_store_2d(&map_o, sqh + kPanel, 64, tile * 128);
-        tma_store_2d(&map_o, sql, 128, tile * 128);
-        tma_store_2d(&map_o, sql + kPanel, 192, tile * 128);
+        const uint8_t* t0 = bufs + b * 4 * kPanel;
+        tma_store_2d(&map_o, t0, 0, tile * 128);                    // hi, channels 0..63
+        tma_store_2d(&map_o, t0 + 2 * kPanel, 64, tile * 128);      // hi, channels 64..127
+        tma_store_2d(&map_o, t0 + kPanel, 128, tile * 128);         // lo, channels 0..63
+        tma_store_2d(&map_o, t0 + 3 * kPanel, 192, tile * 128);     // lo, channels 64..127
         tma_store_commit();
       }
     }
@@ -258,7 +260,9 @@ __global__ void pack_gdn_x3_kernel(int c, float beta_bound, float gamma_bound, f
 // groups that take alternate tiles: TMEM -> registers -> per-warp shared-memory transpose -> coalesced 128-byte row stores.
 // ---------------------------------------------------------------------------------------------
 constexpr int kF3Threads = 160 + 8 * 32;
-constexpr int kPatchW = 20, kPatchH = 35, kPatchCols = 19, kPatchPlane = kPatchH * kPatchW;
+// image patch of a tile: 3 x 35 rows x 24 floats, fetched by ONE TMA box whose first column is 16 tx - 4 (16-byte aligned; the
+// 19 columns the taps touch start 2 floats in); zero fill outside the image is the conv padding
+constexpr int kPatchW = 24, kPatchH = 35, kPatchPlane = kPatchH * kPatchW, kPatchBytes = 3 * kPatchPlane * 4, kPatchStride = 10240;
 constexpr int kScratchRow = 144;                 // bytes per transposed row: 32 f32 + 16 B pad (conflict-free float4 access)
 
 struct First3Params {
@@ -271,13 +275,13 @@ struct First3Params {
 };
 
 struct __align__(8) First3Barriers {
-  uint64_t a_full[2], a_empty[2], w_full, acc_full[2], acc_empty[2];
+  uint64_t a_full[2], a_empty[2], w_full, acc_full[2], acc_empty[2], patch_full[2];
   uint32_t tmem_base;
   volatile int abort_flag;
 };
 
 __global__ void __launch_bounds__(kF3Threads, 1)
-conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ First3Params f) {
+conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_img, const __grid_constant__ First3Params f) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ First3Barriers sb;
@@ -288,6 +292,7 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sb.a_full[i], 128); mbar_init(&sb.a_empty[i], 1);
       mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], 4);
+      mbar_init(&sb.patch_full[i], 1);
     }
     mbar_init(&sb.w_full, 1);
     sb.abort_flag = 0;
@@ -299,7 +304,7 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   tcgen05_fence_after();
   const uint32_t tmem = sb.tmem_base;
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
-  float* patch = reinterpret_cast<float*>(smem + f.off_patch);
+  uint8_t* patch = smem + f.off_patch;
 
   auto tile_coords = [&](int tile, int& img, int& ty, int& tx) {
     tx = tile % f.tiles_x; tile /= f.tiles_x; ty = tile % f.tiles_y; img = tile / f.tiles_y;
@@ -307,44 +312,24 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 
   if (warp < 4) {
     // ===================== producers =====================
-    auto fetch_patch = [&](int tile, int bufi) {
+    auto fetch_patch = [&](int tile, int bufi) {          // one thread: one TMA box per tile
       int img, ty, tx;
       tile_coords(tile, img, ty, tx);
-      const int y0 = 2 * (ty * 16) - 2, x0 = 2 * (tx * 8) - 2;
-      const int gx = x0 + lane;
-      const bool col_ok = lane < kPatchCols && gx >= 0 && gx < f.win;
-      const float* base = f.x + static_cast<long>(img) * 3 * f.hin * f.win + (col_ok ? gx : 0);
-      const uint32_t dst0 = smem_u32(patch + bufi * (3 * kPatchPlane)) + lane * 4;
-      if (lane < kPatchCols) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-#pragma unroll
-          for (int j = 0; j < 9; ++j) {
-            const int yy = warp + 4 * j;
-            if (yy < kPatchH) {
-              const int gy = y0 + yy;
-              const bool ok = col_ok && gy >= 0 && gy < f.hin;
-              const float* src = base + (static_cast<long>(c) * f.hin + (ok ? gy : 0)) * f.win;
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + (c * kPatchPlane + yy * kPatchW) * 4), "l"(src),
-                           "r"(ok ? 4 : 0)
-                           : "memory");
-            }
-          }
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      mbar_expect_tx(&sb.patch_full[bufi], kPatchBytes);
+      tma_load_3d(patch + bufi * kPatchStride, &map_img, &sb.patch_full[bufi], 16 * tx - 4, 32 * ty - 2, img * 3);
     };
-    if (first_tile < f.total_tiles) fetch_patch(first_tile, 0);
+    if (tid == 0) tma_prefetch_desc(&map_img);
+    if (tid == 0 && first_tile < f.total_tiles) fetch_patch(first_tile, 0);
     uint32_t it = 0;
     const int r = tid, g = r >> 3, c8 = r & 7;
     const uint32_t swz = static_cast<uint32_t>(r & 7);
     for (int tile = first_tile; tile < f.total_tiles; tile += tile_step, ++it) {
       const uint32_t st = it & 1;
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("bar.sync 3, 128;" ::: "memory");         // patch(it) visible to all producers; patch(it-1) no longer read
-      if (tile + tile_step < f.total_tiles) fetch_patch(tile + tile_step, st ^ 1);
+      asm volatile("bar.sync 3, 128;" ::: "memory");         // every producer is done with patch(it-1): its buffer may be refilled
+      if (tid == 0 && tile + tile_step < f.total_tiles) fetch_patch(tile + tile_step, st ^ 1);
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.patch_full[st], (it >> 1) & 1, &sb.abort_flag, f.status))) break;
       if (!__all_sync(0xffffffffu, wait_abort(&sb.a_empty[st], ((it >> 1) & 1) ^ 1, &sb.abort_flag, f.status))) break;
-      const float* src = patch + st * (3 * kPatchPlane) + (2 * g) * kPatchW + 2 * c8;
+      const float* src = reinterpret_cast<const float*>(patch + st * kPatchStride) + (2 * g) * kPatchW + 2 * c8 + 2;
       uint8_t* dst = smem + f.off_a + st * (3 * kPanel) + r * 128;
 #pragma unroll
       for (int ch = 0; ch < 10; ++ch) {
@@ -373,7 +358,6 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       fence_proxy_async_smem();
       mbar_arrive(&sb.a_full[st]);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == 4) {
     // ===================== weight loader + MMA issuer =====================
     if (lane == 0) {
@@ -529,16 +513,18 @@ int conv_first_x3(const nic_conv_desc* d, const void* x, const void* w_packed, c
   f.off_a = 0; f.off_w = 6 * kPanel; f.off_scratch = 9 * kPanel; f.off_patch = f.off_scratch + 8 * 32 * kScratchRow;
   f.status = status_word();
   if (!f.status) return fail(NIC_E_CUDA, "conv bf16x3: cannot allocate the status word");
-  const int smem_bytes = f.off_patch + 2 * 3 * kPatchPlane * 4 + 1024 + 64;
-  CUtensorMap map_w;
+  const int smem_bytes = f.off_patch + 2 * kPatchStride + 1024 + 64;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || d->w_in % 4) return fail(NIC_E_BADALIGN, "conv bf16x3 (first layer): the image must be 16-byte aligned with rows of a multiple of 4 floats");
+  CUtensorMap map_w, map_img;
   if (int rc = encode_2d(&map_w, w_packed, 192, 128, 64, 128)) return rc;
+  if (int rc = encode_image_patch(&map_img, x, d->n, 3, d->h_in, d->w_in, kPatchW, kPatchH)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     if (int rc = check_cuda(cudaFuncSetAttribute(conv_first_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
     attr_set = true;
   }
   const int grid = f.total_tiles < kNumSMs ? f.total_tiles : kNumSMs;
-  conv_first_x3_kernel<<<grid, kF3Threads, smem_bytes, st>>>(map_w, f);
+  conv_first_x3_kernel<<<grid, kF3Threads, smem_bytes, st>>>(map_w, map_img, f);
   return check_launch("conv_first_x3_kernel");
 }
 
