@@ -48,7 +48,8 @@ enum {
   NIC_DT_F32 = 0,
   NIC_DT_BF16 = 1,
   NIC_DT_BF16X2 = 2   /* fp32 value carried as a bf16 pair: an NHWC tensor with 2*c channels, [hi(c) | lo(c)], hi = bf16(v),
-                         lo = bf16(v - hi).  Activation format of the NIC_PREC_BF16X3 arm.                              */
+                         lo = bf16(v - hi).  Activation format of the NIC_PREC_BF16X3 arm.  With out_c_total = T a conv
+                         writes hi to channels [off, off + c_out) and lo to [T + off, T + off + c_out) of a 2T-channel tensor. */
 };
 
 /* arithmetic of the contraction */
@@ -56,8 +57,10 @@ enum {
   NIC_PREC_FP32 = 0,   /* CUDA-core FFMA, fp32 operands and accumulation (parity grade)           */
   NIC_PREC_BF16 = 1,   /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulation in TMEM          */
   NIC_PREC_BF16X3 = 2  /* tcgen05, both operands split hi + lo in bf16 and contracted as ONE K-concatenated conv
-                          [A_hi | A_lo | A_hi] . [W_hi | W_hi | W_lo] in a single fp32 TMEM accumulation (fp32 grade,
-                          3x the MMA work); GDN / IGDN and the 3-channel first layer run on the fp32 arm.           */
+                          [A_hi | A_lo | A_hi] . [W_hi | W_hi | W_lo] in a single fp32 TMEM accumulation (fp32 grade:
+                          ~1e-5 relative, 3x the MMA work).  Every layer type of the path is built, including the
+                          3-channel first layer; GDN / IGDN run as a second tensor-core kernel with squares and gamma
+                          split the same way (c = 128).  Activations between layers are NIC_DT_BF16X2 pairs.        */
 };
 
 /* fused epilogues */
@@ -120,14 +123,15 @@ size_t nic_packed_weight_elems(const nic_conv_desc* d);
  * (Components.py:10-16), ConvTranspose2d [c_in, c_out, kh, kw] (Components.py:39-45),
  * masked taps dropped when d->mask_a (the reference zeroes them in place, ContextModels.py:19).
  * fp32: [tap][c_in][c_out] f32.  bf16: [tap][c_out][c_in] bf16 (K-major B operand);
- * bf16x3: [tap][c_out][3 c_in] bf16 = [W_hi | W_hi | W_lo] (first layer: the fp32 pack).
+ * bf16x3: [tap][c_out][3 c_in] bf16 = [W_hi | W_hi | W_lo] (first layer: [128][192] = hi / lo of the 75 taps in three
+ * 64-column panels; last 128 -> 3 transposed layer: its sub-pixel form [9][16][3 c_in]).
  * nic_packed_weight_elems counts 2-byte elements for the two tensor-core precisions.
  */
 int nic_pack_conv_weight(const nic_conv_desc* d, const float* w_ref, void* w_packed, void* stream);
 /*
  * compressai GDN reparametrisation (oracle/gdn.py):
  *   beta_eff = max(beta, sqrt(beta_min + 2^-36))^2 - 2^-36,  gamma_eff = max(gamma, 2^-18)^2 - 2^-36.
- * gamma_packed: fp32 and bf16x3 -> [c_in(j)][c_out(i)] f32; bf16 -> [i][j] bf16.
+ * gamma_packed: fp32 -> [c_in(j)][c_out(i)] f32; bf16 -> [i][j] bf16; bf16x3 -> [2][i][j] bf16 = hi, then lo.
  */
 int nic_pack_gdn(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw,
                  float* beta_eff, void* gamma_packed, int32_t precision, void* stream);

@@ -34,7 +34,7 @@ def _ops_from_sequential(net: nn.Sequential):
 
 
 class _Transform(nn.Module):
-    precision = None   # None -> engine.DEFAULT_PRECISION; set by the owning model
+    precision = None   # None -> engine.resolve_precision (fp32 for a stand-alone transform); set by the owning model
 
     def _build_ops(self):
         self._ops = _ops_from_sequential(self.net)
@@ -44,7 +44,8 @@ class _Transform(nn.Module):
         return self._ops
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return engine.run_sequential_nchw(self._ops, x, self.precision or engine.DEFAULT_PRECISION)
+        # stand-alone call of one transform: the fp32 arm unless the owner asked for a tensor-core arm explicitly
+        return engine.run_sequential_nchw(self._ops, x, engine.resolve_precision(self.precision))
 
 
 def _conv(cin, cout, k, s):

@@ -40,7 +40,7 @@ class MaskedConv2d(nn.Conv2d):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self.apply_mask_()
-        return engine.run_sequential_nchw([self._op], x, self.precision or engine.DEFAULT_PRECISION)
+        return engine.run_sequential_nchw([self._op], x, engine.resolve_precision(self.precision))
 
 
 class ContextModel(nn.Module):

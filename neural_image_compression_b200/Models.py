@@ -36,7 +36,8 @@ class JointAutoregressiveHierarchical(nn.Module):
     latent_channels : int, default=192, number of channels in the bottleneck y (M).
     K : int, default=1.  K == 1 -> mean-scale Gaussian; K > 1 -> mixture of K Gaussians.
     precision : arithmetic of the transforms (keyword-only extension; the reference has no such switch):
-        "fp32"  CUDA-core FFMA kernels, fp32 operands and accumulation - the parity-grade arm (default, or $NIC_PRECISION);
+        None / "auto" (default, or $NIC_PRECISION): "bf16x3" when latent_channels == 128, else "fp32" - both parity grade;
+        "fp32"  CUDA-core FFMA kernels, fp32 operands and accumulation - parity grade, any channel count;
         "bf16"  tcgen05 tensor-core kernels, bf16 operands, fp32 accumulation - the throughput arm;
         "mixed" g_a and h_a (everything upstream of the rounding, i.e. what decides the symbols) in fp32, the entropy
                 path and g_s in bf16: symbols identical to the fp32 arm at ~2.5x its speed;
@@ -65,7 +66,7 @@ class JointAutoregressiveHierarchical(nn.Module):
         self.factorized_entropy_model = FactorizedEntropyBottleneck(self.M)
         self.context_model = ContextModel(latent_channels=self.M)
         self.entropy_parameters = EntropyParameters(latent_channels=self.M, hyper_latent_channels=self.H, K=self.K)
-        self.precision = precision or engine.DEFAULT_PRECISION
+        self.precision = engine.resolve_precision(precision, latent_channels)
         if self.precision not in MODEL_PRECISIONS:
             raise ValueError(f"precision must be one of {MODEL_PRECISIONS}, got {self.precision}")
 

@@ -41,7 +41,7 @@ class EntropyParameters(nn.Module):
 
     def raw(self, combined_feat: Tensor) -> Tensor:
         """The [B, 2M | 3KM, H, W] output of the 1x1 stack."""
-        return engine.run_sequential_nchw(self._ops, combined_feat, self.precision or engine.DEFAULT_PRECISION)
+        return engine.run_sequential_nchw(self._ops, combined_feat, engine.resolve_precision(self.precision))
 
     def forward(self, combined_feat: Tensor) -> Tuple[Tensor, ...]:
         from .EntropyModels import split_entropy_parameters

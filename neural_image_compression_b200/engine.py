@@ -16,7 +16,16 @@ from . import _lib
 from ._lib import (ConvDesc, DT_BF16, DT_BF16X2, DT_F32, EPI_BIAS, EPI_GDN, EPI_IGDN, EPI_LRELU, LAYOUT_NCHW, LAYOUT_NHWC,
                    PRECISIONS, PREC_FP32, check, current_stream, ptr)
 
-DEFAULT_PRECISION = os.environ.get("NIC_PRECISION", "fp32")
+DEFAULT_PRECISION = os.environ.get("NIC_PRECISION", "auto")
+
+
+def resolve_precision(precision: Optional[str], latent_channels: Optional[int] = None) -> str:
+    """None / "auto" -> the parity-grade tensor-core arm ("bf16x3") where it is built (M = 128: the fused GDN contraction
+    is a 128-channel kernel), else the fp32 CUDA-core arm.  Both meet the reference-parity tolerances."""
+    precision = precision or DEFAULT_PRECISION
+    if precision == "auto":
+        return "bf16x3" if latent_channels == 128 else "fp32"
+    return precision
 
 
 def require_cuda(t: torch.Tensor, what: str):
