@@ -49,7 +49,7 @@ int conv_fwd_fp32_ex(const nic_conv_desc* d, const void* x, const void* w_packed
 
 // x3_tc.cu
 int pack_gdn_x3(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, float* beta_eff, void* gamma_packed, cudaStream_t st);
-int gdn_fwd_tc_x3(const float* x, long npix, int c, int inverse, const void* gamma_packed, const float* beta_eff, void* y, cudaStream_t st);
+int gdn_fwd_tc_x3(const void* x, int pair_in, long npix, int c, int inverse, const void* gamma_packed, const float* beta_eff, void* y, cudaStream_t st);
 size_t packed_first_x3_elems();
 int pack_first_x3(const float* w_ref, void* w_packed, cudaStream_t st);
 int conv_first_x3(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, float* y, cudaStream_t st);
@@ -122,14 +122,15 @@ int encode_image_patch(CUtensorMap* m, const void* base, int n, int c, int h, in
   return NIC_OK;
 }
 
-int encode_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, int c, int box_w, int box_h, int stride) {
+int encode_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, int c, int box_w, int box_h, int stride, int elem_bytes) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t eb = elem_bytes;
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+  cuuint64_t strides[3] = {(cuuint64_t)c * eb, (cuuint64_t)w * c * eb, (cuuint64_t)h * w * c * eb};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};   // 128-byte rows
   cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled(nhwc %dx%dx%dx%d, box %dx%d stride %d) failed: %d", n, h, w, c, box_w,
                                      box_h, stride, (int)r);
@@ -179,12 +180,13 @@ struct TcParams {
   int out_dtype;                               // NIC_DT_*
   long ys_n, ys_c, ys_h, ys_w;                 // output strides (elements), channel offset already applied to y
   int flat_hw;                                 // > 0: 1x1 conv over a flattened pixel list; pixel p -> image p / flat_hw
-  int tma_out;                                 // NHWC bf16 output leaves through shared memory + TMA tensor stores
+  int tma_out;                                 // NHWC output leaves through shared memory + TMA tensor stores: 1 = bf16 (two
+                                               // [128 px][64 ch] panels), 2 = f32 (four [128 px][32 ch] panels)
   int out_c_offset;                            // channel window start inside the output tensor (TMA coordinates)
   int shuffle_cout;                            // > 0: sub-pixel (2x2) output: column n = (py * 2 + px) * shuffle_cout + c goes to
                                                //      pixel (2 oy + py, 2 ox + px), channel c of an fp32 tensor (ConvTranspose2d to RGB)
   int bias_mod;                                // bias index = column % bias_mod (shuffle) ; 0 = plain
-  int dbg;                                     // NIC_TC_DEBUG bits (timing experiments only): 1 skip gamma MMA, 2 skip tensor store, 4 skip direct stores
+  int dbg;                                     // NIC_TC_DEBUG bits (timing experiments only): 1 skip gamma MMA, 2 skip tensor store, 4 skip direct stores, 8 skip the epilogue
   long long* dbg_times;                        // NIC_TC_TRACE: [cta][16 tiles][16] clock64 stamps of the pipeline roles (null = off)
   const float* bias;
   const float* beta;
@@ -392,7 +394,12 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
   }
   const int nvalid_c = p.cout - cbase;                      // channels of this N tile that exist
   auto emit_group = [&](int cg, const float* v) {             // one pixel x 32 channels: to the staging tile or to HBM
-    if (p.tma_out) {
+    if (p.tma_out == 2) {
+      uint8_t* panel = sq + cg * (128 * 128) + row * 128;       // f32: one 128-byte row per pixel and 32-channel group
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(panel + ((j ^ (row & 7)) << 4)) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+    } else if (p.tma_out) {
       uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -508,8 +515,13 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
     if (leader && !(p.dbg & 2)) {
       const int wc = ox0 * p.out_stride + px, hc = oy0 * p.out_stride + py;
       const int lo_off = p.split_out ? p.split_lo_off : 0;
-      for (int h = 0; h < 2; ++h)
-        if (h * 64 < nvalid_c) tma_store_4d(map_o_ptr, sq + h * (128 * 128), p.out_c_offset + lo_off + cbase + h * 64, wc, hc, img);
+      if (p.tma_out == 2) {
+        for (int h = 0; h < 4; ++h)
+          if (h * 32 < nvalid_c) tma_store_4d(map_o_ptr, sq + h * (128 * 128), p.out_c_offset + cbase + h * 32, wc, hc, img);
+      } else {
+        for (int h = 0; h < 2; ++h)
+          if (h * 64 < nvalid_c) tma_store_4d(map_o_ptr, sq + h * (128 * 128), p.out_c_offset + lo_off + cbase + h * 64, wc, hc, img);
+      }
       tma_store_commit();
     }
   }
@@ -780,7 +792,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t buf = tcount & 1;
       if (!__all_sync(0xffffffffu, wait_or_abort(&sb.acc_full[buf], (tcount >> 1) & 1, &sb, p.status))) break;
       tcgen05_fence_after();
-      for (int b = 0; b < nblk && ok; ++b)
+      for (int b = 0; b < nblk && ok && !(p.dbg & 8); ++b)
         ok = epilogue_block<kEpiWarps>(p, &sb, s_bias, s_beta, sq, smem + p.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane,
                                        (warp - kFirstEpiWarp) >> 2, warp == kFirstEpiWarp && lane == 0, img, ty * p.tile_h + p.blk_roff[b],
                                        tx * p.tile_w + p.blk_coff[b], ph.py, ph.px, ntile * p.nb, gdn_count, b == 0 ? tcount : 0xffffffffu);
@@ -1320,8 +1332,15 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   p.out_c_offset = d->out_c_offset;
   p.tma_out = (!shuffle && d->out_layout == NIC_LAYOUT_NHWC && p.out_dtype == NIC_DT_BF16 && p.nb == 128 && d->c_out % 64 == 0 &&
                ctot % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) ? 1 : 0;
-  // gamma (32 KB, GDN only) + one 32 KB tile that holds the squares for the gamma contraction and then stages the output
-  const int gdn_bytes = (gdn ? 2 * 128 * 128 : 0) + ((gdn || p.tma_out) ? 2 * 128 * 128 : 0);
+  // f32 NHWC outputs (the conv -> GDN scratch of the bf16x3 arm, y / z before the hand-off): 16-byte scattered stores from the
+  // epilogue put it ON the critical path (g_s layer 3, bf16x3: 1.17 ms, 0.91 ms with the stores removed) - stage + TMA store
+  if (!p.tma_out && !shuffle && !gdn && d->out_layout == NIC_LAYOUT_NHWC && p.out_dtype == NIC_DT_F32 && p.nb == 128 && d->c_out % 32 == 0 &&
+      ctot % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && !getenv("NIC_TC_NO_F32_TMA"))
+    p.tma_out = 2;      // (y and z, the f32 tensors the latent hand-off reads: small layers, the ring depth does not matter there)
+  // gamma (32 KB, GDN only) + one tile (32 KB; 64 KB for f32 outputs) that holds the squares for the gamma contraction and
+  // then stages the output
+  const int stage_bytes = p.tma_out == 2 ? 4 * 128 * 128 : ((gdn || p.tma_out) ? 2 * 128 * 128 : 0);
+  const int gdn_bytes = (gdn ? 2 * 128 * 128 : 0) + stage_bytes;
   const int bres_bytes = tt.ntaps * p.nchunks * p.nb * 128;
   p.b_resident = (p.n_ntiles == 1 && p.nb <= 16 && bres_bytes + 2 * p.slot_bytes + gdn_bytes + 1024 <= kMaxDynSmem) ? 1 : 0;
   int b_bytes;
@@ -1340,21 +1359,29 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
       else if (p.nsb < kMaxBSlots && p.nsa * p.slot_bytes + (p.nsb + 1) * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsb;
       else break;
     }
+    {   // timing experiments: NIC_TC_NSA / NIC_TC_NSB force the ring depths (checked against the shared-memory budget)
+      const char* ea = getenv("NIC_TC_NSA"); const char* eb = getenv("NIC_TC_NSB");
+      const int fa = ea ? atoi(ea) : 0, fb = eb ? atoi(eb) : 0;
+      if ((fa || fb) && tt.nphases > 1) {
+        const int na = fa ? fa : p.nsa, nb2 = fb ? fb : p.nsb;
+        if (na >= 2 && na <= kMaxSlots && nb2 >= 2 && nb2 <= kMaxBSlots && na * p.slot_bytes + nb2 * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) { p.nsa = na; p.nsb = nb2; }
+      }
+    }
     b_bytes = p.nsb * 128 * 128;
   }
   p.off_a = 0; p.off_b = p.nsa * p.slot_bytes; p.off_gamma = p.off_b + b_bytes; p.off_sq = p.off_gamma + (gdn ? 2 * 128 * 128 : 0);
-  p.smem_bytes = p.off_sq + ((gdn || p.tma_out) ? 2 * 128 * 128 : 0) + 1024;
+  p.smem_bytes = p.off_sq + stage_bytes + 1024;
 
   CUtensorMap map_a, map_w, map_g, map_o;
   if (p.split_out && !p.tma_out) return fail(NIC_E_BADALIGN, "conv bf16x3: bf16-pair output must be 16-byte aligned");
-  if (int rc = encode_nhwc(&map_a, x, gn, gh, gw, (x3 ? 2 : 1) * d->c_in, p.pw_cols, p.ph_rows, tt.in_stride)) return rc;
+  if (int rc = encode_nhwc(&map_a, x, gn, gh, gw, (x3 ? 2 : 1) * d->c_in, p.pw_cols, p.ph_rows, tt.in_stride, 2)) return rc;
   if (int rc = encode_2d(&map_w, w_packed, static_cast<uint64_t>(x3 ? 3 : 1) * d->c_in, static_cast<uint64_t>(tt.ntaps) * p.cout_pad, 64, p.nb)) return rc;
   if (gdn) { if (int rc = encode_2d(&map_g, gdn_gamma, 128, 128, 64, 128)) return rc; }
   else map_g = map_w;
   if (p.tma_out) {
     // the output tensor (all ctot channels), walked with the output stride of the phase decomposition
     const int on = flat ? 1 : d->n, oh = flat ? gh : d->h_out, ow = flat ? gw : d->w_out;
-    if (int rc = encode_nhwc(&map_o, y, on, oh, ow, ctot, kTileW, kTileH, tt.out_stride)) return rc;
+    if (int rc = encode_nhwc(&map_o, y, on, oh, ow, ctot, kTileW, kTileH, tt.out_stride, p.tma_out == 2 ? 4 : 2)) return rc;
   } else map_o = map_w;
 
   static bool attr_set = false;
@@ -1392,7 +1419,7 @@ static int launch_first(const nic_conv_desc* d, const void* x, const void* w_pac
   CUtensorMap map_w, map_g, map_o;
   if (int rc = encode_2d(&map_w, w_packed, 128, 128, 64, 128)) return rc;
   if (int rc = encode_2d(&map_g, gdn_gamma, 128, 128, 64, 128)) return rc;
-  if (int rc = encode_nhwc(&map_o, y, d->n, d->h_out, d->w_out, 128, kTileW, kTileH, 1)) return rc;
+  if (int rc = encode_nhwc(&map_o, y, d->n, d->h_out, d->w_out, 128, kTileW, kTileH, 1, 2)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     if (int rc = check_cuda(cudaFuncSetAttribute(conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048), "cudaFuncSetAttribute")) return rc;
@@ -1427,15 +1454,20 @@ int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, con
     if (!gdn_gamma || !gdn_beta) return fail(NIC_E_BADSHAPE, "conv: GDN epilogue without gamma/beta");
     if (d->out_dtype != NIC_DT_BF16X2 || d->out_layout != NIC_LAYOUT_NHWC || d->out_c_total != 0)
       return fail(NIC_E_UNSUPPORTED, "conv bf16x3 + GDN: output must be a plain NHWC bf16-pair tensor");
+    int pair_in = 0;
     if (small_cin(d)) {
       if (int rc = check_first_layer(d)) return rc;
       if (int rc = conv_first_x3(d, x, w_packed, bias, static_cast<float*>(workspace), st)) return rc;
     } else {
+      // the conv hands its result to the GDN kernel as a bf16 hi/lo pair tensor (same 4 B / element as f32): that is the output
+      // format conv_tc_kernel stores through its 32 KB staging tile + TMA, which leaves the weight ring 6 slots; f32 rows
+      // would need 16-byte scattered stores (measured +0.22 ms on g_s layer 3) or a 64 KB staging tile (ring down to 4 slots)
       nic_conv_desc c1 = *d;
-      c1.epilogue = NIC_EPI_BIAS; c1.out_dtype = NIC_DT_F32; c1.out_layout = NIC_LAYOUT_NHWC; c1.out_c_total = 0; c1.out_c_offset = 0;
+      c1.epilogue = NIC_EPI_BIAS; c1.out_dtype = NIC_DT_BF16X2; c1.out_layout = NIC_LAYOUT_NHWC; c1.out_c_total = 0; c1.out_c_offset = 0;
       if (int rc = launch_tc(&c1, tt, x, w_packed, bias, nullptr, nullptr, workspace, st)) return rc;
+      pair_in = 1;
     }
-    return gdn_fwd_tc_x3(static_cast<const float*>(workspace), static_cast<long>(d->n) * d->h_out * d->w_out, d->c_out,
+    return gdn_fwd_tc_x3(workspace, pair_in, static_cast<long>(d->n) * d->h_out * d->w_out, d->c_out,
                          d->epilogue == NIC_EPI_IGDN, gdn_gamma, gdn_beta, y, st);
   }
   if (d->precision != NIC_PREC_BF16) return fail(NIC_E_UNSUPPORTED, "conv: precision %d", d->precision);

@@ -86,6 +86,8 @@ struct __align__(8) GdnBarriers {
   volatile int abort_flag;
 };
 
+// PAIR_IN: x arrives as a bf16 hi/lo pair tensor [npix][256] (what conv_tc_kernel writes fastest) instead of f32 [npix][128]
+template <bool PAIR_IN>
 __global__ void __launch_bounds__(kGdnThreads, 1)
 gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_o,
               const __grid_constant__ GdnX3Params p) {
@@ -122,8 +124,10 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         const uint32_t b = it & 1;
         if (!wait_abort(&sb.x_empty[b], ((it >> 1) & 1) ^ 1, &sb.abort_flag, p.status)) break;
         mbar_expect_tx(&sb.x_full[b], 4 * kPanel);
+        // f32: box k = channels [32 k, 32 k + 32); pairs: panels land as [hi 0..63 | lo 0..63 | hi 64..127 | lo 64..127]
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tma_load_2d(bufs + (b * 4 + k) * kPanel, &map_x, &sb.x_full[b], k * 32, tile * 128);
+        for (int k = 0; k < 4; ++k)
+          tma_load_2d(bufs + (b * 4 + k) * kPanel, &map_x, &sb.x_full[b], PAIR_IN ? (k >> 1) * 64 + (k & 1) * 128 : k * 32, tile * 128);
       }
     }
   } else {
@@ -145,9 +149,19 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const uint32_t off = (static_cast<uint32_t>(j) ^ swz) << 4;
-        const float4 v = *reinterpret_cast<const float4*>(my_h + off), w = *reinterpret_cast<const float4*>(my_l + off);
-        xr[j * 4] = v.x; xr[j * 4 + 1] = v.y; xr[j * 4 + 2] = v.z; xr[j * 4 + 3] = v.w;
-        xr[32 + j * 4] = w.x; xr[32 + j * 4 + 1] = w.y; xr[32 + j * 4 + 2] = w.z; xr[32 + j * 4 + 3] = w.w;
+        if (PAIR_IN) {        // chunk j of the hi and lo rows: channels 8 j .. 8 j + 7 of this thread's half, x = hi + lo
+          const uint4 h = *reinterpret_cast<const uint4*>(my_h + off), l = *reinterpret_cast<const uint4*>(my_l + off);
+          const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            xr[j * 8 + e * 2] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            xr[j * 8 + e * 2 + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+          }
+        } else {
+          const float4 v = *reinterpret_cast<const float4*>(my_h + off), w = *reinterpret_cast<const float4*>(my_l + off);
+          xr[j * 4] = v.x; xr[j * 4 + 1] = v.y; xr[j * 4 + 2] = v.z; xr[j * 4 + 3] = v.w;
+          xr[32 + j * 4] = w.x; xr[32 + j * 4 + 1] = w.y; xr[32 + j * 4 + 2] = w.z; xr[32 + j * 4 + 3] = w.w;
+        }
       }
       if (leader) gtrace(p, it, 2);
       // squares over the rows just read (this thread is their only reader)
@@ -469,8 +483,8 @@ int pack_gdn_x3(int32_t c, float beta_min, const float* beta_raw, const float* g
   return check_launch("pack_gdn_x3_kernel");
 }
 
-// x [npix][128] f32 -> y [npix][256] bf16 pairs
-int gdn_fwd_tc_x3(const float* x, long npix, int c, int inverse, const void* gamma_packed, const float* beta_eff, void* y, cudaStream_t st) {
+// x [npix][128] f32 (or, pair_in, [npix][256] bf16 pairs) -> y [npix][256] bf16 pairs
+int gdn_fwd_tc_x3(const void* x, int pair_in, long npix, int c, int inverse, const void* gamma_packed, const float* beta_eff, void* y, cudaStream_t st) {
   if (c != 128) return fail(NIC_E_UNSUPPORTED, "gdn bf16x3: built for c = 128 (got %d)", c);
   if ((reinterpret_cast<uintptr_t>(x) & 127) || (reinterpret_cast<uintptr_t>(y) & 127) || (reinterpret_cast<uintptr_t>(gamma_packed) & 127))
     return fail(NIC_E_BADALIGN, "gdn bf16x3: tensors must be 128-byte aligned for TMA");
@@ -481,17 +495,20 @@ int gdn_fwd_tc_x3(const float* x, long npix, int c, int inverse, const void* gam
   if (!p.status) return fail(NIC_E_CUDA, "gdn bf16x3: cannot allocate the status word");
   p.dbg_times = reinterpret_cast<long long*>(g_trace_buffer);
   CUtensorMap map_x, map_g, map_o;
-  if (int rc = encode_2d_ex(&map_x, x, 4, 128, static_cast<uint64_t>(npix), 32, 128)) return rc;
+  if (pair_in) { if (int rc = encode_2d(&map_x, x, 256, static_cast<uint64_t>(npix), 64, 128)) return rc; }
+  else if (int rc = encode_2d_ex(&map_x, x, 4, 128, static_cast<uint64_t>(npix), 32, 128)) return rc;
   if (int rc = encode_2d(&map_g, gamma_packed, 128, 256, 64, 128)) return rc;
   if (int rc = encode_2d(&map_o, y, 256, static_cast<uint64_t>(npix), 64, 128)) return rc;
   const int smem_bytes = 12 * kPanel + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(gdn_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
+    if (int rc = check_cuda(cudaFuncSetAttribute(gdn_x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
+    if (int rc = check_cuda(cudaFuncSetAttribute(gdn_x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
     attr_set = true;
   }
   const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
-  gdn_x3_kernel<<<grid, kGdnThreads, smem_bytes, st>>>(map_x, map_g, map_o, p);
+  if (pair_in) gdn_x3_kernel<true><<<grid, kGdnThreads, smem_bytes, st>>>(map_x, map_g, map_o, p);
+  else gdn_x3_kernel<false><<<grid, kGdnThreads, smem_bytes, st>>>(map_x, map_g, map_o, p);
   return check_launch("gdn_x3_kernel");
 }
 

@@ -1,4 +1,5 @@
-"""Pipeline trace of conv_tc_kernel for one layer (GPU box):  python tools/trace_layer.py k2|d2|d3|k3|ep3"""
+"""Pipeline trace of conv_tc_kernel for one layer (GPU box):  python tools/trace_layer.py k2|d2|d3|k3|ep3|k2c|d2c [bf16|bf16x3]
+(k2c / d2c: the conv alone with a bias epilogue and f32 NHWC output, as the bf16x3 arm runs it before gdn_x3_kernel)"""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -8,6 +9,7 @@ from neural_image_compression_b200._lib import EPI_BIAS, EPI_GDN, EPI_IGDN, EPI_
 from neural_image_compression_b200.gdn import GDN
 
 which = sys.argv[1] if len(sys.argv) > 1 else "k2"
+prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
 B = 16
 dev = torch.device("cuda:0")
 cfg = {
@@ -17,12 +19,15 @@ cfg = {
     "d3": (nn.ConvTranspose2d(128, 3, 5, 2, 2, output_padding=1), EPI_BIAS, (256, 384), dict(out_layout=LAYOUT_NCHW, out_dtype=torch.float32)),
     "ep3": (nn.Conv2d(640, 1152, 1), EPI_BIAS, (32, 48), dict(out_layout=LAYOUT_NCHW, out_dtype=torch.float32)),
     "l1": (nn.Conv2d(3, 128, 5, 2, 2), EPI_GDN, (512, 768), dict(in_layout=LAYOUT_NCHW)),
+    "k2c": (nn.Conv2d(128, 128, 5, 2, 2), EPI_BIAS, (256, 384), dict(out_dtype=torch.float32)),
+    "d2c": (nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1), EPI_BIAS, (128, 192), dict(out_dtype=torch.float32)),
 }[which]
 conv, epi, (h, w), kw = cfg
 conv = conv.to(dev)
 g = GDN(128, inverse=(epi == EPI_IGDN)).to(dev) if epi in (EPI_GDN, EPI_IGDN) else None
 op = engine.ConvOp(conv, epi, gdn=g)
-x = torch.randn(B, h, w, conv.in_channels, device=dev).to(torch.bfloat16)
+x = torch.randn(B, h, w, conv.in_channels, device=dev)
+x = engine.to_pair(x) if prec == "bf16x3" else x.to(torch.bfloat16)
 if which == "l1":
     x = torch.rand(B, 3, h, w, device=dev)
     names_l1 = ["P:start", "P:patch_ready", "P:fetched_next", "P:a_empty", "P:built", "M:acc_empty", "M:a_full", "E:acc_full",
@@ -30,12 +35,12 @@ if which == "l1":
 lib = _lib.load()
 lib.nic_debug_set_trace.argtypes = [C.c_void_p]; lib.nic_debug_set_trace.restype = None
 for _ in range(3):
-    op.run(x, B, h, w, "bf16", **kw)
+    op.run(x, B, h, w, prec, **kw)
 torch.cuda.synchronize()
 buf = torch.zeros(148 * 32 * 16, dtype=torch.int64, device=dev)
 lib.nic_debug_set_trace(buf.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); op.run(x, B, h, w, "bf16", **kw); e1.record()
+e0.record(); op.run(x, B, h, w, prec, **kw); e1.record()
 torch.cuda.synchronize()
 lib.nic_debug_set_trace(None)
 t = buf.cpu().reshape(148, 32, 16)
