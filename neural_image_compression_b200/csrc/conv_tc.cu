@@ -648,6 +648,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t sa = 0, pa = 0, sbi = 0, pb = 0;      // ring slot + phase parity of the A and B rings
         bool ok = true;
         if (b_res) { ok = wait_or_abort(&sb.bres_full, 0, &sb, p.status); tcgen05_fence_after(); }
+        // 3x3 stride-1 layers (the sub-pixel form of the 128 -> 3 transposed conv): the nine tap offsets live in registers and
+        // the tap loop is unrolled - 36 back-to-back MMAs per chunk with no shared-memory loads or loop control between them
+        uint32_t ao[9], bo[9];
+        const bool nine = p.nphases == 1 && p.phases[0].nplanes == 1 && p.nslabs == 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { ao[i] = nine ? s_tap_aoff[i] : 0u; bo[i] = nine ? s_tap_brow[i] * nchunks * bb16 : 0u; }
         for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step, ++tcount) {
           int ntile, phase, img, ty, tx;
           decode_tile(p, tile, ntile, phase, img, ty, tx);
@@ -668,7 +674,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tcgen05_fence_after();
               const uint32_t a_slot_lo = a_base_lo + sa * slot16 + blk_off;
               const int t_begin = ph.plane_tap_begin[pl], t_end = ph.plane_tap_begin[pl + 1];
-              if (b_res) {
+              if (nine) {
+                if (live) {
+                  const uint32_t bc = b_base_lo + chunk * bb16;
+#pragma unroll
+                  for (int i = 0; i < 9; ++i) {
+                    const uint32_t b_lo = bc + bo[i], a_lo0 = a_slot_lo + ao[i];
+                    umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo, b_hi, idesc, i == 0 ? accumulate : 1u);
+                    umma_bf16_lohi(d_tmem, a_lo0 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
+                    umma_bf16_lohi(d_tmem, a_lo0 + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
+                    umma_bf16_lohi(d_tmem, a_lo0 + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+                  }
+                  accumulate = 1;
+                }
+              } else if (b_res) {
                 if (live) {
                   for (int t = t_begin; t < t_end; ++t) {
                     const uint32_t b_lo = b_base_lo + (s_tap_brow[t] * nchunks + chunk) * bb16;
