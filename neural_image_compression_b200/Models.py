@@ -170,3 +170,125 @@ class JointAutoregressiveHierarchical(nn.Module):
             else:
                 out.update({"weights": ly["weights"], "mus": ly["mus"], "sigmas": ly["sigmas"]})
         return out
+
+
+class ScalableImageCoding(nn.Module):
+    """The scalable-coding variant of /root/reference/Models.py:208-338: the JointAutoregressiveHierarchical trunk at M
+    channels with y split into a base part y1 (M1 channels) and an enhancement part y2 (M - M1), each with its own
+    (context model, entropy-parameter net, conditional), both heads sharing the hyper features psi.
+
+    The reference's forward raises as committed; this class implements the evident intent,
+    i.e. the reference with these four repairs, and nothing else:
+      * ``self.factorized_entropy_model(z_in, debug)`` (Models.py:302)  ->  ``self.factorized_entropy_model(z_in)``
+      * K == 1: ``conditional(y1, mu1=, sigma1=)`` (:293-294, :305-306)  ->  ``conditional(y1, mu=mu1, sigma=sigma1)``
+      * K > 1: ``params1`` assigned twice (:298-299)                      ->  ``params2`` holds the second head
+      * ``LatentSpaceTransform`` (:256, :319; inconsistent channel counts, Components.py:129-132) is NOT built: the output
+        dict has no 'F_tilde', and reference checkpoints load with their ``LST.*`` entries ignored.
+    Parity for this class is against the reference's own sub-modules called in that repaired order
+    (oracle/make_golden.py: scalable cases) - "parity unpinned" by the reference itself, which has no runnable forward.
+    M = 192 runs on the fp32 arm (the tensor-core GDN kernels are built for 128 channels).
+    """
+
+    def __init__(self, latent_channels: int = 192, base_channels: int = 128, K: int = 1, *, precision: Optional[str] = None):
+        super().__init__()
+        if not isinstance(latent_channels, int) or latent_channels < 1:
+            raise ValueError(f"latent_channels must be int >= 1, got {latent_channels}")
+        if not isinstance(K, int) or K < 1:
+            raise ValueError(f"K must be int >= 1, got {K}")
+        if not isinstance(base_channels, int) or not 0 < base_channels < latent_channels:
+            raise ValueError(f"base_channels must be an int in (0, latent_channels), got {base_channels}")
+        self.M, self.M1, self.M2 = latent_channels, base_channels, latent_channels - base_channels
+        self.H, self.K = latent_channels, K
+        self.distribution = "Mean-Scale Gaussian" if K == 1 else "Mixture of Gaussians"
+        self.conditional = GaussianConditional() if K == 1 else GaussianMixtureConditional()
+        # construction order follows Models.py:237-254 so a seeded build draws the reference's initial weights
+        self.encoder = Encoder5x5(latent_channels=self.M)
+        self.decoder = Decoder5x5(latent_channels=self.M)
+        self.hyper_encoder = HyperEncoder5x5(latent_channels=self.M)
+        self.hyper_decoder = HyperDecoder5x5(latent_channels=self.M)
+        self.factorized_entropy_model = FactorizedEntropyBottleneck(self.M)
+        self.context_model_1 = ContextModel(latent_channels=self.M1)
+        self.context_model_2 = ContextModel(latent_channels=self.M2)
+        self.entropy_parameters_1 = EntropyParameters(latent_channels=self.M1, hyper_latent_channels=self.H, K=self.K)
+        self.entropy_parameters_2 = EntropyParameters(latent_channels=self.M2, hyper_latent_channels=self.H, K=self.K)
+        self.precision = engine.resolve_precision(precision, None)          # fp32 unless asked otherwise
+        if self.precision != "fp32":
+            raise ValueError("ScalableImageCoding runs on the fp32 arm (its transforms are not 128-channel)")
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
+        return super().load_state_dict({k: v for k, v in state_dict.items() if not k.startswith("LST.")}, strict=strict, **kwargs)
+
+    def forward(self, x: torch.Tensor, training: bool = True, debug=False, *,
+                noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        engine.require_cuda(x, "x")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected x of shape [B, 3, H, W], got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        if H % 64 or W % 64:
+            raise ValueError(f"H and W must be multiples of 64; got {H}x{W}")
+        prec, M, M1, M2, K = "fp32", self.M, self.M1, self.M2, self.K
+        x = x.contiguous().float()
+        hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
+        with torch.cuda.device(x.device), torch.no_grad():
+            noise_z = noise_y = None
+            if training:
+                noise_z, noise_y = noise if noise is not None else (torch.rand((B, M, hz, wz), device=x.device) - 0.5,
+                                                                    torch.rand((B, M, hy, wy), device=x.device) - 0.5)
+            qmode = Q_NOISE if training else Q_ROUND
+            a, h, w, layout = x, H, W, LAYOUT_NCHW
+            for op in self.encoder.ops:
+                a = op.run(a, B, h, w, prec, in_layout=layout, out_layout=LAYOUT_NHWC)
+                h, w = engine.conv_out_hw(op.conv, h, w)
+                layout = LAYOUT_NHWC
+            y_nhwc = a
+            y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, qmode, noise_y, torch.float32)
+            a, h, w = y_nhwc, hy, wy
+            for op in self.hyper_encoder.ops:
+                a = op.run(a, B, h, w, prec)
+                h, w = engine.conv_out_hw(op.conv, h, w)
+            z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, qmode, noise_z, torch.float32)
+            # psi once, into head 1's concat buffer [phi1 (2 M1) | psi (2 M)]; head 2's buffer gets a copy of the window
+            comb1 = torch.empty((B, hy, wy, 2 * M1 + 2 * M), dtype=torch.float32, device=x.device)
+            comb2 = torch.empty((B, hy, wy, 2 * M2 + 2 * M), dtype=torch.float32, device=x.device)
+            a, h, w = z_in_nhwc, hz, wz
+            hs = self.hyper_decoder.ops
+            for i, op in enumerate(hs):
+                if i == len(hs) - 1:
+                    op.run(a, B, h, w, prec, out=comb1, out_c_total=2 * M1 + 2 * M, out_c_offset=2 * M1)
+                else:
+                    a = op.run(a, B, h, w, prec)
+                h, w = engine.conv_out_hw(op.conv, h, w)
+            comb2[..., 2 * M2:] = comb1[..., 2 * M1:]
+            y1, y2 = torch.split(y_in, [M1, M2], dim=1)                   # Models.py:279 (views, as in the reference)
+            y1c, y2c = y1.contiguous(), y2.contiguous()
+            heads = []
+            for ctx, ep, comb, mi, yi_nhwc, yi in ((self.context_model_1, self.entropy_parameters_1, comb1, M1,
+                                                    y_in_nhwc[..., :M1].contiguous(), y1c),
+                                                   (self.context_model_2, self.entropy_parameters_2, comb2, M2,
+                                                    y_in_nhwc[..., M1:].contiguous(), y2c)):
+                ctx.masked.apply_mask_()
+                ctx.masked._op.run(yi_nhwc, B, hy, wy, prec, out=comb, out_c_total=comb.shape[-1], out_c_offset=0)
+                a = ep.ops[0].run(comb, B, hy, wy, prec)
+                a = ep.ops[1].run(a, B, hy, wy, prec)
+                raw = ep.ops[2].run(a, B, hy, wy, prec, out_layout=LAYOUT_NCHW, out_dtype=torch.float32)
+                heads.append(gm_likelihood(yi, raw, mi, K, Q_PASSTHRU, full=True, want_y_in=False))
+            _, p_z, logp_z, parts_z = self.factorized_entropy_model.likelihood(z_in, Q_PASSTHRU)
+            a, h, w = y_in_nhwc, hy, wy
+            dec = self.decoder.ops
+            for i, op in enumerate(dec):
+                last = i == len(dec) - 1
+                a = op.run(a, B, h, w, prec, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC)
+                h, w = engine.conv_out_hw(op.conv, h, w)
+            x_hat = a
+        l1, l2 = heads
+        l1["logp"]._nic_partials, l2["logp"]._nic_partials, logp_z._nic_partials = l1["partials"], l2["partials"], parts_z
+        out = {
+            "x_hat": x_hat, "y": y, "y_in": y_in, "y1": y1, "y2": y2, "z": z, "z_in": z_in, "p_z": p_z, "logp_z": logp_z,
+            "p_y1": l1["p"], "logp_y1": l1["logp"], "p_y2": l2["p"], "logp_y2": l2["logp"], "training": training,
+        }
+        if K == 1:
+            out.update({"mu1": l1["mu"], "sigma1": l1["sigma"], "mu2": l2["mu"], "sigma2": l2["sigma"]})
+        else:
+            out.update({"weights1": l1["weights"], "mus1": l1["mus"], "sigmas1": l1["sigmas"],
+                        "weights2": l2["weights"], "mus2": l2["mus"], "sigmas2": l2["sigmas"]})
+        return out

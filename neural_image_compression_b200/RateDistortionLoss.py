@@ -58,3 +58,44 @@ def rd_loss(model_out: dict, x: torch.Tensor, lambda_rd: float):
         "psnr_per_image": -10 * torch.log10(mse_per_image + 1e-8),
         "bits_y": s[6], "bits_z": s[7], "bits_total": s[6] + s[7],
     }
+
+
+def vision_rd_loss(model_out: dict, x: torch.Tensor, lambda_rd: float, gamma: float = 0.0, frozen_activation=None, V=None):
+    """``vision_rd_loss`` of /root/reference/RateDistortionLoss.py:52-121 for ScalableImageCoding outputs: rate terms of the
+    two latent parts and of z, reconstruction MSE / PSNR, ``loss = bpp_total + lambda_rd * mse`` (:98, no 255^2 here).
+    The feature-space term (:89-95) needs a frozen third-party detector and the latent-space transform, neither of which
+    is on this path: ``frozen_activation`` / ``V`` must be None and 'vision_mse' is 0.0, as in the reference's own
+    ``V is None`` branch."""
+    if frozen_activation is not None or V is not None:
+        raise NotImplementedError("the feature-space distortion term (frozen detector + LST) is outside the hot path")
+    lib = _lib.load()
+    x_hat = model_out["x_hat"]
+    engine.require_cuda(x_hat, "x_hat")
+    x = x.to(x_hat.device).contiguous().float()
+    x_hat = x_hat.contiguous().float()
+    b, chw, npix = x.size(0), x[0].numel(), x.size(2) * x.size(3)
+    with torch.cuda.device(x_hat.device):
+        p1, p2, pz = (_logp_partials(model_out[k]) for k in ("logp_y1", "logp_y2", "logp_z"))
+        se = engine.partials(b, x_hat.device)
+        check(lib.nic_sse_fwd(ptr(x_hat), ptr(x), b, chw, ptr(se), current_stream()), "nic_sse_fwd")
+        rows, scal = [], []
+        for py in (p1, p2):                      # the same fold as rd_loss, once per latent part (bits_z / mse repeat)
+            per_image = torch.empty((3, b), dtype=torch.float32, device=x_hat.device)
+            scalars = torch.empty(8, dtype=torch.float32, device=x_hat.device)
+            check(lib.nic_rd_finalize(ptr(py), ptr(pz), ptr(se), b, npix, chw, 0.0, ptr(per_image), ptr(scalars),
+                                      current_stream()), "nic_rd_finalize")
+            rows.append(per_image); scal.append(scalars)
+    s1, s2 = scal[0].tolist(), scal[1].tolist()
+    bpp_y1, bpp_y2, bpp_z, mse, psnr = s1[0], s2[0], s1[1], s1[3], s1[4]
+    bpp_total = bpp_y1 + bpp_y2 + bpp_z
+    mse_per_image = rows[0][2]
+    bits_y1, bits_y2, bits_z = s1[6], s2[6], s1[7]
+    return {
+        "loss": scal[0][0] + scal[1][0] + scal[0][1] + lambda_rd * scal[0][3],
+        "bpp_y1": bpp_y1, "bpp_y2": bpp_y2, "bpp_y": bpp_y1 + bpp_y2, "bpp_z": bpp_z, "bpp_total": bpp_total,
+        "mse": mse, "reconstruction_mse": mse, "psnr": psnr, "vision_mse": 0.0,
+        "mse_per_image": mse_per_image, "reconstruction_mse_per_image": mse_per_image,
+        "psnr_per_image": -10 * torch.log10(mse_per_image + 1e-8), "vision_mse_per_image": 0.0,
+        "bits_y1": bits_y1, "bits_y2": bits_y2, "bits_y": bits_y1 + bits_y2, "bits_z": bits_z,
+        "bits_total": bits_y1 + bits_y2 + bits_z,
+    }

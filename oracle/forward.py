@@ -109,19 +109,19 @@ def mask_a(weight):
     return m
 
 
-def context(sd, y_in, dtype=torch.float32):
+def context(sd, y_in, dtype=torch.float32, prefix="context_model"):
     """ContextModel / MaskedConv2d('A'), ContextModels.py:18-20, 26-33."""
-    w = _p(sd, "context_model.masked.weight", dtype)
+    w = _p(sd, f"{prefix}.masked.weight", dtype)
     w = w * mask_a(w)
-    return F.conv2d(y_in, w, _p(sd, "context_model.masked.bias", dtype), padding=2)
+    return F.conv2d(y_in, w, _p(sd, f"{prefix}.masked.bias", dtype), padding=2)
 
 
-def entropy_parameters_raw(sd, combined, dtype=torch.float32):
+def entropy_parameters_raw(sd, combined, dtype=torch.float32, prefix="entropy_parameters"):
     """EntropyParameters.net, ParametersModels.py:21-35: three 1x1 convs, LeakyReLU(0.01) between."""
     h = combined
     for i in (0, 2, 4):
-        h = F.conv2d(h, _p(sd, f"entropy_parameters.net.{i}.weight", dtype),
-                     _p(sd, f"entropy_parameters.net.{i}.bias", dtype))
+        h = F.conv2d(h, _p(sd, f"{prefix}.net.{i}.weight", dtype),
+                     _p(sd, f"{prefix}.net.{i}.bias", dtype))
         if i != 4:
             h = F.leaky_relu(h, 0.01)
     return h
@@ -243,3 +243,54 @@ def rd_loss(out, x, lambda_rd: float):
         "psnr_per_image": psnr_per_image.detach(), "bits_y": bits_y.mean().item(),
         "bits_z": bits_z.mean().item(), "bits_total": (bits_y + bits_z).mean().item(),
     }
+
+
+def forward_scalable(sd, x, M: int, M1: int, K: int, training: bool = False,
+                     noise_z: Optional[torch.Tensor] = None, noise_y: Optional[torch.Tensor] = None,
+                     dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """ScalableImageCoding.forward, Models.py:259-338, with the four repairs listed in SURVEY.md section 2.4 (the committed
+    forward raises): factorized(z_in) without the stray argument, conditional(y_i, mu=, sigma=) keyword names, the second
+    parameter dict bound to params2, and no LatentSpaceTransform / 'F_tilde'."""
+    x = x.to("cpu", dtype)
+    y = analysis(sd, x, dtype)
+    z = hyper_analysis(sd, y, dtype)
+    if training:
+        z_in, y_in = z + noise_z.to(dtype), y + noise_y.to(dtype)
+    else:
+        z_in, y_in = torch.round(z), torch.round(y)
+    y1, y2 = torch.split(y_in, [M1, M - M1], dim=1)                                   # Models.py:279
+    psi = hyper_synthesis(sd, z_in, dtype)
+    out = {"y": y, "y_in": y_in, "y1": y1, "y2": y2, "z": z, "z_in": z_in, "training": training}
+    for i, (yi, mi) in enumerate(((y1, M1), (y2, M - M1)), start=1):
+        phi = context(sd, yi, dtype, prefix=f"context_model_{i}")                    # :284-285
+        raw = entropy_parameters_raw(sd, torch.cat([phi, psi], dim=1), dtype, prefix=f"entropy_parameters_{i}")   # :287-299
+        params = split_parameters(raw, mi, K)
+        p = conditional_likelihood(yi, params, K)                                     # :305-306
+        out[f"p_y{i}"], out[f"logp_y{i}"] = p, torch.log(p)
+        if K == 1:
+            out[f"mu{i}"], out[f"sigma{i}"] = params
+        else:
+            out[f"weights{i}"], out[f"mus{i}"], out[f"sigmas{i}"] = params
+    p_z = factorized_likelihood(sd, z_in, dtype)                                      # :302
+    out["p_z"], out["logp_z"] = p_z, torch.log(p_z)
+    out["x_hat"] = synthesis(sd, y_in, dtype)                                         # :316
+    return out
+
+
+def vision_rd_loss(out, x, lambda_rd: float):
+    """RateDistortionLoss.py:52-121 with frozen_activation = V = None (no feature-space term)."""
+    x = x.to(out["x_hat"].dtype)
+    ln2 = math.log(2.0)
+    b1 = -torch.sum(out["logp_y1"], dim=(1, 2, 3)) / ln2
+    b2 = -torch.sum(out["logp_y2"], dim=(1, 2, 3)) / ln2
+    bz = -torch.sum(out["logp_z"], dim=(1, 2, 3)) / ln2
+    n = x.size(2) * x.size(3)
+    bpp_y1, bpp_y2, bpp_z = (b1 / n).mean(), (b2 / n).mean(), (bz / n).mean()
+    bpp_total = bpp_y1 + bpp_y2 + bpp_z
+    mse_i = torch.mean((out["x_hat"] - x) ** 2, dim=(1, 2, 3))
+    mse = mse_i.mean()
+    return {"loss": bpp_total + lambda_rd * mse, "bpp_y1": bpp_y1.item(), "bpp_y2": bpp_y2.item(), "bpp_y": (bpp_y1 + bpp_y2).item(),
+            "bpp_z": bpp_z.item(), "bpp_total": bpp_total.item(), "mse": mse.item(), "reconstruction_mse": mse.item(),
+            "psnr": (-10 * torch.log10(mse + 1e-8)).item(), "vision_mse": 0.0, "mse_per_image": mse_i.detach(),
+            "psnr_per_image": (-10 * torch.log10(mse_i + 1e-8)).detach(), "bits_y1": b1.mean().item(), "bits_y2": b2.mean().item(),
+            "bits_y": (b1 + b2).mean().item(), "bits_z": bz.mean().item(), "bits_total": (b1 + b2 + bz).mean().item()}

@@ -8,7 +8,7 @@ reference classes are imported unmodified with two stand-ins placed in
   * ``compressai.layers.gdn.GDN``: oracle/gdn.py (third-party arithmetic that
     is absent from /root/reference and from this image - parity unpinned there).
 
-Usage:  python -m oracle.make_golden          (from the repo root)
+Usage:  python -m oracle.make_golden [scalable]          (from the repo root)
 """
 from __future__ import annotations
 
@@ -89,6 +89,80 @@ def build_reference_model(Models, M, K, init):
     return model
 
 
+SCALABLE_CASES = {
+    # name: (M, M1, K, input shape, init) - BASELINE.json configs[4]'s model at parity-test size
+    "c5_scalable_k1_128_calib": (192, 128, 1, (1, 3, 128, 128), "calib"),
+    "c5_scalable_k3_64x128_calib": (192, 128, 3, (2, 3, 64, 128), "calib"),
+}
+
+
+def apply_init_scalable(sd, init: str):
+    gy, gz, sigma_bias = INITS[init]
+    for k in ("encoder.net.6.weight", "encoder.net.6.bias"):
+        sd[k] = sd[k] * gy
+    for k in ("hyper_encoder.net.4.weight", "hyper_encoder.net.4.bias"):
+        sd[k] = sd[k] * gz
+    if sigma_bias:
+        for head in ("entropy_parameters_1", "entropy_parameters_2"):
+            b = sd[f"{head}.net.4.bias"].clone()
+            n = b.numel()
+            b[(n // 2 if n % 3 else 2 * n // 3):] += sigma_bias
+            sd[f"{head}.net.4.bias"] = b
+    return sd
+
+
+def reference_scalable_forward(model, x):
+    """The reference's OWN sub-modules of ScalableImageCoding called in the order of Models.py:259-338 with the four repairs
+    of SURVEY.md section 2.4 (the committed forward raises): no stray `debug` argument, keyword names mu= / sigma=, params2
+    bound, LatentSpaceTransform skipped."""
+    y = model.encoder(x)
+    z = model.hyper_encoder(y)
+    z_in, y_in = torch.round(z), torch.round(y)
+    y1, y2 = torch.split(y_in, [model.M1, model.M2], dim=1)
+    psi = model.hyper_decoder(z_in)
+    phi1, phi2 = model.context_model_1(y1), model.context_model_2(y2)
+    par1 = model.entropy_parameters_1(torch.cat([phi1, psi], dim=1))
+    par2 = model.entropy_parameters_2(torch.cat([phi2, psi], dim=1))
+    names = ("mu", "sigma") if model.K == 1 else ("weights", "mus", "sigmas")
+    p_z = model.factorized_entropy_model(z_in)
+    p_y1 = model.conditional(y1, **dict(zip(names, par1)))
+    p_y2 = model.conditional(y2, **dict(zip(names, par2)))
+    out = {"x_hat": model.decoder(y_in), "y": y, "y_in": y_in, "y1": y1, "y2": y2, "z": z, "z_in": z_in, "p_z": p_z,
+           "logp_z": torch.log(p_z), "p_y1": p_y1, "logp_y1": torch.log(p_y1), "p_y2": p_y2, "logp_y2": torch.log(p_y2),
+           "training": False}
+    for i, par in ((1, par1), (2, par2)):
+        for n, v in zip(names, par):
+            out[f"{n}{i}"] = v
+    return out
+
+
+def main_scalable():
+    Models, RDL = import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    for name, (M, M1, K, shape, init) in SCALABLE_CASES.items():
+        torch.manual_seed(0)
+        model = Models.ScalableImageCoding(M, M1, K=K)
+        sd = apply_init_scalable({k: v.clone() for k, v in model.state_dict().items()}, init)
+        model.load_state_dict(sd)
+        digest = state_digest({k: v for k, v in sd.items() if not k.startswith("LST.")})
+        torch.manual_seed(1)
+        x = torch.rand(*shape)
+        with torch.no_grad():
+            out = reference_scalable_forward(model, x)
+            rd = RDL.vision_rd_loss(out, x, 0.005, 0.0)           # the reference's own loss, V = None branch
+        blob = {"x": x.numpy(), "state_digest": np.array(digest), "M": np.array(M), "M1": np.array(M1), "K": np.array(K),
+                "init": np.array(init)}
+        for k, v in out.items():
+            if torch.is_tensor(v):
+                blob["out_" + k] = v.numpy()
+        for k, v in rd.items():
+            blob["rd_" + k] = v.detach().numpy() if torch.is_tensor(v) else np.array(v, dtype=np.float64)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **blob)
+        print(f"{name}: bpp_y1 {rd['bpp_y1']:.6f} bpp_y2 {rd['bpp_y2']:.6f} bpp_z {rd['bpp_z']:.6f} psnr {rd['psnr']:.6f} "
+              f"nonzero y_in {int((out['y_in'] != 0).sum())}/{out['y_in'].numel()} -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 def main():
     Models, RDL = import_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -124,4 +198,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "scalable":
+        main_scalable()            # only the c5_* files; the other vectors stay byte-identical
+    else:
+        main()

@@ -16,7 +16,34 @@ INITS = {"plain": (1.0, 1.0, 0.0), "gain": (136.2, 3.86, 0.0), "calib": (34.0, 3
 
 
 def golden_cases():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "c*.npz")))
+    """JointAutoregressiveHierarchical cases (configs 1-3)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "c[1-4]*.npz")))
+
+
+def scalable_cases():
+    """ScalableImageCoding cases (config 5; the reference's sub-modules in the repaired order, see oracle/make_golden.py)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "c5_*.npz")))
+
+
+def seeded_scalable_model(M, M1, K, init="calib"):
+    from neural_image_compression_b200.Models import ScalableImageCoding
+    torch.manual_seed(0)
+    model = ScalableImageCoding(M, M1, K=K, precision="fp32")
+    if init != "plain":
+        sd = {k: v.clone() for k, v in model.state_dict().items()}
+        gy, gz, sigma_bias = INITS[init]
+        for k in ("encoder.net.6.weight", "encoder.net.6.bias"):
+            sd[k] = sd[k] * gy
+        for k in ("hyper_encoder.net.4.weight", "hyper_encoder.net.4.bias"):
+            sd[k] = sd[k] * gz
+        if sigma_bias:
+            for head in ("entropy_parameters_1", "entropy_parameters_2"):
+                b = sd[f"{head}.net.4.bias"].clone()
+                n = b.numel()
+                b[(n // 2 if n % 3 else 2 * n // 3):] += sigma_bias
+                sd[f"{head}.net.4.bias"] = b
+        model.load_state_dict(sd)
+    return model
 
 
 def load_golden(name):

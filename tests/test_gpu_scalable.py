@@ -1,0 +1,75 @@
+"""GPU: ScalableImageCoding (BASELINE.json configs[4]'s model, reference Models.py:208-338 with the repairs of SURVEY.md
+section 2.4) through the module API -> C ABI, against vectors produced by the reference's own sub-modules."""
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", H.scalable_cases())
+def test_scalable_model_matches_reference_vectors(case):
+    from neural_image_compression_b200.RateDistortionLoss import vision_rd_loss
+    g = H.load_golden(case)
+    M, M1, K, init = int(g["M"]), int(g["M1"]), int(g["K"]), str(g["init"])
+    model = H.seeded_scalable_model(M, M1, K, init).cuda()
+    x = torch.from_numpy(g["x"]).cuda()
+    out = model(x, training=False)
+    rd = vision_rd_loss(out, x, 0.005, 0.0)
+    ref = {k[4:]: g[k] for k in g.files if k.startswith("out_")}
+    want = set(ref) | {"training"}
+    assert set(out) == want, set(out) ^ want
+    for k, v in out.items():
+        if torch.is_tensor(v):
+            assert v.dtype == torch.float32 and tuple(v.shape) == tuple(ref[k].shape), k
+    for name, pre in (("y_in", "y"), ("z_in", "z")):
+        real, ties = H.symbol_mismatches(out[name].cpu().numpy(), ref[name], ref[pre], 2e-3)
+        assert real == 0, (name, real, ties)
+    assert torch.equal(torch.cat([out["y1"], out["y2"]], dim=1), out["y_in"])
+    if (out["y_in"].cpu().numpy() == ref["y_in"]).all() and (out["z_in"].cpu().numpy() == ref["z_in"]).all():
+        for name in ("p_y1", "p_y2", "p_z"):
+            bad, worst = H.likelihood_close(out[name].cpu().numpy(), ref[name])
+            assert bad <= 1e-5 * ref[name].size, (name, bad, worst)
+        xe = float(np.abs(out["x_hat"].cpu().numpy() - ref["x_hat"]).max() / np.abs(ref["x_hat"]).max())
+        assert xe < 1e-4, xe
+    for key in ("bpp_y1", "bpp_y2", "bpp_z", "bpp_total"):
+        assert abs(rd[key] - float(g["rd_" + key])) <= H.BPP_TOL, (key, rd[key], float(g["rd_" + key]))
+    assert abs(rd["psnr"] - float(g["rd_psnr"])) <= H.PSNR_TOL
+    assert abs(float(rd["loss"]) - float(g["rd_loss"])) <= 1e-3 * abs(float(g["rd_loss"]))
+    print(case, {k: rd[k] for k in ("bpp_y1", "bpp_y2", "bpp_z", "psnr")})
+
+
+def test_scalable_rejects_bad_arguments_and_ignores_lst_keys():
+    from neural_image_compression_b200.Models import ScalableImageCoding
+    with pytest.raises(ValueError):
+        ScalableImageCoding(192, 192)
+    with pytest.raises(ValueError):
+        ScalableImageCoding(192, 128, K=0)
+    m = ScalableImageCoding(192, 128, K=1)
+    sd = dict(m.state_dict())
+    sd["LST.net.0.weight"] = torch.zeros(1)          # a reference checkpoint carries the latent-space-transform entries
+    m.load_state_dict(sd)
+
+
+def test_scalable_full_size_image_properties():
+    """BASELINE configs[4] shape (2048 x 1536), one image per GPU: size-independent properties instead of an oracle run."""
+    from neural_image_compression_b200.RateDistortionLoss import vision_rd_loss
+    model = H.seeded_scalable_model(192, 128, 1, "calib").cuda()
+    x = H.seeded_input((1, 3, 1536, 2048)).cuda()
+    out = model(x, training=False)
+    rd = vision_rd_loss(out, x, 0.005, 0.0)
+    assert tuple(out["y"].shape) == (1, 192, 96, 128) and tuple(out["z"].shape) == (1, 192, 24, 32)
+    assert tuple(out["p_y1"].shape) == (1, 128, 96, 128) and tuple(out["p_y2"].shape) == (1, 64, 96, 128)
+    assert torch.equal(torch.round(out["y"]), out["y_in"]) and torch.equal(torch.cat([out["y1"], out["y2"]], 1), out["y_in"])
+    for k in ("p_y1", "p_y2", "p_z"):
+        assert float(out[k].min()) >= float(np.float32(1e-9)) and float(out[k].max()) <= 1 + 1e-6
+        assert torch.allclose(out["logp" + k[1:]], torch.log(out[k]), atol=1e-6)
+    bits = -(out["logp_y1"].double().sum() + out["logp_y2"].double().sum() + out["logp_z"].double().sum()) / np.log(2.0)
+    assert abs(float(bits) / (1536 * 2048) - rd["bpp_total"]) < 1e-4
+    mse = float(((out["x_hat"].double() - x.double()) ** 2).mean())
+    assert abs(mse - rd["mse"]) < 1e-5 * mse
+    # a crop-aligned sub-image gives the same interior symbols: the path is convolutional (receptive field << 512 px margin)
+    sub = model(x[:, :, :1024, :1024].contiguous(), training=False)
+    assert torch.equal(sub["y_in"][:, :, :32, :32], out["y_in"][:, :, :32, :32])

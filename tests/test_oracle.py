@@ -74,3 +74,27 @@ def test_training_mode_uses_injected_noise():
     nz, ny = torch.rand(1, 128, 1, 1) - 0.5, torch.rand(1, 128, 4, 4) - 0.5
     out = O.forward(model.state_dict(), x, 128, 1, training=True, noise_z=nz, noise_y=ny)
     assert torch.equal(out["y_in"], out["y"] + ny) and torch.equal(out["z_in"], out["z"] + nz)
+
+
+@pytest.mark.parametrize("case", H.scalable_cases())
+def test_scalable_oracle_matches_reference_submodules(case):
+    """Config 5: the oracle's forward_scalable against the reference's own sub-modules run in the repaired order."""
+    g = H.load_golden(case)
+    M, M1, K, init = int(g["M"]), int(g["M1"]), int(g["K"]), str(g["init"])
+    model = H.seeded_scalable_model(M, M1, K, init)
+    assert H.state_digest(model.state_dict()) == str(g["state_digest"]), "seeded weights differ from the reference's"
+    x = torch.from_numpy(g["x"])
+    out = O.forward_scalable(model.state_dict(), x, M, M1, K)
+    keys = [k for k in g.files if k.startswith("out_")]
+    assert {"out_p_y1", "out_p_y2", "out_y1", "out_y2", "out_x_hat"} <= set(keys)
+    for key in keys:
+        got, ref = out[key[4:]].numpy(), g[key]
+        assert got.shape == ref.shape, key
+        if key in ("out_y_in", "out_z_in", "out_y1", "out_y2"):
+            assert np.array_equal(got, ref), key
+        else:
+            np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-7, err_msg=key)
+    rd = O.vision_rd_loss(out, x, 0.005)
+    for key in ("bpp_y1", "bpp_y2", "bpp_y", "bpp_z", "bpp_total", "mse", "psnr", "bits_y1", "bits_y2", "bits_z", "bits_total"):
+        assert abs(rd[key] - float(g["rd_" + key])) <= 1e-6 * max(1.0, abs(float(g["rd_" + key]))), key
+    assert abs(float(rd["loss"]) - float(g["rd_loss"])) <= 1e-5 * abs(float(g["rd_loss"]))
