@@ -153,3 +153,25 @@ def test_full_size_batch_properties(precision):
     mse = ((out["x_hat"].double() - x.double()) ** 2).mean(dim=(1, 2, 3))
     assert abs(float(mse.mean()) - rd["mse"]) < 1e-5 * float(mse.mean())
     assert abs(-10 * np.log10(float(mse.mean()) + 1e-8) - rd["psnr"]) < 1e-4
+
+
+@pytest.mark.parametrize("precision", PARITY_ARMS)
+def test_config4_training_forward_shape(precision):
+    """BASELINE configs[3]'s forward half: training=True (noise relaxation, injected noise so both sides see the same draw) on
+    8 crops of 256 x 256 (the per-GPU share of batch 64 over 8 GPUs), loss terms against the oracle.  (The backward pass and the
+    optimizer are not built; see DESIGN.md.)"""
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    model = H.seeded_model(128, 3, "calib", precision=precision)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = H.seeded_input((8, 3, 256, 256))
+    torch.manual_seed(13)
+    nz, ny = torch.rand(8, 128, 4, 4) - 0.5, torch.rand(8, 128, 16, 16) - 0.5
+    ref = O.forward(sd, x, 128, 3, training=True, noise_z=nz, noise_y=ny)
+    ref_rd = O.rd_loss(ref, x, 0.005)
+    model = model.cuda()
+    out = model(x.cuda(), training=True, noise=(nz.cuda(), ny.cuda()))
+    rd = rd_loss(out, x.cuda(), 0.005)
+    assert out["training"] is True
+    assert abs(rd["bpp_total"] - ref_rd["bpp_total"]) <= H.BPP_TOL and abs(rd["psnr"] - ref_rd["psnr"]) <= H.PSNR_TOL
+    assert abs(float(rd["loss"]) - float(ref_rd["loss"])) <= 1e-3 * abs(float(ref_rd["loss"]))
+    np.testing.assert_allclose(out["y_in"].cpu().numpy(), ref["y_in"].numpy(), rtol=1e-4, atol=2e-4)
