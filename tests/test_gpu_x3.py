@@ -152,3 +152,25 @@ def test_x3_h_a_shapes():
     c5 = nn.Conv2d(128, 128, 5, 2, 2)
     x = torch.randn(1, 128, 4, 4)
     print(_close(_run(c5, x, EPI_BIAS, out_f32=True), _ref(c5, x, EPI_BIAS)))
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 64, 64), (3, 3, 192, 320), (2, 3, 128, 448), (5, 3, 64, 192)])
+def test_x3_model_ragged_sizes_match_fp32_arm(shape):
+    """Whole model at sizes whose feature maps do not divide into 16 x 16 tiles (edge tiles, one-block tiles, 1x1 z maps, odd
+    batch): the bf16x3 arm must agree with the fp32 CUDA-core arm at fp32 grade."""
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    x = H.seeded_input(shape).cuda()
+    ref_model = H.seeded_model(128, 3, "calib", precision="fp32").cuda()
+    model = H.seeded_model(128, 3, "calib", precision="bf16x3").cuda()
+    ref, out = ref_model(x, training=False), model(x, training=False)
+    r0, r1 = rd_loss(ref, x, 0.005), rd_loss(out, x, 0.005)
+    yerr = float((out["y"] - ref["y"]).abs().max() / ref["y"].abs().max())
+    zerr = float((out["z"] - ref["z"]).abs().max() / ref["z"].abs().max())
+    real, ties = H.symbol_mismatches(out["y_in"].cpu().numpy(), ref["y_in"].cpu().numpy(), ref["y"].cpu().numpy(), 5e-3)
+    realz, tiesz = H.symbol_mismatches(out["z_in"].cpu().numpy(), ref["z_in"].cpu().numpy(), ref["z"].cpu().numpy(), 5e-3)
+    print(shape, f"y {yerr:.2e} z {zerr:.2e} ties {ties}+{tiesz} bpp {r1['bpp_total']:.6f}/{r0['bpp_total']:.6f} psnr {r1['psnr']:.6f}/{r0['psnr']:.6f}")
+    assert yerr < 1e-4 and zerr < 1e-4 and real == 0 and realz == 0
+    assert abs(r1["bpp_total"] - r0["bpp_total"]) < 1e-3 and abs(r1["psnr"] - r0["psnr"]) < 1e-3
+    if ties + tiesz == 0:
+        xe = float((out["x_hat"] - ref["x_hat"]).abs().max() / ref["x_hat"].abs().max())
+        assert xe < 3e-4, xe
