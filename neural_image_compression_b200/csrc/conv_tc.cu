@@ -173,6 +173,9 @@ struct TcParams {
   int split_lo_off;                            //   lo to the same window shifted by split_lo_off channels (the second half)
   int ph_rows, pw_cols;                        // patch rows / cols (pixels)
   int slot_bytes, nsa, nsb;
+  int swap;                                    // operand roles swapped: weights are the M = 128 operand, the 256 pixels of the tile
+                                               // (two vertically stacked blocks) the N = 256 operand; accumulator [c_out lanes][pixel
+                                               // columns] - 6 KB of shared-memory operand reads per 128x128x16 instead of 8 KB
   int b_resident;                              // all weight slabs of the layer stay in shared memory (small c_out)
   int nslabs;                                  // taps over all phases
   int nb, cout_pad;                            // N of the MMA (c_out tile), padded c_out of the packed weights
@@ -528,6 +531,58 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
   return true;
 }
 
+// Epilogue of one tile in the swapped orientation (TcParams::swap): TMEM lane = output channel, column = pixel (block h of the
+// tile owns columns [128 h, 128 h + 128)).  Bias / LeakyReLU per lane, then the tile is TRANSPOSED into the same [pixel][64 ch]
+// 128-byte-swizzled staging panels the TMA stores of the normal orientation use: lane c writes bf16 (pixel p, channel c) with
+// 2-byte stores - a warp covers 32 consecutive channels of one pixel, i.e. four 16-byte chunks of one 128-byte row, conflict
+// free.  bf16 or bf16-pair NHWC outputs only (one staging + store round for hi, one for lo).
+__device__ __forceinline__ bool epilogue_tile_swapped(const TcParams& p, const float* s_bias, uint8_t* sq, const CUtensorMap* map_o_ptr,
+                                                      uint32_t acc_tmem, int q, int lane, int hs, bool leader, int img, int ty, int tx,
+                                                      int py, int px, int cbase, int nblk) {
+  const int c = q * 32 + lane;                                   // channel of this thread inside the N tile
+  const uint32_t lane_addr = acc_tmem + (static_cast<uint32_t>(q * 32) << 16);
+  const float bias = (cbase + c < p.cout) ? s_bias[cbase + c] : 0.f;
+  const int nvalid_c = p.cout - cbase;
+  auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); };
+  uint8_t* col = sq + (c >> 6) * (128 * 128) + (c & 7) * 2;      // panel of this channel + its byte inside a 16-byte chunk
+  const uint32_t cchunk = static_cast<uint32_t>((c & 63) >> 3);
+  const int npass = p.split_out ? 2 : 1;
+  for (int h = 0; h < nblk; ++h) {
+    const int oy0 = ty * p.tile_h + p.blk_roff[h], ox0 = tx * p.tile_w + p.blk_coff[h];
+    const int wc = ox0 * p.out_stride + px, hc = oy0 * p.out_stride + py;
+    for (int pass = 0; pass < npass; ++pass) {
+      if (leader) tma_store_wait_read();                         // the staging tile may still be read by the previous store
+      epi_sync();
+#pragma unroll
+      for (int g2 = 0; g2 < 2; ++g2) {
+        float v[32];
+        tmem_ld_32x32(lane_addr + h * 128 + hs * 64 + g2 * 32, v);
+        tmem_ld_wait();
+        const int r0 = hs * 64 + g2 * 32;                        // pixel row of v[0] inside the block (16 rows x 8 pixels)
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float a = v[j] + bias, b = v[j + 1] + bias;
+          if (p.epilogue == NIC_EPI_LRELU) { a = a > 0.f ? a : 0.01f * a; b = b > 0.f ? b : 0.01f * b; }
+          uint32_t w = pack_bf16x2(a, b);
+          if (pass == 1) w = pack_bf16x2(a - __uint_as_float(w << 16), b - __uint_as_float(w & 0xffff0000u));
+          const int ra = r0 + j, rb = ra + 1;
+          *reinterpret_cast<uint16_t*>(col + ra * 128 + ((cchunk ^ (ra & 7)) << 4)) = static_cast<uint16_t>(w & 0xffffu);
+          *reinterpret_cast<uint16_t*>(col + rb * 128 + ((cchunk ^ (rb & 7)) << 4)) = static_cast<uint16_t>(w >> 16);
+        }
+      }
+      fence_proxy_async_smem();
+      epi_sync();
+      if (leader && !(p.dbg & 2)) {
+        const int off = p.out_c_offset + cbase + (pass == 1 ? p.split_lo_off : 0);
+        for (int k = 0; k < 2; ++k)
+          if (k * 64 < nvalid_c) tma_store_4d(map_o_ptr, sq + k * (128 * 128), off + k * 64, wc, hc, img);
+        tma_store_commit();
+      }
+    }
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p) {
@@ -637,7 +692,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t a_hi = umma_desc_hi(p.pw_cols * 128), b_hi = umma_desc_hi(1024);
       const uint32_t bbytes = p.nb * 128;
       const int nsa = p.nsa, nsb = p.nsb, nchunks = p.nchunks, b_res = p.b_resident;
-      const uint32_t blk_off = mw ? static_cast<uint32_t>((p.blk_roff[1] * p.pw_cols + p.blk_coff[1]) * 128) >> 4 : 0u;
+      const bool swp = p.swap != 0;
+      const uint32_t blk_off = (mw && !swp) ? static_cast<uint32_t>((p.blk_roff[1] * p.pw_cols + p.blk_coff[1]) * 128) >> 4 : 0u;
+      const uint32_t idesc_use = swp ? umma_idesc_bf16(128, 256) : idesc;
+      const uint32_t f_hi = swp ? b_hi : a_hi, g_hi = swp ? a_hi : b_hi;
       const uint32_t a_base_lo = umma_desc_lo(a_base), b_base_lo = umma_desc_lo(b_base);
       const uint32_t slot16 = static_cast<uint32_t>(p.slot_bytes) >> 4, bb16 = bbytes >> 4;
       // Resident weights (N = 16 layers): ONE thread per issuer walks the loop - no barrier polls inside a plane, so dropping the
@@ -739,8 +797,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (!wait_or_abort(&sb.acc_empty[buf], ((tcount >> 1) & 1) ^ 1, &sb, p.status)) break;
           if (lane == 0 && mw == 0) trace(p, tcount, 0);
           tcgen05_fence_after();
-          const uint32_t d_tmem = tmem + buf * 256 + mw * 128;
-          const bool live = mw < nblk;
+          // swapped orientation: issuer 0 alone issues N = 256 MMAs (weights first, the pixels of both blocks second) into the
+          // whole 256-column buffer; issuer 1 walks the rings and only commits
+          const uint32_t d_tmem = tmem + buf * 256 + (swp ? 0 : mw * 128);
+          const bool live = swp ? mw == 0 : mw < nblk;
           uint32_t accumulate = 0;
           for (int chunk = 0; chunk < nchunks && ok; ++chunk) {
             for (int pl = 0; pl < nplanes && ok; ++pl) {
@@ -764,20 +824,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tcgen05_fence_after();
                 const uint32_t b_lo0 = b_base_lo + s0 * ((128 * 128) >> 4), b_lo1 = b_base_lo + s1 * ((128 * 128) >> 4);
                 const uint32_t a_lo0 = a_slot_lo + s_tap_aoff[t] + blk_off, a_lo1 = a_slot_lo + s_tap_aoff[two ? t + 1 : t] + blk_off;
+                // first / second operand of the MMA: (pixels, weights), or (weights, pixels) in the swapped orientation
+                const uint32_t f0 = swp ? b_lo0 : a_lo0, g0 = swp ? a_lo0 : b_lo0, f1 = swp ? b_lo1 : a_lo1, g1 = swp ? a_lo1 : b_lo1;
                 if (elect_one()) {
                   if (live) {
-                    umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo0, b_hi, idesc, accumulate);
-                    umma_bf16_lohi(d_tmem, a_lo0 + 2, a_hi, b_lo0 + 2, b_hi, idesc, 1);
-                    umma_bf16_lohi(d_tmem, a_lo0 + 4, a_hi, b_lo0 + 4, b_hi, idesc, 1);
-                    umma_bf16_lohi(d_tmem, a_lo0 + 6, a_hi, b_lo0 + 6, b_hi, idesc, 1);
+                    umma_bf16_lohi(d_tmem, f0, f_hi, g0, g_hi, idesc_use, accumulate);
+                    umma_bf16_lohi(d_tmem, f0 + 2, f_hi, g0 + 2, g_hi, idesc_use, 1);
+                    umma_bf16_lohi(d_tmem, f0 + 4, f_hi, g0 + 4, g_hi, idesc_use, 1);
+                    umma_bf16_lohi(d_tmem, f0 + 6, f_hi, g0 + 6, g_hi, idesc_use, 1);
                   }
                   umma_commit(&sb.b_empty[s0]);
                   if (two) {
                     if (live) {
-                      umma_bf16_lohi(d_tmem, a_lo1, a_hi, b_lo1, b_hi, idesc, 1);
-                      umma_bf16_lohi(d_tmem, a_lo1 + 2, a_hi, b_lo1 + 2, b_hi, idesc, 1);
-                      umma_bf16_lohi(d_tmem, a_lo1 + 4, a_hi, b_lo1 + 4, b_hi, idesc, 1);
-                      umma_bf16_lohi(d_tmem, a_lo1 + 6, a_hi, b_lo1 + 6, b_hi, idesc, 1);
+                      umma_bf16_lohi(d_tmem, f1, f_hi, g1, g_hi, idesc_use, 1);
+                      umma_bf16_lohi(d_tmem, f1 + 2, f_hi, g1 + 2, g_hi, idesc_use, 1);
+                      umma_bf16_lohi(d_tmem, f1 + 4, f_hi, g1 + 4, g_hi, idesc_use, 1);
+                      umma_bf16_lohi(d_tmem, f1 + 6, f_hi, g1 + 6, g_hi, idesc_use, 1);
                     }
                     umma_commit(&sb.b_empty[s1]);
                   }
@@ -811,6 +873,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t buf = tcount & 1;
       if (!__all_sync(0xffffffffu, wait_or_abort(&sb.acc_full[buf], (tcount >> 1) & 1, &sb, p.status))) break;
       tcgen05_fence_after();
+      if (p.swap) {
+        if (!(p.dbg & 8))
+          ok = epilogue_tile_swapped(p, s_bias, sq, &map_o, tmem + buf * 256, q, lane, (warp - kFirstEpiWarp) >> 2,
+                                     warp == kFirstEpiWarp && lane == 0, img, ty, tx, ph.py, ph.px, ntile * p.nb, nblk);
+      } else
       for (int b = 0; b < nblk && ok && !(p.dbg & 8); ++b)
         ok = epilogue_block<kEpiWarps>(p, &sb, s_bias, s_beta, sq, smem + p.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane,
                                        (warp - kFirstEpiWarp) >> 2, warp == kFirstEpiWarp && lane == 0, img, ty * p.tile_h + p.blk_roff[b],
@@ -1328,18 +1395,33 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   }
   p.hp = (p.hout + tt.out_stride - 1) / tt.out_stride;
   p.wp = (p.wout + tt.out_stride - 1) / tt.out_stride;
+  // Swapped orientation (weights = the M operand, the 256 pixels of a two-block tile = the N operand of ONE N = 256 MMA) for the
+  // layers it is built for: bias / LeakyReLU epilogue, bf16 or bf16-pair NHWC output through TMA, c_out tiles of 128, weights
+  // streamed.  It needs the two blocks stacked vertically (one uniform group stride through the patch), like the flat 1x1 case.
+  const char* swap_env = getenv("NIC_TC_SWAP");
+  const bool out_bf16_tma = !shuffle && d->out_layout == NIC_LAYOUT_NHWC && p.out_dtype == NIC_DT_BF16 && p.nb == 128 && d->c_out % 64 == 0 &&
+                            ctot % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+  // Measured (bf16x3, 16 images): transposed convs gain 6-8 % (g_s layer 3: 1.105 -> 1.04 ms); stride-2 convs LOSE ~8 % (an
+  // N = 256 MMA over their four 34 x 10 plane patches runs at ~160 clk, not 128) and the small stride-1 layers lose a few us to
+  // the heavier transposing epilogue - so the default is transposed convs only; NIC_TC_SWAP=1 forces it wherever it is built,
+  // NIC_TC_SWAP=0 disables it.
+  const bool swap_ok = !gdn && out_bf16_tma && (d->epilogue == NIC_EPI_BIAS || d->epilogue == NIC_EPI_LRELU);
+  bool swap = swap_ok && (swap_env ? atoi(swap_env) != 0 : tt.nphases > 1);
+  const bool stacked = flat || swap;
   // two M = 128 blocks per tile share every weight slab (halves the L2 -> shared-memory weight traffic, which is
   // what bounds M = 128 tiles: profiles/README.md); side by side for images, stacked for the flat 1x1 case
-  p.mt = (flat ? p.hp > kTileH : p.wp > kTileW) ? 2 : 1;
+  p.mt = (stacked ? p.hp > kTileH : p.wp > kTileW) ? 2 : 1;
   {
     // small layers: one block per tile when two-block tiles would leave SMs idle (fewer than two tiles per SM)
-    const long tiles2 = static_cast<long>((p.wp + (flat ? kTileW : 2 * kTileW) - 1) / (flat ? kTileW : 2 * kTileW)) *
-                        ((p.hp + (flat ? 2 * kTileH : kTileH) - 1) / (flat ? 2 * kTileH : kTileH)) * p.n * tt.nphases * p.n_ntiles;
+    const long tiles2 = static_cast<long>((p.wp + (stacked ? kTileW : 2 * kTileW) - 1) / (stacked ? kTileW : 2 * kTileW)) *
+                        ((p.hp + (stacked ? 2 * kTileH : kTileH) - 1) / (stacked ? 2 * kTileH : kTileH)) * p.n * tt.nphases * p.n_ntiles;
     if (tiles2 < 2 * kNumSMs) p.mt = 1;
   }
+  if (p.mt == 1) swap = false;                   // one-block tiles: N = 128 either way, keep the normal orientation
+  p.swap = swap ? 1 : 0;
   p.blk_roff[0] = p.blk_coff[0] = 0;
-  p.blk_roff[1] = flat ? kTileH : 0; p.blk_coff[1] = flat ? 0 : kTileW;
-  p.tile_h = flat ? kTileH * p.mt : kTileH; p.tile_w = flat ? kTileW : kTileW * p.mt;
+  p.blk_roff[1] = stacked ? kTileH : 0; p.blk_coff[1] = stacked ? 0 : kTileW;
+  p.tile_h = stacked ? kTileH * p.mt : kTileH; p.tile_w = stacked ? kTileW : kTileW * p.mt;
   p.ph_rows += p.tile_h - kTileH; p.pw_cols += p.tile_w - kTileW;      // build_tc_geometry sized the patch for one block
   p.tiles_x = (p.wp + p.tile_w - 1) / p.tile_w;
   p.tiles_y = (p.hp + p.tile_h - 1) / p.tile_h;

@@ -20,6 +20,8 @@ cfg = {
     "ep3": (nn.Conv2d(640, 1152, 1), EPI_BIAS, (32, 48), dict(out_layout=LAYOUT_NCHW, out_dtype=torch.float32)),
     "l1": (nn.Conv2d(3, 128, 5, 2, 2), EPI_GDN, (512, 768), dict(in_layout=LAYOUT_NCHW)),
     "k2c": (nn.Conv2d(128, 128, 5, 2, 2), EPI_BIAS, (256, 384), dict(out_dtype=torch.float32)),
+    "k2p": (nn.Conv2d(128, 128, 5, 2, 2), EPI_BIAS, (256, 384), {}),      # pair (bf16x3) or bf16 output: the swapped orientation
+    "d2p": (nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1), EPI_BIAS, (128, 192), {}),
     "d2c": (nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1), EPI_BIAS, (128, 192), dict(out_dtype=torch.float32)),
 }[which]
 conv, epi, (h, w), kw = cfg
