@@ -283,7 +283,9 @@ def main():
     peak = peaks["bf16_burst"]
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture summarised in
     # profiles/r1_ncu_full_v3_summary.txt (403.8 MB + 82.0 MB; algorithmic: 402.7 MB in + 100.7 MB out + 0.8 MB weights)
-    k2_traffic = 485.8e6 if (B == 16 and kern_prec == "bf16") else None
+    # (bf16x3: 956.6 MB + 181.8 MB, profiles/r1_ncu_full_v5_k2_x3.txt; algorithmic: 805.3 MB of pair input + 201.3 MB of output +
+    #  2.5 MB of weights - the three K passes re-read each patch from L2, ~19 % of those re-reads reach DRAM)
+    k2_traffic = {"bf16": 485.8e6, "bf16x3": 1138.4e6}.get(kern_prec) if B == 16 else None
     passes = 3 if kern_prec == "bf16x3" else 1
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": k2_traffic,
                 "kernel": k2_kernel, "ms_per_launch": k2_ms, "mma_passes": passes, "tensor_pipe_frac": passes * achieved / peak,
