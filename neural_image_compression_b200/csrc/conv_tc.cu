@@ -53,6 +53,8 @@ int gdn_fwd_tc_x3(const void* x, int pair_in, long npix, int c, int inverse, con
 size_t packed_first_x3_elems();
 int pack_first_x3(const float* w_ref, void* w_packed, cudaStream_t st);
 int conv_first_x3(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, float* y, cudaStream_t st);
+int conv_first_gdn_x3(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* gamma_packed,
+                      const float* beta_eff, void* y, cudaStream_t st);
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1556,6 +1558,10 @@ int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, con
     if (d->out_dtype != NIC_DT_BF16X2 || d->out_layout != NIC_LAYOUT_NHWC || d->out_c_total != 0)
       return fail(NIC_E_UNSUPPORTED, "conv bf16x3 + GDN: output must be a plain NHWC bf16-pair tensor");
     int pair_in = 0;
+    if (small_cin(d) && !getenv("NIC_X3_FIRST_TWO_KERNELS")) {       // fused conv + GDN (the env switch keeps the two-kernel form testable)
+      if (int rc = check_first_layer(d)) return rc;
+      return conv_first_gdn_x3(d, x, w_packed, bias, gdn_gamma, gdn_beta, y, st);
+    }
     if (small_cin(d)) {
       if (int rc = check_first_layer(d)) return rc;
       if (int rc = conv_first_x3(d, x, w_packed, bias, static_cast<float*>(workspace), st)) return rc;

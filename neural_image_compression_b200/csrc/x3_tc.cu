@@ -270,7 +270,7 @@ __global__ void pack_gdn_x3_kernel(int c, float beta_bound, float gamma_bound, f
 // K = 75 (k = (kh * 5 + kw) * 3 + c, padded to 80).  Operand panels (128 rows x 128 B, 128-byte swizzle):
 //   A: H = hi[k < 64]   L = lo[k < 64]   X = [hi[64..79] | lo[64..79] | unused]     (two stages)
 //   W: same three panels, resident.
-// 13 warps: 0-3 producers (patch fetch with cp.async + im2col expansion), 4 MMA issuer / weight loader, 5-12 two epilogue
+// 11 warps: 0-1 producers (patch fetch with cp.async + im2col expansion), 4 MMA issuer / weight loader, 5-12 two epilogue
 // groups that take alternate tiles: TMEM -> registers -> per-warp shared-memory transpose -> coalesced 128-byte row stores.
 // ---------------------------------------------------------------------------------------------
 constexpr int kF3Threads = 160 + 8 * 32;
@@ -454,6 +454,267 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   if (warp == 4) tmem_dealloc(tmem, 256);
 }
 
+// ---------------------------------------------------------------------------------------------
+// First layer of g_a in the bf16x3 arm, FUSED: Conv2d(3, 128, 5, s2, p2) + bias + GDN, NCHW f32 image -> bf16 hi/lo pair
+// activation, one kernel.  The two-kernel form (conv_first_x3_kernel + gdn_x3_kernel) moves 2.4 GB through HBM per 16 images
+// (f32 scratch out and in, pairs out); this one writes the 0.8 GB of pairs only.
+// 11 warps: 0-1 producers (patch by TMA, im2col with hi/lo split, one A stage), 2 MMA issuer (15 conv MMAs of tile t + 1, then
+// the 16 + 8 GDN MMAs of tile t), 3-10 workers (thread <-> pixel row x 64-channel half: x from TMEM to registers, squares hi
+// -> MMA -> squares lo -> MMA -> x * rsqrt(beta + .) -> hi tile -> TMA store -> lo tile -> TMA store; ONE 32 KB tile serves as
+// squares and staging).  Shared memory: W 48 KB + gamma hi/lo 64 KB + A 48 KB + tile 32 KB + two patches.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFfProducers = 2, kFfWorkers = 8;   // 4 producer warps push the kernel to 416 threads = 128 registers: spills, slower
+constexpr int kFfThreads = (kFfProducers + 1 + kFfWorkers) * 32;
+
+struct FirstFusedParams {
+  const float* bias;
+  const float* beta;
+  int n, hin, win, hout, wout, tiles_x, tiles_y, total_tiles;
+  int off_w, off_gamma, off_a, off_sq, off_patch;
+  int* status;
+};
+
+struct __align__(8) FirstFusedBarriers {
+  uint64_t patch_full[2], a_full, a_empty, w_full, gamma_full, acc_full[2], acc_empty[2], sq1, sq2, g1, g2;
+  uint32_t tmem_base;
+  volatile int abort_flag;
+};
+
+__global__ void __launch_bounds__(kFfThreads, 1)
+first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_img,
+                      const __grid_constant__ CUtensorMap map_o, const __grid_constant__ FirstFusedParams f) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ FirstFusedBarriers sb;
+  __shared__ float s_bias[128];
+  __shared__ __align__(16) float s_beta[128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  if (tid < 128) { s_bias[tid] = f.bias[tid]; s_beta[tid] = f.beta[tid]; }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&sb.patch_full[i], 1); mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], kFfWorkers); }
+    mbar_init(&sb.a_full, kFfProducers * 32); mbar_init(&sb.a_empty, 1); mbar_init(&sb.w_full, 1); mbar_init(&sb.gamma_full, 1);
+    mbar_init(&sb.sq1, kFfWorkers); mbar_init(&sb.sq2, kFfWorkers); mbar_init(&sb.g1, 1); mbar_init(&sb.g2, 1);
+    sb.abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == kFfProducers) { tmem_alloc(&sb.tmem_base, 512); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = sb.tmem_base;
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  uint8_t* patch = smem + f.off_patch;
+  uint8_t* sq = smem + f.off_sq;
+  auto tile_coords = [&](int tile, int& img, int& ty, int& tx) {
+    tx = tile % f.tiles_x; tile /= f.tiles_x; ty = tile % f.tiles_y; img = tile / f.tiles_y;
+  };
+
+  if (warp < kFfProducers) {
+    // ===================== producers: 64 threads, two pixel rows each =====================
+    auto fetch_patch = [&](int tile, int bufi) {
+      int img, ty, tx;
+      tile_coords(tile, img, ty, tx);
+      mbar_expect_tx(&sb.patch_full[bufi], kPatchBytes);
+      tma_load_3d(patch + bufi * kPatchStride, &map_img, &sb.patch_full[bufi], 16 * tx - 4, 32 * ty - 2, img * 3);
+    };
+    if (tid == 0) { tma_prefetch_desc(&map_img); if (first_tile < f.total_tiles) fetch_patch(first_tile, 0); }
+    uint32_t it = 0;
+    for (int tile = first_tile; tile < f.total_tiles; tile += tile_step, ++it) {
+      const uint32_t st = it & 1;
+      asm volatile("bar.sync 3, %0;" ::"n"(kFfProducers * 32) : "memory");      // patch(it-1) is no longer read
+      if (tid == 0 && tile + tile_step < f.total_tiles) fetch_patch(tile + tile_step, st ^ 1);
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.patch_full[st], (it >> 1) & 1, &sb.abort_flag, f.status))) break;
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.a_empty, (it & 1) ^ 1, &sb.abort_flag, f.status))) break;
+#pragma unroll 1
+      for (int rr = 0; rr < 128 / (kFfProducers * 32); ++rr) {
+        const int r = tid + rr * (kFfProducers * 32), g = r >> 3, c8 = r & 7;
+        const uint32_t swz = static_cast<uint32_t>(r & 7);
+        const float* src = reinterpret_cast<const float*>(patch + st * kPatchStride) + (2 * g) * kPatchW + 2 * c8 + 2;
+        uint8_t* dst = smem + f.off_a + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 10; ++ch) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v2[2];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int k = ch * 8 + e * 2 + hh;
+              if (k < 75) { const int tap = k / 3, c = k % 3; v2[hh] = src[c * kPatchPlane + (tap / 5) * kPatchW + (tap % 5)]; }
+              else v2[hh] = 0.f;
+            }
+            split2(v2[0], v2[1], h[e], l[e]);
+          }
+          if (ch < 8) {
+            const uint32_t off = (static_cast<uint32_t>(ch) ^ swz) << 4;
+            *reinterpret_cast<uint4*>(dst + off) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(dst + kPanel + off) = make_uint4(l[0], l[1], l[2], l[3]);
+          } else {
+            const uint32_t offh = (static_cast<uint32_t>(ch - 8) ^ swz) << 4, offl = (static_cast<uint32_t>(ch - 6) ^ swz) << 4;
+            *reinterpret_cast<uint4*>(dst + 2 * kPanel + offh) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(dst + 2 * kPanel + offl) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&sb.a_full);
+    }
+  } else if (warp == kFfProducers) {
+    // ===================== weight / gamma loader + MMA issuer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_g); tma_prefetch_desc(&map_o);
+      mbar_expect_tx(&sb.w_full, 3 * kPanel);
+      for (int k = 0; k < 3; ++k) tma_load_2d(smem + f.off_w + k * kPanel, &map_w, &sb.w_full, k * 64, 0);
+      mbar_expect_tx(&sb.gamma_full, 4 * kPanel);
+      for (int k = 0; k < 4; ++k) tma_load_2d(smem + f.off_gamma + k * kPanel, &map_g, &sb.gamma_full, (k & 1) * 64, (k >> 1) * 128);
+      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      const uint32_t hi = umma_desc_hi(1024);
+      const uint32_t ab = umma_desc_lo(smem_u32(smem + f.off_a)), w_lo = umma_desc_lo(smem_u32(smem + f.off_w));
+      const uint32_t sq_lo = umma_desc_lo(smem_u32(sq));
+      const uint32_t gh = umma_desc_lo(smem_u32(smem + f.off_gamma)), gl = umma_desc_lo(smem_u32(smem + f.off_gamma + 2 * kPanel));
+      constexpr uint32_t P = kPanel >> 4;
+      bool ok = wait_abort(&sb.w_full, 0, &sb.abort_flag, f.status) && wait_abort(&sb.gamma_full, 0, &sb.abort_flag, f.status);
+      const uint32_t d2 = tmem + 256;
+      auto conv_mmas = [&](uint32_t it) -> bool {
+        const uint32_t g = it & 1;
+        if (!wait_abort(&sb.acc_empty[g], ((it >> 1) & 1) ^ 1, &sb.abort_flag, f.status)) return false;
+        if (!wait_abort(&sb.a_full, it & 1, &sb.abort_flag, f.status)) return false;
+        tcgen05_fence_after();
+        const uint32_t d = tmem + g * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + 2 * k, hi, w_lo + 2 * k, hi, idesc, k);
+        umma_bf16_lohi(d, ab + 2 * P, hi, w_lo + 2 * P, hi, idesc, 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + P + 2 * k, hi, w_lo + 2 * k, hi, idesc, 1);
+        umma_bf16_lohi(d, ab + 2 * P + 2, hi, w_lo + 2 * P, hi, idesc, 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + 2 * k, hi, w_lo + P + 2 * k, hi, idesc, 1);
+        umma_bf16_lohi(d, ab + 2 * P, hi, w_lo + 2 * P + 2, hi, idesc, 1);
+        umma_commit(&sb.a_empty);
+        umma_commit(&sb.acc_full[g]);
+        return true;
+      };
+      uint32_t it = 0;
+      int tile = first_tile;
+      if (ok && tile < f.total_tiles) ok = conv_mmas(0);
+      for (; tile < f.total_tiles && ok; tile += tile_step, ++it) {
+        if (tile + tile_step < f.total_tiles) { if (!conv_mmas(it + 1)) break; }       // conv of the next tile first: it overlaps the workers
+        if (!wait_abort(&sb.sq1, it & 1, &sb.abort_flag, f.status)) break;
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const uint32_t o = (k >> 2) * P + (k & 3) * 2; umma_bf16_lohi(d2, sq_lo + o, hi, gh + o, hi, idesc, k); }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const uint32_t o = (k >> 2) * P + (k & 3) * 2; umma_bf16_lohi(d2, sq_lo + o, hi, gl + o, hi, idesc, 1); }
+        umma_commit(&sb.g1);
+        if (!wait_abort(&sb.sq2, it & 1, &sb.abort_flag, f.status)) break;
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const uint32_t o = (k >> 2) * P + (k & 3) * 2; umma_bf16_lohi(d2, sq_lo + o, hi, gh + o, hi, idesc, 1); }
+        umma_commit(&sb.g2);
+      }
+    }
+  } else {
+    // ===================== workers =====================
+    const int wi = warp - kFfProducers - 1;
+    const int q = warp & 3, hs = wi >> 2;
+    const int row = q * 32 + lane;
+    const bool leader = wi == 0 && lane == 0;
+    const uint32_t swz = static_cast<uint32_t>(row & 7);
+    uint8_t* mine = sq + hs * kPanel + row * 128;                // this thread's row of panel hs (64 channels)
+    auto sync_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kFfWorkers * 32) : "memory"); };
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t it = 0;
+    for (int tile = first_tile; tile < f.total_tiles; tile += tile_step, ++it) {
+      int img, ty, tx;
+      tile_coords(tile, img, ty, tx);
+      const uint32_t g = it & 1;
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.acc_full[g], (it >> 1) & 1, &sb.abort_flag, f.status))) break;
+      tcgen05_fence_after();
+      float xr[64];
+      tmem_ld_32x32(tmem + g * 128 + lane_off + hs * 64, xr);
+      tmem_ld_32x32(tmem + g * 128 + lane_off + hs * 64 + 32, xr + 32);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb.acc_empty[g]);                // x is in registers: the accumulator buffer is free again
+#pragma unroll
+      for (int j = 0; j < 64; ++j) xr[j] += s_bias[hs * 64 + j];
+      if (leader) tma_store_wait_read();                           // previous tile's lo store has left the staging tile
+      sync_workers();
+      // squares, hi part
+      uint32_t lo_keep[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float a = xr[j * 8 + e * 2], b = xr[j * 8 + e * 2 + 1]; split2(a * a, b * b, h[e], lo_keep[j * 4 + e]); }
+        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb.sq1);
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.g1, it & 1, &sb.abort_flag, f.status))) break;
+      // squares, lo part (the MMAs over the hi part have completed)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz) << 4)) =
+            make_uint4(lo_keep[j * 4], lo_keep[j * 4 + 1], lo_keep[j * 4 + 2], lo_keep[j * 4 + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb.sq2);
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.g2, it & 1, &sb.abort_flag, f.status))) break;
+      tcgen05_fence_after();
+      float v0[32], v1[32];
+      tmem_ld_32x32(tmem + 256 + lane_off + hs * 64, v0);
+      tmem_ld_32x32(tmem + 256 + lane_off + hs * 64 + 32, v1);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      const float4* beta4 = reinterpret_cast<const float4*>(s_beta + hs * 64);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b0 = beta4[j], b1 = beta4[8 + j];
+        v0[j * 4] = xr[j * 4] * rsqrt_approx(v0[j * 4] + b0.x); v0[j * 4 + 1] = xr[j * 4 + 1] * rsqrt_approx(v0[j * 4 + 1] + b0.y);
+        v0[j * 4 + 2] = xr[j * 4 + 2] * rsqrt_approx(v0[j * 4 + 2] + b0.z); v0[j * 4 + 3] = xr[j * 4 + 3] * rsqrt_approx(v0[j * 4 + 3] + b0.w);
+        v1[j * 4] = xr[32 + j * 4] * rsqrt_approx(v1[j * 4] + b1.x); v1[j * 4 + 1] = xr[32 + j * 4 + 1] * rsqrt_approx(v1[j * 4 + 1] + b1.y);
+        v1[j * 4 + 2] = xr[32 + j * 4 + 2] * rsqrt_approx(v1[j * 4 + 2] + b1.z); v1[j * 4 + 3] = xr[32 + j * 4 + 3] * rsqrt_approx(v1[j * 4 + 3] + b1.w);
+      }
+      // output hi tile (the MMAs over the lo squares have completed), TMA store, then the lo tile
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t h[4];
+        const float* src = (j < 4) ? (v0 + j * 8) : (v1 + (j - 4) * 8);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split2(src[e * 2], src[e * 2 + 1], h[e], lo_keep[j * 4 + e]);
+        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+      }
+      fence_proxy_async_smem();
+      sync_workers();
+      if (leader) {
+        tma_store_4d(&map_o, sq, 0, tx * 8, ty * 16, img);
+        tma_store_4d(&map_o, sq + kPanel, 64, tx * 8, ty * 16, img);
+        tma_store_commit();
+        tma_store_wait_read();
+      }
+      sync_workers();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz) << 4)) =
+            make_uint4(lo_keep[j * 4], lo_keep[j * 4 + 1], lo_keep[j * 4 + 2], lo_keep[j * 4 + 3]);
+      fence_proxy_async_smem();
+      sync_workers();
+      if (leader) {
+        tma_store_4d(&map_o, sq, 128, tx * 8, ty * 16, img);
+        tma_store_4d(&map_o, sq + kPanel, 192, tx * 8, ty * 16, img);
+        tma_store_commit();
+      }
+    }
+    if (leader) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kFfProducers) tmem_dealloc(tmem, 512);
+}
+
 // reference [128, 3, 5, 5] -> bf16 [128][192]: [hi k<64 | lo k<64 | hi k 64..79 | lo k 64..79 | 0], k = (kh * 5 + kw) * 3 + c
 __global__ void pack_first_x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 128 * 192; i += gridDim.x * blockDim.x) {
@@ -543,6 +804,36 @@ int conv_first_x3(const nic_conv_desc* d, const void* x, const void* w_packed, c
   const int grid = f.total_tiles < kNumSMs ? f.total_tiles : kNumSMs;
   conv_first_x3_kernel<<<grid, kF3Threads, smem_bytes, st>>>(map_w, map_img, f);
   return check_launch("conv_first_x3_kernel");
+}
+
+// Conv2d(3, 128, 5, s2, p2) + bias + GDN in one kernel: x NCHW f32 -> y NHWC bf16 pairs [n][h_out][w_out][256]
+int conv_first_gdn_x3(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* gamma_packed,
+                      const float* beta_eff, void* y, cudaStream_t st) {
+  if (d->in_layout != NIC_LAYOUT_NCHW || d->in_dtype != NIC_DT_F32) return fail(NIC_E_UNSUPPORTED, "conv bf16x3 (first layer): input must be the NCHW f32 image");
+  if ((reinterpret_cast<uintptr_t>(w_packed) & 127) || (reinterpret_cast<uintptr_t>(y) & 127) || (reinterpret_cast<uintptr_t>(gamma_packed) & 127) ||
+      (reinterpret_cast<uintptr_t>(x) & 15) || d->w_in % 4)
+    return fail(NIC_E_BADALIGN, "conv bf16x3 (first layer): alignment");
+  FirstFusedParams f{};
+  f.bias = bias; f.beta = beta_eff;
+  f.n = d->n; f.hin = d->h_in; f.win = d->w_in; f.hout = d->h_out; f.wout = d->w_out;
+  f.tiles_x = (d->w_out + 7) / 8; f.tiles_y = (d->h_out + 15) / 16; f.total_tiles = f.tiles_x * f.tiles_y * d->n;
+  f.off_w = 0; f.off_gamma = 3 * kPanel; f.off_a = 7 * kPanel; f.off_sq = 10 * kPanel; f.off_patch = 12 * kPanel;
+  f.status = status_word();
+  if (!f.status) return fail(NIC_E_CUDA, "conv bf16x3: cannot allocate the status word");
+  const int smem_bytes = f.off_patch + 2 * kPatchStride + 1024 + 64;
+  CUtensorMap map_w, map_g, map_img, map_o;
+  if (int rc = encode_2d(&map_w, w_packed, 192, 128, 64, 128)) return rc;
+  if (int rc = encode_2d(&map_g, gamma_packed, 128, 256, 64, 128)) return rc;
+  if (int rc = encode_image_patch(&map_img, x, d->n, 3, d->h_in, d->w_in, kPatchW, kPatchH)) return rc;
+  if (int rc = encode_nhwc(&map_o, y, d->n, d->h_out, d->w_out, 256, 8, 16, 1, 2)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(first_fused_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
+    attr_set = true;
+  }
+  const int grid = f.total_tiles < kNumSMs ? f.total_tiles : kNumSMs;
+  first_fused_x3_kernel<<<grid, kFfThreads, smem_bytes, st>>>(map_w, map_g, map_img, map_o, f);
+  return check_launch("first_fused_x3_kernel");
 }
 
 }  // namespace nic
