@@ -1,0 +1,63 @@
+"""CPU oracle of the TRAINING STEP (forward with injected noise, rd_loss, backward, one Adam update).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  The reference has no backward code of its own: its gradients are whatever
+torch autograd derives from the forward of Models.py:49-106 + RateDistortionLoss.py:5-49, with two hand-written rules on
+the way: compressai's ``LowerBound`` gradient (oracle/gdn.py) and the masked conv's in-place ``weight.data *= mask``
+(ContextModels.py:19: the gradient reaches all 25 taps).  So the oracle is torch autograd over oracle/forward.py run in
+differentiable mode.  The optimizer is ``torch.optim.Adam(model.parameters(), lr=1e-4)`` (Main.ipynb:133, Trainer.py:85-86).
+
+Parity pin: ``oracle/make_golden.py train`` runs the REAL reference model (training=True, torch.rand_like noise reproduced
+from the seed), its own rd_loss, ``loss.backward()`` and one Adam step, and commits per-parameter gradient norms + sampled
+entries + the updated parameters' samples under tests/golden/c4_train_*.npz; tests/test_oracle.py checks this file against them.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import forward as O
+
+BUFFER_SUFFIXES = (".mask", ".pedestal", ".bound")
+
+
+def parameter_keys(sd):
+    """state_dict keys that are nn.Parameters in the reference (buffers: masks and the GDN reparam constants)."""
+    return [k for k in sd.keys() if not k.endswith(BUFFER_SUFFIXES)]
+
+
+def loss_and_grads(sd, x, M: int, K: int, noise_z: torch.Tensor, noise_y: torch.Tensor, lambda_rd: float,
+                   dtype=torch.float32) -> Tuple[Dict[str, float], Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
+    """Returns (rd dict with 'loss' as float, {param key: dLoss/dparam}, forward dict (detached))."""
+    leaves = {k: (v.detach().to("cpu", dtype).clone().requires_grad_(True) if k in set(parameter_keys(sd)) else v.detach().clone())
+              for k, v in sd.items()}
+    prev = O.DIFFERENTIABLE
+    O.DIFFERENTIABLE = True
+    try:
+        out = O.forward(leaves, x, M, K, training=True, noise_z=noise_z, noise_y=noise_y, dtype=dtype)
+        rd = O.rd_loss(out, x, lambda_rd)
+        rd["loss"].backward()
+    finally:
+        O.DIFFERENTIABLE = prev
+    grads = {k: leaves[k].grad.detach() for k in parameter_keys(sd) if leaves[k].grad is not None}
+    rd = dict(rd)
+    rd["loss"] = float(rd["loss"].detach())
+    return rd, grads, {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
+
+
+def adam_step(params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor], state: Optional[dict] = None, lr: float = 1e-4,
+              betas=(0.9, 0.999), eps: float = 1e-8):
+    """One torch.optim.Adam update (defaults of Main.ipynb:133: no weight decay, no amsgrad), restated:
+    m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)."""
+    state = state if state is not None else {"step": 0, "m": {}, "v": {}}
+    state["step"] += 1
+    t = state["step"]
+    out = {}
+    for k, g in grads.items():
+        p = params[k].detach().to(g.dtype)
+        m = state["m"].get(k, torch.zeros_like(p)).mul(betas[0]).add(g, alpha=1 - betas[0])
+        v = state["v"].get(k, torch.zeros_like(p)).mul(betas[1]).addcmul(g, g, value=1 - betas[1])
+        state["m"][k], state["v"][k] = m, v
+        denom = v.sqrt() / (1 - betas[1] ** t) ** 0.5 + eps
+        out[k] = p - (lr / (1 - betas[0] ** t)) * m / denom
+    return out, state

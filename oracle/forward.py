@@ -43,8 +43,12 @@ LIKELIHOOD_BOUND = 1e-9      # EntropyModels.py:18
 SIGMA_FLOOR = 1e-6           # ParametersModels.py:47,62
 
 
+DIFFERENTIABLE = False      # oracle/backward.py sets this while it builds an autograd graph over the parameters
+
+
 def _p(sd, key, dtype):
-    return sd[key].detach().to("cpu", dtype)
+    t = sd[key] if DIFFERENTIABLE else sd[key].detach()
+    return t.to("cpu", dtype)
 
 
 def _gdn(sd, prefix, x, inverse, dtype):
@@ -112,7 +116,12 @@ def mask_a(weight):
 def context(sd, y_in, dtype=torch.float32, prefix="context_model"):
     """ContextModel / MaskedConv2d('A'), ContextModels.py:18-20, 26-33."""
     w = _p(sd, f"{prefix}.masked.weight", dtype)
-    w = w * mask_a(w)
+    if DIFFERENTIABLE:
+        # the reference zeroes the masked taps of the PARAMETER in place (weight.data *= mask, ContextModels.py:19) and then
+        # convolves with the parameter itself: the forward sees w * mask, the gradient reaches all 25 taps
+        w = (w.detach() * mask_a(w) - w.detach()) + w
+    else:
+        w = w * mask_a(w)
     return F.conv2d(y_in, w, _p(sd, f"{prefix}.masked.bias", dtype), padding=2)
 
 

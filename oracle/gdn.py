@@ -31,12 +31,32 @@ REPARAM_OFFSET = 2.0 ** -18
 PEDESTAL = REPARAM_OFFSET ** 2
 
 
+class LowerBoundFunction(torch.autograd.Function):
+    """``compressai.ops.bound_ops.LowerBoundFunction``: forward max(x, bound); the gradient passes where x >= bound OR where it
+    would push x upwards (grad_output < 0), so a parameter sitting below the bound can still move back above it."""
+
+    @staticmethod
+    def forward(ctx, x, bound):
+        ctx.save_for_backward(x, bound)
+        return torch.max(x, bound)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, bound = ctx.saved_tensors
+        pass_through = (x >= bound) | (grad_output < 0)
+        return pass_through.to(grad_output.dtype) * grad_output, None
+
+
+def lower_bound(x, bound: float):
+    return LowerBoundFunction.apply(x, torch.tensor([float(bound)], dtype=x.dtype))
+
+
 def gdn_effective(beta_raw, gamma_raw, beta_min: float = 1e-6):
-    """(beta_eff, gamma_eff) from the stored (reparametrised) parameters."""
+    """(beta_eff, gamma_eff) from the stored (reparametrised) parameters (differentiable, LowerBound gradient rule)."""
     beta_bound = (beta_min + PEDESTAL) ** 0.5
     gamma_bound = (0.0 + PEDESTAL) ** 0.5
-    beta = torch.clamp_min(beta_raw, beta_bound) ** 2 - PEDESTAL
-    gamma = torch.clamp_min(gamma_raw, gamma_bound) ** 2 - PEDESTAL
+    beta = lower_bound(beta_raw, beta_bound) ** 2 - PEDESTAL
+    gamma = lower_bound(gamma_raw, gamma_bound) ** 2 - PEDESTAL
     return beta, gamma
 
 
@@ -46,7 +66,7 @@ class _LowerBound(nn.Module):
         self.register_buffer("bound", torch.tensor([float(bound)]))
 
     def forward(self, x):
-        return torch.max(x, self.bound)   # gradient rule is irrelevant to the forward oracle
+        return LowerBoundFunction.apply(x, self.bound)
 
 
 class _NonNegative(nn.Module):

@@ -8,7 +8,7 @@ reference classes are imported unmodified with two stand-ins placed in
   * ``compressai.layers.gdn.GDN``: oracle/gdn.py (third-party arithmetic that
     is absent from /root/reference and from this image - parity unpinned there).
 
-Usage:  python -m oracle.make_golden [scalable]          (from the repo root)
+Usage:  python -m oracle.make_golden [scalable | train]  (from the repo root)
 """
 from __future__ import annotations
 
@@ -197,8 +197,69 @@ def main():
               f"({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+TRAIN_CASES = {
+    # name: (M, K, input shape, init, noise seed) - BASELINE.json configs[3] (training step) at parity-test size
+    "c4_train_k3_128_calib": (128, 3, (2, 3, 128, 128), "calib", 11),
+    "c4_train_k1_64x128_calib": (128, 1, (2, 3, 64, 128), "calib", 12),
+}
+TRAIN_SAMPLES = 48        # entries kept per gradient tensor
+
+
+def sample_index(numel: int, n: int = TRAIN_SAMPLES):
+    return np.unique(np.linspace(0, numel - 1, num=min(n, numel)).astype(np.int64))
+
+
+def main_train():
+    """The reference's training step (Trainer.py:81-86): model(imgs) with its own torch.rand_like noise, rd_loss,
+    loss.backward(), torch.optim.Adam(lr=1e-4).step().  Gradients are kept as per-tensor L2 norms + sampled entries."""
+    Models, RDL = import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    from oracle import backward as OB
+    for name, (M, K, shape, init, nseed) in TRAIN_CASES.items():
+        model = build_reference_model(Models, M, K, init)
+        sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+        digest = state_digest(sd0)
+        torch.manual_seed(1)
+        x = torch.rand(*shape)
+        B, _, H, W = shape
+        # the reference draws z's noise first, then y's (Models.py:57-58), from the global generator
+        torch.manual_seed(nseed)
+        noise_z = torch.rand(B, M, H // 64, W // 64) - 0.5
+        noise_y = torch.rand(B, M, H // 16, W // 16) - 0.5
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        opt.zero_grad()
+        torch.manual_seed(nseed)
+        out = model(x)                                   # training=True is the default (Trainer.py:82)
+        assert torch.equal(out["z_in"] - out["z"], (out["z"] + noise_z) - out["z"]), "noise stream not reproduced"
+        rd = RDL.rd_loss(out, x, 0.005)
+        rd["loss"].backward()
+        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        opt.step()
+        after = {k: p.detach().clone() for k, p in model.named_parameters()}
+        # fp64 shadow of the same step through the oracle: the conditioning band of each gradient
+        _, g64, _ = OB.loss_and_grads(sd0, x, M, K, noise_z, noise_y, 0.005, dtype=torch.float64)
+        blob = {"x": x.numpy(), "noise_z": noise_z.numpy(), "noise_y": noise_y.numpy(), "state_digest": np.array(digest),
+                "M": np.array(M), "K": np.array(K), "init": np.array(init), "loss": np.array(float(rd["loss"].detach())),
+                "bpp_total": np.array(rd["bpp_total"]), "mse": np.array(rd["mse"])}
+        for k, g in grads.items():
+            idx = sample_index(g.numel())
+            blob["gnorm_" + k] = np.array(float(g.double().norm()))
+            blob["gnorm64_" + k] = np.array(float(g64[k].norm()))
+            blob["gerr64_" + k] = np.array(float((g.double() - g64[k]).norm()))
+            blob["gsamp_" + k] = g.reshape(-1)[idx].numpy()
+            blob["psamp_" + k] = after[k].reshape(-1)[idx].numpy()
+            blob["dnorm_" + k] = np.array(float((after[k].double() - sd0[k].double()).norm()))
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **blob)
+        worst = max(float(blob["gerr64_" + k] / max(blob["gnorm64_" + k], 1e-30)) for k in grads)
+        print(f"{name}: loss {float(rd['loss']):.6f} bpp {rd['bpp_total']:.6f} mse {rd['mse']:.6f}; {len(grads)} gradients, "
+              f"worst fp32-vs-fp64 relative gradient error {worst:.2e} -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "scalable":
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        main_train()               # only the c4_train_* files
+    elif len(sys.argv) > 1 and sys.argv[1] == "scalable":
         main_scalable()            # only the c5_* files; the other vectors stay byte-identical
     else:
         main()

@@ -17,7 +17,16 @@ INITS = {"plain": (1.0, 1.0, 0.0), "gain": (136.2, 3.86, 0.0), "calib": (34.0, 3
 
 def golden_cases():
     """JointAutoregressiveHierarchical cases (configs 1-3)."""
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "c[1-4]*.npz")))
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "c[1-3]*.npz")))
+
+
+def train_cases():
+    """Training-step cases (config 4: the reference's forward + rd_loss + backward + one Adam step, oracle/make_golden.py train)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "c4_train_*.npz")))
+
+
+def sample_index(numel: int, n: int = 48):
+    return np.unique(np.linspace(0, numel - 1, num=min(n, numel)).astype(np.int64))
 
 
 def scalable_cases():

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import backward as OB
 from oracle import forward as O
 from tests import helpers as H
 
@@ -98,3 +99,29 @@ def test_scalable_oracle_matches_reference_submodules(case):
     for key in ("bpp_y1", "bpp_y2", "bpp_y", "bpp_z", "bpp_total", "mse", "psnr", "bits_y1", "bits_y2", "bits_z", "bits_total"):
         assert abs(rd[key] - float(g["rd_" + key])) <= 1e-6 * max(1.0, abs(float(g["rd_" + key]))), key
     assert abs(float(rd["loss"]) - float(g["rd_loss"])) <= 1e-5 * abs(float(g["rd_loss"]))
+
+
+@pytest.mark.parametrize("case", H.train_cases())
+def test_training_step_oracle_matches_reference_gradients(case):
+    """Config 4: autograd over the oracle (+ restated Adam) against the REAL reference's loss.backward() / Adam.step()."""
+    g = H.load_golden(case)
+    M, K, init = int(g["M"]), int(g["K"]), str(g["init"])
+    model = H.seeded_model(M, K, init)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    assert H.state_digest(sd) == str(g["state_digest"])
+    x, nz, ny = (torch.from_numpy(g[k]) for k in ("x", "noise_z", "noise_y"))
+    rd, grads, _ = OB.loss_and_grads(sd, x, M, K, nz, ny, 0.005)
+    assert abs(rd["loss"] - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    keys = [k[6:] for k in g.files if k.startswith("gnorm_")]
+    assert set(keys) == set(grads.keys()) == set(OB.parameter_keys(sd)) and len(keys) == 59
+    sd["context_model.masked.weight"] *= O.mask_a(sd["context_model.masked.weight"])     # the forward's in-place side effect
+    new, _ = OB.adam_step(sd, grads)
+    for k in keys:
+        idx = H.sample_index(grads[k].numel())
+        gn = float(g["gnorm_" + k])
+        assert abs(float(grads[k].double().norm()) - gn) <= 2e-5 * gn + 1e-12, k
+        np.testing.assert_allclose(grads[k].reshape(-1)[idx].numpy(), g["gsamp_" + k], rtol=2e-4, atol=2e-5 * gn / grads[k].numel() ** 0.5, err_msg=k)
+        # the reference's masked taps receive gradient (ContextModels.py:19 masks the data, not the graph)
+        np.testing.assert_allclose(new[k].reshape(-1)[idx].numpy(), g["psamp_" + k], rtol=1e-6, atol=2e-6, err_msg=k)
+    w = grads["context_model.masked.weight"]
+    assert float(w[:, :, 3:].abs().sum()) > 0, "masked taps carry gradient in the reference"
