@@ -245,6 +245,67 @@ int nic_rd_finalize(const float* logp_y_partials, const float* logp_z_partials,
  */
 int nic_rd_reduce(const float* per_image, int32_t b, int32_t num_pixels, float lambda_rd, float* scalars, void* stream);
 
+/* ---- training step: backward kernels (fp32, CUDA cores) -------------------------------------------------------
+ * The reference has no backward code: its gradients are what torch autograd derives from Models.py:49-106 +
+ * RateDistortionLoss.py:5-49 when Trainer.py:85 calls loss.backward().  These entries are those derivatives written
+ * out; all tensors f32.  The DATA gradient of a conv layer is the adjoint conv and goes through nic_conv_fwd with the
+ * mirrored descriptor (Conv2d <-> ConvTranspose2d over the same weight tensor, output_padding chosen to restore the
+ * forward input size).
+ */
+
+/*
+ * Weight (+ bias) gradient of one conv layer.  `d` is the FORWARD descriptor (precision / epilogue ignored; mask_a
+ * ignored: the reference masks the weight DATA, ContextModels.py:19, so all taps receive gradient).
+ *   x  forward input  (d->in_layout)      g  gradient w.r.t. the conv output before its activation (d->out_layout)
+ *   dw reference layout [c_out, c_in, kh, kw] (Conv2d) / [c_in, c_out, kh, kw] (ConvTranspose2d);  db [c_out] or NULL
+ * The tensor with the SMALLER spatial extent (g for Conv2d, x for ConvTranspose2d) must be NHWC with c % 4 == 0; the
+ * other may be NCHW (the 3-channel image side).  Split-K over pixels with a fixed-order fold: deterministic.
+ */
+size_t nic_conv_wgrad_workspace_bytes(const nic_conv_desc* d);
+int nic_conv_wgrad(const nic_conv_desc* d, const float* x, const float* g, float* dw, float* db,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* LeakyReLU(0.01) backward from the saved activation OUTPUT: g_pre = out > 0 ? g : 0.01 g (may run in place on g) */
+int nic_lrelu_bwd(const float* g, const float* out, float* g_pre, int64_t n, void* stream);
+
+/*
+ * compressai GDN / IGDN backward (call sites Components.py:11-15, 40-44), NHWC f32.
+ *   u  the layer input (the conv output before the GDN), g  gradient w.r.t. the GDN output
+ *   du gradient w.r.t. u;  dbeta_raw [c], dgamma_raw [c, c]: gradients w.r.t. the STORED (reparametrised) parameters,
+ *   through eff = LowerBound(raw)^2 - 2^-36 with compressai's rule (passes where raw >= bound or the gradient is < 0).
+ */
+size_t nic_gdn_bwd_workspace_bytes(int32_t n, int32_t c, int32_t h, int32_t w);
+int nic_gdn_bwd(const float* u, const float* g, int32_t n, int32_t c, int32_t h, int32_t w, int32_t inverse, float beta_min,
+                const float* beta_raw, const float* gamma_raw, float* du, float* dbeta_raw, float* dgamma_raw,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Backward of nic_gm_likelihood_fwd w.r.t. y_in and the raw entropy-parameter tensor (softmax / softplus / erf-form CDF
+ * difference / clamp_min(1e-9) / log chain).  g_logp [b, m, hw] = upstream gradient of logp, or NULL: every element's
+ * upstream is g_scalar (rd_loss: -1 / (ln2 * num_pixels * B)).  dy_in [b, m, hw], draw like raw.
+ */
+int nic_gm_likelihood_bwd(const float* y_in, const float* raw, const float* g_logp, float g_scalar,
+                          int32_t b, int32_t m, int32_t hw, int32_t k, float* dy_in, float* draw, void* stream);
+
+/*
+ * Backward of nic_factorized_likelihood_fwd: dz_in [b, c, hw]; dparams [c, 43] = gradients w.r.t. the RAW reference
+ * parameters (matrices / biases / factors) in nic_pack_factorized order (the softplus / tanh chain is applied).
+ */
+int nic_factorized_likelihood_bwd(const float* z_in, const float* fparams, const float* g_logp, float g_scalar,
+                                  int32_t b, int32_t c, int32_t hw, float* dz_in, float* dparams, void* stream);
+
+/* g_x_hat = coef * (x_hat - x): backward of the MSE term (RateDistortionLoss.py:26-34; coef = g_loss * lambda * 255^2 * 2 / (B*C*H*W)) */
+int nic_sse_bwd(const float* x_hat, const float* x, int64_t n, float coef, float* g_x_hat, void* stream);
+
+/* dst += src */
+int nic_add_inplace(float* dst, const float* src, int64_t n, void* stream);
+/* [n, c, hw] -> [n, hw, c] (to_nhwc = 1) or back (0); accumulate = 1: dst += converted src */
+int nic_layout_convert(const float* src, float* dst, int32_t n, int32_t c, int32_t hw, int32_t to_nhwc, int32_t accumulate, void* stream);
+
+/* One torch.optim.Adam update (no weight decay / amsgrad; Main.ipynb:133) of a flat parameter; step = t >= 1 after the increment */
+int nic_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  int32_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

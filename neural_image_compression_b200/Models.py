@@ -84,6 +84,12 @@ class JointAutoregressiveHierarchical(nn.Module):
         B, _, H, W = x.shape
         if H % 64 or W % 64:
             raise ValueError(f"H and W must be multiples of 64 (four stride-2 stages in g_a, two in h_a); got {H}x{W}")
+        if training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # the reference's training call (Trainer.py:82): autograd is on, so the step must be differentiable.  One autograd
+            # node over the fp32 arm with hand-written backward kernels (training.py); under torch.no_grad() the call below
+            # runs the forward-only path of self.precision instead.
+            from . import training as _training
+            return _training.train_forward(self, x, noise=noise, lean=lean)
         prec_up = {"fp32": "fp32", "mixed": "fp32", "bf16x3": "bf16x3", "bf16": "bf16"}[self.precision]   # g_a, h_a
         prec = {"fp32": "fp32", "mixed": "bf16", "bf16x3": "bf16x3", "bf16": "bf16"}[self.precision]    # h_s, context, entropy parameters, g_s
         adt = engine.act_dtype(prec)

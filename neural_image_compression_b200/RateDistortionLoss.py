@@ -48,11 +48,19 @@ def rd_terms(model_out: dict, x: torch.Tensor, lambda_rd: float):
 
 
 def rd_loss(model_out: dict, x: torch.Tensor, lambda_rd: float):
-    per_image, scalars = rd_terms(model_out, x, lambda_rd)
+    with torch.no_grad():
+        per_image, scalars = rd_terms(model_out, x, lambda_rd)
+    loss = scalars[5]
+    diff = [model_out[k] for k in ("logp_y", "logp_z", "x_hat")]
+    if torch.is_grad_enabled() and any(t.requires_grad for t in diff):
+        # Trainer.py:85 calls results['loss'].backward(): the loss is one autograd node over (logp_y, logp_z, x_hat)
+        from .training import _RDLoss
+        xd = x.to(diff[2].device).contiguous().float()
+        loss = _RDLoss.apply(diff[0], diff[1], diff[2].contiguous().float(), xd, float(lambda_rd), scalars)
     s = scalars.tolist()                                   # the one host synchronisation
     mse_per_image = per_image[2]
     return {
-        "loss": scalars[5],
+        "loss": loss,
         "bpp_y": s[0], "bpp_z": s[1], "bpp_total": s[2], "mse": s[3], "psnr": s[4],
         "mse_per_image": mse_per_image,
         "psnr_per_image": -10 * torch.log10(mse_per_image + 1e-8),

@@ -56,6 +56,18 @@ SIGNATURES = {
     "nic_sum_fwd": (C.c_int, [_vp, _i32, _i64, _vp, _vp]),
     "nic_rd_reduce": (C.c_int, [_vp, _i32, _i32, _f32, _vp, _vp]),
     "nic_rd_finalize": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _f32, _vp, _vp, _vp]),
+    # training step (backward)
+    "nic_conv_wgrad_workspace_bytes": (_sz, [C.POINTER(ConvDesc)]),
+    "nic_conv_wgrad": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nic_lrelu_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "nic_gdn_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "nic_gdn_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nic_gm_likelihood_bwd": (C.c_int, [_vp, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "nic_factorized_likelihood_bwd": (C.c_int, [_vp, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "nic_sse_bwd": (C.c_int, [_vp, _vp, _i64, _f32, _vp, _vp]),
+    "nic_add_inplace": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "nic_layout_convert": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "nic_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp]),
 }
 
 _lib = None

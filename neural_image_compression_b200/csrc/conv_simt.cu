@@ -452,6 +452,24 @@ int gdn_fwd_fp32(const float* x, int n, int c, int h, int w, int layout, int inv
   return launch_simt(g, st);
 }
 
+// y[pixels][c_out] = epilogue((x or x^2)[pixels][c_in] . w[c_in][c_out] + bias): the channel-mixing contraction the GDN
+// backward (backward.cu) reuses for the norm and for gamma^T . t.  NIC_EPI_GDN / IGDN read x back as the multiplicand.
+int conv1x1_fp32(const float* x, long pixels, int cin, int cout, const float* w, const float* bias, float* y, int a_square,
+                 int epilogue, cudaStream_t st) {
+  if (pixels > 0x7fffffffL) return fail(NIC_E_BADSHAPE, "conv1x1: %ld pixels", pixels);
+  SimtParams g{};
+  nic_conv_desc gd{};
+  gd.n = 1; gd.c_in = cin; gd.c_out = cout; gd.h_in = gd.h_out = 1; gd.w_in = gd.w_out = static_cast<int>(pixels);
+  gd.kh = gd.kw = 1; gd.stride = 1;
+  if (int rc = build_tap_table(&gd, &g.tt)) return rc;
+  g.n = 1; g.cin = cin; g.cout = cout; g.hin = g.hout = 1; g.win = g.wout = static_cast<int>(pixels);
+  g.x = x; g.w = w; g.bias = bias; g.y = y;
+  set_strides(NIC_LAYOUT_NHWC, cin, 1, pixels, &g.xs_n, &g.xs_c, &g.xs_h, &g.xs_w);
+  set_strides(NIC_LAYOUT_NHWC, cout, 1, pixels, &g.ys_n, &g.ys_c, &g.ys_h, &g.ys_w);
+  g.epilogue = epilogue; g.a_square = a_square;
+  return launch_simt(g, st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // latent hand-off (Models.py:52-66)
 // ---------------------------------------------------------------------------------------------

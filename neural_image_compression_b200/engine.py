@@ -111,11 +111,13 @@ class ConvOp:
 
     def run(self, x: torch.Tensor, n: int, h: int, w: int, precision: str, in_layout=LAYOUT_NHWC, out_layout=LAYOUT_NHWC,
             out: Optional[torch.Tensor] = None, out_c_total: int = 0, out_c_offset: int = 0,
-            out_dtype=None) -> torch.Tensor:
+            out_dtype=None, keep_ws: Optional[list] = None) -> torch.Tensor:
         """x: contiguous tensor in `in_layout`; returns (or fills) the output in `out_layout`.
 
         In the "bf16x3" arm bf16 tensors are hi/lo PAIRS (NIC_DT_BF16X2: NHWC with 2*c channels) and the default output
-        is a pair too; out_dtype=torch.float32 asks for a plain fp32 result."""
+        is a pair too; out_dtype=torch.float32 asks for a plain fp32 result.
+        keep_ws: a list that receives the call's workspace tensor (fp32 arm + GDN epilogue: the conv output BEFORE the GDN,
+        NHWC f32 - what the training step's backward needs)."""
         lib = _lib.load()
         require_cuda(x, "conv input")
         x3 = precision == "bf16x3"
@@ -134,6 +136,8 @@ class ConvOp:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
         check(lib.nic_conv_fwd(C.byref(d), ptr(x), ptr(wp), ptr(bias), ptr(gamma), ptr(beta), ptr(out), ptr(ws), ws_bytes,
                                current_stream()), "nic_conv_fwd")
+        if keep_ws is not None:
+            keep_ws.append(ws)
         return out
 
 

@@ -1,0 +1,389 @@
+"""The training step of the reference (Trainer.py:79-86: ``model(imgs)`` -> ``rd_loss`` -> ``loss.backward()`` -> ``Adam.step()``)
+on the sm_100a kernels.
+
+The reference has no backward code of its own: its gradients are what torch autograd derives from Models.py:49-106 and
+RateDistortionLoss.py:5-49.  Here the whole model is ONE autograd node (``_TrainForward``): its forward is the fp32 arm of
+``JointAutoregressiveHierarchical.forward`` keeping the layer inputs, its backward is a hand-scheduled chain of C-ABI calls
+(include/nic.h, "training step" section):
+
+    data gradient of a conv      nic_conv_fwd with the mirrored descriptor (Conv2d <-> ConvTranspose2d, same weight tensor)
+    weight / bias gradients      nic_conv_wgrad (all 25 taps of the masked conv: ContextModels.py:19 masks the data, not the graph)
+    GDN / IGDN                   nic_gdn_bwd (incl. compressai's LowerBound gradient rule on the stored parameters)
+    LeakyReLU                    nic_lrelu_bwd
+    likelihoods                  nic_gm_likelihood_bwd, nic_factorized_likelihood_bwd
+    distortion                   nic_sse_bwd (``_RDLoss`` below is rd_loss's autograd node)
+    optimizer                    nic_adam_step (``Adam`` below: torch.optim.Adam semantics, Main.ipynb:133)
+
+Differentiable outputs: ``x_hat``, ``logp_y``, ``logp_z`` (what rd_loss consumes).  The other dict entries are returned
+detached.  Arithmetic: fp32 on the CUDA cores (parity grade against the reference's own autograd, tests/test_gpu_train.py);
+the tensor-core arms serve the forward / evaluation path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, engine
+from ._lib import (ConvDesc, DT_F32, EPI_BIAS, LAYOUT_NCHW, LAYOUT_NHWC, PREC_FP32, Q_NOISE, Q_PASSTHRU, check, current_stream, ptr)
+
+PREC = "fp32"
+
+
+def _f32(shape, dev):
+    return torch.empty(shape, dtype=torch.float32, device=dev)
+
+
+def _ws(nbytes: int, dev):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)      # torch allocations are >= 256-byte aligned
+
+
+# ---- single backward ops ------------------------------------------------------------------------------------------
+
+def conv_wgrad(conv: nn.Module, x: torch.Tensor, g: torch.Tensor, n: int, h: int, w: int, in_layout: int, out_layout: int):
+    """(dW in the reference layout, db) of one layer; x = forward input, g = gradient w.r.t. the conv output."""
+    lib = _lib.load()
+    op = engine.ConvOp(conv)
+    d = op.desc(n, h, w, PREC, in_layout, out_layout, DT_F32, DT_F32)
+    d.mask_a = 0
+    dw = torch.empty_like(conv.weight, dtype=torch.float32)
+    db = torch.empty_like(conv.bias, dtype=torch.float32)
+    nbytes = lib.nic_conv_wgrad_workspace_bytes(C.byref(d))
+    ws = _ws(nbytes, x.device)
+    check(lib.nic_conv_wgrad(C.byref(d), ptr(x), ptr(g), ptr(dw), ptr(db), ptr(ws), ws.numel(), current_stream()), "nic_conv_wgrad")
+    return dw, db
+
+
+def conv_dgrad(conv: nn.Module, g: torch.Tensor, n: int, h_in: int, w_in: int, g_layout: int = LAYOUT_NHWC,
+               weight: Optional[torch.Tensor] = None, c_in: Optional[int] = None) -> torch.Tensor:
+    """Gradient w.r.t. the layer input (NHWC f32): the adjoint conv through nic_conv_fwd.
+    (h_in, w_in) = forward input size.  `weight` / `c_in` select a slice of the layer's input channels
+    (weight = the matching slice of conv.weight, contiguous)."""
+    lib = _lib.load()
+    transposed = isinstance(conv, nn.ConvTranspose2d)
+    k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+    h_out, w_out = engine.conv_out_hw(conv, h_in, w_in)
+    wt = (conv.weight if weight is None else weight).detach().float().contiguous()
+    cin = conv.in_channels if c_in is None else c_in
+    d = ConvDesc()
+    d.n, d.c_in, d.h_in, d.w_in = n, conv.out_channels, h_out, w_out
+    d.c_out, d.h_out, d.w_out = cin, h_in, w_in
+    d.kh, d.kw, d.stride, d.pad = k, k, s, p
+    d.transposed = 0 if transposed else 1
+    d.output_padding = 0 if transposed else h_in - ((h_out - 1) * s - 2 * p + k)
+    if not transposed and d.output_padding != w_in - ((w_out - 1) * s - 2 * p + k):
+        raise ValueError("conv_dgrad: height and width need the same output padding")
+    d.mask_a, d.epilogue, d.precision = 0, EPI_BIAS, PREC_FP32
+    d.in_layout, d.out_layout, d.in_dtype, d.out_dtype = g_layout, LAYOUT_NHWC, DT_F32, DT_F32
+    dev = g.device
+    wp = _f32(lib.nic_packed_weight_elems(C.byref(d)), dev)
+    check(lib.nic_pack_conv_weight(C.byref(d), ptr(wt), ptr(wp), current_stream()), "nic_pack_conv_weight")
+    zero = torch.zeros(cin, dtype=torch.float32, device=dev)
+    out = _f32((n, h_in, w_in, cin), dev)
+    check(lib.nic_conv_fwd(C.byref(d), ptr(g), ptr(wp), ptr(zero), None, None, ptr(out), None, 0, current_stream()), "nic_conv_fwd")
+    return out
+
+
+def lrelu_bwd_(g: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    check(_lib.load().nic_lrelu_bwd(ptr(g), ptr(out), ptr(g), g.numel(), current_stream()), "nic_lrelu_bwd")
+    return g
+
+
+def gdn_bwd(gdn: nn.Module, u: torch.Tensor, g: torch.Tensor, n: int, h: int, w: int):
+    """(du, dbeta, dgamma): u = the conv output before the GDN (NHWC f32), g = gradient w.r.t. the GDN output."""
+    lib = _lib.load()
+    c = gdn.in_channels
+    du = torch.empty_like(u)
+    dbeta = torch.empty_like(gdn.beta, dtype=torch.float32)
+    dgamma = torch.empty_like(gdn.gamma, dtype=torch.float32)
+    ws = _ws(lib.nic_gdn_bwd_workspace_bytes(n, c, h, w), u.device)
+    check(lib.nic_gdn_bwd(ptr(u), ptr(g), n, c, h, w, int(gdn.inverse), float(gdn.beta_min), ptr(gdn.beta.detach().float().contiguous()),
+                          ptr(gdn.gamma.detach().float().contiguous()), ptr(du), ptr(dbeta), ptr(dgamma), ptr(ws), ws.numel(),
+                          current_stream()), "nic_gdn_bwd")
+    return du, dbeta, dgamma
+
+
+def to_nhwc(t_nchw: torch.Tensor, accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n, c = t_nchw.shape[:2]
+    hw = t_nchw[0, 0].numel()
+    out = accumulate_into if accumulate_into is not None else _f32((n,) + tuple(t_nchw.shape[2:]) + (c,), t_nchw.device)
+    check(_lib.load().nic_layout_convert(ptr(t_nchw), ptr(out), n, c, hw, 1, int(accumulate_into is not None), current_stream()),
+          "nic_layout_convert")
+    return out
+
+
+def add_(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    check(_lib.load().nic_add_inplace(ptr(dst), ptr(src), dst.numel(), current_stream()), "nic_add_inplace")
+    return dst
+
+
+_FACT_SLICES = (("matrices", 0, 0, 3), ("biases", 0, 3, 6), ("factors", 0, 6, 9), ("matrices", 1, 9, 18), ("biases", 1, 18, 21),
+                ("factors", 1, 21, 24), ("matrices", 2, 24, 33), ("biases", 2, 33, 36), ("factors", 2, 36, 39),
+                ("matrices", 3, 39, 42), ("biases", 3, 42, 43))
+
+
+# ---- the model as one autograd node ------------------------------------------------------------------------------
+
+class _TrainForward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, noise_z, noise_y, lean, *params):
+        lib = _lib.load()
+        dev = x.device
+        B, _, H, W = x.shape
+        M, K = model.M, model.K
+        hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
+        S = {}
+        with torch.cuda.device(dev):
+            # g_a
+            a, h, w, layout = x, H, W, LAYOUT_NCHW
+            enc = model.encoder.ops
+            S["enc_in"], S["enc_u"] = [], []
+            for op in enc:
+                S["enc_in"].append((a, h, w, layout))
+                keep = []
+                a = op.run(a, B, h, w, PREC, in_layout=layout, out_layout=LAYOUT_NHWC, keep_ws=keep)
+                S["enc_u"].append(keep[0].view(torch.float32) if op.gdn is not None else None)
+                h, w = engine.conv_out_hw(op.conv, h, w)
+                layout = LAYOUT_NHWC
+            y_nhwc = a
+            y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, Q_NOISE, noise_y, torch.float32)
+            # h_a (reads the unquantised y)
+            a, h, w = y_nhwc, hy, wy
+            S["ha_in"] = []
+            for op in model.hyper_encoder.ops:
+                S["ha_in"].append((a, h, w))
+                a = op.run(a, B, h, w, PREC)
+                h, w = engine.conv_out_hw(op.conv, h, w)
+            z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, Q_NOISE, noise_z, torch.float32)
+            # h_s -> psi, context -> phi, both windows of `combined`
+            combined = _f32((B, hy, wy, 4 * M), dev)
+            a, h, w = z_in_nhwc, hz, wz
+            hs = model.hyper_decoder.ops
+            S["hs_in"] = []
+            for i, op in enumerate(hs):
+                S["hs_in"].append((a, h, w))
+                if i == len(hs) - 1:
+                    op.run(a, B, h, w, PREC, out=combined, out_c_total=4 * M, out_c_offset=2 * M)
+                else:
+                    a = op.run(a, B, h, w, PREC)
+                h, w = engine.conv_out_hw(op.conv, h, w)
+            model.context_model.masked.apply_mask_()
+            model.context_model.masked._op.run(y_in_nhwc, B, hy, wy, PREC, out=combined, out_c_total=4 * M, out_c_offset=0)
+            ep = model.entropy_parameters.ops
+            e1 = ep[0].run(combined, B, hy, wy, PREC)
+            e2 = ep[1].run(e1, B, hy, wy, PREC)
+            raw = ep[2].run(e2, B, hy, wy, PREC, out_layout=LAYOUT_NCHW, out_dtype=torch.float32)
+            from .EntropyModels import gm_likelihood
+            ly = gm_likelihood(y_in, raw, M, K, Q_PASSTHRU, full=not lean, want_y_in=False)
+            _, p_z, logp_z, parts_z = model.factorized_entropy_model.likelihood(z_in, Q_PASSTHRU)
+            # g_s
+            a, h, w = y_in_nhwc, hy, wy
+            dec = model.decoder.ops
+            S["dec_in"], S["dec_u"] = [], []
+            for i, op in enumerate(dec):
+                last = i == len(dec) - 1
+                S["dec_in"].append((a, h, w))
+                keep = []
+                a = op.run(a, B, h, w, PREC, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC, keep_ws=keep)
+                S["dec_u"].append(keep[0].view(torch.float32) if op.gdn is not None else None)
+                h, w = engine.conv_out_hw(op.conv, h, w)
+            x_hat = a
+        S.update(combined=combined, e1=e1, e2=e2, raw=raw, y_in=y_in, y_in_nhwc=y_in_nhwc, z_in=z_in, z_in_nhwc=z_in_nhwc,
+                 fparams=model.factorized_entropy_model.packed(), shape=(B, H, W))
+        ctx.model, ctx.S = model, S
+        ctx.x_needs_grad = x.requires_grad
+        logp_y = ly["logp"]
+        extra = [] if lean else ([ly["mu"], ly["sigma"]] if K == 1 else [ly["weights"], ly["mus"], ly["sigmas"]])
+        nd = [y, y_in, z, z_in, p_z, ly["p"], ly["partials"], parts_z] + extra
+        ctx.mark_non_differentiable(*nd)
+        return (x_hat, logp_y, logp_z, *nd)
+
+    @staticmethod
+    def backward(ctx, g_xhat, g_logp_y, g_logp_z, *unused):
+        model, S = ctx.model, ctx.S
+        lib = _lib.load()
+        B, H, W = S["shape"]
+        M, K = model.M, model.K
+        hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
+        dev = S["raw"].device
+        grads: Dict[int, torch.Tensor] = {}
+
+        def put(param, g):
+            grads[id(param)] = g if id(param) not in grads else grads[id(param)] + g
+
+        with torch.cuda.device(dev), torch.no_grad():
+            d_yin = None                                             # NHWC gradient w.r.t. y_in, accumulated over its three consumers
+            # ---- g_s ------------------------------------------------------------------------------------------------
+            if g_xhat is not None:
+                g, g_layout = g_xhat.contiguous().float(), LAYOUT_NCHW
+                dec = model.decoder.ops
+                for i in range(len(dec) - 1, -1, -1):
+                    op = dec[i]
+                    a, h, w = S["dec_in"][i]
+                    ho, wo = engine.conv_out_hw(op.conv, h, w)
+                    if op.gdn is not None:
+                        g, dbeta, dgamma = gdn_bwd(op.gdn, S["dec_u"][i], g, B, ho, wo)
+                        put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
+                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, g_layout)
+                    put(op.conv.weight, dw); put(op.conv.bias, db)
+                    g = conv_dgrad(op.conv, g, B, h, w, g_layout)
+                    g_layout = LAYOUT_NHWC
+                d_yin = g
+            # ---- p_y: likelihood, entropy parameters, context model, h_s --------------------------------------------
+            d_zin = None
+            if g_logp_y is not None:
+                gl = g_logp_y.contiguous().float()
+                dy_lik = torch.empty_like(S["y_in"])
+                draw = torch.empty_like(S["raw"])
+                check(lib.nic_gm_likelihood_bwd(ptr(S["y_in"]), ptr(S["raw"]), ptr(gl), 0.0, B, M, hy * wy, K, ptr(dy_lik), ptr(draw),
+                                                current_stream()), "nic_gm_likelihood_bwd")
+                d_yin = to_nhwc(dy_lik, accumulate_into=d_yin)
+                g = to_nhwc(draw)
+                ep = model.entropy_parameters.ops
+                for i, (op, a) in reversed(list(enumerate(zip(ep, (S["combined"], S["e1"], S["e2"]))))):
+                    dw, db = conv_wgrad(op.conv, a, g, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC)
+                    put(op.conv.weight, dw); put(op.conv.bias, db)
+                    if i > 0:
+                        g = lrelu_bwd_(conv_dgrad(op.conv, g, B, hy, wy), a)
+                w0 = ep[0].conv.weight.detach()
+                d_phi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, :2 * M].contiguous(), c_in=2 * M)
+                d_psi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, 2 * M:].contiguous(), c_in=2 * M)
+                masked = model.context_model.masked
+                dw, db = conv_wgrad(masked, S["y_in_nhwc"], d_phi, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC)
+                put(masked.weight, dw); put(masked.bias, db)
+                d_yin = add_(d_yin, conv_dgrad(masked, d_phi, B, hy, wy))
+                g = d_psi
+                hs = model.hyper_decoder.ops
+                for i in range(len(hs) - 1, -1, -1):
+                    op = hs[i]
+                    a, h, w = S["hs_in"][i]
+                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC)
+                    put(op.conv.weight, dw); put(op.conv.bias, db)
+                    g = conv_dgrad(op.conv, g, B, h, w)
+                    if i > 0:
+                        g = lrelu_bwd_(g, a)                         # a = LeakyReLU output of layer i - 1
+                d_zin = g
+            # ---- p_z ----------------------------------------------------------------------------------------------------
+            if g_logp_z is not None:
+                gl = g_logp_z.contiguous().float()
+                fe = model.factorized_entropy_model
+                dz_fac = torch.empty_like(S["z_in"])
+                dpar = _f32((M, 43), dev)
+                check(lib.nic_factorized_likelihood_bwd(ptr(S["z_in"]), ptr(S["fparams"]), ptr(gl), 0.0, B, M, hz * wz, ptr(dz_fac),
+                                                        ptr(dpar), current_stream()), "nic_factorized_likelihood_bwd")
+                for name, idx, lo, hi in _FACT_SLICES:
+                    prm = getattr(fe, name)[idx]
+                    put(prm, dpar[:, lo:hi].reshape(prm.shape).contiguous())
+                d_zin = to_nhwc(dz_fac, accumulate_into=d_zin)
+            # ---- h_a (z_in = z + noise: the gradient passes unchanged) --------------------------------------------------
+            dy = d_yin
+            if d_zin is not None:
+                g = d_zin
+                ha = model.hyper_encoder.ops
+                for i in range(len(ha) - 1, -1, -1):
+                    op = ha[i]
+                    a, h, w = S["ha_in"][i]
+                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC)
+                    put(op.conv.weight, dw); put(op.conv.bias, db)
+                    g = conv_dgrad(op.conv, g, B, h, w)
+                    if i > 0:
+                        g = lrelu_bwd_(g, a)
+                dy = g if dy is None else add_(dy, g)
+            # ---- g_a (y_in = y + noise) ---------------------------------------------------------------------------------
+            if dy is not None:
+                g = dy
+                enc = model.encoder.ops
+                for i in range(len(enc) - 1, -1, -1):
+                    op = enc[i]
+                    a, h, w, layout = S["enc_in"][i]
+                    ho, wo = engine.conv_out_hw(op.conv, h, w)
+                    if op.gdn is not None:
+                        g, dbeta, dgamma = gdn_bwd(op.gdn, S["enc_u"][i], g, B, ho, wo)
+                        put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
+                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, layout, LAYOUT_NHWC)
+                    put(op.conv.weight, dw); put(op.conv.bias, db)
+                    if i > 0:
+                        g = conv_dgrad(op.conv, g, B, h, w)
+        ctx.S = None
+        params = [p for _, p in model.named_parameters()]
+        return (None, None, None, None, None, *[grads.get(id(p)) for p in params])
+
+
+def train_forward(model, x: torch.Tensor, noise=None, lean: bool = False) -> dict:
+    """``model(x, training=True)`` as a differentiable call (used by JointAutoregressiveHierarchical.forward when autograd is on)."""
+    B, _, H, W = x.shape
+    M, K = model.M, model.K
+    if noise is not None:
+        noise_z, noise_y = noise
+    else:                                                    # the reference draws z's noise first (Models.py:57-58)
+        noise_z = torch.rand((B, M, H // 64, W // 64), device=x.device) - 0.5
+        noise_y = torch.rand((B, M, H // 16, W // 16), device=x.device) - 0.5
+    params = [p for _, p in model.named_parameters()]
+    res = _TrainForward.apply(model, x.contiguous().float(), noise_z, noise_y, lean, *params)
+    x_hat, logp_y, logp_z, y, y_in, z, z_in, p_z, p_y, parts_y, parts_z = res[:11]
+    logp_y._nic_partials, logp_z._nic_partials = parts_y, parts_z      # per-image sums of logp ride along for rd_loss
+    out = {"x_hat": x_hat, "y": y, "y_in": y_in, "z": z, "z_in": z_in, "p_z": p_z, "logp_z": logp_z, "p_y": p_y, "logp_y": logp_y,
+           "training": True}
+    if not lean:
+        if K == 1:
+            out["mu"], out["sigma"] = res[11:13]
+        else:
+            out["weights"], out["mus"], out["sigmas"] = res[11:14]
+    return out
+
+
+class _RDLoss(torch.autograd.Function):
+    """loss = bpp_total + lambda * 255^2 * mse (RateDistortionLoss.py:13-34) as one node: the value comes from nic_rd_finalize,
+    the gradients are d loss / d logp = -1 / (ln 2 * H * W * B) and d loss / d x_hat = lambda * 255^2 * 2 (x_hat - x) / (B * C * H * W)."""
+
+    @staticmethod
+    def forward(ctx, logp_y, logp_z, x_hat, x, lambda_rd, scalars):
+        ctx.save_for_backward(x_hat, x)
+        ctx.lambda_rd, ctx.shapes = float(lambda_rd), (logp_y.shape, logp_z.shape)
+        return scalars[5].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        x_hat, x = ctx.saved_tensors
+        B, C_, H, W = x.shape
+        gl = g.float() * (-1.0 / (math.log(2.0) * H * W * B))
+        gx = torch.empty_like(x_hat)
+        coef = ctx.lambda_rd * 65025.0 * 2.0 / x.numel()
+        with torch.cuda.device(x_hat.device):
+            check(_lib.load().nic_sse_bwd(ptr(x_hat), ptr(x), x.numel(), coef, ptr(gx), current_stream()), "nic_sse_bwd")
+        gx.mul_(g.float())
+        return gl.expand(ctx.shapes[0]), gl.expand(ctx.shapes[1]), gx, None, None, None
+
+
+class Adam:
+    """torch.optim.Adam(params, lr) (Main.ipynb:133; defaults betas (0.9, 0.999), eps 1e-8, no weight decay) on nic_adam_step."""
+
+    def __init__(self, params, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.params: List[torch.Tensor] = [p for p in params]
+        self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        self.m = [torch.zeros_like(p, dtype=torch.float32) for p in self.params]
+        self.v = [torch.zeros_like(p, dtype=torch.float32) for p in self.params]
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    @torch.no_grad()
+    def step(self):
+        lib = _lib.load()
+        self.t += 1
+        for p, m, v in zip(self.params, self.m, self.v):
+            if p.grad is None:
+                continue
+            engine.require_cuda(p, "parameter")
+            g = p.grad.contiguous().float()
+            with torch.cuda.device(p.device):
+                check(lib.nic_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                        self.t, current_stream()), "nic_adam_step")
+            torch.autograd.graph.increment_version(p)       # updated behind torch's back: packed-weight caches key on _version

@@ -222,10 +222,9 @@ def main_train():
         torch.manual_seed(1)
         x = torch.rand(*shape)
         B, _, H, W = shape
-        # the reference draws z's noise first, then y's (Models.py:57-58), from the global generator
-        torch.manual_seed(nseed)
-        noise_z = torch.rand(B, M, H // 64, W // 64) - 0.5
-        noise_y = torch.rand(B, M, H // 16, W // 16) - 0.5
+        # the reference draws z's noise first, then y's (Models.py:57-58), from the global generator; the seed is the first one
+        # from `nseed` on that keeps every LeakyReLU pre-activation >= 1e-6 away from its kink (oracle/backward.py: kink_margin)
+        nseed, noise_z, noise_y = OB.noise_with_margin(sd0, x, M, K, nseed)
         opt = torch.optim.Adam(model.parameters(), lr=1e-4)
         opt.zero_grad()
         torch.manual_seed(nseed)
@@ -240,7 +239,8 @@ def main_train():
         _, g64, _ = OB.loss_and_grads(sd0, x, M, K, noise_z, noise_y, 0.005, dtype=torch.float64)
         blob = {"x": x.numpy(), "noise_z": noise_z.numpy(), "noise_y": noise_y.numpy(), "state_digest": np.array(digest),
                 "M": np.array(M), "K": np.array(K), "init": np.array(init), "loss": np.array(float(rd["loss"].detach())),
-                "bpp_total": np.array(rd["bpp_total"]), "mse": np.array(rd["mse"])}
+                "bpp_total": np.array(rd["bpp_total"]), "mse": np.array(rd["mse"]), "noise_seed": np.array(nseed),
+                "kink_margin": np.array(OB.kink_margin(sd0, x, M, K, noise_z, noise_y))}
         for k, g in grads.items():
             idx = sample_index(g.numel())
             blob["gnorm_" + k] = np.array(float(g.double().norm()))
@@ -252,7 +252,7 @@ def main_train():
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **blob)
         worst = max(float(blob["gerr64_" + k] / max(blob["gnorm64_" + k], 1e-30)) for k in grads)
-        print(f"{name}: loss {float(rd['loss']):.6f} bpp {rd['bpp_total']:.6f} mse {rd['mse']:.6f}; {len(grads)} gradients, "
+        print(f"{name}: noise seed {nseed}, LeakyReLU margin {float(blob['kink_margin']):.2e}, loss {float(rd['loss'].detach()):.6f} bpp {rd['bpp_total']:.6f} mse {rd['mse']:.6f}; {len(grads)} gradients, "
               f"worst fp32-vs-fp64 relative gradient error {worst:.2e} -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
 
 

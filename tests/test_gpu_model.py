@@ -108,7 +108,8 @@ def test_training_forward_with_injected_noise(precision):
     torch.manual_seed(12)
     nz, ny = torch.rand(2, 128, 1, 2) - 0.5, torch.rand(2, 128, 4, 8) - 0.5
     ref = O.forward(sd, x, 128, 3, training=True, noise_z=nz, noise_y=ny)
-    out = model.cuda()(x.cuda(), training=True, noise=(nz.cuda(), ny.cuda()))
+    with torch.no_grad():                      # forward-only path of this arm (with autograd on, training=True is the fp32 train step)
+        out = model.cuda()(x.cuda(), training=True, noise=(nz.cuda(), ny.cuda()))
     assert out["training"] is True
     np.testing.assert_allclose(out["y_in"].cpu().numpy(), ref["y_in"].numpy(), rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(out["z_in"].cpu().numpy(), ref["z_in"].numpy(), rtol=1e-4, atol=1e-4)
@@ -117,7 +118,8 @@ def test_training_forward_with_injected_noise(precision):
     # summation) or ~1e-5 relative (bf16x3: 16-bit operand splits), amplified by |u| = |y - mu| / sigma in the tails
     assert bad <= {"fp32": 0.002, "bf16x3": 0.02}[precision] * ref["p_y"].numel() and worst < 5e-5, (bad, worst)
     # without injected noise the draw is internal and in U(-.5, .5)
-    out2 = model(x.cuda(), training=True)
+    with torch.no_grad():
+        out2 = model(x.cuda(), training=True)
     d = (out2["y_in"] - out2["y"]).abs().max()
     assert 0.3 < float(d) <= 0.5
 
@@ -169,7 +171,8 @@ def test_config4_training_forward_shape(precision):
     ref = O.forward(sd, x, 128, 3, training=True, noise_z=nz, noise_y=ny)
     ref_rd = O.rd_loss(ref, x, 0.005)
     model = model.cuda()
-    out = model(x.cuda(), training=True, noise=(nz.cuda(), ny.cuda()))
+    with torch.no_grad():
+        out = model(x.cuda(), training=True, noise=(nz.cuda(), ny.cuda()))
     rd = rd_loss(out, x.cuda(), 0.005)
     assert out["training"] is True
     assert abs(rd["bpp_total"] - ref_rd["bpp_total"]) <= H.BPP_TOL and abs(rd["psnr"] - ref_rd["psnr"]) <= H.PSNR_TOL

@@ -212,7 +212,8 @@ def test_model_bf16_training_forward_and_k1():
         sd = {k: v.clone() for k, v in model.state_dict().items()}
         nz, ny = torch.rand(2, 128, 2, 3) - 0.5, torch.rand(2, 128, 8, 12) - 0.5
         ref = O.forward(sd, x, 128, K, training=True, noise_z=nz, noise_y=ny)
-        out = model.cuda()(x.cuda(), training=True, noise=(nz.cuda(), ny.cuda()))
+        with torch.no_grad():                      # forward-only path of this arm (with autograd on, training=True is the fp32 train step)
+            out = model.cuda()(x.cuda(), training=True, noise=(nz.cuda(), ny.cuda()))
         assert out["training"] is True and set(out) >= ({"mu", "sigma"} if K == 1 else {"weights", "mus", "sigmas"})
         assert float((out["y_in"].cpu() - ref["y_in"]).abs().max() / ref["y_in"].abs().max()) < 3e-2
         bits = -out["logp_y"].double().sum().item() / np.log(2)

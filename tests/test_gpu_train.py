@@ -1,0 +1,147 @@
+"""GPU: the training step (BASELINE configs[3]; reference Trainer.py:79-86) against the oracle's autograd.
+
+model(x) with autograd on -> rd_loss -> loss.backward() -> Adam step, all through the C-ABI backward kernels, compared with
+oracle/backward.py (torch autograd over the restated forward + compressai's LowerBound rule + restated Adam), which is itself
+pinned to the REAL reference's gradients by tests/test_oracle.py (tests/golden/c4_train_*.npz).
+Cases keep every LeakyReLU pre-activation >= 1e-6 away from 0 (the derivative jumps there; see oracle/backward.py).
+Tolerances: every gradient tensor within 2e-4 of its own norm (the reference's fp32-vs-fp64 gradient spread on these cases is
+4e-6 relative; ours adds the accumulation order of split-K sums), loss within 1e-5 relative, Adam-updated parameters within 2e-6.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import backward as OB
+from oracle import forward as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+GRAD_RTOL = 2e-4
+
+
+def rel_err(got, ref):
+    ref = ref.double()
+    return float((got.double().cpu() - ref).norm() / max(float(ref.norm()), 1e-30))
+
+
+@pytest.mark.parametrize("case", H.train_cases())
+def test_training_step_matches_reference_golden(case):
+    """The committed vectors of the REAL reference's backward + Adam step (sampled entries + norms)."""
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    from neural_image_compression_b200.training import Adam
+    g = H.load_golden(case)
+    M, K, init = int(g["M"]), int(g["K"]), str(g["init"])
+    model = H.seeded_model(M, K, init, precision="fp32").cuda()
+    x, nz, ny = (torch.from_numpy(g[k]).cuda() for k in ("x", "noise_z", "noise_y"))
+    opt = Adam(model.parameters(), lr=1e-4)
+    opt.zero_grad()
+    out = model(x, noise=(nz, ny))                      # training=True is the default, as in Trainer.py:82
+    rd = rd_loss(out, x, 0.005)
+    assert abs(float(rd["loss"]) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    rd["loss"].backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    opt.step()
+    torch.cuda.synchronize()
+    assert len(grads) == 59
+    # the Adam kernel itself: restated torch.optim.Adam applied to OUR gradients
+    want, _ = OB.adam_step({k: v.cpu() for k, v in before.items()}, {k: v.cpu() for k, v in grads.items()})
+    for k, p in model.named_parameters():
+        gr = grads[k]
+        idx = H.sample_index(gr.numel())
+        gn = float(g["gnorm_" + k])
+        assert abs(float(gr.double().norm()) - gn) <= GRAD_RTOL * gn + 1e-12, (k, float(gr.double().norm()), gn)
+        g_atol = 10 * GRAD_RTOL * gn / gr.numel() ** 0.5
+        np.testing.assert_allclose(gr.reshape(-1)[idx].cpu().numpy(), g["gsamp_" + k], rtol=1e-3, atol=g_atol, err_msg=k)
+        np.testing.assert_allclose(p.detach().cpu().numpy(), want[k].numpy(), rtol=1e-6, atol=1e-7, err_msg=k)
+        # against the reference's updated parameters: the first Adam step is lr * g / (|g| + eps), whose sensitivity to an
+        # absolute gradient error dg is lr * eps * dg / (|g| + eps)^2 - large only where the gradient itself is ~eps = 1e-8
+        gs = np.abs(g["gsamp_" + k].astype(np.float64))
+        p_atol = 2e-6 + 1e-4 * 1e-8 * g_atol / (gs + 1e-8) ** 2
+        err = np.abs(p.detach().reshape(-1)[idx].cpu().numpy().astype(np.float64) - g["psamp_" + k])
+        bad = err > np.minimum(p_atol, 2.1e-4)
+        assert not bad.any(), (k, err[bad], p_atol[bad], gs[bad], g_atol)
+
+
+@pytest.mark.parametrize("K,shape", [(3, (2, 3, 128, 192)), (1, (3, 3, 64, 64))])
+def test_every_gradient_tensor_against_the_oracle(K, shape):
+    """All 59 gradient tensors in full against the oracle's autograd on the same weights, input and noise."""
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    model = H.seeded_model(128, K, "calib", precision="fp32")
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = H.seeded_input(shape)
+    B, _, Hh, W = shape
+    # a noise draw that keeps every LeakyReLU pre-activation >= 1e-6 from its kink (oracle/backward.py: kink_margin) - closer than
+    # the fp32 accumulation noise, the slope an element gets depends on summation order, in the reference's own runs too
+    _, nz, ny = OB.noise_with_margin(sd, x, 128, K, 21)
+    ref_rd, ref_g, ref_out = OB.loss_and_grads(sd, x, 128, K, nz, ny, 0.005)
+    model = model.cuda()
+    out = model(x.cuda(), training=True, noise=(nz.cuda(), ny.cuda()))
+    rd = rd_loss(out, x.cuda(), 0.005)
+    assert abs(float(rd["loss"]) - ref_rd["loss"]) <= 1e-5 * abs(ref_rd["loss"])
+    assert rel_err(out["x_hat"].detach(), ref_out["x_hat"]) < 1e-5
+    rd["loss"].backward()
+    torch.cuda.synchronize()
+    worst = {}
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        worst[k] = rel_err(p.grad, ref_g[k])
+    bad = {k: v for k, v in worst.items() if v > GRAD_RTOL}
+    print("worst gradient errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    assert not bad, bad
+    # the dict entries the reference returns are all there, the non-differentiable ones detached
+    assert out["logp_y"].requires_grad and out["x_hat"].requires_grad and not out["y_in"].requires_grad
+    assert set(out) >= {"x_hat", "y", "y_in", "z", "z_in", "p_z", "logp_z", "p_y", "logp_y", "training"}
+
+
+def test_gradient_accumulates_and_tensor_core_model_trains_on_the_fp32_arm():
+    """Two backward passes accumulate into .grad like torch; a bf16x3 model's training call takes the same differentiable path."""
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    model = H.seeded_model(128, 3, "calib", precision="bf16x3").cuda()
+    x = H.seeded_input((1, 3, 64, 64)).cuda()
+    torch.manual_seed(5)
+    noise = (torch.rand(1, 128, 1, 1).cuda() - 0.5, torch.rand(1, 128, 4, 4).cuda() - 0.5)
+    rd_loss(model(x, noise=noise), x, 0.005)["loss"].backward()
+    g1 = model.encoder.net[6].weight.grad.clone()
+    rd_loss(model(x, noise=noise), x, 0.005)["loss"].backward()
+    torch.cuda.synchronize()
+    assert torch.allclose(model.encoder.net[6].weight.grad, 2 * g1, rtol=1e-6, atol=0)
+    # determinism: the split-K folds have a fixed order
+    model.zero_grad()
+    rd_loss(model(x, noise=noise), x, 0.005)["loss"].backward()
+    assert torch.equal(model.encoder.net[6].weight.grad, g1)
+
+
+def test_wgrad_kernel_against_torch_autograd_shapes():
+    """nic_conv_wgrad on the layer shapes of the path (incl. the 3-channel NCHW sides, 192 / 640 / 1152 channels, 1x1 and 3x3)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from neural_image_compression_b200 import _lib
+    from neural_image_compression_b200.training import conv_dgrad, conv_wgrad
+    torch.manual_seed(3)
+    cases = [(nn.Conv2d(3, 128, 5, 2, 2), 2, 32, 48, True), (nn.Conv2d(128, 128, 5, 2, 2), 2, 20, 24, False),
+             (nn.ConvTranspose2d(128, 192, 5, 2, 2, 1), 1, 6, 10, False), (nn.ConvTranspose2d(128, 3, 5, 2, 2, 1), 2, 8, 12, False),
+             (nn.Conv2d(192, 256, 3, 1, 1), 1, 9, 7, False), (nn.Conv2d(640, 1152, 1), 2, 5, 6, False),
+             (nn.Conv2d(128, 256, 5, 1, 2), 1, 8, 8, False)]
+    for conv, n, h, w, x_nchw in cases:
+        conv = conv.double()                               # float64 CPU autograd is the reference of this kernel-level check
+        x = torch.randn(n, conv.in_channels, h, w, dtype=torch.float64, requires_grad=True)
+        y = conv(x)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        ref_dw, ref_db, ref_dx = conv.weight.grad.clone(), conv.bias.grad.clone(), x.grad.clone()
+        conv = conv.float().cuda()
+        x, gy = x.detach().float().cuda(), gy.float().cuda()
+        out_nchw = conv.out_channels == 3
+        xi = x.detach() if x_nchw else x.detach().permute(0, 2, 3, 1).contiguous()
+        gi = gy if out_nchw else gy.permute(0, 2, 3, 1).contiguous()
+        dw, db = conv_wgrad(conv, xi, gi, n, h, w, _lib.LAYOUT_NCHW if x_nchw else _lib.LAYOUT_NHWC,
+                            _lib.LAYOUT_NCHW if out_nchw else _lib.LAYOUT_NHWC)
+        assert rel_err(dw, ref_dw) < 5e-6, (conv, rel_err(dw, ref_dw))
+        assert rel_err(db, ref_db) < 5e-6, conv
+        if conv.in_channels >= 16:
+            dx = conv_dgrad(conv, gi, n, h, w, _lib.LAYOUT_NCHW if out_nchw else _lib.LAYOUT_NHWC)
+            assert rel_err(dx.permute(0, 3, 1, 2), ref_dx) < 5e-6, (conv, rel_err(dx.permute(0, 3, 1, 2), ref_dx))
