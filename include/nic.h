@@ -302,6 +302,9 @@ int nic_add_inplace(float* dst, const float* src, int64_t n, void* stream);
 /* [n, c, hw] -> [n, hw, c] (to_nhwc = 1) or back (0); accumulate = 1: dst += converted src */
 int nic_layout_convert(const float* src, float* dst, int32_t n, int32_t c, int32_t hw, int32_t to_nhwc, int32_t accumulate, void* stream);
 
+/* f32 [rows, c] -> NIC_DT_BF16X2 [rows, 2c] = [hi | lo]: hands fp32 activations / gradients to the bf16x3 convs (c % 4 == 0) */
+int nic_to_pair(const float* src, void* dst, int64_t rows, int32_t c, void* stream);
+
 /* One torch.optim.Adam update (no weight decay / amsgrad; Main.ipynb:133) of a flat parameter; step = t >= 1 after the increment */
 int nic_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                   int32_t step, void* stream);

@@ -316,6 +316,27 @@ layout_convert_kernel(const float* __restrict__ src, float* __restrict__ dst, in
   }
 }
 
+// f32 [rows][c] -> bf16 pairs [rows][2c] = [hi(c) | lo(c)] (NIC_DT_BF16X2): feeds fp32 activations / gradients to the bf16x3 convs
+__global__ void __launch_bounds__(256)
+to_pair_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long rows, int c) {
+  const int c4 = c >> 2;
+  const long total = rows * c4;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / c4;
+    const int q = static_cast<int>(i - r * c4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * c + q));
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    __nv_bfloat16* d = dst + r * 2 * c + q;
+    uint2 hi, lo;
+    hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(d) = hi;
+    *reinterpret_cast<uint2*>(d + c) = lo;
+  }
+}
+
 // torch.optim.Adam (no weight decay, no amsgrad): m, v moments; t = step count after the increment
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
                             float beta1, float beta2, float step_size, float sqrt_bc2, float eps) {
@@ -578,6 +599,16 @@ int nic_layout_convert(const float* src, float* dst, int32_t n, int32_t c, int32
   if (!src || !dst) return fail(NIC_E_BADSHAPE, "layout_convert: null pointer");
   layout_convert_kernel<<<dim3((hw + 31) / 32, (c + 31) / 32, n), 256, 0, as_stream(stream)>>>(src, dst, c, hw, to_nhwc, accumulate);
   return check_launch("layout_convert_kernel");
+}
+
+int nic_to_pair(const float* src, void* dst, int64_t rows, int32_t c, void* stream) {
+  if (int rc = nic_check_device()) return rc;
+  if (rows < 0 || c < 4 || c % 4) return fail(NIC_E_BADSHAPE, "to_pair: rows=%lld c=%d (c %% 4 == 0)", static_cast<long long>(rows), c);
+  if (rows == 0) return NIC_OK;
+  if (!src || !dst) return fail(NIC_E_BADSHAPE, "to_pair: null pointer");
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 7)) return fail(NIC_E_BADALIGN, "to_pair: alignment");
+  to_pair_kernel<<<ew_blocks(rows * (c / 4)), 256, 0, as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), rows, c);
+  return check_launch("to_pair_kernel");
 }
 
 int nic_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

@@ -1,4 +1,4 @@
-"""Data-parallel evaluation: the images of a batch are sharded across ranks (one process per GPU).
+"""Data-parallel evaluation and training: the images of a batch are sharded across ranks (one process per GPU).
 
 The forward pass has no cross-image operation (no batch norm; GDN is per pixel), so there is no
 data-path collective.  The only exchange is the one the rate-distortion terms need
@@ -167,3 +167,83 @@ class ShardedEvaluator:
             return out, scalars_to_terms(scalars, per_image)
         per_image = gather_per_image(per_image, self.group)
         return out, rd_terms_on_device(per_image, x_local.shape[2] * x_local.shape[3], self.lambda_rd)
+
+
+# ---- data-parallel training step (BASELINE configs[3]; reference Trainer.py:79-86, single process there) -------------------
+
+def grad_buckets(params, bucket_bytes: int = 8 << 20):
+    """Parameters grouped, in REVERSE registration order (the order backward produces their gradients), into buckets of about
+    `bucket_bytes` of fp32 gradient: a handful of NCCL launches for the 7.3 M parameters instead of one per tensor."""
+    buckets, cur, size = [], [], 0
+    for p in reversed(list(params)):
+        if not p.requires_grad:
+            continue
+        cur.append(p)
+        size += p.numel() * 4
+        if size >= bucket_bytes:
+            buckets.append(cur)
+            cur, size = [], 0
+    if cur:
+        buckets.append(cur)
+    return buckets
+
+
+def allreduce_gradients(buckets, group=None, flats=None):
+    """Average .grad over the ranks: each bucket is flattened into one buffer, summed with one all-reduce (NCCL over NVLink on
+    the GPUs; gloo in the CPU tests), divided by the world size and scattered back.  The reference's loss is a mean over the batch
+    (RateDistortionLoss.py:19-27), so with equal shards the average of the per-rank gradients is the full-batch gradient.
+    Returns the async work handles' count (all are waited before returning)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    world = dist.get_world_size(group)
+    works = []
+    for bi, bucket in enumerate(buckets):
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
+        n = sum(g.numel() for g in grads)
+        flat = None if flats is None else flats[bi]
+        if flat is None or flat.numel() != n or flat.device != grads[0].device:
+            flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+            if flats is not None:
+                flats[bi] = flat
+        torch.cat([g.reshape(-1).float() for g in grads], out=flat)
+        works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, bucket))
+    for work, flat, bucket in works:
+        work.wait()
+        flat.div_(world)
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+    return len(works)
+
+
+class ShardedTrainer:
+    """One training step per call on this rank's shard: model(x) -> rd_loss -> backward -> gradient all-reduce -> Adam.
+
+    Mirrors the body of Trainer.train (Trainer.py:79-86) with the optimizer of Main.ipynb:133; every rank holds the full
+    model and must start from identical weights.  Noise is drawn per rank from the rank's own generator state (seed the
+    ranks differently) or injected through `noise`."""
+
+    def __init__(self, model, lambda_rd: float, lr: float = 1e-4, group=None, bucket_bytes: int = 8 << 20, optimizer=None):
+        from .training import Adam
+        self.model, self.lambda_rd, self.group = model, lambda_rd, group
+        self.optimizer = optimizer if optimizer is not None else Adam(model.parameters(), lr=lr)
+        self.buckets = grad_buckets(model.parameters(), bucket_bytes)
+        self._flats = [None] * len(self.buckets)
+        self.step_count = 0
+
+    def step(self, x_local: torch.Tensor, noise=None) -> dict:
+        from .RateDistortionLoss import rd_loss
+        self.optimizer.zero_grad()
+        out = self.model(x_local, training=True, noise=noise, lean=True)
+        rd = rd_loss(out, x_local, self.lambda_rd)
+        rd["loss"].backward()
+        allreduce_gradients(self.buckets, self.group, self._flats)
+        self.optimizer.step()
+        self.step_count += 1
+        return rd

@@ -15,13 +15,20 @@ RateDistortionLoss.py:5-49.  Here the whole model is ONE autograd node (``_Train
     optimizer                    nic_adam_step (``Adam`` below: torch.optim.Adam semantics, Main.ipynb:133)
 
 Differentiable outputs: ``x_hat``, ``logp_y``, ``logp_z`` (what rd_loss consumes).  The other dict entries are returned
-detached.  Arithmetic: fp32 on the CUDA cores (parity grade against the reference's own autograd, tests/test_gpu_train.py);
-the tensor-core arms serve the forward / evaluation path.
+detached.
+
+Arithmetic arms of the step (``NIC_TRAIN_PRECISION`` or ``model.train_precision``):
+  "bf16x3" (default when every conv has c_in % 64 == 0, i.e. M = 128): the convolutions of the forward pass AND the data-gradient
+           convolutions run on the tcgen05 tensor cores with hi/lo-split bf16 operands (fp32 grade, the arm the evaluation path
+           uses); activations and gradients stay fp32 NHWC between layers and are split on the fly (nic_to_pair).  Weight
+           gradients, GDN, LeakyReLU and the likelihood chain run in fp32 on the CUDA cores.
+  "fp32":  everything on the CUDA cores; gradients within 5e-6 of the reference's autograd (tests/test_gpu_train.py).
 """
 from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -31,6 +38,15 @@ from . import _lib, engine
 from ._lib import (ConvDesc, DT_F32, EPI_BIAS, LAYOUT_NCHW, LAYOUT_NHWC, PREC_FP32, Q_NOISE, Q_PASSTHRU, check, current_stream, ptr)
 
 PREC = "fp32"
+
+
+def train_precision(model) -> str:
+    arm = getattr(model, "train_precision", None) or os.environ.get("NIC_TRAIN_PRECISION", "auto")
+    if arm == "auto":
+        arm = "bf16x3" if model.M % 64 == 0 else "fp32"
+    if arm not in ("fp32", "bf16x3"):
+        raise ValueError(f"train precision must be fp32 or bf16x3, got {arm}")
+    return arm
 
 
 def _f32(shape, dev):
@@ -57,11 +73,93 @@ def conv_wgrad(conv: nn.Module, x: torch.Tensor, g: torch.Tensor, n: int, h: int
     return dw, db
 
 
+def to_pair(x: torch.Tensor) -> torch.Tensor:
+    """f32 [..., c] -> bf16 [..., 2c] = [hi | lo] (NIC_DT_BF16X2) through nic_to_pair."""
+    c = x.shape[-1]
+    out = torch.empty(tuple(x.shape[:-1]) + (2 * c,), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().nic_to_pair(ptr(x), ptr(out), x.numel() // c, c, current_stream()), "nic_to_pair")
+    return out
+
+
+def _train_op(conv: nn.Module, epilogue: int, mask_a: bool = False) -> engine.ConvOp:
+    """ConvOp of a layer WITHOUT its GDN (the training step keeps the pre-GDN tensor), cached on the module."""
+    cache = conv.__dict__.setdefault("_nic_train_ops", {})
+    key = (epilogue, mask_a)
+    if key not in cache:
+        cache[key] = engine.ConvOp(conv, epilogue, mask_a=mask_a)
+    return cache[key]
+
+
+def conv_forward(arm: str, conv: nn.Module, epilogue: int, x: torch.Tensor, n: int, h: int, w: int, in_layout: int = LAYOUT_NHWC,
+                 out_layout: int = LAYOUT_NHWC, out: Optional[torch.Tensor] = None, out_c_total: int = 0, out_c_offset: int = 0,
+                 mask_a: bool = False) -> torch.Tensor:
+    """One conv (+ bias / LeakyReLU) with f32 tensors at both ends; the contraction on the tensor cores in the bf16x3 arm."""
+    op = _train_op(conv, epilogue, mask_a)
+    if arm == "bf16x3" and in_layout == LAYOUT_NHWC and conv.in_channels % 64 == 0:
+        return op.run(to_pair(x), n, h, w, "bf16x3", out_layout=out_layout, out=out, out_c_total=out_c_total,
+                      out_c_offset=out_c_offset, out_dtype=torch.float32)
+    return op.run(x, n, h, w, PREC, in_layout=in_layout, out_layout=out_layout, out=out, out_c_total=out_c_total,
+                  out_c_offset=out_c_offset)
+
+
+def gdn_forward(gdn: nn.Module, u: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+    """GDN / IGDN of an NHWC f32 tensor (nic_gdn_fwd)."""
+    lib = _lib.load()
+    c = gdn.in_channels
+    gamma = _f32(c * c, u.device)
+    beta = _f32(c, u.device)
+    check(lib.nic_pack_gdn(c, float(gdn.beta_min), ptr(gdn.beta.detach().float().contiguous()), ptr(gdn.gamma.detach().float().contiguous()),
+                           ptr(beta), ptr(gamma), PREC_FP32, current_stream()), "nic_pack_gdn")
+    y = torch.empty_like(u)
+    check(lib.nic_gdn_fwd(ptr(u), n, c, h, w, LAYOUT_NHWC, int(gdn.inverse), ptr(gamma), ptr(beta), ptr(y), current_stream()), "nic_gdn_fwd")
+    return y
+
+
+def _adjoint(conv: nn.Module, weight: Optional[torch.Tensor], c_in: int, h_in: int, w_in: int):
+    """(module, ConvOp) of the adjoint conv of `conv` as a regular layer of the engine, cached on the module:
+       Conv2d stride 2      -> ConvTranspose2d over the SAME weight tensor (output_padding restores the input size)
+       ConvTranspose2d      -> Conv2d over the same weight tensor
+       Conv2d stride 1      -> Conv2d with the flipped, channel-transposed kernel (re-derived every call: the weights move)."""
+    transposed = isinstance(conv, nn.ConvTranspose2d)
+    k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+    cache = conv.__dict__.setdefault("_nic_adjoint", {})
+    key = (c_in, None if weight is None else weight.shape, h_in % s, w_in % s)
+    wsrc = (conv.weight if weight is None else weight).detach()
+    if key not in cache:
+        dev = wsrc.device
+        with torch.device(dev):
+            if transposed:
+                adj = nn.Conv2d(conv.out_channels, c_in, k, stride=s, padding=p)
+            elif s == 1:
+                adj = nn.Conv2d(conv.out_channels, c_in, k, stride=1, padding=k - 1 - p)
+            else:
+                h_out, w_out = engine.conv_out_hw(conv, h_in, w_in)
+                oph, opw = h_in - ((h_out - 1) * s - 2 * p + k), w_in - ((w_out - 1) * s - 2 * p + k)
+                if oph != opw:
+                    raise ValueError("conv_dgrad: height and width need the same output padding")
+                adj = nn.ConvTranspose2d(conv.out_channels, c_in, k, stride=s, padding=p, output_padding=oph)
+        adj.requires_grad_(False)
+        adj.bias.data.zero_()
+        cache[key] = (adj, engine.ConvOp(adj, EPI_BIAS))
+    adj, op = cache[key]
+    if not transposed and s == 1:
+        adj.weight = nn.Parameter(wsrc.flip(2, 3).transpose(0, 1).contiguous(), requires_grad=False)
+        op._cache.clear()          # a fresh tensor every call: its (address, version) key could repeat with different contents
+    elif adj.weight.data_ptr() != wsrc.data_ptr():
+        adj.weight = nn.Parameter(wsrc, requires_grad=False)              # shares storage and version counter with the layer's weight
+    return adj, op
+
+
 def conv_dgrad(conv: nn.Module, g: torch.Tensor, n: int, h_in: int, w_in: int, g_layout: int = LAYOUT_NHWC,
-               weight: Optional[torch.Tensor] = None, c_in: Optional[int] = None) -> torch.Tensor:
+               weight: Optional[torch.Tensor] = None, c_in: Optional[int] = None, arm: str = "fp32") -> torch.Tensor:
     """Gradient w.r.t. the layer input (NHWC f32): the adjoint conv through nic_conv_fwd.
     (h_in, w_in) = forward input size.  `weight` / `c_in` select a slice of the layer's input channels
     (weight = the matching slice of conv.weight, contiguous)."""
+    if arm == "bf16x3" and g_layout == LAYOUT_NHWC and conv.out_channels % 64 == 0:
+        cin = conv.in_channels if c_in is None else c_in
+        h_out, w_out = engine.conv_out_hw(conv, h_in, w_in)
+        adj, op = _adjoint(conv, weight, cin, h_in, w_in)
+        return op.run(to_pair(g), n, h_out, w_out, "bf16x3", out_dtype=torch.float32)
     lib = _lib.load()
     transposed = isinstance(conv, nn.ConvTranspose2d)
     k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
@@ -136,17 +234,19 @@ class _TrainForward(torch.autograd.Function):
         M, K = model.M, model.K
         hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
         S = {}
+        arm = train_precision(model)
         with torch.cuda.device(dev):
-            # g_a
+            # g_a: conv (+ bias) -> u, kept for the GDN backward; GDN -> the next layer's input, kept for its weight gradient
             a, h, w, layout = x, H, W, LAYOUT_NCHW
             enc = model.encoder.ops
             S["enc_in"], S["enc_u"] = [], []
             for op in enc:
                 S["enc_in"].append((a, h, w, layout))
-                keep = []
-                a = op.run(a, B, h, w, PREC, in_layout=layout, out_layout=LAYOUT_NHWC, keep_ws=keep)
-                S["enc_u"].append(keep[0].view(torch.float32) if op.gdn is not None else None)
+                a = conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, in_layout=layout)
                 h, w = engine.conv_out_hw(op.conv, h, w)
+                S["enc_u"].append(a if op.gdn is not None else None)
+                if op.gdn is not None:
+                    a = gdn_forward(op.gdn, a, B, h, w)
                 layout = LAYOUT_NHWC
             y_nhwc = a
             y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, Q_NOISE, noise_y, torch.float32)
@@ -155,7 +255,7 @@ class _TrainForward(torch.autograd.Function):
             S["ha_in"] = []
             for op in model.hyper_encoder.ops:
                 S["ha_in"].append((a, h, w))
-                a = op.run(a, B, h, w, PREC)
+                a = conv_forward(arm, op.conv, op.epilogue, a, B, h, w)
                 h, w = engine.conv_out_hw(op.conv, h, w)
             z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, Q_NOISE, noise_z, torch.float32)
             # h_s -> psi, context -> phi, both windows of `combined`
@@ -166,16 +266,17 @@ class _TrainForward(torch.autograd.Function):
             for i, op in enumerate(hs):
                 S["hs_in"].append((a, h, w))
                 if i == len(hs) - 1:
-                    op.run(a, B, h, w, PREC, out=combined, out_c_total=4 * M, out_c_offset=2 * M)
+                    conv_forward(arm, op.conv, op.epilogue, a, B, h, w, out=combined, out_c_total=4 * M, out_c_offset=2 * M)
                 else:
-                    a = op.run(a, B, h, w, PREC)
+                    a = conv_forward(arm, op.conv, op.epilogue, a, B, h, w)
                 h, w = engine.conv_out_hw(op.conv, h, w)
-            model.context_model.masked.apply_mask_()
-            model.context_model.masked._op.run(y_in_nhwc, B, hy, wy, PREC, out=combined, out_c_total=4 * M, out_c_offset=0)
+            masked = model.context_model.masked
+            masked.apply_mask_()
+            conv_forward(arm, masked, EPI_BIAS, y_in_nhwc, B, hy, wy, out=combined, out_c_total=4 * M, out_c_offset=0, mask_a=True)
             ep = model.entropy_parameters.ops
-            e1 = ep[0].run(combined, B, hy, wy, PREC)
-            e2 = ep[1].run(e1, B, hy, wy, PREC)
-            raw = ep[2].run(e2, B, hy, wy, PREC, out_layout=LAYOUT_NCHW, out_dtype=torch.float32)
+            e1 = conv_forward(arm, ep[0].conv, ep[0].epilogue, combined, B, hy, wy)
+            e2 = conv_forward(arm, ep[1].conv, ep[1].epilogue, e1, B, hy, wy)
+            raw = conv_forward(arm, ep[2].conv, ep[2].epilogue, e2, B, hy, wy, out_layout=LAYOUT_NCHW)
             from .EntropyModels import gm_likelihood
             ly = gm_likelihood(y_in, raw, M, K, Q_PASSTHRU, full=not lean, want_y_in=False)
             _, p_z, logp_z, parts_z = model.factorized_entropy_model.likelihood(z_in, Q_PASSTHRU)
@@ -186,11 +287,13 @@ class _TrainForward(torch.autograd.Function):
             for i, op in enumerate(dec):
                 last = i == len(dec) - 1
                 S["dec_in"].append((a, h, w))
-                keep = []
-                a = op.run(a, B, h, w, PREC, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC, keep_ws=keep)
-                S["dec_u"].append(keep[0].view(torch.float32) if op.gdn is not None else None)
+                a = conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC)
                 h, w = engine.conv_out_hw(op.conv, h, w)
+                S["dec_u"].append(a if op.gdn is not None else None)
+                if op.gdn is not None:
+                    a = gdn_forward(op.gdn, a, B, h, w)
             x_hat = a
+        S["arm"] = arm
         S.update(combined=combined, e1=e1, e2=e2, raw=raw, y_in=y_in, y_in_nhwc=y_in_nhwc, z_in=z_in, z_in_nhwc=z_in_nhwc,
                  fparams=model.factorized_entropy_model.packed(), shape=(B, H, W))
         ctx.model, ctx.S = model, S
@@ -209,6 +312,7 @@ class _TrainForward(torch.autograd.Function):
         M, K = model.M, model.K
         hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
         dev = S["raw"].device
+        arm = S["arm"]
         grads: Dict[int, torch.Tensor] = {}
 
         def put(param, g):
@@ -229,7 +333,7 @@ class _TrainForward(torch.autograd.Function):
                         put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
                     dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, g_layout)
                     put(op.conv.weight, dw); put(op.conv.bias, db)
-                    g = conv_dgrad(op.conv, g, B, h, w, g_layout)
+                    g = conv_dgrad(op.conv, g, B, h, w, g_layout, arm=arm)
                     g_layout = LAYOUT_NHWC
                 d_yin = g
             # ---- p_y: likelihood, entropy parameters, context model, h_s --------------------------------------------
@@ -247,14 +351,14 @@ class _TrainForward(torch.autograd.Function):
                     dw, db = conv_wgrad(op.conv, a, g, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC)
                     put(op.conv.weight, dw); put(op.conv.bias, db)
                     if i > 0:
-                        g = lrelu_bwd_(conv_dgrad(op.conv, g, B, hy, wy), a)
+                        g = lrelu_bwd_(conv_dgrad(op.conv, g, B, hy, wy, arm=arm), a)
                 w0 = ep[0].conv.weight.detach()
-                d_phi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, :2 * M].contiguous(), c_in=2 * M)
-                d_psi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, 2 * M:].contiguous(), c_in=2 * M)
+                d_phi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, :2 * M].contiguous(), c_in=2 * M, arm=arm)
+                d_psi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, 2 * M:].contiguous(), c_in=2 * M, arm=arm)
                 masked = model.context_model.masked
                 dw, db = conv_wgrad(masked, S["y_in_nhwc"], d_phi, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC)
                 put(masked.weight, dw); put(masked.bias, db)
-                d_yin = add_(d_yin, conv_dgrad(masked, d_phi, B, hy, wy))
+                d_yin = add_(d_yin, conv_dgrad(masked, d_phi, B, hy, wy, arm=arm))
                 g = d_psi
                 hs = model.hyper_decoder.ops
                 for i in range(len(hs) - 1, -1, -1):
@@ -262,7 +366,7 @@ class _TrainForward(torch.autograd.Function):
                     a, h, w = S["hs_in"][i]
                     dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC)
                     put(op.conv.weight, dw); put(op.conv.bias, db)
-                    g = conv_dgrad(op.conv, g, B, h, w)
+                    g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
                     if i > 0:
                         g = lrelu_bwd_(g, a)                         # a = LeakyReLU output of layer i - 1
                 d_zin = g
@@ -288,7 +392,7 @@ class _TrainForward(torch.autograd.Function):
                     a, h, w = S["ha_in"][i]
                     dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC)
                     put(op.conv.weight, dw); put(op.conv.bias, db)
-                    g = conv_dgrad(op.conv, g, B, h, w)
+                    g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
                     if i > 0:
                         g = lrelu_bwd_(g, a)
                 dy = g if dy is None else add_(dy, g)
@@ -306,7 +410,7 @@ class _TrainForward(torch.autograd.Function):
                     dw, db = conv_wgrad(op.conv, a, g, B, h, w, layout, LAYOUT_NHWC)
                     put(op.conv.weight, dw); put(op.conv.bias, db)
                     if i > 0:
-                        g = conv_dgrad(op.conv, g, B, h, w)
+                        g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
         ctx.S = None
         params = [p for _, p in model.named_parameters()]
         return (None, None, None, None, None, *[grads.get(id(p)) for p in params])

@@ -20,6 +20,18 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 GRAD_RTOL = 2e-4
+ARMS = ("fp32", "bf16x3")       # arithmetic of the step's convolutions (training.py): CUDA cores / tensor cores with hi/lo-split operands
+
+
+def grad_tol(arm, key):
+    """fp32 arm: 2e-4 of the tensor's norm everywhere (measured: <= 5e-6).  bf16x3 arm: the split-operand convs carry ~1e-5 per
+    layer (5e-4 allowed), and their pre-activation error (~5e-7 absolute) exceeds the 1e-6 kink margin of the cases now and then:
+    one LeakyReLU element taking the other slope moves every gradient UPSTREAM of that layer by up to ~1e-2 of its norm
+    (oracle/backward.py: kink_margin), so the tensors behind a LeakyReLU get 3e-2 in that arm."""
+    if arm == "fp32":
+        return GRAD_RTOL
+    exposed = key.startswith(("hyper_encoder.", "hyper_decoder.", "context_model.", "entropy_parameters.net.0", "entropy_parameters.net.2"))
+    return 3e-2 if exposed else 5e-4
 
 
 def rel_err(got, ref):
@@ -27,20 +39,22 @@ def rel_err(got, ref):
     return float((got.double().cpu() - ref).norm() / max(float(ref.norm()), 1e-30))
 
 
+@pytest.mark.parametrize("arm", ARMS)
 @pytest.mark.parametrize("case", H.train_cases())
-def test_training_step_matches_reference_golden(case):
+def test_training_step_matches_reference_golden(case, arm):
     """The committed vectors of the REAL reference's backward + Adam step (sampled entries + norms)."""
     from neural_image_compression_b200.RateDistortionLoss import rd_loss
     from neural_image_compression_b200.training import Adam
     g = H.load_golden(case)
     M, K, init = int(g["M"]), int(g["K"]), str(g["init"])
     model = H.seeded_model(M, K, init, precision="fp32").cuda()
+    model.train_precision = arm
     x, nz, ny = (torch.from_numpy(g[k]).cuda() for k in ("x", "noise_z", "noise_y"))
     opt = Adam(model.parameters(), lr=1e-4)
     opt.zero_grad()
     out = model(x, noise=(nz, ny))                      # training=True is the default, as in Trainer.py:82
     rd = rd_loss(out, x, 0.005)
-    assert abs(float(rd["loss"]) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert abs(float(rd["loss"].detach()) - float(g["loss"])) <= (1e-5 if arm == "fp32" else 5e-5) * abs(float(g["loss"]))
     rd["loss"].backward()
     grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
     before = {k: p.detach().clone() for k, p in model.named_parameters()}
@@ -53,9 +67,10 @@ def test_training_step_matches_reference_golden(case):
         gr = grads[k]
         idx = H.sample_index(gr.numel())
         gn = float(g["gnorm_" + k])
-        assert abs(float(gr.double().norm()) - gn) <= GRAD_RTOL * gn + 1e-12, (k, float(gr.double().norm()), gn)
-        g_atol = 10 * GRAD_RTOL * gn / gr.numel() ** 0.5
-        np.testing.assert_allclose(gr.reshape(-1)[idx].cpu().numpy(), g["gsamp_" + k], rtol=1e-3, atol=g_atol, err_msg=k)
+        tol = grad_tol(arm, k)
+        assert abs(float(gr.double().norm()) - gn) <= tol * gn + 1e-12, (k, float(gr.double().norm()), gn)
+        g_atol = 10 * tol * gn / gr.numel() ** 0.5
+        np.testing.assert_allclose(gr.reshape(-1)[idx].cpu().numpy(), g["gsamp_" + k], rtol=5 * tol, atol=g_atol, err_msg=k)
         np.testing.assert_allclose(p.detach().cpu().numpy(), want[k].numpy(), rtol=1e-6, atol=1e-7, err_msg=k)
         # against the reference's updated parameters: the first Adam step is lr * g / (|g| + eps), whose sensitivity to an
         # absolute gradient error dg is lr * eps * dg / (|g| + eps)^2 - large only where the gradient itself is ~eps = 1e-8
@@ -66,8 +81,9 @@ def test_training_step_matches_reference_golden(case):
         assert not bad.any(), (k, err[bad], p_atol[bad], gs[bad], g_atol)
 
 
+@pytest.mark.parametrize("arm", ARMS)
 @pytest.mark.parametrize("K,shape", [(3, (2, 3, 128, 192)), (1, (3, 3, 64, 64))])
-def test_every_gradient_tensor_against_the_oracle(K, shape):
+def test_every_gradient_tensor_against_the_oracle(K, shape, arm):
     """All 59 gradient tensors in full against the oracle's autograd on the same weights, input and noise."""
     from neural_image_compression_b200.RateDistortionLoss import rd_loss
     model = H.seeded_model(128, K, "calib", precision="fp32")
@@ -79,26 +95,28 @@ def test_every_gradient_tensor_against_the_oracle(K, shape):
     _, nz, ny = OB.noise_with_margin(sd, x, 128, K, 21)
     ref_rd, ref_g, ref_out = OB.loss_and_grads(sd, x, 128, K, nz, ny, 0.005)
     model = model.cuda()
+    model.train_precision = arm
     out = model(x.cuda(), training=True, noise=(nz.cuda(), ny.cuda()))
     rd = rd_loss(out, x.cuda(), 0.005)
-    assert abs(float(rd["loss"]) - ref_rd["loss"]) <= 1e-5 * abs(ref_rd["loss"])
-    assert rel_err(out["x_hat"].detach(), ref_out["x_hat"]) < 1e-5
+    assert abs(float(rd["loss"].detach()) - ref_rd["loss"]) <= (1e-5 if arm == "fp32" else 5e-5) * abs(ref_rd["loss"])
+    assert rel_err(out["x_hat"].detach(), ref_out["x_hat"]) < (1e-5 if arm == "fp32" else 1e-4)
     rd["loss"].backward()
     torch.cuda.synchronize()
     worst = {}
     for k, p in model.named_parameters():
         assert p.grad is not None, k
         worst[k] = rel_err(p.grad, ref_g[k])
-    bad = {k: v for k, v in worst.items() if v > GRAD_RTOL}
-    print("worst gradient errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    bad = {k: v for k, v in worst.items() if v > grad_tol(arm, k)}
+    print(arm, "worst gradient errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
     assert not bad, bad
     # the dict entries the reference returns are all there, the non-differentiable ones detached
     assert out["logp_y"].requires_grad and out["x_hat"].requires_grad and not out["y_in"].requires_grad
     assert set(out) >= {"x_hat", "y", "y_in", "z", "z_in", "p_z", "logp_z", "p_y", "logp_y", "training"}
 
 
-def test_gradient_accumulates_and_tensor_core_model_trains_on_the_fp32_arm():
-    """Two backward passes accumulate into .grad like torch; a bf16x3 model's training call takes the same differentiable path."""
+def test_gradient_accumulates_and_is_deterministic():
+    """Two backward passes accumulate into .grad like torch; a bf16x3 model's training call takes the differentiable path
+    (default step arm for M = 128: tensor-core convs)."""
     from neural_image_compression_b200.RateDistortionLoss import rd_loss
     model = H.seeded_model(128, 3, "calib", precision="bf16x3").cuda()
     x = H.seeded_input((1, 3, 64, 64)).cuda()
