@@ -280,6 +280,23 @@ int nic_gdn_bwd(const float* u, const float* g, int32_t n, int32_t c, int32_t h,
                 void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same GDN forward / backward in pieces, for callers that run the two channel-mixing contractions (norm = beta + gamma . u^2
+ * and r = gamma^T . t) elsewhere - the training step runs them as 1x1 convs on the tensor cores (nic_conv_fwd, NIC_PREC_BF16X3):
+ *   nic_gdn_reparam     beta_eff [c], gamma_eff [c, c] (= the [c_out, c_in] weight of the norm conv), gamma_eff_t (its transpose)
+ *   nic_gdn_apply       out = u * rsqrt(norm)   (inverse: u * sqrt(norm))
+ *   nic_gdn_bwd_prep    t = d out / d norm * g,  du = g * rsqrt(norm) (inverse: g * sqrt(norm))
+ *   nic_gdn_bwd_finish  du += 2 u r;  dgamma_raw, dbeta_raw from (u, t) through the LowerBound rule
+ */
+int nic_gdn_reparam(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, float* beta_eff, float* gamma_eff,
+                    float* gamma_eff_t, void* stream);
+int nic_gdn_apply(const float* u, const float* norm, int64_t n, int32_t inverse, float* out, void* stream);
+int nic_gdn_bwd_prep(const float* u, const float* g, const float* norm, int64_t n, int32_t inverse, float* t, float* du, void* stream);
+size_t nic_gdn_bwd_finish_workspace_bytes(int64_t pixels, int32_t c);
+int nic_gdn_bwd_finish(const float* u, const float* t, const float* r, int64_t pixels, int32_t c, float beta_min,
+                       const float* beta_raw, const float* gamma_raw, float* du, float* dbeta_raw, float* dgamma_raw,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Backward of nic_gm_likelihood_fwd w.r.t. y_in and the raw entropy-parameter tensor (softmax / softplus / erf-form CDF
  * difference / clamp_min(1e-9) / log chain).  g_logp [b, m, hw] = upstream gradient of logp, or NULL: every element's
  * upstream is g_scalar (rd_loss: -1 / (ln2 * num_pixels * B)).  dy_in [b, m, hw], draw like raw.
@@ -303,7 +320,7 @@ int nic_add_inplace(float* dst, const float* src, int64_t n, void* stream);
 int nic_layout_convert(const float* src, float* dst, int32_t n, int32_t c, int32_t hw, int32_t to_nhwc, int32_t accumulate, void* stream);
 
 /* f32 [rows, c] -> NIC_DT_BF16X2 [rows, 2c] = [hi | lo]: hands fp32 activations / gradients to the bf16x3 convs (c % 4 == 0) */
-int nic_to_pair(const float* src, void* dst, int64_t rows, int32_t c, void* stream);
+int nic_to_pair(const float* src, void* dst, int64_t rows, int32_t c, int32_t square /* 1: split src^2 */, void* stream);
 
 /* One torch.optim.Adam update (no weight decay / amsgrad; Main.ipynb:133) of a flat parameter; step = t >= 1 after the increment */
 int nic_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

@@ -247,6 +247,13 @@ __global__ void gdn_bwd_prep_kernel(const float* __restrict__ g, const float* __
     else { t[i] = -0.5f * gv * uv * rs / nv; du[i] = gv * rs; }
   }
 }
+// out = u * rsqrt(norm)  (inverse: u * sqrt(norm)) - the GDN once its norm = beta + gamma . u^2 is known
+__global__ void gdn_apply_kernel(const float* __restrict__ u, const float* __restrict__ nrm, int inverse, float* __restrict__ out, long n) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float nv = nrm[i];
+    out[i] = inverse ? u[i] * sqrtf(nv) : u[i] * (1.0f / sqrtf(nv));
+  }
+}
 __global__ void gdn_bwd_finish_kernel(const float* __restrict__ u, const float* __restrict__ r, float* __restrict__ du, long n) {
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
     du[i] = fmaf(2.0f * u[i], r[i], du[i]);
@@ -318,13 +325,14 @@ layout_convert_kernel(const float* __restrict__ src, float* __restrict__ dst, in
 
 // f32 [rows][c] -> bf16 pairs [rows][2c] = [hi(c) | lo(c)] (NIC_DT_BF16X2): feeds fp32 activations / gradients to the bf16x3 convs
 __global__ void __launch_bounds__(256)
-to_pair_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long rows, int c) {
+to_pair_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long rows, int c, int square) {
   const int c4 = c >> 2;
   const long total = rows * c4;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const long r = i / c4;
     const int q = static_cast<int>(i - r * c4) * 4;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * c + q));
+    float4 v = __ldg(reinterpret_cast<const float4*>(src + r * c + q));
+    if (square) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
     const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
     const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
     const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
@@ -576,6 +584,72 @@ int nic_gdn_bwd(const float* u, const float* g, int32_t n, int32_t c, int32_t h,
   return check_launch("gdn_reparam_bwd_kernel");
 }
 
+/* ---- the same backward in three calls, for callers that run the two channel-mixing contractions elsewhere (tensor cores) ---- */
+
+int nic_gdn_reparam(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, float* beta_eff, float* gamma_eff,
+                    float* gamma_eff_t, void* stream) {
+  if (int rc = nic_check_device()) return rc;
+  if (c < 1 || !beta_raw || !gamma_raw || !beta_eff || !gamma_eff || !gamma_eff_t) return fail(NIC_E_BADSHAPE, "gdn_reparam: bad arguments");
+  const float pedestal = static_cast<float>(3.814697265625e-06 * 3.814697265625e-06);
+  const float beta_bound = static_cast<float>(sqrt(static_cast<double>(beta_min) + static_cast<double>(pedestal)));
+  const float gamma_bound = static_cast<float>(sqrt(static_cast<double>(pedestal)));
+  gdn_reparam_kernel<<<(c * c + 255) / 256, 256, 0, as_stream(stream)>>>(c, beta_bound, gamma_bound, pedestal, beta_raw, gamma_raw, beta_eff, gamma_eff, gamma_eff_t);
+  return check_launch("gdn_reparam_kernel");
+}
+
+int nic_gdn_apply(const float* u, const float* norm, int64_t n, int32_t inverse, float* out, void* stream) {
+  if (int rc = nic_check_device()) return rc;
+  if (n < 0 || (n > 0 && (!u || !norm || !out))) return fail(NIC_E_BADSHAPE, "gdn_apply: bad arguments");
+  if (n == 0) return NIC_OK;
+  gdn_apply_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(u, norm, inverse, out, n);
+  return check_launch("gdn_apply_kernel");
+}
+
+int nic_gdn_bwd_prep(const float* u, const float* g, const float* norm, int64_t n, int32_t inverse, float* t, float* du, void* stream) {
+  if (int rc = nic_check_device()) return rc;
+  if (n < 0 || (n > 0 && (!u || !g || !norm || !t || !du))) return fail(NIC_E_BADSHAPE, "gdn_bwd_prep: bad arguments");
+  if (n == 0) return NIC_OK;
+  gdn_bwd_prep_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(g, u, norm, inverse, t, du, n);
+  return check_launch("gdn_bwd_prep_kernel");
+}
+
+size_t nic_gdn_bwd_finish_workspace_bytes(int64_t pixels, int32_t c) {
+  if (pixels < 0 || c < 1) return 0;
+  const WgradPlan wp = plan_wgrad(1, c, c, pixels, false);
+  return 2 * align256(static_cast<size_t>(c) * c * sizeof(float)) + 2 * align256(c * sizeof(float)) +
+         align256(static_cast<size_t>(wp.splits) * c * c * sizeof(float)) + colsum_part_bytes(1, c) + 256;
+}
+
+int nic_gdn_bwd_finish(const float* u, const float* t, const float* r, int64_t pixels, int32_t c, float beta_min,
+                       const float* beta_raw, const float* gamma_raw, float* du, float* dbeta_raw, float* dgamma_raw,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = nic_check_device()) return rc;
+  if (pixels < 1 || pixels > 0x7fffffffL || c < 4 || c % 4) return fail(NIC_E_BADSHAPE, "gdn_bwd_finish: pixels=%lld c=%d", static_cast<long long>(pixels), c);
+  if (!u || !t || !r || !beta_raw || !gamma_raw || !du || !dbeta_raw || !dgamma_raw) return fail(NIC_E_BADSHAPE, "gdn_bwd_finish: null pointer");
+  const size_t need = nic_gdn_bwd_finish_workspace_bytes(pixels, c);
+  if (!workspace || workspace_bytes < need) return fail(NIC_E_WORKSPACE, "gdn_bwd_finish: workspace %zu < %zu bytes", workspace_bytes, need);
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(NIC_E_BADALIGN, "gdn_bwd_finish: workspace must be 256-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const size_t cc = align256(static_cast<size_t>(c) * c * sizeof(float)), c1 = align256(c * sizeof(float));
+  char* ws = static_cast<char*>(workspace);
+  float* dgamma_eff = reinterpret_cast<float*>(ws); ws += 2 * cc;
+  float* dbeta_eff = reinterpret_cast<float*>(ws); ws += 2 * c1;
+  const WgradPlan wp = plan_wgrad(1, c, c, pixels, false);
+  float* wpart = reinterpret_cast<float*>(ws); ws += align256(static_cast<size_t>(wp.splits) * c * c * sizeof(float));
+  float* cpart = reinterpret_cast<float*>(ws);
+  const long elems = pixels * c;
+  gdn_bwd_finish_kernel<<<ew_blocks(elems), 256, 0, st>>>(u, r, du, elems);
+  if (int rc = check_launch("gdn_bwd_finish_kernel")) return rc;
+  WgradShape s{}; s.cb = c; s.cs = c; s.hb = s.hs = 1; s.wb = s.ws = static_cast<int>(pixels); s.big_layout = NIC_LAYOUT_NHWC; s.big_is_input = true;
+  if (int rc = run_wgrad(u, t, 1, s, 1, 0, 1, 1, 1, dgamma_eff, wpart, st)) return rc;
+  if (int rc = run_colsum_nhwc(t, pixels, c, dbeta_eff, cpart, st)) return rc;
+  const float pedestal = static_cast<float>(3.814697265625e-06 * 3.814697265625e-06);
+  const float beta_bound = static_cast<float>(sqrt(static_cast<double>(beta_min) + static_cast<double>(pedestal)));
+  const float gamma_bound = static_cast<float>(sqrt(static_cast<double>(pedestal)));
+  gdn_reparam_bwd_kernel<<<(c * c + 255) / 256, 256, 0, st>>>(c, beta_bound, gamma_bound, beta_raw, gamma_raw, dbeta_eff, dgamma_eff, dbeta_raw, dgamma_raw);
+  return check_launch("gdn_reparam_bwd_kernel");
+}
+
 int nic_sse_bwd(const float* x_hat, const float* x, int64_t n, float coef, float* g_x_hat, void* stream) {
   if (int rc = nic_check_device()) return rc;
   if (n < 0 || (n > 0 && (!x_hat || !x || !g_x_hat))) return fail(NIC_E_BADSHAPE, "sse_bwd: bad arguments");
@@ -601,13 +675,13 @@ int nic_layout_convert(const float* src, float* dst, int32_t n, int32_t c, int32
   return check_launch("layout_convert_kernel");
 }
 
-int nic_to_pair(const float* src, void* dst, int64_t rows, int32_t c, void* stream) {
+int nic_to_pair(const float* src, void* dst, int64_t rows, int32_t c, int32_t square, void* stream) {
   if (int rc = nic_check_device()) return rc;
   if (rows < 0 || c < 4 || c % 4) return fail(NIC_E_BADSHAPE, "to_pair: rows=%lld c=%d (c %% 4 == 0)", static_cast<long long>(rows), c);
   if (rows == 0) return NIC_OK;
   if (!src || !dst) return fail(NIC_E_BADSHAPE, "to_pair: null pointer");
   if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 7)) return fail(NIC_E_BADALIGN, "to_pair: alignment");
-  to_pair_kernel<<<ew_blocks(rows * (c / 4)), 256, 0, as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), rows, c);
+  to_pair_kernel<<<ew_blocks(rows * (c / 4)), 256, 0, as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), rows, c, square);
   return check_launch("to_pair_kernel");
 }
 

@@ -73,11 +73,11 @@ def conv_wgrad(conv: nn.Module, x: torch.Tensor, g: torch.Tensor, n: int, h: int
     return dw, db
 
 
-def to_pair(x: torch.Tensor) -> torch.Tensor:
-    """f32 [..., c] -> bf16 [..., 2c] = [hi | lo] (NIC_DT_BF16X2) through nic_to_pair."""
+def to_pair(x: torch.Tensor, square: bool = False) -> torch.Tensor:
+    """f32 [..., c] -> bf16 [..., 2c] = [hi | lo] (NIC_DT_BF16X2) of x (or of x^2) through nic_to_pair."""
     c = x.shape[-1]
     out = torch.empty(tuple(x.shape[:-1]) + (2 * c,), dtype=torch.bfloat16, device=x.device)
-    check(_lib.load().nic_to_pair(ptr(x), ptr(out), x.numel() // c, c, current_stream()), "nic_to_pair")
+    check(_lib.load().nic_to_pair(ptr(x), ptr(out), x.numel() // c, c, int(square), current_stream()), "nic_to_pair")
     return out
 
 
@@ -102,17 +102,52 @@ def conv_forward(arm: str, conv: nn.Module, epilogue: int, x: torch.Tensor, n: i
                   out_c_offset=out_c_offset)
 
 
-def gdn_forward(gdn: nn.Module, u: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
-    """GDN / IGDN of an NHWC f32 tensor (nic_gdn_fwd)."""
+def _gdn_tc(gdn: nn.Module):
+    """The two channel-mixing contractions of a GDN layer as 1x1 convs of the tensor-core engine: norm = beta + gamma . u^2
+    (weight gamma_eff [i, j], bias beta_eff) and r = gamma^T . t (weight gamma_eff^T).  The effective parameters live in
+    persistent buffers refreshed by nic_gdn_reparam whenever beta / gamma changed."""
+    st = gdn.__dict__.get("_nic_tc")
+    c, dev = gdn.in_channels, gdn.gamma.device
+    if st is None or st["dev"] != dev:
+        beta_eff, gamma_eff, gamma_t = _f32(c, dev), _f32((c, c, 1, 1), dev), _f32((c, c, 1, 1), dev)
+        with torch.device(dev):
+            norm_conv, rt_conv = nn.Conv2d(c, c, 1), nn.Conv2d(c, c, 1)
+        for m in (norm_conv, rt_conv):
+            m.requires_grad_(False)
+        norm_conv.weight, norm_conv.bias = nn.Parameter(gamma_eff, requires_grad=False), nn.Parameter(beta_eff, requires_grad=False)
+        rt_conv.weight = nn.Parameter(gamma_t, requires_grad=False)
+        rt_conv.bias.data.zero_()
+        st = {"dev": dev, "beta_eff": beta_eff, "gamma_eff": gamma_eff, "gamma_t": gamma_t, "key": None,
+              "norm_op": engine.ConvOp(norm_conv, EPI_BIAS), "rt_op": engine.ConvOp(rt_conv, EPI_BIAS)}
+        gdn.__dict__["_nic_tc"] = st
+    key = (gdn.beta.data_ptr(), gdn.beta._version, gdn.gamma.data_ptr(), gdn.gamma._version)
+    if st["key"] != key:
+        check(_lib.load().nic_gdn_reparam(c, float(gdn.beta_min), ptr(gdn.beta.detach().float().contiguous()),
+                                          ptr(gdn.gamma.detach().float().contiguous()), ptr(st["beta_eff"]), ptr(st["gamma_eff"]),
+                                          ptr(st["gamma_t"]), current_stream()), "nic_gdn_reparam")
+        st["norm_op"]._cache.clear(); st["rt_op"]._cache.clear()       # the buffers changed behind torch's back
+        st["key"] = key
+    return st
+
+
+def gdn_forward(arm: str, gdn: nn.Module, u: torch.Tensor, n: int, h: int, w: int):
+    """GDN / IGDN of an NHWC f32 tensor -> (out, norm | None).  bf16x3 arm: the norm is a tensor-core 1x1 conv over the split
+    squares and is kept for the backward; fp32 arm: nic_gdn_fwd (the backward recomputes the norm)."""
     lib = _lib.load()
     c = gdn.in_channels
+    if arm == "bf16x3" and c % 64 == 0:
+        st = _gdn_tc(gdn)
+        norm = st["norm_op"].run(to_pair(u, square=True), n, h, w, "bf16x3", out_dtype=torch.float32)
+        out = torch.empty_like(u)
+        check(lib.nic_gdn_apply(ptr(u), ptr(norm), u.numel(), int(gdn.inverse), ptr(out), current_stream()), "nic_gdn_apply")
+        return out, norm
     gamma = _f32(c * c, u.device)
     beta = _f32(c, u.device)
     check(lib.nic_pack_gdn(c, float(gdn.beta_min), ptr(gdn.beta.detach().float().contiguous()), ptr(gdn.gamma.detach().float().contiguous()),
                            ptr(beta), ptr(gamma), PREC_FP32, current_stream()), "nic_pack_gdn")
     y = torch.empty_like(u)
     check(lib.nic_gdn_fwd(ptr(u), n, c, h, w, LAYOUT_NHWC, int(gdn.inverse), ptr(gamma), ptr(beta), ptr(y), current_stream()), "nic_gdn_fwd")
-    return y
+    return y, None
 
 
 def _adjoint(conv: nn.Module, weight: Optional[torch.Tensor], c_in: int, h_in: int, w_in: int):
@@ -190,13 +225,25 @@ def lrelu_bwd_(g: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return g
 
 
-def gdn_bwd(gdn: nn.Module, u: torch.Tensor, g: torch.Tensor, n: int, h: int, w: int):
-    """(du, dbeta, dgamma): u = the conv output before the GDN (NHWC f32), g = gradient w.r.t. the GDN output."""
+def gdn_bwd(gdn: nn.Module, u: torch.Tensor, g: torch.Tensor, n: int, h: int, w: int, norm: Optional[torch.Tensor] = None):
+    """(du, dbeta, dgamma): u = the conv output before the GDN (NHWC f32), g = gradient w.r.t. the GDN output.
+    With the forward's `norm` (bf16x3 arm) the gamma^T . t contraction runs on the tensor cores."""
     lib = _lib.load()
     c = gdn.in_channels
     du = torch.empty_like(u)
     dbeta = torch.empty_like(gdn.beta, dtype=torch.float32)
     dgamma = torch.empty_like(gdn.gamma, dtype=torch.float32)
+    if norm is not None:
+        st = _gdn_tc(gdn)
+        t = torch.empty_like(u)
+        check(lib.nic_gdn_bwd_prep(ptr(u), ptr(g), ptr(norm), u.numel(), int(gdn.inverse), ptr(t), ptr(du), current_stream()), "nic_gdn_bwd_prep")
+        r = st["rt_op"].run(to_pair(t), n, h, w, "bf16x3", out_dtype=torch.float32)
+        pixels = n * h * w
+        ws = _ws(lib.nic_gdn_bwd_finish_workspace_bytes(pixels, c), u.device)
+        check(lib.nic_gdn_bwd_finish(ptr(u), ptr(t), ptr(r), pixels, c, float(gdn.beta_min), ptr(gdn.beta.detach().float().contiguous()),
+                                     ptr(gdn.gamma.detach().float().contiguous()), ptr(du), ptr(dbeta), ptr(dgamma), ptr(ws), ws.numel(),
+                                     current_stream()), "nic_gdn_bwd_finish")
+        return du, dbeta, dgamma
     ws = _ws(lib.nic_gdn_bwd_workspace_bytes(n, c, h, w), u.device)
     check(lib.nic_gdn_bwd(ptr(u), ptr(g), n, c, h, w, int(gdn.inverse), float(gdn.beta_min), ptr(gdn.beta.detach().float().contiguous()),
                           ptr(gdn.gamma.detach().float().contiguous()), ptr(du), ptr(dbeta), ptr(dgamma), ptr(ws), ws.numel(),
@@ -244,9 +291,12 @@ class _TrainForward(torch.autograd.Function):
                 S["enc_in"].append((a, h, w, layout))
                 a = conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, in_layout=layout)
                 h, w = engine.conv_out_hw(op.conv, h, w)
-                S["enc_u"].append(a if op.gdn is not None else None)
                 if op.gdn is not None:
-                    a = gdn_forward(op.gdn, a, B, h, w)
+                    u = a
+                    a, nrm = gdn_forward(arm, op.gdn, u, B, h, w)
+                    S["enc_u"].append((u, nrm))
+                else:
+                    S["enc_u"].append(None)
                 layout = LAYOUT_NHWC
             y_nhwc = a
             y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, Q_NOISE, noise_y, torch.float32)
@@ -289,9 +339,12 @@ class _TrainForward(torch.autograd.Function):
                 S["dec_in"].append((a, h, w))
                 a = conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC)
                 h, w = engine.conv_out_hw(op.conv, h, w)
-                S["dec_u"].append(a if op.gdn is not None else None)
                 if op.gdn is not None:
-                    a = gdn_forward(op.gdn, a, B, h, w)
+                    u = a
+                    a, nrm = gdn_forward(arm, op.gdn, u, B, h, w)
+                    S["dec_u"].append((u, nrm))
+                else:
+                    S["dec_u"].append(None)
             x_hat = a
         S["arm"] = arm
         S.update(combined=combined, e1=e1, e2=e2, raw=raw, y_in=y_in, y_in_nhwc=y_in_nhwc, z_in=z_in, z_in_nhwc=z_in_nhwc,
@@ -329,7 +382,7 @@ class _TrainForward(torch.autograd.Function):
                     a, h, w = S["dec_in"][i]
                     ho, wo = engine.conv_out_hw(op.conv, h, w)
                     if op.gdn is not None:
-                        g, dbeta, dgamma = gdn_bwd(op.gdn, S["dec_u"][i], g, B, ho, wo)
+                        g, dbeta, dgamma = gdn_bwd(op.gdn, S["dec_u"][i][0], g, B, ho, wo, norm=S["dec_u"][i][1])
                         put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
                     dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, g_layout)
                     put(op.conv.weight, dw); put(op.conv.bias, db)
@@ -405,7 +458,7 @@ class _TrainForward(torch.autograd.Function):
                     a, h, w, layout = S["enc_in"][i]
                     ho, wo = engine.conv_out_hw(op.conv, h, w)
                     if op.gdn is not None:
-                        g, dbeta, dgamma = gdn_bwd(op.gdn, S["enc_u"][i], g, B, ho, wo)
+                        g, dbeta, dgamma = gdn_bwd(op.gdn, S["enc_u"][i][0], g, B, ho, wo, norm=S["enc_u"][i][1])
                         put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
                     dw, db = conv_wgrad(op.conv, a, g, B, h, w, layout, LAYOUT_NHWC)
                     put(op.conv.weight, dw); put(op.conv.bias, db)
