@@ -326,6 +326,14 @@ int nic_to_pair(const float* src, void* dst, int64_t rows, int32_t c, int32_t sq
 int nic_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                   int32_t step, void* stream);
 
+/*
+ * The same update for MANY tensors in one launch (64 tensors per launch).  The *_host arguments are HOST arrays of `count` device
+ * pointers / element counts; the pointers travel to the kernel as launch arguments, so there is no table upload and no host
+ * synchronisation.  A tensor with n = 0 is skipped.
+ */
+int nic_adam_multi_step(float* const* p_host, const float* const* g_host, float* const* m_host, float* const* v_host,
+                        const int64_t* n_host, int32_t count, float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,7 +35,7 @@ struct WgradParams {
   long bs_n, bs_c, bs_h, bs_w;
   int stride, ntaps, a_square;
   int8_t dy[kMaxTaps], dx[kMaxTaps];
-  long P, pix_per_split;
+  int P, pix_per_split;        // pixel counts fit 32 bits (checked by the host): the per-load index arithmetic stays 32-bit
   int mtiles_per_tap;          // vector path: ceil(cb / 128)
 };
 
@@ -45,9 +45,10 @@ wgrad_kernel(const WgradParams p) {
   __shared__ __align__(16) float As[2][WBK][WT];
   __shared__ __align__(16) float Bs[2][WBK][WT];
   const int tid = threadIdx.x;
-  const long p_begin = static_cast<long>(blockIdx.z) * p.pix_per_split;
-  long p_end = p_begin + p.pix_per_split;
+  const int p_begin = blockIdx.z * p.pix_per_split;
+  int p_end = p_begin + p.pix_per_split;
   if (p_end > p.P) p_end = p.P;
+  const int hw_s = p.hs * p.ws;
   const int n0 = blockIdx.y * WT;
   const int mtot = p.ntaps * p.cb;
   // M tile: vector path = 128 channels of one tap; gather path = 128 rows of the flattened (tap, channel) index
@@ -66,15 +67,15 @@ wgrad_kernel(const WgradParams p) {
 
   float4 a4[2], b4[2];
   float ag[8];
-  auto load_global = [&](long pk0) {
+  auto load_global = [&](int pk0) {
     if (GATHER) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const long pk = pk0 + (tid >> 7) + 2 * j;
+        const int pk = pk0 + (tid >> 7) + 2 * j;
         float v = 0.f;
         if (g_ok && pk < p_end) {
-          const int x = static_cast<int>(pk % p.ws), y = static_cast<int>((pk / p.ws) % p.hs);
-          const int img = static_cast<int>(pk / (static_cast<long>(p.ws) * p.hs));
+          const int img = pk / hw_s, rem = pk - img * hw_s;
+          const int y = rem / p.ws, x = rem - y * p.ws;
           const int by = y * p.stride + g_dy, bx = x * p.stride + g_dx;
           if (by >= 0 && by < p.hb && bx >= 0 && bx < p.wb) v = __ldg(p.big + img * p.bs_n + by * p.bs_h + bx * p.bs_w + g_coff);
         }
@@ -83,12 +84,12 @@ wgrad_kernel(const WgradParams p) {
     } else {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const long pk = pk0 + (tid >> 5) + 8 * j;
+        const int pk = pk0 + (tid >> 5) + 8 * j;
         const int c = cb0 + (tid & 31) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (pk < p_end && c < p.cb) {
-          const int x = static_cast<int>(pk % p.ws), y = static_cast<int>((pk / p.ws) % p.hs);
-          const int img = static_cast<int>(pk / (static_cast<long>(p.ws) * p.hs));
+          const int img = pk / hw_s, rem = pk - img * hw_s;
+          const int y = rem / p.ws, x = rem - y * p.ws;
           const int by = y * p.stride + v_dy, bx = x * p.stride + v_dx;
           if (by >= 0 && by < p.hb && bx >= 0 && bx < p.wb)
             v = __ldg(reinterpret_cast<const float4*>(p.big + img * p.bs_n + by * p.bs_h + bx * p.bs_w + c));
@@ -99,10 +100,10 @@ wgrad_kernel(const WgradParams p) {
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const long pk = pk0 + (tid >> 5) + 8 * j;
+      const int pk = pk0 + (tid >> 5) + 8 * j;
       const int c = n0 + (tid & 31) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (pk < p_end && c < p.cs) v = __ldg(reinterpret_cast<const float4*>(p.small + pk * p.cs + c));
+      if (pk < p_end && c < p.cs) v = __ldg(reinterpret_cast<const float4*>(p.small + static_cast<long>(pk) * p.cs + c));
       b4[j] = v;
     }
   };
@@ -125,8 +126,8 @@ wgrad_kernel(const WgradParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  const long npix = p_end > p_begin ? p_end - p_begin : 0;
-  const int steps = static_cast<int>((npix + WBK - 1) / WBK);
+  const int npix = p_end > p_begin ? p_end - p_begin : 0;
+  const int steps = (npix + WBK - 1) / WBK;
   if (steps > 0) {
     load_global(p_begin);
     store_smem(0);
@@ -134,7 +135,7 @@ wgrad_kernel(const WgradParams p) {
   __syncthreads();
   for (int step = 0; step < steps; ++step) {
     const int buf = step & 1;
-    if (step + 1 < steps) load_global(p_begin + static_cast<long>(step + 1) * WBK);
+    if (step + 1 < steps) load_global(p_begin + (step + 1) * WBK);
 #pragma unroll
     for (int k = 0; k < WBK; ++k) {
       float a[8], b[8];
@@ -358,6 +359,35 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// many tensors in ONE launch: the pointers travel as kernel arguments (no table upload, no host synchronisation);
+// block b works on chunk (b - blk_start[t]) of the tensor t whose block range contains b
+constexpr int kAdamMaxTensors = 64;
+constexpr int kAdamChunk = 256 * 16;
+struct AdamArgs {
+  float* p[kAdamMaxTensors]; const float* g[kAdamMaxTensors]; float* m[kAdamMaxTensors]; float* v[kAdamMaxTensors];
+  long n[kAdamMaxTensors];
+  int blk_start[kAdamMaxTensors + 1];
+  int count;
+};
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const __grid_constant__ AdamArgs a, float beta1, float beta2, float step_size, float sqrt_bc2, float eps) {
+  int lo = 0, hi = a.count;                                   // largest t with blk_start[t] <= blockIdx.x
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.blk_start[mid] <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid; }
+  const int t = lo;
+  float* __restrict__ p = a.p[t]; const float* __restrict__ g = a.g[t]; float* __restrict__ m = a.m[t]; float* __restrict__ v = a.v[t];
+  const long n = a.n[t];
+  const long i0 = static_cast<long>(blockIdx.x - a.blk_start[t]) * kAdamChunk;
+  long i1 = i0 + kAdamChunk;
+  if (i1 > n) i1 = n;
+  for (long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const float gv = g[i];
+    const float mv = m[i] + (gv - m[i]) * (1.0f - beta1);
+    const float vv = v[i] * beta2 + (1.0f - beta2) * gv * gv;
+    m[i] = mv; v[i] = vv;
+    p[i] -= step_size * (mv / (sqrtf(vv) / sqrt_bc2 + eps));
+  }
+}
+
 static inline int ew_blocks(long n) {
   long b = (n + 255) / 256;
   const long cap = static_cast<long>(kNumSMs) * 8;
@@ -423,7 +453,8 @@ static int run_wgrad(const float* big, const float* small, int n, const WgradSha
   p.bs_n = bn; p.bs_c = bc; p.bs_h = bh; p.bs_w = bw;
   p.stride = stride; p.ntaps = tt.ntaps; p.a_square = a_square;
   for (int t = 0; t < tt.ntaps; ++t) { p.dy[t] = tt.dy[t]; p.dx[t] = tt.dx[t]; }
-  p.P = P; p.pix_per_split = w.pix_per_split; p.mtiles_per_tap = w.mtiles_per_tap;
+  if (P + w.pix_per_split > 0x7fffffffL) return fail(NIC_E_BADSHAPE, "wgrad: %ld pixels", P);
+  p.P = static_cast<int>(P); p.pix_per_split = static_cast<int>(w.pix_per_split); p.mtiles_per_tap = w.mtiles_per_tap;
   dim3 grid(w.mtiles, w.ntiles, w.splits);
   if (gather) wgrad_kernel<true><<<grid, 256, 0, st>>>(p);
   else wgrad_kernel<false><<<grid, 256, 0, st>>>(p);
@@ -673,6 +704,32 @@ int nic_layout_convert(const float* src, float* dst, int32_t n, int32_t c, int32
   if (!src || !dst) return fail(NIC_E_BADSHAPE, "layout_convert: null pointer");
   layout_convert_kernel<<<dim3((hw + 31) / 32, (c + 31) / 32, n), 256, 0, as_stream(stream)>>>(src, dst, c, hw, to_nhwc, accumulate);
   return check_launch("layout_convert_kernel");
+}
+
+int nic_adam_multi_step(float* const* p_host, const float* const* g_host, float* const* m_host, float* const* v_host,
+                        const int64_t* n_host, int32_t count, float lr, float beta1, float beta2, float eps, int32_t step, void* stream) {
+  if (int rc = nic_check_device()) return rc;
+  if (count < 0 || step < 1 || (count > 0 && (!p_host || !g_host || !m_host || !v_host || !n_host))) return fail(NIC_E_BADSHAPE, "adam_multi_step: bad arguments");
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step), bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  for (int base = 0; base < count; base += kAdamMaxTensors) {
+    AdamArgs a{};
+    const int cnt = count - base < kAdamMaxTensors ? count - base : kAdamMaxTensors;
+    long blocks = 0;
+    for (int i = 0; i < cnt; ++i) {
+      a.p[i] = p_host[base + i]; a.g[i] = g_host[base + i]; a.m[i] = m_host[base + i]; a.v[i] = v_host[base + i]; a.n[i] = n_host[base + i];
+      if (a.n[i] < 0 || (a.n[i] > 0 && (!a.p[i] || !a.g[i] || !a.m[i] || !a.v[i]))) return fail(NIC_E_BADSHAPE, "adam_multi_step: tensor %d", base + i);
+      a.blk_start[i] = static_cast<int>(blocks);
+      blocks += (a.n[i] + kAdamChunk - 1) / kAdamChunk;
+      if (blocks > 0x7fffffffL) return fail(NIC_E_BADSHAPE, "adam_multi_step: too many elements");
+    }
+    a.blk_start[cnt] = static_cast<int>(blocks);
+    a.count = cnt;
+    if (blocks == 0) continue;
+    adam_multi_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(a, beta1, beta2, static_cast<float>(lr / bc1),
+                                                                                  static_cast<float>(sqrt(bc2)), eps);
+    if (int rc = check_launch("adam_multi_kernel")) return rc;
+  }
+  return NIC_OK;
 }
 
 int nic_to_pair(const float* src, void* dst, int64_t rows, int32_t c, int32_t square, void* stream) {

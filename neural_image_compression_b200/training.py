@@ -533,14 +533,20 @@ class Adam:
 
     @torch.no_grad()
     def step(self):
+        """One update of every parameter that has a gradient, in ONE kernel launch per 64 tensors (nic_adam_multi_step): the
+        pointers travel as launch arguments, so nothing is uploaded and the host does not synchronise."""
         lib = _lib.load()
         self.t += 1
-        for p, m, v in zip(self.params, self.m, self.v):
-            if p.grad is None:
-                continue
+        live = [(p, p.grad.contiguous().float(), m, v) for p, m, v in zip(self.params, self.m, self.v) if p.grad is not None]
+        if not live:
+            return
+        for p, _, _, _ in live:
             engine.require_cuda(p, "parameter")
-            g = p.grad.contiguous().float()
-            with torch.cuda.device(p.device):
-                check(lib.nic_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
-                                        self.t, current_stream()), "nic_adam_step")
+        n = len(live)
+        arr = lambda k: (C.c_void_p * n)(*[t[k].data_ptr() for t in live])     # noqa: E731
+        counts = (C.c_int64 * n)(*[t[0].numel() for t in live])
+        with torch.cuda.device(live[0][0].device):
+            check(lib.nic_adam_multi_step(arr(0), arr(1), arr(2), arr(3), counts, n, self.lr, self.betas[0], self.betas[1], self.eps,
+                                          self.t, current_stream()), "nic_adam_multi_step")
+        for p, _, _, _ in live:
             torch.autograd.graph.increment_version(p)       # updated behind torch's back: packed-weight caches key on _version
