@@ -19,6 +19,10 @@ One "step" = model(x, training=False) + the rd terms on one batch.
             ALGORITHMIC FLOPs / its CUDA-event duration, against the measured bf16 peak of MEASURED_PEAKS.json; in the
             bf16x3 arm the kernel issues 3x the algorithmic MMA work (roofline.tensor_pipe_frac counts the issued FLOPs)
   cpu_baseline: the oracle (torch CPU port of the reference's path) on the box's host cores, bounded sample
+  train_step  : (extra, not the headline) BASELINE.json configs[3] - the reference's training step (Trainer.py:79-86: forward with
+            noise, rd_loss, backward, Adam) on 8 x 3 x 256 x 256 crops PER GPU through ShardedTrainer (hand-written backward
+            kernels, bucketed NCCL gradient all-reduce), CUDA-event timed, max over ranks; the oracle's autograd step on the
+            host cores beside it (rank 0, bounded sample)
 
 --impl reference runs only that CPU arm (rank 0) and prints the same line shape with "impl": "reference".
 """
@@ -108,6 +112,25 @@ def cpu_reference_arm(images: int, iters: int):
                       f"({torch.get_num_threads()} threads)", "bpp_total": rd["bpp_total"], "psnr": rd["psnr"], "s_per_pass": t}
 
 
+def cpu_train_step(images: int = 2):
+    """The reference's training step on the host cores: autograd over the oracle port + restated Adam, one pass (bounded sample)."""
+    import torch
+    from oracle import backward as OB
+    from tests import helpers as Hh
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = Hh.seeded_model(M, K, "calib")
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = Hh.seeded_input((images, 3, 256, 256))
+    torch.manual_seed(5)
+    nz, ny = torch.rand(images, M, 4, 4) - 0.5, torch.rand(images, M, 16, 16) - 0.5
+    t0 = time.perf_counter()
+    _, grads, _ = OB.loss_and_grads(sd, x, M, K, nz, ny, LAMBDA)
+    OB.adam_step(sd, grads)
+    t = time.perf_counter() - t0
+    return {"value": images / t, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"one step on {images} x 3x256x256 crops (forward + rd_loss + autograd backward + Adam), torch CPU fp32"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -121,6 +144,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-arms", action="store_true", help="skip the short runs of the other precision arms reported beside the headline")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the training-step line item (BASELINE.json configs[3])")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -315,6 +339,38 @@ def main():
     roofline_lik = {"bound": "hbm", "kernel": "gm_likelihood_kernel<K=3, full>", "unit": "GB/s", "peak": peaks["hbm"],
                     "bytes_per_y_element": 88, "peak_source": f"{peaks['src']} copy bandwidth", **lik}
 
+    # ---- the training step (BASELINE.json configs[3]) - extra line item, every rank takes part (gradient all-reduce) ----------
+    train = None
+    if not args.no_train_step:
+        del evaluator, flush
+        torch.cuda.empty_cache()
+        tb = 8
+        tmodel = Hh.seeded_model(M, K, "calib", precision=args.precision).to(dev)
+        trainer = parallel.ShardedTrainer(tmodel, LAMBDA, lr=1e-4)
+        tgen = torch.Generator(device="cpu"); tgen.manual_seed(2000 + rank)
+        crops = [torch.rand((tb, 3, 256, 256), generator=tgen).to(dev) for _ in range(4)]
+        for i in range(3):
+            trainer.step(crops[i % 4])
+        sync_all()
+        tl0 = lib.nic_launch_count()
+        ts, te = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nt = max(5, args.steps)
+        ts.record()
+        for i in range(nt):
+            trd = trainer.step(crops[i % 4])
+        te.record()
+        sync_all()
+        tt_ms = torch.tensor([ts.elapsed_time(te)], device=dev)
+        if world > 1:
+            dist.all_reduce(tt_ms, op=dist.ReduceOp.MAX)
+        from neural_image_compression_b200.training import train_precision
+        train = {"workload": "rate-distortion training step, 256x256 crops, batch 8 per GPU (BASELINE.json configs[3]): forward with noise, "
+                             "rd_loss, backward, gradient all-reduce, Adam(lr 1e-4)",
+                 "value": tb * world * nt / (float(tt_ms.item()) / 1e3), "unit": "images/s", "ms_per_step": float(tt_ms.item()) / nt,
+                 "steps": nt, "arm": train_precision(tmodel), "gpu_launches_per_step": (lib.nic_launch_count() - tl0) / nt,
+                 "loss_last": float(trd["loss"].detach()), "scaling": "weak"}
+        del trainer, tmodel, crops
+
     assert lib.nic_pipeline_status() == 0, "a tensor-core kernel aborted on an expired pipeline wait: numbers invalid"
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_reference_arm(2, 3)
@@ -338,6 +394,10 @@ def main():
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["rd"]["cpu_sample_bpp_total"] = cpu["bpp_total"]
+        if train is not None:
+            if not args.no_cpu_baseline:
+                train["cpu_baseline"] = cpu_train_step(2)
+            line["train_step"] = train
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if world > 1:
