@@ -265,6 +265,18 @@ size_t nic_conv_wgrad_workspace_bytes(const nic_conv_desc* d);
 int nic_conv_wgrad(const nic_conv_desc* d, const float* x, const float* g, float* dw, float* db,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * The same weight gradient on the tcgen05 tensor cores (bf16x3: hi/lo-split operands, fp32 accumulation in TMEM; ~1e-5 relative).
+ * x_pair / g_pair are the NIC_DT_BF16X2 NHWC forms (nic_to_pair) of the layer input and of the output gradient; g (f32 NHWC) is
+ * only read for db.  The contraction index is the pixel and both tensors are channels-contiguous, so TMA boxes of
+ * [pixels][64 channels] are fed to the MMA as MN-major operands with no transposition (csrc/wgrad_tc.cu).
+ * Built for c_in % 128 == 0, c_out % 128 == 0, square kernels, both tensors NHWC, >= 8 x 8 pixels on the smaller side:
+ * nic_conv_wgrad_tc_workspace_bytes returns 0 for any other layer (use nic_conv_wgrad).
+ */
+size_t nic_conv_wgrad_tc_workspace_bytes(const nic_conv_desc* d);
+int nic_conv_wgrad_tc(const nic_conv_desc* d, const void* x_pair, const void* g_pair, const float* g, float* dw, float* db,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* LeakyReLU(0.01) backward from the saved activation OUTPUT: g_pre = out > 0 ? g : 0.01 g (may run in place on g) */
 int nic_lrelu_bwd(const float* g, const float* out, float* g_pre, int64_t n, void* stream);
 

@@ -59,6 +59,8 @@ SIGNATURES = {
     # training step (backward)
     "nic_conv_wgrad_workspace_bytes": (_sz, [C.POINTER(ConvDesc)]),
     "nic_conv_wgrad": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nic_conv_wgrad_tc_workspace_bytes": (_sz, [C.POINTER(ConvDesc)]),
+    "nic_conv_wgrad_tc": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nic_lrelu_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "nic_gdn_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "nic_gdn_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -14,6 +14,11 @@
 
 namespace nic {
 
+// wgrad_tc.cu
+bool wgrad_tc_supported(const nic_conv_desc* d);
+size_t wgrad_tc_workspace_bytes(const nic_conv_desc* d);
+int wgrad_tc_launch(const nic_conv_desc* d, const void* x_pair, const void* g_pair, float* part, int* splits_out, cudaStream_t st);
+
 int conv1x1_fp32(const float* x, long pixels, int cin, int cout, const float* w, const float* bias, float* y, int a_square,
                  int epilogue, cudaStream_t st);
 
@@ -538,6 +543,44 @@ int nic_conv_wgrad(const nic_conv_desc* d, const float* x, const float* g, float
     if (d->out_layout == NIC_LAYOUT_NHWC) return run_colsum_nhwc(g, static_cast<long>(d->n) * hw, d->c_out, db, cpart, st);
     return run_colsum_nchw(g, d->n, d->c_out, hw, db, cpart, st);
   }
+  return NIC_OK;
+}
+
+size_t nic_conv_wgrad_tc_workspace_bytes(const nic_conv_desc* d) {
+  if (!d || validate_conv_desc(d) || !wgrad_tc_supported(d)) return 0;
+  return wgrad_tc_workspace_bytes(d) + colsum_part_bytes(d->n, d->c_out) + 256;
+}
+
+int nic_conv_wgrad_tc(const nic_conv_desc* d, const void* x_pair, const void* g_pair, const float* g, float* dw, float* db,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = nic_check_device()) return rc;
+  if (int rc = validate_conv_desc(d)) return rc;
+  if (!wgrad_tc_supported(d)) return fail(NIC_E_UNSUPPORTED, "conv_wgrad_tc: layer shape not built for the tensor-core path");
+  if (!x_pair || !g_pair || !dw || (db && !g)) return fail(NIC_E_BADSHAPE, "conv_wgrad_tc: null pointer");
+  const size_t need = nic_conv_wgrad_tc_workspace_bytes(d);
+  if (!workspace || workspace_bytes < need) return fail(NIC_E_WORKSPACE, "conv_wgrad_tc: workspace %zu < %zu bytes", workspace_bytes, need);
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(NIC_E_BADALIGN, "conv_wgrad_tc: workspace must be 256-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  if (d->n == 0) {
+    cudaMemsetAsync(dw, 0, sizeof(float) * d->c_in * d->c_out * d->kh * d->kw, st);
+    if (db) cudaMemsetAsync(db, 0, sizeof(float) * d->c_out, st);
+    return NIC_OK;
+  }
+  char* ws = static_cast<char*>(workspace);
+  float* part = reinterpret_cast<float*>(ws);
+  float* cpart = reinterpret_cast<float*>(ws + wgrad_tc_workspace_bytes(d));
+  int splits = 0;
+  if (int rc = wgrad_tc_launch(d, x_pair, g_pair, part, &splits, st)) return rc;
+  nic_conv_desc full{};
+  full.n = 1; full.c_in = full.c_out = 1; full.kh = d->kh; full.kw = d->kw; full.stride = 1; full.pad = d->pad;
+  full.h_in = full.w_in = 64; full.h_out = full.w_out = 64 + 2 * d->pad - d->kh + 1;
+  TapTable tt;
+  if (int rc = build_tap_table(&full, &tt)) return rc;
+  const WgradShape s = wgrad_shape(d);
+  const long total = static_cast<long>(tt.ntaps) * s.cb * s.cs;
+  wgrad_fold_kernel<<<ew_blocks(total), 256, 0, st>>>(part, splits, tt.ntaps, s.cb, s.cs, d->kh, d->kw, tt, dw);
+  if (int rc = check_launch("wgrad_fold_kernel")) return rc;
+  if (db) return run_colsum_nhwc(g, static_cast<long>(d->n) * d->h_out * d->w_out, d->c_out, db, cpart, st);
   return NIC_OK;
 }
 

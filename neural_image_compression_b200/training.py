@@ -38,6 +38,7 @@ from . import _lib, engine
 from ._lib import (ConvDesc, DT_F32, EPI_BIAS, LAYOUT_NCHW, LAYOUT_NHWC, PREC_FP32, Q_NOISE, Q_PASSTHRU, check, current_stream, ptr)
 
 PREC = "fp32"
+WGRAD_TC = os.environ.get("NIC_WGRAD_TC", "1") != "0"      # tensor-core weight gradients in the bf16x3 arm (0: fp32 kernel everywhere)
 
 
 def train_precision(model) -> str:
@@ -59,14 +60,24 @@ def _ws(nbytes: int, dev):
 
 # ---- single backward ops ------------------------------------------------------------------------------------------
 
-def conv_wgrad(conv: nn.Module, x: torch.Tensor, g: torch.Tensor, n: int, h: int, w: int, in_layout: int, out_layout: int):
-    """(dW in the reference layout, db) of one layer; x = forward input, g = gradient w.r.t. the conv output."""
+def conv_wgrad(conv: nn.Module, x: torch.Tensor, g: torch.Tensor, n: int, h: int, w: int, in_layout: int, out_layout: int,
+               arm: str = "fp32"):
+    """(dW in the reference layout, db) of one layer; x = forward input, g = gradient w.r.t. the conv output.
+    bf16x3 arm: the tensor-core kernel (nic_conv_wgrad_tc) for the layer shapes it is built for, else the fp32 kernel."""
     lib = _lib.load()
     op = engine.ConvOp(conv)
     d = op.desc(n, h, w, PREC, in_layout, out_layout, DT_F32, DT_F32)
     d.mask_a = 0
     dw = torch.empty_like(conv.weight, dtype=torch.float32)
     db = torch.empty_like(conv.bias, dtype=torch.float32)
+    if arm == "bf16x3" and WGRAD_TC:
+        nbytes = lib.nic_conv_wgrad_tc_workspace_bytes(C.byref(d))
+        if nbytes:
+            ws = _ws(nbytes, x.device)
+            xp, gp = to_pair(x), to_pair(g)            # named: a temporary would be freed (and its memory reused) before the launch
+            check(lib.nic_conv_wgrad_tc(C.byref(d), ptr(xp), ptr(gp), ptr(g), ptr(dw), ptr(db), ptr(ws), ws.numel(),
+                                        current_stream()), "nic_conv_wgrad_tc")
+            return dw, db
     nbytes = lib.nic_conv_wgrad_workspace_bytes(C.byref(d))
     ws = _ws(nbytes, x.device)
     check(lib.nic_conv_wgrad(C.byref(d), ptr(x), ptr(g), ptr(dw), ptr(db), ptr(ws), ws.numel(), current_stream()), "nic_conv_wgrad")
@@ -384,7 +395,7 @@ class _TrainForward(torch.autograd.Function):
                     if op.gdn is not None:
                         g, dbeta, dgamma = gdn_bwd(op.gdn, S["dec_u"][i][0], g, B, ho, wo, norm=S["dec_u"][i][1])
                         put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
-                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, g_layout)
+                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, g_layout, arm=arm)
                     put(op.conv.weight, dw); put(op.conv.bias, db)
                     g = conv_dgrad(op.conv, g, B, h, w, g_layout, arm=arm)
                     g_layout = LAYOUT_NHWC
@@ -401,7 +412,7 @@ class _TrainForward(torch.autograd.Function):
                 g = to_nhwc(draw)
                 ep = model.entropy_parameters.ops
                 for i, (op, a) in reversed(list(enumerate(zip(ep, (S["combined"], S["e1"], S["e2"]))))):
-                    dw, db = conv_wgrad(op.conv, a, g, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC)
+                    dw, db = conv_wgrad(op.conv, a, g, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
                     put(op.conv.weight, dw); put(op.conv.bias, db)
                     if i > 0:
                         g = lrelu_bwd_(conv_dgrad(op.conv, g, B, hy, wy, arm=arm), a)
@@ -409,7 +420,7 @@ class _TrainForward(torch.autograd.Function):
                 d_phi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, :2 * M].contiguous(), c_in=2 * M, arm=arm)
                 d_psi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, 2 * M:].contiguous(), c_in=2 * M, arm=arm)
                 masked = model.context_model.masked
-                dw, db = conv_wgrad(masked, S["y_in_nhwc"], d_phi, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC)
+                dw, db = conv_wgrad(masked, S["y_in_nhwc"], d_phi, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
                 put(masked.weight, dw); put(masked.bias, db)
                 d_yin = add_(d_yin, conv_dgrad(masked, d_phi, B, hy, wy, arm=arm))
                 g = d_psi
@@ -417,7 +428,7 @@ class _TrainForward(torch.autograd.Function):
                 for i in range(len(hs) - 1, -1, -1):
                     op = hs[i]
                     a, h, w = S["hs_in"][i]
-                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC)
+                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
                     put(op.conv.weight, dw); put(op.conv.bias, db)
                     g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
                     if i > 0:
@@ -443,7 +454,7 @@ class _TrainForward(torch.autograd.Function):
                 for i in range(len(ha) - 1, -1, -1):
                     op = ha[i]
                     a, h, w = S["ha_in"][i]
-                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC)
+                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
                     put(op.conv.weight, dw); put(op.conv.bias, db)
                     g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
                     if i > 0:
@@ -460,7 +471,7 @@ class _TrainForward(torch.autograd.Function):
                     if op.gdn is not None:
                         g, dbeta, dgamma = gdn_bwd(op.gdn, S["enc_u"][i][0], g, B, ho, wo, norm=S["enc_u"][i][1])
                         put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
-                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, layout, LAYOUT_NHWC)
+                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, layout, LAYOUT_NHWC, arm=arm)
                     put(op.conv.weight, dw); put(op.conv.bias, db)
                     if i > 0:
                         g = conv_dgrad(op.conv, g, B, h, w, arm=arm)

@@ -163,3 +163,38 @@ def test_wgrad_kernel_against_torch_autograd_shapes():
         if conv.in_channels >= 16:
             dx = conv_dgrad(conv, gi, n, h, w, _lib.LAYOUT_NCHW if out_nchw else _lib.LAYOUT_NHWC)
             assert rel_err(dx.permute(0, 3, 1, 2), ref_dx) < 5e-6, (conv, rel_err(dx.permute(0, 3, 1, 2), ref_dx))
+
+
+def test_wgrad_tensor_core_kernel_against_float64_autograd():
+    """nic_conv_wgrad_tc (tcgen05, MN-major operands straight from the NHWC tensors, hi/lo-split): every layer type it is built for."""
+    import torch.nn as nn
+    from neural_image_compression_b200 import _lib
+    from neural_image_compression_b200.training import conv_wgrad
+    torch.manual_seed(4)
+    cases = [(nn.Conv2d(128, 128, 1), 2, 16, 16), (nn.Conv2d(128, 128, 3, 1, 1), 2, 16, 24), (nn.Conv2d(128, 256, 5, 1, 2), 1, 16, 16),
+             (nn.Conv2d(128, 128, 5, 2, 2), 2, 32, 48), (nn.ConvTranspose2d(128, 128, 5, 2, 2, 1), 2, 8, 16),
+             (nn.Conv2d(640, 1152, 1), 2, 8, 16), (nn.Conv2d(128, 128, 5, 2, 2), 3, 40, 24)]
+    results = []
+    for conv, n, h, w in cases:
+        conv = conv.double()
+        x = torch.randn(n, conv.in_channels, h, w, dtype=torch.float64, requires_grad=True)
+        y = conv(x)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        ref_dw, ref_db = conv.weight.grad.clone(), conv.bias.grad.clone()
+        conv = conv.float().cuda()
+        xi = x.detach().float().cuda().permute(0, 2, 3, 1).contiguous()
+        gi = gy.float().cuda().permute(0, 2, 3, 1).contiguous()
+        d = __import__("neural_image_compression_b200.engine", fromlist=["ConvOp"]).ConvOp(conv).desc(
+            n, h, w, "fp32", _lib.LAYOUT_NHWC, _lib.LAYOUT_NHWC, _lib.DT_F32, _lib.DT_F32)
+        assert _lib.load().nic_conv_wgrad_tc_workspace_bytes(ctypes_byref(d)) > 0, conv
+        dw, db = conv_wgrad(conv, xi, gi, n, h, w, _lib.LAYOUT_NHWC, _lib.LAYOUT_NHWC, arm="bf16x3")
+        torch.cuda.synchronize()
+        results.append((str(conv), rel_err(dw, ref_dw), rel_err(db, ref_db)))
+    print("\n".join(f"{e1:.2e} {e2:.2e} {c}" for c, e1, e2 in results))
+    assert all(e1 < 5e-5 and e2 < 5e-6 for _, e1, e2 in results), results
+
+
+def ctypes_byref(d):
+    import ctypes
+    return ctypes.byref(d)
