@@ -297,7 +297,9 @@ int nic_gdn_bwd(const float* u, const float* g, int32_t n, int32_t c, int32_t h,
  *   nic_gdn_reparam     beta_eff [c], gamma_eff [c, c] (= the [c_out, c_in] weight of the norm conv), gamma_eff_t (its transpose)
  *   nic_gdn_apply       out = u * rsqrt(norm)   (inverse: u * sqrt(norm))
  *   nic_gdn_bwd_prep    t = d out / d norm * g,  du = g * rsqrt(norm) (inverse: g * sqrt(norm))
- *   nic_gdn_bwd_finish  du += 2 u r;  dgamma_raw, dbeta_raw from (u, t) through the LowerBound rule
+ *   nic_gdn_bwd_finish  du += 2 u r;  dgamma_raw, dbeta_raw from (u, t) through the LowerBound rule; dgamma_eff_in [c, c] /
+ *                       dbeta_eff_in [c] (both or neither): the gradients w.r.t. the EFFECTIVE parameters when the caller has
+ *                       already formed them (sum_pix t_i u_j^2 is the weight gradient of a 1x1 conv: nic_conv_wgrad_tc)
  */
 int nic_gdn_reparam(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, float* beta_eff, float* gamma_eff,
                     float* gamma_eff_t, void* stream);
@@ -305,8 +307,8 @@ int nic_gdn_apply(const float* u, const float* norm, int64_t n, int32_t inverse,
 int nic_gdn_bwd_prep(const float* u, const float* g, const float* norm, int64_t n, int32_t inverse, float* t, float* du, void* stream);
 size_t nic_gdn_bwd_finish_workspace_bytes(int64_t pixels, int32_t c);
 int nic_gdn_bwd_finish(const float* u, const float* t, const float* r, int64_t pixels, int32_t c, float beta_min,
-                       const float* beta_raw, const float* gamma_raw, float* du, float* dbeta_raw, float* dgamma_raw,
-                       void* workspace, size_t workspace_bytes, void* stream);
+                       const float* beta_raw, const float* gamma_raw, const float* dgamma_eff_in, const float* dbeta_eff_in,
+                       float* du, float* dbeta_raw, float* dgamma_raw, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Backward of nic_gm_likelihood_fwd w.r.t. y_in and the raw entropy-parameter tensor (softmax / softplus / erf-form CDF

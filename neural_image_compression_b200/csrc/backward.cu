@@ -417,7 +417,7 @@ static WgradPlan plan_wgrad(int ntaps, int cb, int cs, long P, bool gather) {
   const long max_splits = (P + 255) / 256;                           // >= 256 pixels per split
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  if (splits > 512) splits = 512;
+  if (splits > 128) splits = 128;                                  // the fold walks the splits serially: keep it short
   long per = (P + splits - 1) / splits;
   per = (per + WBK - 1) / WBK * WBK;
   w.pix_per_split = per;
@@ -695,8 +695,8 @@ size_t nic_gdn_bwd_finish_workspace_bytes(int64_t pixels, int32_t c) {
 }
 
 int nic_gdn_bwd_finish(const float* u, const float* t, const float* r, int64_t pixels, int32_t c, float beta_min,
-                       const float* beta_raw, const float* gamma_raw, float* du, float* dbeta_raw, float* dgamma_raw,
-                       void* workspace, size_t workspace_bytes, void* stream) {
+                       const float* beta_raw, const float* gamma_raw, const float* dgamma_eff_in, const float* dbeta_eff_in,
+                       float* du, float* dbeta_raw, float* dgamma_raw, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = nic_check_device()) return rc;
   if (pixels < 1 || pixels > 0x7fffffffL || c < 4 || c % 4) return fail(NIC_E_BADSHAPE, "gdn_bwd_finish: pixels=%lld c=%d", static_cast<long long>(pixels), c);
   if (!u || !t || !r || !beta_raw || !gamma_raw || !du || !dbeta_raw || !dgamma_raw) return fail(NIC_E_BADSHAPE, "gdn_bwd_finish: null pointer");
@@ -714,9 +714,13 @@ int nic_gdn_bwd_finish(const float* u, const float* t, const float* r, int64_t p
   const long elems = pixels * c;
   gdn_bwd_finish_kernel<<<ew_blocks(elems), 256, 0, st>>>(u, r, du, elems);
   if (int rc = check_launch("gdn_bwd_finish_kernel")) return rc;
-  WgradShape s{}; s.cb = c; s.cs = c; s.hb = s.hs = 1; s.wb = s.ws = static_cast<int>(pixels); s.big_layout = NIC_LAYOUT_NHWC; s.big_is_input = true;
-  if (int rc = run_wgrad(u, t, 1, s, 1, 0, 1, 1, 1, dgamma_eff, wpart, st)) return rc;
-  if (int rc = run_colsum_nhwc(t, pixels, c, dbeta_eff, cpart, st)) return rc;
+  if (dgamma_eff_in && dbeta_eff_in) {          // the caller ran the (u^2, t) weight gradient elsewhere (nic_conv_wgrad_tc on a 1x1 descriptor)
+    dgamma_eff = const_cast<float*>(dgamma_eff_in); dbeta_eff = const_cast<float*>(dbeta_eff_in);
+  } else {
+    WgradShape s{}; s.cb = c; s.cs = c; s.hb = s.hs = 1; s.wb = s.ws = static_cast<int>(pixels); s.big_layout = NIC_LAYOUT_NHWC; s.big_is_input = true;
+    if (int rc = run_wgrad(u, t, 1, s, 1, 0, 1, 1, 1, dgamma_eff, wpart, st)) return rc;
+    if (int rc = run_colsum_nhwc(t, pixels, c, dbeta_eff, cpart, st)) return rc;
+  }
   const float pedestal = static_cast<float>(3.814697265625e-06 * 3.814697265625e-06);
   const float beta_bound = static_cast<float>(sqrt(static_cast<double>(beta_min) + static_cast<double>(pedestal)));
   const float gamma_bound = static_cast<float>(sqrt(static_cast<double>(pedestal)));

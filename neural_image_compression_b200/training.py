@@ -84,12 +84,27 @@ def conv_wgrad(conv: nn.Module, x: torch.Tensor, g: torch.Tensor, n: int, h: int
     return dw, db
 
 
+_PAIRS: Dict[tuple, tuple] = {}        # (data_ptr, version, square) -> (source tensor, its pair form): one conversion per tensor and step
+
+
 def to_pair(x: torch.Tensor, square: bool = False) -> torch.Tensor:
-    """f32 [..., c] -> bf16 [..., 2c] = [hi | lo] (NIC_DT_BF16X2) of x (or of x^2) through nic_to_pair."""
+    """f32 [..., c] -> bf16 [..., 2c] = [hi | lo] (NIC_DT_BF16X2) of x (or of x^2) through nic_to_pair.
+    A layer input is consumed in pair form by its forward conv AND by its weight gradient, a gradient by the data-gradient conv
+    AND the weight gradient: the conversions are memoised until the step ends (`forget_pairs`); the source tensor is kept alive
+    by the entry, so its address cannot be recycled under the key."""
+    key = (x.data_ptr(), x._version, tuple(x.shape), bool(square))
+    hit = _PAIRS.get(key)
+    if hit is not None:
+        return hit[1]
     c = x.shape[-1]
     out = torch.empty(tuple(x.shape[:-1]) + (2 * c,), dtype=torch.bfloat16, device=x.device)
     check(_lib.load().nic_to_pair(ptr(x), ptr(out), x.numel() // c, c, int(square), current_stream()), "nic_to_pair")
+    _PAIRS[key] = (x, out)
     return out
+
+
+def forget_pairs():
+    _PAIRS.clear()
 
 
 def _train_op(conv: nn.Module, epilogue: int, mask_a: bool = False) -> engine.ConvOp:
@@ -248,12 +263,23 @@ def gdn_bwd(gdn: nn.Module, u: torch.Tensor, g: torch.Tensor, n: int, h: int, w:
         st = _gdn_tc(gdn)
         t = torch.empty_like(u)
         check(lib.nic_gdn_bwd_prep(ptr(u), ptr(g), ptr(norm), u.numel(), int(gdn.inverse), ptr(t), ptr(du), current_stream()), "nic_gdn_bwd_prep")
-        r = st["rt_op"].run(to_pair(t), n, h, w, "bf16x3", out_dtype=torch.float32)
+        tp = to_pair(t)
+        r = st["rt_op"].run(tp, n, h, w, "bf16x3", out_dtype=torch.float32)
         pixels = n * h * w
+        # d gamma_eff[i][j] = sum_pix t_i u_j^2 is the weight gradient of the norm conv (1x1, input u^2, output gradient t)
+        dge = dbe = None
+        d = st["norm_op"].desc(n, h, w, PREC, LAYOUT_NHWC, LAYOUT_NHWC, DT_F32, DT_F32)
+        nb = lib.nic_conv_wgrad_tc_workspace_bytes(C.byref(d)) if WGRAD_TC else 0
+        if nb:
+            dge, dbe = _f32((c, c), u.device), _f32(c, u.device)
+            wws = _ws(nb, u.device)
+            u2p = to_pair(u, square=True)
+            check(lib.nic_conv_wgrad_tc(C.byref(d), ptr(u2p), ptr(tp), ptr(t), ptr(dge), ptr(dbe), ptr(wws), wws.numel(), current_stream()),
+                  "nic_conv_wgrad_tc")
         ws = _ws(lib.nic_gdn_bwd_finish_workspace_bytes(pixels, c), u.device)
         check(lib.nic_gdn_bwd_finish(ptr(u), ptr(t), ptr(r), pixels, c, float(gdn.beta_min), ptr(gdn.beta.detach().float().contiguous()),
-                                     ptr(gdn.gamma.detach().float().contiguous()), ptr(du), ptr(dbeta), ptr(dgamma), ptr(ws), ws.numel(),
-                                     current_stream()), "nic_gdn_bwd_finish")
+                                     ptr(gdn.gamma.detach().float().contiguous()), ptr(dge), ptr(dbe), ptr(du), ptr(dbeta), ptr(dgamma),
+                                     ptr(ws), ws.numel(), current_stream()), "nic_gdn_bwd_finish")
         return du, dbeta, dgamma
     ws = _ws(lib.nic_gdn_bwd_workspace_bytes(n, c, h, w), u.device)
     check(lib.nic_gdn_bwd(ptr(u), ptr(g), n, c, h, w, int(gdn.inverse), float(gdn.beta_min), ptr(gdn.beta.detach().float().contiguous()),
@@ -476,6 +502,7 @@ class _TrainForward(torch.autograd.Function):
                     if i > 0:
                         g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
         ctx.S = None
+        forget_pairs()
         params = [p for _, p in model.named_parameters()]
         return (None, None, None, None, None, *[grads.get(id(p)) for p in params])
 
@@ -489,6 +516,7 @@ def train_forward(model, x: torch.Tensor, noise=None, lean: bool = False) -> dic
     else:                                                    # the reference draws z's noise first (Models.py:57-58)
         noise_z = torch.rand((B, M, H // 64, W // 64), device=x.device) - 0.5
         noise_y = torch.rand((B, M, H // 16, W // 16), device=x.device) - 0.5
+    forget_pairs()
     params = [p for _, p in model.named_parameters()]
     res = _TrainForward.apply(model, x.contiguous().float(), noise_z, noise_y, lean, *params)
     x_hat, logp_y, logp_z, y, y_in, z, z_in, p_z, p_y, parts_y, parts_z = res[:11]
