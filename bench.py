@@ -346,13 +346,12 @@ def main():
         torch.cuda.empty_cache()
         tb = 8
         tmodel = Hh.seeded_model(M, K, "calib", precision=args.precision).to(dev)
-        trainer = parallel.ShardedTrainer(tmodel, LAMBDA, lr=1e-4)
+        trainer = parallel.ShardedTrainer(tmodel, LAMBDA, lr=1e-4, graph=use_graph)
         tgen = torch.Generator(device="cpu"); tgen.manual_seed(2000 + rank)
         crops = [torch.rand((tb, 3, 256, 256), generator=tgen).to(dev) for _ in range(4)]
         for i in range(3):
             trainer.step(crops[i % 4])
         sync_all()
-        tl0 = lib.nic_launch_count()
         ts, te = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         nt = max(5, args.steps)
         ts.record()
@@ -367,7 +366,8 @@ def main():
         train = {"workload": "rate-distortion training step, 256x256 crops, batch 8 per GPU (BASELINE.json configs[3]): forward with noise, "
                              "rd_loss, backward, gradient all-reduce, Adam(lr 1e-4)",
                  "value": tb * world * nt / (float(tt_ms.item()) / 1e3), "unit": "images/s", "ms_per_step": float(tt_ms.item()) / nt,
-                 "steps": nt, "arm": train_precision(tmodel), "gpu_launches_per_step": (lib.nic_launch_count() - tl0) / nt,
+                 "steps": nt, "arm": train_precision(tmodel),
+                 "launch": "forward + loss + backward (+ Adam on one rank) replayed from one CUDA graph" if use_graph else "per-kernel launches",
                  "loss_last": float(trd["loss"].detach()), "scaling": "weak"}
         del trainer, tmodel, crops
 

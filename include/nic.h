@@ -343,10 +343,14 @@ int nic_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
 /*
  * The same update for MANY tensors in one launch (64 tensors per launch).  The *_host arguments are HOST arrays of `count` device
  * pointers / element counts; the pointers travel to the kernel as launch arguments, so there is no table upload and no host
- * synchronisation.  A tensor with n = 0 is skipped.
+ * synchronisation.  A tensor with n = 0 is skipped.  step_dev (device int32, or NULL): when given, the step count t is read from
+ * it by the kernel instead of `step` - a CUDA-graph replay of the launch then sees the t that nic_counter_increment advanced.
  */
 int nic_adam_multi_step(float* const* p_host, const float* const* g_host, float* const* m_host, float* const* v_host,
-                        const int64_t* n_host, int32_t count, float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+                        const int64_t* n_host, int32_t count, float lr, float beta1, float beta2, float eps, int32_t step,
+                        const int32_t* step_dev, void* stream);
+/* *counter += 1 on the device (stream-ordered, graph-capturable) */
+int nic_counter_increment(int32_t* counter, void* stream);
 
 #ifdef __cplusplus
 }

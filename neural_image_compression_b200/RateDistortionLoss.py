@@ -47,16 +47,22 @@ def rd_terms(model_out: dict, x: torch.Tensor, lambda_rd: float):
     return per_image, scalars
 
 
-def rd_loss(model_out: dict, x: torch.Tensor, lambda_rd: float):
+def rd_loss_device(model_out: dict, x: torch.Tensor, lambda_rd: float):
+    """(loss, per_image [3, B], scalars [8]) without touching the host: `loss` is differentiable when the model output is
+    (Trainer.py:85 calls results['loss'].backward(): one autograd node over logp_y, logp_z, x_hat).  CUDA-graph safe."""
     with torch.no_grad():
         per_image, scalars = rd_terms(model_out, x, lambda_rd)
     loss = scalars[5]
     diff = [model_out[k] for k in ("logp_y", "logp_z", "x_hat")]
     if torch.is_grad_enabled() and any(t.requires_grad for t in diff):
-        # Trainer.py:85 calls results['loss'].backward(): the loss is one autograd node over (logp_y, logp_z, x_hat)
         from .training import _RDLoss
         xd = x.to(diff[2].device).contiguous().float()
         loss = _RDLoss.apply(diff[0], diff[1], diff[2].contiguous().float(), xd, float(lambda_rd), scalars)
+    return loss, per_image, scalars
+
+
+def rd_loss(model_out: dict, x: torch.Tensor, lambda_rd: float):
+    loss, per_image, scalars = rd_loss_device(model_out, x, lambda_rd)
     s = scalars.tolist()                                   # the one host synchronisation
     mse_per_image = per_image[2]
     return {

@@ -374,8 +374,17 @@ struct AdamArgs {
   int blk_start[kAdamMaxTensors + 1];
   int count;
 };
+__global__ void counter_increment_kernel(int* c) { if (threadIdx.x == 0 && blockIdx.x == 0) *c += 1; }
+
+// step_dev != NULL: the step count lives on the device (a CUDA-graph replay of the launch must see a new t every time)
 __global__ void __launch_bounds__(256)
-adam_multi_kernel(const __grid_constant__ AdamArgs a, float beta1, float beta2, float step_size, float sqrt_bc2, float eps) {
+adam_multi_kernel(const __grid_constant__ AdamArgs a, float beta1, float beta2, float lr, float step_size, float sqrt_bc2, float eps,
+                  const int* __restrict__ step_dev) {
+  if (step_dev) {
+    const int t = *step_dev;
+    step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(beta1), t)));
+    sqrt_bc2 = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)));
+  }
   int lo = 0, hi = a.count;                                   // largest t with blk_start[t] <= blockIdx.x
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.blk_start[mid] <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid; }
   const int t = lo;
@@ -753,9 +762,18 @@ int nic_layout_convert(const float* src, float* dst, int32_t n, int32_t c, int32
   return check_launch("layout_convert_kernel");
 }
 
-int nic_adam_multi_step(float* const* p_host, const float* const* g_host, float* const* m_host, float* const* v_host,
-                        const int64_t* n_host, int32_t count, float lr, float beta1, float beta2, float eps, int32_t step, void* stream) {
+int nic_counter_increment(int32_t* counter, void* stream) {
   if (int rc = nic_check_device()) return rc;
+  if (!counter) return fail(NIC_E_BADSHAPE, "counter_increment: null pointer");
+  counter_increment_kernel<<<1, 32, 0, as_stream(stream)>>>(counter);
+  return check_launch("counter_increment_kernel");
+}
+
+int nic_adam_multi_step(float* const* p_host, const float* const* g_host, float* const* m_host, float* const* v_host,
+                        const int64_t* n_host, int32_t count, float lr, float beta1, float beta2, float eps, int32_t step,
+                        const int32_t* step_dev, void* stream) {
+  if (int rc = nic_check_device()) return rc;
+  if (step_dev) step = 1;                       // unused: the kernel reads the device counter
   if (count < 0 || step < 1 || (count > 0 && (!p_host || !g_host || !m_host || !v_host || !n_host))) return fail(NIC_E_BADSHAPE, "adam_multi_step: bad arguments");
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step), bc2 = 1.0 - pow(static_cast<double>(beta2), step);
   for (int base = 0; base < count; base += kAdamMaxTensors) {
@@ -772,8 +790,8 @@ int nic_adam_multi_step(float* const* p_host, const float* const* g_host, float*
     a.blk_start[cnt] = static_cast<int>(blocks);
     a.count = cnt;
     if (blocks == 0) continue;
-    adam_multi_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(a, beta1, beta2, static_cast<float>(lr / bc1),
-                                                                                  static_cast<float>(sqrt(bc2)), eps);
+    adam_multi_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(a, beta1, beta2, lr, static_cast<float>(lr / bc1),
+                                                                                  static_cast<float>(sqrt(bc2)), eps, step_dev);
     if (int rc = check_launch("adam_multi_kernel")) return rc;
   }
   return NIC_OK;

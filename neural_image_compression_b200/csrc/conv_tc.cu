@@ -1195,8 +1195,11 @@ __global__ void pack_first_bf16_kernel(const float* __restrict__ w, __nv_bfloat1
 }
 
 int check_first_layer(const nic_conv_desc* d) {
+  // bf16x3 also serves the bare conv (bias epilogue, f32 NHWC output): the training step keeps the pre-GDN tensor, and the
+  // data gradient of the last g_s layer is this same conv over the image-shaped gradient
+  const bool bare_x3 = d->precision == NIC_PREC_BF16X3 && d->epilogue == NIC_EPI_BIAS;
   if (d->c_in != 3 || d->c_out != 128 || d->kh != 5 || d->kw != 5 || d->stride != 2 || d->pad != 2 || d->transposed || d->mask_a ||
-      d->epilogue != NIC_EPI_GDN)
+      (d->epilogue != NIC_EPI_GDN && !bare_x3))
     return fail(NIC_E_UNSUPPORTED, "conv bf16: the only c_in < 64 layer built is Conv2d(3, 128, 5, stride 2, pad 2) + GDN (g_a layer 1)");
   return NIC_OK;
 }
@@ -1547,7 +1550,12 @@ int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, con
       return launch_tc(&e, te, x, w_packed, bias, nullptr, nullptr, y, st, d);
     }
     if (!gdn) {
-      if (small_cin(d)) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: the only c_in < 64 layer built is Conv2d(3, 128, 5, s2, p2) + GDN");
+      if (small_cin(d)) {            // Conv2d(3, 128, 5, s2, p2) + bias from the NCHW f32 image into a plain NHWC f32 tensor
+        if (int rc = check_first_layer(d)) return rc;
+        if (d->out_layout != NIC_LAYOUT_NHWC || d->out_dtype != NIC_DT_F32 || d->out_c_total != 0)
+          return fail(NIC_E_UNSUPPORTED, "conv bf16x3 (first layer, bias epilogue): output must be a plain NHWC f32 tensor");
+        return conv_first_x3(d, x, w_packed, bias, static_cast<float*>(y), st);
+      }
       return launch_tc(d, tt, x, w_packed, bias, nullptr, nullptr, y, st);
     }
     // GDN / IGDN layer: conv + bias on the tensor cores into an fp32 NHWC scratch, then the hi/lo-split gamma contraction

@@ -215,7 +215,7 @@ static int plan_wgrad_tc(const nic_conv_desc* d, WgTcPlan* out) {
   p.yblocks = (p.hs + 7) / 8; p.xblocks = (p.ws + 7) / 8;
   p.kblocks = p.n * p.yblocks * p.xblocks;
   const int base = p.ngroups * p.mtiles * p.ntiles;
-  int splits = (2 * kNumSMs + base - 1) / base;
+  int splits = (kNumSMs + base - 1) / base;        // one CTA per SM fits (shared memory): aim at ONE wave, fewer partials to fold
   if (splits > p.kblocks) splits = p.kblocks;
   if (splits < 1) splits = 1;
   p.kb_per_split = (p.kblocks + splits - 1) / splits;

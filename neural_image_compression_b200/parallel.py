@@ -227,17 +227,79 @@ class ShardedTrainer:
 
     Mirrors the body of Trainer.train (Trainer.py:79-86) with the optimizer of Main.ipynb:133; every rank holds the full
     model and must start from identical weights.  Noise is drawn per rank from the rank's own generator state (seed the
-    ranks differently) or injected through `noise`."""
+    ranks differently) or injected through `noise`.
 
-    def __init__(self, model, lambda_rd: float, lr: float = 1e-4, group=None, bucket_bytes: int = 8 << 20, optimizer=None):
+    graph=True captures forward + loss + backward (+ the Adam launch when there is a single rank) in a CUDA graph per input
+    shape and replays it: the ~380 kernel launches of a step, their tensor-map encodes and the Python around them are paid
+    once.  The noise comes from torch's graph-safe Philox state (a fresh draw every replay).  The returned dict then holds
+    device tensors only ('loss', 'scalars' = the 8 rd scalars of nic_rd_finalize); read them when needed.  Steps with injected
+    noise run eagerly."""
+
+    def __init__(self, model, lambda_rd: float, lr: float = 1e-4, group=None, bucket_bytes: int = 8 << 20, optimizer=None,
+                 graph: bool = False):
         from .training import Adam
-        self.model, self.lambda_rd, self.group = model, lambda_rd, group
+        self.model, self.lambda_rd, self.group, self.graph = model, lambda_rd, group, graph
         self.optimizer = optimizer if optimizer is not None else Adam(model.parameters(), lr=lr)
         self.buckets = grad_buckets(model.parameters(), bucket_bytes)
         self._flats = [None] * len(self.buckets)
+        self._graphs = {}
         self.step_count = 0
 
+    def _distributed(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _forward_backward(self, x_local, noise=None):
+        """forward + loss + backward on the calling thread and stream (training.step_gradients: the same kernels loss.backward()
+        runs, without the autograd engine, whose device thread cannot take part in a stream capture)."""
+        from .training import step_gradients
+        self.optimizer.zero_grad()
+        return step_gradients(self.model, x_local, self.lambda_rd, noise=noise)
+
+    def _graphed(self, x_local):
+        key = (tuple(x_local.shape), x_local.device)
+        ent = self._graphs.get(key)
+        fuse_adam = not self._distributed() and hasattr(self.optimizer, "launch")
+        if ent is None:
+            static_x = torch.empty_like(x_local)
+            static_x.copy_(x_local)
+            side = torch.cuda.Stream(device=x_local.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                     # warm-up: allocations, attribute setting, the device status word
+                self._forward_backward(static_x)
+            torch.cuda.current_stream().wait_stream(side)
+            if fuse_adam:
+                self.optimizer.prepare(x_local.device)
+            # every derived cache (packed conv weights, adjoint packs, GDN effective parameters, the factorized table, the masked
+            # conv's zeroing) is keyed on the parameters' version counters: bump them so that the capture RECORDS the kernels that
+            # rebuild those caches - a replay must re-derive them from the weights the previous replay's Adam launch wrote
+            for p in self.model.parameters():
+                torch.autograd.graph.increment_version(p)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                res = self._forward_backward(static_x)
+                if fuse_adam:
+                    self.optimizer.launch()                  # counter increment + update: the step count lives on the device
+            ent = (g, static_x, res)
+            self._graphs[key] = ent
+        g, static_x, res = ent
+        if static_x.data_ptr() != x_local.data_ptr():
+            static_x.copy_(x_local, non_blocking=True)
+        g.replay()
+        if fuse_adam:
+            self.optimizer.t += 1
+            for p in self.model.parameters():                 # updated inside the replay: packed-weight caches key on _version
+                torch.autograd.graph.increment_version(p)
+        return res, fuse_adam
+
     def step(self, x_local: torch.Tensor, noise=None) -> dict:
+        if self.graph and noise is None:
+            (loss, per_image, scalars), adam_done = self._graphed(x_local)
+            allreduce_gradients(self.buckets, self.group, self._flats)
+            if not adam_done:
+                self.optimizer.step()
+            self.step_count += 1
+            return {"loss": loss, "scalars": scalars, "mse_per_image": per_image[2]}
         from .RateDistortionLoss import rd_loss
         self.optimizer.zero_grad()
         out = self.model(x_local, training=True, noise=noise, lean=True)

@@ -116,11 +116,19 @@ def _train_op(conv: nn.Module, epilogue: int, mask_a: bool = False) -> engine.Co
     return cache[key]
 
 
+def _is_first_layer_shape(conv: nn.Module) -> bool:
+    return (isinstance(conv, nn.Conv2d) and not isinstance(conv, nn.ConvTranspose2d) and conv.in_channels == 3 and conv.out_channels == 128
+            and conv.kernel_size == (5, 5) and conv.stride == (2, 2) and conv.padding == (2, 2))
+
+
 def conv_forward(arm: str, conv: nn.Module, epilogue: int, x: torch.Tensor, n: int, h: int, w: int, in_layout: int = LAYOUT_NHWC,
                  out_layout: int = LAYOUT_NHWC, out: Optional[torch.Tensor] = None, out_c_total: int = 0, out_c_offset: int = 0,
                  mask_a: bool = False) -> torch.Tensor:
     """One conv (+ bias / LeakyReLU) with f32 tensors at both ends; the contraction on the tensor cores in the bf16x3 arm."""
     op = _train_op(conv, epilogue, mask_a)
+    if arm == "bf16x3" and _is_first_layer_shape(conv) and in_layout == LAYOUT_NCHW and out_layout == LAYOUT_NHWC and out is None \
+            and epilogue == EPI_BIAS and w % 4 == 0:
+        return op.run(x, n, h, w, "bf16x3", in_layout=LAYOUT_NCHW, out_dtype=torch.float32)       # the dedicated 3 -> 128 kernel
     if arm == "bf16x3" and in_layout == LAYOUT_NHWC and conv.in_channels % 64 == 0:
         return op.run(to_pair(x), n, h, w, "bf16x3", out_layout=out_layout, out=out, out_c_total=out_c_total,
                       out_c_offset=out_c_offset, out_dtype=torch.float32)
@@ -216,6 +224,11 @@ def conv_dgrad(conv: nn.Module, g: torch.Tensor, n: int, h_in: int, w_in: int, g
     """Gradient w.r.t. the layer input (NHWC f32): the adjoint conv through nic_conv_fwd.
     (h_in, w_in) = forward input size.  `weight` / `c_in` select a slice of the layer's input channels
     (weight = the matching slice of conv.weight, contiguous)."""
+    if arm == "bf16x3" and g_layout == LAYOUT_NCHW and weight is None and isinstance(conv, nn.ConvTranspose2d) and g.shape[-1] % 4 == 0:
+        adj, op = _adjoint(conv, None, conv.in_channels, h_in, w_in)          # ConvTranspose2d(128, 3) backward = the 3 -> 128 conv
+        if _is_first_layer_shape(adj):
+            h_out, w_out = engine.conv_out_hw(conv, h_in, w_in)
+            return op.run(g, n, h_out, w_out, "bf16x3", in_layout=LAYOUT_NCHW, out_dtype=torch.float32)
     if arm == "bf16x3" and g_layout == LAYOUT_NHWC and conv.out_channels % 64 == 0:
         cin = conv.in_channels if c_in is None else c_in
         h_out, w_out = engine.conv_out_hw(conv, h_in, w_in)
@@ -309,9 +322,9 @@ _FACT_SLICES = (("matrices", 0, 0, 3), ("biases", 0, 3, 6), ("factors", 0, 6, 9)
 
 # ---- the model as one autograd node ------------------------------------------------------------------------------
 
-class _TrainForward(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, model, x, noise_z, noise_y, lean, *params):
+def _forward_impl(model, x, noise_z, noise_y, lean):
+    """The training forward (fp32 NHWC tensors between layers, layer inputs kept): -> (outputs tuple, saved state S)."""
+    if True:
         lib = _lib.load()
         dev = x.device
         B, _, H, W = x.shape
@@ -386,17 +399,15 @@ class _TrainForward(torch.autograd.Function):
         S["arm"] = arm
         S.update(combined=combined, e1=e1, e2=e2, raw=raw, y_in=y_in, y_in_nhwc=y_in_nhwc, z_in=z_in, z_in_nhwc=z_in_nhwc,
                  fparams=model.factorized_entropy_model.packed(), shape=(B, H, W))
-        ctx.model, ctx.S = model, S
-        ctx.x_needs_grad = x.requires_grad
         logp_y = ly["logp"]
         extra = [] if lean else ([ly["mu"], ly["sigma"]] if K == 1 else [ly["weights"], ly["mus"], ly["sigmas"]])
         nd = [y, y_in, z, z_in, p_z, ly["p"], ly["partials"], parts_z] + extra
-        ctx.mark_non_differentiable(*nd)
-        return (x_hat, logp_y, logp_z, *nd)
+        return (x_hat, logp_y, logp_z, *nd), S
 
-    @staticmethod
-    def backward(ctx, g_xhat, g_logp_y, g_logp_z, *unused):
-        model, S = ctx.model, ctx.S
+
+def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tensor]:
+    """The hand-scheduled backward: {id(parameter): gradient} from the gradients of x_hat / logp_y / logp_z (any may be None)."""
+    if True:
         lib = _lib.load()
         B, H, W = S["shape"]
         M, K = model.M, model.K
@@ -501,10 +512,60 @@ class _TrainForward(torch.autograd.Function):
                     put(op.conv.weight, dw); put(op.conv.bias, db)
                     if i > 0:
                         g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
-        ctx.S = None
         forget_pairs()
+        return grads
+
+
+class _TrainForward(torch.autograd.Function):
+    """The whole model as ONE autograd node (what makes the reference trainer's loss.backward() work, Trainer.py:85)."""
+
+    @staticmethod
+    def forward(ctx, model, x, noise_z, noise_y, lean, *params):
+        outs, S = _forward_impl(model, x, noise_z, noise_y, lean)
+        ctx.model, ctx.S = model, S
+        ctx.mark_non_differentiable(*outs[3:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_xhat, g_logp_y, g_logp_z, *unused):
+        model, S = ctx.model, ctx.S
+        grads = _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z)
+        ctx.S = None
         params = [p for _, p in model.named_parameters()]
         return (None, None, None, None, None, *[grads.get(id(p)) for p in params])
+
+
+@torch.no_grad()
+def step_gradients(model, x: torch.Tensor, lambda_rd: float, noise=None):
+    """forward + rd_loss + backward of one step WITHOUT the autograd engine (everything on the calling thread and its current
+    stream - what a CUDA-graph capture needs): accumulates into .grad like loss.backward() and returns
+    (loss [device scalar], per_image [3, B], scalars [8])."""
+    from .RateDistortionLoss import rd_terms
+    B, _, H, W = x.shape
+    M = model.M
+    if noise is not None:
+        noise_z, noise_y = noise
+    else:
+        noise_z = torch.rand((B, M, H // 64, W // 64), device=x.device) - 0.5
+        noise_y = torch.rand((B, M, H // 16, W // 16), device=x.device) - 0.5
+    forget_pairs()
+    x = x.contiguous().float()
+    outs, S = _forward_impl(model, x, noise_z, noise_y, True)
+    x_hat, logp_y, logp_z = outs[:3]
+    logp_y._nic_partials, logp_z._nic_partials = outs[9], outs[10]
+    per_image, scalars = rd_terms({"x_hat": x_hat, "logp_y": logp_y, "logp_z": logp_z}, x, lambda_rd)
+    # d loss / d logp = -1 / (ln 2 * H * W * B); d loss / d x_hat = lambda * 255^2 * 2 (x_hat - x) / numel  (RateDistortionLoss.py:13-34)
+    gl = torch.full((1,), -1.0 / (math.log(2.0) * H * W * B), dtype=torch.float32, device=x.device)
+    gx = torch.empty_like(x_hat)
+    with torch.cuda.device(x.device):
+        check(_lib.load().nic_sse_bwd(ptr(x_hat), ptr(x), x.numel(), float(lambda_rd) * 65025.0 * 2.0 / x.numel(), ptr(gx), current_stream()),
+              "nic_sse_bwd")
+    grads = _backward_impl(model, S, gx, gl.expand(logp_y.shape), gl.expand(logp_z.shape))
+    for p in model.parameters():
+        g = grads.get(id(p))
+        if g is not None:
+            p.grad = g if p.grad is None else p.grad + g
+    return scalars[5], per_image, scalars
 
 
 def train_forward(model, x: torch.Tensor, noise=None, lean: bool = False) -> dict:
@@ -560,6 +621,7 @@ class Adam:
     def __init__(self, params, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
         self.params: List[torch.Tensor] = [p for p in params]
         self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        self._t_dev = None                               # the step count on the device (what the update kernel reads)
         self.m = [torch.zeros_like(p, dtype=torch.float32) for p in self.params]
         self.v = [torch.zeros_like(p, dtype=torch.float32) for p in self.params]
 
@@ -571,21 +633,35 @@ class Adam:
                 p.grad.zero_()
 
     @torch.no_grad()
-    def step(self):
-        """One update of every parameter that has a gradient, in ONE kernel launch per 64 tensors (nic_adam_multi_step): the
-        pointers travel as launch arguments, so nothing is uploaded and the host does not synchronise."""
+    def launch(self):
+        """Advance the device step counter and update every parameter that has a gradient: two stream-ordered launches
+        (nic_counter_increment, nic_adam_multi_step with the pointers as launch arguments), no upload, no host
+        synchronisation, capturable in a CUDA graph (the bias corrections are formed on the device from the counter)."""
         lib = _lib.load()
-        self.t += 1
         live = [(p, p.grad.contiguous().float(), m, v) for p, m, v in zip(self.params, self.m, self.v) if p.grad is not None]
         if not live:
             return
         for p, _, _, _ in live:
             engine.require_cuda(p, "parameter")
+        dev = live[0][0].device
+        self.prepare(dev)
         n = len(live)
         arr = lambda k: (C.c_void_p * n)(*[t[k].data_ptr() for t in live])     # noqa: E731
         counts = (C.c_int64 * n)(*[t[0].numel() for t in live])
-        with torch.cuda.device(live[0][0].device):
+        with torch.cuda.device(dev):
+            check(lib.nic_counter_increment(ptr(self._t_dev), current_stream()), "nic_counter_increment")
             check(lib.nic_adam_multi_step(arr(0), arr(1), arr(2), arr(3), counts, n, self.lr, self.betas[0], self.betas[1], self.eps,
-                                          self.t, current_stream()), "nic_adam_multi_step")
-        for p, _, _, _ in live:
-            torch.autograd.graph.increment_version(p)       # updated behind torch's back: packed-weight caches key on _version
+                                          1, ptr(self._t_dev), current_stream()), "nic_adam_multi_step")
+        self._keep = live                                 # the gradients stay alive until the next launch
+
+    def prepare(self, dev):
+        """Create the device step counter (outside any CUDA-graph capture: a captured fill would reset it on every replay)."""
+        if self._t_dev is None or self._t_dev.device != dev:
+            self._t_dev = torch.full((1,), self.t, dtype=torch.int32, device=dev)
+
+    def step(self):
+        self.launch()
+        self.t += 1
+        for p in self.params:
+            if p.grad is not None:
+                torch.autograd.graph.increment_version(p)       # updated behind torch's back: packed-weight caches key on _version

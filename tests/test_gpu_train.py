@@ -198,3 +198,46 @@ def test_wgrad_tensor_core_kernel_against_float64_autograd():
 def ctypes_byref(d):
     import ctypes
     return ctypes.byref(d)
+
+
+def test_graphed_trainer_steps_like_the_eager_one():
+    """ShardedTrainer(graph=True): forward + loss + backward + Adam replayed from one CUDA graph.  The noise is drawn inside the
+    graph (a new draw per replay), so the check is statistical: same first loss within the noise spread, the step counter
+    advances on the device, parameters move by ~lr per step, and the loss goes down over 30 steps like the eager trainer's."""
+    from neural_image_compression_b200 import parallel
+    x = H.seeded_input((2, 3, 128, 128)).cuda()
+    losses = {}
+    for mode in (False, True):
+        model = H.seeded_model(128, 3, "calib", precision="bf16x3").cuda()
+        w0 = model.decoder.net[6].weight.detach().clone()
+        tr = parallel.ShardedTrainer(model, 0.005, lr=1e-4, graph=mode)
+        ls = []
+        for _ in range(30):
+            rd = tr.step(x)
+            ls.append(float(rd["loss"].detach()))
+        torch.cuda.synchronize()
+        losses[mode] = ls
+        assert tr.optimizer.t == 30 and int(tr.optimizer._t_dev) == 30
+        moved = float((model.decoder.net[6].weight.detach() - w0).abs().max())
+        assert 5e-4 < moved <= 30 * 3.2e-4, moved            # Adam: a few lr per step at most, and the weights did move
+    assert abs(losses[True][0] - losses[False][0]) < 0.02 * losses[False][0], (losses[True][0], losses[False][0])
+    assert losses[True][-1] < losses[True][0] and abs(losses[True][-1] - losses[False][-1]) < 0.05 * losses[False][-1], losses
+
+
+def test_step_gradients_equals_autograd_backward():
+    """training.step_gradients (the autograd-free path the graphed trainer captures) deposits the same .grad as loss.backward()."""
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    from neural_image_compression_b200.training import step_gradients
+    model = H.seeded_model(128, 3, "calib", precision="bf16x3").cuda()
+    x = H.seeded_input((2, 3, 64, 128)).cuda()
+    torch.manual_seed(9)
+    noise = (torch.rand(2, 128, 1, 2).cuda() - 0.5, torch.rand(2, 128, 4, 8).cuda() - 0.5)
+    rd = rd_loss(model(x, noise=noise), x, 0.005)
+    rd["loss"].backward()
+    ref = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad()
+    loss, per_image, scalars = step_gradients(model, x, 0.005, noise=noise)
+    torch.cuda.synchronize()
+    assert float(loss) == float(rd["loss"].detach())
+    for k, p in model.named_parameters():
+        assert torch.equal(p.grad, ref[k]), k

@@ -72,5 +72,19 @@ e1.record()
 torch.cuda.synchronize()
 if rank == 0:
     print(f"ShardedTrainer.step back to back: {e0.elapsed_time(e1) / steps:.2f} ms / step = {B * world * steps / e0.elapsed_time(e1) * 1e3:.0f} images/s")
+# the same step replayed from a CUDA graph (forward + loss + backward [+ Adam on one rank] captured once)
+gtrainer = parallel.ShardedTrainer(model, 0.005, lr=1e-4, graph=True)
+for i in range(3):
+    rd = gtrainer.step(xs[i % 4])
+torch.cuda.synchronize()
+e0.record()
+for i in range(steps):
+    rd = gtrainer.step(xs[i % 4])
+e1.record()
+torch.cuda.synchronize()
+if rank == 0:
+    print(f"ShardedTrainer(graph=True).step: {e0.elapsed_time(e1) / steps:.2f} ms / step = {B * world * steps / e0.elapsed_time(e1) * 1e3:.0f} images/s; "
+          f"loss {float(rd['loss']):.4f}, device step counter {int(gtrainer.optimizer._t_dev) if gtrainer.optimizer._t_dev is not None else -1}")
+assert lib.nic_pipeline_status() == 0
 if world > 1:
     dist.destroy_process_group()
