@@ -194,10 +194,17 @@ static int plan_wgrad_tc(const nic_conv_desc* d, WgTcPlan* out) {
   const int qmin = fdiv(-pad, s), qmax = fdiv(k - 1 - pad, s);
   p.qmin = qmin; p.ph = p.pw = 8 + qmax - qmin;
   p.big_slab = (p.ph * p.pw * 128 + 1023) / 1024 * 1024;
-  // groups: taps of one parity plane, four at a time
+  // groups: the taps of one parity plane in equal shares of <= 4 (5x5 stride 2: 9 / 6 / 6 / 4 taps -> 3+3+3, 3+3, 3+3, 4), so
+  // that the CTAs of a wave carry about the same number of MMAs
   int g = 0;
   for (int ry = 0; ry < s; ++ry)
     for (int rx = 0; rx < s; ++rx) {
+      int total = 0;
+      for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw)
+          if (((kh - pad) % s + s) % s == ry && ((kw - pad) % s + s) % s == rx) ++total;
+      if (total == 0) continue;
+      const int ngr = (total + 3) / 4, share = (total + ngr - 1) / ngr;
       int cnt = 0;
       for (int kh = 0; kh < k; ++kh)
         for (int kw = 0; kw < k; ++kw) {
@@ -206,7 +213,7 @@ static int plan_wgrad_tc(const nic_conv_desc* d, WgTcPlan* out) {
           if (cnt == 0) { if (g >= kMaxGroups) return fail(NIC_E_UNSUPPORTED, "wgrad tc: too many tap groups"); p.g_ry[g] = ry; p.g_rx[g] = rx; }
           p.g_tap[g][cnt] = static_cast<int8_t>(kh * k + kw);
           p.g_qy[g][cnt] = static_cast<int8_t>(fdiv(dy, s)); p.g_qx[g][cnt] = static_cast<int8_t>(fdiv(dx, s));
-          if (++cnt == 4) { p.g_ntaps[g++] = 4; cnt = 0; }
+          if (++cnt == share) { p.g_ntaps[g++] = static_cast<int8_t>(cnt); cnt = 0; }
         }
       if (cnt) p.g_ntaps[g++] = static_cast<int8_t>(cnt);
     }
@@ -215,7 +222,7 @@ static int plan_wgrad_tc(const nic_conv_desc* d, WgTcPlan* out) {
   p.yblocks = (p.hs + 7) / 8; p.xblocks = (p.ws + 7) / 8;
   p.kblocks = p.n * p.yblocks * p.xblocks;
   const int base = p.ngroups * p.mtiles * p.ntiles;
-  int splits = (kNumSMs + base - 1) / base;        // one CTA per SM fits (shared memory): aim at ONE wave, fewer partials to fold
+  int splits = kNumSMs / base;                     // one CTA per SM fits (shared memory): at most ONE wave, few partials to fold
   if (splits > p.kblocks) splits = p.kblocks;
   if (splits < 1) splits = 1;
   p.kb_per_split = (p.kblocks + splits - 1) / splits;
