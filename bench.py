@@ -19,6 +19,7 @@ One "step" = model(x, training=False) + the rd terms on one batch.
             ALGORITHMIC FLOPs / its CUDA-event duration, against the measured bf16 peak of MEASURED_PEAKS.json; in the
             bf16x3 arm the kernel issues 3x the algorithmic MMA work (roofline.tensor_pipe_frac counts the issued FLOPs)
   cpu_baseline: the oracle (torch CPU port of the reference's path) on the box's host cores, bounded sample
+  scalable_variant : (extra) BASELINE.json configs[4] - ScalableImageCoding(192, 128) on one 2048 x 1536 image per GPU, bf16x3 arm
   train_step  : (extra, not the headline) BASELINE.json configs[3] - the reference's training step (Trainer.py:79-86: forward with
             noise, rd_loss, backward, Adam) on 8 x 3 x 256 x 256 crops PER GPU through ShardedTrainer (hand-written backward
             kernels, bucketed NCCL gradient all-reduce), CUDA-event timed, max over ranks; the oracle's autograd step on the
@@ -144,6 +145,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-arms", action="store_true", help="skip the short runs of the other precision arms reported beside the headline")
+    ap.add_argument("--no-scalable", action="store_true", help="skip the scalable-coding line item (BASELINE.json configs[4])")
     ap.add_argument("--no-train-step", action="store_true", help="skip the training-step line item (BASELINE.json configs[3])")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -371,6 +373,35 @@ def main():
                  "loss_last": float(trd["loss"].detach()), "scaling": "weak"}
         del trainer, tmodel, crops
 
+    # ---- the scalable-coding variant (BASELINE.json configs[4]): one 2048 x 1536 image per GPU, forward + vision_rd_loss ---------
+    scalable = None
+    if not args.no_scalable:
+        from neural_image_compression_b200.RateDistortionLoss import vision_rd_loss
+        smodel = Hh.seeded_scalable_model(192, 128, 1, "calib", precision="bf16x3").to(dev)
+        sgen = torch.Generator(device="cpu"); sgen.manual_seed(3000 + rank)
+        simgs = [torch.rand((1, 3, 1536, 2048), generator=sgen).to(dev) for _ in range(2)]
+        with torch.no_grad():
+            for i in range(3):
+                vision_rd_loss(smodel(simgs[i % 2], training=False), simgs[i % 2], LAMBDA)
+            sync_all()
+            ss, se = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ns = 5
+            ss.record()
+            for i in range(ns):
+                srd = vision_rd_loss(smodel(simgs[i % 2], training=False), simgs[i % 2], LAMBDA)
+            se.record()
+            sync_all()
+        st_ms = torch.tensor([ss.elapsed_time(se)], device=dev)
+        if world > 1:
+            dist.all_reduce(st_ms, op=dist.ReduceOp.MAX)
+        scalable = {"workload": "ScalableImageCoding(192, 128, K=1) eval forward + vision_rd_loss, synthetic 2048x1536, one image per GPU "
+                                "(BASELINE.json configs[4]; the reference's forward with the four repairs of SURVEY.md 2.4, no LST)",
+                    "value": world * ns / (float(st_ms.item()) / 1e3), "unit": "images/s", "ms_per_image": float(st_ms.item()) / ns,
+                    "precision": "bf16x3", "algorithmic_tflops": 1.2547 * world * ns / (float(st_ms.item()) / 1e3),
+                    "bpp_total": float(srd["bpp_total"]), "psnr": float(srd["psnr"]), "scaling": "weak"}
+        del smodel, simgs
+        torch.cuda.empty_cache()
+
     assert lib.nic_pipeline_status() == 0, "a tensor-core kernel aborted on an expired pipeline wait: numbers invalid"
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_reference_arm(2, 3)
@@ -398,6 +429,8 @@ def main():
             if not args.no_cpu_baseline:
                 train["cpu_baseline"] = cpu_train_step(2)
             line["train_step"] = train
+        if scalable is not None:
+            line["scalable_variant"] = scalable
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if world > 1:

@@ -192,7 +192,8 @@ class ScalableImageCoding(nn.Module):
         dict has no 'F_tilde', and reference checkpoints load with their ``LST.*`` entries ignored.
     Parity for this class is against the reference's own sub-modules called in that repaired order
     (oracle/make_golden.py: scalable cases) - "parity unpinned" by the reference itself, which has no runnable forward.
-    M = 192 runs on the fp32 arm (the tensor-core GDN kernels are built for 128 channels).
+    Arithmetic: precision="bf16x3" (default for channel counts that are multiples of 64) runs the convolutions and the GDN
+    contractions on the tensor cores, "fp32" on the CUDA cores; both meet the parity bar (tests/test_gpu_scalable.py).
     """
 
     def __init__(self, latent_channels: int = 192, base_channels: int = 128, K: int = 1, *, precision: Optional[str] = None):
@@ -217,9 +218,15 @@ class ScalableImageCoding(nn.Module):
         self.context_model_2 = ContextModel(latent_channels=self.M2)
         self.entropy_parameters_1 = EntropyParameters(latent_channels=self.M1, hyper_latent_channels=self.H, K=self.K)
         self.entropy_parameters_2 = EntropyParameters(latent_channels=self.M2, hyper_latent_channels=self.H, K=self.K)
-        self.precision = engine.resolve_precision(precision, None)          # fp32 unless asked otherwise
-        if self.precision != "fp32":
-            raise ValueError("ScalableImageCoding runs on the fp32 arm (its transforms are not 128-channel)")
+        # "bf16x3" (default when every channel count is a multiple of 64, e.g. the reference's 192 / 128): every convolution
+        # and the GDN channel contractions on the tcgen05 engine with hi/lo-split operands (fp32 grade), fp32 NHWC tensors
+        # between layers split on the fly - the layer-by-layer form the training step uses (training.conv_forward / gdn_forward);
+        # "fp32": CUDA cores.
+        tc_ok = all(c % 64 == 0 for c in (self.M, self.M1, self.M2))
+        precision = precision or engine.DEFAULT_PRECISION
+        self.precision = ("bf16x3" if tc_ok else "fp32") if precision == "auto" else precision
+        if self.precision not in ("fp32", "bf16x3") or (self.precision == "bf16x3" and not tc_ok):
+            raise ValueError("ScalableImageCoding: precision must be 'fp32', or 'bf16x3' with channel counts that are multiples of 64")
 
     def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
         return super().load_state_dict({k: v for k, v in state_dict.items() if not k.startswith("LST.")}, strict=strict, **kwargs)
@@ -232,7 +239,20 @@ class ScalableImageCoding(nn.Module):
         B, _, H, W = x.shape
         if H % 64 or W % 64:
             raise ValueError(f"H and W must be multiples of 64; got {H}x{W}")
-        prec, M, M1, M2, K = "fp32", self.M, self.M1, self.M2, self.K
+        arm, M, M1, M2, K = self.precision, self.M, self.M1, self.M2, self.K
+        from . import training as T
+
+        def layer(op, a, h, w, **kw):
+            """One conv (+ GDN / LeakyReLU) with f32 tensors at both ends."""
+            if arm == "fp32":
+                return op.run(a, B, h, w, "fp32", **kw)
+            u = T.conv_forward(arm, op.conv, engine.EPI_BIAS if op.gdn is not None else op.epilogue, a, B, h, w,
+                               mask_a=op.mask_a, **kw)
+            if op.gdn is not None:
+                ho, wo = engine.conv_out_hw(op.conv, h, w)
+                u = T.gdn_forward(arm, op.gdn, u, B, ho, wo)[0]
+            T.forget_pairs()                     # the split copies are per layer here (the training step keeps them for its backward)
+            return u
         x = x.contiguous().float()
         hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
         with torch.cuda.device(x.device), torch.no_grad():
@@ -243,14 +263,14 @@ class ScalableImageCoding(nn.Module):
             qmode = Q_NOISE if training else Q_ROUND
             a, h, w, layout = x, H, W, LAYOUT_NCHW
             for op in self.encoder.ops:
-                a = op.run(a, B, h, w, prec, in_layout=layout, out_layout=LAYOUT_NHWC)
+                a = layer(op, a, h, w, in_layout=layout, out_layout=LAYOUT_NHWC)
                 h, w = engine.conv_out_hw(op.conv, h, w)
                 layout = LAYOUT_NHWC
             y_nhwc = a
             y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, qmode, noise_y, torch.float32)
             a, h, w = y_nhwc, hy, wy
             for op in self.hyper_encoder.ops:
-                a = op.run(a, B, h, w, prec)
+                a = layer(op, a, h, w)
                 h, w = engine.conv_out_hw(op.conv, h, w)
             z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, qmode, noise_z, torch.float32)
             # psi once, into head 1's concat buffer [phi1 (2 M1) | psi (2 M)]; head 2's buffer gets a copy of the window
@@ -260,9 +280,9 @@ class ScalableImageCoding(nn.Module):
             hs = self.hyper_decoder.ops
             for i, op in enumerate(hs):
                 if i == len(hs) - 1:
-                    op.run(a, B, h, w, prec, out=comb1, out_c_total=2 * M1 + 2 * M, out_c_offset=2 * M1)
+                    layer(op, a, h, w, out=comb1, out_c_total=2 * M1 + 2 * M, out_c_offset=2 * M1)
                 else:
-                    a = op.run(a, B, h, w, prec)
+                    a = layer(op, a, h, w)
                 h, w = engine.conv_out_hw(op.conv, h, w)
             comb2[..., 2 * M2:] = comb1[..., 2 * M1:]
             y1, y2 = torch.split(y_in, [M1, M2], dim=1)                   # Models.py:279 (views, as in the reference)
@@ -273,17 +293,17 @@ class ScalableImageCoding(nn.Module):
                                                    (self.context_model_2, self.entropy_parameters_2, comb2, M2,
                                                     y_in_nhwc[..., M1:].contiguous(), y2c)):
                 ctx.masked.apply_mask_()
-                ctx.masked._op.run(yi_nhwc, B, hy, wy, prec, out=comb, out_c_total=comb.shape[-1], out_c_offset=0)
-                a = ep.ops[0].run(comb, B, hy, wy, prec)
-                a = ep.ops[1].run(a, B, hy, wy, prec)
-                raw = ep.ops[2].run(a, B, hy, wy, prec, out_layout=LAYOUT_NCHW, out_dtype=torch.float32)
+                layer(ctx.masked._op, yi_nhwc, hy, wy, out=comb, out_c_total=comb.shape[-1], out_c_offset=0)
+                a = layer(ep.ops[0], comb, hy, wy)
+                a = layer(ep.ops[1], a, hy, wy)
+                raw = layer(ep.ops[2], a, hy, wy, out_layout=LAYOUT_NCHW)
                 heads.append(gm_likelihood(yi, raw, mi, K, Q_PASSTHRU, full=True, want_y_in=False))
             _, p_z, logp_z, parts_z = self.factorized_entropy_model.likelihood(z_in, Q_PASSTHRU)
             a, h, w = y_in_nhwc, hy, wy
             dec = self.decoder.ops
             for i, op in enumerate(dec):
                 last = i == len(dec) - 1
-                a = op.run(a, B, h, w, prec, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC)
+                a = layer(op, a, h, w, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC)
                 h, w = engine.conv_out_hw(op.conv, h, w)
             x_hat = a
         l1, l2 = heads

@@ -34,10 +34,10 @@ def scalable_cases():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "c5_*.npz")))
 
 
-def seeded_scalable_model(M, M1, K, init="calib"):
+def seeded_scalable_model(M, M1, K, init="calib", precision="fp32"):
     from neural_image_compression_b200.Models import ScalableImageCoding
     torch.manual_seed(0)
-    model = ScalableImageCoding(M, M1, K=K, precision="fp32")
+    model = ScalableImageCoding(M, M1, K=K, precision=precision)
     if init != "plain":
         sd = {k: v.clone() for k, v in model.state_dict().items()}
         gy, gz, sigma_bias = INITS[init]

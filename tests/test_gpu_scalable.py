@@ -9,12 +9,16 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 
+ARMS = ("fp32", "bf16x3")       # CUDA cores / tensor cores with hi/lo-split operands: both parity grade
+
+
+@pytest.mark.parametrize("precision", ARMS)
 @pytest.mark.parametrize("case", H.scalable_cases())
-def test_scalable_model_matches_reference_vectors(case):
+def test_scalable_model_matches_reference_vectors(case, precision):
     from neural_image_compression_b200.RateDistortionLoss import vision_rd_loss
     g = H.load_golden(case)
     M, M1, K, init = int(g["M"]), int(g["M1"]), int(g["K"]), str(g["init"])
-    model = H.seeded_scalable_model(M, M1, K, init).cuda()
+    model = H.seeded_scalable_model(M, M1, K, init, precision=precision).cuda()
     x = torch.from_numpy(g["x"]).cuda()
     out = model(x, training=False)
     rd = vision_rd_loss(out, x, 0.005, 0.0)
@@ -31,9 +35,9 @@ def test_scalable_model_matches_reference_vectors(case):
     if (out["y_in"].cpu().numpy() == ref["y_in"]).all() and (out["z_in"].cpu().numpy() == ref["z_in"]).all():
         for name in ("p_y1", "p_y2", "p_z"):
             bad, worst = H.likelihood_close(out[name].cpu().numpy(), ref[name])
-            assert bad <= 1e-5 * ref[name].size, (name, bad, worst)
+            assert bad <= (1e-5 if precision == "fp32" else 2e-3) * ref[name].size, (name, bad, worst)
         xe = float(np.abs(out["x_hat"].cpu().numpy() - ref["x_hat"]).max() / np.abs(ref["x_hat"]).max())
-        assert xe < 1e-4, xe
+        assert xe < (1e-4 if precision == "fp32" else 5e-4), xe
     for key in ("bpp_y1", "bpp_y2", "bpp_z", "bpp_total"):
         assert abs(rd[key] - float(g["rd_" + key])) <= H.BPP_TOL, (key, rd[key], float(g["rd_" + key]))
     assert abs(rd["psnr"] - float(g["rd_psnr"])) <= H.PSNR_TOL
@@ -53,10 +57,11 @@ def test_scalable_rejects_bad_arguments_and_ignores_lst_keys():
     m.load_state_dict(sd)
 
 
-def test_scalable_full_size_image_properties():
+@pytest.mark.parametrize("precision", ARMS)
+def test_scalable_full_size_image_properties(precision):
     """BASELINE configs[4] shape (2048 x 1536), one image per GPU: size-independent properties instead of an oracle run."""
     from neural_image_compression_b200.RateDistortionLoss import vision_rd_loss
-    model = H.seeded_scalable_model(192, 128, 1, "calib").cuda()
+    model = H.seeded_scalable_model(192, 128, 1, "calib", precision=precision).cuda()
     x = H.seeded_input((1, 3, 1536, 2048)).cuda()
     out = model(x, training=False)
     rd = vision_rd_loss(out, x, 0.005, 0.0)
@@ -73,3 +78,7 @@ def test_scalable_full_size_image_properties():
     # a crop-aligned sub-image gives the same interior symbols: the path is convolutional (receptive field << 512 px margin)
     sub = model(x[:, :, :1024, :1024].contiguous(), training=False)
     assert torch.equal(sub["y_in"][:, :, :32, :32], out["y_in"][:, :, :32, :32])
+    # timing of the full-size forward (CUDA events, second call): the tensor-core arm against the CUDA-core arm
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); model(x, training=False); e1.record(); torch.cuda.synchronize()
+    print(f"ScalableImageCoding(192, 128, K=1) 2048x1536 forward, {precision}: {e0.elapsed_time(e1):.1f} ms")
