@@ -90,6 +90,29 @@ class JointAutoregressiveHierarchical(nn.Module):
             # runs the forward-only path of self.precision instead.
             from . import training as _training
             return _training.train_forward(self, x, noise=noise, lean=lean)
+        if self.precision == "bf16x3" and self.M != 128:
+            # the fused pair-tensor pipeline (GDN kernels, first layer) is built for 128 channels; other channel counts that are
+            # multiples of 64 (the reference's default M = 192) run layer by layer: every conv and both GDN contractions on the
+            # tcgen05 engine, fp32 NHWC tensors in between (training._forward_impl with rounding instead of noise)
+            if self.M % 64:
+                raise ValueError(f"precision='bf16x3' needs latent_channels % 64 == 0, got {self.M}")
+            from . import training as _training
+            from ._lib import Q_NOISE as _QN, Q_ROUND as _QR
+            with torch.no_grad():
+                nz = ny = None
+                if training:
+                    nz, ny = noise if noise is not None else (torch.rand((B, self.M, H // 64, W // 64), device=x.device) - 0.5,
+                                                              torch.rand((B, self.M, H // 16, W // 16), device=x.device) - 0.5)
+                _training.forget_pairs()
+                res, _ = _training._forward_impl(self, x.contiguous().float(), nz, ny, lean, qmode=_QN if training else _QR, arm="bf16x3")
+                _training.forget_pairs()
+            x_hat, logp_y, logp_z, y, y_in, z, z_in, p_z, p_y, parts_y, parts_z = res[:11]
+            logp_y._nic_partials, logp_z._nic_partials = parts_y, parts_z
+            out = {"x_hat": x_hat, "y": y, "y_in": y_in, "z": z, "z_in": z_in, "p_z": p_z, "logp_z": logp_z, "p_y": p_y,
+                   "logp_y": logp_y, "training": training}
+            if not lean:
+                out.update(dict(zip(("mu", "sigma") if self.K == 1 else ("weights", "mus", "sigmas"), res[11:])))
+            return out
         prec_up = {"fp32": "fp32", "mixed": "fp32", "bf16x3": "bf16x3", "bf16": "bf16"}[self.precision]   # g_a, h_a
         prec = {"fp32": "fp32", "mixed": "bf16", "bf16x3": "bf16x3", "bf16": "bf16"}[self.precision]    # h_s, context, entropy parameters, g_s
         adt = engine.act_dtype(prec)

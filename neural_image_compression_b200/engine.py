@@ -20,11 +20,12 @@ DEFAULT_PRECISION = os.environ.get("NIC_PRECISION", "auto")
 
 
 def resolve_precision(precision: Optional[str], latent_channels: Optional[int] = None) -> str:
-    """None / "auto" -> the parity-grade tensor-core arm ("bf16x3") where it is built (M = 128: the fused GDN contraction
-    is a 128-channel kernel), else the fp32 CUDA-core arm.  Both meet the reference-parity tolerances."""
+    """None / "auto" -> the parity-grade tensor-core arm ("bf16x3") where it is built (channel counts that are multiples of 64:
+    M = 128 runs the fused pair-tensor pipeline, other M - e.g. the reference's default 192 - the layer-by-layer form with the
+    GDN contractions as tensor-core 1x1 convs), else the fp32 CUDA-core arm.  Both meet the reference-parity tolerances."""
     precision = precision or DEFAULT_PRECISION
     if precision == "auto":
-        return "bf16x3" if latent_channels == 128 else "fp32"
+        return "bf16x3" if (latent_channels is not None and latent_channels % 64 == 0) else "fp32"
     return precision
 
 

@@ -35,7 +35,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, engine
-from ._lib import (ConvDesc, DT_F32, EPI_BIAS, LAYOUT_NCHW, LAYOUT_NHWC, PREC_FP32, Q_NOISE, Q_PASSTHRU, check, current_stream, ptr)
+from ._lib import (ConvDesc, DT_F32, EPI_BIAS, LAYOUT_NCHW, LAYOUT_NHWC, PREC_FP32, Q_NOISE, Q_PASSTHRU, Q_ROUND, check, current_stream, ptr)
 
 PREC = "fp32"
 WGRAD_TC = os.environ.get("NIC_WGRAD_TC", "1") != "0"      # tensor-core weight gradients in the bf16x3 arm (0: fp32 kernel everywhere)
@@ -322,8 +322,10 @@ _FACT_SLICES = (("matrices", 0, 0, 3), ("biases", 0, 3, 6), ("factors", 0, 6, 9)
 
 # ---- the model as one autograd node ------------------------------------------------------------------------------
 
-def _forward_impl(model, x, noise_z, noise_y, lean):
-    """The training forward (fp32 NHWC tensors between layers, layer inputs kept): -> (outputs tuple, saved state S)."""
+def _forward_impl(model, x, noise_z, noise_y, lean, qmode: int = Q_NOISE, arm: Optional[str] = None):
+    """The layer-by-layer forward (fp32 NHWC tensors between layers, layer inputs kept): -> (outputs tuple, saved state S).
+    qmode = Q_NOISE is the training forward; Q_ROUND the evaluation forward of a model whose channel count the fused
+    pair-tensor pipeline is not built for (Models.py uses it for M != 128 on the bf16x3 arm)."""
     if True:
         lib = _lib.load()
         dev = x.device
@@ -331,7 +333,7 @@ def _forward_impl(model, x, noise_z, noise_y, lean):
         M, K = model.M, model.K
         hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
         S = {}
-        arm = train_precision(model)
+        arm = arm or train_precision(model)
         with torch.cuda.device(dev):
             # g_a: conv (+ bias) -> u, kept for the GDN backward; GDN -> the next layer's input, kept for its weight gradient
             a, h, w, layout = x, H, W, LAYOUT_NCHW
@@ -349,7 +351,7 @@ def _forward_impl(model, x, noise_z, noise_y, lean):
                     S["enc_u"].append(None)
                 layout = LAYOUT_NHWC
             y_nhwc = a
-            y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, Q_NOISE, noise_y, torch.float32)
+            y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, qmode, noise_y, torch.float32)
             # h_a (reads the unquantised y)
             a, h, w = y_nhwc, hy, wy
             S["ha_in"] = []
@@ -357,7 +359,7 @@ def _forward_impl(model, x, noise_z, noise_y, lean):
                 S["ha_in"].append((a, h, w))
                 a = conv_forward(arm, op.conv, op.epilogue, a, B, h, w)
                 h, w = engine.conv_out_hw(op.conv, h, w)
-            z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, Q_NOISE, noise_z, torch.float32)
+            z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, qmode, noise_z, torch.float32)
             # h_s -> psi, context -> phi, both windows of `combined`
             combined = _f32((B, hy, wy, 4 * M), dev)
             a, h, w = z_in_nhwc, hz, wz
