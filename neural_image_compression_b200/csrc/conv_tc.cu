@@ -150,7 +150,7 @@ constexpr int kMmaWarps = 2;                    // one MMA-issuing warp per M = 
 constexpr int kFirstEpiWarp = 2 + kMmaWarps;
 constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;
 constexpr int kMaxDynSmem = 232448 - 8192;    // 227 KB opt-in limit minus this kernel's static shared memory
-constexpr int kMaxCout = 1280;                // bias table staged in shared memory
+constexpr int kMaxCout = 1792;                // bias table staged in shared memory (M = 192, K = 3: 1728 channels)
 
 struct TcTap { int8_t plane, roff, coff, slab; };
 struct TcPhase {
@@ -1354,6 +1354,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     return fail(NIC_E_UNSUPPORTED, "conv %s: input must be NHWC %s", x3 ? "bf16x3" : "bf16", x3 ? "bf16 pairs" : "bf16");
   if (x3 && gdn) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: the conv kernel has bias / LeakyReLU epilogues only (GDN follows as gdn_x3_kernel)");
   if (d->c_in % 64) return fail(NIC_E_UNSUPPORTED, "conv bf16: c_in=%d must be a multiple of 64", d->c_in);
+  if (d->c_out > kMaxCout) return fail(NIC_E_UNSUPPORTED, "conv bf16: c_out=%d exceeds the %d-entry bias table of the kernel", d->c_out, kMaxCout);
   if (gdn && (d->c_out != 128 || !gdn_gamma || !gdn_beta)) return fail(NIC_E_UNSUPPORTED, "conv bf16: the fused GDN epilogue needs c_out = 128 and packed gamma/beta");
   if ((reinterpret_cast<uintptr_t>(x) & 127) || (reinterpret_cast<uintptr_t>(w_packed) & 127)) return fail(NIC_E_BADALIGN, "conv bf16: tensors must be 128-byte aligned for TMA");
   p.n = d->n; p.hin = d->h_in; p.win = d->w_in; p.cin = d->c_in; p.cout = d->c_out; p.hout = d->h_out; p.wout = d->w_out;

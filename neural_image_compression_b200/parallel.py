@@ -213,11 +213,9 @@ def allreduce_gradients(buckets, group=None, flats=None):
         off = 0
         for p in bucket:
             n = p.numel()
-            g = flat[off:off + n].view_as(p)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
+            # .grad becomes a VIEW of the averaged bucket (no copy back; with `flats` given the buffer persists until the next call,
+            # which is after the optimizer has consumed it)
+            p.grad = flat[off:off + n].view_as(p) if flats is not None else flat[off:off + n].view_as(p).clone()
             off += n
     return len(works)
 

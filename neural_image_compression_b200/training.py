@@ -129,7 +129,7 @@ def conv_forward(arm: str, conv: nn.Module, epilogue: int, x: torch.Tensor, n: i
     if arm == "bf16x3" and _is_first_layer_shape(conv) and in_layout == LAYOUT_NCHW and out_layout == LAYOUT_NHWC and out is None \
             and epilogue == EPI_BIAS and w % 4 == 0:
         return op.run(x, n, h, w, "bf16x3", in_layout=LAYOUT_NCHW, out_dtype=torch.float32)       # the dedicated 3 -> 128 kernel
-    if arm == "bf16x3" and in_layout == LAYOUT_NHWC and conv.in_channels % 64 == 0:
+    if arm == "bf16x3" and in_layout == LAYOUT_NHWC and conv.in_channels % 64 == 0 and conv.out_channels <= 1792:
         return op.run(to_pair(x), n, h, w, "bf16x3", out_layout=out_layout, out=out, out_c_total=out_c_total,
                       out_c_offset=out_c_offset, out_dtype=torch.float32)
     return op.run(x, n, h, w, PREC, in_layout=in_layout, out_layout=out_layout, out=out, out_c_total=out_c_total,
