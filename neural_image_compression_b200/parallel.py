@@ -113,12 +113,16 @@ class ShardedEvaluator:
             with torch.cuda.graph(g):
                 res = self._local(static_x)
             self.launches_per_step = int(lib.nic_launch_count() - n0)      # kernels of this library inside one replay
-            ent = (g, static_x, res)
+            # the gradients the capture produced: every replay rewrites THESE tensors, so .grad must point at them again after
+            # a replay (the all-reduce below re-points .grad at views of its averaged buckets)
+            ent = (g, static_x, res, [p.grad for p in self.model.parameters()])
             self._graphs[key] = ent
-        g, static_x, res = ent
+        g, static_x, res, static_grads = ent
         if static_x.data_ptr() != x_local.data_ptr():
             static_x.copy_(x_local, non_blocking=True)
         g.replay()
+        for p, sg in zip(self.model.parameters(), static_grads):
+            p.grad = sg
         return res
 
     def static_input(self, shape, device):
@@ -278,12 +282,16 @@ class ShardedTrainer:
                 res = self._forward_backward(static_x)
                 if fuse_adam:
                     self.optimizer.launch()                  # counter increment + update: the step count lives on the device
-            ent = (g, static_x, res)
+            # the gradients the capture produced: every replay rewrites THESE tensors, so .grad must point at them again after
+            # a replay (the all-reduce below re-points .grad at views of its averaged buckets)
+            ent = (g, static_x, res, [p.grad for p in self.model.parameters()])
             self._graphs[key] = ent
-        g, static_x, res = ent
+        g, static_x, res, static_grads = ent
         if static_x.data_ptr() != x_local.data_ptr():
             static_x.copy_(x_local, non_blocking=True)
         g.replay()
+        for p, sg in zip(self.model.parameters(), static_grads):
+            p.grad = sg
         if fuse_adam:
             self.optimizer.t += 1
             for p in self.model.parameters():                 # updated inside the replay: packed-weight caches key on _version
