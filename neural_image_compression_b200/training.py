@@ -326,196 +326,194 @@ def _forward_impl(model, x, noise_z, noise_y, lean, qmode: int = Q_NOISE, arm: O
     """The layer-by-layer forward (fp32 NHWC tensors between layers, layer inputs kept): -> (outputs tuple, saved state S).
     qmode = Q_NOISE is the training forward; Q_ROUND the evaluation forward of a model whose channel count the fused
     pair-tensor pipeline is not built for (Models.py uses it for M != 128 on the bf16x3 arm)."""
-    if True:
-        lib = _lib.load()
-        dev = x.device
-        B, _, H, W = x.shape
-        M, K = model.M, model.K
-        hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
-        S = {}
-        arm = arm or train_precision(model)
-        with torch.cuda.device(dev):
-            # g_a: conv (+ bias) -> u, kept for the GDN backward; GDN -> the next layer's input, kept for its weight gradient
-            a, h, w, layout = x, H, W, LAYOUT_NCHW
-            enc = model.encoder.ops
-            S["enc_in"], S["enc_u"] = [], []
-            for op in enc:
-                S["enc_in"].append((a, h, w, layout))
-                a = conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, in_layout=layout)
-                h, w = engine.conv_out_hw(op.conv, h, w)
-                if op.gdn is not None:
-                    u = a
-                    a, nrm = gdn_forward(arm, op.gdn, u, B, h, w)
-                    S["enc_u"].append((u, nrm))
-                else:
-                    S["enc_u"].append(None)
-                layout = LAYOUT_NHWC
-            y_nhwc = a
-            y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, qmode, noise_y, torch.float32)
-            # h_a (reads the unquantised y)
-            a, h, w = y_nhwc, hy, wy
-            S["ha_in"] = []
-            for op in model.hyper_encoder.ops:
-                S["ha_in"].append((a, h, w))
+    lib = _lib.load()
+    dev = x.device
+    B, _, H, W = x.shape
+    M, K = model.M, model.K
+    hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
+    S = {}
+    arm = arm or train_precision(model)
+    with torch.cuda.device(dev):
+        # g_a: conv (+ bias) -> u, kept for the GDN backward; GDN -> the next layer's input, kept for its weight gradient
+        a, h, w, layout = x, H, W, LAYOUT_NCHW
+        enc = model.encoder.ops
+        S["enc_in"], S["enc_u"] = [], []
+        for op in enc:
+            S["enc_in"].append((a, h, w, layout))
+            a = conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, in_layout=layout)
+            h, w = engine.conv_out_hw(op.conv, h, w)
+            if op.gdn is not None:
+                u = a
+                a, nrm = gdn_forward(arm, op.gdn, u, B, h, w)
+                S["enc_u"].append((u, nrm))
+            else:
+                S["enc_u"].append(None)
+            layout = LAYOUT_NHWC
+        y_nhwc = a
+        y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, qmode, noise_y, torch.float32)
+        # h_a (reads the unquantised y)
+        a, h, w = y_nhwc, hy, wy
+        S["ha_in"] = []
+        for op in model.hyper_encoder.ops:
+            S["ha_in"].append((a, h, w))
+            a = conv_forward(arm, op.conv, op.epilogue, a, B, h, w)
+            h, w = engine.conv_out_hw(op.conv, h, w)
+        z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, qmode, noise_z, torch.float32)
+        # h_s -> psi, context -> phi, both windows of `combined`
+        combined = _f32((B, hy, wy, 4 * M), dev)
+        a, h, w = z_in_nhwc, hz, wz
+        hs = model.hyper_decoder.ops
+        S["hs_in"] = []
+        for i, op in enumerate(hs):
+            S["hs_in"].append((a, h, w))
+            if i == len(hs) - 1:
+                conv_forward(arm, op.conv, op.epilogue, a, B, h, w, out=combined, out_c_total=4 * M, out_c_offset=2 * M)
+            else:
                 a = conv_forward(arm, op.conv, op.epilogue, a, B, h, w)
-                h, w = engine.conv_out_hw(op.conv, h, w)
-            z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, qmode, noise_z, torch.float32)
-            # h_s -> psi, context -> phi, both windows of `combined`
-            combined = _f32((B, hy, wy, 4 * M), dev)
-            a, h, w = z_in_nhwc, hz, wz
-            hs = model.hyper_decoder.ops
-            S["hs_in"] = []
-            for i, op in enumerate(hs):
-                S["hs_in"].append((a, h, w))
-                if i == len(hs) - 1:
-                    conv_forward(arm, op.conv, op.epilogue, a, B, h, w, out=combined, out_c_total=4 * M, out_c_offset=2 * M)
-                else:
-                    a = conv_forward(arm, op.conv, op.epilogue, a, B, h, w)
-                h, w = engine.conv_out_hw(op.conv, h, w)
-            masked = model.context_model.masked
-            masked.apply_mask_()
-            conv_forward(arm, masked, EPI_BIAS, y_in_nhwc, B, hy, wy, out=combined, out_c_total=4 * M, out_c_offset=0, mask_a=True)
-            ep = model.entropy_parameters.ops
-            e1 = conv_forward(arm, ep[0].conv, ep[0].epilogue, combined, B, hy, wy)
-            e2 = conv_forward(arm, ep[1].conv, ep[1].epilogue, e1, B, hy, wy)
-            raw = conv_forward(arm, ep[2].conv, ep[2].epilogue, e2, B, hy, wy, out_layout=LAYOUT_NCHW)
-            from .EntropyModels import gm_likelihood
-            ly = gm_likelihood(y_in, raw, M, K, Q_PASSTHRU, full=not lean, want_y_in=False)
-            _, p_z, logp_z, parts_z = model.factorized_entropy_model.likelihood(z_in, Q_PASSTHRU)
-            # g_s
-            a, h, w = y_in_nhwc, hy, wy
-            dec = model.decoder.ops
-            S["dec_in"], S["dec_u"] = [], []
-            for i, op in enumerate(dec):
-                last = i == len(dec) - 1
-                S["dec_in"].append((a, h, w))
-                a = conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC)
-                h, w = engine.conv_out_hw(op.conv, h, w)
-                if op.gdn is not None:
-                    u = a
-                    a, nrm = gdn_forward(arm, op.gdn, u, B, h, w)
-                    S["dec_u"].append((u, nrm))
-                else:
-                    S["dec_u"].append(None)
-            x_hat = a
-        S["arm"] = arm
-        S.update(combined=combined, e1=e1, e2=e2, raw=raw, y_in=y_in, y_in_nhwc=y_in_nhwc, z_in=z_in, z_in_nhwc=z_in_nhwc,
-                 fparams=model.factorized_entropy_model.packed(), shape=(B, H, W))
-        logp_y = ly["logp"]
-        extra = [] if lean else ([ly["mu"], ly["sigma"]] if K == 1 else [ly["weights"], ly["mus"], ly["sigmas"]])
-        nd = [y, y_in, z, z_in, p_z, ly["p"], ly["partials"], parts_z] + extra
-        return (x_hat, logp_y, logp_z, *nd), S
+            h, w = engine.conv_out_hw(op.conv, h, w)
+        masked = model.context_model.masked
+        masked.apply_mask_()
+        conv_forward(arm, masked, EPI_BIAS, y_in_nhwc, B, hy, wy, out=combined, out_c_total=4 * M, out_c_offset=0, mask_a=True)
+        ep = model.entropy_parameters.ops
+        e1 = conv_forward(arm, ep[0].conv, ep[0].epilogue, combined, B, hy, wy)
+        e2 = conv_forward(arm, ep[1].conv, ep[1].epilogue, e1, B, hy, wy)
+        raw = conv_forward(arm, ep[2].conv, ep[2].epilogue, e2, B, hy, wy, out_layout=LAYOUT_NCHW)
+        from .EntropyModels import gm_likelihood
+        ly = gm_likelihood(y_in, raw, M, K, Q_PASSTHRU, full=not lean, want_y_in=False)
+        _, p_z, logp_z, parts_z = model.factorized_entropy_model.likelihood(z_in, Q_PASSTHRU)
+        # g_s
+        a, h, w = y_in_nhwc, hy, wy
+        dec = model.decoder.ops
+        S["dec_in"], S["dec_u"] = [], []
+        for i, op in enumerate(dec):
+            last = i == len(dec) - 1
+            S["dec_in"].append((a, h, w))
+            a = conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC)
+            h, w = engine.conv_out_hw(op.conv, h, w)
+            if op.gdn is not None:
+                u = a
+                a, nrm = gdn_forward(arm, op.gdn, u, B, h, w)
+                S["dec_u"].append((u, nrm))
+            else:
+                S["dec_u"].append(None)
+        x_hat = a
+    S["arm"] = arm
+    S.update(combined=combined, e1=e1, e2=e2, raw=raw, y_in=y_in, y_in_nhwc=y_in_nhwc, z_in=z_in, z_in_nhwc=z_in_nhwc,
+             fparams=model.factorized_entropy_model.packed(), shape=(B, H, W))
+    logp_y = ly["logp"]
+    extra = [] if lean else ([ly["mu"], ly["sigma"]] if K == 1 else [ly["weights"], ly["mus"], ly["sigmas"]])
+    nd = [y, y_in, z, z_in, p_z, ly["p"], ly["partials"], parts_z] + extra
+    return (x_hat, logp_y, logp_z, *nd), S
 
 
 def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tensor]:
     """The hand-scheduled backward: {id(parameter): gradient} from the gradients of x_hat / logp_y / logp_z (any may be None)."""
-    if True:
-        lib = _lib.load()
-        B, H, W = S["shape"]
-        M, K = model.M, model.K
-        hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
-        dev = S["raw"].device
-        arm = S["arm"]
-        grads: Dict[int, torch.Tensor] = {}
+    lib = _lib.load()
+    B, H, W = S["shape"]
+    M, K = model.M, model.K
+    hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
+    dev = S["raw"].device
+    arm = S["arm"]
+    grads: Dict[int, torch.Tensor] = {}
 
-        def put(param, g):
-            grads[id(param)] = g if id(param) not in grads else grads[id(param)] + g
+    def put(param, g):
+        grads[id(param)] = g if id(param) not in grads else grads[id(param)] + g
 
-        with torch.cuda.device(dev), torch.no_grad():
-            d_yin = None                                             # NHWC gradient w.r.t. y_in, accumulated over its three consumers
-            # ---- g_s ------------------------------------------------------------------------------------------------
-            if g_xhat is not None:
-                g, g_layout = g_xhat.contiguous().float(), LAYOUT_NCHW
-                dec = model.decoder.ops
-                for i in range(len(dec) - 1, -1, -1):
-                    op = dec[i]
-                    a, h, w = S["dec_in"][i]
-                    ho, wo = engine.conv_out_hw(op.conv, h, w)
-                    if op.gdn is not None:
-                        g, dbeta, dgamma = gdn_bwd(op.gdn, S["dec_u"][i][0], g, B, ho, wo, norm=S["dec_u"][i][1])
-                        put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
-                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, g_layout, arm=arm)
-                    put(op.conv.weight, dw); put(op.conv.bias, db)
-                    g = conv_dgrad(op.conv, g, B, h, w, g_layout, arm=arm)
-                    g_layout = LAYOUT_NHWC
-                d_yin = g
-            # ---- p_y: likelihood, entropy parameters, context model, h_s --------------------------------------------
-            d_zin = None
-            if g_logp_y is not None:
-                gl = g_logp_y.contiguous().float()
-                dy_lik = torch.empty_like(S["y_in"])
-                draw = torch.empty_like(S["raw"])
-                check(lib.nic_gm_likelihood_bwd(ptr(S["y_in"]), ptr(S["raw"]), ptr(gl), 0.0, B, M, hy * wy, K, ptr(dy_lik), ptr(draw),
-                                                current_stream()), "nic_gm_likelihood_bwd")
-                d_yin = to_nhwc(dy_lik, accumulate_into=d_yin)
-                g = to_nhwc(draw)
-                ep = model.entropy_parameters.ops
-                for i, (op, a) in reversed(list(enumerate(zip(ep, (S["combined"], S["e1"], S["e2"]))))):
-                    dw, db = conv_wgrad(op.conv, a, g, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
-                    put(op.conv.weight, dw); put(op.conv.bias, db)
-                    if i > 0:
-                        g = lrelu_bwd_(conv_dgrad(op.conv, g, B, hy, wy, arm=arm), a)
-                w0 = ep[0].conv.weight.detach()
-                d_phi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, :2 * M].contiguous(), c_in=2 * M, arm=arm)
-                d_psi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, 2 * M:].contiguous(), c_in=2 * M, arm=arm)
-                masked = model.context_model.masked
-                dw, db = conv_wgrad(masked, S["y_in_nhwc"], d_phi, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
-                put(masked.weight, dw); put(masked.bias, db)
-                d_yin = add_(d_yin, conv_dgrad(masked, d_phi, B, hy, wy, arm=arm))
-                g = d_psi
-                hs = model.hyper_decoder.ops
-                for i in range(len(hs) - 1, -1, -1):
-                    op = hs[i]
-                    a, h, w = S["hs_in"][i]
-                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
-                    put(op.conv.weight, dw); put(op.conv.bias, db)
+    with torch.cuda.device(dev), torch.no_grad():
+        d_yin = None                                             # NHWC gradient w.r.t. y_in, accumulated over its three consumers
+        # ---- g_s ------------------------------------------------------------------------------------------------
+        if g_xhat is not None:
+            g, g_layout = g_xhat.contiguous().float(), LAYOUT_NCHW
+            dec = model.decoder.ops
+            for i in range(len(dec) - 1, -1, -1):
+                op = dec[i]
+                a, h, w = S["dec_in"][i]
+                ho, wo = engine.conv_out_hw(op.conv, h, w)
+                if op.gdn is not None:
+                    g, dbeta, dgamma = gdn_bwd(op.gdn, S["dec_u"][i][0], g, B, ho, wo, norm=S["dec_u"][i][1])
+                    put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
+                dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, g_layout, arm=arm)
+                put(op.conv.weight, dw); put(op.conv.bias, db)
+                g = conv_dgrad(op.conv, g, B, h, w, g_layout, arm=arm)
+                g_layout = LAYOUT_NHWC
+            d_yin = g
+        # ---- p_y: likelihood, entropy parameters, context model, h_s --------------------------------------------
+        d_zin = None
+        if g_logp_y is not None:
+            gl = g_logp_y.contiguous().float()
+            dy_lik = torch.empty_like(S["y_in"])
+            draw = torch.empty_like(S["raw"])
+            check(lib.nic_gm_likelihood_bwd(ptr(S["y_in"]), ptr(S["raw"]), ptr(gl), 0.0, B, M, hy * wy, K, ptr(dy_lik), ptr(draw),
+                                            current_stream()), "nic_gm_likelihood_bwd")
+            d_yin = to_nhwc(dy_lik, accumulate_into=d_yin)
+            g = to_nhwc(draw)
+            ep = model.entropy_parameters.ops
+            for i, (op, a) in reversed(list(enumerate(zip(ep, (S["combined"], S["e1"], S["e2"]))))):
+                dw, db = conv_wgrad(op.conv, a, g, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
+                put(op.conv.weight, dw); put(op.conv.bias, db)
+                if i > 0:
+                    g = lrelu_bwd_(conv_dgrad(op.conv, g, B, hy, wy, arm=arm), a)
+            w0 = ep[0].conv.weight.detach()
+            d_phi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, :2 * M].contiguous(), c_in=2 * M, arm=arm)
+            d_psi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, 2 * M:].contiguous(), c_in=2 * M, arm=arm)
+            masked = model.context_model.masked
+            dw, db = conv_wgrad(masked, S["y_in_nhwc"], d_phi, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
+            put(masked.weight, dw); put(masked.bias, db)
+            d_yin = add_(d_yin, conv_dgrad(masked, d_phi, B, hy, wy, arm=arm))
+            g = d_psi
+            hs = model.hyper_decoder.ops
+            for i in range(len(hs) - 1, -1, -1):
+                op = hs[i]
+                a, h, w = S["hs_in"][i]
+                dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
+                put(op.conv.weight, dw); put(op.conv.bias, db)
+                g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
+                if i > 0:
+                    g = lrelu_bwd_(g, a)                         # a = LeakyReLU output of layer i - 1
+            d_zin = g
+        # ---- p_z ----------------------------------------------------------------------------------------------------
+        if g_logp_z is not None:
+            gl = g_logp_z.contiguous().float()
+            fe = model.factorized_entropy_model
+            dz_fac = torch.empty_like(S["z_in"])
+            dpar = _f32((M, 43), dev)
+            check(lib.nic_factorized_likelihood_bwd(ptr(S["z_in"]), ptr(S["fparams"]), ptr(gl), 0.0, B, M, hz * wz, ptr(dz_fac),
+                                                    ptr(dpar), current_stream()), "nic_factorized_likelihood_bwd")
+            for name, idx, lo, hi in _FACT_SLICES:
+                prm = getattr(fe, name)[idx]
+                put(prm, dpar[:, lo:hi].reshape(prm.shape).contiguous())
+            d_zin = to_nhwc(dz_fac, accumulate_into=d_zin)
+        # ---- h_a (z_in = z + noise: the gradient passes unchanged) --------------------------------------------------
+        dy = d_yin
+        if d_zin is not None:
+            g = d_zin
+            ha = model.hyper_encoder.ops
+            for i in range(len(ha) - 1, -1, -1):
+                op = ha[i]
+                a, h, w = S["ha_in"][i]
+                dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
+                put(op.conv.weight, dw); put(op.conv.bias, db)
+                g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
+                if i > 0:
+                    g = lrelu_bwd_(g, a)
+            dy = g if dy is None else add_(dy, g)
+        # ---- g_a (y_in = y + noise) ---------------------------------------------------------------------------------
+        if dy is not None:
+            g = dy
+            enc = model.encoder.ops
+            for i in range(len(enc) - 1, -1, -1):
+                op = enc[i]
+                a, h, w, layout = S["enc_in"][i]
+                ho, wo = engine.conv_out_hw(op.conv, h, w)
+                if op.gdn is not None:
+                    g, dbeta, dgamma = gdn_bwd(op.gdn, S["enc_u"][i][0], g, B, ho, wo, norm=S["enc_u"][i][1])
+                    put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
+                dw, db = conv_wgrad(op.conv, a, g, B, h, w, layout, LAYOUT_NHWC, arm=arm)
+                put(op.conv.weight, dw); put(op.conv.bias, db)
+                if i > 0:
                     g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
-                    if i > 0:
-                        g = lrelu_bwd_(g, a)                         # a = LeakyReLU output of layer i - 1
-                d_zin = g
-            # ---- p_z ----------------------------------------------------------------------------------------------------
-            if g_logp_z is not None:
-                gl = g_logp_z.contiguous().float()
-                fe = model.factorized_entropy_model
-                dz_fac = torch.empty_like(S["z_in"])
-                dpar = _f32((M, 43), dev)
-                check(lib.nic_factorized_likelihood_bwd(ptr(S["z_in"]), ptr(S["fparams"]), ptr(gl), 0.0, B, M, hz * wz, ptr(dz_fac),
-                                                        ptr(dpar), current_stream()), "nic_factorized_likelihood_bwd")
-                for name, idx, lo, hi in _FACT_SLICES:
-                    prm = getattr(fe, name)[idx]
-                    put(prm, dpar[:, lo:hi].reshape(prm.shape).contiguous())
-                d_zin = to_nhwc(dz_fac, accumulate_into=d_zin)
-            # ---- h_a (z_in = z + noise: the gradient passes unchanged) --------------------------------------------------
-            dy = d_yin
-            if d_zin is not None:
-                g = d_zin
-                ha = model.hyper_encoder.ops
-                for i in range(len(ha) - 1, -1, -1):
-                    op = ha[i]
-                    a, h, w = S["ha_in"][i]
-                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
-                    put(op.conv.weight, dw); put(op.conv.bias, db)
-                    g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
-                    if i > 0:
-                        g = lrelu_bwd_(g, a)
-                dy = g if dy is None else add_(dy, g)
-            # ---- g_a (y_in = y + noise) ---------------------------------------------------------------------------------
-            if dy is not None:
-                g = dy
-                enc = model.encoder.ops
-                for i in range(len(enc) - 1, -1, -1):
-                    op = enc[i]
-                    a, h, w, layout = S["enc_in"][i]
-                    ho, wo = engine.conv_out_hw(op.conv, h, w)
-                    if op.gdn is not None:
-                        g, dbeta, dgamma = gdn_bwd(op.gdn, S["enc_u"][i][0], g, B, ho, wo, norm=S["enc_u"][i][1])
-                        put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
-                    dw, db = conv_wgrad(op.conv, a, g, B, h, w, layout, LAYOUT_NHWC, arm=arm)
-                    put(op.conv.weight, dw); put(op.conv.bias, db)
-                    if i > 0:
-                        g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
-        forget_pairs()
-        return grads
+    forget_pairs()
+    return grads
 
 
 class _TrainForward(torch.autograd.Function):

@@ -82,7 +82,7 @@ def test_training_step_matches_reference_golden(case, arm):
 
 
 @pytest.mark.parametrize("arm", ARMS)
-@pytest.mark.parametrize("K,shape", [(3, (2, 3, 128, 192)), (1, (3, 3, 64, 64))])
+@pytest.mark.parametrize("K,shape", [(3, (2, 3, 128, 192)), (1, (3, 3, 64, 64)), (2, (1, 3, 192, 64))])
 def test_every_gradient_tensor_against_the_oracle(K, shape, arm):
     """All 59 gradient tensors in full against the oracle's autograd on the same weights, input and noise."""
     from neural_image_compression_b200.RateDistortionLoss import rd_loss
