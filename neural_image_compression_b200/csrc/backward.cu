@@ -74,17 +74,20 @@ wgrad_kernel(const WgradParams p) {
   float ag[8];
   auto load_global = [&](int pk0) {
     if (GATHER) {
+      // this thread's eight pixels are pk, pk + 2, ...: decode the first one, then step (x, y, img) instead of dividing again
+      int pk = pk0 + (tid >> 7);
+      int img = pk / hw_s, rem = pk - img * hw_s;
+      int y = rem / p.ws, x = rem - y * p.ws;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int pk = pk0 + (tid >> 7) + 2 * j;
         float v = 0.f;
         if (g_ok && pk < p_end) {
-          const int img = pk / hw_s, rem = pk - img * hw_s;
-          const int y = rem / p.ws, x = rem - y * p.ws;
           const int by = y * p.stride + g_dy, bx = x * p.stride + g_dx;
           if (by >= 0 && by < p.hb && bx >= 0 && bx < p.wb) v = __ldg(p.big + img * p.bs_n + by * p.bs_h + bx * p.bs_w + g_coff);
         }
         ag[j] = p.a_square ? v * v : v;
+        pk += 2; x += 2;
+        while (x >= p.ws) { x -= p.ws; if (++y >= p.hs) { y = 0; ++img; } }
       }
     } else {
 #pragma unroll
