@@ -1,7 +1,8 @@
 /*
  * nic.h - C ABI of libnic_b200.so: hand-written sm_100a kernels for the forward pass
  * (+ likelihood / rate-distortion terms) of the hyperprior / autoregressive-context
- * image codec of achraf-15/neural_image_compression.
+ * image codec of achraf-15/neural_image_compression, and for its training step
+ * (the backward of that forward + Adam; section "training step" below).
  *
  * The reference has no FFI of its own (it is pure PyTorch); each entry below names the
  * reference Python call (file:line under /root/reference) whose arithmetic it replaces.

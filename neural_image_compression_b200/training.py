@@ -326,6 +326,7 @@ def _forward_impl(model, x, noise_z, noise_y, lean, qmode: int = Q_NOISE, arm: O
     """The layer-by-layer forward (fp32 NHWC tensors between layers, layer inputs kept): -> (outputs tuple, saved state S).
     qmode = Q_NOISE is the training forward; Q_ROUND the evaluation forward of a model whose channel count the fused
     pair-tensor pipeline is not built for (Models.py uses it for M != 128 on the bf16x3 arm)."""
+    engine.require_cuda(x, "x")
     lib = _lib.load()
     dev = x.device
     B, _, H, W = x.shape

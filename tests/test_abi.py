@@ -57,3 +57,25 @@ def test_product_path_fails_loudly_without_a_gpu():
     with pytest.raises(_lib.NicError):
         rd_loss({"x_hat": torch.rand(1, 3, 64, 64), "logp_y": torch.zeros(1, 1), "logp_z": torch.zeros(1, 1)},
                 torch.rand(1, 3, 64, 64), 0.005)
+
+
+def test_training_path_fails_loudly_without_a_gpu():
+    """model(x) with autograd on (the reference trainer's call) and the optimizer have no CPU path either."""
+    import pytest
+    import torch
+    from neural_image_compression_b200 import _lib
+    from neural_image_compression_b200.Models import JointAutoregressiveHierarchical
+    from neural_image_compression_b200.training import Adam, step_gradients
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    model = JointAutoregressiveHierarchical(128, K=1)
+    x = torch.rand(1, 3, 64, 64)
+    with pytest.raises(_lib.NicError):
+        model(x)                                   # training=True, grad enabled -> the differentiable path
+    with pytest.raises(_lib.NicError):
+        step_gradients(model, x, 0.005)
+    opt = Adam(model.parameters(), lr=1e-4)
+    for p in model.parameters():
+        p.grad = torch.zeros_like(p)
+    with pytest.raises(_lib.NicError):
+        opt.step()

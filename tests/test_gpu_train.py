@@ -241,3 +241,33 @@ def test_step_gradients_equals_autograd_backward():
     assert float(loss) == float(rd["loss"].detach())
     for k, p in model.named_parameters():
         assert torch.equal(p.grad, ref[k]), k
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_evaluation_after_training_sees_the_updated_weights(graph):
+    """The optimizer writes the parameters behind torch's back (nic_adam_multi_step, also from inside a graph replay): every derived
+    cache (packed conv weights of all arms, GDN tables, the factorized table, the masked taps) must follow.  After a few steps the
+    fused evaluation path must agree with the oracle run on the model's CURRENT state_dict."""
+    from neural_image_compression_b200 import parallel
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    model = H.seeded_model(128, 3, "calib", precision="bf16x3").cuda()
+    x = H.seeded_input((2, 3, 128, 128))
+    with torch.no_grad():
+        before = rd_loss(model(x.cuda(), training=False), x.cuda(), 0.005)["bpp_total"]       # fills the evaluation arm's caches
+    tr = parallel.ShardedTrainer(model, 0.005, lr=1e-4, graph=graph)
+    for _ in range(6):
+        tr.step(x.cuda())
+    torch.cuda.synchronize()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    assert float(sd["context_model.masked.weight"][:, :, 3:].abs().max()) > 0      # Adam moved the masked taps (as in the reference) ...
+    ref = O.forward(sd, x, 128, 3)
+    ref_rd = O.rd_loss(ref, x, 0.005)
+    band = abs(ref_rd["bpp_total"] - O.rd_loss(O.forward(sd, x, 128, 3, dtype=torch.float64), x, 0.005)["bpp_total"])   # conditioning of the moved weights
+    with torch.no_grad():
+        out = model(x.cuda(), training=False)
+        rd = rd_loss(out, x.cuda(), 0.005)
+    assert float(model.context_model.masked.weight.detach()[:, :, 3:].abs().max()) == 0     # ... and the forward zeroes them again (ContextModels.py:19)
+    real, ties = H.symbol_mismatches(out["y_in"].cpu().numpy(), ref["y_in"].numpy(), ref["y"].numpy(), 2e-3)
+    assert real == 0, (real, ties)
+    assert abs(rd["bpp_total"] - ref_rd["bpp_total"]) <= H.BPP_TOL + band and abs(rd["psnr"] - ref_rd["psnr"]) <= H.PSNR_TOL, (rd, ref_rd, band)
+    assert abs(rd["bpp_total"] - before) > 1e-3, "six steps at lr 1e-4 must have changed the rate"
