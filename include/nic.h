@@ -271,7 +271,7 @@ int nic_conv_wgrad(const nic_conv_desc* d, const float* x, const float* g, float
  * x_pair / g_pair are the NIC_DT_BF16X2 NHWC forms (nic_to_pair) of the layer input and of the output gradient; g (f32 NHWC) is
  * only read for db.  The contraction index is the pixel and both tensors are channels-contiguous, so TMA boxes of
  * [pixels][64 channels] are fed to the MMA as MN-major operands with no transposition (csrc/wgrad_tc.cu).
- * Built for c_in % 128 == 0, c_out % 128 == 0, square kernels, both tensors NHWC, >= 8 x 8 pixels on the smaller side:
+ * Built for c_in % 64 == 0, c_out % 64 == 0, square kernels, both tensors NHWC, >= 8 x 8 pixels on the smaller side:
  * nic_conv_wgrad_tc_workspace_bytes returns 0 for any other layer (use nic_conv_wgrad).
  */
 size_t nic_conv_wgrad_tc_workspace_bytes(const nic_conv_desc* d);

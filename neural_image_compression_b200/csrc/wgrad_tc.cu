@@ -144,11 +144,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_big, const __grid_consta
     const int quarter = warp & 3;
     const long mtot = static_cast<long>(p.ntaps) * p.cb;
     float* out = p.part + static_cast<long>(split) * mtot * p.cs;
+    const bool row_ok = m0 + quarter * 32 + lane < p.cb;           // half-full last M tile (channel counts that are 64 mod 128)
+    const int ncc = (p.cs - n0 >= 128) ? 4 : (p.cs - n0) / 32;     // half-full last N tile
     for (int t = 0; t < gtaps; ++t) {
       const int tap = p.g_tap[grp][t];
       float* row = out + (static_cast<long>(tap) * p.cb + m0 + quarter * 32 + lane) * p.cs + n0;
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int cc = 0; cc < ncc; ++cc) {
         float v[32];
         if (nkb > 0 && ok) {
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 128 + cc * 32, v);
@@ -157,8 +159,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_big, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
+        if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(row + cc * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(row + cc * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
       }
     }
   }
@@ -175,7 +179,7 @@ bool wgrad_tc_supported(const nic_conv_desc* d) {
   const bool tr = d->transposed != 0;
   const int cb = tr ? d->c_out : d->c_in, cs = tr ? d->c_in : d->c_out;
   const int hs = tr ? d->h_in : d->h_out, ws = tr ? d->w_in : d->w_out;
-  if (cb % 128 || cs % 128 || hs < 8 || ws < 8 || d->kh != d->kw) return false;
+  if (cb % 64 || cs % 64 || hs < 8 || ws < 8 || d->kh != d->kw) return false;     // 64-channel slabs; a last tile may be half full
   if (d->in_layout != NIC_LAYOUT_NHWC || d->out_layout != NIC_LAYOUT_NHWC || d->out_c_total != 0) return false;
   return true;
 }
@@ -218,7 +222,7 @@ static int plan_wgrad_tc(const nic_conv_desc* d, WgTcPlan* out) {
       if (cnt) p.g_ntaps[g++] = static_cast<int8_t>(cnt);
     }
   p.ngroups = g;
-  p.mtiles = p.cb / 128; p.ntiles = p.cs / 128;
+  p.mtiles = (p.cb + 127) / 128; p.ntiles = (p.cs + 127) / 128;       // a half-full last tile: its upper 64 rows / columns are not stored
   p.yblocks = (p.hs + 7) / 8; p.xblocks = (p.ws + 7) / 8;
   p.kblocks = p.n * p.yblocks * p.xblocks;
   const int base = p.ngroups * p.mtiles * p.ntiles;

@@ -173,7 +173,9 @@ def test_wgrad_tensor_core_kernel_against_float64_autograd():
     torch.manual_seed(4)
     cases = [(nn.Conv2d(128, 128, 1), 2, 16, 16), (nn.Conv2d(128, 128, 3, 1, 1), 2, 16, 24), (nn.Conv2d(128, 256, 5, 1, 2), 1, 16, 16),
              (nn.Conv2d(128, 128, 5, 2, 2), 2, 32, 48), (nn.ConvTranspose2d(128, 128, 5, 2, 2, 1), 2, 8, 16),
-             (nn.Conv2d(640, 1152, 1), 2, 8, 16), (nn.Conv2d(128, 128, 5, 2, 2), 3, 40, 24)]
+             (nn.Conv2d(640, 1152, 1), 2, 8, 16), (nn.Conv2d(128, 128, 5, 2, 2), 3, 40, 24),
+             (nn.ConvTranspose2d(128, 192, 5, 2, 2, 1), 1, 8, 16), (nn.Conv2d(192, 256, 3, 1, 1), 2, 16, 8), (nn.Conv2d(192, 192, 5, 2, 2), 1, 32, 32),
+             (nn.Conv2d(64, 128, 5, 1, 2), 1, 8, 8)]
     results = []
     for conv, n, h, w in cases:
         conv = conv.double()
