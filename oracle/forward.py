@@ -44,11 +44,12 @@ SIGMA_FLOOR = 1e-6           # ParametersModels.py:47,62
 
 
 DIFFERENTIABLE = False      # oracle/backward.py sets this while it builds an autograd graph over the parameters
+DEVICE = "cpu"              # tools/library_baseline.py sets "cuda" to time the same torch ops on the GPU (cuDNN / ATen eager)
 
 
 def _p(sd, key, dtype):
     t = sd[key] if DIFFERENTIABLE else sd[key].detach()
-    return t.to("cpu", dtype)
+    return t.to(DEVICE, dtype)
 
 
 def _gdn(sd, prefix, x, inverse, dtype):
@@ -203,12 +204,12 @@ def forward(sd, x, M: int, K: int, training: bool = False,
     ``training=True`` needs the two U(-0.5, 0.5) tensors injected (the reference draws the
     z noise before the y noise, Models.py:57-58).
     """
-    x = x.to("cpu", dtype)
+    x = x.to(DEVICE, dtype)
     y = analysis(sd, x, dtype)
     z = hyper_analysis(sd, y, dtype)
     if training:
-        z_in = z + noise_z.to(dtype)
-        y_in = y + noise_y.to(dtype)
+        z_in = z + noise_z.to(DEVICE, dtype)
+        y_in = y + noise_y.to(DEVICE, dtype)
     else:
         z_in = torch.round(z)
         y_in = torch.round(y)

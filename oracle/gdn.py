@@ -48,7 +48,7 @@ class LowerBoundFunction(torch.autograd.Function):
 
 
 def lower_bound(x, bound: float):
-    return LowerBoundFunction.apply(x, torch.tensor([float(bound)], dtype=x.dtype))
+    return LowerBoundFunction.apply(x, torch.tensor([float(bound)], dtype=x.dtype, device=x.device))
 
 
 def gdn_effective(beta_raw, gamma_raw, beta_min: float = 1e-6):
