@@ -353,6 +353,26 @@ int nic_adam_multi_step(float* const* p_host, const float* const* g_host, float*
 /* *counter += 1 on the device (stream-ordered, graph-capturable) */
 int nic_counter_increment(int32_t* counter, void* stream);
 
+/* ---- evaluator-side distortion metrics (Evaluator.py:26-53: compute_metrics on imgs and x_hat.clamp(0, 1)) -------------------- */
+
+/* mse_rgb_y [b][2] = per image: mean over (3, h, w) of (orig - recon)^2, and the same over the luma plane
+ * Y = 0.299 R + 0.587 G + 0.114 B (Evaluator.py:27-30, 34, 41-43); clamp01 = 1 clamps recon to [0, 1] on the fly (Evaluator.py:73).
+ * NCHW f32; partials [b][nic_partials_per_image()][2] scratch. */
+int nic_eval_mse(const float* orig, const float* recon, int32_t b, int32_t h, int32_t w, int32_t clamp01, float* mse_rgb_y, float* partials,
+                 void* stream);
+/* y [b][h][w] = luma of an NCHW RGB batch; clamp01 = 1 clamps the input to [0, 1] first */
+int nic_luma(const float* rgb, float* y, int32_t b, int32_t h, int32_t w, int32_t clamp01, void* stream);
+/*
+ * The five scales of pytorch_msssim.ms_ssim (11-tap Gaussian, sigma 1.5, valid convolution, 2x2 average pooling with padding
+ * size % 2 between scales; third-party package, absent here: the published algorithm restated - parity unpinned):
+ * level_means [5][planes][2] = (mean ssim, mean cs) of every scale for `planes` = b * c planes of h x w (f32, plane-contiguous).
+ * clamp_y = 1 clamps the second tensor to [0, 1] on the fly (x_hat.clamp(0, 1)).  ms_ssim of a plane =
+ * prod_{l<4} relu(cs_l)^w_l * relu(ssim_4)^w_4, w = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333); the smaller side must exceed 160.
+ */
+size_t nic_ms_ssim_workspace_bytes(int32_t planes, int32_t h, int32_t w);
+int nic_ms_ssim_levels(const float* x, const float* y, int32_t planes, int32_t h, int32_t w, float data_range, int32_t clamp_y,
+                       float* level_means, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

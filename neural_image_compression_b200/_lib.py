@@ -69,6 +69,10 @@ SIGNATURES = {
     "nic_sse_bwd": (C.c_int, [_vp, _vp, _i64, _f32, _vp, _vp]),
     "nic_add_inplace": (C.c_int, [_vp, _vp, _i64, _vp]),
     "nic_layout_convert": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "nic_eval_mse": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "nic_luma": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "nic_ms_ssim_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "nic_ms_ssim_levels": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _sz, _vp]),
     "nic_adam_multi_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
     "nic_counter_increment": (C.c_int, [_vp, _vp]),
     "nic_to_pair": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),

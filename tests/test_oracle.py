@@ -125,3 +125,19 @@ def test_training_step_oracle_matches_reference_gradients(case):
         np.testing.assert_allclose(new[k].reshape(-1)[idx].numpy(), g["psamp_" + k], rtol=1e-6, atol=2e-6, err_msg=k)
     w = grads["context_model.masked.weight"]
     assert float(w[:, :, 3:].abs().sum()) > 0, "masked taps carry gradient in the reference"
+
+
+def test_metrics_oracle_basic_properties():
+    """oracle/metrics.py (Evaluator.py:26-53 + the restated pytorch_msssim): identity, symmetry, monotonicity, luma weights."""
+    from oracle import metrics as OM
+    torch.manual_seed(0)
+    x = torch.rand(1, 3, 176, 208)
+    assert abs(float(OM.ms_ssim(x, x)) - 1.0) < 1e-6
+    y1, y2 = (x + 0.02 * torch.randn_like(x)).clamp(0, 1), (x + 0.1 * torch.randn_like(x)).clamp(0, 1)
+    a, b = float(OM.ms_ssim(y1, x)), float(OM.ms_ssim(y2, x))
+    assert 1.0 > a > b > 0.0 and abs(a - float(OM.ms_ssim(x, y1))) < 1e-6
+    m = OM.compute_metrics(x, y1)
+    assert abs(m["PSNR(RGB)"] - 10 * np.log10(1.0 / float(((x - y1) ** 2).mean()))) < 1e-9
+    assert torch.allclose(OM.rgb_to_luma(torch.ones(1, 3, 2, 2)), torch.ones(1, 2, 2))
+    g = OM._gauss()
+    assert abs(float(g.sum()) - 1.0) < 1e-6 and g.argmax() == 5 and g.numel() == 11
