@@ -2,26 +2,32 @@
 on the sm_100a kernels.
 
 The reference has no backward code of its own: its gradients are what torch autograd derives from Models.py:49-106 and
-RateDistortionLoss.py:5-49.  Here the whole model is ONE autograd node (``_TrainForward``): its forward is the fp32 arm of
-``JointAutoregressiveHierarchical.forward`` keeping the layer inputs, its backward is a hand-scheduled chain of C-ABI calls
-(include/nic.h, "training step" section):
+RateDistortionLoss.py:5-49.  Here the whole model is ONE autograd node (``_TrainForward``): its forward (``_forward_impl``) runs
+layer by layer with fp32 NHWC tensors in between and keeps the layer inputs, its backward (``_backward_impl``) is a hand-scheduled
+chain of C-ABI calls (include/nic.h, "training step" section):
 
     data gradient of a conv      nic_conv_fwd with the mirrored descriptor (Conv2d <-> ConvTranspose2d, same weight tensor)
-    weight / bias gradients      nic_conv_wgrad (all 25 taps of the masked conv: ContextModels.py:19 masks the data, not the graph)
-    GDN / IGDN                   nic_gdn_bwd (incl. compressai's LowerBound gradient rule on the stored parameters)
+    weight / bias gradients      nic_conv_wgrad_tc (tcgen05, MN-major operands) / nic_conv_wgrad (fp32) - all 25 taps of the masked
+                                 conv: ContextModels.py:19 masks the data, not the graph
+    GDN / IGDN                   nic_gdn_bwd, or nic_gdn_reparam / _apply / _bwd_prep / _bwd_finish around tensor-core contractions
+                                 (incl. compressai's LowerBound gradient rule on the stored parameters)
     LeakyReLU                    nic_lrelu_bwd
     likelihoods                  nic_gm_likelihood_bwd, nic_factorized_likelihood_bwd
     distortion                   nic_sse_bwd (``_RDLoss`` below is rd_loss's autograd node)
-    optimizer                    nic_adam_step (``Adam`` below: torch.optim.Adam semantics, Main.ipynb:133)
+    optimizer                    nic_adam_multi_step (``Adam`` below: torch.optim.Adam semantics, Main.ipynb:133; one launch)
+
+``step_gradients`` runs the same forward + loss + backward WITHOUT the autograd engine (calling thread, current stream): the form
+``parallel.ShardedTrainer(graph=True)`` captures in a CUDA graph.
 
 Differentiable outputs: ``x_hat``, ``logp_y``, ``logp_z`` (what rd_loss consumes).  The other dict entries are returned
 detached.
 
 Arithmetic arms of the step (``NIC_TRAIN_PRECISION`` or ``model.train_precision``):
-  "bf16x3" (default when every conv has c_in % 64 == 0, i.e. M = 128): the convolutions of the forward pass AND the data-gradient
-           convolutions run on the tcgen05 tensor cores with hi/lo-split bf16 operands (fp32 grade, the arm the evaluation path
-           uses); activations and gradients stay fp32 NHWC between layers and are split on the fly (nic_to_pair).  Weight
-           gradients, GDN, LeakyReLU and the likelihood chain run in fp32 on the CUDA cores.
+  "bf16x3" (default when M % 64 == 0): the convolutions of the forward pass, the data-gradient convolutions, the weight gradients
+           of every layer the kernel is built for and the GDN channel contractions run on the tcgen05 tensor cores with hi/lo-split
+           bf16 operands (fp32 grade, the arm the evaluation path uses); activations and gradients stay fp32 NHWC between layers and
+           are split on the fly (nic_to_pair, one conversion per tensor and step).  LeakyReLU, the remaining weight gradients and
+           the likelihood chain run in fp32 on the CUDA cores.
   "fp32":  everything on the CUDA cores; gradients within 5e-6 of the reference's autograd (tests/test_gpu_train.py).
 """
 from __future__ import annotations
