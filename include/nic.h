@@ -302,6 +302,11 @@ int nic_gdn_bwd(const float* u, const float* g, int32_t n, int32_t c, int32_t h,
  *                       dbeta_eff_in [c] (both or neither): the gradients w.r.t. the EFFECTIVE parameters when the caller has
  *                       already formed them (sum_pix t_i u_j^2 is the weight gradient of a 1x1 conv: nic_conv_wgrad_tc)
  */
+/* the two halves of nic_gdn_bwd_finish on their own (data path: du += 2 u r; parameter path: the LowerBound chain) - the
+ * training step runs the parameter path on a side stream */
+int nic_gdn_bwd_du(const float* u, const float* r, float* du, int64_t n, void* stream);
+int nic_gdn_reparam_bwd(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, const float* dbeta_eff,
+                        const float* dgamma_eff, float* dbeta_raw, float* dgamma_raw, void* stream);
 int nic_gdn_reparam(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, float* beta_eff, float* gamma_eff,
                     float* gamma_eff_t, void* stream);
 int nic_gdn_apply(const float* u, const float* norm, int64_t n, int32_t inverse, float* out, void* stream);

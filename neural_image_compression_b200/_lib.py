@@ -79,6 +79,8 @@ SIGNATURES = {
     "nic_gdn_reparam": (C.c_int, [_i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nic_gdn_apply": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "nic_gdn_bwd_prep": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "nic_gdn_bwd_du": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "nic_gdn_reparam_bwd": (C.c_int, [_i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nic_gdn_bwd_finish_workspace_bytes": (_sz, [_i64, _i32]),
     "nic_gdn_bwd_finish": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nic_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp]),

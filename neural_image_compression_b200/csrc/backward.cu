@@ -740,6 +740,26 @@ int nic_gdn_bwd_finish(const float* u, const float* t, const float* r, int64_t p
   return check_launch("gdn_reparam_bwd_kernel");
 }
 
+int nic_gdn_bwd_du(const float* u, const float* r, float* du, int64_t n, void* stream) {
+  if (int rc = nic_check_device()) return rc;
+  if (n < 0 || (n > 0 && (!u || !r || !du))) return fail(NIC_E_BADSHAPE, "gdn_bwd_du: bad arguments");
+  if (n == 0) return NIC_OK;
+  gdn_bwd_finish_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(u, r, du, n);
+  return check_launch("gdn_bwd_finish_kernel");
+}
+
+int nic_gdn_reparam_bwd(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, const float* dbeta_eff,
+                        const float* dgamma_eff, float* dbeta_raw, float* dgamma_raw, void* stream) {
+  if (int rc = nic_check_device()) return rc;
+  if (c < 1 || !beta_raw || !gamma_raw || !dbeta_eff || !dgamma_eff || !dbeta_raw || !dgamma_raw) return fail(NIC_E_BADSHAPE, "gdn_reparam_bwd: bad arguments");
+  const float pedestal = static_cast<float>(3.814697265625e-06 * 3.814697265625e-06);
+  const float beta_bound = static_cast<float>(sqrt(static_cast<double>(beta_min) + static_cast<double>(pedestal)));
+  const float gamma_bound = static_cast<float>(sqrt(static_cast<double>(pedestal)));
+  gdn_reparam_bwd_kernel<<<(c * c + 255) / 256, 256, 0, as_stream(stream)>>>(c, beta_bound, gamma_bound, beta_raw, gamma_raw, dbeta_eff, dgamma_eff,
+                                                                            dbeta_raw, dgamma_raw);
+  return check_launch("gdn_reparam_bwd_kernel");
+}
+
 int nic_sse_bwd(const float* x_hat, const float* x, int64_t n, float coef, float* g_x_hat, void* stream) {
   if (int rc = nic_check_device()) return rc;
   if (n < 0 || (n > 0 && (!x_hat || !x || !g_x_hat))) return fail(NIC_E_BADSHAPE, "sse_bwd: bad arguments");

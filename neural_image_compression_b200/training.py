@@ -45,6 +45,17 @@ from ._lib import (ConvDesc, DT_F32, EPI_BIAS, LAYOUT_NCHW, LAYOUT_NHWC, PREC_FP
 
 PREC = "fp32"
 WGRAD_TC = os.environ.get("NIC_WGRAD_TC", "1") != "0"      # tensor-core weight gradients in the bf16x3 arm (0: fp32 kernel everywhere)
+# weight gradients on a side stream: they are off the critical path (the data-gradient chain), and most kernels of a step at
+# 8 x 256 x 256 fill only part of the GPU - in a CUDA-graph capture the fork / join become parallel branches of the graph
+WGRAD_OVERLAP = os.environ.get("NIC_WGRAD_OVERLAP", "1") != "0"
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[idx]
 
 
 def train_precision(model) -> str:
@@ -66,8 +77,17 @@ def _ws(nbytes: int, dev):
 
 # ---- single backward ops ------------------------------------------------------------------------------------------
 
+def wgrad_on_tensor_cores(conv: nn.Module, n: int, h: int, w: int, in_layout: int, out_layout: int, arm: str) -> bool:
+    """Whether conv_wgrad will take the tensor-core kernel for this layer (then it consumes the pair forms of x and g)."""
+    if arm != "bf16x3" or not WGRAD_TC:
+        return False
+    d = engine.ConvOp(conv).desc(n, h, w, PREC, in_layout, out_layout, DT_F32, DT_F32)
+    d.mask_a = 0
+    return _lib.load().nic_conv_wgrad_tc_workspace_bytes(C.byref(d)) > 0
+
+
 def conv_wgrad(conv: nn.Module, x: torch.Tensor, g: torch.Tensor, n: int, h: int, w: int, in_layout: int, out_layout: int,
-               arm: str = "fp32"):
+               arm: str = "fp32", pairs=None):
     """(dW in the reference layout, db) of one layer; x = forward input, g = gradient w.r.t. the conv output.
     bf16x3 arm: the tensor-core kernel (nic_conv_wgrad_tc) for the layer shapes it is built for, else the fp32 kernel."""
     lib = _lib.load()
@@ -80,7 +100,7 @@ def conv_wgrad(conv: nn.Module, x: torch.Tensor, g: torch.Tensor, n: int, h: int
         nbytes = lib.nic_conv_wgrad_tc_workspace_bytes(C.byref(d))
         if nbytes:
             ws = _ws(nbytes, x.device)
-            xp, gp = to_pair(x), to_pair(g)            # named: a temporary would be freed (and its memory reused) before the launch
+            xp, gp = pairs if pairs is not None else (to_pair(x), to_pair(g))   # named: a temporary would be freed before the launch
             check(lib.nic_conv_wgrad_tc(C.byref(d), ptr(xp), ptr(gp), ptr(g), ptr(dw), ptr(db), ptr(ws), ws.numel(),
                                         current_stream()), "nic_conv_wgrad_tc")
             return dw, db
@@ -270,7 +290,8 @@ def lrelu_bwd_(g: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return g
 
 
-def gdn_bwd(gdn: nn.Module, u: torch.Tensor, g: torch.Tensor, n: int, h: int, w: int, norm: Optional[torch.Tensor] = None):
+def gdn_bwd(gdn: nn.Module, u: torch.Tensor, g: torch.Tensor, n: int, h: int, w: int, norm: Optional[torch.Tensor] = None,
+            side=None, keep: Optional[list] = None):
     """(du, dbeta, dgamma): u = the conv output before the GDN (NHWC f32), g = gradient w.r.t. the GDN output.
     With the forward's `norm` (bf16x3 arm) the gamma^T . t contraction runs on the tensor cores."""
     lib = _lib.load()
@@ -289,6 +310,23 @@ def gdn_bwd(gdn: nn.Module, u: torch.Tensor, g: torch.Tensor, n: int, h: int, w:
         dge = dbe = None
         d = st["norm_op"].desc(n, h, w, PREC, LAYOUT_NHWC, LAYOUT_NHWC, DT_F32, DT_F32)
         nb = lib.nic_conv_wgrad_tc_workspace_bytes(C.byref(d)) if WGRAD_TC else 0
+        if nb and side is not None:
+            # data path on this stream: du += 2 u r.  Parameter path (gamma / beta gradients + LowerBound chain) on the side stream.
+            u2p = to_pair(u, square=True)
+            check(lib.nic_gdn_bwd_du(ptr(u), ptr(r), ptr(du), u.numel(), current_stream()), "nic_gdn_bwd_du")
+            main = torch.cuda.current_stream(u.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dge, dbe = _f32((c, c), u.device), _f32(c, u.device)
+                wws = _ws(nb, u.device)
+                check(lib.nic_conv_wgrad_tc(C.byref(d), ptr(u2p), ptr(tp), ptr(t), ptr(dge), ptr(dbe), ptr(wws), wws.numel(), current_stream()),
+                      "nic_conv_wgrad_tc")
+                check(lib.nic_gdn_reparam_bwd(c, float(gdn.beta_min), ptr(gdn.beta.detach().float().contiguous()),
+                                              ptr(gdn.gamma.detach().float().contiguous()), ptr(dbe), ptr(dge), ptr(dbeta), ptr(dgamma),
+                                              current_stream()), "nic_gdn_reparam_bwd")
+            if keep is not None:
+                keep.extend((u, t, tp, u2p, dge, dbe))
+            return du, dbeta, dgamma
         if nb:
             dge, dbe = _f32((c, c), u.device), _f32(c, u.device)
             wws = _ws(nb, u.device)
@@ -426,6 +464,22 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tens
     def put(param, g):
         grads[id(param)] = g if id(param) not in grads else grads[id(param)] + g
 
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev) if WGRAD_OVERLAP else None
+    keep = []                      # tensors the side stream reads: held until the join so the allocator cannot recycle them early
+
+    def conv_wgrad_async(conv, a, g, n, h, w, in_layout, out_layout, arm="fp32"):
+        """conv_wgrad on the side stream.  The pair forms are made on the MAIN stream first (the data-gradient conv of the same
+        layer reuses them from the memo), then the side stream waits for everything main has enqueued so far."""
+        if side is None:
+            return conv_wgrad(conv, a, g, n, h, w, in_layout, out_layout, arm=arm)
+        pairs = (to_pair(a), to_pair(g)) if wgrad_on_tensor_cores(conv, n, h, w, in_layout, out_layout, arm) else None
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            out = conv_wgrad(conv, a, g, n, h, w, in_layout, out_layout, arm=arm, pairs=pairs)
+        keep.extend((a, g, pairs))
+        return out
+
     with torch.cuda.device(dev), torch.no_grad():
         d_yin = None                                             # NHWC gradient w.r.t. y_in, accumulated over its three consumers
         # ---- g_s ------------------------------------------------------------------------------------------------
@@ -437,9 +491,9 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tens
                 a, h, w = S["dec_in"][i]
                 ho, wo = engine.conv_out_hw(op.conv, h, w)
                 if op.gdn is not None:
-                    g, dbeta, dgamma = gdn_bwd(op.gdn, S["dec_u"][i][0], g, B, ho, wo, norm=S["dec_u"][i][1])
+                    g, dbeta, dgamma = gdn_bwd(op.gdn, S["dec_u"][i][0], g, B, ho, wo, norm=S["dec_u"][i][1], side=side, keep=keep)
                     put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
-                dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, g_layout, arm=arm)
+                dw, db = conv_wgrad_async(op.conv, a, g, B, h, w, LAYOUT_NHWC, g_layout, arm=arm)
                 put(op.conv.weight, dw); put(op.conv.bias, db)
                 g = conv_dgrad(op.conv, g, B, h, w, g_layout, arm=arm)
                 g_layout = LAYOUT_NHWC
@@ -456,7 +510,7 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tens
             g = to_nhwc(draw)
             ep = model.entropy_parameters.ops
             for i, (op, a) in reversed(list(enumerate(zip(ep, (S["combined"], S["e1"], S["e2"]))))):
-                dw, db = conv_wgrad(op.conv, a, g, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
+                dw, db = conv_wgrad_async(op.conv, a, g, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
                 put(op.conv.weight, dw); put(op.conv.bias, db)
                 if i > 0:
                     g = lrelu_bwd_(conv_dgrad(op.conv, g, B, hy, wy, arm=arm), a)
@@ -464,7 +518,7 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tens
             d_phi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, :2 * M].contiguous(), c_in=2 * M, arm=arm)
             d_psi = conv_dgrad(ep[0].conv, g, B, hy, wy, weight=w0[:, 2 * M:].contiguous(), c_in=2 * M, arm=arm)
             masked = model.context_model.masked
-            dw, db = conv_wgrad(masked, S["y_in_nhwc"], d_phi, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
+            dw, db = conv_wgrad_async(masked, S["y_in_nhwc"], d_phi, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
             put(masked.weight, dw); put(masked.bias, db)
             d_yin = add_(d_yin, conv_dgrad(masked, d_phi, B, hy, wy, arm=arm))
             g = d_psi
@@ -472,7 +526,7 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tens
             for i in range(len(hs) - 1, -1, -1):
                 op = hs[i]
                 a, h, w = S["hs_in"][i]
-                dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
+                dw, db = conv_wgrad_async(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
                 put(op.conv.weight, dw); put(op.conv.bias, db)
                 g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
                 if i > 0:
@@ -498,7 +552,7 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tens
             for i in range(len(ha) - 1, -1, -1):
                 op = ha[i]
                 a, h, w = S["ha_in"][i]
-                dw, db = conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
+                dw, db = conv_wgrad_async(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
                 put(op.conv.weight, dw); put(op.conv.bias, db)
                 g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
                 if i > 0:
@@ -513,12 +567,15 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tens
                 a, h, w, layout = S["enc_in"][i]
                 ho, wo = engine.conv_out_hw(op.conv, h, w)
                 if op.gdn is not None:
-                    g, dbeta, dgamma = gdn_bwd(op.gdn, S["enc_u"][i][0], g, B, ho, wo, norm=S["enc_u"][i][1])
+                    g, dbeta, dgamma = gdn_bwd(op.gdn, S["enc_u"][i][0], g, B, ho, wo, norm=S["enc_u"][i][1], side=side, keep=keep)
                     put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
-                dw, db = conv_wgrad(op.conv, a, g, B, h, w, layout, LAYOUT_NHWC, arm=arm)
+                dw, db = conv_wgrad_async(op.conv, a, g, B, h, w, layout, LAYOUT_NHWC, arm=arm)
                 put(op.conv.weight, dw); put(op.conv.bias, db)
                 if i > 0:
                     g = conv_dgrad(op.conv, g, B, h, w, arm=arm)
+    if side is not None:
+        main.wait_stream(side)     # join: every weight gradient is complete before the caller (optimizer, all-reduce) reads it
+    keep.clear()
     forget_pairs()
     return grads
 
