@@ -45,14 +45,25 @@ from ._lib import (ConvDesc, DT_F32, EPI_BIAS, LAYOUT_NCHW, LAYOUT_NHWC, PREC_FP
 
 PREC = "fp32"
 WGRAD_TC = os.environ.get("NIC_WGRAD_TC", "1") != "0"      # tensor-core weight gradients in the bf16x3 arm (0: fp32 kernel everywhere)
-# weight gradients on a side stream: they are off the critical path (the data-gradient chain), and most kernels of a step at
-# 8 x 256 x 256 fill only part of the GPU - in a CUDA-graph capture the fork / join become parallel branches of the graph
-WGRAD_OVERLAP = os.environ.get("NIC_WGRAD_OVERLAP", "1") != "0"
-_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+# Branch parallelism of the step: weight gradients (off the critical path of the data-gradient chain) on one side stream, g_s and
+# its backward (independent of the entropy path between y_in and the merge of the y gradients) on another.  Most kernels of a step
+# at 8 x 256 x 256 fill only part of the GPU; in a CUDA-graph capture the forks / joins become parallel branches of the graph
+# (4.98 -> 3.86 ms per step).  Launched eagerly the step is host-bound and the extra event traffic only costs (7.7 -> 14.7 ms), so
+# "auto" forks only while a capture is under way; NIC_STEP_OVERLAP = 0 / 1 forces it off / on.
+_OVERLAP_ENV = os.environ.get("NIC_STEP_OVERLAP", "auto")
 
 
-def _side_stream(dev) -> "torch.cuda.Stream":
-    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+def _overlap() -> bool:
+    if _OVERLAP_ENV == "auto":
+        return torch.cuda.is_current_stream_capturing()
+    return _OVERLAP_ENV != "0"
+_SIDE_STREAMS: Dict[tuple, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(dev, which: int = 0) -> "torch.cuda.Stream":
+    """which = 0: the weight-gradient stream; 1: the synthesis-transform branch (g_s and its backward are independent of the
+    entropy path between y_in and the merge of the y gradients)."""
+    idx = (dev.index if dev.index is not None else torch.cuda.current_device(), which)
     if idx not in _SIDE_STREAMS:
         _SIDE_STREAMS[idx] = torch.cuda.Stream(device=dev)
     return _SIDE_STREAMS[idx]
@@ -396,6 +407,32 @@ def _forward_impl(model, x, noise_z, noise_y, lean, qmode: int = Q_NOISE, arm: O
             layout = LAYOUT_NHWC
         y_nhwc = a
         y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, qmode, noise_y, torch.float32)
+        def synthesis():
+            a, h, w = y_in_nhwc, hy, wy
+            dec = model.decoder.ops
+            S["dec_in"], S["dec_u"] = [], []
+            for i, op in enumerate(dec):
+                last = i == len(dec) - 1
+                S["dec_in"].append((a, h, w))
+                a = conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC)
+                h, w = engine.conv_out_hw(op.conv, h, w)
+                if op.gdn is not None:
+                    u = a
+                    a, nrm = gdn_forward(arm, op.gdn, u, B, h, w)
+                    S["dec_u"].append((u, nrm))
+                else:
+                    S["dec_u"].append(None)
+            return a
+        # g_s reads only y_in: it runs as its own branch (a second stream; a parallel branch of a captured graph) beside the
+        # entropy path h_a -> h_s -> context -> entropy parameters -> likelihoods
+        main = torch.cuda.current_stream(dev)
+        branch = _side_stream(dev, 1) if _overlap() else None
+        if branch is not None:
+            if arm == "bf16x3":
+                to_pair(y_in_nhwc)               # both branches consume the pair form: make it before the fork
+            branch.wait_stream(main)
+            with torch.cuda.stream(branch):
+                x_hat = synthesis()
         # h_a (reads the unquantised y)
         a, h, w = y_nhwc, hy, wy
         S["ha_in"] = []
@@ -426,22 +463,10 @@ def _forward_impl(model, x, noise_z, noise_y, lean, qmode: int = Q_NOISE, arm: O
         from .EntropyModels import gm_likelihood
         ly = gm_likelihood(y_in, raw, M, K, Q_PASSTHRU, full=not lean, want_y_in=False)
         _, p_z, logp_z, parts_z = model.factorized_entropy_model.likelihood(z_in, Q_PASSTHRU)
-        # g_s
-        a, h, w = y_in_nhwc, hy, wy
-        dec = model.decoder.ops
-        S["dec_in"], S["dec_u"] = [], []
-        for i, op in enumerate(dec):
-            last = i == len(dec) - 1
-            S["dec_in"].append((a, h, w))
-            a = conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC)
-            h, w = engine.conv_out_hw(op.conv, h, w)
-            if op.gdn is not None:
-                u = a
-                a, nrm = gdn_forward(arm, op.gdn, u, B, h, w)
-                S["dec_u"].append((u, nrm))
-            else:
-                S["dec_u"].append(None)
-        x_hat = a
+        if branch is not None:
+            main.wait_stream(branch)
+        else:
+            x_hat = synthesis()
     S["arm"] = arm
     S.update(combined=combined, e1=e1, e2=e2, raw=raw, y_in=y_in, y_in_nhwc=y_in_nhwc, z_in=z_in, z_in_nhwc=z_in_nhwc,
              fparams=model.factorized_entropy_model.packed(), shape=(B, H, W))
@@ -465,39 +490,46 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tens
         grads[id(param)] = g if id(param) not in grads else grads[id(param)] + g
 
     main = torch.cuda.current_stream(dev)
-    side = _side_stream(dev) if WGRAD_OVERLAP else None
+    side = _side_stream(dev) if _overlap() else None
     keep = []                      # tensors the side stream reads: held until the join so the allocator cannot recycle them early
 
     def conv_wgrad_async(conv, a, g, n, h, w, in_layout, out_layout, arm="fp32"):
-        """conv_wgrad on the side stream.  The pair forms are made on the MAIN stream first (the data-gradient conv of the same
-        layer reuses them from the memo), then the side stream waits for everything main has enqueued so far."""
+        """conv_wgrad on the side stream.  The pair forms are made on the CURRENT stream first (the data-gradient conv of the same
+        layer reuses them from the memo), then the side stream waits for everything that stream has enqueued so far."""
         if side is None:
             return conv_wgrad(conv, a, g, n, h, w, in_layout, out_layout, arm=arm)
         pairs = (to_pair(a), to_pair(g)) if wgrad_on_tensor_cores(conv, n, h, w, in_layout, out_layout, arm) else None
-        side.wait_stream(main)
+        side.wait_stream(torch.cuda.current_stream(dev))           # the producing stream: main, or the g_s branch
         with torch.cuda.stream(side):
             out = conv_wgrad(conv, a, g, n, h, w, in_layout, out_layout, arm=arm, pairs=pairs)
         keep.extend((a, g, pairs))
         return out
 
     with torch.cuda.device(dev), torch.no_grad():
-        d_yin = None                                             # NHWC gradient w.r.t. y_in, accumulated over its three consumers
+        d_yin = None                                             # NHWC gradient w.r.t. y_in from the entropy path (likelihood, context)
+        d_yin_gs = None                                          # ... and from g_s, whose backward runs as its own branch
+        branch = _side_stream(dev, 1) if (_overlap() and g_xhat is not None) else None
         # ---- g_s ------------------------------------------------------------------------------------------------
         if g_xhat is not None:
-            g, g_layout = g_xhat.contiguous().float(), LAYOUT_NCHW
-            dec = model.decoder.ops
-            for i in range(len(dec) - 1, -1, -1):
-                op = dec[i]
-                a, h, w = S["dec_in"][i]
-                ho, wo = engine.conv_out_hw(op.conv, h, w)
-                if op.gdn is not None:
-                    g, dbeta, dgamma = gdn_bwd(op.gdn, S["dec_u"][i][0], g, B, ho, wo, norm=S["dec_u"][i][1], side=side, keep=keep)
-                    put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
-                dw, db = conv_wgrad_async(op.conv, a, g, B, h, w, LAYOUT_NHWC, g_layout, arm=arm)
-                put(op.conv.weight, dw); put(op.conv.bias, db)
-                g = conv_dgrad(op.conv, g, B, h, w, g_layout, arm=arm)
-                g_layout = LAYOUT_NHWC
-            d_yin = g
+            import contextlib
+            if branch is not None:
+                branch.wait_stream(main)
+            with (torch.cuda.stream(branch) if branch is not None else contextlib.nullcontext()):
+                g, g_layout = g_xhat.contiguous().float(), LAYOUT_NCHW
+                dec = model.decoder.ops
+                for i in range(len(dec) - 1, -1, -1):
+                    op = dec[i]
+                    a, h, w = S["dec_in"][i]
+                    ho, wo = engine.conv_out_hw(op.conv, h, w)
+                    if op.gdn is not None:
+                        g, dbeta, dgamma = gdn_bwd(op.gdn, S["dec_u"][i][0], g, B, ho, wo, norm=S["dec_u"][i][1], side=side, keep=keep)
+                        put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
+                    dw, db = conv_wgrad_async(op.conv, a, g, B, h, w, LAYOUT_NHWC, g_layout, arm=arm)
+                    put(op.conv.weight, dw); put(op.conv.bias, db)
+                    keep.append(g)
+                    g = conv_dgrad(op.conv, g, B, h, w, g_layout, arm=arm)
+                    g_layout = LAYOUT_NHWC
+                d_yin_gs = g
         # ---- p_y: likelihood, entropy parameters, context model, h_s --------------------------------------------
         d_zin = None
         if g_logp_y is not None:
@@ -558,6 +590,11 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tens
                 if i > 0:
                     g = lrelu_bwd_(g, a)
             dy = g if dy is None else add_(dy, g)
+        # ---- merge the branches: dy = d(entropy path) + d(h_a) + d(g_s) ---------------------------------------------------------
+        if branch is not None:
+            main.wait_stream(branch)
+        if d_yin_gs is not None:
+            dy = d_yin_gs if dy is None else add_(dy, d_yin_gs)
         # ---- g_a (y_in = y + noise) ---------------------------------------------------------------------------------
         if dy is not None:
             g = dy
