@@ -141,11 +141,14 @@ class ShardedEvaluator:
         copy_stream = torch.cuda.Stream(device=dev)
         it = iter(host_batches)
         staging, ready = [None, None], [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [None, None]                          # recorded on the compute stream once a step has been queued on the slot
 
         def upload(slot, hb):
             if staging[slot] is None or staging[slot].shape != hb.shape:
                 staging[slot] = torch.empty(hb.shape, dtype=torch.float32, device=dev)
             with torch.cuda.stream(copy_stream):
+                if consumed[slot] is not None:
+                    copy_stream.wait_event(consumed[slot])       # the step that read this slot may still be running
                 staging[slot].copy_(hb, non_blocking=True)
                 ready[slot].record(copy_stream)
 
@@ -153,6 +156,12 @@ class ShardedEvaluator:
         if nxt is None:
             return
         upload(0, nxt)
+        # results come back through two pinned buffers: the device -> host copy of batch i is queued behind its kernels and
+        # read one iteration later, so the host queues batch i + 1 before it blocks on batch i (the device never idles
+        # between batches; every batch still pays its own host -> device copy and device -> host read)
+        res_host = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+        res_done = [torch.cuda.Event(), torch.cuda.Event()]
+        pending = None
         i = 0
         while nxt is not None:
             cur = i & 1
@@ -161,8 +170,18 @@ class ShardedEvaluator:
                 upload(cur ^ 1, nxt)                    # overlaps the step below; slot cur^1 was consumed two steps ago
             torch.cuda.current_stream().wait_event(ready[cur])
             _, terms = self.step(staging[cur])
-            yield terms["scalars"].tolist()             # device -> host read of this batch's result (synchronises)
+            if consumed[cur] is None:
+                consumed[cur] = torch.cuda.Event()
+            consumed[cur].record()
+            res_host[cur].copy_(terms["scalars"], non_blocking=True)
+            res_done[cur].record()
+            if pending is not None:
+                res_done[pending].synchronize()
+                yield res_host[pending].tolist()
+            pending = cur
             i += 1
+        res_done[pending].synchronize()
+        yield res_host[pending].tolist()
 
     @torch.no_grad()
     def step(self, x_local: torch.Tensor):
