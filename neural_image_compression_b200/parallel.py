@@ -263,6 +263,7 @@ class ShardedTrainer:
         from .training import Adam
         self.model, self.lambda_rd, self.group, self.graph = model, lambda_rd, group, graph
         self.optimizer = optimizer if optimizer is not None else Adam(model.parameters(), lr=lr)
+        self._scalable = type(model).__name__ == "ScalableImageCoding"
         self.buckets = grad_buckets(model.parameters(), bucket_bytes)
         self._flats = [None] * len(self.buckets)
         self._graphs = {}
@@ -274,8 +275,12 @@ class ShardedTrainer:
     def _forward_backward(self, x_local, noise=None):
         """forward + loss + backward on the calling thread and stream (training.step_gradients: the same kernels loss.backward()
         runs, without the autograd engine, whose device thread cannot take part in a stream capture)."""
-        from .training import step_gradients
         self.optimizer.zero_grad()
+        if self._scalable:                                   # two-head model, vision_rd_loss (training_scalable.py)
+            from .training_scalable import step_gradients as scalable_step
+            loss, terms = scalable_step(self.model, x_local, self.lambda_rd, noise=noise)
+            return loss, None, torch.stack([terms[k] for k in ("bpp_y1", "bpp_y2", "bpp_z", "mse", "psnr", "loss")])
+        from .training import step_gradients
         return step_gradients(self.model, x_local, self.lambda_rd, noise=noise)
 
     def _graphed(self, x_local):
@@ -320,13 +325,17 @@ class ShardedTrainer:
         return res, fuse_adam
 
     def step(self, x_local: torch.Tensor, noise=None) -> dict:
-        if self.graph and noise is None:
-            (loss, per_image, scalars), adam_done = self._graphed(x_local)
+        if (self.graph and noise is None) or self._scalable:
+            if self.graph and noise is None:
+                (loss, per_image, scalars), adam_done = self._graphed(x_local)
+            else:
+                (loss, per_image, scalars), adam_done = self._forward_backward(x_local, noise), False
             allreduce_gradients(self.buckets, self.group, self._flats)
             if not adam_done:
                 self.optimizer.step()
             self.step_count += 1
-            return {"loss": loss, "scalars": scalars, "mse_per_image": per_image[2]}
+            # scalars: the 8 rd scalars of nic_rd_finalize; ScalableImageCoding: (bpp_y1, bpp_y2, bpp_z, mse, psnr, loss)
+            return {"loss": loss, "scalars": scalars, "mse_per_image": None if per_image is None else per_image[2]}
         from .RateDistortionLoss import rd_loss
         self.optimizer.zero_grad()
         out = self.model(x_local, training=True, noise=noise, lean=True)

@@ -1,0 +1,215 @@
+"""Training step of ``ScalableImageCoding`` (reference Models.py:208-338 with the repairs of SURVEY.md section 2.4, loss
+``vision_rd_loss`` of RateDistortionLoss.py:52-121 with V = None): forward with noise, loss, hand-written backward.
+
+Same kernels and helpers as training.py; what differs from the single-head model is the split of y into a base part (M1 channels)
+and an enhancement part (M - M1), each with its own (context model, entropy-parameter net) over the SHARED hyper features psi:
+the psi gradient is the sum over the two heads, the y gradient of the entropy path is the channel concatenation of the heads'.
+The step runs on the calling thread (``step_gradients``; no autograd node): gradients are accumulated into ``.grad`` like
+``loss.backward()`` would, ``training.Adam`` / ``torch.optim.Adam`` step them.  Oracle: torch autograd over
+``oracle.forward.forward_scalable`` + ``vision_rd_loss`` (``oracle/backward.py: loss_and_grads_scalable``); the reference itself
+has no runnable forward for this class, so parity is against that repaired restatement (parity unpinned by the reference).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+from . import _lib, engine
+from . import training as T
+from ._lib import EPI_BIAS, LAYOUT_NCHW, LAYOUT_NHWC, Q_NOISE, Q_PASSTHRU, check, current_stream, ptr
+
+
+@torch.no_grad()
+def step_gradients(model, x: torch.Tensor, lambda_rd: float, noise=None):
+    """One training step's forward + vision_rd_loss + backward.  Returns (loss [device scalar], terms dict of device scalars)."""
+    from .EntropyModels import gm_likelihood
+    from .RateDistortionLoss import _logp_partials  # noqa: F401  (same partial-sum layout)
+    engine.require_cuda(x, "x")
+    lib = _lib.load()
+    dev = x.device
+    x = x.contiguous().float()
+    B, _, H, W = x.shape
+    M, M1, M2, K = model.M, model.M1, model.M2, model.K
+    hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
+    arm = T.train_precision(model)
+    if noise is not None:
+        noise_z, noise_y = noise
+    else:
+        noise_z = torch.rand((B, M, hz, wz), device=dev) - 0.5
+        noise_y = torch.rand((B, M, hy, wy), device=dev) - 0.5
+    heads = ((model.context_model_1, model.entropy_parameters_1, 0, M1), (model.context_model_2, model.entropy_parameters_2, M1, M))
+    T.forget_pairs()
+    grads: Dict[int, torch.Tensor] = {}
+
+    def put(param, g):
+        grads[id(param)] = g if id(param) not in grads else grads[id(param)] + g
+
+    with torch.cuda.device(dev):
+        # ---------------------------------------------------------------- forward ----------------------------------------------
+        a, h, w, layout = x, H, W, LAYOUT_NCHW
+        enc_in, enc_u = [], []
+        for op in model.encoder.ops:
+            enc_in.append((a, h, w, layout))
+            a = T.conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, in_layout=layout)
+            h, w = engine.conv_out_hw(op.conv, h, w)
+            if op.gdn is not None:
+                u = a
+                a, nrm = T.gdn_forward(arm, op.gdn, u, B, h, w)
+                enc_u.append((u, nrm))
+            else:
+                enc_u.append(None)
+            layout = LAYOUT_NHWC
+        y_nhwc = a
+        y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, Q_NOISE, noise_y, torch.float32)
+        a, h, w = y_nhwc, hy, wy
+        ha_in = []
+        for op in model.hyper_encoder.ops:
+            ha_in.append((a, h, w))
+            a = T.conv_forward(arm, op.conv, op.epilogue, a, B, h, w)
+            h, w = engine.conv_out_hw(op.conv, h, w)
+        z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, Q_NOISE, noise_z, torch.float32)
+        combs = [T._f32((B, hy, wy, 2 * (c1 - c0) + 2 * M), dev) for _, _, c0, c1 in heads]
+        a, h, w = z_in_nhwc, hz, wz
+        hs_in = []
+        hs = model.hyper_decoder.ops
+        for i, op in enumerate(hs):
+            hs_in.append((a, h, w))
+            if i == len(hs) - 1:
+                T.conv_forward(arm, op.conv, op.epilogue, a, B, h, w, out=combs[0], out_c_total=combs[0].shape[-1], out_c_offset=2 * M1)
+            else:
+                a = T.conv_forward(arm, op.conv, op.epilogue, a, B, h, w)
+            h, w = engine.conv_out_hw(op.conv, h, w)
+        combs[1][..., 2 * M2:] = combs[0][..., 2 * M1:]                       # the second head reads the same psi
+        head_state = []
+        for (ctx, ep, c0, c1), comb in zip(heads, combs):
+            mi = c1 - c0
+            yi_nhwc = y_in_nhwc[..., c0:c1].contiguous()
+            yi = y_in[:, c0:c1].contiguous()
+            ctx.masked.apply_mask_()
+            T.conv_forward(arm, ctx.masked, EPI_BIAS, yi_nhwc, B, hy, wy, out=comb, out_c_total=comb.shape[-1], out_c_offset=0, mask_a=True)
+            e1 = T.conv_forward(arm, ep.ops[0].conv, ep.ops[0].epilogue, comb, B, hy, wy)
+            e2 = T.conv_forward(arm, ep.ops[1].conv, ep.ops[1].epilogue, e1, B, hy, wy)
+            raw = T.conv_forward(arm, ep.ops[2].conv, ep.ops[2].epilogue, e2, B, hy, wy, out_layout=LAYOUT_NCHW)
+            ly = gm_likelihood(yi, raw, mi, K, Q_PASSTHRU, full=False, want_y_in=False)
+            head_state.append(dict(yi=yi, yi_nhwc=yi_nhwc, comb=comb, e1=e1, e2=e2, raw=raw, parts=ly["partials"]))
+        fe = model.factorized_entropy_model
+        _, p_z, logp_z, parts_z = fe.likelihood(z_in, Q_PASSTHRU)
+        a, h, w = y_in_nhwc, hy, wy
+        dec_in, dec_u = [], []
+        dec = model.decoder.ops
+        for i, op in enumerate(dec):
+            last = i == len(dec) - 1
+            dec_in.append((a, h, w))
+            a = T.conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC)
+            h, w = engine.conv_out_hw(op.conv, h, w)
+            if op.gdn is not None:
+                u = a
+                a, nrm = T.gdn_forward(arm, op.gdn, u, B, h, w)
+                dec_u.append((u, nrm))
+            else:
+                dec_u.append(None)
+        x_hat = a
+        # ---------------------------------------------------------------- loss -------------------------------------------------
+        # vision_rd_loss (RateDistortionLoss.py:52-121, V = None): loss = bpp_y1 + bpp_y2 + bpp_z + lambda * mse  (no 255^2 here)
+        chw, npix = x[0].numel(), H * W
+        se = engine.partials(B, dev)
+        check(lib.nic_sse_fwd(ptr(x_hat), ptr(x), B, chw, ptr(se), current_stream()), "nic_sse_fwd")
+        scal = []
+        for hsd in head_state:
+            per_image = T._f32((3, B), dev)
+            scalars = T._f32(8, dev)
+            check(lib.nic_rd_finalize(ptr(hsd["parts"]), ptr(parts_z), ptr(se), B, npix, chw, 0.0, ptr(per_image), ptr(scalars), current_stream()),
+                  "nic_rd_finalize")
+            scal.append(scalars)
+        loss = scal[0][0] + scal[1][0] + scal[0][1] + float(lambda_rd) * scal[0][3]
+        terms = {"bpp_y1": scal[0][0], "bpp_y2": scal[1][0], "bpp_z": scal[0][1], "mse": scal[0][3], "psnr": scal[0][4], "loss": loss}
+        # ---------------------------------------------------------------- backward ---------------------------------------------
+        gl = torch.full((1,), -1.0 / (math.log(2.0) * npix * B), dtype=torch.float32, device=dev)
+        g = torch.empty_like(x_hat)
+        check(lib.nic_sse_bwd(ptr(x_hat), ptr(x), x.numel(), float(lambda_rd) * 2.0 / x.numel(), ptr(g), current_stream()), "nic_sse_bwd")
+        g_layout = LAYOUT_NCHW
+        for i in range(len(dec) - 1, -1, -1):                                  # g_s
+            op = dec[i]
+            a, h, w = dec_in[i]
+            ho, wo = engine.conv_out_hw(op.conv, h, w)
+            if op.gdn is not None:
+                g, dbeta, dgamma = T.gdn_bwd(op.gdn, dec_u[i][0], g, B, ho, wo, norm=dec_u[i][1])
+                put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
+            dw, db = T.conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, g_layout, arm=arm)
+            put(op.conv.weight, dw); put(op.conv.bias, db)
+            g = T.conv_dgrad(op.conv, g, B, h, w, g_layout, arm=arm)
+            g_layout = LAYOUT_NHWC
+        d_yin_gs = g
+        d_psi, d_yin_parts = None, []
+        for (ctx, ep, c0, c1), hsd in zip(heads, head_state):                  # the two entropy heads
+            mi = c1 - c0
+            glh = gl.expand(hsd["yi"].shape).contiguous()
+            dy_lik = torch.empty_like(hsd["yi"])
+            draw = torch.empty_like(hsd["raw"])
+            check(lib.nic_gm_likelihood_bwd(ptr(hsd["yi"]), ptr(hsd["raw"]), ptr(glh), 0.0, B, mi, hy * wy, K, ptr(dy_lik), ptr(draw),
+                                            current_stream()), "nic_gm_likelihood_bwd")
+            d_yi = T.to_nhwc(dy_lik)
+            g = T.to_nhwc(draw)
+            for j, (op, a) in reversed(list(enumerate(zip(ep.ops, (hsd["comb"], hsd["e1"], hsd["e2"]))))):
+                dw, db = T.conv_wgrad(op.conv, a, g, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
+                put(op.conv.weight, dw); put(op.conv.bias, db)
+                if j > 0:
+                    g = T.lrelu_bwd_(T.conv_dgrad(op.conv, g, B, hy, wy, arm=arm), a)
+            w0 = ep.ops[0].conv.weight.detach()
+            d_phi = T.conv_dgrad(ep.ops[0].conv, g, B, hy, wy, weight=w0[:, :2 * mi].contiguous(), c_in=2 * mi, arm=arm)
+            d_psi_i = T.conv_dgrad(ep.ops[0].conv, g, B, hy, wy, weight=w0[:, 2 * mi:].contiguous(), c_in=2 * M, arm=arm)
+            d_psi = d_psi_i if d_psi is None else T.add_(d_psi, d_psi_i)
+            dw, db = T.conv_wgrad(ctx.masked, hsd["yi_nhwc"], d_phi, B, hy, wy, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
+            put(ctx.masked.weight, dw); put(ctx.masked.bias, db)
+            d_yin_parts.append(T.add_(d_yi, T.conv_dgrad(ctx.masked, d_phi, B, hy, wy, arm=arm)))
+        g = d_psi                                                              # h_s
+        for i in range(len(hs) - 1, -1, -1):
+            op = hs[i]
+            a, h, w = hs_in[i]
+            dw, db = T.conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
+            put(op.conv.weight, dw); put(op.conv.bias, db)
+            g = T.conv_dgrad(op.conv, g, B, h, w, arm=arm)
+            if i > 0:
+                g = T.lrelu_bwd_(g, a)
+        d_zin = g
+        glz = gl.expand(z_in.shape).contiguous()                               # factorized prior
+        dz_fac = torch.empty_like(z_in)
+        dpar = T._f32((M, 43), dev)
+        check(lib.nic_factorized_likelihood_bwd(ptr(z_in), ptr(fe.packed()), ptr(glz), 0.0, B, M, hz * wz, ptr(dz_fac), ptr(dpar),
+                                                current_stream()), "nic_factorized_likelihood_bwd")
+        for name, idx, lo, hi in T._FACT_SLICES:
+            prm = getattr(fe, name)[idx]
+            put(prm, dpar[:, lo:hi].reshape(prm.shape).contiguous())
+        d_zin = T.to_nhwc(dz_fac, accumulate_into=d_zin)
+        g = d_zin                                                              # h_a
+        ha = model.hyper_encoder.ops
+        for i in range(len(ha) - 1, -1, -1):
+            op = ha[i]
+            a, h, w = ha_in[i]
+            dw, db = T.conv_wgrad(op.conv, a, g, B, h, w, LAYOUT_NHWC, LAYOUT_NHWC, arm=arm)
+            put(op.conv.weight, dw); put(op.conv.bias, db)
+            g = T.conv_dgrad(op.conv, g, B, h, w, arm=arm)
+            if i > 0:
+                g = T.lrelu_bwd_(g, a)
+        dy = T.add_(T.add_(g, torch.cat(d_yin_parts, dim=-1).contiguous()), d_yin_gs)
+        g = dy                                                                 # g_a
+        enc = model.encoder.ops
+        for i in range(len(enc) - 1, -1, -1):
+            op = enc[i]
+            a, h, w, layout = enc_in[i]
+            ho, wo = engine.conv_out_hw(op.conv, h, w)
+            if op.gdn is not None:
+                g, dbeta, dgamma = T.gdn_bwd(op.gdn, enc_u[i][0], g, B, ho, wo, norm=enc_u[i][1])
+                put(op.gdn.beta, dbeta); put(op.gdn.gamma, dgamma)
+            dw, db = T.conv_wgrad(op.conv, a, g, B, h, w, layout, LAYOUT_NHWC, arm=arm)
+            put(op.conv.weight, dw); put(op.conv.bias, db)
+            if i > 0:
+                g = T.conv_dgrad(op.conv, g, B, h, w, arm=arm)
+    T.forget_pairs()
+    for p in model.parameters():
+        gp = grads.get(id(p))
+        if gp is not None:
+            p.grad = gp if p.grad is None else p.grad + gp
+    return loss, terms
