@@ -262,6 +262,10 @@ class ScalableImageCoding(nn.Module):
         B, _, H, W = x.shape
         if H % 64 or W % 64:
             raise ValueError(f"H and W must be multiples of 64; got {H}x{W}")
+        if training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # the training call with autograd on: one autograd node over the layer-by-layer forward (training_scalable.py)
+            from . import training_scalable as _ts
+            return _ts.train_forward(self, x, noise=noise)
         arm, M, M1, M2, K = self.precision, self.M, self.M1, self.M2, self.K
         from . import training as T
 

@@ -104,8 +104,13 @@ def vision_rd_loss(model_out: dict, x: torch.Tensor, lambda_rd: float, gamma: fl
     bpp_total = bpp_y1 + bpp_y2 + bpp_z
     mse_per_image = rows[0][2]
     bits_y1, bits_y2, bits_z = s1[6], s2[6], s1[7]
+    loss = scal[0][0] + scal[1][0] + scal[0][1] + lambda_rd * scal[0][3]
+    diff = [model_out[k] for k in ("logp_y1", "logp_y2", "logp_z", "x_hat")]
+    if torch.is_grad_enabled() and any(t.requires_grad for t in diff):
+        from .training_scalable import _VisionRDLoss          # the loss as one autograd node (the trainer calls loss.backward())
+        loss = _VisionRDLoss.apply(diff[0], diff[1], diff[2], diff[3].contiguous().float(), x, float(lambda_rd), loss)
     return {
-        "loss": scal[0][0] + scal[1][0] + scal[0][1] + lambda_rd * scal[0][3],
+        "loss": loss,
         "bpp_y1": bpp_y1, "bpp_y2": bpp_y2, "bpp_y": bpp_y1 + bpp_y2, "bpp_z": bpp_z, "bpp_total": bpp_total,
         "mse": mse, "reconstruction_mse": mse, "psnr": psnr, "vision_mse": 0.0,
         "mse_per_image": mse_per_image, "reconstruction_mse_per_image": mse_per_image,

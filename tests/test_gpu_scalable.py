@@ -123,3 +123,27 @@ def test_scalable_trainer_steps(graph):
     losses = [float(tr.step(x)["loss"]) for _ in range(12)]
     torch.cuda.synchronize()
     assert tr.optimizer.t == 12 and losses[-1] < losses[0], losses
+
+
+def test_scalable_autograd_path_equals_step_gradients():
+    """model(x) with autograd on + vision_rd_loss(...)['loss'].backward() (the reference trainer's calls) deposit the same gradients
+    as the autograd-free step, and the training dict has the reference's keys."""
+    from neural_image_compression_b200.RateDistortionLoss import vision_rd_loss
+    from neural_image_compression_b200.training_scalable import step_gradients
+    model = H.seeded_scalable_model(192, 128, 3, "calib192", precision="bf16x3").cuda()
+    x = H.seeded_input((1, 3, 64, 128)).cuda()
+    torch.manual_seed(23)
+    noise = (torch.rand(1, 192, 1, 2).cuda() - 0.5, torch.rand(1, 192, 4, 8).cuda() - 0.5)
+    out = model(x, noise=noise)
+    assert set(out) == {"x_hat", "y", "y_in", "y1", "y2", "z", "z_in", "p_z", "logp_z", "p_y1", "logp_y1", "p_y2", "logp_y2", "training",
+                        "weights1", "mus1", "sigmas1", "weights2", "mus2", "sigmas2"}
+    assert out["logp_y1"].requires_grad and out["x_hat"].requires_grad and not out["y_in"].requires_grad
+    rd = vision_rd_loss(out, x, 0.005)
+    rd["loss"].backward()
+    ref = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad()
+    loss, _ = step_gradients(model, x, 0.005, noise=noise)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(rd["loss"].detach())) <= 1e-6 * abs(float(loss))
+    for k, p in model.named_parameters():
+        assert torch.allclose(p.grad, ref[k], rtol=1e-6, atol=0), k
