@@ -273,3 +273,24 @@ def test_evaluation_after_training_sees_the_updated_weights(graph):
     assert real == 0, (real, ties)
     assert abs(rd["bpp_total"] - ref_rd["bpp_total"]) <= H.BPP_TOL + band and abs(rd["psnr"] - ref_rd["psnr"]) <= H.PSNR_TOL, (rd, ref_rd, band)
     assert abs(rd["bpp_total"] - before) > 1e-3, "six steps at lr 1e-4 must have changed the rate"
+
+
+def test_adam_kernel_over_several_steps():
+    """training.Adam (nic_adam_multi_step with the device-side step counter) against the restated torch.optim.Adam for t = 1..6,
+    on tensors of odd sizes (one launch for all of them)."""
+    from neural_image_compression_b200.training import Adam
+    torch.manual_seed(4)
+    shapes = [(7, 5), (11,), (4099,), (3, 128, 5, 5), (1,)]
+    params = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    cur = {str(i): p.detach().cpu().clone() for i, p in enumerate(params)}
+    opt, state = Adam(params, lr=1e-4), None
+    for t in range(6):
+        grads = {str(i): torch.randn(*s) * (10.0 ** (t - 3)) for i, s in enumerate(shapes)}
+        for i, p in enumerate(params):
+            p.grad = grads[str(i)].cuda()
+        opt.step()
+        cur, state = OB.adam_step(cur, grads, state)
+        torch.cuda.synchronize()
+        for i, p in enumerate(params):
+            np.testing.assert_allclose(p.detach().cpu().numpy(), cur[str(i)].numpy(), rtol=2e-6, atol=1e-8, err_msg=f"tensor {i} step {t + 1}")
+    assert opt.t == 6 and int(opt._t_dev) == 6

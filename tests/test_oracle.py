@@ -141,3 +141,20 @@ def test_metrics_oracle_basic_properties():
     assert torch.allclose(OM.rgb_to_luma(torch.ones(1, 3, 2, 2)), torch.ones(1, 2, 2))
     g = OM._gauss()
     assert abs(float(g.sum()) - 1.0) < 1e-6 and g.argmax() == 5 and g.numel() == 11
+
+
+def test_restated_adam_matches_torch_optim_over_several_steps():
+    """oracle/backward.py: adam_step against torch.optim.Adam(lr=1e-4) (Main.ipynb:133) for t = 1..6 (bias corrections included)."""
+    torch.manual_seed(3)
+    p0 = {"a": torch.randn(7, 5), "b": torch.randn(11)}
+    params = {k: torch.nn.Parameter(v.clone()) for k, v in p0.items()}
+    opt = torch.optim.Adam(params.values(), lr=1e-4)
+    cur, state = {k: v.clone() for k, v in p0.items()}, None
+    for t in range(6):
+        grads = {k: torch.randn_like(v) * (10.0 ** (t - 3)) for k, v in p0.items()}
+        for k, p in params.items():
+            p.grad = grads[k].clone()
+        opt.step()
+        cur, state = OB.adam_step(cur, grads, state)
+        for k in p0:
+            np.testing.assert_allclose(cur[k].numpy(), params[k].detach().numpy(), rtol=1e-6, atol=1e-9, err_msg=f"{k} step {t + 1}")
