@@ -294,3 +294,76 @@ def test_adam_kernel_over_several_steps():
         for i, p in enumerate(params):
             np.testing.assert_allclose(p.detach().cpu().numpy(), cur[str(i)].numpy(), rtol=2e-6, atol=1e-8, err_msg=f"tensor {i} step {t + 1}")
     assert opt.t == 6 and int(opt._t_dev) == 6
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 5])
+def test_likelihood_backward_kernel_against_autograd(K):
+    """nic_gm_likelihood_bwd on random latents / raw parameters (incl. elements at the 1e-9 clamp, where the reference's clamp_min
+    passes no gradient) against torch autograd over the oracle's split_parameters + conditional_likelihood + log."""
+    from neural_image_compression_b200 import _lib
+    from neural_image_compression_b200._lib import check, current_stream, ptr
+    torch.manual_seed(40 + K)
+    b, m, h, w = 2, 16, 6, 10
+    y = torch.round(4 * torch.randn(b, m, h, w))
+    y[0, 0, 0, :4] = 60.0                                          # far tails: mass below the clamp
+    raw = torch.randn(b, (2 if K == 1 else 3 * K) * m, h, w)
+    gl = torch.randn(b, m, h, w)
+    yr, rr = y.double().requires_grad_(True), raw.double().requires_grad_(True)
+    p = O.conditional_likelihood(yr, O.split_parameters(rr, m, K), K)
+    (torch.log(p) * gl.double()).sum().backward()
+    clamped = int((p.detach() <= 1e-9).sum())
+    assert clamped >= 4
+    dy = torch.empty_like(y).cuda()
+    draw = torch.empty_like(raw).cuda()
+    yc, rc, gc = y.cuda(), raw.cuda(), gl.cuda()                   # named: a temporary's memory would be recycled before the launch
+    check(_lib.load().nic_gm_likelihood_bwd(ptr(yc), ptr(rc), ptr(gc), 0.0, b, m, h * w, K, ptr(dy), ptr(draw), current_stream()),
+          "nic_gm_likelihood_bwd")
+    torch.cuda.synchronize()
+    # the kernel evaluates the reference's fp32 erf difference: p carries ~1e-7 of absolute rounding noise, so d log p = dp / p is
+    # conditioned like 1e-7 / p.  Compare tightly where p > 1e-3, by norm everywhere (the float64 autograd is the yardstick).
+    good = (p.detach() > 1e-3)
+    e_y = (dy.cpu().double() - yr.grad)[good].abs().max() / yr.grad[good].abs().max()
+    assert float(e_y) < 5e-4, float(e_y)
+    planes = raw.shape[1] // m
+    gmask = good.unsqueeze(1).expand(b, planes, m, h, w)
+    dr, rr_g = draw.cpu().double().view(b, planes, m, h, w)[gmask], rr.grad.view(b, planes, m, h, w)[gmask]
+    e_r = (dr - rr_g).abs().max() / rr_g.abs().max()
+    assert float(e_r) < 5e-4, float(e_r)                            # in the tails (p << 1e-3) fp32 and float64 gradients differ by O(1): not compared
+    assert float(dy.cpu()[0, 0, 0, :4].abs().max()) == 0.0 and float(draw.cpu()[0, :, 0, :4][::m].abs().max()) == 0.0     # clamped: no gradient
+
+
+def test_factorized_backward_kernel_against_autograd():
+    """nic_factorized_likelihood_bwd (per-channel 1-3-3-3-1 MLP, softplus / tanh chains, 43 block-summed parameter gradients)."""
+    from neural_image_compression_b200 import _lib
+    from neural_image_compression_b200._lib import check, current_stream, ptr
+    from neural_image_compression_b200.EntropyModels import FactorizedEntropyBottleneck
+    from neural_image_compression_b200.training import _FACT_SLICES
+    torch.manual_seed(50)
+    c, b, h, w = 12, 3, 5, 7
+    fe = FactorizedEntropyBottleneck(c)
+    with torch.no_grad():
+        for f in fe.factors:
+            f.uniform_(-0.5, 0.5)                                  # the default init (zeros) would hide the tanh chain
+        for mtx in fe.matrices:
+            mtx.add_(0.3 * torch.randn_like(mtx))
+    sd = {"factorized_entropy_model." + k: v.detach().double().requires_grad_(True) for k, v in fe.state_dict().items()}
+    z = (3 * torch.randn(b, c, h, w) + torch.rand(b, c, h, w) - 0.5)
+    gl = torch.randn(b, c, h, w)
+    zr = z.double().requires_grad_(True)
+    prev, O.DIFFERENTIABLE = O.DIFFERENTIABLE, True
+    try:
+        p = O.factorized_likelihood(sd, zr, dtype=torch.float64)
+        (torch.log(p) * gl.double()).sum().backward()
+    finally:
+        O.DIFFERENTIABLE = prev
+    fe = fe.cuda()
+    dz = torch.empty_like(z).cuda()
+    dpar = torch.empty(c, 43, device="cuda")
+    zc, gc, fp = z.cuda(), gl.cuda(), fe.packed()
+    check(_lib.load().nic_factorized_likelihood_bwd(ptr(zc), ptr(fp), ptr(gc), 0.0, b, c, h * w, ptr(dz), ptr(dpar),
+                                                    current_stream()), "nic_factorized_likelihood_bwd")
+    torch.cuda.synchronize()
+    assert rel_err(dz, zr.grad) < 1e-4, rel_err(dz, zr.grad)
+    for name, idx, lo, hi in _FACT_SLICES:
+        ref = sd[f"factorized_entropy_model.{name}.{idx}"].grad
+        assert rel_err(dpar[:, lo:hi].reshape(ref.shape), ref) < 1e-4, (name, idx, rel_err(dpar[:, lo:hi].reshape(ref.shape), ref))
