@@ -1,3 +1,5 @@
+"""Debug aid (GPU box): nic_conv_wgrad_tc against the fp32 weight-gradient kernel on a few layer shapes, with per-tap and
+per-64-channel-slab error breakdowns when they disagree.   python tools/debug_wgrad_tc.py"""
 import sys, torch, torch.nn as nn
 sys.path.insert(0, ".")
 from neural_image_compression_b200 import _lib
