@@ -119,6 +119,102 @@ def likelihood_close(p, p_ref):
     return int(bad.sum()), float(err.max())
 
 
+# ---- end-to-end comparison in the presence of rounding-tie flips --------------------------------------------------
+#
+# A symbol whose pre-rounding value sits within a few 1e-4 of a half-integer may legitimately round the other way in a pipeline
+# with a different (but fp32-grade) accumulation order; the reference's own fp32 and fp64 runs flip 3 of 393 216 (SURVEY.md
+# fact 7).  A flipped symbol changes every tensor downstream of it, so the per-element likelihood / x_hat comparison against
+# the reference's vectors is made on the elements that are NOT a function of a flipped symbol (masks below), and a second
+# comparison - the oracle's entropy path and synthesis transform evaluated on THIS run's symbols - covers 100 % of the elements.
+TIE_TAU = 2e-3            # |frac(y_ref) - 0.5| below which a flip counts as a tie
+TIE_RATE = 2e-4           # bound on tie flips / symbols (observed: 4e-5 .. 9e-5 at std(y) = 8, the calib / gain weight sets)
+
+
+def _dilate(m, kh, kw):
+    """binary [B,1,H,W] map: 1 where any 1 lies within the (kh x kw) window centred on the pixel"""
+    return torch.nn.functional.max_pool2d(m, (kh, kw), stride=1, padding=(kh // 2, kw // 2))
+
+
+def flip_masks(y_in, y_ref, z_in, z_ref, x_shape):
+    """Boolean maps of the elements that do NOT depend on a flipped symbol:
+    ok_y [B,1,hy,wy] for p_y (causal 5x5 footprint of the masked context conv, ContextModels.py:13-16, and the h_s receptive
+    field of a flipped z: ConvT5 s2 -> ConvT5 s2 -> 3x3 = +-7 around 4 i), ok_z [B,C,hz,wz] for p_z (elementwise),
+    ok_x [B,1,H,W] for x_hat (g_s: four ConvT 5x5 s2 = +-30 around 16 i)."""
+    y_in, y_ref, z_in, z_ref = (torch.as_tensor(np.asarray(a)) for a in (y_in, y_ref, z_in, z_ref))
+    fy = (y_in != y_ref).any(dim=1, keepdim=True).float()
+    fz = (z_in != z_ref)
+    k = torch.zeros(1, 1, 5, 5)
+    k[0, 0, :2, :] = 1; k[0, 0, 2, :3] = 1          # taps the context conv reads + the symbol itself
+    # output pixel (i', j') reads flip[i' + di, j' + dj] over the live taps: cross-correlation with the live-tap kernel
+    bad_y = torch.nn.functional.conv2d(fy, k, padding=2) > 0
+    fzp = fz.any(dim=1, keepdim=True).float()
+    if fzp.sum() > 0:
+        up = torch.zeros_like(fy)
+        up[:, :, ::4, ::4] = fzp
+        bad_y |= _dilate(up, 15, 15) > 0
+    B, _, Hx, Wx = x_shape
+    upx = torch.zeros(B, 1, Hx, Wx)
+    upx[:, :, ::16, ::16] = fy
+    bad_x = _dilate(upx, 61, 61) > 0 if fy.sum() > 0 else torch.zeros(B, 1, Hx, Wx, dtype=torch.bool)
+    return (~bad_y).numpy(), (~fz).numpy(), (~bad_x).numpy()
+
+
+def masked_likelihood_close(p, p_ref, ok):
+    """(outliers, worst abs err, compared elements, compared fraction) over the elements where ok (broadcast over channels)"""
+    p, p_ref = np.asarray(p, np.float64), np.asarray(p_ref, np.float64)
+    ok = np.broadcast_to(ok, p.shape)
+    err = np.abs(p - p_ref)
+    bad = (err > P_RTOL * p_ref + P_ATOL) & ok
+    n = int(ok.sum())
+    return int(bad.sum()), float(err[ok].max()) if n else 0.0, n, n / p.size
+
+
+def oracle_given_symbols(sd, y_in, z_in, M, K):
+    """The reference's entropy path and synthesis transform (oracle restatement) evaluated on GIVEN symbols: what p_y, p_z and
+    x_hat must be for this run's y_in / z_in (Models.py:69-90)."""
+    from oracle import forward as O
+    sd = {k: v.detach().cpu() for k, v in sd.items()}
+    y_in, z_in = torch.as_tensor(np.asarray(y_in)), torch.as_tensor(np.asarray(z_in))
+    with torch.no_grad():
+        psi = O.hyper_synthesis(sd, z_in)
+        phi = O.context(sd, y_in)
+        raw = O.entropy_parameters_raw(sd, torch.cat([phi, psi], dim=1))
+        p_y = O.conditional_likelihood(y_in, O.split_parameters(raw, M, K), K)
+        p_z = O.factorized_likelihood(sd, z_in)
+        x_hat = O.synthesis(sd, y_in)
+    return p_y.numpy(), p_z.numpy(), x_hat.numpy()
+
+
+def oracle_scalable_given_symbols(sd, y_in, z_in, M, M1, K):
+    """oracle_given_symbols for ScalableImageCoding (two entropy heads over the shared psi; oracle.forward_scalable's order)."""
+    from oracle import forward as O
+    sd = {k: v.detach().cpu() for k, v in sd.items()}
+    y_in, z_in = torch.as_tensor(np.asarray(y_in)), torch.as_tensor(np.asarray(z_in))
+    out = {}
+    with torch.no_grad():
+        psi = O.hyper_synthesis(sd, z_in)
+        for i, (yi, mi) in enumerate(zip(torch.split(y_in, [M1, M - M1], dim=1), (M1, M - M1)), start=1):
+            phi = O.context(sd, yi, prefix=f"context_model_{i}")
+            raw = O.entropy_parameters_raw(sd, torch.cat([phi, psi], dim=1), prefix=f"entropy_parameters_{i}")
+            out[f"p_y{i}"] = O.conditional_likelihood(yi, O.split_parameters(raw, mi, K), K).numpy()
+        out["p_z"] = O.factorized_likelihood(sd, z_in).numpy()
+        out["x_hat"] = O.synthesis(sd, y_in).numpy()
+    return out
+
+
+def record_report(name, report):
+    """Append one line to gpurun_out/parity_report.jsonl (copied to profiles/ per round: the judged evidence of what the parity
+    tests compared)."""
+    import json
+    d = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: (list(v) if isinstance(v, tuple) else v) for k, v in report.items()}}) + "\n")
+    except OSError:
+        pass
+
+
 def symbol_mismatches(sym, sym_ref, pre_ref, tau):
     """Mismatching symbols, split into near-tie ones (|frac(pre_ref)| within tau of .5) and real ones."""
     sym, sym_ref, pre_ref = (np.asarray(a) for a in (sym, sym_ref, pre_ref))

@@ -12,49 +12,79 @@ pytestmark = pytest.mark.gpu
 DICT_KEYS_K1 = {"x_hat", "y", "y_in", "z", "z_in", "p_z", "logp_z", "p_y", "logp_y", "training", "mu", "sigma"}
 DICT_KEYS_KN = (DICT_KEYS_K1 - {"mu", "sigma"}) | {"weights", "mus", "sigmas"}
 
-# near-tie window for end-to-end symbol comparison: an fp32 pipeline in a different accumulation order moves y by
-# a few 1e-6 relative; symbols whose pre-rounding value sits closer than TAU to a half-integer may flip legitimately
-TAU = {"fp32": 2e-3, "bf16x3": 5e-3}
+# near-tie window for end-to-end symbol comparison (tests/helpers.py): an fp32-grade pipeline in a different accumulation order
+# moves y by a few 1e-6 .. 1e-5 relative; symbols whose pre-rounding value sits closer than TIE_TAU to a half-integer may flip
+# legitimately.  The window is the same for both arms and the NUMBER of tie flips is bounded (TIE_RATE).
+TAU = {"fp32": H.TIE_TAU, "bf16x3": H.TIE_TAU}
 
 
-def check_against(out, rd, ref, ref_rd, K, precision="fp32", x_hat_tol=1e-4, bpp_band=0.0):
-    """bpp_band: |bpp(reference fp32) - bpp(reference arithmetic in fp64)| of the case.  Where it exceeds the 1e-3
-    criterion (gain-init: most likelihoods sit at the 1e-9 clamp and are erf-difference rounding noise) the total is
-    required to land within that band of the reference instead, and bits are additionally compared on the
-    well-conditioned elements (p_ref >= 1e-6) at the strict tolerance."""
-    report = {}
+def check_against(out, rd, ref, ref_rd, K, precision="fp32", x_hat_tol=1e-4, bpp_band=0.0, sd=None, M=128, name="", min_frac=0.8):
+    """The north-star criteria on one run: symbols bit-exact (away from rounding ties, tie flips counted and bounded),
+    likelihoods within 1e-4 relative, bpp / PSNR within 1e-3.
+
+    Per-element likelihoods and x_hat are compared
+      (a) against the reference's own vectors on every element that is not a function of a flipped symbol (helpers.flip_masks);
+          the compared fraction must be >= min_frac (a flipped symbol feeds ALL output channels of the 13 pixels whose causal
+          window contains it, so at the observed flip rate of ~8e-5 per symbol x 128 channels ~1 % of the pixels flip and
+          ~12 % of them are masked: 0.8 is the floor, the measured fraction is in the report), and
+      (b) when any symbol flipped, additionally on 100 % of the elements against the oracle's entropy path / synthesis transform
+          evaluated on this run's symbols (helpers.oracle_given_symbols; needs sd).
+    bpp_band: |bpp(reference fp32) - bpp(reference arithmetic in fp64)| of the case.  Where it exceeds the 1e-3 criterion
+    (gain-init: most likelihoods sit at the 1e-9 clamp and are erf-difference rounding noise) the total is required to land within
+    that band of the reference instead, and bits are additionally compared on the well-conditioned elements (p_ref >= 1e-6) at
+    the strict tolerance."""
+    report = {"precision": precision}
     assert set(out) == (DICT_KEYS_K1 if K == 1 else DICT_KEYS_KN)
     for k, v in out.items():
         if torch.is_tensor(v):
             assert v.dtype == torch.float32 and tuple(v.shape) == tuple(ref[k].shape), k
+    o = {k: out[k].cpu().numpy() for k in ("y", "y_in", "z", "z_in", "p_y", "p_z", "logp_y", "x_hat")}
     tau = TAU[precision]
-    for name, pre in (("y_in", "y"), ("z_in", "z")):
-        real, ties = H.symbol_mismatches(out[name].cpu().numpy(), ref[name], ref[pre], tau)
-        report[name] = (real, ties)
-        assert real == 0, f"{name}: {real} symbols differ away from rounding ties ({ties} at ties)"
-    same = (out["y_in"].cpu().numpy() == ref["y_in"]).all(axis=1, keepdims=True)     # per-pixel: every channel equal
-    # likelihoods are compared where the symbols (and hence the context) agree
-    if same.all() and (out["z_in"].cpu().numpy() == ref["z_in"]).all():
-        for name in ("p_y", "p_z"):
-            bad, worst = H.likelihood_close(out[name].cpu().numpy(), ref[name])
-            report[name] = (bad, worst)
-            assert bad <= 1e-5 * ref[name].size, f"{name}: {bad} outside tolerance (max abs err {worst:.2e})"
+    flips = 0
+    for name_, pre in (("y_in", "y"), ("z_in", "z")):
+        real, ties = H.symbol_mismatches(o[name_], ref[name_], ref[pre], tau)
+        report[name_ + "_flips_real_ties"] = (real, ties)
+        flips += real + ties
+        assert real == 0, f"{name_}: {real} symbols differ away from rounding ties ({ties} at ties)"
+        assert ties <= max(2, H.TIE_RATE * ref[name_].size), f"{name_}: {ties} tie flips of {ref[name_].size} symbols"
+        d = np.abs(o[pre] - ref[pre])
+        report[pre + "_max_abs_err"] = float(d.max())
+    ok_y, ok_z, ok_x = H.flip_masks(o["y_in"], ref["y_in"], o["z_in"], ref["z_in"], ref["x_hat"].shape)
+    # (a) against the reference's vectors, off the flipped symbols' footprints
+    for name_, ok in (("p_y", ok_y), ("p_z", ok_z)):
+        bad, worst, n, frac = H.masked_likelihood_close(o[name_], ref[name_], ok)
+        report[name_] = {"outliers": bad, "max_abs_err": worst, "compared": n, "fraction": frac}
+        # (a flipped z symbol reaches 15 x 15 y pixels through h_s - the whole grid of the small cases; part (b) covers those)
+        assert frac >= min_frac or not ok_z.all(), f"{name_}: only {frac:.3f} of the elements are comparable"
+        assert bad <= 1e-5 * n, f"{name_}: {bad} of {n} outside tolerance (max abs err {worst:.2e})"
+    okx = np.broadcast_to(ok_x, ref["x_hat"].shape)
+    xe = float(np.abs(o["x_hat"] - ref["x_hat"])[okx].max() / np.abs(ref["x_hat"]).max()) if okx.any() else 0.0
+    report["x_hat"] = {"rel_err": xe, "fraction": float(okx.mean())}
+    assert xe < x_hat_tol, xe
+    # (b) on everything, given this run's symbols
+    if flips and sd is not None:
+        p_y, p_z, x_hat = H.oracle_given_symbols(sd, o["y_in"], o["z_in"], M, K)
+        for name_, r in (("p_y", p_y), ("p_z", p_z)):
+            bad, worst = H.likelihood_close(o[name_], r)
+            report[name_ + "_given_symbols"] = {"outliers": bad, "max_abs_err": worst, "compared": int(r.size)}
+            assert bad <= 1e-5 * r.size, f"{name_} (given symbols): {bad} outside tolerance (max abs err {worst:.2e})"
+        xe2 = float(np.abs(o["x_hat"] - x_hat).max() / np.abs(x_hat).max())
+        report["x_hat_given_symbols_rel_err"] = xe2
+        assert xe2 < x_hat_tol, xe2
     tol = max(H.BPP_TOL, bpp_band)
     report["bpp"] = (rd["bpp_total"], ref_rd["bpp_total"])
     assert abs(rd["bpp_total"] - ref_rd["bpp_total"]) <= tol, (rd["bpp_total"], ref_rd["bpp_total"], tol)
     assert abs(rd["bpp_y"] - ref_rd["bpp_y"]) <= tol and abs(rd["bpp_z"] - ref_rd["bpp_z"]) <= H.BPP_TOL
-    if same.all():
-        good = ref["p_y"] >= 1e-6
-        npix = ref["x_hat"].shape[0] * ref["x_hat"].shape[2] * ref["x_hat"].shape[3]
-        ours = -(out["logp_y"].cpu().numpy().astype(np.float64)[good]).sum() / np.log(2.0) / npix
-        theirs = -(ref["logp_y"].astype(np.float64)[good]).sum() / np.log(2.0) / npix
-        report["bpp_y_conditioned"] = (ours, theirs)
-        assert abs(ours - theirs) <= H.BPP_TOL, (ours, theirs)
+    good = (ref["p_y"] >= 1e-6) & np.broadcast_to(ok_y, ref["p_y"].shape)
+    npix = ref["x_hat"].shape[0] * ref["x_hat"].shape[2] * ref["x_hat"].shape[3]
+    ours = -(o["logp_y"].astype(np.float64)[good]).sum() / np.log(2.0) / npix
+    theirs = -(ref["logp_y"].astype(np.float64)[good]).sum() / np.log(2.0) / npix
+    report["bpp_y_conditioned"] = (ours, theirs)
+    assert abs(ours - theirs) <= H.BPP_TOL, (ours, theirs)
+    report["psnr"] = (rd["psnr"], ref_rd["psnr"])
     assert abs(rd["psnr"] - ref_rd["psnr"]) <= H.PSNR_TOL, (rd["psnr"], ref_rd["psnr"])
-    xe = float(np.abs(out["x_hat"].cpu().numpy() - ref["x_hat"]).max() / np.abs(ref["x_hat"]).max())
-    report["x_hat_rel"] = xe
-    if same.all():
-        assert xe < x_hat_tol, xe
+    if name:
+        H.record_report(name, report)
     return report
 
 
@@ -75,7 +105,10 @@ def test_model_matches_reference_vectors(case, precision):
     rd = rd_loss(out, x, 0.005)
     ref = {k[4:]: g[k] for k in g.files if k.startswith("out_")}
     ref_rd = {k[3:]: float(g[k]) for k in g.files if k.startswith("rd_") and g[k].ndim == 0}
-    rep = check_against(out, rd, ref, ref_rd, K, precision=precision, x_hat_tol=X_HAT_TOL[precision], bpp_band=band)
+    # the golden cases are small (y grids of 8 x 12 .. 16 x 16 pixels: one flipped symbol's footprint is > 10 % of the grid), so the
+    # compared-fraction floor applies to the Kodak-shape test below; here part (b) of check_against covers the rest
+    rep = check_against(out, rd, ref, ref_rd, K, precision=precision, x_hat_tol=X_HAT_TOL[precision], bpp_band=band,
+                        sd=model.state_dict(), M=M, name=f"golden/{case}/{precision}", min_frac=0.5)
     print(case, precision, rep)
     assert out["training"] is False
 
@@ -97,7 +130,8 @@ def test_model_matches_oracle_at_kodak_shape(init, precision):
     model = model.cuda()
     out = model(x.cuda(), training=False)
     rd = rd_loss(out, x.cuda(), 0.005)
-    print(init, precision, check_against(out, rd, ref, ref_rd, 3, precision=precision, x_hat_tol=X_HAT_TOL[precision], bpp_band=band))
+    print(init, precision, check_against(out, rd, ref, ref_rd, 3, precision=precision, x_hat_tol=X_HAT_TOL[precision], bpp_band=band,
+                                         sd=sd, M=128, name=f"kodak_shape/{init}/{precision}"))
 
 
 @pytest.mark.parametrize("precision", PARITY_ARMS)
@@ -161,7 +195,7 @@ def test_full_size_batch_properties(precision):
 def test_config4_training_forward_shape(precision):
     """BASELINE configs[3]'s forward half: training=True (noise relaxation, injected noise so both sides see the same draw) on
     8 crops of 256 x 256 (the per-GPU share of batch 64 over 8 GPUs), loss terms against the oracle.  (The backward pass and the
-    optimizer are not built; see DESIGN.md.)"""
+    optimizer step of the same config: tests/test_gpu_train.py.)"""
     from neural_image_compression_b200.RateDistortionLoss import rd_loss
     model = H.seeded_model(128, 3, "calib", precision=precision)
     sd = {k: v.clone() for k, v in model.state_dict().items()}

@@ -28,16 +28,39 @@ def test_scalable_model_matches_reference_vectors(case, precision):
     for k, v in out.items():
         if torch.is_tensor(v):
             assert v.dtype == torch.float32 and tuple(v.shape) == tuple(ref[k].shape), k
+    o = {k: out[k].cpu().numpy() for k in ("y", "y_in", "z", "z_in", "p_y1", "p_y2", "p_z", "x_hat")}
+    rep, flips = {"precision": precision}, 0
     for name, pre in (("y_in", "y"), ("z_in", "z")):
-        real, ties = H.symbol_mismatches(out[name].cpu().numpy(), ref[name], ref[pre], 2e-3)
+        real, ties = H.symbol_mismatches(o[name], ref[name], ref[pre], H.TIE_TAU)
+        rep[name + "_flips_real_ties"] = [real, ties]
+        flips += ties
         assert real == 0, (name, real, ties)
+        assert ties <= max(2, H.TIE_RATE * ref[name].size), (name, ties)
     assert torch.equal(torch.cat([out["y1"], out["y2"]], dim=1), out["y_in"])
-    if (out["y_in"].cpu().numpy() == ref["y_in"]).all() and (out["z_in"].cpu().numpy() == ref["z_in"]).all():
+    # per-element likelihoods / x_hat: (a) against the reference's vectors off the footprints of flipped symbols (a symbol of
+    # either head's channel range only reaches that head's context conv, but the masks are per pixel: conservative), at the
+    # main model's bounds (1e-5 outliers, both arms); (b) if anything flipped, everywhere against the oracle on this run's symbols
+    ok_y, ok_z, ok_x = H.flip_masks(o["y_in"], ref["y_in"], o["z_in"], ref["z_in"], ref["x_hat"].shape)
+    x_tol = 1e-4 if precision == "fp32" else 3e-4
+    for name, ok in (("p_y1", ok_y), ("p_y2", ok_y), ("p_z", ok_z)):
+        bad, worst, n, frac = H.masked_likelihood_close(o[name], ref[name], ok)
+        rep[name] = {"outliers": bad, "max_abs_err": worst, "compared": n, "fraction": frac}
+        assert bad <= 1e-5 * n + 1, (name, bad, n, worst)
+    okx = np.broadcast_to(ok_x, ref["x_hat"].shape)
+    if okx.any():
+        xe = float(np.abs(o["x_hat"] - ref["x_hat"])[okx].max() / np.abs(ref["x_hat"]).max())
+        rep["x_hat"] = {"rel_err": xe, "fraction": float(okx.mean())}
+        assert xe < x_tol, xe
+    if flips:
+        want_given = H.oracle_scalable_given_symbols(model.state_dict(), o["y_in"], o["z_in"], M, M1, K)
         for name in ("p_y1", "p_y2", "p_z"):
-            bad, worst = H.likelihood_close(out[name].cpu().numpy(), ref[name])
-            assert bad <= (1e-5 if precision == "fp32" else 2e-3) * ref[name].size, (name, bad, worst)
-        xe = float(np.abs(out["x_hat"].cpu().numpy() - ref["x_hat"]).max() / np.abs(ref["x_hat"]).max())
-        assert xe < (1e-4 if precision == "fp32" else 5e-4), xe
+            bad, worst = H.likelihood_close(o[name], want_given[name])
+            rep[name + "_given_symbols"] = {"outliers": bad, "max_abs_err": worst}
+            assert bad <= 1e-5 * want_given[name].size + 1, (name, bad, worst)
+        xe2 = float(np.abs(o["x_hat"] - want_given["x_hat"]).max() / np.abs(want_given["x_hat"]).max())
+        rep["x_hat_given_symbols_rel_err"] = xe2
+        assert xe2 < x_tol, xe2
+    H.record_report(f"scalable/{case}/{precision}", rep)
     for key in ("bpp_y1", "bpp_y2", "bpp_z", "bpp_total"):
         assert abs(rd[key] - float(g["rd_" + key])) <= H.BPP_TOL, (key, rd[key], float(g["rd_" + key]))
     assert abs(rd["psnr"] - float(g["rd_psnr"])) <= H.PSNR_TOL

@@ -1,6 +1,7 @@
 """GPU: the bf16x3 arm (hi/lo-split operands on the tensor cores, fp32 grade) layer by layer against a float64 CPU
 convolution of the SAME fp32 operands.  The split keeps 16 mantissa bits per operand, so every layer must land within
 ~1e-5 of the exact result relative to the tensor's scale; the bound asserted is 1e-4."""
+import numpy as np
 import pytest
 import torch
 import torch.nn as nn
@@ -166,11 +167,34 @@ def test_x3_model_ragged_sizes_match_fp32_arm(shape):
     r0, r1 = rd_loss(ref, x, 0.005), rd_loss(out, x, 0.005)
     yerr = float((out["y"] - ref["y"]).abs().max() / ref["y"].abs().max())
     zerr = float((out["z"] - ref["z"]).abs().max() / ref["z"].abs().max())
-    real, ties = H.symbol_mismatches(out["y_in"].cpu().numpy(), ref["y_in"].cpu().numpy(), ref["y"].cpu().numpy(), 5e-3)
-    realz, tiesz = H.symbol_mismatches(out["z_in"].cpu().numpy(), ref["z_in"].cpu().numpy(), ref["z"].cpu().numpy(), 5e-3)
+    real, ties = H.symbol_mismatches(out["y_in"].cpu().numpy(), ref["y_in"].cpu().numpy(), ref["y"].cpu().numpy(), H.TIE_TAU)
+    realz, tiesz = H.symbol_mismatches(out["z_in"].cpu().numpy(), ref["z_in"].cpu().numpy(), ref["z"].cpu().numpy(), H.TIE_TAU)
     print(shape, f"y {yerr:.2e} z {zerr:.2e} ties {ties}+{tiesz} bpp {r1['bpp_total']:.6f}/{r0['bpp_total']:.6f} psnr {r1['psnr']:.6f}/{r0['psnr']:.6f}")
     assert yerr < 1e-4 and zerr < 1e-4 and real == 0 and realz == 0
+    assert ties <= max(2, H.TIE_RATE * out["y_in"].numel()) and tiesz <= max(2, H.TIE_RATE * out["z_in"].numel())
     assert abs(r1["bpp_total"] - r0["bpp_total"]) < 1e-3 and abs(r1["psnr"] - r0["psnr"]) < 1e-3
-    if ties + tiesz == 0:
-        xe = float((out["x_hat"] - ref["x_hat"]).abs().max() / ref["x_hat"].abs().max())
+    # per-element comparison off the footprints of the tie flips (tests/helpers.flip_masks) ...
+    o = {k: out[k].cpu().numpy() for k in ("y_in", "z_in", "p_y", "p_z", "x_hat")}
+    r = {k: ref[k].cpu().numpy() for k in ("y_in", "z_in", "p_y", "p_z", "x_hat")}
+    ok_y, ok_z, ok_x = H.flip_masks(o["y_in"], r["y_in"], o["z_in"], r["z_in"], r["x_hat"].shape)
+    rep = {"shape": list(shape), "y_rel_err": yerr, "z_rel_err": zerr, "ties": [ties, tiesz]}
+    for name, ok in (("p_y", ok_y), ("p_z", ok_z)):
+        bad, worst, n, frac = H.masked_likelihood_close(o[name], r[name], ok)
+        rep[name] = {"outliers": bad, "max_abs_err": worst, "compared": n, "fraction": frac}
+        assert bad <= 1e-5 * n + 1, (name, bad, n, worst)
+    okx = np.broadcast_to(ok_x, r["x_hat"].shape)
+    if okx.any():
+        xe = float(np.abs(o["x_hat"] - r["x_hat"])[okx].max() / np.abs(r["x_hat"]).max())
+        rep["x_hat"] = {"rel_err": xe, "fraction": float(okx.mean())}
         assert xe < 3e-4, xe
+    # ... and, if anything flipped, on all elements against the oracle evaluated on this run's symbols
+    if ties + tiesz:
+        p_y, p_z, x_hat = H.oracle_given_symbols(model.state_dict(), o["y_in"], o["z_in"], 128, 3)
+        for name, rr in (("p_y", p_y), ("p_z", p_z)):
+            bad, worst = H.likelihood_close(o[name], rr)
+            rep[name + "_given_symbols"] = {"outliers": bad, "max_abs_err": worst}
+            assert bad <= 1e-5 * rr.size + 1, (name, bad, worst)
+        xe2 = float(np.abs(o["x_hat"] - x_hat).max() / np.abs(x_hat).max())
+        rep["x_hat_given_symbols_rel_err"] = xe2
+        assert xe2 < 3e-4, xe2
+    H.record_report(f"ragged/{'x'.join(map(str, shape))}", rep)
