@@ -53,6 +53,50 @@ K2_CONV_FLOPS_PER_IMAGE = 2.0 * 128 * 192 * 128 * 128 * 25
 K2_GDN_FLOPS_PER_IMAGE = 2.0 * 128 * 192 * 128 * 128
 
 
+# seeded weights of the benchmark model: the reference's default init under torch.manual_seed(0), re-scaled so that the symbols are
+# non-trivial and the likelihoods well conditioned (the "calib" set of oracle/make_golden.py: last g_a conv x34, last h_a conv
+# x3.86, +3 on the sigma biases of the entropy-parameter head)
+def bench_model(precision="fp32", device=None):
+    import torch
+    from neural_image_compression_b200.Models import JointAutoregressiveHierarchical
+    torch.manual_seed(0)
+    model = JointAutoregressiveHierarchical(M, K=K, precision=precision)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    for k in ("encoder.net.6.weight", "encoder.net.6.bias"):
+        sd[k] = sd[k] * 34.0
+    for k in ("hyper_encoder.net.4.weight", "hyper_encoder.net.4.bias"):
+        sd[k] = sd[k] * 3.86
+    b = sd["entropy_parameters.net.4.bias"].clone()
+    b[2 * b.numel() // 3:] += 3.0
+    sd["entropy_parameters.net.4.bias"] = b
+    model.load_state_dict(sd)
+    return model if device is None else model.to(device)
+
+
+def bench_scalable_model(device):
+    import torch
+    from neural_image_compression_b200.Models import ScalableImageCoding
+    torch.manual_seed(0)
+    model = ScalableImageCoding(192, 128, K=1, precision="bf16x3")
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    for k in ("encoder.net.6.weight", "encoder.net.6.bias"):
+        sd[k] = sd[k] * 34.0
+    for k in ("hyper_encoder.net.4.weight", "hyper_encoder.net.4.bias"):
+        sd[k] = sd[k] * 3.86
+    for head in ("entropy_parameters_1", "entropy_parameters_2"):
+        b = sd[f"{head}.net.4.bias"].clone()
+        b[b.numel() // 2:] += 3.0
+        sd[f"{head}.net.4.bias"] = b
+    model.load_state_dict(sd)
+    return model.to(device)
+
+
+def seeded_input(shape, seed=1):
+    import torch
+    g = torch.Generator(device="cpu"); g.manual_seed(seed)
+    return torch.rand(*shape, generator=g)
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -90,38 +134,39 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_reference_arm(images: int, iters: int):
-    """The reference's CPU path (oracle port, torch CPU fp32, all host threads) on a bounded sample."""
+def cpu_reference_arm(images: int, iters: int, warmup: int = 1):
+    """The reference's CPU path (oracle port, torch CPU fp32, all host threads): `warmup` untimed + `iters` timed passes over
+    `images` images of the workload."""
     import torch
     from oracle import forward as O
-    from tests import helpers as Hh
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model = Hh.seeded_model(M, K, "calib")
+    model = bench_model()
     sd = {k: v.clone() for k, v in model.state_dict().items()}
-    x = Hh.seeded_input((images, 3, H_IMG, W_IMG))
+    x = seeded_input((images, 3, H_IMG, W_IMG))
     with torch.no_grad():
-        O.rd_loss(O.forward(sd, x[:1], M, K), x[:1], LAMBDA)          # warm-up
+        for _ in range(max(1, warmup)):
+            O.rd_loss(O.forward(sd, x, M, K), x, LAMBDA)              # warm-up passes (thread pool, allocator), untimed
         times = []
         for _ in range(iters):
             t0 = time.perf_counter()
             rd = O.rd_loss(O.forward(sd, x, M, K), x, LAMBDA)
             times.append(time.perf_counter() - t0)
-    t = statistics.median(times)
+    t = sum(times) / len(times)
     return {"value": images / t, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{images} x 3x512x768 images per pass, median of {iters} passes after 1 warm-up, torch CPU fp32 "
-                      f"({torch.get_num_threads()} threads)", "bpp_total": rd["bpp_total"], "psnr": rd["psnr"], "s_per_pass": t}
+            "sample": f"{iters} timed passes over {images} x 3x512x768 images after {max(1, warmup)} warm-up pass(es), torch CPU "
+                      f"fp32 ({torch.get_num_threads()} threads)", "bpp_total": rd["bpp_total"], "psnr": rd["psnr"], "s_per_pass": t,
+            "total_s": sum(times)}
 
 
 def cpu_train_step(images: int = 2):
     """The reference's training step on the host cores: autograd over the oracle port + restated Adam, one pass (bounded sample)."""
     import torch
     from oracle import backward as OB
-    from tests import helpers as Hh
     torch.set_num_threads(os.cpu_count() or 1)
-    model = Hh.seeded_model(M, K, "calib")
+    model = bench_model()
     sd = {k: v.clone() for k, v in model.state_dict().items()}
-    x = Hh.seeded_input((images, 3, 256, 256))
+    x = seeded_input((images, 3, 256, 256))
     torch.manual_seed(5)
     nz, ny = torch.rand(images, M, 4, 4) - 0.5, torch.rand(images, M, 16, 16) - 0.5
     t0 = time.perf_counter()
@@ -144,6 +189,9 @@ def main():
                          "tcgen05 throughput arm; fp32 = CUDA-core parity arm; mixed = g_a/h_a fp32, rest bf16")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-max-seconds", type=float, default=150.0, help="--impl reference: bound on the timed region (the step count is cut, and reported, if needed)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling line item (global batch 16 split over the ranks)")
+    ap.add_argument("--no-config3", action="store_true", help="skip the isolated context + entropy-parameter (+ likelihood) line item (BASELINE.json configs[2])")
     ap.add_argument("--no-other-arms", action="store_true", help="skip the short runs of the other precision arms reported beside the headline")
     ap.add_argument("--no-scalable", action="store_true", help="skip the scalable-coding line item (BASELINE.json configs[4])")
     ap.add_argument("--no-train-step", action="store_true", help="skip the training-step line item (BASELINE.json configs[3])")
@@ -156,13 +204,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        images = 2
-        base = cpu_reference_arm(images, max(1, min(args.steps, 5)))
+        # every step is ONE pass over the full 16-image batch of the workload (1.7 s on 16 host threads): exactly `steps` timed
+        # passes after `warmup` warm-up passes, like the GPU arm; --ref-max-seconds bounds the run (fewer timed steps, reported)
+        images = args.batch
+        est = 2.0 * images / 10.0                                  # ~10 images/s on a 16-thread host
+        steps = max(1, min(args.steps, int(args.ref_max_seconds / max(est, 1e-3))))
+        base = cpu_reference_arm(images, steps, warmup=args.warmup)
         line = {"impl": "reference", "metric": "768x512 images/s (fwd+likelihood+rd terms)", "value": base["value"], "unit": "images/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["s_per_pass"] * 1e3,
+                "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": base["s_per_pass"] * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "note": "reference CPU path = oracle port (torch CPU fp32); each step is a "
-                           f"bounded sample of {images} images of the workload"},
+                "config": {"workload": WORKLOAD, "global_batch": images, "parallelism": "host cores (rank 0)", "precision": "f32",
+                           "steps_requested": args.steps,
+                           "reference": "the reference's CPU path = oracle port (torch CPU fp32, same ops in the same order; the reference "
+                                        "itself is 14 loose scripts that cannot be installed or travel to the GPU box, DESIGN.md section 2)"},
                 "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -178,7 +232,6 @@ def main():
     import torch.distributed as dist
     from neural_image_compression_b200 import _lib, engine, parallel
     from neural_image_compression_b200.RateDistortionLoss import rd_loss, rd_terms
-    from tests import helpers as Hh
 
     assert torch.cuda.is_available(), "bench.py needs a B200"
     torch.cuda.set_device(local_rank)
@@ -191,7 +244,7 @@ def main():
     peaks = load_peaks()
 
     B = args.batch
-    model = Hh.seeded_model(M, K, "calib", precision=args.precision).to(dev)
+    model = bench_model(args.precision, dev)
     nbuf = 4
     gen = torch.Generator(device="cpu"); gen.manual_seed(1000 + rank)
     host_batches = [torch.rand((B, 3, H_IMG, W_IMG), generator=gen).pin_memory() for _ in range(nbuf)]
@@ -255,13 +308,99 @@ def main():
 
     _, terms = evaluator.step(dev_batches[0])
     terms = {k: float(terms[k]) for k in ("bpp_total", "psnr")}
+
+    # ---- strong scaling: BASELINE configs[1] is "batch=16" - the SAME 16 images split over the ranks
+    # (16 / world per GPU), with the local graph replay and the all-gather + fold of the per-image terms broken out ------------
+    strong = None
+    if not args.no_strong and 16 % world == 0:
+        bs = 16 // world
+        ev_s = evaluator if bs == B else parallel.ShardedEvaluator(model, LAMBDA, lean=False, graph=use_graph)
+        xs = [db[:bs].contiguous() for db in dev_batches]
+        ns = max(20, args.steps)
+
+        def timed(fn, n):
+            for i in range(3):
+                fn(i)
+            sync_all()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(n):
+                fn(i)
+            b.record()
+            sync_all()
+            tt = torch.tensor([a.elapsed_time(b)], device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()) / n
+        ms_step = timed(lambda i: ev_s.step(xs[i % nbuf]), ns)
+        ms_local = timed(lambda i: (ev_s._graphed_local(xs[i % nbuf]) if use_graph else ev_s._local(xs[i % nbuf])), ns)
+        per_img = torch.rand((3, bs), device=dev)
+        ms_coll = timed(lambda i: parallel.rd_terms_on_device(parallel.gather_per_image(per_img), H_IMG * W_IMG, LAMBDA), ns) if world > 1 else 0.0
+        strong = {"scaling": "strong", "global_batch": bs * world, "images_per_gpu": bs, "value": bs * world / (ms_step / 1e3), "unit": "images/s",
+                  "ms_per_step": ms_step, "local_step_ms": ms_local, "allgather_and_fold_ms": ms_coll, "steps": ns,
+                  "note": "the same 16-image batch split over the ranks; per-GPU work shrinks with N, so launch latency and the "
+                          "collective's latency (a 3 x B_local float all-gather + one fold kernel) weigh in"}
+        if ev_s is not evaluator:
+            del ev_s
+
+    # ---- BASELINE configs[2] isolated (SURVEY.md section 8d "Config 3"): masked 5x5 context conv + entropy-parameter 1x1 stack
+    # (+ the GM likelihood kernel) on y_in [B,128,32,48], psi [B,256,32,48]: 5.74 GFLOP / image algorithmic (12 live taps) --------
+    config3 = None
+    if not args.no_config3 and args.precision in ("bf16x3", "bf16"):
+        from neural_image_compression_b200.EntropyModels import gm_likelihood as _gml
+        from neural_image_compression_b200._lib import Q_PASSTHRU as _QP
+        pair = args.precision == "bf16x3"
+        cw = 2 if pair else 1
+        hy, wy = H_IMG // 16, W_IMG // 16
+        yq = torch.round(4 * torch.randn((B, hy, wy, M), device=dev))
+        y_in_nhwc = engine.to_pair(yq) if pair else yq.to(torch.bfloat16)
+        y_in_nchw = yq.permute(0, 3, 1, 2).contiguous()
+        psi = torch.randn((B, hy, wy, 2 * M), device=dev)
+        combined = torch.zeros((B, hy, wy, cw * 4 * M), dtype=torch.bfloat16, device=dev)
+        if pair:
+            pp = engine.to_pair(psi)
+            combined[..., 2 * M:4 * M] = pp[..., :2 * M]; combined[..., 6 * M:8 * M] = pp[..., 2 * M:]
+        else:
+            combined[..., 2 * M:] = psi.to(torch.bfloat16)
+        ep = model.entropy_parameters.ops
+        model.context_model.masked.apply_mask_()
+
+        def ctx_ep(i, with_lik=True):
+            model.context_model.masked._op.run(y_in_nhwc, B, hy, wy, args.precision, out=combined, out_c_total=4 * M, out_c_offset=0)
+            a = ep[0].run(combined, B, hy, wy, args.precision)
+            a = ep[1].run(a, B, hy, wy, args.precision)
+            raw = ep[2].run(a, B, hy, wy, args.precision, out_layout=_lib.LAYOUT_NCHW, out_dtype=torch.float32)
+            if with_lik:
+                _gml(y_in_nchw, raw, M, K, _QP, full=True, want_y_in=False)
+
+        def time_c3(with_lik):
+            for i in range(3):
+                ctx_ep(i, with_lik)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n3 = max(20, args.steps)
+            a.record()
+            for i in range(n3):
+                ctx_ep(i, with_lik)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n3
+        with torch.no_grad():
+            ms_c3, ms_c3l = time_c3(False), time_c3(True)
+        c3_flops = 5.7378e9 * B
+        config3 = {"workload": "BASELINE.json configs[2] isolated: masked 5x5 context conv (12 live taps) + entropy-parameter 1x1 stack "
+                               "512->640->640->1152 on y_in [B,128,32,48], psi [B,256,32,48]; + GM-K3 likelihood kernel (full dict)",
+                   "batch": B, "ms_context_plus_stack": ms_c3, "ms_with_likelihood": ms_c3l, "algorithmic_gflop": c3_flops / 1e9,
+                   "tflops": c3_flops / (ms_c3 / 1e3) / 1e12, "frac_of_bf16_peak": c3_flops / (ms_c3 / 1e3) / 1e12 / peaks["bf16_burst"],
+                   "images_per_s": B / (ms_c3l / 1e3), "launch": "per-kernel launches (back to back, inputs L2-resident as in the model)"}
+        del combined, psi, yq
     # ---- the other precision arms on the same workload (short runs), reported beside the headline arm -----------------
     other_arms = {}
     if not args.no_other_arms:
         for arm in ("bf16x3", "bf16", "fp32"):
             if arm == args.precision:
                 continue
-            m2 = Hh.seeded_model(M, K, "calib", precision=arm).to(dev)
+            m2 = bench_model(arm, dev)
             ev2 = parallel.ShardedEvaluator(m2, LAMBDA, lean=False, graph=use_graph and arm != "fp32")
             n2 = 3 if arm == "fp32" else max(5, args.steps)
             for i in range(3):
@@ -348,7 +487,7 @@ def main():
             del evaluator, flush
             torch.cuda.empty_cache()
             tb = 8
-            tmodel = Hh.seeded_model(M, K, "calib", precision=args.precision).to(dev)
+            tmodel = bench_model(args.precision, dev)
             trainer = parallel.ShardedTrainer(tmodel, LAMBDA, lr=1e-4, graph=use_graph)
             tgen = torch.Generator(device="cpu"); tgen.manual_seed(2000 + rank)
             crops = [torch.rand((tb, 3, 256, 256), generator=tgen).to(dev) for _ in range(4)]
@@ -381,7 +520,7 @@ def main():
     if not args.no_scalable:
         try:
             from neural_image_compression_b200.RateDistortionLoss import vision_rd_loss
-            smodel = Hh.seeded_scalable_model(192, 128, 1, "calib", precision="bf16x3").to(dev)
+            smodel = bench_scalable_model(dev)
             sgen = torch.Generator(device="cpu"); sgen.manual_seed(3000 + rank)
             simgs = [torch.rand((1, 3, 1536, 2048), generator=sgen).to(dev) for _ in range(2)]
             with torch.no_grad():
@@ -410,7 +549,7 @@ def main():
 
     assert lib.nic_pipeline_status() == 0, "a tensor-core kernel aborted on an expired pipeline wait: numbers invalid"
     if rank == 0:
-        cpu = None if args.no_cpu_baseline else cpu_reference_arm(2, 3)
+        cpu = None if args.no_cpu_baseline else cpu_reference_arm(B_PER_GPU, 6, warmup=1)
         line = {
             "metric": "768x512 images/s (fwd+likelihood+rd terms)", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -437,6 +576,10 @@ def main():
             line["train_step"] = train
         if scalable is not None:
             line["scalable_variant"] = scalable
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if config3 is not None:
+            line["config3_context_entropy"] = config3
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if world > 1:

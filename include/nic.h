@@ -92,7 +92,7 @@ typedef struct nic_conv_desc {
   int32_t kh, kw, stride, pad;      /* kernel, stride (1|2), padding                            */
   int32_t transposed;               /* 0: Conv2d, 1: ConvTranspose2d                            */
   int32_t output_padding;           /* ConvTranspose2d only                                     */
-  int32_t mask_a;                   /* 1: PixelCNN mask 'A' (ContextModels.py:13-16)            */
+  int32_t mask_a;                   /* 1: PixelCNN mask 'A', 2: mask 'B' (ContextModels.py:13-16) */
   int32_t epilogue;                 /* NIC_EPI_*                                                */
   int32_t precision;                /* NIC_PREC_*                                               */
   int32_t in_layout, out_layout;    /* NIC_LAYOUT_*                                             */
@@ -200,6 +200,10 @@ int nic_gm_likelihood_fwd(const float* y, const float* raw, const float* noise,
  */
 int nic_gm_pmf_fwd(const float* x, const float* weights, const float* mus, const float* sigmas,
                    int32_t b, int32_t m, int32_t hw, int32_t k, float* p, void* stream);
+/* The same WITHOUT the clamp: GaussianConditional.discretized_gaussian_pmf (EntropyModels.py:192-204, k = 1) and
+ * GaussianMixtureConditional.discretized_mixture_pmf (:214-230), public methods of the reference that return the raw mass. */
+int nic_gm_pmf_mass_fwd(const float* x, const float* weights, const float* mus, const float* sigmas,
+                        int32_t b, int32_t m, int32_t hw, int32_t k, float* mass, void* stream);
 
 /*
  * Factorized prior likelihood (per-channel 1-3-3-3-1 MLP), NCHW f32.
@@ -355,6 +359,12 @@ int nic_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
 int nic_adam_multi_step(float* const* p_host, const float* const* g_host, float* const* m_host, float* const* v_host,
                         const int64_t* n_host, int32_t count, float lr, float beta1, float beta2, float eps, int32_t step,
                         const int32_t* step_dev, void* stream);
+/* The same with (a) the learning rate read from DEVICE memory when lr_dev != NULL (an lr scheduler's change - Trainer.py:33-36,
+ * 103 - then reaches a captured launch without re-capturing; `lr` is ignored) and (b) every gradient multiplied by grad_scale
+ * first (1 / world folds the data-parallel averaging of all-reduced SUMS into the update; 1 = plain Adam). */
+int nic_adam_multi_step_ex(float* const* p_host, const float* const* g_host, float* const* m_host, float* const* v_host,
+                           const int64_t* n_host, int32_t count, float lr, const float* lr_dev, float grad_scale, float beta1, float beta2,
+                           float eps, int32_t step, const int32_t* step_dev, void* stream);
 /* *counter += 1 on the device (stream-ordered, graph-capturable) */
 int nic_counter_increment(int32_t* counter, void* stream);
 

@@ -19,15 +19,13 @@ class MaskedConv2d(nn.Conv2d):
         super().__init__(*args, **kwargs)
         if mask_type not in ("A", "B"):
             raise AssertionError("mask_type must be 'A' or 'B'")
-        if mask_type == "B":
-            raise NotImplementedError("mask 'B' is not on the reference's path (ContextModels.py:27 uses 'A')")
         kh, kw = self.kernel_size
         mask = torch.ones_like(self.weight.data)
-        mask[:, :, kh // 2, kw // 2:] = 0
+        mask[:, :, kh // 2, kw // 2 + (mask_type == "B"):] = 0      # 'B' keeps the centre tap (ContextModels.py:15)
         mask[:, :, kh // 2 + 1:] = 0
         self.register_buffer("mask", mask)
         self.precision = None
-        self._op = engine.ConvOp(self, EPI_BIAS, mask_a=True)
+        self._op = engine.ConvOp(self, EPI_BIAS, mask_a=1 if mask_type == "A" else 2)
         self._masked_version = None
 
     def apply_mask_(self):

@@ -179,7 +179,7 @@ class FactorizedEntropyBottleneck(EntropyModel):
         return (up - lo).clamp_min(1e-12)
 
 
-def _gm_pmf(x: Tensor, weights, mus: Tensor, sigmas: Tensor, K: int) -> Tensor:
+def _gm_pmf(x: Tensor, weights, mus: Tensor, sigmas: Tensor, K: int, clamp: bool = True) -> Tensor:
     lib = _lib.load()
     engine.require_cuda(x, "x")
     x = x.contiguous().float()
@@ -191,8 +191,8 @@ def _gm_pmf(x: Tensor, weights, mus: Tensor, sigmas: Tensor, K: int) -> Tensor:
     weights, mus, sigmas = prep(weights), prep(mus), prep(sigmas)
     p = torch.empty_like(x)
     with torch.cuda.device(x.device):
-        check(lib.nic_gm_pmf_fwd(ptr(x), ptr(weights), ptr(mus), ptr(sigmas), b, m, hw, K, ptr(p), current_stream()),
-              "nic_gm_pmf_fwd")
+        fn = lib.nic_gm_pmf_fwd if clamp else lib.nic_gm_pmf_mass_fwd
+        check(fn(ptr(x), ptr(weights), ptr(mus), ptr(sigmas), b, m, hw, K, ptr(p), current_stream()), "nic_gm_pmf_fwd")
     return p
 
 
@@ -200,7 +200,15 @@ class GaussianConditional(EntropyModel):
     """Mean-scale Gaussian bin mass (EntropyModels.py:188-207)."""
 
     def discretized_gaussian_pmf(self, x: Tensor, mu: Tensor, sigma: Tensor) -> Tensor:
-        raise NotImplementedError("use forward(); the unclamped mass is not materialised by the kernel")
+        """Phi((x + .5 - mu) / sigma) - Phi((x - .5 - mu) / sigma), unclamped (EntropyModels.py:192-204).  x [B, M, ...] with mu /
+        sigma broadcastable to it; the reference's mixture code also calls it with x [B, 1, M, ...] against [B, K, M, ...]
+        parameters - that form returns the per-component masses [B, K, M, ...]."""
+        if x.dim() >= 3 and mu.dim() == x.dim() and x.shape[1] == 1 and mu.shape[1] > 1 and x.shape[2:] == mu.shape[2:]:
+            K = int(mu.shape[1])
+            xe = x.expand(mu.shape).reshape((x.shape[0], K * mu.shape[2]) + tuple(mu.shape[3:]))
+            flat = lambda t: t.expand(mu.shape).reshape(xe.shape)                 # noqa: E731
+            return _gm_pmf(xe, None, flat(mu), flat(sigma), 1, clamp=False).reshape(mu.shape)
+        return _gm_pmf(x, None, mu, sigma, 1, clamp=False)
 
     def _likelihood(self, x: Tensor, mu: Tensor, sigma: Tensor) -> Tensor:
         return _gm_pmf(x, None, mu, sigma, 1)
@@ -208,6 +216,10 @@ class GaussianConditional(EntropyModel):
 
 class GaussianMixtureConditional(GaussianConditional):
     """K-component mixture of Gaussian bin masses (EntropyModels.py:210-233)."""
+
+    def discretized_mixture_pmf(self, x: Tensor, weights: Tensor, mus: Tensor, sigmas: Tensor) -> Tensor:
+        """sum_k w_k * pmf_k, unclamped (EntropyModels.py:214-230): x [B, M, H, W]; weights / mus / sigmas [B, K, M, H, W]."""
+        return _gm_pmf(x, weights, mus, sigmas, int(mus.shape[1]), clamp=False)
 
     def _likelihood(self, x: Tensor, weights: Tensor, mus: Tensor, sigmas: Tensor) -> Tensor:
         return _gm_pmf(x, weights, mus, sigmas, int(mus.shape[1]))

@@ -50,6 +50,7 @@ SIGNATURES = {
     "nic_partials_per_image": (_i32, []),
     "nic_gm_likelihood_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nic_gm_pmf_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "nic_gm_pmf_mass_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "nic_pack_factorized": (C.c_int, [_i32] + [_vp] * 11 + [_vp, _vp]),
     "nic_factorized_likelihood_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "nic_sse_fwd": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
@@ -74,6 +75,7 @@ SIGNATURES = {
     "nic_ms_ssim_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "nic_ms_ssim_levels": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _sz, _vp]),
     "nic_adam_multi_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
+    "nic_adam_multi_step_ex": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
     "nic_counter_increment": (C.c_int, [_vp, _vp]),
     "nic_to_pair": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "nic_gdn_reparam": (C.c_int, [_i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),

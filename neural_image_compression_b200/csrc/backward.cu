@@ -382,11 +382,16 @@ __global__ void counter_increment_kernel(int* c) { if (threadIdx.x == 0 && block
 // step_dev != NULL: the step count lives on the device (a CUDA-graph replay of the launch must see a new t every time)
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(const __grid_constant__ AdamArgs a, float beta1, float beta2, float lr, float step_size, float sqrt_bc2, float eps,
-                  const int* __restrict__ step_dev) {
-  if (step_dev) {
-    const int t = *step_dev;
+                  const int* __restrict__ step_dev, const float* __restrict__ lr_dev, float gscale) {
+  if (lr_dev) lr = *lr_dev;                  // learning rate on the device: a scheduler's change reaches a CUDA-graph replay
+  if (step_dev || lr_dev) {
+    const int t = step_dev ? *step_dev : 0;
+    if (!step_dev) {                           // host step count: only the learning rate is re-read
+      step_size = lr * step_size;              // step_size carries 1 / bc1 in this case (see nic_adam_multi_step_ex)
+    } else {
     step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(beta1), t)));
     sqrt_bc2 = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), t)));
+    }
   }
   int lo = 0, hi = a.count;                                   // largest t with blk_start[t] <= blockIdx.x
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.blk_start[mid] <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid; }
@@ -397,7 +402,7 @@ adam_multi_kernel(const __grid_constant__ AdamArgs a, float beta1, float beta2, 
   long i1 = i0 + kAdamChunk;
   if (i1 > n) i1 = n;
   for (long i = i0 + threadIdx.x; i < i1; i += 256) {
-    const float gv = g[i];
+    const float gv = g[i] * gscale;                             // gscale = 1 / world: the all-reduced SUM becomes the mean here
     const float mv = m[i] + (gv - m[i]) * (1.0f - beta1);
     const float vv = v[i] * beta2 + (1.0f - beta2) * gv * gv;
     m[i] = mv; v[i] = vv;
@@ -795,6 +800,12 @@ int nic_counter_increment(int32_t* counter, void* stream) {
 int nic_adam_multi_step(float* const* p_host, const float* const* g_host, float* const* m_host, float* const* v_host,
                         const int64_t* n_host, int32_t count, float lr, float beta1, float beta2, float eps, int32_t step,
                         const int32_t* step_dev, void* stream) {
+  return nic_adam_multi_step_ex(p_host, g_host, m_host, v_host, n_host, count, lr, nullptr, 1.0f, beta1, beta2, eps, step, step_dev, stream);
+}
+
+int nic_adam_multi_step_ex(float* const* p_host, const float* const* g_host, float* const* m_host, float* const* v_host,
+                           const int64_t* n_host, int32_t count, float lr, const float* lr_dev, float grad_scale, float beta1, float beta2,
+                           float eps, int32_t step, const int32_t* step_dev, void* stream) {
   if (int rc = nic_check_device()) return rc;
   if (step_dev) step = 1;                       // unused: the kernel reads the device counter
   if (count < 0 || step < 1 || (count > 0 && (!p_host || !g_host || !m_host || !v_host || !n_host))) return fail(NIC_E_BADSHAPE, "adam_multi_step: bad arguments");
@@ -813,8 +824,10 @@ int nic_adam_multi_step(float* const* p_host, const float* const* g_host, float*
     a.blk_start[cnt] = static_cast<int>(blocks);
     a.count = cnt;
     if (blocks == 0) continue;
-    adam_multi_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(a, beta1, beta2, lr, static_cast<float>(lr / bc1),
-                                                                                  static_cast<float>(sqrt(bc2)), eps, step_dev);
+    // device learning rate with a HOST step count: the kernel forms step_size = lr_dev / bc1 from the 1 / bc1 passed here
+    const float step_size = (lr_dev && !step_dev) ? static_cast<float>(1.0 / bc1) : static_cast<float>(lr / bc1);
+    adam_multi_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(a, beta1, beta2, lr, step_size,
+                                                                                  static_cast<float>(sqrt(bc2)), eps, step_dev, lr_dev, grad_scale);
     if (int rc = check_launch("adam_multi_kernel")) return rc;
   }
   return NIC_OK;

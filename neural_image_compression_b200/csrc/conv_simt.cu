@@ -47,7 +47,7 @@ int build_tap_table(const nic_conv_desc* d, TapTable* t) {
     t->py[0] = t->px[0] = 0; t->phase_begin[0] = 0;
     for (int kh = 0; kh < d->kh; ++kh)
       for (int kw = 0; kw < d->kw; ++kw) {
-        if (d->mask_a && !(kh < d->kh / 2 || (kh == d->kh / 2 && kw < d->kw / 2))) continue;
+        if (d->mask_a && !(kh < d->kh / 2 || (kh == d->kh / 2 && kw < d->kw / 2 + (d->mask_a == 2 ? 1 : 0)))) continue;   // 'A'; 2 = 'B': centre tap kept
         t->dy[q] = kh - d->pad; t->dx[q] = kw - d->pad; t->kh[q] = kh; t->kw[q] = kw; ++q;
       }
     t->phase_begin[1] = q;

@@ -93,9 +93,18 @@ class ShardedEvaluator:
         per_image, scalars = rd_terms(out, x_local, self.lambda_rd)
         return out, per_image, scalars
 
-    def _graphed_local(self, x_local):
-        key = (tuple(x_local.shape), x_local.device)
+    def _params_key(self):
+        """(storage, version) of every parameter and buffer: a captured graph is valid for exactly these weights."""
+        return tuple((t.data_ptr(), t._version) for t in list(self.model.parameters()) + list(self.model.buffers()))
+
+    def _graphed_local(self, x_local, slot: int = 0):
+        key = (tuple(x_local.shape), x_local.device, slot)
         ent = self._graphs.get(key)
+        if ent is not None and ent[3] != self._params_key():
+            # the weights changed since the capture (optimizer step, load_state_dict, .to()): the graph holds pointers to packed
+            # weights / GDN parameters / the factorized table derived from the OLD values - drop it and capture again
+            ent = None
+            self._graphs.pop(key)
         if ent is None:
             static_x = torch.empty_like(x_local)
             static_x.copy_(x_local)
@@ -113,21 +122,22 @@ class ShardedEvaluator:
             with torch.cuda.graph(g):
                 res = self._local(static_x)
             self.launches_per_step = int(lib.nic_launch_count() - n0)      # kernels of this library inside one replay
-            # the gradients the capture produced: every replay rewrites THESE tensors, so .grad must point at them again after
-            # a replay (the all-reduce below re-points .grad at views of its averaged buckets)
-            ent = (g, static_x, res, [p.grad for p in self.model.parameters()])
+            # the key is taken AFTER the warm-up (the masked conv zeroes its dead taps in place on the first forward, which
+            # bumps that parameter's version once); the packed caches the graph reads stay alive in the ConvOps until a
+            # weight changes, and a changed weight changes this key before the next replay
+            ent = (g, static_x, res, self._params_key())
             self._graphs[key] = ent
-        g, static_x, res, static_grads = ent
+        g, static_x, res, _ = ent
         if static_x.data_ptr() != x_local.data_ptr():
             static_x.copy_(x_local, non_blocking=True)
         g.replay()
-        for p, sg in zip(self.model.parameters(), static_grads):
-            p.grad = sg
         return res
 
-    def static_input(self, shape, device):
-        """The graph's input buffer for `shape` (fill it directly, e.g. with a pinned-host copy, to skip one device copy)."""
-        ent = self._graphs.get((tuple(shape), device))
+    def static_input(self, shape, device, slot: int = 0):
+        """The input buffer of graph `slot` for `shape` (fill it directly, e.g. with a pinned-host copy, to skip one device copy).
+        Two slots = two captured instances of the step with their own input and intermediate buffers: the host -> device copy
+        into one slot's input overlaps the replay of the other."""
+        ent = self._graphs.get((tuple(shape), device, slot))
         return None if ent is None else ent[1]
 
     @torch.no_grad()
@@ -144,7 +154,14 @@ class ShardedEvaluator:
         consumed = [None, None]                          # recorded on the compute stream once a step has been queued on the slot
 
         def upload(slot, hb):
-            if staging[slot] is None or staging[slot].shape != hb.shape:
+            if self.graph:
+                # the copy lands in the INPUT BUFFER of this slot's captured graph (captured on first use): no device -> device hop
+                tgt = self.static_input(hb.shape, dev, slot)
+                if tgt is None:
+                    self._graphed_local(hb.to(dev), slot)
+                    tgt = self.static_input(hb.shape, dev, slot)
+                staging[slot] = tgt
+            elif staging[slot] is None or staging[slot].shape != hb.shape:
                 staging[slot] = torch.empty(hb.shape, dtype=torch.float32, device=dev)
             with torch.cuda.stream(copy_stream):
                 if consumed[slot] is not None:
@@ -169,7 +186,7 @@ class ShardedEvaluator:
             if nxt is not None:
                 upload(cur ^ 1, nxt)                    # overlaps the step below; slot cur^1 was consumed two steps ago
             torch.cuda.current_stream().wait_event(ready[cur])
-            _, terms = self.step(staging[cur])
+            _, terms = self.step(staging[cur], slot=cur)
             if consumed[cur] is None:
                 consumed[cur] = torch.cuda.Event()
             consumed[cur].record()
@@ -184,8 +201,8 @@ class ShardedEvaluator:
         yield res_host[pending].tolist()
 
     @torch.no_grad()
-    def step(self, x_local: torch.Tensor):
-        out, per_image, scalars = self._graphed_local(x_local) if self.graph else self._local(x_local)
+    def step(self, x_local: torch.Tensor, slot: int = 0):
+        out, per_image, scalars = self._graphed_local(x_local, slot) if self.graph else self._local(x_local)
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return out, scalars_to_terms(scalars, per_image)
         per_image = gather_per_image(per_image, self.group)
@@ -213,10 +230,11 @@ def grad_buckets(params, bucket_bytes: int = 32 << 20):
     return buckets
 
 
-def allreduce_gradients(buckets, group=None, flats=None):
+def allreduce_gradients(buckets, group=None, flats=None, average: bool = True):
     """Average .grad over the ranks: each bucket is flattened into one buffer, summed with one all-reduce (NCCL over NVLink on
     the GPUs; gloo in the CPU tests), divided by the world size and scattered back.  The reference's loss is a mean over the batch
     (RateDistortionLoss.py:19-27), so with equal shards the average of the per-rank gradients is the full-batch gradient.
+    average=False leaves the SUM in .grad (training.Adam then applies 1 / world inside its update kernel: grad_scale).
     Returns the async work handles' count (all are waited before returning)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
@@ -234,7 +252,8 @@ def allreduce_gradients(buckets, group=None, flats=None):
         works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, bucket))
     for work, flat, bucket in works:
         work.wait()
-        flat.div_(world)
+        if average:
+            flat.div_(world)
         off = 0
         for p in bucket:
             n = p.numel()
@@ -271,6 +290,13 @@ class ShardedTrainer:
 
     def _distributed(self) -> bool:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _allreduce(self):
+        """Gradient all-reduce; with training.Adam the division by the world size happens inside the update kernel."""
+        fold = hasattr(self.optimizer, "grad_scale") and self._distributed()
+        if fold:
+            self.optimizer.grad_scale = 1.0 / dist.get_world_size(self.group)
+        allreduce_gradients(self.buckets, self.group, self._flats, average=not fold)
 
     def _forward_backward(self, x_local, noise=None):
         """forward + loss + backward on the calling thread and stream (training.step_gradients: the same kernels loss.backward()
@@ -315,6 +341,8 @@ class ShardedTrainer:
         g, static_x, res, static_grads = ent
         if static_x.data_ptr() != x_local.data_ptr():
             static_x.copy_(x_local, non_blocking=True)
+        if fuse_adam and hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()                          # a scheduler's new lr reaches the captured update through device memory
         g.replay()
         for p, sg in zip(self.model.parameters(), static_grads):
             p.grad = sg
@@ -330,7 +358,7 @@ class ShardedTrainer:
                 (loss, per_image, scalars), adam_done = self._graphed(x_local)
             else:
                 (loss, per_image, scalars), adam_done = self._forward_backward(x_local, noise), False
-            allreduce_gradients(self.buckets, self.group, self._flats)
+            self._allreduce()
             if not adam_done:
                 self.optimizer.step()
             self.step_count += 1
@@ -341,7 +369,7 @@ class ShardedTrainer:
         out = self.model(x_local, training=True, noise=noise, lean=True)
         rd = rd_loss(out, x_local, self.lambda_rd)
         rd["loss"].backward()
-        allreduce_gradients(self.buckets, self.group, self._flats)
+        self._allreduce()
         self.optimizer.step()
         self.step_count += 1
         return rd

@@ -716,15 +716,75 @@ class _RDLoss(torch.autograd.Function):
         return gl.expand(ctx.shapes[0]), gl.expand(ctx.shapes[1]), gx, None, None, None
 
 
-class Adam:
-    """torch.optim.Adam(params, lr) (Main.ipynb:133; defaults betas (0.9, 0.999), eps 1e-8, no weight decay) on nic_adam_step."""
+class Adam(torch.optim.Optimizer):
+    """torch.optim.Adam(params, lr) (Main.ipynb:133; defaults betas (0.9, 0.999), eps 1e-8, no weight decay) on the one-launch
+    update kernel (nic_adam_multi_step_ex).
 
-    def __init__(self, params, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
-        self.params: List[torch.Tensor] = [p for p in params]
-        self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+    A torch.optim.Optimizer: ``param_groups`` (so ``ReduceLROnPlateau`` / ``CosineAnnealingLR`` and ``param_groups[0]['lr']`` of
+    Trainer.py:33-36, 103 work), and ``state_dict()`` / ``load_state_dict()`` in torch.optim.Adam's own format (per parameter
+    ``step``, ``exp_avg``, ``exp_avg_sq``), so the reference's checkpoints (Trainer.py:52-68) round-trip in both directions.
+    The learning rate the kernel uses lives in DEVICE memory and is refreshed from ``param_groups`` before every launch / replay
+    (``sync_lr``): a scheduler's change reaches a CUDA-graph replay of the update without re-capturing.  One parameter group."""
+
+    def __init__(self, params, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, amsgrad: bool = False):
+        if weight_decay != 0.0 or amsgrad:
+            raise ValueError("Adam: weight_decay / amsgrad are not built (the reference trains with torch.optim.Adam(lr) defaults)")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0.0, amsgrad=False, maximize=False, foreach=None, capturable=False,
+                        differentiable=False, fused=None, decoupled_weight_decay=False)
+        super().__init__(params, defaults)
+        if len(self.param_groups) != 1:
+            raise ValueError("Adam: one parameter group")
+        self.params: List[torch.Tensor] = list(self.param_groups[0]["params"])
+        self.t = 0                                       # steps taken (host mirror of the device counter)
         self._t_dev = None                               # the step count on the device (what the update kernel reads)
+        self._lr_dev, self._lr_host = None, None         # the learning rate on the device + the value last written there
+        self.grad_scale = 1.0                            # gradients are multiplied by this inside the kernel (1 / world for SUM all-reduces)
         self.m = [torch.zeros_like(p, dtype=torch.float32) for p in self.params]
         self.v = [torch.zeros_like(p, dtype=torch.float32) for p in self.params]
+
+    # ---- torch.optim.Adam-compatible checkpoint format -------------------------------------------------------------------
+    @property
+    def lr(self) -> float:
+        return float(self.param_groups[0]["lr"])
+
+    @lr.setter
+    def lr(self, value: float):
+        self.param_groups[0]["lr"] = float(value)
+
+    @property
+    def betas(self):
+        return tuple(self.param_groups[0]["betas"])
+
+    @property
+    def eps(self) -> float:
+        return float(self.param_groups[0]["eps"])
+
+    def _publish_state(self):
+        """self.state in torch.optim.Adam's layout; exp_avg / exp_avg_sq ALIAS the buffers the kernel updates."""
+        for p, m, v in zip(self.params, self.m, self.v):
+            self.state[p] = {"step": torch.tensor(float(self.t)), "exp_avg": m, "exp_avg_sq": v}
+
+    def state_dict(self):
+        self._publish_state()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self.params = list(self.param_groups[0]["params"])
+        steps = set()
+        for i, p in enumerate(self.params):
+            st = self.state.get(p)
+            if not st:
+                continue
+            self.m[i] = st["exp_avg"].to(device=p.device, dtype=torch.float32).contiguous()
+            self.v[i] = st["exp_avg_sq"].to(device=p.device, dtype=torch.float32).contiguous()
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"Adam.load_state_dict: parameters at different step counts {sorted(steps)} (one shared counter is built)")
+        self.t = steps.pop() if steps else 0
+        if self._t_dev is not None:
+            self._t_dev.fill_(self.t)                     # the device counter follows the restored step count
+        self._lr_host = None                              # re-upload the restored learning rate
 
     def zero_grad(self, set_to_none: bool = True):
         for p in self.params:
@@ -733,11 +793,23 @@ class Adam:
             elif p.grad is not None:
                 p.grad.zero_()
 
+    def sync_lr(self, dev=None):
+        """Write param_groups[0]['lr'] to the device scalar if it changed (a 4-byte stream-ordered copy; called before every launch
+        and before every graph replay - never inside a capture)."""
+        if self._lr_dev is None:
+            if dev is None:
+                return
+            self._lr_dev = torch.empty(1, dtype=torch.float32, device=dev)
+        if self._lr_host != self.lr and not torch.cuda.is_current_stream_capturing():
+            self._lr_dev.fill_(self.lr)
+            self._lr_host = self.lr
+
     @torch.no_grad()
     def launch(self):
         """Advance the device step counter and update every parameter that has a gradient: two stream-ordered launches
-        (nic_counter_increment, nic_adam_multi_step with the pointers as launch arguments), no upload, no host
-        synchronisation, capturable in a CUDA graph (the bias corrections are formed on the device from the counter)."""
+        (nic_counter_increment, nic_adam_multi_step_ex with the pointers as launch arguments), no upload, no host
+        synchronisation, capturable in a CUDA graph (the bias corrections are formed on the device from the counter, the
+        learning rate is read from its device scalar)."""
         lib = _lib.load()
         live = [(p, p.grad.contiguous().float(), m, v) for p, m, v in zip(self.params, self.m, self.v) if p.grad is not None]
         if not live:
@@ -750,19 +822,26 @@ class Adam:
         arr = lambda k: (C.c_void_p * n)(*[t[k].data_ptr() for t in live])     # noqa: E731
         counts = (C.c_int64 * n)(*[t[0].numel() for t in live])
         with torch.cuda.device(dev):
+            self.sync_lr(dev)
             check(lib.nic_counter_increment(ptr(self._t_dev), current_stream()), "nic_counter_increment")
-            check(lib.nic_adam_multi_step(arr(0), arr(1), arr(2), arr(3), counts, n, self.lr, self.betas[0], self.betas[1], self.eps,
-                                          1, ptr(self._t_dev), current_stream()), "nic_adam_multi_step")
+            check(lib.nic_adam_multi_step_ex(arr(0), arr(1), arr(2), arr(3), counts, n, self.lr, ptr(self._lr_dev), float(self.grad_scale),
+                                             self.betas[0], self.betas[1], self.eps, 1, ptr(self._t_dev), current_stream()),
+                  "nic_adam_multi_step_ex")
         self._keep = live                                 # the gradients stay alive until the next launch
 
     def prepare(self, dev):
-        """Create the device step counter (outside any CUDA-graph capture: a captured fill would reset it on every replay)."""
+        """Create the device step counter and learning-rate scalar (outside any CUDA-graph capture: a captured fill would reset
+        them on every replay)."""
         if self._t_dev is None or self._t_dev.device != dev:
             self._t_dev = torch.full((1,), self.t, dtype=torch.int32, device=dev)
+        if self._lr_dev is None or self._lr_dev.device != dev:
+            self._lr_dev, self._lr_host = torch.full((1,), self.lr, dtype=torch.float32, device=dev), self.lr
 
-    def step(self):
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
         self.launch()
         self.t += 1
         for p in self.params:
             if p.grad is not None:
                 torch.autograd.graph.increment_version(p)       # updated behind torch's back: packed-weight caches key on _version
+        return loss

@@ -127,7 +127,15 @@ def likelihood_close(p, p_ref):
 # the reference's vectors is made on the elements that are NOT a function of a flipped symbol (masks below), and a second
 # comparison - the oracle's entropy path and synthesis transform evaluated on THIS run's symbols - covers 100 % of the elements.
 TIE_TAU = 2e-3            # |frac(y_ref) - 0.5| below which a flip counts as a tie
-TIE_RATE = 2e-4           # bound on tie flips / symbols (observed: 4e-5 .. 9e-5 at std(y) = 8, the calib / gain weight sets)
+PRE_RTOL = 1e-4           # fp32-grade bound on max |y - y_ref| / max |y_ref| (and z likewise), measured before the rounding
+
+
+def tie_flip_bound(pre, pre_ref):
+    """How many rounding-tie flips the measured pre-rounding error explains.  The fractional part of y is uniformly distributed, so a
+    value perturbed by d rounds the other way with probability 2 |d|: the expected number of flips is 2 sum |y - y_ref|
+    (calib weights, std(y) = 2: ~7e-5 of the symbols in the bf16x3 arm; gain weights, std(y) = 8: ~3e-4).  Bound: 3x that + 3
+    (Poisson slack).  Together with PRE_RTOL this ties the flip count to an fp32-grade error on y instead of exempting a window."""
+    return 6.0 * float(np.abs(np.asarray(pre, np.float64) - np.asarray(pre_ref, np.float64)).sum()) + 3.0
 
 
 def _dilate(m, kh, kw):

@@ -119,6 +119,44 @@ def test_conditional_modules_match_oracle(dev):
     assert H.likelihood_close(p1.cpu().numpy(), O.conditional_likelihood(x, (mu[:, 0], s[:, 0]), 1).numpy())[0] == 0
 
 
+def test_public_pmf_methods_are_unclamped_like_the_reference(dev):
+    """GaussianConditional.discretized_gaussian_pmf / GaussianMixtureConditional.discretized_mixture_pmf (EntropyModels.py:192-230)
+    return the raw bin mass: no 1e-9 clamp (it is EntropyModel.forward that clamps, :29-31)."""
+    from neural_image_compression_b200.EntropyModels import GaussianConditional, GaussianMixtureConditional
+    torch.manual_seed(8)
+    x = torch.round(12 * torch.randn(2, 16, 4, 4))                     # far tails: many masses below the clamp
+    raw = torch.randn(2, 9 * 16, 4, 4)
+    w, mu, s = O.split_parameters(raw, 16, 3)
+    ref_k = O.gaussian_pmf(x.unsqueeze(1), mu, s)
+    ref = torch.sum(w * ref_k, dim=1)
+    assert float(ref.min()) < 1e-9
+    gm = GaussianMixtureConditional()
+    got = gm.discretized_mixture_pmf(x.to(dev), w.to(dev), mu.to(dev), s.to(dev)).cpu()
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-4, atol=H.P_ATOL)
+    assert float(got.min()) < 1e-9
+    got_k = gm.discretized_gaussian_pmf(x.to(dev).unsqueeze(1), mu.to(dev), s.to(dev)).cpu()        # the reference's own inner call
+    assert got_k.shape == ref_k.shape
+    np.testing.assert_allclose(got_k.numpy(), ref_k.numpy(), rtol=1e-4, atol=H.P_ATOL)
+    got1 = GaussianConditional().discretized_gaussian_pmf(x.to(dev), mu[:, 0].to(dev), s[:, 0].to(dev)).cpu()
+    np.testing.assert_allclose(got1.numpy(), O.gaussian_pmf(x, mu[:, 0], s[:, 0]).numpy(), rtol=1e-4, atol=H.P_ATOL)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_masked_conv_type_b_keeps_the_centre_tap(dev, precision):
+    """MaskedConv2d('B', ...) is accepted by the reference (ContextModels.py:11, 15) though its model only uses 'A'."""
+    import torch.nn.functional as F
+    from neural_image_compression_b200.ContextModels import MaskedConv2d
+    torch.manual_seed(9)
+    conv = MaskedConv2d("B", in_channels=128, out_channels=256, kernel_size=5, stride=1, padding=2)
+    conv.precision = precision
+    assert int(conv.mask[0, 0].sum()) == 13 and float(conv.mask[0, 0, 2, 2]) == 1
+    x = torch.round(4 * torch.randn(2, 128, 8, 12))
+    ref = F.conv2d(x.double(), (conv.weight.detach() * conv.mask).double(), conv.bias.detach().double(), padding=2)
+    got = conv.to(dev)(x.to(dev)).cpu().double()
+    assert float((got - ref).abs().max() / ref.abs().max()) < 3e-5
+    assert float(conv.weight.detach()[:, :, 2, 3:].abs().max()) == 0 and float(conv.weight.detach()[:, :, 2, 2].abs().max()) > 0
+
+
 def test_rd_loss_terms_match_oracle(dev):
     from neural_image_compression_b200.RateDistortionLoss import rd_loss
     torch.manual_seed(7)

@@ -367,3 +367,75 @@ def test_factorized_backward_kernel_against_autograd():
     for name, idx, lo, hi in _FACT_SLICES:
         ref = sd[f"factorized_entropy_model.{name}.{idx}"].grad
         assert rel_err(dpar[:, lo:hi].reshape(ref.shape), ref) < 1e-4, (name, idx, rel_err(dpar[:, lo:hi].reshape(ref.shape), ref))
+
+
+def test_adam_is_a_torch_optimizer_with_reference_checkpoint_format():
+    """training.Adam against torch.optim.Adam itself: identical updates over 5 steps with an lr schedule (CosineAnnealingLR writes
+    param_groups[0]['lr'], Trainer.py:33-36), and state_dict() / load_state_dict() interchange in both directions mid-run
+    (the reference's checkpoint carries optimizer.state_dict(), Trainer.py:52-68)."""
+    from neural_image_compression_b200.training import Adam
+    torch.manual_seed(21)
+    shapes = [(33, 7), (129,), (2, 64, 5, 5)]
+    ours = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    theirs = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    a, t = Adam(ours, lr=1e-3), torch.optim.Adam(theirs, lr=1e-3)
+    sa, st = torch.optim.lr_scheduler.CosineAnnealingLR(a, T_max=8), torch.optim.lr_scheduler.CosineAnnealingLR(t, T_max=8)
+
+    def one_step(a, t):
+        for p, q in zip(a.param_groups[0]["params"], t.param_groups[0]["params"]):
+            g = torch.randn_like(p)
+            p.grad, q.grad = g, g.clone()
+        a.step(); t.step()
+
+    for _ in range(3):
+        one_step(a, t); sa.step(); st.step()
+    assert abs(a.param_groups[0]["lr"] - t.param_groups[0]["lr"]) < 1e-12 and a.param_groups[0]["lr"] < 1e-3
+    for p, q in zip(ours, theirs):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=3e-6, atol=1e-8)
+    # ours -> torch: a fresh torch.optim.Adam resumes from our checkpoint;  torch -> ours: and the other way round
+    t2 = torch.optim.Adam(theirs, lr=5e-2); t2.load_state_dict(a.state_dict())
+    a2 = Adam(ours, lr=5e-2); a2.load_state_dict(t.state_dict())
+    assert a2.t == 3 and abs(a2.lr - t.param_groups[0]["lr"]) < 1e-12 and abs(t2.param_groups[0]["lr"] - a.lr) < 1e-12
+    for _ in range(2):
+        one_step(a2, t2)
+    torch.cuda.synchronize()
+    assert a2.t == 5 and int(a2._t_dev) == 5 and float(t2.state[theirs[0]]["step"]) == 5
+    for p, q in zip(ours, theirs):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=3e-6, atol=1e-8)
+
+
+def test_graphed_trainer_follows_a_learning_rate_change():
+    """The learning rate of a captured Adam launch lives on the device: lr = 0 between replays freezes the weights, and restoring
+    it moves them again - without re-capturing (a by-value lr would be baked into the graph)."""
+    from neural_image_compression_b200 import parallel
+    x = H.seeded_input((2, 3, 64, 64)).cuda()
+    model = H.seeded_model(128, 3, "calib", precision="bf16x3").cuda()
+    tr = parallel.ShardedTrainer(model, 0.005, lr=1e-4, graph=True)
+    tr.step(x); tr.step(x)
+    torch.cuda.synchronize()
+    ngraphs = len(tr._graphs)
+    w1 = model.decoder.net[6].weight.detach().clone()
+    tr.optimizer.param_groups[0]["lr"] = 0.0
+    tr.step(x); torch.cuda.synchronize()
+    assert torch.equal(model.decoder.net[6].weight.detach(), w1)
+    tr.optimizer.param_groups[0]["lr"] = 1e-4
+    tr.step(x); torch.cuda.synchronize()
+    assert not torch.equal(model.decoder.net[6].weight.detach(), w1) and len(tr._graphs) == ngraphs
+
+
+def test_graphed_evaluator_recaptures_after_a_weight_change():
+    """ShardedEvaluator(graph=True) held across optimizer steps / load_state_dict must not replay against stale packed weights."""
+    from neural_image_compression_b200 import parallel
+    x = H.seeded_input((2, 3, 64, 128)).cuda()
+    model = H.seeded_model(128, 3, "calib", precision="bf16x3").cuda()
+    ev = parallel.ShardedEvaluator(model, 0.005, lean=True, graph=True)
+    _, t0 = ev.step(x)
+    _, t0b = ev.step(x)
+    assert float(t0["bpp_total"]) == float(t0b["bpp_total"])
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["entropy_parameters.net.4.bias"] = sd["entropy_parameters.net.4.bias"] + 0.5
+    model.load_state_dict(sd)
+    _, t1 = ev.step(x)
+    fresh = parallel.ShardedEvaluator(model, 0.005, lean=True, graph=False)
+    _, t2 = fresh.step(x)
+    assert float(t1["bpp_total"]) == float(t2["bpp_total"]) and abs(float(t1["bpp_total"]) - float(t0["bpp_total"])) > 1e-4

@@ -18,7 +18,8 @@ def _perturbed_run(sd, x, M, K, eps):
         y = O.analysis(sd, x)
         z = O.hyper_analysis(sd, y)
         torch.manual_seed(5)
-        y_in, z_in = torch.round(y + eps * torch.randn_like(y)), torch.round(z)
+        y = y + eps * torch.randn_like(y)                      # "our" y: the reference's + an fp32-grade error
+        y_in, z_in = torch.round(y), torch.round(z)
         psi, phi = O.hyper_synthesis(sd, z_in), O.context(sd, y_in)
         params = O.split_parameters(O.entropy_parameters_raw(sd, torch.cat([phi, psi], 1)), M, K)
         p_z, p_y = O.factorized_likelihood(sd, z_in), O.conditional_likelihood(y_in, params, K)
