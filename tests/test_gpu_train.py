@@ -391,7 +391,7 @@ def test_adam_is_a_torch_optimizer_with_reference_checkpoint_format():
         one_step(a, t); sa.step(); st.step()
     assert abs(a.param_groups[0]["lr"] - t.param_groups[0]["lr"]) < 1e-12 and a.param_groups[0]["lr"] < 1e-3
     for p, q in zip(ours, theirs):
-        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=3e-6, atol=1e-8)
+        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=3e-6, atol=1e-7)
     # ours -> torch: a fresh torch.optim.Adam resumes from our checkpoint;  torch -> ours: and the other way round
     t2 = torch.optim.Adam(theirs, lr=5e-2); t2.load_state_dict(a.state_dict())
     a2 = Adam(ours, lr=5e-2); a2.load_state_dict(t.state_dict())
@@ -401,7 +401,7 @@ def test_adam_is_a_torch_optimizer_with_reference_checkpoint_format():
     torch.cuda.synchronize()
     assert a2.t == 5 and int(a2._t_dev) == 5 and float(t2.state[theirs[0]]["step"]) == 5
     for p, q in zip(ours, theirs):
-        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=3e-6, atol=1e-8)
+        np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=3e-6, atol=1e-7)
 
 
 def test_graphed_trainer_follows_a_learning_rate_change():

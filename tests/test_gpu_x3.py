@@ -135,7 +135,7 @@ def test_x3_masked_context_conv_and_pointwise_stack():
     print(_close(_run(c3, x3, EPI_BIAS, out_nchw_f32=True), _ref(c3, x3, EPI_BIAS)))
 
 
-@pytest.mark.parametrize("hw", [(16, 24), (12, 20)])
+@pytest.mark.parametrize("hw", [(16, 24), (12, 20), (6, 14), (7, 15), (1, 1), (37, 53)])
 def test_x3_last_layer_to_rgb_nchw(hw):
     from neural_image_compression_b200._lib import EPI_BIAS
     torch.manual_seed(45)
