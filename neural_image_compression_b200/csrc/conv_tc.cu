@@ -191,6 +191,8 @@ struct TcParams {
   int out_dtype;                               // NIC_DT_*
   long ys_n, ys_c, ys_h, ys_w;                 // output strides (elements), channel offset already applied to y
   int flat_hw;                                 // > 0: 1x1 conv over a flattened pixel list; pixel p -> image p / flat_hw
+  int stage2;                                  // bf16-pair output with TWO staging tiles (hi tile, lo tile): no store is waited for
+                                               // right after it was issued (layers whose mainloop is as short as their epilogue)
   int tma_out;                                 // NHWC output leaves through shared memory + TMA tensor stores: 1 = bf16 (two
                                                // [128 px][64 ch] panels), 2 = f32 (four [128 px][32 ch] panels)
   int out_c_offset;                            // channel window start inside the output tensor (TMA coordinates)
@@ -342,10 +344,12 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
   }
   auto epi_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NW * 32) : "memory"); };
   if (p.tma_out) {
-    // the staging tile (= the squares tile) may still be read by the previous block's tensor store
-    if (leader) tma_store_wait_read();
+    // the staging tile (= the squares tile) may still be read by the previous block's tensor store; with two staging tiles
+    // the hi tile was handed to the store BEFORE the most recent one (the previous block's lo store)
+    if (leader) { if (p.stage2) tma_store_wait_read_1(); else tma_store_wait_read(); }
     epi_sync();
   }
+  uint8_t* stg = sq;                                        // staging tile of the current pass
   if (leader) trace(p, trace_tile, trace_base + 0);
   float xr[KEEPX ? NG * 32 : 32];
   if (gdn) {
@@ -411,7 +415,7 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(panel + ((j ^ (row & 7)) << 4)) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
     } else if (p.tma_out) {
-      uint8_t* half = sq + (cg >> 1) * (128 * 128) + row * 128;
+      uint8_t* half = stg + (cg >> 1) * (128 * 128) + row * 128;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int chunk = ((cg & 1) * 4 + j) ^ (row & 7);
@@ -491,8 +495,10 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
           for (int h = 0; h < 2; ++h)
             if (h * 64 < nvalid_c) tma_store_4d(map_o_ptr, sq + h * (128 * 128), p.out_c_offset + cbase + h * 64, wc, hc, img);
           tma_store_commit();
-          tma_store_wait_read();
+          // one tile: wait for this store; two tiles: the lo tile was handed to the store before this one (previous block)
+          if (p.stage2) tma_store_wait_read_1(); else tma_store_wait_read();
         }
+        if (p.stage2) stg = sq + 2 * 128 * 128;
         epi_sync();
       }
       for (int cg = first; cg < last; ++cg) {
@@ -531,7 +537,7 @@ __device__ __forceinline__ bool epilogue_block(const TcParams& p, TcBarriers* sb
           if (h * 32 < nvalid_c) tma_store_4d(map_o_ptr, sq + h * (128 * 128), p.out_c_offset + cbase + h * 32, wc, hc, img);
       } else {
         for (int h = 0; h < 2; ++h)
-          if (h * 64 < nvalid_c) tma_store_4d(map_o_ptr, sq + h * (128 * 128), p.out_c_offset + lo_off + cbase + h * 64, wc, hc, img);
+          if (h * 64 < nvalid_c) tma_store_4d(map_o_ptr, stg + h * (128 * 128), p.out_c_offset + lo_off + cbase + h * 64, wc, hc, img);
       }
       tma_store_commit();
     }
@@ -810,6 +816,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t d_tmem = tmem + buf * 256 + (swp ? 0 : mw * 128);
           const bool live = swp ? mw == 0 : mw < nblk;
           uint32_t accumulate = 0;
+          if (nplanes == 1 && ph.plane_tap_begin[1] - ph.plane_tap_begin[0] == 1) {
+            // one tap per K chunk (1x1 convs): the per-chunk bookkeeping of the generic loop below (one ring wait, one elect / warp
+            // barrier and two commits for 4 MMAs) costs more than the MMAs - two chunks per iteration: 8 MMAs per wait / elect round
+            const uint32_t aoff = s_tap_aoff[ph.plane_tap_begin[0]] + blk_off;
+            for (int chunk = 0; chunk < nchunks && ok; chunk += 2) {
+              const bool two = chunk + 1 < nchunks;
+              if (!mbar_try_wait(&sb.a_full[sa], pa) && !wait_or_abort(&sb.a_full[sa], pa, &sb, p.status)) { ok = false; break; }
+              if (chunk == 0 && lane == 0 && mw == 0) trace(p, tcount, 1);
+              const uint32_t sa0 = sa;
+              if (++sa == static_cast<uint32_t>(nsa)) { sa = 0; pa ^= 1; }
+              uint32_t sa1 = sa0;
+              if (two) {
+                if (!mbar_try_wait(&sb.a_full[sa], pa) && !wait_or_abort(&sb.a_full[sa], pa, &sb, p.status)) { ok = false; break; }
+                sa1 = sa;
+                if (++sa == static_cast<uint32_t>(nsa)) { sa = 0; pa ^= 1; }
+              }
+              if (!mbar_try_wait(&sb.b_full[sbi], pb) && !wait_or_abort(&sb.b_full[sbi], pb, &sb, p.status)) { ok = false; break; }
+              const uint32_t s0 = sbi;
+              if (++sbi == static_cast<uint32_t>(nsb)) { sbi = 0; pb ^= 1; }
+              uint32_t s1 = s0;
+              if (two) {
+                if (!mbar_try_wait(&sb.b_full[sbi], pb) && !wait_or_abort(&sb.b_full[sbi], pb, &sb, p.status)) { ok = false; break; }
+                s1 = sbi;
+                if (++sbi == static_cast<uint32_t>(nsb)) { sbi = 0; pb ^= 1; }
+              }
+              tcgen05_fence_after();
+              const uint32_t a_lo0 = a_base_lo + sa0 * slot16 + aoff, a_lo1 = a_base_lo + sa1 * slot16 + aoff;
+              const uint32_t b_lo0 = b_base_lo + s0 * ((128 * 128) >> 4), b_lo1 = b_base_lo + s1 * ((128 * 128) >> 4);
+              const uint32_t f0 = swp ? b_lo0 : a_lo0, g0 = swp ? a_lo0 : b_lo0, f1 = swp ? b_lo1 : a_lo1, g1 = swp ? a_lo1 : b_lo1;
+              if (elect_one()) {
+                if (live) {
+                  umma_bf16_lohi(d_tmem, f0, f_hi, g0, g_hi, idesc_use, accumulate);
+                  umma_bf16_lohi(d_tmem, f0 + 2, f_hi, g0 + 2, g_hi, idesc_use, 1);
+                  umma_bf16_lohi(d_tmem, f0 + 4, f_hi, g0 + 4, g_hi, idesc_use, 1);
+                  umma_bf16_lohi(d_tmem, f0 + 6, f_hi, g0 + 6, g_hi, idesc_use, 1);
+                }
+                umma_commit(&sb.b_empty[s0]);
+                umma_commit(&sb.a_empty[sa0]);
+                if (two) {
+                  if (live) {
+                    umma_bf16_lohi(d_tmem, f1, f_hi, g1, g_hi, idesc_use, 1);
+                    umma_bf16_lohi(d_tmem, f1 + 2, f_hi, g1 + 2, g_hi, idesc_use, 1);
+                    umma_bf16_lohi(d_tmem, f1 + 4, f_hi, g1 + 4, g_hi, idesc_use, 1);
+                    umma_bf16_lohi(d_tmem, f1 + 6, f_hi, g1 + 6, g_hi, idesc_use, 1);
+                  }
+                  umma_commit(&sb.b_empty[s1]);
+                  umma_commit(&sb.a_empty[sa1]);
+                }
+              }
+              __syncwarp();
+              accumulate = 1;
+            }
+          } else
           for (int chunk = 0; chunk < nchunks && ok; ++chunk) {
             for (int pl = 0; pl < nplanes && ok; ++pl) {
               if (!mbar_try_wait(&sb.a_full[sa], pa) && !wait_or_abort(&sb.a_full[sa], pa, &sb, p.status)) { ok = false; break; }
@@ -1429,7 +1488,12 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     // small layers: one block per tile when two-block tiles would leave SMs idle (fewer than two tiles per SM)
     const long tiles2 = static_cast<long>((p.wp + (stacked ? kTileW : 2 * kTileW) - 1) / (stacked ? kTileW : 2 * kTileW)) *
                         ((p.hp + (stacked ? 2 * kTileH : kTileH) - 1) / (stacked ? 2 * kTileH : kTileH)) * p.n * tt.nphases * p.n_ntiles;
-    if (tiles2 < 2 * kNumSMs) p.mt = 1;
+    // measured (bf16x3, 16 images, tools/layer_bench.py): with ONE block per tile only one of the two MMA issuers works and its
+    // per-tap bookkeeping bounds the tile, so two-block tiles win down to ~half a wave of tiles (h_a layer 1, 96 tiles: 46.9 ->
+    // 39.5 us; g_a layer 4, 96 tiles: 98.8 -> 67.9 us; context conv, 192 tiles: 80.8 -> 71.6 us) and lose below (h_a layer 2,
+    // 24 tiles: 54.9 -> 67.0 us)
+    if (tiles2 < kNumSMs / 2) p.mt = 1;
+    if (const char* e = getenv("NIC_TC_MT")) { const int f = atoi(e); if (f == 1) p.mt = 1; else if (f == 2 && (stacked ? p.hp > kTileH : p.wp > kTileW)) p.mt = 2; }   // timing experiments
   }
   if (p.mt == 1) swap = false;                   // one-block tiles: N = 128 either way, keep the normal orientation
   p.swap = swap ? 1 : 0;
@@ -1454,7 +1518,13 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     p.tma_out = 2;      // (y and z, the f32 tensors the latent hand-off reads: small layers, the ring depth does not matter there)
   // gamma (32 KB, GDN only) + one tile (32 KB; 64 KB for f32 outputs) that holds the squares for the gamma contraction and
   // then stages the output
-  const int stage_bytes = p.tma_out == 2 ? 4 * 128 * 128 : ((gdn || p.tma_out) ? 2 * 128 * 128 : 0);
+  // bf16-pair outputs of layers with a short mainloop (<= 96 tap-chunks per tile: the 1x1 stack, the 3x3 layers, the masked
+  // context conv): a second staging tile, so that the hi and lo stores of a block never wait for each other (each
+  // cp.async.bulk.wait_group.read right after its store costs 3-5k clk behind the TMA loads in flight - as long as such a
+  // layer's whole mainloop)
+  const int tapchunks = (tt.ntaps / tt.nphases) * p.nchunks;
+  p.stage2 = (p.split_out && p.tma_out == 1 && !gdn && !p.swap && tapchunks <= 96 && getenv("NIC_TC_STAGE2")) ? 1 : 0;   // measured: no gain (the smaller rings cost as much: ep2 96.5 -> 109.8 us), so opt-in only
+  const int stage_bytes = p.tma_out == 2 ? 4 * 128 * 128 : ((gdn || p.tma_out) ? (p.stage2 ? 4 : 2) * 128 * 128 : 0);
   const int gdn_bytes = (gdn ? 2 * 128 * 128 : 0) + stage_bytes;
   const int bres_bytes = tt.ntaps * p.nchunks * p.nb * 128;
   p.b_resident = (p.n_ntiles == 1 && p.nb <= 16 && bres_bytes + 2 * p.slot_bytes + gdn_bytes + 1024 <= kMaxDynSmem) ? 1 : 0;
@@ -1466,8 +1536,19 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   } else {
     // prefer a deep weight ring (TMA latency ~1 us vs ~0.13 us of MMA per slab and block), then A slots
     p.nsa = 2; p.nsb = 4;
-    if (2 * p.slot_bytes + 4 * 128 * 128 + gdn_bytes + 1024 > kMaxDynSmem)
+    if (2 * p.slot_bytes + 4 * 128 * 128 + gdn_bytes + 1024 > kMaxDynSmem) {
+      if (p.stage2) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: internal: staging tiles do not fit");   // cannot happen: slots of these layers are <= 42 KB
       return fail(NIC_E_UNSUPPORTED, "conv bf16: patch of %d x %d pixels does not fit shared memory", p.ph_rows, p.pw_cols);
+    }
+    const bool one_tap = tt.ntaps == tt.nphases;       // 1x1: an A slot is consumed per weight slab - balance the rings in slots, not bytes
+    if (one_tap) {
+      p.nsa = 2; p.nsb = 2;
+      for (;;) {
+        if (p.nsa <= p.nsb && p.nsa < kMaxSlots && (p.nsa + 1) * p.slot_bytes + p.nsb * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsa;
+        else if (p.nsb < kMaxBSlots && p.nsa * p.slot_bytes + (p.nsb + 1) * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsb;
+        else break;
+      }
+    } else
     for (;;) {
       if (p.nsb < kMaxBSlots && p.nsa * p.slot_bytes + (p.nsb + 1) * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem && p.nsb < 2 * p.nsa + 2) ++p.nsb;
       else if (p.nsa < kMaxSlots && (p.nsa + 1) * p.slot_bytes + p.nsb * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsa;
@@ -1477,7 +1558,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     {   // timing experiments: NIC_TC_NSA / NIC_TC_NSB force the ring depths (checked against the shared-memory budget)
       const char* ea = getenv("NIC_TC_NSA"); const char* eb = getenv("NIC_TC_NSB");
       const int fa = ea ? atoi(ea) : 0, fb = eb ? atoi(eb) : 0;
-      if ((fa || fb) && tt.nphases > 1) {
+      if (fa || fb) {
         const int na = fa ? fa : p.nsa, nb2 = fb ? fb : p.nsb;
         if (na >= 2 && na <= kMaxSlots && nb2 >= 2 && nb2 <= kMaxBSlots && na * p.slot_bytes + nb2 * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) { p.nsa = na; p.nsb = nb2; }
       }

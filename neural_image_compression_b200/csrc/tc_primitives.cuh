@@ -97,6 +97,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// at most ONE bulk store group still reading shared memory (two staging tiles in rotation: the tile about to be rewritten
+// was handed to the store before the most recent one)
+__device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- TMEM -----------------------------------------------------------------------------------------

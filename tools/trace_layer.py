@@ -18,6 +18,13 @@ cfg = {
     "d2": (nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1), EPI_IGDN, (128, 192), {}),
     "d3": (nn.ConvTranspose2d(128, 3, 5, 2, 2, output_padding=1), EPI_BIAS, (256, 384), dict(out_layout=LAYOUT_NCHW, out_dtype=torch.float32)),
     "ep3": (nn.Conv2d(640, 1152, 1), EPI_BIAS, (32, 48), dict(out_layout=LAYOUT_NCHW, out_dtype=torch.float32)),
+    "ep1": (nn.Conv2d(512, 640, 1), EPI_LRELU, (32, 48), {}),
+    "ep2": (nn.Conv2d(640, 640, 1), EPI_LRELU, (32, 48), {}),
+    "hs3": (nn.Conv2d(192, 256, 3, 1, 1), EPI_BIAS, (32, 48), {}),
+    "hs2": (nn.ConvTranspose2d(128, 192, 5, 2, 2, output_padding=1), EPI_LRELU, (16, 24), {}),
+    "ha1": (nn.Conv2d(128, 128, 3, 1, 1), EPI_LRELU, (32, 48), {}),
+    "ha2": (nn.Conv2d(128, 128, 5, 2, 2), EPI_LRELU, (32, 48), {}),
+    "ctx": (nn.Conv2d(128, 256, 5, 1, 2), EPI_BIAS, (32, 48), {}),
     "l1": (nn.Conv2d(3, 128, 5, 2, 2), EPI_GDN, (512, 768), dict(in_layout=LAYOUT_NCHW)),
     "k2c": (nn.Conv2d(128, 128, 5, 2, 2), EPI_BIAS, (256, 384), dict(out_dtype=torch.float32)),
     "k2p": (nn.Conv2d(128, 128, 5, 2, 2), EPI_BIAS, (256, 384), {}),      # pair (bf16x3) or bf16 output: the swapped orientation
