@@ -147,6 +147,16 @@ size_t nic_conv_workspace_bytes(const nic_conv_desc* d);
 int nic_conv_fwd(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                  const void* gdn_gamma, const float* gdn_beta, void* y,
                  void* workspace, size_t workspace_bytes, void* stream);
+/*
+ * nic_conv_fwd with a hint about the input of a NIC_PREC_BF16X3 conv: in_lo_nonzero (device int32 written by
+ * nic_latent_handoff_ex, or NULL) == 0 says the lo half of the bf16-pair input is all zero - true for the quantised y_in / z_in the
+ * context model, g_s and h_s read in eval mode (Models.py:63-71, 90) - and the kernel then runs 2 of its 3 MMA passes
+ * (hi.W_hi + hi.W_lo; the skipped lo.W_hi term is exactly 0).  The flag is read on the device: no host synchronisation, and a
+ * CUDA-graph replay follows the data.
+ */
+int nic_conv_fwd_ex(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                    const void* gdn_gamma, const float* gdn_beta, void* y,
+                    void* workspace, size_t workspace_bytes, const int32_t* in_lo_nonzero, void* stream);
 
 /*
  * Stand-alone GDN / IGDN (compressai.layers.gdn.GDN.forward; call sites Components.py:11-15, 40-44) for
@@ -168,6 +178,12 @@ int nic_gdn_fwd(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, int3
 int nic_latent_handoff(const float* v_nhwc, int32_t n, int32_t c, int32_t h, int32_t w, int32_t qmode,
                        const float* noise_nchw, float* v_nchw, float* v_in_nchw, void* v_in_nhwc,
                        int32_t out_dtype, void* v_nhwc_lowp, int32_t lowp_dtype, void* stream);
+
+/* The same; in_lo_nonzero (optional device int32, out): set to 0, then to 1 if any element of the NIC_DT_BF16X2 copy v_in_nhwc has a
+ * non-zero lo half.  Rounded symbols below 256 split exactly (lo = 0), and nic_conv_fwd_ex skips one of its three passes on 0. */
+int nic_latent_handoff_ex(const float* v_nhwc, int32_t n, int32_t c, int32_t h, int32_t w, int32_t qmode,
+                          const float* noise_nchw, float* v_nchw, float* v_in_nchw, void* v_in_nhwc,
+                          int32_t out_dtype, void* v_nhwc_lowp, int32_t lowp_dtype, int32_t* in_lo_nonzero, void* stream);
 
 /* ---- likelihoods --------------------------------------------------------------------------- */
 

@@ -154,16 +154,19 @@ class JointAutoregressiveHierarchical(nn.Module):
 
             # ---- h_s -> psi = combined[..., 2M:4M];  context -> phi = combined[..., 0:2M] -------
             combined = torch.empty((B, hy, wy, cw * 4 * M), dtype=adt, device=x.device)
+            # the quantised symbols split into bf16 pairs with an all-zero lo half (the hand-off kernel checks and flags it on the
+            # device): their first consumers - h_s layer 1, the context conv, g_s layer 1 - run 2 of the 3 MMA passes
+            y_flag, z_flag = getattr(y_in_nhwc, "_nic_lo_flag", None), getattr(z_in_nhwc, "_nic_lo_flag", None)
             a, h, w = z_in_nhwc, hz, wz
             hs = self.hyper_decoder.ops
             for i, op in enumerate(hs):
                 if i == len(hs) - 1:
                     op.run(a, B, h, w, prec, out=combined, out_c_total=4 * M, out_c_offset=2 * M)
                 else:
-                    a = op.run(a, B, h, w, prec)
+                    a = op.run(a, B, h, w, prec, in_lo_flag=z_flag if i == 0 else None)
                 h, w = engine.conv_out_hw(op.conv, h, w)
             self.context_model.masked.apply_mask_()
-            self.context_model.masked._op.run(y_in_nhwc, B, hy, wy, prec, out=combined, out_c_total=4 * M, out_c_offset=0)
+            self.context_model.masked._op.run(y_in_nhwc, B, hy, wy, prec, out=combined, out_c_total=4 * M, out_c_offset=0, in_lo_flag=y_flag)
 
             # ---- entropy parameters (1x1 stack) ---------------------------------------------------
             ep = self.entropy_parameters.ops
@@ -182,7 +185,7 @@ class JointAutoregressiveHierarchical(nn.Module):
             for i, op in enumerate(dec):
                 last = i == len(dec) - 1
                 a = op.run(a, B, h, w, prec, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC,
-                           out_dtype=torch.float32 if last else None)
+                           out_dtype=torch.float32 if last else None, in_lo_flag=y_flag if i == 0 else None)
                 h, w = engine.conv_out_hw(op.conv, h, w)
             x_hat = a
 

@@ -7,7 +7,8 @@ int conv_fwd_fp32(const nic_conv_desc*, const void*, const void*, const float*, 
 __global__ void pack_weight_f32_kernel(const float*, float*, int, int, int, int, int, TapTable);
 __global__ void pack_gdn_f32_kernel(int, float, float, float, const float*, const float*, float*, float*);
 // conv_tc.cu
-int conv_fwd_tc(const nic_conv_desc*, const void*, const void*, const float*, const void*, const float*, void*, void*, size_t, cudaStream_t);
+int conv_fwd_tc(const nic_conv_desc*, const void*, const void*, const float*, const void*, const float*, void*, void*, size_t, cudaStream_t,
+                const int* lo_flag);
 int pack_weight_tc(const nic_conv_desc*, const TapTable&, const float*, void*, cudaStream_t);
 int pack_gdn_tc(int32_t, float, const float*, const float*, float*, void*, int32_t, cudaStream_t);
 size_t packed_weight_elems_tc(const nic_conv_desc*, const TapTable&);
@@ -69,6 +70,12 @@ size_t nic_conv_workspace_bytes(const nic_conv_desc* d) {
 int nic_conv_fwd(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                  const void* gdn_gamma, const float* gdn_beta, void* y,
                  void* workspace, size_t workspace_bytes, void* stream) {
+  return nic_conv_fwd_ex(d, x, w_packed, bias, gdn_gamma, gdn_beta, y, workspace, workspace_bytes, nullptr, stream);
+}
+
+int nic_conv_fwd_ex(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                    const void* gdn_gamma, const float* gdn_beta, void* y,
+                    void* workspace, size_t workspace_bytes, const int32_t* in_lo_nonzero, void* stream) {
   if (int rc = nic_check_device()) return rc;
   if (int rc = validate_conv_desc(d)) return rc;
   if (d->n == 0) return NIC_OK;
@@ -78,7 +85,7 @@ int nic_conv_fwd(const nic_conv_desc* d, const void* x, const void* w_packed, co
       return conv_fwd_fp32(d, x, w_packed, bias, gdn_gamma, gdn_beta, y, workspace, workspace_bytes, as_stream(stream));
     case NIC_PREC_BF16:
     case NIC_PREC_BF16X3:
-      return conv_fwd_tc(d, x, w_packed, bias, gdn_gamma, gdn_beta, y, workspace, workspace_bytes, as_stream(stream));
+      return conv_fwd_tc(d, x, w_packed, bias, gdn_gamma, gdn_beta, y, workspace, workspace_bytes, as_stream(stream), in_lo_nonzero);
     default:
       return fail(NIC_E_BADSHAPE, "conv: precision %d", d->precision);
   }

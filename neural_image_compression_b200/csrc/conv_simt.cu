@@ -476,7 +476,7 @@ int conv1x1_fp32(const float* x, long pixels, int cin, int cout, const float* w,
 __global__ void __launch_bounds__(256)
 latent_handoff_kernel(const float* __restrict__ v, int n, int c, int h, int w, int qmode, const float* __restrict__ noise,
                       float* __restrict__ v_nchw, float* __restrict__ vin_nchw, void* __restrict__ vin_nhwc, int out_dtype,
-                      __nv_bfloat16* __restrict__ v_lowp, int lowp_dtype) {
+                      __nv_bfloat16* __restrict__ v_lowp, int lowp_dtype, int* __restrict__ lo_nonzero) {
   // 32 x 32 (pixel x channel) transpose tiles through shared memory: coalesced on both layouts
   __shared__ float tile[32][33];
   __shared__ float tile_q[32][33];
@@ -525,8 +525,10 @@ latent_handoff_kernel(const float* __restrict__ v, int n, int c, int h, int w, i
         else if (out_dtype == NIC_DT_BF16X2) {
           const long o2 = (static_cast<long>(img) * hw + pix) * 2 * c + ch;
           const __nv_bfloat16 hi = __float2bfloat16_rn(tile_q[r][tx]);
+          const float lo = tile_q[r][tx] - __bfloat162float(hi);
           static_cast<__nv_bfloat16*>(vin_nhwc)[o2] = hi;
-          static_cast<__nv_bfloat16*>(vin_nhwc)[o2 + c] = __float2bfloat16_rn(tile_q[r][tx] - __bfloat162float(hi));
+          static_cast<__nv_bfloat16*>(vin_nhwc)[o2 + c] = __float2bfloat16_rn(lo);
+          if (lo_nonzero && lo != 0.f) *lo_nonzero = 1;          // integer symbols below 256 split exactly: lo stays all zero
         } else static_cast<float*>(vin_nhwc)[o] = tile_q[r][tx];
       }
     }
@@ -550,14 +552,23 @@ int nic_gdn_fwd(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, int3
 int nic_latent_handoff(const float* v_nhwc, int32_t n, int32_t c, int32_t h, int32_t w, int32_t qmode,
                        const float* noise_nchw, float* v_nchw, float* v_in_nchw, void* v_in_nhwc,
                        int32_t out_dtype, void* v_nhwc_lowp, int32_t lowp_dtype, void* stream) {
+  return nic_latent_handoff_ex(v_nhwc, n, c, h, w, qmode, noise_nchw, v_nchw, v_in_nchw, v_in_nhwc, out_dtype, v_nhwc_lowp, lowp_dtype, nullptr, stream);
+}
+
+int nic_latent_handoff_ex(const float* v_nhwc, int32_t n, int32_t c, int32_t h, int32_t w, int32_t qmode,
+                          const float* noise_nchw, float* v_nchw, float* v_in_nchw, void* v_in_nhwc,
+                          int32_t out_dtype, void* v_nhwc_lowp, int32_t lowp_dtype, int32_t* in_lo_nonzero, void* stream) {
   if (int rc = nic_check_device()) return rc;
   if (n < 0 || c < 1 || h < 1 || w < 1) return fail(NIC_E_BADSHAPE, "latent_handoff: n=%d c=%d h=%d w=%d", n, c, h, w);
   if (qmode == NIC_Q_NOISE && !noise_nchw) return fail(NIC_E_BADSHAPE, "latent_handoff: NIC_Q_NOISE needs noise");
   if (n == 0) return NIC_OK;
   if (n > 65535) return fail(NIC_E_BADSHAPE, "latent_handoff: n=%d > 65535", n);
   dim3 grid((h * w + 31) / 32, (c + 31) / 32, n);
+  if (in_lo_nonzero) {
+    if (int rc = check_cuda(cudaMemsetAsync(in_lo_nonzero, 0, sizeof(int32_t), as_stream(stream)), "cudaMemsetAsync")) return rc;
+  }
   latent_handoff_kernel<<<grid, 256, 0, as_stream(stream)>>>(v_nhwc, n, c, h, w, qmode, noise_nchw, v_nchw, v_in_nchw, v_in_nhwc, out_dtype,
-                                                                   static_cast<__nv_bfloat16*>(v_nhwc_lowp), lowp_dtype);
+                                                                   static_cast<__nv_bfloat16*>(v_nhwc_lowp), lowp_dtype, in_lo_nonzero);
   return check_launch("latent_handoff_kernel");
 }
 

@@ -177,6 +177,8 @@ struct TcParams {
   int tiles_x, tiles_y, n_ntiles, total_tiles;
   int nchunks;                                 // K chunks of 64 (cin / 64; 3 cin / 64 in the bf16x3 arm)
   int a_chunk_mod;                             // input channel chunk of K chunk c is c % a_chunk_mod (bf16x3: [hi | lo | hi again])
+  const int* lo_flag;                          // bf16x3, optional device flag: 0 = the lo half of the input pair tensor is all zero
+                                               // (integer-valued symbols, Models.py:63-64) -> the lo . W_hi chunks are skipped
   int split_out;                               // bf16-pair output: hi to the channel window of the first half of the tensor,
   int split_lo_off;                            //   lo to the same window shifted by split_lo_off channels (the second half)
   int ph_rows, pw_cols;                        // patch rows / cols (pixels)
@@ -615,6 +617,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (p.beta) for (int i = threadIdx.x; i < 128; i += kThreads) s_beta[i] = p.beta[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool gdn = p.epilogue == NIC_EPI_GDN || p.epilogue == NIC_EPI_IGDN;
+  // K chunks this launch walks: all of [hi | lo | hi] x [W_hi | W_hi | W_lo], or - when the producer of the input flagged its lo
+  // half as all zero - without the middle third (every role derives the same list from the same device word)
+  int nchunks_eff = p.nchunks, skip_from = 1 << 30, skip_add = 0;
+  if (p.lo_flag && __ldg(p.lo_flag) == 0) { skip_add = p.a_chunk_mod / 2; skip_from = skip_add; nchunks_eff = p.nchunks - skip_add; }
+  auto kchunk = [&](int chunk) { return chunk + (chunk >= skip_from ? skip_add : 0); };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sb.a_full[i], 1); mbar_init(&sb.a_empty[i], kMmaWarps); }
@@ -643,16 +650,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int ntile, phase, img, ty, tx;
         decode_tile(p, tile, ntile, phase, img, ty, tx);
         const TcPhase& ph = p.phases[phase];
-        for (int chunk = 0; chunk < p.nchunks && ok; ++chunk) {
+        for (int chunk = 0; chunk < nchunks_eff && ok; ++chunk) {
+          const int kc = kchunk(chunk);
           for (int pl = 0; pl < ph.nplanes; ++pl, ++it) {
             const int s = it % p.nsa;
             if (!wait_or_abort(&sb.a_empty[s], ((it / p.nsa) & 1) ^ 1, &sb, p.status)) { ok = false; break; }
             if (chunk == 0 && pl == 0) trace(p, (tile - first_tile) / tile_step, 5);
-            if (chunk == p.nchunks - 1 && pl == ph.nplanes - 1) trace(p, (tile - first_tile) / tile_step, 6);
+            if (chunk == nchunks_eff - 1 && pl == ph.nplanes - 1) trace(p, (tile - first_tile) / tile_step, 6);
             mbar_expect_tx(&sb.a_full[s], bytes);
             const int w0 = p.in_stride * (tx * p.tile_w + ph.plane_dxmin[pl]) + ph.plane_pw[pl];
             const int h0 = p.in_stride * (ty * p.tile_h + ph.plane_dymin[pl]) + ph.plane_ph[pl];
-            tma_load_4d(smem + p.off_a + s * p.slot_bytes, &map_a, &sb.a_full[s], (chunk % p.a_chunk_mod) * 64, w0, h0, img);
+            tma_load_4d(smem + p.off_a + s * p.slot_bytes, &map_a, &sb.a_full[s], (kc % p.a_chunk_mod) * 64, w0, h0, img);
           }
         }
       }
@@ -680,12 +688,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           decode_tile(p, tile, ntile, phase, img, ty, tx);
           const TcPhase& ph = p.phases[phase];
           const int t0 = ph.plane_tap_begin[0], t1 = ph.plane_tap_begin[ph.nplanes];
-          for (int chunk = 0; chunk < p.nchunks && ok; ++chunk) {
+          for (int chunk = 0; chunk < nchunks_eff && ok; ++chunk) {
+            const int kc = kchunk(chunk);
             for (int t = t0; t < t1; ++t, ++it) {
               const int s = it % p.nsb;
               if (!wait_or_abort(&sb.b_empty[s], ((it / p.nsb) & 1) ^ 1, &sb, p.status)) { ok = false; break; }
               mbar_expect_tx(&sb.b_full[s], bytes);
-              tma_load_2d(smem + p.off_b + s * (128 * 128), &map_w, &sb.b_full[s], chunk * 64, s_tap_brow[t] * p.cout_pad + ntile * p.nb);
+              tma_load_2d(smem + p.off_b + s * (128 * 128), &map_w, &sb.b_full[s], kc * 64, s_tap_brow[t] * p.cout_pad + ntile * p.nb);
             }
           }
         }
@@ -705,7 +714,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t a_base = smem_u32(smem + p.off_a), b_base = smem_u32(smem + p.off_b);
       const uint32_t a_hi = umma_desc_hi(p.pw_cols * 128), b_hi = umma_desc_hi(1024);
       const uint32_t bbytes = p.nb * 128;
-      const int nsa = p.nsa, nsb = p.nsb, nchunks = p.nchunks, b_res = p.b_resident;
+      const int nsa = p.nsa, nsb = p.nsb, nchunks = nchunks_eff, b_res = p.b_resident;
       const bool swp = p.swap != 0;
       const uint32_t blk_off = (mw && !swp) ? static_cast<uint32_t>((p.blk_roff[1] * p.pw_cols + p.blk_coff[1]) * 128) >> 4 : 0u;
       const uint32_t idesc_use = swp ? umma_idesc_bf16(128, 256) : idesc;
@@ -1412,7 +1421,7 @@ size_t conv_workspace_bytes_tc(const nic_conv_desc* d) {
 // `shuffle`: non-null when `d` is the 3x3 stride-1 sub-pixel form of a stride-2 transposed conv (see conv_fwd_tc); it is the
 // ORIGINAL descriptor, whose output tensor the epilogue scatters into.
 static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, const void* w_packed, const float* bias, const void* gdn_gamma,
-                     const float* gdn_beta, void* y, cudaStream_t st, const nic_conv_desc* shuffle = nullptr) {
+                     const float* gdn_beta, void* y, cudaStream_t st, const nic_conv_desc* shuffle = nullptr, const int* lo_flag = nullptr) {
   TcParams p{};
   if (int rc = build_tc_geometry(d, tt, &p)) return rc;
   const bool gdn = d->epilogue == NIC_EPI_GDN || d->epilogue == NIC_EPI_IGDN;
@@ -1430,6 +1439,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   p.n_ntiles = p.cout_pad / p.nb;
   p.nchunks = (x3 ? 3 : 1) * d->c_in / 64;
   p.a_chunk_mod = (x3 ? 2 : 1) * d->c_in / 64;
+  p.lo_flag = x3 ? lo_flag : nullptr;
   p.split_out = d->out_dtype == NIC_DT_BF16X2;
   if (p.split_out && (!x3 || d->out_layout != NIC_LAYOUT_NHWC || d->c_out % 64 || d->out_c_total % 64 || d->out_c_offset % 64))
     return fail(NIC_E_UNSUPPORTED, "conv: bf16-pair output needs the bf16x3 arm, NHWC, channel counts / offsets multiples of 64");
@@ -1479,7 +1489,9 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   // the heavier transposing epilogue - so the default is transposed convs only; NIC_TC_SWAP=1 forces it wherever it is built,
   // NIC_TC_SWAP=0 disables it.
   const bool swap_ok = !gdn && out_bf16_tma && (d->epilogue == NIC_EPI_BIAS || d->epilogue == NIC_EPI_LRELU);
-  bool swap = swap_ok && (swap_env ? atoi(swap_env) != 0 : tt.nphases > 1);
+  // (round 2, after the two-chunk issue loop: the stride-1 layers now gain too - entropy-parameter 1x1s 90 -> 74 / 97 -> 88 us, h_a
+  // layer 1 38.6 -> 32.8, h_s layer 3 81 -> 74, context conv 72 -> 67 us; the stride-2 g_a layer 4 still loses, 65 -> 69 us)
+  bool swap = swap_ok && (swap_env ? atoi(swap_env) != 0 : (tt.nphases > 1 || tt.in_stride == 1));
   const bool stacked = flat || swap;
   // two M = 128 blocks per tile share every weight slab (halves the L2 -> shared-memory weight traffic, which is
   // what bounds M = 128 tiles: profiles/README.md); side by side for images, stacked for the flat 1x1 case
@@ -1528,6 +1540,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   const int gdn_bytes = (gdn ? 2 * 128 * 128 : 0) + stage_bytes;
   const int bres_bytes = tt.ntaps * p.nchunks * p.nb * 128;
   p.b_resident = (p.n_ntiles == 1 && p.nb <= 16 && bres_bytes + 2 * p.slot_bytes + gdn_bytes + 1024 <= kMaxDynSmem) ? 1 : 0;
+  if (p.b_resident) p.lo_flag = nullptr;          // resident weights are indexed by chunk position: always the full list
   int b_bytes;
   if (p.b_resident) {
     b_bytes = (bres_bytes + 1023) / 1024 * 1024; p.nsb = 1;
@@ -1627,7 +1640,7 @@ static int launch_first(const nic_conv_desc* d, const void* x, const void* w_pac
 }
 
 int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* gdn_gamma, const float* gdn_beta,
-                void* y, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                void* y, void* workspace, size_t workspace_bytes, cudaStream_t st, const int* lo_flag) {
   TapTable tt;
   if (int rc = build_tap_table(d, &tt)) return rc;
   if (d->precision == NIC_PREC_BF16X3) {
@@ -1647,7 +1660,7 @@ int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, con
           return fail(NIC_E_UNSUPPORTED, "conv bf16x3 (first layer, bias epilogue): output must be a plain NHWC f32 tensor");
         return conv_first_x3(d, x, w_packed, bias, static_cast<float*>(y), st);
       }
-      return launch_tc(d, tt, x, w_packed, bias, nullptr, nullptr, y, st);
+      return launch_tc(d, tt, x, w_packed, bias, nullptr, nullptr, y, st, nullptr, lo_flag);
     }
     // GDN / IGDN layer: conv + bias on the tensor cores into an fp32 NHWC scratch, then the hi/lo-split gamma contraction
     // (gdn_x3_kernel) writes the bf16-pair activation
@@ -1670,7 +1683,7 @@ int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, con
       // would need 16-byte scattered stores (measured +0.22 ms on g_s layer 3) or a 64 KB staging tile (ring down to 4 slots)
       nic_conv_desc c1 = *d;
       c1.epilogue = NIC_EPI_BIAS; c1.out_dtype = NIC_DT_BF16X2; c1.out_layout = NIC_LAYOUT_NHWC; c1.out_c_total = 0; c1.out_c_offset = 0;
-      if (int rc = launch_tc(&c1, tt, x, w_packed, bias, nullptr, nullptr, workspace, st)) return rc;
+      if (int rc = launch_tc(&c1, tt, x, w_packed, bias, nullptr, nullptr, workspace, st, nullptr, lo_flag)) return rc;
       pair_in = 1;
     }
     return gdn_fwd_tc_x3(workspace, pair_in, static_cast<long>(d->n) * d->h_out * d->w_out, d->c_out,

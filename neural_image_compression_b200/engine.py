@@ -112,13 +112,15 @@ class ConvOp:
 
     def run(self, x: torch.Tensor, n: int, h: int, w: int, precision: str, in_layout=LAYOUT_NHWC, out_layout=LAYOUT_NHWC,
             out: Optional[torch.Tensor] = None, out_c_total: int = 0, out_c_offset: int = 0,
-            out_dtype=None, keep_ws: Optional[list] = None) -> torch.Tensor:
+            out_dtype=None, keep_ws: Optional[list] = None, in_lo_flag: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x: contiguous tensor in `in_layout`; returns (or fills) the output in `out_layout`.
 
         In the "bf16x3" arm bf16 tensors are hi/lo PAIRS (NIC_DT_BF16X2: NHWC with 2*c channels) and the default output
         is a pair too; out_dtype=torch.float32 asks for a plain fp32 result.
         keep_ws: a list that receives the call's workspace tensor (fp32 arm + GDN epilogue: the conv output BEFORE the GDN,
-        NHWC f32 - what the training step's backward needs)."""
+        NHWC f32 - what the training step's backward needs).
+        in_lo_flag: device int32 written by latent_handoff (0 = the lo half of the pair input is all zero: quantised symbols) -
+        the bf16x3 conv then skips its lo . W_hi pass (nic_conv_fwd_ex)."""
         lib = _lib.load()
         require_cuda(x, "conv input")
         x3 = precision == "bf16x3"
@@ -135,8 +137,8 @@ class ConvOp:
         wp, bias, gamma, beta = self.packed(precision)
         ws_bytes = lib.nic_conv_workspace_bytes(C.byref(d))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
-        check(lib.nic_conv_fwd(C.byref(d), ptr(x), ptr(wp), ptr(bias), ptr(gamma), ptr(beta), ptr(out), ptr(ws), ws_bytes,
-                               current_stream()), "nic_conv_fwd")
+        check(lib.nic_conv_fwd_ex(C.byref(d), ptr(x), ptr(wp), ptr(bias), ptr(gamma), ptr(beta), ptr(out), ptr(ws), ws_bytes,
+                                  ptr(in_lo_flag) if x3 else None, current_stream()), "nic_conv_fwd")
         if keep_ws is not None:
             keep_ws.append(ws)
         return out
@@ -176,7 +178,8 @@ def run_sequential_nchw(ops, x: torch.Tensor, precision: str) -> torch.Tensor:
 
 def latent_handoff(v_nhwc: torch.Tensor, qmode: int, noise: Optional[torch.Tensor], in_dtype: torch.dtype,
                    want_lowp: bool = False, lowp_pair: bool = False):
-    """Models.py:52-66.  Returns (v_nchw, v_in_nchw, v_in_nhwc, v_nhwc_lowp | None); lowp_pair -> hi/lo pair (2c channels)."""
+    """Models.py:52-66.  Returns (v_nchw, v_in_nchw, v_in_nhwc, v_nhwc_lowp | None); lowp_pair -> hi/lo pair (2c channels).
+    With a pair-format v_in_nhwc the tensor carries `_nic_lo_flag`: a device int32 that is 0 when its lo half is all zero."""
     lib = _lib.load()
     n, h, w, c = v_nhwc.shape
     v = torch.empty((n, c, h, w), dtype=torch.float32, device=v_nhwc.device)
@@ -188,10 +191,13 @@ def latent_handoff(v_nhwc: torch.Tensor, qmode: int, noise: Optional[torch.Tenso
     v_lowp = torch.empty((n, h, w, 2 * c if lowp_pair else c), dtype=torch.bfloat16, device=v_nhwc.device) if want_lowp else None
     if noise is not None:
         noise = noise.contiguous().float()
-    check(lib.nic_latent_handoff(ptr(v_nhwc), n, c, h, w, qmode, ptr(noise), ptr(v), ptr(v_in), ptr(v_in_nhwc),
-                                 DT_BF16X2 if in_pair else (DT_BF16 if in_dtype == torch.bfloat16 else DT_F32), ptr(v_lowp),
-                                 DT_BF16X2 if lowp_pair else DT_BF16, current_stream()),
+    flag = torch.empty(1, dtype=torch.int32, device=v_nhwc.device) if in_pair else None
+    check(lib.nic_latent_handoff_ex(ptr(v_nhwc), n, c, h, w, qmode, ptr(noise), ptr(v), ptr(v_in), ptr(v_in_nhwc),
+                                    DT_BF16X2 if in_pair else (DT_BF16 if in_dtype == torch.bfloat16 else DT_F32), ptr(v_lowp),
+                                    DT_BF16X2 if lowp_pair else DT_BF16, ptr(flag), current_stream()),
           "nic_latent_handoff")
+    if flag is not None:
+        v_in_nhwc._nic_lo_flag = flag
     return v, v_in, v_in_nhwc, v_lowp
 
 

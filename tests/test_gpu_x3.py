@@ -198,3 +198,35 @@ def test_x3_model_ragged_sizes_match_fp32_arm(shape):
         rep["x_hat_given_symbols_rel_err"] = xe2
         assert xe2 < 3e-4, xe2
     H.record_report(f"ragged/{'x'.join(map(str, shape))}", rep)
+
+
+@pytest.mark.parametrize("kind", ["context", "synthesis", "hyper_synthesis"])
+def test_x3_two_pass_on_integer_symbols(kind):
+    """The first consumers of the quantised symbols (context conv, g_s layer 1 incl. its IGDN, h_s layer 1) skip the lo . W_hi pass
+    when the hand-off kernel flags the lo half of its pair output as all zero - exact, since that term is 0.  Symbols of 256 and
+    more do not split exactly: the flag must then read 1 and all three passes run."""
+    from neural_image_compression_b200 import engine
+    from neural_image_compression_b200._lib import EPI_BIAS, EPI_IGDN, EPI_LRELU, Q_ROUND
+    dev = torch.device("cuda:0")
+    torch.manual_seed(47)
+    if kind == "context":
+        conv, epi, g, mask_a = nn.Conv2d(128, 256, 5, 1, 2), EPI_BIAS, None, 1
+    elif kind == "synthesis":
+        conv, epi, g, mask_a = nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1), EPI_IGDN, _gdn(inverse=True), 0
+    else:
+        conv, epi, g, mask_a = nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1), EPI_LRELU, None, 0
+    mask = O.mask_a(conv.weight.detach().cpu()) if mask_a else None
+    op = engine.ConvOp(conv.to(dev), epi, gdn=None if g is None else g.to(dev), mask_a=mask_a)
+    for scale, want_flag in ((6.0, 0), (200.0, 1)):
+        v = (scale * torch.randn(2, 16, 24, 128)).to(dev)               # NHWC, pre-rounding
+        _, v_in, v_in_nhwc, _ = engine.latent_handoff(v, Q_ROUND, None, "bf16x2")
+        flag = v_in_nhwc._nic_lo_flag
+        torch.cuda.synchronize()
+        assert int(flag) == want_flag, (scale, int(flag), float(v_in.abs().max()))
+        y = op.run(v_in_nhwc, 2, 16, 24, "bf16x3", in_lo_flag=flag)
+        y_full = op.run(v_in_nhwc, 2, 16, 24, "bf16x3")                   # no hint: three passes
+        torch.cuda.synchronize()
+        got, full = engine.from_pair(y).float().cpu().permute(0, 3, 1, 2), engine.from_pair(y_full).float().cpu().permute(0, 3, 1, 2)
+        ref = _ref(conv, v_in.cpu(), epi, gdn=g, mask=mask)
+        print(kind, scale, _close(got, ref), float((got - full).abs().max() / full.abs().max()))
+        assert float((got - full).abs().max() / full.abs().max()) < 2e-6
