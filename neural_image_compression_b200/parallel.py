@@ -10,6 +10,7 @@ the same order.  Works with any torch.distributed backend (gloo on CPU in the te
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -298,7 +299,7 @@ class ShardedTrainer:
             self.optimizer.grad_scale = 1.0 / dist.get_world_size(self.group)
         allreduce_gradients(self.buckets, self.group, self._flats, average=not fold)
 
-    def _forward_backward(self, x_local, noise=None):
+    def _forward_backward(self, x_local, noise=None, partial_hook=None):
         """forward + loss + backward on the calling thread and stream (training.step_gradients: the same kernels loss.backward()
         runs, without the autograd engine, whose device thread cannot take part in a stream capture)."""
         self.optimizer.zero_grad()
@@ -307,12 +308,56 @@ class ShardedTrainer:
             loss, terms = scalable_step(self.model, x_local, self.lambda_rd, noise=noise)
             return loss, None, torch.stack([terms[k] for k in ("bpp_y1", "bpp_y2", "bpp_z", "mse", "psnr", "loss")])
         from .training import step_gradients
-        return step_gradients(self.model, x_local, self.lambda_rd, noise=noise)
+        return step_gradients(self.model, x_local, self.lambda_rd, noise=noise, partial_hook=partial_hook)
+
+    # ---- gradient all-reduce INSIDE the captured step, overlapped with g_a's backward -------------------------------------------
+    def _comm_setup(self, device):
+        """Two flat fp32 buckets: 'early' = every parameter except g_a's (their gradients are final before g_a's backward starts),
+        'late' = g_a's.  The gradients are copied into the buckets inside the graph, the buckets are summed over the ranks by NCCL
+        launches captured in the same graph (the early one on a side stream, beside g_a's backward), and .grad becomes views of
+        the buckets; training.Adam divides by the world size inside its update kernel."""
+        if getattr(self, "_comm", None) is not None:
+            return self._comm
+        enc = {id(p) for p in self.model.encoder.parameters()}
+        early = [p for p in self.model.parameters() if p.requires_grad and id(p) not in enc]
+        late = [p for p in self.model.parameters() if p.requires_grad and id(p) in enc]
+        mk = lambda ps: torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=device)      # noqa: E731
+        self._comm = {"early": early, "late": late, "flat_early": mk(early), "flat_late": mk(late),
+                      "stream": torch.cuda.Stream(device=device)}
+        return self._comm
+
+    @staticmethod
+    def _views(params, flat):
+        out, off = {}, 0
+        for p in params:
+            out[id(p)] = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        return out
+
+    def _reduce_bucket(self, params, flat, grads):
+        """grads of `params` -> flat -> all-reduce(SUM) on the current stream; returns {id: view of flat}."""
+        views = self._views(params, flat)
+        srcs = [grads[id(p)] if id(p) in grads else None for p in params]
+        dsts = [views[id(p)] for p in params]
+        for d, g in zip(dsts, srcs):
+            if g is None:
+                d.zero_()
+        torch._foreach_copy_([d for d, g in zip(dsts, srcs) if g is not None], [g.reshape(d.shape) for d, g in zip(dsts, srcs) if g is not None])
+        # the sources were produced on other streams than the one that copies them: hold them until the capture ends, so that the
+        # allocator cannot hand their memory to a later tensor of the same graph
+        self._comm.setdefault("keep", []).extend(g for g in srcs if g is not None)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        return views
 
     def _graphed(self, x_local):
         key = (tuple(x_local.shape), x_local.device)
         ent = self._graphs.get(key)
-        fuse_adam = not self._distributed() and hasattr(self.optimizer, "launch")
+        dist_on = self._distributed()
+        has_launch = hasattr(self.optimizer, "launch")
+        # data parallel: the all-reduce (and with it Adam) joins the graph unless NIC_GRAPH_ALLREDUCE=0
+        comm_in_graph = dist_on and has_launch and not self._scalable and hasattr(self.optimizer, "grad_scale") \
+            and os.environ.get("NIC_GRAPH_ALLREDUCE", "1") != "0"
+        fuse_adam = has_launch and (not dist_on or comm_in_graph)
         if ent is None:
             static_x = torch.empty_like(x_local)
             static_x.copy_(x_local)
@@ -320,9 +365,14 @@ class ShardedTrainer:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                     # warm-up: allocations, attribute setting, the device status word
                 self._forward_backward(static_x)
+                if comm_in_graph:                              # ... and the NCCL communicator
+                    c = self._comm_setup(x_local.device)
+                    dist.all_reduce(c["flat_early"], group=self.group); dist.all_reduce(c["flat_late"], group=self.group)
             torch.cuda.current_stream().wait_stream(side)
             if fuse_adam:
                 self.optimizer.prepare(x_local.device)
+            if comm_in_graph:
+                self.optimizer.grad_scale = 1.0 / dist.get_world_size(self.group)
             # every derived cache (packed conv weights, adjoint packs, GDN effective parameters, the factorized table, the masked
             # conv's zeroing) is keyed on the parameters' version counters: bump them so that the capture RECORDS the kernels that
             # rebuild those caches - a replay must re-derive them from the weights the previous replay's Adam launch wrote
@@ -331,13 +381,31 @@ class ShardedTrainer:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                res = self._forward_backward(static_x)
+                hook = None
+                if comm_in_graph:
+                    c = self._comm_setup(x_local.device)
+                    cur = torch.cuda.current_stream()
+
+                    def hook(grads, streams, c=c):
+                        # every gradient outside g_a is enqueued: sum them over the ranks on the side stream while g_a's backward runs
+                        for st in streams:
+                            c["stream"].wait_stream(st)
+                        with torch.cuda.stream(c["stream"]):
+                            grads.update(self._reduce_bucket(c["early"], c["flat_early"], grads))
+                res = self._forward_backward(static_x, partial_hook=hook)
+                if comm_in_graph:
+                    late = self._reduce_bucket(c["late"], c["flat_late"], {id(p): p.grad for p in c["late"] if p.grad is not None})
+                    for p in c["late"]:
+                        p.grad = late[id(p)]
+                    cur.wait_stream(c["stream"])              # join: the early bucket is reduced
                 if fuse_adam:
                     self.optimizer.launch()                  # counter increment + update: the step count lives on the device
             # the gradients the capture produced: every replay rewrites THESE tensors, so .grad must point at them again after
             # a replay (the all-reduce below re-points .grad at views of its averaged buckets)
             ent = (g, static_x, res, [p.grad for p in self.model.parameters()])
             self._graphs[key] = ent
+            if comm_in_graph:
+                self._comm["keep"] = []
         g, static_x, res, static_grads = ent
         if static_x.data_ptr() != x_local.data_ptr():
             static_x.copy_(x_local, non_blocking=True)
@@ -350,15 +418,17 @@ class ShardedTrainer:
             self.optimizer.t += 1
             for p in self.model.parameters():                 # updated inside the replay: packed-weight caches key on _version
                 torch.autograd.graph.increment_version(p)
-        return res, fuse_adam
+        return res, fuse_adam, comm_in_graph
 
     def step(self, x_local: torch.Tensor, noise=None) -> dict:
         if (self.graph and noise is None) or self._scalable:
+            reduced = False
             if self.graph and noise is None:
-                (loss, per_image, scalars), adam_done = self._graphed(x_local)
+                (loss, per_image, scalars), adam_done, reduced = self._graphed(x_local)
             else:
                 (loss, per_image, scalars), adam_done = self._forward_backward(x_local, noise), False
-            self._allreduce()
+            if not reduced:
+                self._allreduce()
             if not adam_done:
                 self.optimizer.step()
             self.step_count += 1

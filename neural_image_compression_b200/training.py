@@ -476,8 +476,11 @@ def _forward_impl(model, x, noise_z, noise_y, lean, qmode: int = Q_NOISE, arm: O
     return (x_hat, logp_y, logp_z, *nd), S
 
 
-def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tensor]:
-    """The hand-scheduled backward: {id(parameter): gradient} from the gradients of x_hat / logp_y / logp_z (any may be None)."""
+def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z, partial_hook=None) -> Dict[int, torch.Tensor]:
+    """The hand-scheduled backward: {id(parameter): gradient} from the gradients of x_hat / logp_y / logp_z (any may be None).
+    partial_hook(grads, streams): called once, when every gradient except g_a's has been ENQUEUED (g_s, the entropy path and h_a
+    are done, on `streams`) and only g_a's backward remains - the data-parallel trainer starts the all-reduce of those ~24 of the
+    29 MB there, so that it overlaps g_a's backward; the hook may replace entries of `grads` (views of its reduced bucket)."""
     lib = _lib.load()
     B, H, W = S["shape"]
     M, K = model.M, model.K
@@ -595,6 +598,8 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z) -> Dict[int, torch.Tens
             main.wait_stream(branch)
         if d_yin_gs is not None:
             dy = d_yin_gs if dy is None else add_(dy, d_yin_gs)
+        if partial_hook is not None:
+            partial_hook(grads, [st for st in (main, side) if st is not None])
         # ---- g_a (y_in = y + noise) ---------------------------------------------------------------------------------
         if dy is not None:
             g = dy
@@ -637,7 +642,7 @@ class _TrainForward(torch.autograd.Function):
 
 
 @torch.no_grad()
-def step_gradients(model, x: torch.Tensor, lambda_rd: float, noise=None):
+def step_gradients(model, x: torch.Tensor, lambda_rd: float, noise=None, partial_hook=None):
     """forward + rd_loss + backward of one step WITHOUT the autograd engine (everything on the calling thread and its current
     stream - what a CUDA-graph capture needs): accumulates into .grad like loss.backward() and returns
     (loss [device scalar], per_image [3, B], scalars [8])."""
@@ -661,7 +666,7 @@ def step_gradients(model, x: torch.Tensor, lambda_rd: float, noise=None):
     with torch.cuda.device(x.device):
         check(_lib.load().nic_sse_bwd(ptr(x_hat), ptr(x), x.numel(), float(lambda_rd) * 65025.0 * 2.0 / x.numel(), ptr(gx), current_stream()),
               "nic_sse_bwd")
-    grads = _backward_impl(model, S, gx, gl.expand(logp_y.shape), gl.expand(logp_z.shape))
+    grads = _backward_impl(model, S, gx, gl.expand(logp_y.shape), gl.expand(logp_z.shape), partial_hook=partial_hook)
     for p in model.parameters():
         g = grads.get(id(p))
         if g is not None:
