@@ -50,16 +50,16 @@ int conv_fwd_fp32_ex(const nic_conv_desc* d, const void* x, const void* w_packed
 // x3_tc.cu
 int pack_gdn_x3(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, float* beta_eff, void* gamma_packed, cudaStream_t st);
 int gdn_fwd_tc_x3(const void* x, int pair_in, long npix, int c, int inverse, const void* gamma_packed, const float* beta_eff, void* y, cudaStream_t st);
-size_t packed_first_x3_elems();
-int pack_first_x3(const float* w_ref, void* w_packed, cudaStream_t st);
+size_t packed_first_x3_elems(int cout);
+int pack_first_x3(const float* w_ref, void* w_packed, int cout, cudaStream_t st);
 int conv_first_x3(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, float* y, cudaStream_t st);
 int conv_first_gdn_x3(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* gamma_packed,
                       const float* beta_eff, void* y, cudaStream_t st);
 
 // last_tc.cu
 bool last_scatter_applies(const nic_conv_desc* d);
-size_t packed_last_scatter_elems();
-int pack_last_scatter(const float* w_ref, void* w_packed, cudaStream_t st);
+size_t packed_last_scatter_elems(int cin);
+int pack_last_scatter(const float* w_ref, void* w_packed, int cin, cudaStream_t st);
 int conv_last_scatter_x3(const nic_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y, cudaStream_t st);
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1270,11 +1270,13 @@ __global__ void pack_first_bf16_kernel(const float* __restrict__ w, __nv_bfloat1
 
 int check_first_layer(const nic_conv_desc* d) {
   // bf16x3 also serves the bare conv (bias epilogue, f32 NHWC output): the training step keeps the pre-GDN tensor, and the
-  // data gradient of the last g_s layer is this same conv over the image-shaped gradient
+  // data gradient of the last g_s layer is this same conv over the image-shaped gradient; that form is also built for 192
+  // output channels (the reference's default capacity, Models.py:17, and ScalableImageCoding(192, 128))
   const bool bare_x3 = d->precision == NIC_PREC_BF16X3 && d->epilogue == NIC_EPI_BIAS;
-  if (d->c_in != 3 || d->c_out != 128 || d->kh != 5 || d->kw != 5 || d->stride != 2 || d->pad != 2 || d->transposed || d->mask_a ||
+  const bool cout_ok = d->c_out == 128 || (d->precision == NIC_PREC_BF16X3 && d->c_out == 192);
+  if (d->c_in != 3 || !cout_ok || d->kh != 5 || d->kw != 5 || d->stride != 2 || d->pad != 2 || d->transposed || d->mask_a ||
       (d->epilogue != NIC_EPI_GDN && !bare_x3))
-    return fail(NIC_E_UNSUPPORTED, "conv bf16: the only c_in < 64 layer built is Conv2d(3, 128, 5, stride 2, pad 2) + GDN (g_a layer 1)");
+    return fail(NIC_E_UNSUPPORTED, "conv bf16: the only c_in < 64 layer built is Conv2d(3, 128 | 192, 5, stride 2, pad 2) (+ GDN for 128) (g_a layer 1)");
   return NIC_OK;
 }
 
@@ -1341,8 +1343,8 @@ int read_and_clear_status() {
 //   c_in  = 3  : [c_out = 128][k padded to 128], k = (kh * kw_size + kw) * 3 + c   (first layer, conv_first_tc_kernel)
 size_t packed_weight_elems_tc(const nic_conv_desc* d, const TapTable& tt) {
   if (d->precision == NIC_PREC_BF16X3) {
-    if (small_cin(d)) return packed_first_x3_elems();
-    if (last_scatter_applies(d)) return packed_last_scatter_elems();
+    if (small_cin(d)) return packed_first_x3_elems(d->c_out == 192 ? 192 : 128);
+    if (last_scatter_applies(d)) return packed_last_scatter_elems(d->c_in);
     if (subpixel_form(d)) return static_cast<size_t>(9) * 16 * 3 * d->c_in;
     const int cp = (d->c_out + 127) / 128 * 128;
     return static_cast<size_t>(tt.ntaps) * cp * 3 * d->c_in;
@@ -1360,10 +1362,10 @@ int pack_weight_tc(const nic_conv_desc* d, const TapTable& tt, const float* w_re
   if (d->precision == NIC_PREC_BF16X3) {
     if (small_cin(d)) {
       if (int rc = check_first_layer(d)) return rc;
-      return pack_first_x3(w_ref, w_packed, st);
+      return pack_first_x3(w_ref, w_packed, d->c_out, st);
     }
     if (d->c_in % 64) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: c_in=%d must be a multiple of 64 (or 3 for the first layer)", d->c_in);
-    if (last_scatter_applies(d)) return pack_last_scatter(w_ref, w_packed, st);
+    if (last_scatter_applies(d)) return pack_last_scatter(w_ref, w_packed, d->c_in, st);
     if (subpixel_form(d)) {
       const long total = 9L * 16 * 3 * d->c_in;
       pack_weight_subpixel_x3_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed), d->c_in,
@@ -1670,7 +1672,7 @@ int conv_fwd_tc(const nic_conv_desc* d, const void* x, const void* w_packed, con
     if (d->out_dtype != NIC_DT_BF16X2 || d->out_layout != NIC_LAYOUT_NHWC || d->out_c_total != 0)
       return fail(NIC_E_UNSUPPORTED, "conv bf16x3 + GDN: output must be a plain NHWC bf16-pair tensor");
     int pair_in = 0;
-    if (small_cin(d) && !getenv("NIC_X3_FIRST_TWO_KERNELS")) {       // fused conv + GDN (the env switch keeps the two-kernel form testable)
+    if (small_cin(d) && d->c_out == 128 && !getenv("NIC_X3_FIRST_TWO_KERNELS")) {       // fused conv + GDN (the env switch keeps the two-kernel form testable; 192 channels: two kernels)
       if (int rc = check_first_layer(d)) return rc;
       return conv_first_gdn_x3(d, x, w_packed, bias, gdn_gamma, gdn_beta, y, st);
     }

@@ -34,7 +34,7 @@ constexpr int kBH = 8, kBW = 16;                    // block of input pixels = t
 constexpr int kIH = kBH - 2, kIW = kBW - 2;         // interior: 6 x 14 pixels whose outputs the tile writes
 constexpr int kN = 80;                              // MMA N: 75 live columns, padded to a multiple of 16
 constexpr int kTStride = 81;                        // words per T row: odd, so scalar accesses of consecutive rows are conflict free
-constexpr int kSlots = 3;
+constexpr int kMaxSlots = 3;
 constexpr int kPanelA = 128 * 128;                  // [128 pixels][64 bf16] K-major, 128-byte swizzle
 constexpr int kPanelW = kN * 128;                   // [80 columns][64 bf16]
 constexpr int kTBytes = 128 * kTStride * 4;
@@ -58,10 +58,12 @@ struct LastParams {
   const float* bias;
   int* status;
   int off_w, off_a, off_t;
+  int kc;                                           // 64-channel panels per half of the pair input: c_in / 64 (2 or 3)
+  int nslots, ngroups;                              // ring depth (half-tiles) and epilogue groups that fit next to the weights
 };
 
 struct __align__(8) LastBarriers {
-  uint64_t a_full[kSlots], a_empty[kSlots], w_full, acc_full[2], acc_empty[2];
+  uint64_t a_full[kMaxSlots], a_empty[kMaxSlots], w_full, acc_full[2], acc_empty[2];
   uint32_t tmem_base;
   volatile int abort_flag;
 };
@@ -85,7 +87,7 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < 3) s_bias[threadIdx.x] = p.bias[threadIdx.x];
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSlots; ++i) { mbar_init(&sb.a_full[i], 1); mbar_init(&sb.a_empty[i], 1); }
+    for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sb.a_full[i], 1); mbar_init(&sb.a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], 4); }
     mbar_init(&sb.w_full, 1);
     sb.abort_flag = 0;
@@ -98,13 +100,15 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const uint32_t tmem = sb.tmem_base;
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
   const int per_img = p.tiles_x * p.tiles_y;
+  const int kc = p.kc, nslots = p.nslots;
 
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
       tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w);
-      mbar_expect_tx(&sb.w_full, 4 * kPanelW);
-      for (int k = 0; k < 4; ++k) tma_load_2d(smem + p.off_w + k * kPanelW, &map_w, &sb.w_full, (k & 1) * 64, (k >> 1) * kN);
+      mbar_expect_tx(&sb.w_full, 2 * kc * kPanelW);           // panels [W_hi: kc][W_lo: kc]
+      for (int part = 0; part < 2; ++part)
+        for (int j = 0; j < kc; ++j) tma_load_2d(smem + p.off_w + (part * kc + j) * kPanelW, &map_w, &sb.w_full, j * 64, part * kN);
       uint32_t it = 0;
       bool ok = true;
       for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step) {
@@ -112,12 +116,11 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int r0 = ty * kIH - 1, c0 = tx * kIW - 1;
         for (int half = 0; half < 2; ++half, ++it) {
-          const uint32_t s = it % kSlots;
-          if (!wait_abort(&sb.a_empty[s], ((it / kSlots) & 1) ^ 1, &sb.abort_flag, p.status)) { ok = false; break; }
-          mbar_expect_tx(&sb.a_full[s], 2 * kPanelA);
-          uint8_t* dst = smem + p.off_a + s * (2 * kPanelA);
-          tma_load_4d(dst, &map_a, &sb.a_full[s], half * 128, c0, r0, img);
-          tma_load_4d(dst + kPanelA, &map_a, &sb.a_full[s], half * 128 + 64, c0, r0, img);
+          const uint32_t s = it % nslots;
+          if (!wait_abort(&sb.a_empty[s], ((it / nslots) & 1) ^ 1, &sb.abort_flag, p.status)) { ok = false; break; }
+          mbar_expect_tx(&sb.a_full[s], kc * kPanelA);
+          uint8_t* dst = smem + p.off_a + s * (kc * kPanelA);
+          for (int j = 0; j < kc; ++j) tma_load_4d(dst + j * kPanelA, &map_a, &sb.a_full[s], (half * kc + j) * 64, c0, r0, img);
         }
       }
     }
@@ -135,23 +138,27 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         if (!wait_abort(&sb.acc_empty[g], ((tcount >> 1) & 1) ^ 1, &sb.abort_flag, p.status)) break;
         const uint32_t d = tmem + g * 128;
         // hi panels: . W_hi, then . W_lo
-        uint32_t s = it % kSlots;
-        if (!wait_abort(&sb.a_full[s], (it / kSlots) & 1, &sb.abort_flag, p.status)) break;
+        uint32_t s = it % nslots;
+        if (!wait_abort(&sb.a_full[s], (it / nslots) & 1, &sb.abort_flag, p.status)) break;
         tcgen05_fence_after();
-        uint32_t a = a0 + s * (2 * PA);
+        uint32_t a = a0 + s * (kc * PA);
+        uint32_t acc_on = 0;
+        for (int j = 0; j < kc; ++j)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16_lohi(d, a + (k >> 2) * PA + (k & 3) * 2, hi, w0 + (k >> 2) * PW + (k & 3) * 2, hi, idesc, k);
+          for (int k = 0; k < 4; ++k) { umma_bf16_lohi(d, a + j * PA + k * 2, hi, w0 + j * PW + k * 2, hi, idesc, acc_on); acc_on = 1; }
+        for (int j = 0; j < kc; ++j)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16_lohi(d, a + (k >> 2) * PA + (k & 3) * 2, hi, w0 + (2 + (k >> 2)) * PW + (k & 3) * 2, hi, idesc, 1);
+          for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, a + j * PA + k * 2, hi, w0 + (kc + j) * PW + k * 2, hi, idesc, 1);
         umma_commit(&sb.a_empty[s]);
         ++it;
         // lo panels: . W_hi
-        s = it % kSlots;
-        if (!wait_abort(&sb.a_full[s], (it / kSlots) & 1, &sb.abort_flag, p.status)) break;
+        s = it % nslots;
+        if (!wait_abort(&sb.a_full[s], (it / nslots) & 1, &sb.abort_flag, p.status)) break;
         tcgen05_fence_after();
-        a = a0 + s * (2 * PA);
+        a = a0 + s * (kc * PA);
+        for (int j = 0; j < kc; ++j)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16_lohi(d, a + (k >> 2) * PA + (k & 3) * 2, hi, w0 + (k >> 2) * PW + (k & 3) * 2, hi, idesc, 1);
+          for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, a + j * PA + k * 2, hi, w0 + j * PW + k * 2, hi, idesc, 1);
         umma_commit(&sb.a_empty[s]);
         ++it;
         umma_commit(&sb.acc_full[g]);
@@ -159,7 +166,7 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
   } else {
     // ===================== epilogue: group g = (warp - 2) / 4 takes the tiles of parity g =====================
-    const int g = (warp - 2) >> 2, q = warp & 3;
+    const int g = (warp - 2) >> 2, q = warp & 3;        // with one group (c_in = 192: one T buffer fits) warps 6-9 have no work
     const int row = q * 32 + lane;
     const int li = row >> 4, lj = row & 15;                    // position of this lane's pixel inside the 8 x 16 block
     float* T = reinterpret_cast<float*>(smem + p.off_t + g * kTBytes);
@@ -168,14 +175,15 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     auto sync_group = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     uint32_t tcount = 0;
-    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tcount) {
-      if ((tcount & 1) != static_cast<uint32_t>(g)) continue;
+    for (int tile = first_tile; tile < p.total_tiles && g < p.ngroups; tile += tile_step, ++tcount) {
+      if (p.ngroups == 2 && (tcount & 1) != static_cast<uint32_t>(g)) continue;
+      const uint32_t ab = tcount & 1;                          // accumulator buffer of this tile
       const int img = tile / per_img, rem = tile - img * per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      if (!__all_sync(0xffffffffu, wait_abort(&sb.acc_full[g], (tcount >> 1) & 1, &sb.abort_flag, p.status))) break;
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.acc_full[ab], (tcount >> 1) & 1, &sb.abort_flag, p.status))) break;
       tcgen05_fence_after();
       sync_group();                                            // the group's previous gather no longer reads T
-      const uint32_t acc = tmem + g * 128 + lane_off;
+      const uint32_t acc = tmem + ab * 128 + lane_off;
       {
         float v[32];
         tmem_ld_32x32(acc, v);
@@ -193,7 +201,7 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sb.acc_empty[g]);             // the accumulator buffer is free for the tile after next
+      if (lane == 0) mbar_arrive(&sb.acc_empty[ab]);            // the accumulator buffer is free for the tile after next
       sync_group();                                            // T complete
       const int oy = ty * kIH - 1 + li, ox = tx * kIW - 1 + lj;
       if (interior && oy < p.h && ox < p.w) {
@@ -232,10 +240,10 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
-// reference weight [128 (c_in), 3 (c_out), 5, 5] -> bf16 [2 (hi | lo)][80 columns][128 c_in], column = slab_off(s) + ((py * npx + px) * 3 + c)
-__global__ void pack_last_scatter_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * kN * 128; i += gridDim.x * blockDim.x) {
-    const int ci = i % 128, col = (i / 128) % kN, part = i / (128 * kN);
+// reference weight [c_in, 3 (c_out), 5, 5] -> bf16 [2 (hi | lo)][80 columns][c_in], column = slab_off(s) + ((py * npx + px) * 3 + c)
+__global__ void pack_last_scatter_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * kN * cin; i += gridDim.x * blockDim.x) {
+    const int ci = i % cin, col = (i / cin) % kN, part = i / (cin * kN);
     float v = 0.f;
     if (col < 75) {
       int s = 0;
@@ -256,13 +264,13 @@ __global__ void pack_last_scatter_kernel(const float* __restrict__ w, __nv_bfloa
 bool last_scatter_applies(const nic_conv_desc* d) {
   static const bool off = getenv("NIC_LAST_SUBPIXEL") != nullptr;      // A/B switch: the nine-shifted-MMA sub-pixel path of conv_tc_kernel
   return !off && d->precision == NIC_PREC_BF16X3 && d->transposed && d->stride == 2 && d->kh == 5 && d->kw == 5 && d->pad == 2 &&
-         d->output_padding == 1 && d->c_in == 128 && d->c_out == 3 && d->epilogue == NIC_EPI_BIAS;
+         d->output_padding == 1 && (d->c_in == 128 || d->c_in == 192) && d->c_out == 3 && d->epilogue == NIC_EPI_BIAS;
 }
 
-size_t packed_last_scatter_elems() { return static_cast<size_t>(2) * kN * 128; }
+size_t packed_last_scatter_elems(int cin) { return static_cast<size_t>(2) * kN * cin; }
 
-int pack_last_scatter(const float* w_ref, void* w_packed, cudaStream_t st) {
-  pack_last_scatter_kernel<<<80, 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed));
+int pack_last_scatter(const float* w_ref, void* w_packed, int cin, cudaStream_t st) {
+  pack_last_scatter_kernel<<<(2 * kN * cin + 255) / 256, 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed), cin);
   return check_launch("pack_last_scatter_kernel");
 }
 
@@ -282,15 +290,19 @@ int conv_last_scatter_x3(const nic_conv_desc* d, const void* x, const void* w_pa
   p.bias = bias;
   p.status = status_word();
   if (!p.status) return fail(NIC_E_CUDA, "conv bf16x3: cannot allocate the status word");
-  p.off_w = 0; p.off_a = 4 * kPanelW; p.off_t = p.off_a + kSlots * 2 * kPanelA;
-  const int smem_bytes = p.off_t + 2 * kTBytes + 1024;
+  // 128 channels: three 32 KB half-tile slots and two epilogue groups; 192 channels (48 KB half-tiles, 60 KB of weights): two
+  // slots and one group is what fits 227 KB
+  p.kc = d->c_in / 64;
+  p.nslots = p.kc == 2 ? 3 : 2; p.ngroups = p.kc == 2 ? 2 : 1;
+  p.off_w = 0; p.off_a = 2 * p.kc * kPanelW; p.off_t = p.off_a + p.nslots * p.kc * kPanelA;
+  const int smem_bytes = p.off_t + p.ngroups * kTBytes + 1024;
   CUtensorMap map_a, map_w;
   if (int rc = encode_nhwc(&map_a, x, d->n, d->h_in, d->w_in, 2 * d->c_in, kBW, kBH, 1, 2)) return rc;
-  if (int rc = encode_2d(&map_w, w_packed, 128, 2 * kN, 64, kN)) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (int rc = encode_2d(&map_w, w_packed, d->c_in, 2 * kN, 64, kN)) return rc;
+  static int attr_bytes = 0;
+  if (attr_bytes < smem_bytes) {
     if (int rc = check_cuda(cudaFuncSetAttribute(last_scatter_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
-    attr_set = true;
+    attr_bytes = smem_bytes;
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
   last_scatter_x3_kernel<<<grid, kThreads, smem_bytes, st>>>(map_a, map_w, p);

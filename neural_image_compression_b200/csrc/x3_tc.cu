@@ -252,6 +252,202 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   if (warp == kGdnWorkers) tmem_dealloc(tmem, 128);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same GDN / IGDN for c = 64 NP channels where gamma hi / lo (4 c^2 bytes: 144 KB at c = 192) cannot stay in shared memory
+// next to two tile buffers: gamma STREAMS through a small ring in [64 out x 64 in] pieces (hi + lo = 16 KB per ring slot, all
+// NP^2 piece pairs once per 128-pixel tile - they live in L2), and the norm is accumulated per 64-channel output piece:
+//   for n, k:  D[:, 64 n ..] += sq_hi[k] . g_hi[n][k] + sq_hi[k] . g_lo[n][k] + sq_lo[k] . g_hi[n][k]        (12 MMAs of N = 64)
+// 4 NP worker warps (thread <-> pixel row x 64-channel group), one warp that loads the x tiles, one that feeds the gamma ring;
+// worker thread 0 issues the MMAs.  Used for the reference's default capacity M = 192 (Models.py:17) and ScalableImageCoding.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGRing = 2;                       // ring slots of one (g_hi, g_lo) piece pair
+constexpr int kPiece = 64 * 128;                // [64 out rows][64 in] bf16, 128-byte swizzle
+
+struct __align__(8) GdnCBarriers {
+  uint64_t x_full[2], x_empty[2], g_full[kGRing], g_empty[kGRing], mma_done;
+  uint32_t tmem_base;
+  volatile int abort_flag;
+};
+
+template <int NP, bool PAIR_IN>
+__global__ void __launch_bounds__((4 * NP + 2) * 32, 1)
+gdn_x3c_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_o,
+               const __grid_constant__ GdnX3Params p) {
+  constexpr int C = 64 * NP, kWorkers = 4 * NP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* ring = smem;                            // kGRing x [g_hi piece | g_lo piece]
+  uint8_t* bufs = smem + kGRing * 2 * kPiece;      // two tile buffers of 2 NP panels: [hi 0 | lo 0 | hi 1 | lo 1 | ...] once squared
+  __shared__ GdnCBarriers sb;
+  __shared__ __align__(16) float s_beta[C];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < C) s_beta[threadIdx.x] = p.beta[threadIdx.x];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&sb.x_full[i], 1); mbar_init(&sb.x_empty[i], 1); }
+    for (int i = 0; i < kGRing; ++i) { mbar_init(&sb.g_full[i], 1); mbar_init(&sb.g_empty[i], 1); }
+    mbar_init(&sb.mma_done, 1);
+    sb.abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == kWorkers) { tmem_alloc(&sb.tmem_base, 256); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = sb.tmem_base;
+
+  if (warp == kWorkers) {
+    // ===================== x tiles =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_o);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const uint32_t b = it & 1;
+        if (!wait_abort(&sb.x_empty[b], ((it >> 1) & 1) ^ 1, &sb.abort_flag, p.status)) break;
+        mbar_expect_tx(&sb.x_full[b], 2 * NP * kPanel);
+        // f32: box k = channels [32 k, 32 k + 32); pairs: panel 2 g = hi of channel group g, panel 2 g + 1 = its lo
+#pragma unroll
+        for (int k = 0; k < 2 * NP; ++k)
+          tma_load_2d(bufs + (b * 2 * NP + k) * kPanel, &map_x, &sb.x_full[b], PAIR_IN ? (k >> 1) * 64 + (k & 1) * C : k * 32, tile * 128);
+      }
+    }
+  } else if (warp == kWorkers + 1) {
+    // ===================== gamma ring: every (n, k) piece pair once per tile =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&map_g);
+      uint32_t step = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.ntiles && ok; tile += gridDim.x) {
+        for (int nk = 0; nk < NP * NP; ++nk, ++step) {
+          const uint32_t s = step % kGRing;
+          if (!wait_abort(&sb.g_empty[s], ((step / kGRing) & 1) ^ 1, &sb.abort_flag, p.status)) { ok = false; break; }
+          const int n = nk / NP, k = nk % NP;
+          mbar_expect_tx(&sb.g_full[s], 2 * kPiece);
+          tma_load_2d(ring + s * 2 * kPiece, &map_g, &sb.g_full[s], k * 64, n * 64);                 // g_hi[n][k]
+          tma_load_2d(ring + s * 2 * kPiece + kPiece, &map_g, &sb.g_full[s], k * 64, C + n * 64);     // g_lo[n][k]
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, hs = warp >> 2;            // hs = 64-channel group of this thread
+    const int row = q * 32 + lane;
+    const bool leader = threadIdx.x == 0;
+    const uint32_t swz = static_cast<uint32_t>(row & 7);
+    const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + hs * 64;
+    auto sync_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers * 32) : "memory"); };
+    uint32_t it = 0, step = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t b = it & 1;
+      uint8_t* my_h = bufs + (b * 2 * NP + 2 * hs) * kPanel + row * 128;
+      uint8_t* my_l = my_h + kPanel;
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.x_full[b], (it >> 1) & 1, &sb.abort_flag, p.status))) break;
+      float xr[64];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t off = (static_cast<uint32_t>(j) ^ swz) << 4;
+        if (PAIR_IN) {
+          const uint4 h = *reinterpret_cast<const uint4*>(my_h + off), l = *reinterpret_cast<const uint4*>(my_l + off);
+          const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            xr[j * 8 + e * 2] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            xr[j * 8 + e * 2 + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+          }
+        } else {
+          const float4 v = *reinterpret_cast<const float4*>(my_h + off), w = *reinterpret_cast<const float4*>(my_l + off);
+          xr[j * 4] = v.x; xr[j * 4 + 1] = v.y; xr[j * 4 + 2] = v.z; xr[j * 4 + 3] = v.w;
+          xr[32 + j * 4] = w.x; xr[32 + j * 4 + 1] = w.y; xr[32 + j * 4 + 2] = w.z; xr[32 + j * 4 + 3] = w.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = xr[j * 8 + e * 2], c = xr[j * 8 + e * 2 + 1];
+          split2(a * a, c * c, h[e], l[e]);
+        }
+        const uint32_t off = (static_cast<uint32_t>(j) ^ swz) << 4;
+        *reinterpret_cast<uint4*>(my_h + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(my_l + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      sync_workers();
+      if (leader) {
+        // the stores of tile it - 1 have been reading the other buffer since the end of the last iteration: once they are done
+        // with it, tile it + 1 may be loaded there (overlaps this tile's MMAs)
+        if (it > 0) { tma_store_wait_read(); mbar_arrive(&sb.x_empty[b ^ 1]); }
+        tcgen05_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(128, 64);
+        const uint32_t hi = umma_desc_hi(1024);
+        const uint32_t sq = umma_desc_lo(smem_u32(bufs + b * 2 * NP * kPanel));
+        const uint32_t r0 = umma_desc_lo(smem_u32(ring));
+        constexpr uint32_t P = kPanel >> 4, PP = kPiece >> 4;
+        bool ok = true;
+        for (int n = 0; n < NP && ok; ++n) {
+          for (int k = 0; k < NP; ++k, ++step) {
+            const uint32_t s = step % kGRing;
+            if (!wait_abort(&sb.g_full[s], (step / kGRing) & 1, &sb.abort_flag, p.status)) { ok = false; break; }
+            tcgen05_fence_after();
+            const uint32_t gh = r0 + s * 2 * PP, gl = gh + PP, sh = sq + 2 * k * P, sl = sh + P;
+            const uint32_t d = tmem + n * 64;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(d, sh + kk * 2, hi, gh + kk * 2, hi, idesc, (k | kk) ? 1u : 0u);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(d, sh + kk * 2, hi, gl + kk * 2, hi, idesc, 1);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(d, sl + kk * 2, hi, gh + kk * 2, hi, idesc, 1);
+            umma_commit(&sb.g_empty[s]);
+          }
+        }
+        umma_commit(&sb.mma_done);
+      }
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.mma_done, it & 1, &sb.abort_flag, p.status))) break;
+      tcgen05_fence_after();
+      const float4* beta4 = reinterpret_cast<const float4*>(s_beta + hs * 64);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld_32x32(taddr + half * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b0 = beta4[half * 8 + j];
+          const float n0[4] = {v[j * 4] + b0.x, v[j * 4 + 1] + b0.y, v[j * 4 + 2] + b0.z, v[j * 4 + 3] + b0.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            v[j * 4 + e] = xr[half * 32 + j * 4 + e] * (p.inverse ? sqrt_approx(n0[e]) : rsqrt_approx(n0[e]));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split2(v[j * 8 + e * 2], v[j * 8 + e * 2 + 1], h[e], l[e]);
+          const uint32_t off = (static_cast<uint32_t>(half * 4 + j) ^ swz) << 4;
+          *reinterpret_cast<uint4*>(my_h + off) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(my_l + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      sync_workers();
+      if (leader) {
+        const uint8_t* t0 = bufs + b * 2 * NP * kPanel;
+#pragma unroll
+        for (int g = 0; g < NP; ++g) {
+          tma_store_2d(&map_o, t0 + (2 * g) * kPanel, g * 64, tile * 128);            // hi, channel group g
+          tma_store_2d(&map_o, t0 + (2 * g + 1) * kPanel, C + g * 64, tile * 128);    // lo
+        }
+        tma_store_commit();
+      }
+    }
+    if (leader) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kWorkers) tmem_dealloc(tmem, 256);
+}
+
 // gamma_eff [i (out)][j (in)] split hi | lo: bf16 [2][c][c], K-major B operands; beta_eff f32 [c]
 __global__ void pack_gdn_x3_kernel(int c, float beta_bound, float gamma_bound, float pedestal, const float* __restrict__ beta,
                                    const float* __restrict__ gamma, float* __restrict__ beta_eff, __nv_bfloat16* __restrict__ out) {
@@ -285,6 +481,7 @@ struct First3Params {
   float* y;                       // [n, hout, wout, 128] f32
   int n, hin, win, hout, wout, tiles_x, tiles_y, total_tiles;
   int off_a, off_w, off_scratch, off_patch;
+  int cout;                       // 128 or 192 output channels (N of the MMAs; one [cout x 64] weight panel = cout * 128 bytes)
   int* status;
 };
 
@@ -299,9 +496,9 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ First3Barriers sb;
-  __shared__ float s_bias[128];
+  __shared__ float s_bias[256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  if (tid < 128) s_bias[tid] = f.bias[tid];
+  if (tid < f.cout) s_bias[tid] = f.bias[tid];
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sb.a_full[i], 128); mbar_init(&sb.a_empty[i], 1);
@@ -312,7 +509,7 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     sb.abort_flag = 0;
     fence_barrier_init();
   }
-  if (warp == 4) { tmem_alloc(&sb.tmem_base, 256); tmem_relinquish(); }
+  if (warp == 4) { tmem_alloc(&sb.tmem_base, 512); tmem_relinquish(); }       // two accumulators of up to 256 columns
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -376,14 +573,16 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     // ===================== weight loader + MMA issuer =====================
     if (lane == 0) {
       tma_prefetch_desc(&map_w);
-      mbar_expect_tx(&sb.w_full, 3 * kPanel);
+      const uint32_t wpanel = static_cast<uint32_t>(f.cout) * 128u;
+      mbar_expect_tx(&sb.w_full, 3 * wpanel);
       tma_load_2d(smem + f.off_w, &map_w, &sb.w_full, 0, 0);
-      tma_load_2d(smem + f.off_w + kPanel, &map_w, &sb.w_full, 64, 0);
-      tma_load_2d(smem + f.off_w + 2 * kPanel, &map_w, &sb.w_full, 128, 0);
-      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      tma_load_2d(smem + f.off_w + wpanel, &map_w, &sb.w_full, 64, 0);
+      tma_load_2d(smem + f.off_w + 2 * wpanel, &map_w, &sb.w_full, 128, 0);
+      const uint32_t idesc = umma_idesc_bf16(128, f.cout);
       const uint32_t hi = umma_desc_hi(1024);
       const uint32_t a_lo = umma_desc_lo(smem_u32(smem + f.off_a)), w_lo = umma_desc_lo(smem_u32(smem + f.off_w));
       constexpr uint32_t P = kPanel >> 4;
+      const uint32_t PW = wpanel >> 4;
       bool ok = wait_abort(&sb.w_full, 0, &sb.abort_flag, f.status);
       uint32_t it = 0;
       for (int tile = first_tile; tile < f.total_tiles && ok; tile += tile_step, ++it) {
@@ -391,20 +590,20 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         if (!wait_abort(&sb.acc_empty[g], par ^ 1, &sb.abort_flag, f.status)) break;
         if (!wait_abort(&sb.a_full[g], par, &sb.abort_flag, f.status)) break;
         tcgen05_fence_after();
-        const uint32_t d = tmem + g * 128;
+        const uint32_t d = tmem + g * 256;
         const uint32_t ab = a_lo + g * (3 * P);
         // A_hi . W_hi
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + 2 * k, hi, w_lo + 2 * k, hi, idesc, k);
-        umma_bf16_lohi(d, ab + 2 * P, hi, w_lo + 2 * P, hi, idesc, 1);
+        umma_bf16_lohi(d, ab + 2 * P, hi, w_lo + 2 * PW, hi, idesc, 1);
         // A_lo . W_hi
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + P + 2 * k, hi, w_lo + 2 * k, hi, idesc, 1);
-        umma_bf16_lohi(d, ab + 2 * P + 2, hi, w_lo + 2 * P, hi, idesc, 1);
+        umma_bf16_lohi(d, ab + 2 * P + 2, hi, w_lo + 2 * PW, hi, idesc, 1);
         // A_hi . W_lo
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + 2 * k, hi, w_lo + P + 2 * k, hi, idesc, 1);
-        umma_bf16_lohi(d, ab + 2 * P, hi, w_lo + 2 * P + 2, hi, idesc, 1);
+        for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, ab + 2 * k, hi, w_lo + PW + 2 * k, hi, idesc, 1);
+        umma_bf16_lohi(d, ab + 2 * P, hi, w_lo + 2 * PW + 2, hi, idesc, 1);
         umma_commit(&sb.a_empty[g]);
         umma_commit(&sb.acc_full[g]);
       }
@@ -421,9 +620,10 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       tile_coords(tile, img, ty, tx);
       if (!__all_sync(0xffffffffu, wait_abort(&sb.acc_full[grp], (it >> 1) & 1, &sb.abort_flag, f.status))) break;
       tcgen05_fence_after();
-      const uint32_t acc = tmem + grp * 128 + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t acc = tmem + grp * 256 + (static_cast<uint32_t>(q * 32) << 16);
+      const int ncg = f.cout / 32;
 #pragma unroll 1
-      for (int cg = 0; cg < 4; ++cg) {
+      for (int cg = 0; cg < ncg; ++cg) {
         float v[32];
         tmem_ld_32x32(acc + cg * 32, v);
         tmem_ld_wait();
@@ -440,7 +640,7 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
           const int row = q * 32 + rr;
           const int oy = ty * 16 + (row >> 3), ox = tx * 8 + (row & 7);
           if (oy < f.hout && ox < f.wout)
-            *reinterpret_cast<float4*>(f.y + ((static_cast<long>(img) * f.hout + oy) * f.wout + ox) * 128 + cg * 32 + chunk * 4) = val;
+            *reinterpret_cast<float4*>(f.y + ((static_cast<long>(img) * f.hout + oy) * f.wout + ox) * f.cout + cg * 32 + chunk * 4) = val;
         }
         __syncwarp();
       }
@@ -451,7 +651,7 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 256);
+  if (warp == 4) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -716,8 +916,8 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
 }
 
 // reference [128, 3, 5, 5] -> bf16 [128][192]: [hi k<64 | lo k<64 | hi k 64..79 | lo k 64..79 | 0], k = (kh * 5 + kw) * 3 + c
-__global__ void pack_first_x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 128 * 192; i += gridDim.x * blockDim.x) {
+__global__ void pack_first_x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cout * 192; i += gridDim.x * blockDim.x) {
     const int co = i / 192, col = i % 192;
     int k = -1, lo = 0;
     if (col < 64) k = col;
@@ -745,11 +945,39 @@ int pack_gdn_x3(int32_t c, float beta_min, const float* beta_raw, const float* g
 }
 
 // x [npix][128] f32 (or, pair_in, [npix][256] bf16 pairs) -> y [npix][256] bf16 pairs
+template <int NP>
+static int launch_gdn_c(const void* x, int pair_in, long npix, int inverse, const void* gamma_packed, const float* beta_eff, void* y, cudaStream_t st) {
+  constexpr int c = 64 * NP;
+  GdnX3Params p{};
+  p.ntiles = static_cast<int>((npix + 127) / 128); p.inverse = inverse; p.beta = beta_eff;
+  p.status = status_word();
+  if (!p.status) return fail(NIC_E_CUDA, "gdn bf16x3: cannot allocate the status word");
+  p.dbg_times = nullptr;
+  CUtensorMap map_x, map_g, map_o;
+  if (pair_in) { if (int rc = encode_2d(&map_x, x, 2 * c, static_cast<uint64_t>(npix), 64, 128)) return rc; }
+  else if (int rc = encode_2d_ex(&map_x, x, 4, c, static_cast<uint64_t>(npix), 32, 128)) return rc;
+  if (int rc = encode_2d(&map_g, gamma_packed, c, 2 * c, 64, 64)) return rc;
+  if (int rc = encode_2d(&map_o, y, 2 * c, static_cast<uint64_t>(npix), 64, 128)) return rc;
+  const int smem_bytes = kGRing * 2 * kPiece + 2 * 2 * NP * kPanel + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(gdn_x3c_kernel<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
+    if (int rc = check_cuda(cudaFuncSetAttribute(gdn_x3c_kernel<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
+    attr_set = true;
+  }
+  const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
+  if (pair_in) gdn_x3c_kernel<NP, true><<<grid, (4 * NP + 2) * 32, smem_bytes, st>>>(map_x, map_g, map_o, p);
+  else gdn_x3c_kernel<NP, false><<<grid, (4 * NP + 2) * 32, smem_bytes, st>>>(map_x, map_g, map_o, p);
+  return check_launch("gdn_x3c_kernel");
+}
+
+// x [npix][c] f32 (or, pair_in, [npix][2c] bf16 pairs) -> y [npix][2c] bf16 pairs; c = 128 (gamma resident) or 192 (gamma streamed)
 int gdn_fwd_tc_x3(const void* x, int pair_in, long npix, int c, int inverse, const void* gamma_packed, const float* beta_eff, void* y, cudaStream_t st) {
-  if (c != 128) return fail(NIC_E_UNSUPPORTED, "gdn bf16x3: built for c = 128 (got %d)", c);
+  if (c != 128 && c != 192) return fail(NIC_E_UNSUPPORTED, "gdn bf16x3: built for c = 128 and c = 192 (got %d)", c);
   if ((reinterpret_cast<uintptr_t>(x) & 127) || (reinterpret_cast<uintptr_t>(y) & 127) || (reinterpret_cast<uintptr_t>(gamma_packed) & 127))
     return fail(NIC_E_BADALIGN, "gdn bf16x3: tensors must be 128-byte aligned for TMA");
   if (npix <= 0) return NIC_OK;
+  if (c == 192) return launch_gdn_c<3>(x, pair_in, npix, inverse, gamma_packed, beta_eff, y, st);
   GdnX3Params p{};
   p.ntiles = static_cast<int>((npix + 127) / 128); p.inverse = inverse; p.beta = beta_eff;
   p.status = status_word();
@@ -773,10 +1001,10 @@ int gdn_fwd_tc_x3(const void* x, int pair_in, long npix, int c, int inverse, con
   return check_launch("gdn_x3_kernel");
 }
 
-size_t packed_first_x3_elems() { return static_cast<size_t>(128) * 192; }
+size_t packed_first_x3_elems(int cout) { return static_cast<size_t>(cout) * 192; }
 
-int pack_first_x3(const float* w_ref, void* w_packed, cudaStream_t st) {
-  pack_first_x3_kernel<<<96, 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed));
+int pack_first_x3(const float* w_ref, void* w_packed, int cout, cudaStream_t st) {
+  pack_first_x3_kernel<<<(cout * 192 + 255) / 256, 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed), cout);
   return check_launch("pack_first_x3_kernel");
 }
 
@@ -788,18 +1016,19 @@ int conv_first_x3(const nic_conv_desc* d, const void* x, const void* w_packed, c
   f.x = static_cast<const float*>(x); f.bias = bias; f.y = y;
   f.n = d->n; f.hin = d->h_in; f.win = d->w_in; f.hout = d->h_out; f.wout = d->w_out;
   f.tiles_x = (d->w_out + 7) / 8; f.tiles_y = (d->h_out + 15) / 16; f.total_tiles = f.tiles_x * f.tiles_y * d->n;
-  f.off_a = 0; f.off_w = 6 * kPanel; f.off_scratch = 9 * kPanel; f.off_patch = f.off_scratch + 8 * 32 * kScratchRow;
+  f.cout = d->c_out;
+  f.off_a = 0; f.off_w = 6 * kPanel; f.off_scratch = f.off_w + 3 * f.cout * 128; f.off_patch = f.off_scratch + 8 * 32 * kScratchRow;
   f.status = status_word();
   if (!f.status) return fail(NIC_E_CUDA, "conv bf16x3: cannot allocate the status word");
   const int smem_bytes = f.off_patch + 2 * kPatchStride + 1024 + 64;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || d->w_in % 4) return fail(NIC_E_BADALIGN, "conv bf16x3 (first layer): the image must be 16-byte aligned with rows of a multiple of 4 floats");
   CUtensorMap map_w, map_img;
-  if (int rc = encode_2d(&map_w, w_packed, 192, 128, 64, 128)) return rc;
+  if (int rc = encode_2d(&map_w, w_packed, 192, f.cout, 64, f.cout)) return rc;
   if (int rc = encode_image_patch(&map_img, x, d->n, 3, d->h_in, d->w_in, kPatchW, kPatchH)) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int attr_bytes = 0;
+  if (attr_bytes < smem_bytes) {
     if (int rc = check_cuda(cudaFuncSetAttribute(conv_first_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
-    attr_set = true;
+    attr_bytes = smem_bytes;
   }
   const int grid = f.total_tiles < kNumSMs ? f.total_tiles : kNumSMs;
   conv_first_x3_kernel<<<grid, kF3Threads, smem_bytes, st>>>(map_w, map_img, f);

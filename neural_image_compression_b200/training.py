@@ -154,7 +154,7 @@ def _train_op(conv: nn.Module, epilogue: int, mask_a: bool = False) -> engine.Co
 
 
 def _is_first_layer_shape(conv: nn.Module) -> bool:
-    return (isinstance(conv, nn.Conv2d) and not isinstance(conv, nn.ConvTranspose2d) and conv.in_channels == 3 and conv.out_channels == 128
+    return (isinstance(conv, nn.Conv2d) and not isinstance(conv, nn.ConvTranspose2d) and conv.in_channels == 3 and conv.out_channels in (128, 192)
             and conv.kernel_size == (5, 5) and conv.stride == (2, 2) and conv.padding == (2, 2))
 
 

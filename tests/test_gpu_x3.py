@@ -66,9 +66,9 @@ def _close(y, ref, tol=TOL):
     return err
 
 
-def _gdn(inverse=False):
+def _gdn(inverse=False, c=128):
     from neural_image_compression_b200.gdn import GDN
-    g = GDN(128, inverse=inverse)
+    g = GDN(c, inverse=inverse)
     with torch.no_grad():
         g.gamma.add_(0.02 * torch.rand_like(g.gamma)); g.beta.add_(0.1 * torch.rand_like(g.beta))
     return g
@@ -94,6 +94,37 @@ def test_x3_conv_then_gdn_on_tensor_cores(inverse, hw):
     conv = nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1) if inverse else nn.Conv2d(128, 128, 5, 2, 2)
     x = torch.randn(2, 128, *hw)
     print(_close(_run(conv, x, epi, gdn=g), _ref(conv, x, epi, gdn=g)))
+
+
+@pytest.mark.parametrize("inverse,hw", [(False, (32, 48)), (True, (16, 24)), (False, (20, 28)), (True, (5, 9))])
+def test_x3_192_channels_conv_then_gdn(inverse, hw):
+    """The reference's default capacity (Models.py:17: latent_channels = 192): conv with two N tiles + the GDN kernel that
+    streams gamma through a ring (gdn_x3c_kernel)."""
+    from neural_image_compression_b200._lib import EPI_GDN, EPI_IGDN
+    torch.manual_seed(48)
+    g = _gdn(inverse, c=192)
+    epi = EPI_IGDN if inverse else EPI_GDN
+    conv = nn.ConvTranspose2d(192, 192, 5, 2, 2, output_padding=1) if inverse else nn.Conv2d(192, 192, 5, 2, 2)
+    x = torch.randn(2, 192, *hw)
+    print(_close(_run(conv, x, epi, gdn=g), _ref(conv, x, epi, gdn=g)))
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 96), (1, 3, 80, 48)])
+def test_x3_first_layer_192_channels(shape):
+    from neural_image_compression_b200._lib import EPI_GDN
+    torch.manual_seed(49)
+    conv, g = nn.Conv2d(3, 192, 5, 2, 2), _gdn(c=192)
+    x = torch.rand(*shape)
+    print(_close(_run(conv, x, EPI_GDN, gdn=g, from_image=True), _ref(conv, x, EPI_GDN, gdn=g)))
+
+
+@pytest.mark.parametrize("hw", [(16, 24), (7, 15)])
+def test_x3_last_layer_192_channels(hw):
+    from neural_image_compression_b200._lib import EPI_BIAS
+    torch.manual_seed(50)
+    conv = nn.ConvTranspose2d(192, 3, 5, 2, 2, output_padding=1)
+    x = torch.randn(2, 192, *hw)
+    print(_close(_run(conv, x, EPI_BIAS, out_nchw_f32=True), _ref(conv, x, EPI_BIAS)))
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 64, 96), (1, 3, 80, 48), (3, 3, 32, 32)])
