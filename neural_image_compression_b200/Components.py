@@ -105,3 +105,7 @@ class HyperDecoder5x5(_Transform):
         self.net = nn.Sequential(_deconv(m, m), nn.LeakyReLU(inplace=True), _deconv(m, int(1.5 * m)),
                                  nn.LeakyReLU(inplace=True), _conv(int(1.5 * m), 2 * m, 3, 1))
         self._build_ops()
+        mid = int(1.5 * m)
+        if mid % 64 and mid > 64:       # e.g. m = 192: 288 channels travel as 320 on the tensor-core arms (engine.ConvOp)
+            pad = (mid + 63) // 64 * 64
+            self._ops[1].tc_pad_cout, self._ops[2].tc_pad_cin = pad, pad

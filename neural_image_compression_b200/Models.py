@@ -31,6 +31,69 @@ from .EntropyModels import FactorizedEntropyBottleneck, GaussianConditional, Gau
 from .ParametersModels import EntropyParameters
 
 
+def _pair_trunk(model, x, training, noise, prec_up, prec):
+    """g_a -> y hand-off -> h_a -> z hand-off of the fused pipeline (Models.py:52-66): activations NHWC between layers (bf16 hi/lo
+    pairs in the bf16x3 arm).  Returns (y, y_in, y_in_nhwc, z, z_in, z_in_nhwc)."""
+    B, _, H, W = x.shape
+    M = model.M
+    adt = engine.act_dtype(prec)
+    pair = prec == "bf16x3"
+    hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
+    noise_z = noise_y = None
+    if training:
+        if noise is not None:
+            noise_z, noise_y = noise
+        else:
+            noise_z = torch.rand((B, M, hz, wz), device=x.device) - 0.5
+            noise_y = torch.rand((B, M, hy, wy), device=x.device) - 0.5
+    qmode = Q_NOISE if training else Q_ROUND
+    a, h, w, layout = x, H, W, LAYOUT_NCHW
+    enc = model.encoder.ops
+    for i, op in enumerate(enc):
+        a = op.run(a, B, h, w, prec_up, in_layout=layout, out_layout=LAYOUT_NHWC,
+                   out_dtype=torch.float32 if i == len(enc) - 1 else None)
+        h, w = engine.conv_out_hw(op.conv, h, w)
+        layout = LAYOUT_NHWC
+    y_nhwc = a                                                     # f32 [B, hy, wy, M]
+    lowp = prec_up != "fp32"
+    y, y_in, y_in_nhwc, y_lowp = engine.latent_handoff(y_nhwc, qmode, noise_y, "bf16x2" if pair else adt, want_lowp=lowp,
+                                                       lowp_pair=prec_up == "bf16x3")
+    # h_a reads the unquantised y (Models.py:53)
+    a, h, w = (y_lowp if lowp else y_nhwc), hy, wy
+    ha = model.hyper_encoder.ops
+    for i, op in enumerate(ha):
+        a = op.run(a, B, h, w, prec_up, out_dtype=torch.float32 if i == len(ha) - 1 else None)
+        h, w = engine.conv_out_hw(op.conv, h, w)
+    z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, qmode, noise_z, "bf16x2" if pair else adt)
+    return y, y_in, y_in_nhwc, z, z_in, z_in_nhwc
+
+
+def _pair_h_s_into(model, z_in_nhwc, B, hz, wz, prec, combined, c_total, c_offset):
+    """h_s (Models.py:69) with its last conv writing psi into channels [c_offset, c_offset + 2M) of `combined`."""
+    z_flag = getattr(z_in_nhwc, "_nic_lo_flag", None)
+    a, h, w = z_in_nhwc, hz, wz
+    hs = model.hyper_decoder.ops
+    for i, op in enumerate(hs):
+        if i == len(hs) - 1:
+            op.run(a, B, h, w, prec, out=combined, out_c_total=c_total, out_c_offset=c_offset)
+        else:
+            a = op.run(a, B, h, w, prec, in_lo_flag=z_flag if i == 0 else None)
+        h, w = engine.conv_out_hw(op.conv, h, w)
+
+
+def _pair_g_s(model, y_in_nhwc, B, hy, wy, prec):
+    """g_s (Models.py:90): NHWC symbols -> x_hat NCHW f32."""
+    y_flag = getattr(y_in_nhwc, "_nic_lo_flag", None)
+    a, h, w = y_in_nhwc, hy, wy
+    dec = model.decoder.ops
+    for i, op in enumerate(dec):
+        last = i == len(dec) - 1
+        a = op.run(a, B, h, w, prec, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC,
+                   out_dtype=torch.float32 if last else None, in_lo_flag=y_flag if i == 0 else None)
+        h, w = engine.conv_out_hw(op.conv, h, w)
+    return a
+
+
 class JointAutoregressiveHierarchical(nn.Module):
     """
     latent_channels : int, default=192, number of channels in the bottleneck y (M).
@@ -90,9 +153,9 @@ class JointAutoregressiveHierarchical(nn.Module):
             # runs the forward-only path of self.precision instead.
             from . import training as _training
             return _training.train_forward(self, x, noise=noise, lean=lean)
-        if self.precision == "bf16x3" and self.M != 128:
-            # the fused pair-tensor pipeline (GDN kernels, first layer) is built for 128 channels; other channel counts that are
-            # multiples of 64 (the reference's default M = 192) run layer by layer: every conv and both GDN contractions on the
+        if self.precision == "bf16x3" and self.M not in (128, 192):
+            # the fused pair-tensor pipeline (GDN kernels, first layer) is built for 128 and 192 channels (the reference's default);
+            # other channel counts that are multiples of 64 run layer by layer: every conv and both GDN contractions on the
             # tcgen05 engine, fp32 NHWC tensors in between (training._forward_impl with rounding instead of noise)
             if self.M % 64:
                 raise ValueError(f"precision='bf16x3' needs latent_channels % 64 == 0, got {self.M}")
@@ -122,51 +185,16 @@ class JointAutoregressiveHierarchical(nn.Module):
         x = x.contiguous().float()
         hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
         with torch.cuda.device(x.device), torch.no_grad():
-            noise_z = noise_y = None
-            if training:
-                if noise is not None:
-                    noise_z, noise_y = noise
-                else:
-                    noise_z = torch.rand((B, M, hz, wz), device=x.device) - 0.5
-                    noise_y = torch.rand((B, M, hy, wy), device=x.device) - 0.5
-            qmode = Q_NOISE if training else Q_ROUND
-
-            # ---- g_a ------------------------------------------------------------------------------
-            a, h, w, layout = x, H, W, LAYOUT_NCHW
-            enc = self.encoder.ops
-            for i, op in enumerate(enc):
-                a = op.run(a, B, h, w, prec_up, in_layout=layout, out_layout=LAYOUT_NHWC,
-                           out_dtype=torch.float32 if i == len(enc) - 1 else None)
-                h, w = engine.conv_out_hw(op.conv, h, w)
-                layout = LAYOUT_NHWC
-            y_nhwc = a                                                     # f32 [B, hy, wy, M]
-            lowp = prec_up != "fp32"
-            y, y_in, y_in_nhwc, y_lowp = engine.latent_handoff(y_nhwc, qmode, noise_y, "bf16x2" if pair else adt, want_lowp=lowp,
-                                                               lowp_pair=prec_up == "bf16x3")
-
-            # ---- h_a (reads the unquantised y, Models.py:53) ------------------------------------
-            a, h, w = (y_lowp if lowp else y_nhwc), hy, wy
-            ha = self.hyper_encoder.ops
-            for i, op in enumerate(ha):
-                a = op.run(a, B, h, w, prec_up, out_dtype=torch.float32 if i == len(ha) - 1 else None)
-                h, w = engine.conv_out_hw(op.conv, h, w)
-            z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, qmode, noise_z, "bf16x2" if pair else adt)
+            y, y_in, y_in_nhwc, z, z_in, z_in_nhwc = _pair_trunk(self, x, training, noise, prec_up, prec)
 
             # ---- h_s -> psi = combined[..., 2M:4M];  context -> phi = combined[..., 0:2M] -------
+            # (the quantised symbols split into bf16 pairs with an all-zero lo half - the hand-off kernel checks and flags it on the
+            #  device: their first consumers - h_s layer 1, the context conv, g_s layer 1 - run 2 of the 3 MMA passes)
             combined = torch.empty((B, hy, wy, cw * 4 * M), dtype=adt, device=x.device)
-            # the quantised symbols split into bf16 pairs with an all-zero lo half (the hand-off kernel checks and flags it on the
-            # device): their first consumers - h_s layer 1, the context conv, g_s layer 1 - run 2 of the 3 MMA passes
-            y_flag, z_flag = getattr(y_in_nhwc, "_nic_lo_flag", None), getattr(z_in_nhwc, "_nic_lo_flag", None)
-            a, h, w = z_in_nhwc, hz, wz
-            hs = self.hyper_decoder.ops
-            for i, op in enumerate(hs):
-                if i == len(hs) - 1:
-                    op.run(a, B, h, w, prec, out=combined, out_c_total=4 * M, out_c_offset=2 * M)
-                else:
-                    a = op.run(a, B, h, w, prec, in_lo_flag=z_flag if i == 0 else None)
-                h, w = engine.conv_out_hw(op.conv, h, w)
+            _pair_h_s_into(self, z_in_nhwc, B, hz, wz, prec, combined, 4 * M, 2 * M)
             self.context_model.masked.apply_mask_()
-            self.context_model.masked._op.run(y_in_nhwc, B, hy, wy, prec, out=combined, out_c_total=4 * M, out_c_offset=0, in_lo_flag=y_flag)
+            self.context_model.masked._op.run(y_in_nhwc, B, hy, wy, prec, out=combined, out_c_total=4 * M, out_c_offset=0,
+                                              in_lo_flag=getattr(y_in_nhwc, "_nic_lo_flag", None))
 
             # ---- entropy parameters (1x1 stack) ---------------------------------------------------
             ep = self.entropy_parameters.ops
@@ -180,14 +208,7 @@ class JointAutoregressiveHierarchical(nn.Module):
             p_y, logp_y = ly["p"], ly["logp"]
 
             # ---- g_s -----------------------------------------------------------------------------------
-            a, h, w = y_in_nhwc, hy, wy
-            dec = self.decoder.ops
-            for i, op in enumerate(dec):
-                last = i == len(dec) - 1
-                a = op.run(a, B, h, w, prec, out_layout=LAYOUT_NCHW if last else LAYOUT_NHWC,
-                           out_dtype=torch.float32 if last else None, in_lo_flag=y_flag if i == 0 else None)
-                h, w = engine.conv_out_hw(op.conv, h, w)
-            x_hat = a
+            x_hat = _pair_g_s(self, y_in_nhwc, B, hy, wy, prec)
 
         # per-image partial sums of logp ride along for rd_loss (RateDistortionLoss.py:13-14)
         logp_y._nic_partials = ly["partials"]
@@ -257,6 +278,50 @@ class ScalableImageCoding(nn.Module):
     def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
         return super().load_state_dict({k: v for k, v in state_dict.items() if not k.startswith("LST.")}, strict=strict, **kwargs)
 
+    def _forward_pairs(self, x, training, noise):
+        """The bf16x3 arm on the fused pipeline of JointAutoregressiveHierarchical (conv -> GDN kernel, activations as bf16 hi/lo
+        pairs, no fp32 round trips): the shared trunk, then the two (context, entropy-parameter, likelihood) heads over psi."""
+        B, _, H, W = x.shape
+        M, M1, M2, K = self.M, self.M1, self.M2, self.K
+        prec = "bf16x3"
+        x = x.contiguous().float()
+        hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
+        with torch.cuda.device(x.device), torch.no_grad():
+            y, y_in, y_in_nhwc, z, z_in, z_in_nhwc = _pair_trunk(self, x, training, noise, prec, prec)
+            y_flag = getattr(y_in_nhwc, "_nic_lo_flag", None)
+            c1, c2 = 2 * M1 + 2 * M, 2 * M2 + 2 * M                       # [phi_i (2 M_i) | psi (2 M)] channels of the two heads
+            comb1 = torch.empty((B, hy, wy, 2 * c1), dtype=torch.bfloat16, device=x.device)      # pair tensors: [hi(c) | lo(c)]
+            comb2 = torch.empty((B, hy, wy, 2 * c2), dtype=torch.bfloat16, device=x.device)
+            _pair_h_s_into(self, z_in_nhwc, B, hz, wz, prec, comb1, c1, 2 * M1)                  # psi once, into head 1's buffer
+            comb2[..., 2 * M2:c2] = comb1[..., 2 * M1:c1]                                        # ... head 2 gets a copy: hi half,
+            comb2[..., c2 + 2 * M2:] = comb1[..., c1 + 2 * M1:]                                  # lo half
+            y1, y2 = torch.split(y_in, [M1, M2], dim=1)                   # Models.py:279 (views, as in the reference)
+            heads = []
+            for ctx, ep, comb, ct, lo, hi_, yi in ((self.context_model_1, self.entropy_parameters_1, comb1, c1, 0, M1, y1),
+                                                   (self.context_model_2, self.entropy_parameters_2, comb2, c2, M1, M, y2)):
+                mi = hi_ - lo
+                yi_pair = torch.cat([y_in_nhwc[..., lo:hi_], y_in_nhwc[..., M + lo:M + hi_]], dim=-1).contiguous()
+                ctx.masked.apply_mask_()
+                ctx.masked._op.run(yi_pair, B, hy, wy, prec, out=comb, out_c_total=ct, out_c_offset=0, in_lo_flag=y_flag)
+                a = ep.ops[0].run(comb, B, hy, wy, prec)
+                a = ep.ops[1].run(a, B, hy, wy, prec)
+                raw = ep.ops[2].run(a, B, hy, wy, prec, out_layout=LAYOUT_NCHW, out_dtype=torch.float32)
+                heads.append(gm_likelihood(yi.contiguous(), raw, mi, K, Q_PASSTHRU, full=True, want_y_in=False))
+            _, p_z, logp_z, parts_z = self.factorized_entropy_model.likelihood(z_in, Q_PASSTHRU)
+            x_hat = _pair_g_s(self, y_in_nhwc, B, hy, wy, prec)
+        l1, l2 = heads
+        l1["logp"]._nic_partials, l2["logp"]._nic_partials, logp_z._nic_partials = l1["partials"], l2["partials"], parts_z
+        out = {
+            "x_hat": x_hat, "y": y, "y_in": y_in, "y1": y1, "y2": y2, "z": z, "z_in": z_in, "p_z": p_z, "logp_z": logp_z,
+            "p_y1": l1["p"], "logp_y1": l1["logp"], "p_y2": l2["p"], "logp_y2": l2["logp"], "training": training,
+        }
+        if K == 1:
+            out.update({"mu1": l1["mu"], "sigma1": l1["sigma"], "mu2": l2["mu"], "sigma2": l2["sigma"]})
+        else:
+            out.update({"weights1": l1["weights"], "mus1": l1["mus"], "sigmas1": l1["sigmas"],
+                        "weights2": l2["weights"], "mus2": l2["mus"], "sigmas2": l2["sigmas"]})
+        return out
+
     def forward(self, x: torch.Tensor, training: bool = True, debug=False, *,
                 noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
         engine.require_cuda(x, "x")
@@ -270,6 +335,8 @@ class ScalableImageCoding(nn.Module):
             from . import training_scalable as _ts
             return _ts.train_forward(self, x, noise=noise)
         arm, M, M1, M2, K = self.precision, self.M, self.M1, self.M2, self.K
+        if arm == "bf16x3" and M in (128, 192) and M1 % 64 == 0 and M2 % 64 == 0:
+            return self._forward_pairs(x, training, noise)
         from . import training as T
 
         def layer(op, a, h, w, **kw):

@@ -53,17 +53,28 @@ class ConvOp:
     storage or its in-place version counter changes (load_state_dict, optimizer step, .to()).
     """
 
-    def __init__(self, conv: nn.Module, epilogue: int = EPI_BIAS, gdn: Optional[nn.Module] = None, mask_a: bool = False):
+    def __init__(self, conv: nn.Module, epilogue: int = EPI_BIAS, gdn: Optional[nn.Module] = None, mask_a: bool = False,
+                 tc_pad_cin: Optional[int] = None, tc_pad_cout: Optional[int] = None):
         self.conv, self.epilogue, self.gdn, self.mask_a = conv, epilogue, gdn, mask_a
         self.transposed = isinstance(conv, nn.ConvTranspose2d)
+        # tensor-core arms only: the layer runs with its input / output channels zero-padded to these counts (the engine walks
+        # channels in chunks of 64; h_s of the 192-channel model has a 288-channel tensor between its last two layers, which
+        # travels as 320 channels whose last 32 are exactly 0 = LeakyReLU(0 . x + 0))
+        self.tc_pad_cin, self.tc_pad_cout = tc_pad_cin, tc_pad_cout
         self._cache = {}
+
+    def channels(self, precision):
+        cv, tc = self.conv, precision != "fp32"
+        return ((self.tc_pad_cin if tc and self.tc_pad_cin else cv.in_channels),
+                (self.tc_pad_cout if tc and self.tc_pad_cout else cv.out_channels))
 
     def desc(self, n, h, w, precision, in_layout, out_layout, in_dtype, out_dtype, out_c_total=0, out_c_offset=0) -> ConvDesc:
         cv = self.conv
         ho, wo = conv_out_hw(cv, h, w)
         d = ConvDesc()
-        d.n, d.c_in, d.h_in, d.w_in = n, cv.in_channels, h, w
-        d.c_out, d.h_out, d.w_out = cv.out_channels, ho, wo
+        cin, cout = self.channels(precision)
+        d.n, d.c_in, d.h_in, d.w_in = n, cin, h, w
+        d.c_out, d.h_out, d.w_out = cout, ho, wo
         d.kh, d.kw, d.stride, d.pad = cv.kernel_size[0], cv.kernel_size[1], cv.stride[0], cv.padding[0]
         d.transposed = int(self.transposed)
         d.output_padding = cv.output_padding[0] if self.transposed else 0
@@ -95,8 +106,13 @@ class ConvOp:
         wp = torch.empty(elems, dtype=act_dtype(precision), device=dev)
         with torch.cuda.device(dev):
             w32 = cv.weight.detach().float().contiguous()
-            check(lib.nic_pack_conv_weight(C.byref(d), ptr(w32), ptr(wp), current_stream()), "nic_pack_conv_weight")
             bias = cv.bias.detach().float().contiguous()
+            cin, cout = self.channels(precision)
+            if (cin, cout) != (cv.in_channels, cv.out_channels):          # zero padding of the channel dimensions (see __init__)
+                pi, po = cin - cv.in_channels, cout - cv.out_channels
+                w32 = torch.nn.functional.pad(w32, (0, 0, 0, 0, 0, po, 0, pi) if self.transposed else (0, 0, 0, 0, 0, pi, 0, po)).contiguous()
+                bias = torch.nn.functional.pad(bias, (0, po)).contiguous()
+            check(lib.nic_pack_conv_weight(C.byref(d), ptr(w32), ptr(wp), current_stream()), "nic_pack_conv_weight")
             gamma = beta = None
             if self.gdn is not None:
                 c = cv.out_channels
