@@ -6,7 +6,8 @@ Same class names, constructor arguments and ``net.<i>`` parameter names as the r
 conv (+ the GDN / IGDN / LeakyReLU after it) is one ``nic_conv_fwd`` call with the activation fused
 into the epilogue, activations staying NHWC between layers.
 
-The 3x3 residual family (Encoder3x3 ... and Layers.py) is outside the hot path.
+The 3x3 residual family (Encoder3x3 / Decoder3x3 / HyperEncoder3x3 / HyperDecoder3x3, Components.py:20-32, 49-62, 77-91,
+107-122; blocks in Layers.py) runs layer by layer on the same engine.
 """
 from __future__ import annotations
 
@@ -109,3 +110,96 @@ class HyperDecoder5x5(_Transform):
         if mid % 64 and mid > 64:       # e.g. m = 192: 288 channels travel as 320 on the tensor-core arms (engine.ConvOp)
             pad = (mid + 63) // 64 * 64
             self._ops[1].tc_pad_cout, self._ops[2].tc_pad_cin = pad, pad
+
+
+# ---- the 3x3 residual family -----------------------------------------------------------------------
+
+class _Chain(nn.Module):
+    """`net` = the reference's nn.Sequential of residual blocks / convs / LeakyReLUs, executed as a chain of engine calls on f32
+    NHWC tensors: a conv followed by nn.LeakyReLU runs with the LeakyReLU epilogue fused."""
+    precision = None
+
+    def run_nhwc(self, x, n, h, w, arm, in_layout=None):
+        from . import Layers as L
+        from ._lib import LAYOUT_NHWC
+        layout = LAYOUT_NHWC if in_layout is None else in_layout
+        mods, i = list(self.net), 0
+        while i < len(mods):
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            fuse = isinstance(nxt, nn.LeakyReLU)
+            if isinstance(m, L.TransposedDeconv3x3):
+                x, h, w = m.run_nhwc(x, n, h, w, arm, in_layout=layout, epilogue=EPI_LRELU if fuse else EPI_BIAS)
+            elif isinstance(m, L._Block):
+                x, h, w = m.run_nhwc(x, n, h, w, arm, in_layout=layout)
+                fuse = False
+            elif isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                x, h, w = L._conv(arm, m, EPI_LRELU if fuse else EPI_BIAS, x, n, h, w, in_layout=layout)
+            else:
+                raise TypeError(f"unexpected module in a transform: {type(m).__name__}")
+            layout = LAYOUT_NHWC
+            i += 2 if fuse else 1
+        return x, h, w
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import Layers as L
+        from ._lib import LAYOUT_NCHW
+        engine.require_cuda(x, "x")
+        n, c, h, w = x.shape
+        arm = L._arm(self.precision, c if c >= 64 else 64)
+        with torch.cuda.device(x.device), torch.no_grad():
+            y, _, _ = self.run_nhwc(x.contiguous().float(), n, h, w, arm, in_layout=LAYOUT_NCHW)
+        return y.permute(0, 3, 1, 2).contiguous()
+
+
+class Encoder3x3(_Chain):
+    """g_a of the residual family: three (strided residual block + GDN, residual block) pairs and a stride-2 3x3 bottleneck
+    (Components.py:20-32)."""
+
+    def __init__(self, latent_channels=192):
+        super().__init__()
+        from .Layers import ResidualBlock, ResidualBlockWithStride
+        m, blocks, cin = latent_channels, [], 3
+        for _ in range(3):
+            blocks += [ResidualBlockWithStride(cin, m, stride=2), ResidualBlock(m, m)]
+            cin = m
+        self.net = nn.Sequential(*blocks, nn.Conv2d(m, m, kernel_size=3, stride=2, padding=1))
+
+
+class Decoder3x3(_Chain):
+    """g_s: (residual block, upsampling residual block + IGDN) x 3, a residual block and a 3x3 stride-2 transposed conv to RGB
+    (Components.py:49-62)."""
+
+    def __init__(self, latent_channels=192):
+        super().__init__()
+        from .Layers import ResidualBlock, ResidualBlockUpsample, TransposedDeconv3x3
+        m, blocks = latent_channels, []
+        for _ in range(3):
+            blocks += [ResidualBlock(m, m), ResidualBlockUpsample(m, m, 2)]
+        self.net = nn.Sequential(*blocks, ResidualBlock(m, m), TransposedDeconv3x3(m, 3, 2))
+
+
+class HyperEncoder3x3(_Chain):
+    """h_a: five 3x3 convs (strides 1, 1, 2, 1, 2) with LeakyReLU between (Components.py:77-91)."""
+
+    def __init__(self, latent_channels=192):
+        super().__init__()
+        m, layers = latent_channels, []
+        for i, s in enumerate((1, 1, 2, 1, 2)):
+            layers.append(nn.Conv2d(m, m, kernel_size=3, stride=s, padding=1))
+            if i < 4:
+                layers.append(nn.LeakyReLU(inplace=True))
+        self.net = nn.Sequential(*layers)
+
+
+class HyperDecoder3x3(_Chain):
+    """h_s: conv, deconv x2, conv (-> 1.5 M), deconv x2, conv (-> 2 M), LeakyReLU between (Components.py:107-122)."""
+
+    def __init__(self, latent_channels=192):
+        super().__init__()
+        from .Layers import TransposedDeconv3x3
+        m, mid = latent_channels, int(1.5 * latent_channels)
+        act = lambda: nn.LeakyReLU(inplace=True)      # noqa: E731
+        self.net = nn.Sequential(nn.Conv2d(m, m, kernel_size=3, stride=1, padding=1), act(), TransposedDeconv3x3(m, m, 2), act(),
+                                 nn.Conv2d(m, mid, kernel_size=3, stride=1, padding=1), act(), TransposedDeconv3x3(mid, mid, 2), act(),
+                                 nn.Conv2d(mid, 2 * m, kernel_size=3, stride=1, padding=1))

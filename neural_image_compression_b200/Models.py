@@ -225,6 +225,93 @@ class JointAutoregressiveHierarchical(nn.Module):
         return out
 
 
+class HierarchicalMixtureResidual(nn.Module):
+    """``HierarchicalMixtureResidual`` of /root/reference/Models.py:109-205: the same entropy side and output dict as
+    JointAutoregressiveHierarchical with the 3x3 residual transforms (Encoder3x3 / Decoder3x3 / HyperEncoder3x3 / HyperDecoder3x3,
+    Components.py:20-122, blocks of Layers.py).  Same constructor, attributes and ``state_dict`` keys.
+
+    Forward-only (evaluation, or training=True under torch.no_grad() with the noise relaxation): the transforms run layer by
+    layer on the conv engine (f32 NHWC tensors between layers; residual sums by nic_add_inplace), the entropy side on the same
+    kernels as the 5x5 model.  precision: "bf16x3" (default when latent_channels is a multiple of 64: tensor cores with hi/lo-
+    split operands; the 3-channel first block on the fp32 CUDA-core kernels) or "fp32".  The training step (backward) of this
+    family is not built: calling it with autograd enabled raises."""
+
+    def __init__(self, latent_channels: int = 192, K: int = 1, *, precision: Optional[str] = None):
+        super().__init__()
+        if not isinstance(latent_channels, int) or latent_channels < 1:
+            raise ValueError(f"latent_channels must be int >= 1, got {latent_channels}")
+        if not isinstance(K, int) or K < 1:
+            raise ValueError(f"K must be int >= 1, got {K}")
+        from .Components import Decoder3x3, Encoder3x3, HyperDecoder3x3, HyperEncoder3x3
+        self.M = latent_channels
+        self.K = K
+        self.H = latent_channels
+        self.distribution = "Mean-Scale Gaussian" if K == 1 else "Mixture of Gaussians"
+        self.conditional = GaussianConditional() if K == 1 else GaussianMixtureConditional()
+        # construction order follows Models.py:133-146 so a seeded build draws the reference's initial weights
+        self.encoder = Encoder3x3(latent_channels=self.M)
+        self.decoder = Decoder3x3(latent_channels=self.M)
+        self.hyper_encoder = HyperEncoder3x3(latent_channels=self.M)
+        self.hyper_decoder = HyperDecoder3x3(latent_channels=self.M)
+        self.factorized_entropy_model = FactorizedEntropyBottleneck(self.M)
+        self.context_model = ContextModel(latent_channels=self.M)
+        self.entropy_parameters = EntropyParameters(latent_channels=self.M, hyper_latent_channels=self.H, K=self.K)
+        precision = precision or engine.DEFAULT_PRECISION
+        self.precision = ("bf16x3" if self.M % 64 == 0 else "fp32") if precision == "auto" else precision
+        if self.precision not in ("fp32", "bf16x3") or (self.precision == "bf16x3" and self.M % 64):
+            raise ValueError("HierarchicalMixtureResidual: precision must be 'fp32', or 'bf16x3' with latent_channels % 64 == 0")
+
+    def forward(self, x: torch.Tensor, training: bool = True, *, noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                lean: bool = False):
+        engine.require_cuda(x, "x")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected x of shape [B, 3, H, W], got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        if H % 64 or W % 64:
+            raise ValueError(f"H and W must be multiples of 64; got {H}x{W}")
+        if training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("HierarchicalMixtureResidual: the training step (backward kernels) of the 3x3 residual family is "
+                                      "not built; call under torch.no_grad() for the forward pass")
+        from . import training as T
+        arm, M, K = self.precision, self.M, self.K
+        hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
+        x = x.contiguous().float()
+        with torch.cuda.device(x.device), torch.no_grad():
+            noise_z = noise_y = None
+            if training:
+                noise_z, noise_y = noise if noise is not None else (torch.rand((B, M, hz, wz), device=x.device) - 0.5,
+                                                                    torch.rand((B, M, hy, wy), device=x.device) - 0.5)
+            qmode = Q_NOISE if training else Q_ROUND
+            y_nhwc, _, _ = self.encoder.run_nhwc(x, B, H, W, arm, in_layout=LAYOUT_NCHW)
+            y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, qmode, noise_y, torch.float32)
+            z_nhwc, _, _ = self.hyper_encoder.run_nhwc(y_nhwc, B, hy, wy, arm)
+            z, z_in, z_in_nhwc, _ = engine.latent_handoff(z_nhwc, qmode, noise_z, torch.float32)
+            psi, _, _ = self.hyper_decoder.run_nhwc(z_in_nhwc, B, hz, wz, arm)
+            combined = torch.empty((B, hy, wy, 4 * M), dtype=torch.float32, device=x.device)
+            combined[..., 2 * M:] = psi                      # torch.cat([phi, psi]) of Models.py:171: phi is written in place below
+            masked = self.context_model.masked
+            masked.apply_mask_()
+            T.conv_forward(arm, masked, engine.EPI_BIAS, y_in_nhwc, B, hy, wy, out=combined, out_c_total=4 * M, out_c_offset=0,
+                           mask_a=masked._op.mask_a)
+            ep = self.entropy_parameters.ops
+            a = T.conv_forward(arm, ep[0].conv, ep[0].epilogue, combined, B, hy, wy)
+            a = T.conv_forward(arm, ep[1].conv, ep[1].epilogue, a, B, hy, wy)
+            raw = T.conv_forward(arm, ep[2].conv, ep[2].epilogue, a, B, hy, wy, out_layout=LAYOUT_NCHW)
+            T.forget_pairs()
+            ly = gm_likelihood(y_in, raw, M, K, Q_PASSTHRU, full=not lean, want_y_in=False)
+            _, p_z, logp_z, parts_z = self.factorized_entropy_model.likelihood(z_in, Q_PASSTHRU)
+            x_nhwc, _, _ = self.decoder.run_nhwc(y_in_nhwc, B, hy, wy, arm)
+            x_hat = x_nhwc.permute(0, 3, 1, 2).contiguous()
+        p_y, logp_y = ly["p"], ly["logp"]
+        logp_y._nic_partials, logp_z._nic_partials = ly["partials"], parts_z
+        out = {"x_hat": x_hat, "y": y, "y_in": y_in, "z": z, "z_in": z_in, "p_z": p_z, "logp_z": logp_z, "p_y": p_y, "logp_y": logp_y,
+               "training": training}
+        if not lean:
+            out.update({"mu": ly["mu"], "sigma": ly["sigma"]} if K == 1 else
+                       {"weights": ly["weights"], "mus": ly["mus"], "sigmas": ly["sigmas"]})
+        return out
+
+
 class ScalableImageCoding(nn.Module):
     """The scalable-coding variant of /root/reference/Models.py:208-338: the JointAutoregressiveHierarchical trunk at M
     channels with y split into a base part y1 (M1 channels) and an enhancement part y2 (M - M1), each with its own

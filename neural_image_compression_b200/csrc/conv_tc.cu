@@ -1346,7 +1346,8 @@ size_t packed_weight_elems_tc(const nic_conv_desc* d, const TapTable& tt) {
     if (small_cin(d)) return packed_first_x3_elems(d->c_out == 192 ? 192 : 128);
     if (last_scatter_applies(d)) return packed_last_scatter_elems(d->c_in);
     if (subpixel_form(d)) return static_cast<size_t>(9) * 16 * 3 * d->c_in;
-    const int cp = (d->c_out + 127) / 128 * 128;
+    const int nbx = nb_for(d->c_out);
+    const int cp = (d->c_out + nbx - 1) / nbx * nbx;          // the kernel's c_out padding: N tiles of 128, or one of 16
     return static_cast<size_t>(tt.ntaps) * cp * 3 * d->c_in;
   }
   if (small_cin(d)) return static_cast<size_t>(128) * 128;
@@ -1372,7 +1373,8 @@ int pack_weight_tc(const nic_conv_desc* d, const TapTable& tt, const float* w_re
                                                                                          d->c_out, tt);
       return check_launch("pack_weight_subpixel_x3_kernel");
     }
-    const int cp = (d->c_out + 127) / 128 * 128;
+    const int nbx = nb_for(d->c_out);
+    const int cp = (d->c_out + nbx - 1) / nbx * nbx;
     const long total = static_cast<long>(tt.ntaps) * cp * 3 * d->c_in;
     const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
     pack_weight_x3_kernel<<<blocks, 256, 0, st>>>(w_ref, static_cast<__nv_bfloat16*>(w_packed), d->c_in, d->c_out, cp, d->kh, d->kw,

@@ -28,6 +28,7 @@ Reference lines followed (all under /root/reference):
   EntropyModels.py:192-230    discretized Gaussian / mixture pmf
   utils.py:6-8                Phi(u) = 0.5 * (1 + erf(u / sqrt(2)))
   RateDistortionLoss.py:5-49  rd_loss
+  Layers.py:18-119, Components.py:20-122, Models.py:150-205   the 3x3 residual family (forward_residual)
 """
 from __future__ import annotations
 
@@ -253,6 +254,99 @@ def rd_loss(out, x, lambda_rd: float):
         "psnr_per_image": psnr_per_image.detach(), "bits_y": bits_y.mean().item(),
         "bits_z": bits_z.mean().item(), "bits_total": (bits_y + bits_z).mean().item(),
     }
+
+
+# ---- the 3x3 residual family (Layers.py, Components.py:20-122, Models.py:109-205) -------------------------------------------------
+
+def _c(sd, key, x, dtype, stride=1, padding=0):
+    return F.conv2d(x, _p(sd, key + ".weight", dtype), _p(sd, key + ".bias", dtype), stride=stride, padding=padding)
+
+
+def _d(sd, key, x, dtype):
+    """TransposedDeconv3x3, Layers.py:18-24: ConvTranspose2d(3, stride 2, padding 1, output_padding 1)."""
+    return F.conv_transpose2d(x, _p(sd, key + ".deconv.weight", dtype), _p(sd, key + ".deconv.bias", dtype), stride=2, padding=1,
+                              output_padding=1)
+
+
+def _res_block(sd, k, x, dtype):
+    """ResidualBlock, Layers.py:91-119 (in_ch == out_ch on this path: identity skip)."""
+    out = F.leaky_relu(_c(sd, k + ".conv1", x, dtype, padding=1), 0.01)
+    out = F.leaky_relu(_c(sd, k + ".conv2", out, dtype, padding=1), 0.01)
+    idn = _c(sd, k + ".skip", x, dtype) if (k + ".skip.weight") in sd else x
+    return out + idn
+
+
+def _res_stride(sd, k, x, dtype):
+    """ResidualBlockWithStride, Layers.py:27-61: conv(s2) - LeakyReLU - conv - GDN, + 1x1 strided skip."""
+    out = F.leaky_relu(_c(sd, k + ".conv1", x, dtype, stride=2, padding=1), 0.01)
+    out = _gdn(sd, k + ".gdn", _c(sd, k + ".conv2", out, dtype, padding=1), False, dtype)
+    return out + _c(sd, k + ".skip", x, dtype, stride=2)
+
+
+def _res_up(sd, k, x, dtype):
+    """ResidualBlockUpsample, Layers.py:64-88: deconv - LeakyReLU - conv - IGDN, + deconv skip."""
+    out = F.leaky_relu(_d(sd, k + ".subpel_conv", x, dtype), 0.01)
+    out = _gdn(sd, k + ".igdn", _c(sd, k + ".conv", out, dtype, padding=1), True, dtype)
+    return out + _d(sd, k + ".upsample", x, dtype)
+
+
+def analysis_3x3(sd, x, dtype=torch.float32):
+    """Encoder3x3, Components.py:20-32."""
+    h = x
+    for i in (0, 2, 4):
+        h = _res_block(sd, f"encoder.net.{i + 1}", _res_stride(sd, f"encoder.net.{i}", h, dtype), dtype)
+    return _c(sd, "encoder.net.6", h, dtype, stride=2, padding=1)
+
+
+def synthesis_3x3(sd, y_in, dtype=torch.float32):
+    """Decoder3x3, Components.py:49-62."""
+    h = y_in
+    for i in (0, 2, 4):
+        h = _res_up(sd, f"decoder.net.{i + 1}", _res_block(sd, f"decoder.net.{i}", h, dtype), dtype)
+    return _d(sd, "decoder.net.7", _res_block(sd, "decoder.net.6", h, dtype), dtype)
+
+
+def hyper_analysis_3x3(sd, y, dtype=torch.float32):
+    """HyperEncoder3x3, Components.py:77-91."""
+    h = y
+    for i, s in zip((0, 2, 4, 6, 8), (1, 1, 2, 1, 2)):
+        h = _c(sd, f"hyper_encoder.net.{i}", h, dtype, stride=s, padding=1)
+        if i != 8:
+            h = F.leaky_relu(h, 0.01)
+    return h
+
+
+def hyper_synthesis_3x3(sd, z_in, dtype=torch.float32):
+    """HyperDecoder3x3, Components.py:107-122."""
+    h = F.leaky_relu(_c(sd, "hyper_decoder.net.0", z_in, dtype, padding=1), 0.01)
+    h = F.leaky_relu(_d(sd, "hyper_decoder.net.2", h, dtype), 0.01)
+    h = F.leaky_relu(_c(sd, "hyper_decoder.net.4", h, dtype, padding=1), 0.01)
+    h = F.leaky_relu(_d(sd, "hyper_decoder.net.6", h, dtype), 0.01)
+    return _c(sd, "hyper_decoder.net.8", h, dtype, padding=1)
+
+
+def forward_residual(sd, x, M: int, K: int, training: bool = False, noise_z=None, noise_y=None, dtype=torch.float32):
+    """HierarchicalMixtureResidual.forward, Models.py:150-205 (same orchestration as `forward` with the 3x3 transforms)."""
+    x = x.to(DEVICE, dtype)
+    y = analysis_3x3(sd, x, dtype)
+    z = hyper_analysis_3x3(sd, y, dtype)
+    if training:
+        z_in, y_in = z + noise_z.to(DEVICE, dtype), y + noise_y.to(DEVICE, dtype)
+    else:
+        z_in, y_in = torch.round(z), torch.round(y)
+    psi = hyper_synthesis_3x3(sd, z_in, dtype)
+    phi = context(sd, y_in, dtype)
+    raw = entropy_parameters_raw(sd, torch.cat([phi, psi], dim=1), dtype)
+    params = split_parameters(raw, M, K)
+    p_z = factorized_likelihood(sd, z_in, dtype)
+    p_y = conditional_likelihood(y_in, params, K)
+    out = {"x_hat": synthesis_3x3(sd, y_in, dtype), "y": y, "y_in": y_in, "z": z, "z_in": z_in, "p_z": p_z, "logp_z": torch.log(p_z),
+           "p_y": p_y, "logp_y": torch.log(p_y), "training": training}
+    if K == 1:
+        out["mu"], out["sigma"] = params
+    else:
+        out["weights"], out["mus"], out["sigmas"] = params
+    return out
 
 
 def forward_scalable(sd, x, M: int, M1: int, K: int, training: bool = False,

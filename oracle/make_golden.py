@@ -8,7 +8,7 @@ reference classes are imported unmodified with two stand-ins placed in
   * ``compressai.layers.gdn.GDN``: oracle/gdn.py (third-party arithmetic that
     is absent from /root/reference and from this image - parity unpinned there).
 
-Usage:  python -m oracle.make_golden [scalable | train]  (from the repo root)
+Usage:  python -m oracle.make_golden [scalable | train | residual]  (from the repo root)
 """
 from __future__ import annotations
 
@@ -197,6 +197,66 @@ def main():
               f"({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+RESIDUAL_CASES = {
+    # name: (M, K, input shape) - HierarchicalMixtureResidual (Models.py:109-205), the 3x3 residual family
+    "c6_res3x3_k3_128_calib": (128, 3, (1, 3, 128, 192)),
+    "c6_res3x3_k1_128_calib": (128, 1, (2, 3, 64, 128)),
+}
+
+
+def residual_init(sd, gy, gz, sigma_bias=3.0):
+    """The 'calib' recipe for the residual model: gains on the bottleneck conv of g_a (net.6) and the last conv of h_a (net.8),
+    + sigma_bias on the sigma biases of the entropy-parameter head."""
+    for k in ("encoder.net.6.weight", "encoder.net.6.bias"):
+        sd[k] = sd[k] * gy
+    for k in ("hyper_encoder.net.8.weight", "hyper_encoder.net.8.bias"):
+        sd[k] = sd[k] * gz
+    b = sd["entropy_parameters.net.4.bias"].clone()
+    n = b.numel()
+    b[(n // 2 if n % 3 else 2 * n // 3):] += sigma_bias
+    sd["entropy_parameters.net.4.bias"] = b
+    return sd
+
+
+def main_residual():
+    """The reference's own HierarchicalMixtureResidual (unmodified classes) on seeded weights.  The gains are chosen per case so that
+    std(y) = 2 and std(z) = 3 on the case's input (non-trivial symbols, well-conditioned likelihoods) and stored in the file."""
+    Models, RDL = import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    from oracle import forward as O
+    for name, (M, K, shape) in RESIDUAL_CASES.items():
+        torch.manual_seed(0)
+        model = Models.HierarchicalMixtureResidual(M, K=K)
+        sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+        torch.manual_seed(1)
+        x = torch.rand(*shape)
+        with torch.no_grad():
+            o = model(x, training=False)
+            gy = float(np.float32(2.0 / float(o["y"].std())))
+            sd1 = residual_init({k: v.clone() for k, v in sd0.items()}, gy, 1.0, 0.0)
+            model.load_state_dict(sd1)
+            gz = float(np.float32(3.0 / float(model(x, training=False)["z"].std())))
+        sd = residual_init({k: v.clone() for k, v in sd0.items()}, gy, gz)
+        model.load_state_dict(sd)
+        digest = state_digest(sd)
+        with torch.no_grad():
+            out = model(x, training=False)
+            rd = RDL.rd_loss(out, x, 0.005)
+            rd64 = O.rd_loss(O.forward_residual(sd, x, M, K, dtype=torch.float64), x, 0.005)
+        blob = {"x": x.numpy(), "state_digest": np.array(digest), "M": np.array(M), "K": np.array(K), "gain_y": np.array(gy, np.float32),
+                "gain_z": np.array(gz, np.float32), "fp64_bpp_total": np.array(rd64["bpp_total"]), "fp64_psnr": np.array(rd64["psnr"])}
+        for k, v in out.items():
+            if torch.is_tensor(v):
+                blob["out_" + k] = v.numpy()
+        for k, v in rd.items():
+            blob["rd_" + k] = v.detach().numpy() if torch.is_tensor(v) else np.array(v, dtype=np.float64)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **blob)
+        print(f"{name}: gains {gy:.4f} / {gz:.4f}, bpp_y {rd['bpp_y']:.6f} bpp_z {rd['bpp_z']:.6f} (fp64 total {rd64['bpp_total']:.6f}) psnr {rd['psnr']:.6f} "
+              f"nonzero y_in {int((out['y_in'] != 0).sum())}/{out['y_in'].numel()} min p_y {float(out['p_y'].min()):.2e} -> {path} "
+              f"({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 TRAIN_CASES = {
     # name: (M, K, input shape, init, noise seed) - BASELINE.json configs[3] (training step) at parity-test size
     "c4_train_k3_128_calib": (128, 3, (2, 3, 128, 128), "calib", 11),
@@ -259,6 +319,8 @@ def main_train():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "train":
         main_train()               # only the c4_train_* files
+    elif len(sys.argv) > 1 and sys.argv[1] == "residual":
+        main_residual()            # only the c6_* files
     elif len(sys.argv) > 1 and sys.argv[1] == "scalable":
         main_scalable()            # only the c5_* files; the other vectors stay byte-identical
     else:

@@ -58,6 +58,28 @@ def seeded_scalable_model(M, M1, K, init="calib", precision="fp32"):
     return model
 
 
+def residual_cases():
+    """HierarchicalMixtureResidual cases (the 3x3 residual family; oracle/make_golden.py residual)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "c6_*.npz")))
+
+
+def seeded_residual_model(M, K, gain_y, gain_z, precision="fp32", sigma_bias=3.0):
+    from neural_image_compression_b200.Models import HierarchicalMixtureResidual
+    torch.manual_seed(0)
+    model = HierarchicalMixtureResidual(M, K=K, precision=precision)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    for k in ("encoder.net.6.weight", "encoder.net.6.bias"):
+        sd[k] = sd[k] * gain_y
+    for k in ("hyper_encoder.net.8.weight", "hyper_encoder.net.8.bias"):
+        sd[k] = sd[k] * gain_z
+    b = sd["entropy_parameters.net.4.bias"].clone()
+    n = b.numel()
+    b[(n // 2 if n % 3 else 2 * n // 3):] += sigma_bias
+    sd["entropy_parameters.net.4.bias"] = b
+    model.load_state_dict(sd)
+    return model
+
+
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 

@@ -1,0 +1,143 @@
+"""GPU: the 3x3 residual family (/root/reference/Layers.py, Components.py:20-122,
+Models.py:109-205) through the module API -> C ABI: every new layer shape against a float64 CPU convolution, every block
+against the oracle, and HierarchicalMixtureResidual against vectors produced by the reference's own class."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import forward as O
+from tests import helpers as H
+from tests.test_gpu_model import check_against
+
+pytestmark = pytest.mark.gpu
+ARMS = ("fp32", "bf16x3")
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+
+@pytest.mark.parametrize("arm", ARMS)
+@pytest.mark.parametrize("kind,hw", [("c3s2", (16, 24)), ("c3s2", (10, 14)), ("c1s2", (16, 24)), ("t3s2", (8, 12)), ("t3s2", (5, 7)),
+                                     ("t3s2_rgb", (8, 12)), ("c3s1_288", (8, 12)), ("t3s2_288", (4, 6))])
+def test_new_layer_shapes(kind, hw, arm):
+    """Conv2d 3x3 stride 2 / 1x1 stride 2, ConvTranspose2d 3x3 stride 2 (pad 1, output_padding 1), incl. the 3-channel output
+    and the 288-channel h_s layers of M = 192 (not a multiple of 64: CUDA-core kernels in both arms)."""
+    from neural_image_compression_b200 import Layers as L
+    from neural_image_compression_b200._lib import EPI_BIAS
+    torch.manual_seed(60)
+    conv = {"c3s2": lambda: nn.Conv2d(128, 128, 3, 2, 1), "c1s2": lambda: nn.Conv2d(128, 128, 1, 2),
+            "t3s2": lambda: nn.ConvTranspose2d(128, 128, 3, 2, 1, output_padding=1),
+            "t3s2_rgb": lambda: nn.ConvTranspose2d(128, 3, 3, 2, 1, output_padding=1),
+            "c3s1_288": lambda: nn.Conv2d(192, 288, 3, 1, 1), "t3s2_288": lambda: nn.ConvTranspose2d(288, 288, 3, 2, 1, output_padding=1)}[kind]()
+    x = torch.randn(2, conv.in_channels, *hw)
+    if isinstance(conv, nn.ConvTranspose2d):
+        ref = F.conv_transpose2d(x.double(), conv.weight.double(), conv.bias.double(), stride=2, padding=1, output_padding=1)
+    else:
+        ref = F.conv2d(x.double(), conv.weight.double(), conv.bias.double(), stride=conv.stride, padding=conv.padding)
+    xn = x.permute(0, 2, 3, 1).contiguous().cuda()
+    y, ho, wo = L._conv(arm, conv.cuda(), EPI_BIAS, xn, 2, hw[0], hw[1])
+    torch.cuda.synchronize()
+    got = y.cpu().permute(0, 3, 1, 2)
+    assert got.shape == ref.shape and _rel(got, ref) < (2e-5 if arm == "fp32" else 1e-4), (kind, _rel(got, ref))
+
+
+@pytest.mark.parametrize("arm", ARMS)
+def test_blocks_match_oracle(arm):
+    from neural_image_compression_b200 import Layers as L
+    torch.manual_seed(61)
+    for blk, fn, shape in ((L.ResidualBlock(128, 128), O._res_block, (2, 128, 8, 12)),
+                           (L.ResidualBlockWithStride(128, 128, 2), O._res_stride, (2, 128, 16, 24)),
+                           (L.ResidualBlockWithStride(3, 128, 2), O._res_stride, (2, 3, 32, 32)),
+                           (L.ResidualBlockUpsample(128, 128, 2), O._res_up, (2, 128, 8, 12))):
+        blk.precision = arm
+        with torch.no_grad():
+            for g in ("gdn", "igdn"):
+                if hasattr(blk, g):
+                    getattr(blk, g).gamma.add_(0.02 * torch.rand_like(getattr(blk, g).gamma))
+        x = torch.randn(*shape) if shape[1] > 3 else torch.rand(*shape)
+        sd = {"b." + k: v.detach().clone().double() for k, v in blk.state_dict().items()}
+        with torch.no_grad():
+            ref = fn(sd, "b", x.double(), torch.float64)
+        got = blk.cuda()(x.cuda()).cpu()
+        assert got.shape == ref.shape and _rel(got, ref) < (3e-5 if arm == "fp32" else 1.5e-4), (type(blk).__name__, _rel(got, ref))
+
+
+def test_subpel_conv_matches_torch():
+    """SubpelConv3x3 (Layers.py:6-16) is public in the reference although its models build TransposedDeconv3x3 instead."""
+    from neural_image_compression_b200 import Layers as L
+    torch.manual_seed(62)
+    m = L.SubpelConv3x3(128, 64, 2)
+    x = torch.randn(2, 128, 8, 12)
+    with torch.no_grad():
+        ref = F.pixel_shuffle(F.conv2d(x.double(), m.conv.weight.double(), m.conv.bias.double(), padding=1), 2)
+    m.precision = "fp32"
+    got = m.cuda()(x.cuda()).cpu()
+    assert got.shape == ref.shape and _rel(got, ref) < 2e-5
+
+
+@pytest.mark.parametrize("precision", ARMS)
+@pytest.mark.parametrize("case", H.residual_cases())
+def test_residual_model_matches_reference_vectors(case, precision):
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    g = H.load_golden(case)
+    M, K = int(g["M"]), int(g["K"])
+    model = H.seeded_residual_model(M, K, float(g["gain_y"]), float(g["gain_z"]), precision=precision)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    x = torch.from_numpy(g["x"]).cuda()
+    out = model(x, training=False)
+    rd = rd_loss(out, x, 0.005)
+    ref = {k[4:]: g[k] for k in g.files if k.startswith("out_")}
+    ref_rd = {k[3:]: float(g[k]) for k in g.files if k.startswith("rd_") and g[k].ndim == 0}
+    o = {k: out[k].cpu().numpy() for k in ("y", "y_in", "z", "z_in", "p_y", "p_z", "x_hat")}
+    rep = {"precision": precision}
+    # symbols: bit exact away from rounding ties; the tie flips are bounded by what the measured error on y / z explains.  This
+    # family is 16 convs + 3 GDN deep before the rounding (the 5x5 model: 4 + 3), so the pre-rounding bound is 3e-4 here.
+    for name, pre in (("y_in", "y"), ("z_in", "z")):
+        real, ties = H.symbol_mismatches(o[name], ref[name], ref[pre], H.TIE_TAU)
+        rel = float(np.abs(o[pre] - ref[pre]).max() / np.abs(ref[pre]).max())
+        rep[name + "_flips_real_ties"], rep[pre + "_rel_err"] = [real, ties], rel
+        assert real == 0 and ties <= H.tie_flip_bound(o[pre], ref[pre]) and rel <= 3e-4, (name, real, ties, rel)
+    ok_y, ok_z, ok_x = H.flip_masks(o["y_in"], ref["y_in"], o["z_in"], ref["z_in"], ref["x_hat"].shape)
+    for name, ok in (("p_y", ok_y), ("p_z", ok_z)):
+        bad, worst, n, frac = H.masked_likelihood_close(o[name], ref[name], ok)
+        rep[name] = {"outliers": bad, "max_abs_err": worst, "compared": n, "fraction": frac}
+        assert bad <= 1e-5 * n + 1, (name, bad, n, worst)
+    okx = np.broadcast_to(ok_x, ref["x_hat"].shape)
+    if okx.any():
+        xe = float(np.abs(o["x_hat"] - ref["x_hat"])[okx].max() / np.abs(ref["x_hat"]).max())
+        rep["x_hat"] = {"rel_err": xe, "fraction": float(okx.mean())}
+        assert xe < 5e-4, xe
+    if not (ok_y.all() and ok_z.all()):                       # flips: everything else against the oracle on this run's symbols
+        with torch.no_grad():
+            yi, zi = torch.from_numpy(o["y_in"]), torch.from_numpy(o["z_in"])
+            raw = O.entropy_parameters_raw(sd, torch.cat([O.context(sd, yi), O.hyper_synthesis_3x3(sd, zi)], dim=1))
+            p_y = O.conditional_likelihood(yi, O.split_parameters(raw, M, K), K).numpy()
+            x_hat = O.synthesis_3x3(sd, yi).numpy()
+        bad, worst = H.likelihood_close(o["p_y"], p_y)
+        rep["p_y_given_symbols"] = {"outliers": bad, "max_abs_err": worst}
+        assert bad <= 1e-5 * p_y.size + 1, (bad, worst)
+        xe2 = float(np.abs(o["x_hat"] - x_hat).max() / np.abs(x_hat).max())
+        rep["x_hat_given_symbols_rel_err"] = xe2
+        assert xe2 < 5e-4, xe2
+    assert abs(rd["bpp_total"] - ref_rd["bpp_total"]) <= H.BPP_TOL and abs(rd["psnr"] - ref_rd["psnr"]) <= H.PSNR_TOL, (rd, ref_rd)
+    H.record_report(f"residual/{case}/{precision}", rep)
+    assert set(out) == set(ref) | {"training"}
+
+
+def test_residual_model_rejects_autograd_training_call_and_bad_arguments():
+    from neural_image_compression_b200.Models import HierarchicalMixtureResidual
+    with pytest.raises(ValueError):
+        HierarchicalMixtureResidual(0)
+    with pytest.raises(ValueError):
+        HierarchicalMixtureResidual(128, K=0)
+    m = HierarchicalMixtureResidual(128, K=1).cuda()
+    x = torch.rand(1, 3, 64, 64).cuda()
+    with pytest.raises(NotImplementedError):
+        m(x)                                                  # training=True with autograd on: the backward is not built
+    with torch.no_grad():
+        out = m(x, training=True)
+    assert out["training"] is True and float((out["y_in"] - out["y"]).abs().max()) <= 0.5

@@ -158,3 +158,24 @@ def test_restated_adam_matches_torch_optim_over_several_steps():
         cur, state = OB.adam_step(cur, grads, state)
         for k in p0:
             np.testing.assert_allclose(cur[k].numpy(), params[k].detach().numpy(), rtol=1e-6, atol=1e-9, err_msg=f"{k} step {t + 1}")
+
+
+@pytest.mark.parametrize("case", H.residual_cases())
+def test_residual_family_oracle_matches_reference_vectors(case):
+    """oracle.forward_residual (Layers.py / Components.py:20-122 / Models.py:150-205 restated) against vectors produced by the
+    reference's own HierarchicalMixtureResidual, and the product class draws the same seeded weights (state_dict digest)."""
+    g = H.load_golden(case)
+    M, K = int(g["M"]), int(g["K"])
+    model = H.seeded_residual_model(M, K, float(g["gain_y"]), float(g["gain_z"]))
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    assert H.state_digest(sd) == str(g["state_digest"])
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        out = O.forward_residual(sd, x, M, K)
+        rd = O.rd_loss(out, x, 0.005)
+    for k in g.files:
+        if k.startswith("out_"):
+            ref, got = g[k], out[k[4:]].numpy()
+            assert got.shape == ref.shape, k
+            np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-6, err_msg=k)
+    assert abs(rd["bpp_total"] - float(g["rd_bpp_total"])) < 1e-6 and abs(rd["psnr"] - float(g["rd_psnr"])) < 1e-5
