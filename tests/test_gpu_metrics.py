@@ -5,6 +5,7 @@ import pytest
 import torch
 
 from oracle import metrics as OM
+from oracle import metrics_np as ON
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -29,6 +30,8 @@ def test_compute_metrics_matches_the_oracle(shape):
     np.testing.assert_allclose(per.numpy(), OM.ms_ssim(raw.clamp(0, 1), orig, size_average=False).numpy(), atol=2e-5)
     np.testing.assert_allclose(ev.rgb_to_luma(orig.cuda()).cpu().numpy(), OM.rgb_to_luma(orig).numpy(), atol=1e-6)
     assert abs(float(ms_ssim(orig.cuda(), orig.cuda())) - 1.0) < 1e-6
+    # ... and against the second, independent (float64 numpy / scipy) statement of the algorithm
+    assert abs(got["MS-SSIM(RGB)"] - ON.ms_ssim(raw.clamp(0, 1).numpy(), orig.numpy())) <= 2e-5
 
 
 def test_ms_ssim_rejects_small_images_like_the_reference_package():

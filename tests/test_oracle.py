@@ -143,6 +143,24 @@ def test_metrics_oracle_basic_properties():
     assert abs(float(g.sum()) - 1.0) < 1e-6 and g.argmax() == 5 and g.numel() == 11
 
 
+@pytest.mark.parametrize("shape", [(1, 3, 176, 200), (2, 1, 161, 163), (1, 2, 203, 181)])
+def test_two_independent_ms_ssim_restatements_agree(shape):
+    """pytorch_msssim cannot be obtained here (parity unpinned at that boundary): the published algorithm is therefore stated twice
+    by different routes - oracle/metrics.py (torch, separable depth-wise convs, avg_pool2d) and oracle/metrics_np.py (float64
+    numpy / scipy: dense 11 x 11 window, correlate2d, explicit zero-padded block means) - and the two must agree to rounding at
+    even, odd and mixed sizes; the GPU kernel is checked against both (tests/test_gpu_metrics.py)."""
+    from oracle import metrics as OM, metrics_np as ON
+    torch.manual_seed(sum(shape))
+    x = torch.rand(*shape)
+    y = (x + 0.07 * torch.randn(*shape)).clamp(0, 1)
+    a64, b = float(OM.ms_ssim(x.double(), y.double())), ON.ms_ssim(x.numpy(), y.numpy())
+    assert abs(a64 - b) < 1e-12, (a64, b)
+    assert abs(float(OM.ms_ssim(x, y)) - b) < 5e-6            # the float32 run of the torch statement
+    assert abs(ON.ms_ssim(x.numpy(), x.numpy()) - 1.0) < 1e-12
+    with pytest.raises(ValueError):
+        ON.ms_ssim_plane(np.zeros((160, 200)), np.zeros((160, 200)))
+
+
 def test_restated_adam_matches_torch_optim_over_several_steps():
     """oracle/backward.py: adam_step against torch.optim.Adam(lr=1e-4) (Main.ipynb:133) for t = 1..6 (bias corrections included)."""
     torch.manual_seed(3)
