@@ -563,6 +563,54 @@ __device__ __forceinline__ bool epilogue_tile_swapped(const TcParams& p, const f
   uint8_t* col = sq + (c >> 6) * (128 * 128) + (c & 7) * 2;      // panel of this channel + its byte inside a 16-byte chunk
   const uint32_t cchunk = static_cast<uint32_t>((c & 63) >> 3);
   const int npass = p.split_out ? 2 : 1;
+  if (p.split_out && p.stage2) {
+    // bf16-pair output through TWO staging tiles (hi tile, lo tile): every accumulator column is read ONCE, hi and lo are formed
+    // together in registers BEFORE the wait for the previous block's stores (so that wait overlaps the TMEM loads and the
+    // arithmetic), and one round of four TMA stores per block replaces two rounds of two - half the barriers, half the TMEM traffic
+    for (int h = 0; h < nblk; ++h) {
+      const int oy0 = ty * p.tile_h + p.blk_roff[h], ox0 = tx * p.tile_w + p.blk_coff[h];
+      const int wc = ox0 * p.out_stride + px, hc = oy0 * p.out_stride + py;
+      uint32_t whi[32], wlo[32];                                     // 64 pixel columns of this lane's channel, packed in pairs
+#pragma unroll
+      for (int g2 = 0; g2 < 2; ++g2) {
+        float v[32];
+        tmem_ld_32x32(lane_addr + h * 128 + hs * 64 + g2 * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float a = v[j] + bias, b = v[j + 1] + bias;
+          if (p.epilogue == NIC_EPI_LRELU) { a = a > 0.f ? a : 0.01f * a; b = b > 0.f ? b : 0.01f * b; }
+          const uint32_t w = pack_bf16x2(a, b);
+          whi[g2 * 16 + (j >> 1)] = w;
+          wlo[g2 * 16 + (j >> 1)] = pack_bf16x2(a - __uint_as_float(w << 16), b - __uint_as_float(w & 0xffff0000u));
+        }
+      }
+      if (leader) tma_store_wait_read();                             // the previous block's stores have read both tiles
+      epi_sync();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int ra = hs * 64 + 2 * i, rb = ra + 1;                 // pixel rows of the pair inside the block
+        uint8_t* pa = col + ra * 128 + ((cchunk ^ (ra & 7)) << 4);
+        uint8_t* pb = col + rb * 128 + ((cchunk ^ (rb & 7)) << 4);
+        *reinterpret_cast<uint16_t*>(pa) = static_cast<uint16_t>(whi[i] & 0xffffu);
+        *reinterpret_cast<uint16_t*>(pb) = static_cast<uint16_t>(whi[i] >> 16);
+        *reinterpret_cast<uint16_t*>(pa + 2 * 128 * 128) = static_cast<uint16_t>(wlo[i] & 0xffffu);
+        *reinterpret_cast<uint16_t*>(pb + 2 * 128 * 128) = static_cast<uint16_t>(wlo[i] >> 16);
+      }
+      fence_proxy_async_smem();
+      epi_sync();
+      if (leader && !(p.dbg & 2)) {
+        const int off = p.out_c_offset + cbase;
+        for (int k = 0; k < 2; ++k)
+          if (k * 64 < nvalid_c) {
+            tma_store_4d(map_o_ptr, sq + k * (128 * 128), off + k * 64, wc, hc, img);
+            tma_store_4d(map_o_ptr, sq + (2 + k) * (128 * 128), off + p.split_lo_off + k * 64, wc, hc, img);
+          }
+        tma_store_commit();
+      }
+    }
+    return true;
+  }
   for (int h = 0; h < nblk; ++h) {
     const int oy0 = ty * p.tile_h + p.blk_roff[h], ox0 = tx * p.tile_w + p.blk_coff[h];
     const int wc = ox0 * p.out_stride + px, hc = oy0 * p.out_stride + py;
@@ -1539,7 +1587,17 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   // cp.async.bulk.wait_group.read right after its store costs 3-5k clk behind the TMA loads in flight - as long as such a
   // layer's whole mainloop)
   const int tapchunks = (tt.ntaps / tt.nphases) * p.nchunks;
-  p.stage2 = (p.split_out && p.tma_out == 1 && !gdn && !p.swap && tapchunks <= 96 && getenv("NIC_TC_STAGE2")) ? 1 : 0;   // measured: no gain (the smaller rings cost as much: ep2 96.5 -> 109.8 us), so opt-in only
+  // normal orientation: measured, no gain (the smaller rings cost as much: ep2 96.5 -> 109.8 us) - opt-in only (NIC_TC_STAGE2=1).
+  // Swapped orientation: the transposing epilogue then reads every accumulator column once and stores once per block
+  // (epilogue_tile_swapped).  Measured (bf16x3, 16 images): it pays on the small multi-tap layers (h_s layers 1, 2: 30.1 -> 26.4,
+  // 56.3 -> 52.6 us; h_a layer 1: 34.0 -> 29.3; h_s layer 3: 74.3 -> 70.9) and not on the 1x1 stack (88.7 -> 95.6 us) or the big
+  // transposed convs (g_s layer 3: 1069 -> 1081 us incl. its IGDN: the two ring slots it costs weigh as much) - so: swapped,
+  // 2 .. 96 tap-chunks per tile, and only if two A slots and four ring slots still fit.  NIC_TC_STAGE2=0 / 1 forces it off / on.
+  const char* st2 = getenv("NIC_TC_STAGE2");
+  const bool st2_fits = 2 * p.slot_bytes + 4 * 128 * 128 + 4 * 128 * 128 + 1024 <= kMaxDynSmem;
+  const bool st2_auto = p.swap && tapchunks <= 96 && tt.ntaps > tt.nphases;
+  p.stage2 = (p.split_out && p.tma_out == 1 && !gdn && st2_fits &&
+              (st2 ? (atoi(st2) != 0 && (p.swap || tapchunks <= 96)) : st2_auto)) ? 1 : 0;
   const int stage_bytes = p.tma_out == 2 ? 4 * 128 * 128 : ((gdn || p.tma_out) ? (p.stage2 ? 4 : 2) * 128 * 128 : 0);
   const int gdn_bytes = (gdn ? 2 * 128 * 128 : 0) + stage_bytes;
   const int bres_bytes = tt.ntaps * p.nchunks * p.nb * 128;

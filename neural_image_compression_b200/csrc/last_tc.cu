@@ -34,7 +34,11 @@ constexpr int kBH = 8, kBW = 16;                    // block of input pixels = t
 constexpr int kIH = kBH - 2, kIW = kBW - 2;         // interior: 6 x 14 pixels whose outputs the tile writes
 constexpr int kN = 80;                              // MMA N: 75 live columns, padded to a multiple of 16
 constexpr int kTStride = 81;                        // words per T row: odd, so scalar accesses of consecutive rows are conflict free
-constexpr int kMaxSlots = 3;
+#ifndef NIC_LAST_SLOTS
+#define NIC_LAST_SLOTS 3
+#define NIC_LAST_GROUPS 2
+#endif
+constexpr int kMaxSlots = 4;
 constexpr int kPanelA = 128 * 128;                  // [128 pixels][64 bf16] K-major, 128-byte swizzle
 constexpr int kPanelW = kN * 128;                   // [80 columns][64 bf16]
 constexpr int kTBytes = 128 * kTStride * 4;
@@ -78,6 +82,7 @@ __device__ __forceinline__ bool wait_abort(uint64_t* bar, uint32_t parity, volat
   return false;
 }
 
+template <int KC>                      // 64-channel panels per half of the pair input (c_in / 64): compile-time, so that the issue loops unroll
 __global__ void __launch_bounds__(kThreads, 1)
 last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ LastParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -100,7 +105,7 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const uint32_t tmem = sb.tmem_base;
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
   const int per_img = p.tiles_x * p.tiles_y;
-  const int kc = p.kc, nslots = p.nslots;
+  constexpr int kc = KC, nslots = KC == 2 ? NIC_LAST_SLOTS : 2, ngroups = KC == 2 ? NIC_LAST_GROUPS : 1;
 
   if (warp == 0) {
     // ===================== producer =====================
@@ -120,6 +125,7 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           if (!wait_abort(&sb.a_empty[s], ((it / nslots) & 1) ^ 1, &sb.abort_flag, p.status)) { ok = false; break; }
           mbar_expect_tx(&sb.a_full[s], kc * kPanelA);
           uint8_t* dst = smem + p.off_a + s * (kc * kPanelA);
+#pragma unroll
           for (int j = 0; j < kc; ++j) tma_load_4d(dst + j * kPanelA, &map_a, &sb.a_full[s], (half * kc + j) * 64, c0, r0, img);
         }
       }
@@ -143,9 +149,11 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         tcgen05_fence_after();
         uint32_t a = a0 + s * (kc * PA);
         uint32_t acc_on = 0;
+#pragma unroll
         for (int j = 0; j < kc; ++j)
 #pragma unroll
           for (int k = 0; k < 4; ++k) { umma_bf16_lohi(d, a + j * PA + k * 2, hi, w0 + j * PW + k * 2, hi, idesc, acc_on); acc_on = 1; }
+#pragma unroll
         for (int j = 0; j < kc; ++j)
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, a + j * PA + k * 2, hi, w0 + (kc + j) * PW + k * 2, hi, idesc, 1);
@@ -156,6 +164,7 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         if (!wait_abort(&sb.a_full[s], (it / nslots) & 1, &sb.abort_flag, p.status)) break;
         tcgen05_fence_after();
         a = a0 + s * (kc * PA);
+#pragma unroll
         for (int j = 0; j < kc; ++j)
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_lohi(d, a + j * PA + k * 2, hi, w0 + j * PW + k * 2, hi, idesc, 1);
@@ -175,8 +184,8 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     auto sync_group = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     uint32_t tcount = 0;
-    for (int tile = first_tile; tile < p.total_tiles && g < p.ngroups; tile += tile_step, ++tcount) {
-      if (p.ngroups == 2 && (tcount & 1) != static_cast<uint32_t>(g)) continue;
+    for (int tile = first_tile; tile < p.total_tiles && g < ngroups; tile += tile_step, ++tcount) {
+      if (ngroups == 2 && (tcount & 1) != static_cast<uint32_t>(g)) continue;
       const uint32_t ab = tcount & 1;                          // accumulator buffer of this tile
       const int img = tile / per_img, rem = tile - img * per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -293,19 +302,20 @@ int conv_last_scatter_x3(const nic_conv_desc* d, const void* x, const void* w_pa
   // 128 channels: three 32 KB half-tile slots and two epilogue groups; 192 channels (48 KB half-tiles, 60 KB of weights): two
   // slots and one group is what fits 227 KB
   p.kc = d->c_in / 64;
-  p.nslots = p.kc == 2 ? 3 : 2; p.ngroups = p.kc == 2 ? 2 : 1;
+  p.nslots = p.kc == 2 ? NIC_LAST_SLOTS : 2; p.ngroups = p.kc == 2 ? NIC_LAST_GROUPS : 1;
   p.off_w = 0; p.off_a = 2 * p.kc * kPanelW; p.off_t = p.off_a + p.nslots * p.kc * kPanelA;
   const int smem_bytes = p.off_t + p.ngroups * kTBytes + 1024;
   CUtensorMap map_a, map_w;
   if (int rc = encode_nhwc(&map_a, x, d->n, d->h_in, d->w_in, 2 * d->c_in, kBW, kBH, 1, 2)) return rc;
   if (int rc = encode_2d(&map_w, w_packed, d->c_in, 2 * kN, 64, kN)) return rc;
-  static int attr_bytes = 0;
-  if (attr_bytes < smem_bytes) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(last_scatter_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
-    attr_bytes = smem_bytes;
+  static bool attr_set[2] = {false, false};
+  auto kern = p.kc == 2 ? last_scatter_x3_kernel<2> : last_scatter_x3_kernel<3>;
+  if (!attr_set[p.kc - 2]) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
+    attr_set[p.kc - 2] = true;
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  last_scatter_x3_kernel<<<grid, kThreads, smem_bytes, st>>>(map_a, map_w, p);
+  kern<<<grid, kThreads, smem_bytes, st>>>(map_a, map_w, p);
   return check_launch("last_scatter_x3_kernel");
 }
 
