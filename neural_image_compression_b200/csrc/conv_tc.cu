@@ -657,20 +657,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __shared__ float s_beta[128];
   __shared__ int s_tap_brow[kMaxTaps];           // weight row of the tap's slab (TMA coordinate of the B producer)
   __shared__ uint32_t s_tap_aoff[kMaxTaps];      // descriptor offset (16-byte units) of the tap's first pixel inside the patch
+  pdl_launch_dependents();
   if (threadIdx.x < kMaxTaps) {
     s_tap_brow[threadIdx.x] = p.taps[threadIdx.x].slab;
     s_tap_aoff[threadIdx.x] = static_cast<uint32_t>((p.taps[threadIdx.x].roff * p.pw_cols + p.taps[threadIdx.x].coff) * 128) >> 4;
   }
-  for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = p.bias[p.bias_mod ? i % p.bias_mod : i];
-  if (p.beta) for (int i = threadIdx.x; i < 128; i += kThreads) s_beta[i] = p.beta[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool gdn = p.epilogue == NIC_EPI_GDN || p.epilogue == NIC_EPI_IGDN;
-  // K chunks this launch walks: all of [hi | lo | hi] x [W_hi | W_hi | W_lo], or - when the producer of the input flagged its lo
-  // half as all zero - without the middle third (every role derives the same list from the same device word)
-  int nchunks_eff = p.nchunks, skip_from = 1 << 30, skip_add = 0;
-  if (p.lo_flag && __ldg(p.lo_flag) == 0) { skip_add = p.a_chunk_mod / 2; skip_from = skip_add; nchunks_eff = p.nchunks - skip_add; }
-  auto kchunk = [&](int chunk) { return chunk + (chunk >= skip_from ? skip_add : 0); };
-
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sb.a_full[i], 1); mbar_init(&sb.a_empty[i], kMmaWarps); }
     for (int i = 0; i < kMaxBSlots; ++i) { mbar_init(&sb.b_full[i], 1); mbar_init(&sb.b_empty[i], kMmaWarps); }
@@ -681,6 +674,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   if (warp == 2) { tmem_alloc(&sb.tmem_base, 512); tmem_relinquish(); }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); if (gdn) tma_prefetch_desc(&map_g); if (p.tma_out) tma_prefetch_desc(&map_o); }
+  // everything above is independent of the preceding kernel; from here on global memory it may have written is read
+  pdl_wait();
+  for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = p.bias[p.bias_mod ? i % p.bias_mod : i];
+  if (p.beta) for (int i = threadIdx.x; i < 128; i += kThreads) s_beta[i] = p.beta[i];
+  // K chunks this launch walks: all of [hi | lo | hi] x [W_hi | W_hi | W_lo], or - when the producer of the input flagged its lo
+  // half as all zero - without the middle third (every role derives the same list from the same device word)
+  int nchunks_eff = p.nchunks, skip_from = 1 << 30, skip_add = 0;
+  if (p.lo_flag && __ldg(p.lo_flag) == 0) { skip_add = p.a_chunk_mod / 2; skip_from = skip_add; nchunks_eff = p.nchunks - skip_add; }
+  auto kchunk = [&](int chunk) { return chunk + (chunk >= skip_from ? skip_add : 0); };
+
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -1661,7 +1664,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     attr_set = true;
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  conv_tc_kernel<<<grid, kThreads, p.smem_bytes, st>>>(map_a, map_w, map_g, map_o, p);
+  if (int rc = check_cuda(launch_pdl(conv_tc_kernel, grid, kThreads, p.smem_bytes, st, map_a, map_w, map_g, map_o, p), "conv_tc_kernel launch")) return rc;
   return check_launch("conv_tc_kernel");
 }
 

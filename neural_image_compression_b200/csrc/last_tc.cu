@@ -90,7 +90,7 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   __shared__ LastBarriers sb;
   __shared__ float s_bias[4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < 3) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sb.a_full[i], 1); mbar_init(&sb.a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], 4); }
@@ -99,6 +99,8 @@ last_scatter_x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(&sb.tmem_base, 256); tmem_relinquish(); }
+  pdl_wait();                                       // g_s layer 3's IGDN kernel has written the activation
+  if (threadIdx.x < 3) s_bias[threadIdx.x] = p.bias[threadIdx.x];
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -315,7 +317,7 @@ int conv_last_scatter_x3(const nic_conv_desc* d, const void* x, const void* w_pa
     attr_set[p.kc - 2] = true;
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  kern<<<grid, kThreads, smem_bytes, st>>>(map_a, map_w, p);
+  if (int rc = check_cuda(launch_pdl(kern, grid, kThreads, smem_bytes, st, map_a, map_w, p), "last_scatter_x3_kernel launch")) return rc;
   return check_launch("last_scatter_x3_kernel");
 }
 

@@ -50,6 +50,14 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32
   return false;
 }
 
+// ---- programmatic dependent launch (the kernels of a forward pass run back to back in one stream / CUDA graph) --------------
+// launch_dependents: the next kernel of the stream may be scheduled as soon as every CTA of this grid has executed it (its CTAs
+// then start on SMs this grid has left and run their prologue - barrier init, TMEM allocation, descriptor prefetch);
+// wait: blocks until the preceding grid has completed and its memory is visible - nothing the predecessor wrote is read before it.
+// Both are no-ops in a kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- proxies / fences ---------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

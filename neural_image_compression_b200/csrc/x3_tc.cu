@@ -98,7 +98,7 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   __shared__ GdnBarriers sb;
   __shared__ __align__(16) float s_beta[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < 128) s_beta[threadIdx.x] = p.beta[threadIdx.x];
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&sb.x_full[i], 1); mbar_init(&sb.x_empty[i], 1); }
     mbar_init(&sb.gamma_full, 1); mbar_init(&sb.mma_done, 1);
@@ -106,6 +106,8 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == kGdnWorkers) { tmem_alloc(&sb.tmem_base, 128); tmem_relinquish(); }
+  pdl_wait();                                       // the conv that wrote x has completed
+  if (threadIdx.x < 128) s_beta[threadIdx.x] = p.beta[threadIdx.x];
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -281,7 +283,7 @@ gdn_x3c_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   __shared__ GdnCBarriers sb;
   __shared__ __align__(16) float s_beta[C];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < C) s_beta[threadIdx.x] = p.beta[threadIdx.x];
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&sb.x_full[i], 1); mbar_init(&sb.x_empty[i], 1); }
     for (int i = 0; i < kGRing; ++i) { mbar_init(&sb.g_full[i], 1); mbar_init(&sb.g_empty[i], 1); }
@@ -290,6 +292,8 @@ gdn_x3c_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == kWorkers) { tmem_alloc(&sb.tmem_base, 256); tmem_relinquish(); }
+  pdl_wait();
+  if (threadIdx.x < C) s_beta[threadIdx.x] = p.beta[threadIdx.x];
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -689,7 +693,7 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   __shared__ float s_bias[128];
   __shared__ __align__(16) float s_beta[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  if (tid < 128) { s_bias[tid] = f.bias[tid]; s_beta[tid] = f.beta[tid]; }
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&sb.patch_full[i], 1); mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], kFfWorkers); }
     mbar_init(&sb.a_full, kFfProducers * 32); mbar_init(&sb.a_empty, 1); mbar_init(&sb.w_full, 1); mbar_init(&sb.gamma_full, 1);
@@ -698,6 +702,8 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     fence_barrier_init();
   }
   if (warp == kFfProducers) { tmem_alloc(&sb.tmem_base, 512); tmem_relinquish(); }
+  pdl_wait();
+  if (tid < 128) { s_bias[tid] = f.bias[tid]; s_beta[tid] = f.beta[tid]; }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -966,8 +972,9 @@ static int launch_gdn_c(const void* x, int pair_in, long npix, int inverse, cons
     attr_set = true;
   }
   const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
-  if (pair_in) gdn_x3c_kernel<NP, true><<<grid, (4 * NP + 2) * 32, smem_bytes, st>>>(map_x, map_g, map_o, p);
-  else gdn_x3c_kernel<NP, false><<<grid, (4 * NP + 2) * 32, smem_bytes, st>>>(map_x, map_g, map_o, p);
+  if (int rc = check_cuda(pair_in ? launch_pdl(gdn_x3c_kernel<NP, true>, grid, (4 * NP + 2) * 32, smem_bytes, st, map_x, map_g, map_o, p)
+                                  : launch_pdl(gdn_x3c_kernel<NP, false>, grid, (4 * NP + 2) * 32, smem_bytes, st, map_x, map_g, map_o, p),
+                          "gdn_x3c_kernel launch")) return rc;
   return check_launch("gdn_x3c_kernel");
 }
 
@@ -996,8 +1003,9 @@ int gdn_fwd_tc_x3(const void* x, int pair_in, long npix, int c, int inverse, con
     attr_set = true;
   }
   const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
-  if (pair_in) gdn_x3_kernel<true><<<grid, kGdnThreads, smem_bytes, st>>>(map_x, map_g, map_o, p);
-  else gdn_x3_kernel<false><<<grid, kGdnThreads, smem_bytes, st>>>(map_x, map_g, map_o, p);
+  if (int rc = check_cuda(pair_in ? launch_pdl(gdn_x3_kernel<true>, grid, kGdnThreads, smem_bytes, st, map_x, map_g, map_o, p)
+                                  : launch_pdl(gdn_x3_kernel<false>, grid, kGdnThreads, smem_bytes, st, map_x, map_g, map_o, p),
+                          "gdn_x3_kernel launch")) return rc;
   return check_launch("gdn_x3_kernel");
 }
 
@@ -1061,7 +1069,7 @@ int conv_first_gdn_x3(const nic_conv_desc* d, const void* x, const void* w_packe
     attr_set = true;
   }
   const int grid = f.total_tiles < kNumSMs ? f.total_tiles : kNumSMs;
-  first_fused_x3_kernel<<<grid, kFfThreads, smem_bytes, st>>>(map_w, map_g, map_img, map_o, f);
+  if (int rc = check_cuda(launch_pdl(first_fused_x3_kernel, grid, kFfThreads, smem_bytes, st, map_w, map_g, map_img, map_o, f), "first_fused_x3_kernel launch")) return rc;
   return check_launch("first_fused_x3_kernel");
 }
 
