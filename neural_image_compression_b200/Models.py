@@ -18,6 +18,8 @@ the host):
 """
 from __future__ import annotations
 
+import contextlib
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -31,22 +33,22 @@ from .EntropyModels import FactorizedEntropyBottleneck, GaussianConditional, Gau
 from .ParametersModels import EntropyParameters
 
 
-def _pair_trunk(model, x, training, noise, prec_up, prec):
-    """g_a -> y hand-off -> h_a -> z hand-off of the fused pipeline (Models.py:52-66): activations NHWC between layers (bf16 hi/lo
-    pairs in the bf16x3 arm).  Returns (y, y_in, y_in_nhwc, z, z_in, z_in_nhwc)."""
+def _pair_noise(model, x, training, noise):
     B, _, H, W = x.shape
+    if not training:
+        return None, None
+    if noise is not None:
+        return noise
     M = model.M
+    return (torch.rand((B, M, H // 64, W // 64), device=x.device) - 0.5, torch.rand((B, M, H // 16, W // 16), device=x.device) - 0.5)
+
+
+def _pair_g_a(model, x, training, noise_y, prec_up, prec):
+    """g_a -> y hand-off of the fused pipeline (Models.py:52, 57-64): activations NHWC between layers (bf16 hi/lo pairs in the bf16x3
+    arm).  Returns (y, y_in, y_in_nhwc, y_src) with y_src = the unquantised y in the engine's layout for h_a (Models.py:53)."""
+    B, _, H, W = x.shape
     adt = engine.act_dtype(prec)
     pair = prec == "bf16x3"
-    hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
-    noise_z = noise_y = None
-    if training:
-        if noise is not None:
-            noise_z, noise_y = noise
-        else:
-            noise_z = torch.rand((B, M, hz, wz), device=x.device) - 0.5
-            noise_y = torch.rand((B, M, hy, wy), device=x.device) - 0.5
-    qmode = Q_NOISE if training else Q_ROUND
     a, h, w, layout = x, H, W, LAYOUT_NCHW
     enc = model.encoder.ops
     for i, op in enumerate(enc):
@@ -56,16 +58,21 @@ def _pair_trunk(model, x, training, noise, prec_up, prec):
         layout = LAYOUT_NHWC
     y_nhwc = a                                                     # f32 [B, hy, wy, M]
     lowp = prec_up != "fp32"
-    y, y_in, y_in_nhwc, y_lowp = engine.latent_handoff(y_nhwc, qmode, noise_y, "bf16x2" if pair else adt, want_lowp=lowp,
-                                                       lowp_pair=prec_up == "bf16x3")
-    # h_a reads the unquantised y (Models.py:53)
-    a, h, w = (y_lowp if lowp else y_nhwc), hy, wy
+    y, y_in, y_in_nhwc, y_lowp = engine.latent_handoff(y_nhwc, Q_NOISE if training else Q_ROUND, noise_y, "bf16x2" if pair else adt,
+                                                       want_lowp=lowp, lowp_pair=prec_up == "bf16x3")
+    return y, y_in, y_in_nhwc, (y_lowp if lowp else y_nhwc)
+
+
+def _pair_h_a(model, y_src, B, hy, wy, training, noise_z, prec_up, prec):
+    """h_a -> z hand-off (Models.py:53, 57-64).  Returns (z, z_in, z_in_nhwc)."""
+    adt = engine.act_dtype(prec)
+    a, h, w = y_src, hy, wy
     ha = model.hyper_encoder.ops
     for i, op in enumerate(ha):
         a = op.run(a, B, h, w, prec_up, out_dtype=torch.float32 if i == len(ha) - 1 else None)
         h, w = engine.conv_out_hw(op.conv, h, w)
-    z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, qmode, noise_z, "bf16x2" if pair else adt)
-    return y, y_in, y_in_nhwc, z, z_in, z_in_nhwc
+    z, z_in, z_in_nhwc, _ = engine.latent_handoff(a, Q_NOISE if training else Q_ROUND, noise_z, "bf16x2" if prec == "bf16x3" else adt)
+    return z, z_in, z_in_nhwc
 
 
 def _pair_h_s_into(model, z_in_nhwc, B, hz, wz, prec, combined, c_total, c_offset):
@@ -79,6 +86,22 @@ def _pair_h_s_into(model, z_in_nhwc, B, hz, wz, prec, combined, c_total, c_offse
         else:
             a = op.run(a, B, h, w, prec, in_lo_flag=z_flag if i == 0 else None)
         h, w = engine.conv_out_hw(op.conv, h, w)
+
+
+_SIDE_STREAMS = {}
+
+
+def _branch_stream(device, index: int = 0):
+    """A second stream for g_s while the forward pass is being CAPTURED in a CUDA graph: g_s (y_in -> x_hat) and the entropy side
+    (h_a, h_s, context, entropy parameters, likelihoods) only share y / y_in, so the graph gets two parallel branches and the small
+    launches of the entropy side (32-128 CTAs on 148 SMs) and the tails of the big ones overlap the other branch.  Eager launches
+    stay on one stream (they are host-bound; forking costs events).  NIC_EVAL_OVERLAP=0 switches it off."""
+    if os.environ.get("NIC_EVAL_OVERLAP", "1") == "0" or not torch.cuda.is_current_stream_capturing():
+        return None
+    key = (str(device), index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
 
 
 def _pair_g_s(model, y_in_nhwc, B, hy, wy, prec):
@@ -185,16 +208,31 @@ class JointAutoregressiveHierarchical(nn.Module):
         x = x.contiguous().float()
         hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
         with torch.cuda.device(x.device), torch.no_grad():
-            y, y_in, y_in_nhwc, z, z_in, z_in_nhwc = _pair_trunk(self, x, training, noise, prec_up, prec)
+            noise_z, noise_y = _pair_noise(self, x, training, noise)
+            y, y_in, y_in_nhwc, y_src = _pair_g_a(self, x, training, noise_y, prec_up, prec)
 
-            # ---- h_s -> psi = combined[..., 2M:4M];  context -> phi = combined[..., 0:2M] -------
+            # ---- two parallel branches while the pass is captured in a CUDA graph: g_s (needs y_in only) and the context conv
+            # (y_in only) run beside h_a -> h_s; the context conv joins before the 1x1 stack, g_s at the end
+            branch, main_stream = _branch_stream(x.device), torch.cuda.current_stream(x.device)
+            if branch is not None:
+                branch.wait_stream(main_stream)
+                with torch.cuda.stream(branch):
+                    x_hat = _pair_g_s(self, y_in_nhwc, B, hy, wy, prec)
+            # phi = combined[..., 0:2M] (context), psi = combined[..., 2M:4M] (h_s): torch.cat([phi, psi]) never happens.
             # (the quantised symbols split into bf16 pairs with an all-zero lo half - the hand-off kernel checks and flags it on the
             #  device: their first consumers - h_s layer 1, the context conv, g_s layer 1 - run 2 of the 3 MMA passes)
             combined = torch.empty((B, hy, wy, cw * 4 * M), dtype=adt, device=x.device)
-            _pair_h_s_into(self, z_in_nhwc, B, hz, wz, prec, combined, 4 * M, 2 * M)
             self.context_model.masked.apply_mask_()
-            self.context_model.masked._op.run(y_in_nhwc, B, hy, wy, prec, out=combined, out_c_total=4 * M, out_c_offset=0,
-                                              in_lo_flag=getattr(y_in_nhwc, "_nic_lo_flag", None))
+            branch2 = _branch_stream(x.device, 1)
+            if branch2 is not None:
+                branch2.wait_stream(main_stream)
+            with (torch.cuda.stream(branch2) if branch2 is not None else contextlib.nullcontext()):
+                self.context_model.masked._op.run(y_in_nhwc, B, hy, wy, prec, out=combined, out_c_total=4 * M, out_c_offset=0,
+                                                  in_lo_flag=getattr(y_in_nhwc, "_nic_lo_flag", None))
+            z, z_in, z_in_nhwc = _pair_h_a(self, y_src, B, hy, wy, training, noise_z, prec_up, prec)
+            _pair_h_s_into(self, z_in_nhwc, B, hz, wz, prec, combined, 4 * M, 2 * M)
+            if branch2 is not None:
+                main_stream.wait_stream(branch2)
 
             # ---- entropy parameters (1x1 stack) ---------------------------------------------------
             ep = self.entropy_parameters.ops
@@ -208,7 +246,10 @@ class JointAutoregressiveHierarchical(nn.Module):
             p_y, logp_y = ly["p"], ly["logp"]
 
             # ---- g_s -----------------------------------------------------------------------------------
-            x_hat = _pair_g_s(self, y_in_nhwc, B, hy, wy, prec)
+            if branch is not None:
+                main_stream.wait_stream(branch)                 # join
+            else:
+                x_hat = _pair_g_s(self, y_in_nhwc, B, hy, wy, prec)
 
         # per-image partial sums of logp ride along for rd_loss (RateDistortionLoss.py:13-14)
         logp_y._nic_partials = ly["partials"]
@@ -374,7 +415,14 @@ class ScalableImageCoding(nn.Module):
         x = x.contiguous().float()
         hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
         with torch.cuda.device(x.device), torch.no_grad():
-            y, y_in, y_in_nhwc, z, z_in, z_in_nhwc = _pair_trunk(self, x, training, noise, prec, prec)
+            noise_z, noise_y = _pair_noise(self, x, training, noise)
+            y, y_in, y_in_nhwc, y_src = _pair_g_a(self, x, training, noise_y, prec, prec)
+            branch, main_stream = _branch_stream(x.device), torch.cuda.current_stream(x.device)
+            if branch is not None:                                        # g_s as a parallel branch of a captured graph
+                branch.wait_stream(main_stream)
+                with torch.cuda.stream(branch):
+                    x_hat = _pair_g_s(self, y_in_nhwc, B, hy, wy, prec)
+            z, z_in, z_in_nhwc = _pair_h_a(self, y_src, B, hy, wy, training, noise_z, prec, prec)
             y_flag = getattr(y_in_nhwc, "_nic_lo_flag", None)
             c1, c2 = 2 * M1 + 2 * M, 2 * M2 + 2 * M                       # [phi_i (2 M_i) | psi (2 M)] channels of the two heads
             comb1 = torch.empty((B, hy, wy, 2 * c1), dtype=torch.bfloat16, device=x.device)      # pair tensors: [hi(c) | lo(c)]
@@ -395,7 +443,10 @@ class ScalableImageCoding(nn.Module):
                 raw = ep.ops[2].run(a, B, hy, wy, prec, out_layout=LAYOUT_NCHW, out_dtype=torch.float32)
                 heads.append(gm_likelihood(yi.contiguous(), raw, mi, K, Q_PASSTHRU, full=True, want_y_in=False))
             _, p_z, logp_z, parts_z = self.factorized_entropy_model.likelihood(z_in, Q_PASSTHRU)
-            x_hat = _pair_g_s(self, y_in_nhwc, B, hy, wy, prec)
+            if branch is not None:
+                main_stream.wait_stream(branch)
+            else:
+                x_hat = _pair_g_s(self, y_in_nhwc, B, hy, wy, prec)
         l1, l2 = heads
         l1["logp"]._nic_partials, l2["logp"]._nic_partials, logp_z._nic_partials = l1["partials"], l2["partials"], parts_z
         out = {
