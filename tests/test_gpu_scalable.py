@@ -173,3 +173,24 @@ def test_scalable_autograd_path_equals_step_gradients():
     assert abs(float(loss) - float(rd["loss"].detach())) <= 1e-6 * abs(float(loss))
     for k, p in model.named_parameters():
         assert torch.allclose(p.grad, ref[k], rtol=1e-6, atol=0), k
+
+
+def test_graphed_forward_matches_the_eager_call_and_follows_weight_changes():
+    """parallel.GraphedForward: the scalable model's forward replayed from a CUDA graph (with g_s as a parallel branch) returns
+    the eager call's tensors bit for bit, and re-captures after load_state_dict."""
+    from neural_image_compression_b200 import parallel
+    model = H.seeded_scalable_model(192, 128, 1, "calib", precision="bf16x3").cuda()
+    x = H.seeded_input((1, 3, 128, 192)).cuda()
+    eager = model(x, training=False)
+    gf = parallel.GraphedForward(model)
+    for _ in range(2):
+        out = gf(x)
+    torch.cuda.synchronize()
+    for k in ("x_hat", "y_in", "z_in", "p_y1", "p_y2", "p_z"):
+        assert torch.equal(out[k], eager[k]), k
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["entropy_parameters_1.net.4.bias"] = sd["entropy_parameters_1.net.4.bias"] + 0.25
+    model.load_state_dict(sd)
+    out2 = gf(x)
+    torch.cuda.synchronize()
+    assert torch.equal(out2["p_y1"], model(x, training=False)["p_y1"]) and not torch.equal(out2["p_y1"], eager["p_y1"])
