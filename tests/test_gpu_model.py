@@ -133,8 +133,11 @@ def test_model_matches_oracle_at_kodak_shape(init, precision):
     model = model.cuda()
     out = model(x.cuda(), training=False)
     rd = rd_loss(out, x.cuda(), 0.005)
+    # compared-fraction floor: 0.8 on calib (std(y) = 2: ~20 tie flips of 196 608 symbols, each masking its 13-pixel causal
+    # footprint); gain has std(y) = 8, i.e. 4x the |dy| and ~4x the flips (50-60: about half of the 1536 pixels masked) - 0.4
+    # there; part (b) of check_against covers 100 % of the elements in both cases
     print(init, precision, check_against(out, rd, ref, ref_rd, 3, precision=precision, x_hat_tol=X_HAT_TOL[precision], bpp_band=band,
-                                         sd=sd, M=128, name=f"kodak_shape/{init}/{precision}"))
+                                         sd=sd, M=128, name=f"kodak_shape/{init}/{precision}", min_frac=0.8 if init == "calib" else 0.4))
 
 
 @pytest.mark.parametrize("precision", PARITY_ARMS)
