@@ -11,6 +11,7 @@ from neural_image_compression_b200.gdn import GDN
 
 T = nn.ConvTranspose2d
 CFG = {
+    "k1": (nn.Conv2d(3, 128, 5, 2, 2), EPI_GDN, (512, 768), dict(in_layout=LAYOUT_NCHW, image=True)),
     "k2": (nn.Conv2d(128, 128, 5, 2, 2), EPI_GDN, (256, 384), {}),
     "k3": (nn.Conv2d(128, 128, 5, 2, 2), EPI_GDN, (128, 192), {}),
     "k4": (nn.Conv2d(128, 128, 5, 2, 2), EPI_BIAS, (64, 96), dict(out_dtype=torch.float32)),
@@ -40,11 +41,14 @@ for which in layers:
     conv, epi, (h, w), kw = CFG[which]
     kw = dict(kw)
     mask_a = kw.pop("mask_a", 0)
+    image = kw.pop("image", False)
     conv = conv.to(dev)
     g = GDN(128, inverse=(epi == EPI_IGDN)).to(dev) if epi in (EPI_GDN, EPI_IGDN) else None
     op = engine.ConvOp(conv, epi, gdn=g, mask_a=mask_a)
     x = torch.round(3 * torch.randn(B, h, w, conv.in_channels, device=dev)) if os.environ.get("LB_INT") else torch.randn(B, h, w, conv.in_channels, device=dev)
     x = engine.to_pair(x) if prec == "bf16x3" else x.to(torch.bfloat16)
+    if image:
+        x = torch.rand(B, 3, h, w, device=dev)
     s = torch.cuda.Stream()
     with torch.cuda.stream(s), torch.no_grad():
         for _ in range(3):
