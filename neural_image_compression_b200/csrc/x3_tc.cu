@@ -671,6 +671,8 @@ constexpr int kFfProducers = 2, kFfWorkers = 8;   // 4 producer warps push the k
 constexpr int kFfThreads = (kFfProducers + 1 + kFfWorkers) * 32;
 
 struct FirstFusedParams {
+  __nv_bfloat16* y;               // [n, hout, wout, 256] bf16 pairs (the lo half is written with direct stores)
+  long long* dbg_times;           // NIC trace hook (tools/trace_first.py): [cta][32 tiles][16] clock64 stamps, null = off
   const float* bias;
   const float* beta;
   int n, hin, win, hout, wout, tiles_x, tiles_y, total_tiles;
@@ -683,6 +685,10 @@ struct __align__(8) FirstFusedBarriers {
   uint32_t tmem_base;
   volatile int abort_flag;
 };
+
+__device__ __forceinline__ void ftrace(const FirstFusedParams& f, uint32_t it, int slot) {
+  if (f.dbg_times && it < 32) f.dbg_times[(static_cast<long>(blockIdx.x) * 32 + it) * 16 + slot] = clock64();
+}
 
 __global__ void __launch_bounds__(kFfThreads, 1)
 first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_img,
@@ -764,6 +770,7 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       }
       fence_proxy_async_smem();
       mbar_arrive(&sb.a_full);
+      if (tid == 0) ftrace(f, it, 14);
     }
   } else if (warp == kFfProducers) {
     // ===================== weight / gamma loader + MMA issuer =====================
@@ -805,7 +812,9 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       if (ok && tile < f.total_tiles) ok = conv_mmas(0);
       for (; tile < f.total_tiles && ok; tile += tile_step, ++it) {
         if (tile + tile_step < f.total_tiles) { if (!conv_mmas(it + 1)) break; }       // conv of the next tile first: it overlaps the workers
+        ftrace(f, it, 11);
         if (!wait_abort(&sb.sq1, it & 1, &sb.abort_flag, f.status)) break;
+        ftrace(f, it, 12);
         tcgen05_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k) { const uint32_t o = (k >> 2) * P + (k & 3) * 2; umma_bf16_lohi(d2, sq_lo + o, hi, gh + o, hi, idesc, k); }
@@ -813,6 +822,7 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         for (int k = 0; k < 8; ++k) { const uint32_t o = (k >> 2) * P + (k & 3) * 2; umma_bf16_lohi(d2, sq_lo + o, hi, gl + o, hi, idesc, 1); }
         umma_commit(&sb.g1);
         if (!wait_abort(&sb.sq2, it & 1, &sb.abort_flag, f.status)) break;
+        ftrace(f, it, 13);
         tcgen05_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k) { const uint32_t o = (k >> 2) * P + (k & 3) * 2; umma_bf16_lohi(d2, sq_lo + o, hi, gh + o, hi, idesc, 1); }
@@ -834,7 +844,9 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       int img, ty, tx;
       tile_coords(tile, img, ty, tx);
       const uint32_t g = it & 1;
+      if (leader) ftrace(f, it, 0);
       if (!__all_sync(0xffffffffu, wait_abort(&sb.acc_full[g], (it >> 1) & 1, &sb.abort_flag, f.status))) break;
+      if (leader) ftrace(f, it, 1);
       tcgen05_fence_after();
       float xr[64];
       tmem_ld_32x32(tmem + g * 128 + lane_off + hs * 64, xr);
@@ -845,8 +857,10 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       if (lane == 0) mbar_arrive(&sb.acc_empty[g]);                // x is in registers: the accumulator buffer is free again
 #pragma unroll
       for (int j = 0; j < 64; ++j) xr[j] += s_bias[hs * 64 + j];
+      if (leader) ftrace(f, it, 2);
       if (leader) tma_store_wait_read();                           // previous tile's lo store has left the staging tile
       sync_workers();
+      if (leader) ftrace(f, it, 3);
       // squares, hi part
       uint32_t lo_keep[32];
 #pragma unroll
@@ -859,7 +873,9 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb.sq1);
+      if (leader) ftrace(f, it, 4);
       if (!__all_sync(0xffffffffu, wait_abort(&sb.g1, it & 1, &sb.abort_flag, f.status))) break;
+      if (leader) ftrace(f, it, 5);
       // squares, lo part (the MMAs over the hi part have completed)
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -868,7 +884,9 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb.sq2);
+      if (leader) ftrace(f, it, 6);
       if (!__all_sync(0xffffffffu, wait_abort(&sb.g2, it & 1, &sb.abort_flag, f.status))) break;
+      if (leader) ftrace(f, it, 7);
       tcgen05_fence_after();
       float v0[32], v1[32];
       tmem_ld_32x32(tmem + 256 + lane_off + hs * 64, v0);
@@ -895,6 +913,7 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       }
       fence_proxy_async_smem();
       sync_workers();
+      if (leader) ftrace(f, it, 8);
       if (leader) {
         tma_store_4d(&map_o, sq, 0, tx * 8, ty * 16, img);
         tma_store_4d(&map_o, sq + kPanel, 64, tx * 8, ty * 16, img);
@@ -902,6 +921,9 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         tma_store_wait_read();
       }
       sync_workers();
+      if (leader) ftrace(f, it, 9);
+      // (the lo half through direct 16-byte global stores instead of a second staging round was tried in round 2: the eight
+      //  stores per thread take 1600 clk - L2-transaction bound - against 500 clk for staging + TMA; reverted)
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz) << 4)) =
@@ -912,6 +934,7 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         tma_store_4d(&map_o, sq, 128, tx * 8, ty * 16, img);
         tma_store_4d(&map_o, sq + kPanel, 192, tx * 8, ty * 16, img);
         tma_store_commit();
+        ftrace(f, it, 10);
       }
     }
     if (leader) tma_store_wait_all();
@@ -1051,7 +1074,8 @@ int conv_first_gdn_x3(const nic_conv_desc* d, const void* x, const void* w_packe
       (reinterpret_cast<uintptr_t>(x) & 15) || d->w_in % 4)
     return fail(NIC_E_BADALIGN, "conv bf16x3 (first layer): alignment");
   FirstFusedParams f{};
-  f.bias = bias; f.beta = beta_eff;
+  f.bias = bias; f.beta = beta_eff; f.y = static_cast<__nv_bfloat16*>(y);
+  f.dbg_times = reinterpret_cast<long long*>(g_trace_buffer);
   f.n = d->n; f.hin = d->h_in; f.win = d->w_in; f.hout = d->h_out; f.wout = d->w_out;
   f.tiles_x = (d->w_out + 7) / 8; f.tiles_y = (d->h_out + 15) / 16; f.total_tiles = f.tiles_x * f.tiles_y * d->n;
   f.off_w = 0; f.off_gamma = 3 * kPanel; f.off_a = 7 * kPanel; f.off_sq = 10 * kPanel; f.off_patch = 12 * kPanel;
