@@ -19,6 +19,9 @@ One "step" = model(x, training=False) + the rd terms on one batch.
             ALGORITHMIC FLOPs / its CUDA-event duration, against the measured bf16 peak of MEASURED_PEAKS.json; in the
             bf16x3 arm the kernel issues 3x the algorithmic MMA work (roofline.tensor_pipe_frac counts the issued FLOPs)
   cpu_baseline: the oracle (torch CPU port of the reference's path) on the box's host cores, bounded sample
+  residual_variant : (extra) the 3x3 residual family (HierarchicalMixtureResidual), batch 4 per GPU
+  strong_scaling   : (extra) the same 16-image batch split over the ranks (graph replay and collective timed apart)
+  config3_context_entropy : (extra) BASELINE.json configs[2] isolated: context conv + entropy-parameter stack (+ likelihood)
   scalable_variant : (extra) BASELINE.json configs[4] - ScalableImageCoding(192, 128) on one 2048 x 1536 image per GPU, bf16x3 arm
   train_step  : (extra, not the headline) BASELINE.json configs[3] - the reference's training step (Trainer.py:79-86: forward with
             noise, rd_loss, backward, Adam) on 8 x 3 x 256 x 256 crops PER GPU through ShardedTrainer (hand-written backward
@@ -190,6 +193,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-max-seconds", type=float, default=150.0, help="--impl reference: bound on the timed region (the step count is cut, and reported, if needed)")
+    ap.add_argument("--no-residual", action="store_true", help="skip the 3x3 residual-family line item (HierarchicalMixtureResidual, SURVEY.md 8 f4)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling line item (global batch 16 split over the ranks)")
     ap.add_argument("--no-config3", action="store_true", help="skip the isolated context + entropy-parameter (+ likelihood) line item (BASELINE.json configs[2])")
     ap.add_argument("--no-other-arms", action="store_true", help="skip the short runs of the other precision arms reported beside the headline")
@@ -548,6 +552,39 @@ def main():
         except Exception as e:               # noqa: BLE001
             scalable = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    # ---- the 3x3 residual family: HierarchicalMixtureResidual(128, K=3), same workload shape -------------
+    residual = None
+    if not args.no_residual:
+        try:
+            from neural_image_compression_b200.Models import HierarchicalMixtureResidual
+            torch.manual_seed(0)
+            rmodel = HierarchicalMixtureResidual(M, K=K, precision="bf16x3").to(dev)
+            rfwd = parallel.GraphedForward(rmodel, lean=True) if use_graph else (lambda t: rmodel(t, training=False, lean=True))
+            rb = 4
+            rx = [db[:rb].contiguous() for db in dev_batches[:2]]
+            with torch.no_grad():
+                for i in range(3):
+                    rd_loss(rfwd(rx[i % 2]), rx[i % 2], LAMBDA)
+                sync_all()
+                rs, re_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                nr = 10
+                rs.record()
+                for i in range(nr):
+                    rrd = rd_loss(rfwd(rx[i % 2]), rx[i % 2], LAMBDA)
+                re_.record()
+                sync_all()
+            rt_ms = torch.tensor([rs.elapsed_time(re_)], device=dev)
+            if world > 1:
+                dist.all_reduce(rt_ms, op=dist.ReduceOp.MAX)
+            residual = {"workload": "HierarchicalMixtureResidual(128, K=3) (3x3 residual transforms, Models.py:109-205) eval forward + rd_loss, synthetic "
+                                    "768x512, batch 4 per GPU, layer-by-layer on the conv engine (random-init weights)",
+                        "value": rb * world * nr / (float(rt_ms.item()) / 1e3), "unit": "images/s", "ms_per_step": float(rt_ms.item()) / nr,
+                        "precision": "bf16x3", "bpp_total": float(rrd["bpp_total"]), "scaling": "weak"}
+            del rmodel, rfwd, rx
+            torch.cuda.empty_cache()
+        except Exception as e:               # noqa: BLE001
+            residual = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     assert lib.nic_pipeline_status() == 0, "a tensor-core kernel aborted on an expired pipeline wait: numbers invalid"
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_reference_arm(B_PER_GPU, 6, warmup=1)
@@ -577,6 +614,8 @@ def main():
             line["train_step"] = train
         if scalable is not None:
             line["scalable_variant"] = scalable
+        if residual is not None:
+            line["residual_variant"] = residual
         if strong is not None:
             line["strong_scaling"] = strong
         if config3 is not None:

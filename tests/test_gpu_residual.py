@@ -141,3 +141,19 @@ def test_residual_model_rejects_autograd_training_call_and_bad_arguments():
     with torch.no_grad():
         out = m(x, training=True)
     assert out["training"] is True and float((out["y_in"] - out["y"]).abs().max()) <= 0.5
+
+
+def test_graphed_forward_of_the_main_and_residual_models():
+    """parallel.GraphedForward on JointAutoregressiveHierarchical (captured with its parallel branches: g_s and the context conv
+    beside h_a -> h_s) and on HierarchicalMixtureResidual: bit-identical to the eager calls."""
+    from neural_image_compression_b200 import parallel
+    x = H.seeded_input((2, 3, 128, 192)).cuda()
+    for model in (H.seeded_model(128, 3, "calib", precision="bf16x3").cuda(),
+                  H.seeded_residual_model(128, 1, 17.98, 141.28, precision="bf16x3").cuda()):
+        eager = model(x, training=False)
+        gf = parallel.GraphedForward(model)
+        for _ in range(3):
+            out = gf(x)
+        torch.cuda.synchronize()
+        for k in ("x_hat", "y_in", "z_in", "p_y", "p_z", "logp_y"):
+            assert torch.equal(out[k], eager[k]), (type(model).__name__, k)
