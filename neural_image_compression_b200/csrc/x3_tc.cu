@@ -256,17 +256,20 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 
 // ---------------------------------------------------------------------------------------------
 // The same GDN / IGDN for c = 64 NP channels where gamma hi / lo (4 c^2 bytes: 144 KB at c = 192) cannot stay in shared memory
-// next to two tile buffers: gamma STREAMS through a small ring in [64 out x 64 in] pieces (hi + lo = 16 KB per ring slot, all
-// NP^2 piece pairs once per 128-pixel tile - they live in L2), and the norm is accumulated per 64-channel output piece:
+// next to the tile: gamma STREAMS through a ring in [64 out x 64 in] pieces (hi + lo = 16 KB per ring slot, all NP^2 piece pairs
+// once per 128-pixel tile - they live in L2), and the norm is accumulated per 64-channel output piece:
 //   for n, k:  D[:, 64 n ..] += sq_hi[k] . g_hi[n][k] + sq_hi[k] . g_lo[n][k] + sq_lo[k] . g_hi[n][k]        (12 MMAs of N = 64)
 // 4 NP worker warps (thread <-> pixel row x 64-channel group), one warp that loads the x tiles, one that feeds the gamma ring;
 // worker thread 0 issues the MMAs.  Used for the reference's default capacity M = 192 (Models.py:17) and ScalableImageCoding.
+// Shared memory: ONE 96 KB tile buffer + an 8-slot ring (128 KB).  The first version had two tile buffers and a 2-slot ring and
+// was ring-latency bound (traced: 1600 clk for each of the 9 steps of a tile, 23.5k clk per tile); with 8 pairs in flight the MMA
+// loop runs at the tensor rate and the price is that a tile's load no longer overlaps the previous tile's arithmetic.
 // ---------------------------------------------------------------------------------------------
-constexpr int kGRing = 2;                       // ring slots of one (g_hi, g_lo) piece pair
+constexpr int kGRing = 8;                       // ring slots of one (g_hi, g_lo) piece pair
 constexpr int kPiece = 64 * 128;                // [64 out rows][64 in] bf16, 128-byte swizzle
 
 struct __align__(8) GdnCBarriers {
-  uint64_t x_full[2], x_empty[2], g_full[kGRing], g_empty[kGRing], mma_done;
+  uint64_t x_full, x_empty, sq_ready, g_full[kGRing], g_empty[kGRing], mma_done;
   uint32_t tmem_base;
   volatile int abort_flag;
 };
@@ -279,13 +282,13 @@ gdn_x3c_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;                            // kGRing x [g_hi piece | g_lo piece]
-  uint8_t* bufs = smem + kGRing * 2 * kPiece;      // two tile buffers of 2 NP panels: [hi 0 | lo 0 | hi 1 | lo 1 | ...] once squared
+  uint8_t* bufs = smem + kGRing * 2 * kPiece;      // the tile buffer, 2 NP panels: [hi 0 | lo 0 | hi 1 | lo 1 | ...] once squared
   __shared__ GdnCBarriers sb;
   __shared__ __align__(16) float s_beta[C];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&sb.x_full[i], 1); mbar_init(&sb.x_empty[i], 1); }
+    mbar_init(&sb.x_full, 1); mbar_init(&sb.x_empty, 1); mbar_init(&sb.sq_ready, kWorkers);
     for (int i = 0; i < kGRing; ++i) { mbar_init(&sb.g_full[i], 1); mbar_init(&sb.g_empty[i], 1); }
     mbar_init(&sb.mma_done, 1);
     sb.abort_flag = 0;
@@ -300,18 +303,47 @@ gdn_x3c_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const uint32_t tmem = sb.tmem_base;
 
   if (warp == kWorkers) {
-    // ===================== x tiles =====================
+    // ===================== x tiles + MMA issue =====================
+    // (a worker thread issuing the MMAs shares its warp with 31 lanes that spin on the completion barrier: traced at 115 clk per
+    //  N = 64 MMA; this warp has nothing else to do)
     if (lane == 0) {
       tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_o);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const uint32_t b = it & 1;
-        if (!wait_abort(&sb.x_empty[b], ((it >> 1) & 1) ^ 1, &sb.abort_flag, p.status)) break;
-        mbar_expect_tx(&sb.x_full[b], 2 * NP * kPanel);
+      const uint32_t idesc = umma_idesc_bf16(128, 64);
+      const uint32_t hi = umma_desc_hi(1024);
+      const uint32_t sq = umma_desc_lo(smem_u32(bufs));
+      const uint32_t r0 = umma_desc_lo(smem_u32(ring));
+      constexpr uint32_t P = kPanel >> 4, PP = kPiece >> 4;
+      uint32_t it = 0, step = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.ntiles && ok; tile += gridDim.x, ++it) {
+        if (!wait_abort(&sb.x_empty, (it & 1) ^ 1, &sb.abort_flag, p.status)) break;
+        mbar_expect_tx(&sb.x_full, 2 * NP * kPanel);
         // f32: box k = channels [32 k, 32 k + 32); pairs: panel 2 g = hi of channel group g, panel 2 g + 1 = its lo
 #pragma unroll
         for (int k = 0; k < 2 * NP; ++k)
-          tma_load_2d(bufs + (b * 2 * NP + k) * kPanel, &map_x, &sb.x_full[b], PAIR_IN ? (k >> 1) * 64 + (k & 1) * C : k * 32, tile * 128);
+          tma_load_2d(bufs + k * kPanel, &map_x, &sb.x_full, PAIR_IN ? (k >> 1) * 64 + (k & 1) * C : k * 32, tile * 128);
+        if (!wait_abort(&sb.sq_ready, it & 1, &sb.abort_flag, p.status)) break;          // the workers have written the squares
+        tcgen05_fence_after();
+#pragma unroll
+        for (int n = 0; n < NP; ++n) {
+#pragma unroll
+          for (int k = 0; k < NP; ++k, ++step) {
+            const uint32_t s = step % kGRing;
+            if (!wait_abort(&sb.g_full[s], (step / kGRing) & 1, &sb.abort_flag, p.status)) { ok = false; break; }
+            tcgen05_fence_after();
+            const uint32_t gh = r0 + s * 2 * PP, gl = gh + PP, sh = sq + 2 * k * P, sl = sh + P;
+            const uint32_t d = tmem + n * 64;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(d, sh + kk * 2, hi, gh + kk * 2, hi, idesc, (k | kk) ? 1u : 0u);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(d, sh + kk * 2, hi, gl + kk * 2, hi, idesc, 1);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(d, sl + kk * 2, hi, gh + kk * 2, hi, idesc, 1);
+            umma_commit(&sb.g_empty[s]);
+          }
+          if (!ok) break;
+        }
+        umma_commit(&sb.mma_done);
       }
     }
   } else if (warp == kWorkers + 1) {
@@ -338,12 +370,13 @@ gdn_x3c_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t swz = static_cast<uint32_t>(row & 7);
     const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + hs * 64;
     auto sync_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers * 32) : "memory"); };
-    uint32_t it = 0, step = 0;
+    uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const uint32_t b = it & 1;
-      uint8_t* my_h = bufs + (b * 2 * NP + 2 * hs) * kPanel + row * 128;
+      uint8_t* my_h = bufs + (2 * hs) * kPanel + row * 128;
       uint8_t* my_l = my_h + kPanel;
-      if (!__all_sync(0xffffffffu, wait_abort(&sb.x_full[b], (it >> 1) & 1, &sb.abort_flag, p.status))) break;
+      if (leader) gtrace(p, it, 0);
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.x_full, it & 1, &sb.abort_flag, p.status))) break;
+      if (leader) gtrace(p, it, 1);
       float xr[64];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -376,37 +409,11 @@ gdn_x3c_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
-      sync_workers();
-      if (leader) {
-        // the stores of tile it - 1 have been reading the other buffer since the end of the last iteration: once they are done
-        // with it, tile it + 1 may be loaded there (overlaps this tile's MMAs)
-        if (it > 0) { tma_store_wait_read(); mbar_arrive(&sb.x_empty[b ^ 1]); }
-        tcgen05_fence_after();
-        const uint32_t idesc = umma_idesc_bf16(128, 64);
-        const uint32_t hi = umma_desc_hi(1024);
-        const uint32_t sq = umma_desc_lo(smem_u32(bufs + b * 2 * NP * kPanel));
-        const uint32_t r0 = umma_desc_lo(smem_u32(ring));
-        constexpr uint32_t P = kPanel >> 4, PP = kPiece >> 4;
-        bool ok = true;
-        for (int n = 0; n < NP && ok; ++n) {
-          for (int k = 0; k < NP; ++k, ++step) {
-            const uint32_t s = step % kGRing;
-            if (!wait_abort(&sb.g_full[s], (step / kGRing) & 1, &sb.abort_flag, p.status)) { ok = false; break; }
-            tcgen05_fence_after();
-            const uint32_t gh = r0 + s * 2 * PP, gl = gh + PP, sh = sq + 2 * k * P, sl = sh + P;
-            const uint32_t d = tmem + n * 64;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(d, sh + kk * 2, hi, gh + kk * 2, hi, idesc, (k | kk) ? 1u : 0u);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(d, sh + kk * 2, hi, gl + kk * 2, hi, idesc, 1);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(d, sl + kk * 2, hi, gh + kk * 2, hi, idesc, 1);
-            umma_commit(&sb.g_empty[s]);
-          }
-        }
-        umma_commit(&sb.mma_done);
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb.sq_ready);
+      if (leader) gtrace(p, it, 2);
       if (!__all_sync(0xffffffffu, wait_abort(&sb.mma_done, it & 1, &sb.abort_flag, p.status))) break;
+      if (leader) gtrace(p, it, 5);
       tcgen05_fence_after();
       const float4* beta4 = reinterpret_cast<const float4*>(s_beta + hs * 64);
 #pragma unroll
@@ -436,13 +443,17 @@ gdn_x3c_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       fence_proxy_async_smem();
       sync_workers();
       if (leader) {
-        const uint8_t* t0 = bufs + b * 2 * NP * kPanel;
+        gtrace(p, it, 6);
+        const uint8_t* t0 = bufs;
 #pragma unroll
         for (int g = 0; g < NP; ++g) {
           tma_store_2d(&map_o, t0 + (2 * g) * kPanel, g * 64, tile * 128);            // hi, channel group g
           tma_store_2d(&map_o, t0 + (2 * g + 1) * kPanel, C + g * 64, tile * 128);    // lo
         }
         tma_store_commit();
+        tma_store_wait_read();                       // the stores have read the tile: the next one may be loaded over it
+        mbar_arrive(&sb.x_empty);
+        gtrace(p, it, 3);
       }
     }
     if (leader) tma_store_wait_all();
@@ -981,13 +992,13 @@ static int launch_gdn_c(const void* x, int pair_in, long npix, int inverse, cons
   p.ntiles = static_cast<int>((npix + 127) / 128); p.inverse = inverse; p.beta = beta_eff;
   p.status = status_word();
   if (!p.status) return fail(NIC_E_CUDA, "gdn bf16x3: cannot allocate the status word");
-  p.dbg_times = nullptr;
+  p.dbg_times = reinterpret_cast<long long*>(g_trace_buffer);
   CUtensorMap map_x, map_g, map_o;
   if (pair_in) { if (int rc = encode_2d(&map_x, x, 2 * c, static_cast<uint64_t>(npix), 64, 128)) return rc; }
   else if (int rc = encode_2d_ex(&map_x, x, 4, c, static_cast<uint64_t>(npix), 32, 128)) return rc;
   if (int rc = encode_2d(&map_g, gamma_packed, c, 2 * c, 64, 64)) return rc;
   if (int rc = encode_2d(&map_o, y, 2 * c, static_cast<uint64_t>(npix), 64, 128)) return rc;
-  const int smem_bytes = kGRing * 2 * kPiece + 2 * 2 * NP * kPanel + 1024;
+  const int smem_bytes = kGRing * 2 * kPiece + 2 * NP * kPanel + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     if (int rc = check_cuda(cudaFuncSetAttribute(gdn_x3c_kernel<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
