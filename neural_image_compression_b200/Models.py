@@ -193,7 +193,8 @@ class JointAutoregressiveHierarchical(nn.Module):
                 res, _ = _training._forward_impl(self, x.contiguous().float(), nz, ny, lean, qmode=_QN if training else _QR, arm="bf16x3")
                 _training.forget_pairs()
             x_hat, logp_y, logp_z, y, y_in, z, z_in, p_z, p_y, parts_y, parts_z = res[:11]
-            logp_y._nic_partials, logp_z._nic_partials = parts_y, parts_z
+            engine.attach_partials(logp_y, parts_y)
+            engine.attach_partials(logp_z, parts_z)
             out = {"x_hat": x_hat, "y": y, "y_in": y_in, "z": z, "z_in": z_in, "p_z": p_z, "logp_z": logp_z, "p_y": p_y,
                    "logp_y": logp_y, "training": training}
             if not lean:
@@ -252,8 +253,8 @@ class JointAutoregressiveHierarchical(nn.Module):
                 x_hat = _pair_g_s(self, y_in_nhwc, B, hy, wy, prec)
 
         # per-image partial sums of logp ride along for rd_loss (RateDistortionLoss.py:13-14)
-        logp_y._nic_partials = ly["partials"]
-        logp_z._nic_partials = parts_z
+        engine.attach_partials(logp_y, ly["partials"])
+        engine.attach_partials(logp_z, parts_z)
         out = {
             "x_hat": x_hat, "y": y, "y_in": y_in, "z": z, "z_in": z_in,
             "p_z": p_z, "logp_z": logp_z, "p_y": p_y, "logp_y": logp_y, "training": training,
@@ -344,7 +345,8 @@ class HierarchicalMixtureResidual(nn.Module):
             x_nhwc, _, _ = self.decoder.run_nhwc(y_in_nhwc, B, hy, wy, arm)
             x_hat = x_nhwc.permute(0, 3, 1, 2).contiguous()
         p_y, logp_y = ly["p"], ly["logp"]
-        logp_y._nic_partials, logp_z._nic_partials = ly["partials"], parts_z
+        engine.attach_partials(logp_y, ly["partials"])
+        engine.attach_partials(logp_z, parts_z)
         out = {"x_hat": x_hat, "y": y, "y_in": y_in, "z": z, "z_in": z_in, "p_z": p_z, "logp_z": logp_z, "p_y": p_y, "logp_y": logp_y,
                "training": training}
         if not lean:
@@ -448,7 +450,9 @@ class ScalableImageCoding(nn.Module):
             else:
                 x_hat = _pair_g_s(self, y_in_nhwc, B, hy, wy, prec)
         l1, l2 = heads
-        l1["logp"]._nic_partials, l2["logp"]._nic_partials, logp_z._nic_partials = l1["partials"], l2["partials"], parts_z
+        engine.attach_partials(l1["logp"], l1["partials"])
+        engine.attach_partials(l2["logp"], l2["partials"])
+        engine.attach_partials(logp_z, parts_z)
         out = {
             "x_hat": x_hat, "y": y, "y_in": y_in, "y1": y1, "y2": y2, "z": z, "z_in": z_in, "p_z": p_z, "logp_z": logp_z,
             "p_y1": l1["p"], "logp_y1": l1["logp"], "p_y2": l2["p"], "logp_y2": l2["logp"], "training": training,
@@ -542,7 +546,9 @@ class ScalableImageCoding(nn.Module):
                 h, w = engine.conv_out_hw(op.conv, h, w)
             x_hat = a
         l1, l2 = heads
-        l1["logp"]._nic_partials, l2["logp"]._nic_partials, logp_z._nic_partials = l1["partials"], l2["partials"], parts_z
+        engine.attach_partials(l1["logp"], l1["partials"])
+        engine.attach_partials(l2["logp"], l2["partials"])
+        engine.attach_partials(logp_z, parts_z)
         out = {
             "x_hat": x_hat, "y": y, "y_in": y_in, "y1": y1, "y2": y2, "z": z, "z_in": z_in, "p_z": p_z, "logp_z": logp_z,
             "p_y1": l1["p"], "logp_y1": l1["logp"], "p_y2": l2["p"], "logp_y2": l2["logp"], "training": training,

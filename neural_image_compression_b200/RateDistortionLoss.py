@@ -16,8 +16,8 @@ from ._lib import check, current_stream, ptr
 
 def _logp_partials(logp: torch.Tensor) -> torch.Tensor:
     parts = getattr(logp, "_nic_partials", None)
-    if parts is not None:
-        return parts
+    if parts is not None and getattr(logp, "_nic_partials_version", None) == logp._version:
+        return parts                                       # the sums the likelihood kernel produced alongside logp (still valid: logp unmodified)
     lib = _lib.load()
     b = logp.shape[0]
     logp = logp.contiguous().float()

@@ -36,12 +36,26 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into one shared object, one nvcc process per file in parallel."""
+    """Compile every .cu under csrc/ into one shared object, one nvcc process per file in parallel.  Serialised across processes
+    by a file lock (data-parallel ranks that start on a stale checkout would otherwise write the same objects concurrently);
+    staleness is re-checked under the lock, so only the first rank compiles."""
     if not force and not is_stale():
         return LIB_PATH
-    nvcc = _nvcc()
+    import fcntl
     objdir = os.path.join(PKG_DIR, "build")
     os.makedirs(objdir, exist_ok=True)
+    with open(os.path.join(objdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():
+                return LIB_PATH
+            return _build_locked(objdir, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(objdir: str, verbose: bool) -> str:
+    nvcc = _nvcc()
     procs = []
     objs = []
     for src in sources():
@@ -57,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out:
             print(out)
-    tmp = LIB_PATH + ".tmp"
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
     link = subprocess.run([nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if link.returncode != 0:

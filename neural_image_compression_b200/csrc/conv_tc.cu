@@ -79,10 +79,12 @@ static EncodeTiledFn get_encode() {
 
 void* g_trace_buffer = nullptr;   // set through nic_debug_set_trace (timing experiments; not part of the product ABI surface)
 
-int* status_word() {       // one device int per process: the kernels' "a bounded wait expired" flag
-  static int* d = nullptr;
-  if (!d) { if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return nullptr; cudaMemset(d, 0, sizeof(int)); }
-  return d;
+int* status_word() {       // one device int per DEVICE: the kernels' "a bounded wait expired" flag
+  static int* d[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!d[dev]) { if (cudaMalloc(&d[dev], sizeof(int)) != cudaSuccess) return nullptr; cudaMemset(d[dev], 0, sizeof(int)); }
+  return d[dev];
 }
 
 int encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {

@@ -175,8 +175,12 @@ __global__ void eval_sse_fold_kernel(const float* __restrict__ partials, int par
   }
 }
 
-static int ensure_gauss() {
-  static bool done = false;
+static int ensure_gauss() {                       // the constant-memory window is per device: upload once on each
+  static bool done_dev[64] = {};
+  int dev = 0;
+  if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  if (dev < 0 || dev >= 64) return fail(NIC_E_CUDA, "ms_ssim: device index %d", dev);
+  bool& done = done_dev[dev];
   if (done) return NIC_OK;
   // pytorch_msssim._fspecial_gauss_1d(11, 1.5): exp(-(i - 5)^2 / (2 sigma^2)) normalised, in float32
   float g[kWin]; float s = 0.f;

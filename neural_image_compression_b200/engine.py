@@ -217,5 +217,12 @@ def latent_handoff(v_nhwc: torch.Tensor, qmode: int, noise: Optional[torch.Tenso
     return v, v_in, v_in_nhwc, v_lowp
 
 
+def attach_partials(logp: torch.Tensor, parts: torch.Tensor) -> None:
+    """Let the per-image partial sums the likelihood kernel produced ride along with `logp` for rd_loss (RateDistortionLoss.py:
+    13-14), together with logp's version: a caller that modifies logp in place invalidates them (rd_loss then re-sums)."""
+    logp._nic_partials = parts
+    logp._nic_partials_version = logp._version
+
+
 def partials(b: int, device) -> torch.Tensor:
     return torch.empty((b, _lib.load().nic_partials_per_image()), dtype=torch.float32, device=device)

@@ -635,6 +635,9 @@ class _TrainForward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_xhat, g_logp_y, g_logp_z, *unused):
         model, S = ctx.model, ctx.S
+        if S is None:
+            raise RuntimeError("the saved activations of this forward pass were released by its first backward(); run the forward "
+                               "again (retain_graph=True is not supported by the hand-written backward)")
         grads = _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z)
         ctx.S = None
         params = [p for _, p in model.named_parameters()]
@@ -658,7 +661,8 @@ def step_gradients(model, x: torch.Tensor, lambda_rd: float, noise=None, partial
     x = x.contiguous().float()
     outs, S = _forward_impl(model, x, noise_z, noise_y, True)
     x_hat, logp_y, logp_z = outs[:3]
-    logp_y._nic_partials, logp_z._nic_partials = outs[9], outs[10]
+    engine.attach_partials(logp_y, outs[9])
+    engine.attach_partials(logp_z, outs[10])
     per_image, scalars = rd_terms({"x_hat": x_hat, "logp_y": logp_y, "logp_z": logp_z}, x, lambda_rd)
     # d loss / d logp = -1 / (ln 2 * H * W * B); d loss / d x_hat = lambda * 255^2 * 2 (x_hat - x) / numel  (RateDistortionLoss.py:13-34)
     gl = torch.full((1,), -1.0 / (math.log(2.0) * H * W * B), dtype=torch.float32, device=x.device)
@@ -687,7 +691,8 @@ def train_forward(model, x: torch.Tensor, noise=None, lean: bool = False) -> dic
     params = [p for _, p in model.named_parameters()]
     res = _TrainForward.apply(model, x.contiguous().float(), noise_z, noise_y, lean, *params)
     x_hat, logp_y, logp_z, y, y_in, z, z_in, p_z, p_y, parts_y, parts_z = res[:11]
-    logp_y._nic_partials, logp_z._nic_partials = parts_y, parts_z      # per-image sums of logp ride along for rd_loss
+    engine.attach_partials(logp_y, parts_y)
+    engine.attach_partials(logp_z, parts_z)      # per-image sums of logp ride along for rd_loss
     out = {"x_hat": x_hat, "y": y, "y_in": y_in, "z": z, "z_in": z_in, "p_z": p_z, "logp_z": logp_z, "p_y": p_y, "logp_y": logp_y,
            "training": True}
     if not lean:

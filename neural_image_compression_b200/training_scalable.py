@@ -282,7 +282,9 @@ def train_forward(model, x: torch.Tensor, noise=None) -> dict:
     params = [p for _, p in model.named_parameters()]
     res = _ScalableTrainForward.apply(model, x.contiguous().float(), noise_z, noise_y, *params)
     x_hat, logp_y1, logp_y2, logp_z, y, y_in, z, z_in, p_z, p_y1, p_y2, parts1, parts2, parts_z = res[:14]
-    logp_y1._nic_partials, logp_y2._nic_partials, logp_z._nic_partials = parts1, parts2, parts_z
+    engine.attach_partials(logp_y1, parts1)
+    engine.attach_partials(logp_y2, parts2)
+    engine.attach_partials(logp_z, parts_z)
     y1, y2 = torch.split(y_in, [M1, M - M1], dim=1)
     out = {"x_hat": x_hat, "y": y, "y_in": y_in, "y1": y1, "y2": y2, "z": z, "z_in": z_in, "p_z": p_z, "logp_z": logp_z,
            "p_y1": p_y1, "logp_y1": logp_y1, "p_y2": p_y2, "logp_y2": logp_y2, "training": True}

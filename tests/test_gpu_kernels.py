@@ -255,3 +255,16 @@ def test_conv_empty_batch_and_bad_shapes(dev):
         model(torch.zeros(1, 3, 60, 64, device=dev), training=False)
     with pytest.raises(ValueError):
         model(torch.zeros(1, 1, 64, 64, device=dev), training=False)
+
+
+def test_rd_loss_resums_when_logp_was_modified_in_place(dev):
+    """The likelihood kernel's per-image partial sums ride along with logp (engine.attach_partials); a caller that edits logp in place
+     must get the loss of the EDITED tensor, not of the stale sums."""
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    model = H.seeded_model(128, 3, "plain", precision="fp32").to(dev)
+    x = H.seeded_input((1, 3, 64, 64)).to(dev)
+    out = model(x, training=False)
+    a = rd_loss(out, x, 0.005)["bpp_y"]
+    out["logp_y"].mul_(2.0)
+    b = rd_loss(out, x, 0.005)["bpp_y"]
+    assert abs(b - 2 * a) < 1e-5 * abs(a)
