@@ -14,6 +14,14 @@ from . import _lib, engine
 from ._lib import check, current_stream, ptr
 
 
+def _check_pipeline():
+    """The tensor-core kernels bound every barrier wait and raise a device flag instead of hanging; this is the natural place to
+    look at it: the loss has just synchronised with the device anyway.  An aborted kernel means the outputs above are garbage."""
+    if _lib.load().nic_pipeline_status() != 0:
+        raise _lib.NicError("a tensor-core kernel gave up on an expired pipeline wait (nic_pipeline_status): the results of this "
+                            "forward pass are invalid")
+
+
 def _logp_partials(logp: torch.Tensor) -> torch.Tensor:
     parts = getattr(logp, "_nic_partials", None)
     if parts is not None and getattr(logp, "_nic_partials_version", None) == logp._version:
@@ -64,6 +72,7 @@ def rd_loss_device(model_out: dict, x: torch.Tensor, lambda_rd: float):
 def rd_loss(model_out: dict, x: torch.Tensor, lambda_rd: float):
     loss, per_image, scalars = rd_loss_device(model_out, x, lambda_rd)
     s = scalars.tolist()                                   # the one host synchronisation
+    _check_pipeline()
     mse_per_image = per_image[2]
     return {
         "loss": loss,
@@ -100,6 +109,7 @@ def vision_rd_loss(model_out: dict, x: torch.Tensor, lambda_rd: float, gamma: fl
                                       current_stream()), "nic_rd_finalize")
             rows.append(per_image); scal.append(scalars)
     s1, s2 = scal[0].tolist(), scal[1].tolist()
+    _check_pipeline()
     bpp_y1, bpp_y2, bpp_z, mse, psnr = s1[0], s2[0], s1[1], s1[3], s1[4]
     bpp_total = bpp_y1 + bpp_y2 + bpp_z
     mse_per_image = rows[0][2]
