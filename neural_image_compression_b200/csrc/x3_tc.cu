@@ -673,16 +673,27 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 // First layer of g_a in the bf16x3 arm, FUSED: Conv2d(3, 128, 5, s2, p2) + bias + GDN, NCHW f32 image -> bf16 hi/lo pair
 // activation, one kernel.  The two-kernel form (conv_first_x3_kernel + gdn_x3_kernel) moves 2.4 GB through HBM per 16 images
 // (f32 scratch out and in, pairs out); this one writes the 0.8 GB of pairs only.
-// 11 warps: 0-1 producers (patch by TMA, im2col with hi/lo split, one A stage), 2 MMA issuer (15 conv MMAs of tile t + 1, then
-// the 16 + 8 GDN MMAs of tile t), 3-10 workers (thread <-> pixel row x 64-channel half: x from TMEM to registers, squares hi
-// -> MMA -> squares lo -> MMA -> x * rsqrt(beta + .) -> hi tile -> TMA store -> lo tile -> TMA store; ONE 32 KB tile serves as
-// squares and staging).  Shared memory: W 48 KB + gamma hi/lo 64 KB + A 48 KB + tile 32 KB + two patches.
+//
+// 16 warps in four groups of four (the unit of setmaxnreg): 0-3 producers (patch by TMA, im2col with hi/lo split, one pixel row
+// per thread, one A stage), 4 MMA issuer (5-7 idle), 8-15 workers (thread <-> pixel row x 64-channel half).  The producers and
+// the issuer give registers back (64 each) so that the workers run with 192.
+//
+// Tensor memory (512 columns): conv accumulators X0, X1 (2 x 128), GDN accumulator (128), SQUARES (128: 64 columns of packed
+// bf16x2 hi, 64 of lo).  The squares are the A operand of the 24 GDN MMAs straight from tensor memory (the [a_tmem] form of
+// tcgen05.mma): these MMAs read only gamma through the shared-memory port, all 24 are issued back to back, and the 32 KB tile of
+// shared memory is staging only.  Per tile t a worker warp does, with no barrier between warps:
+//   norm(t) from TMEM | lo half of tile t - 1 -> its staging slice -> its own TMA store | x(t + 1) from TMEM, squares -> TMEM,
+//   GDN(t + 1) starts | x(t) from TMEM again, y = x * rsqrt(beta + norm) | hi half of tile t -> slice -> TMA store
+// so that GDN(t + 1) is covered by the normalisation and the hi store, and the TMA read of a staged half by the work after it.
+// Shared memory: W 48 KB + gamma hi/lo 64 KB + A 48 KB + staging 32 KB + two patches.
+// History (16 images, 512 x 768): squares through shared memory, one tile in the worker stage at a time 383 us (a chain of
+// 8.2k clk per tile) -> squares in TMEM 291 -> per-warp staging / stores 260 -> this layout (see profiles/README.md).
 // ---------------------------------------------------------------------------------------------
-constexpr int kFfProducers = 2, kFfWorkers = 8;   // 4 producer warps push the kernel to 416 threads = 128 registers: spills, slower
-constexpr int kFfThreads = (kFfProducers + 1 + kFfWorkers) * 32;
+constexpr int kFfProducers = 4, kFfIssuerWarp = 4, kFfFirstWorker = 8, kFfWorkers = 8;
+constexpr int kFfThreads = (kFfFirstWorker + kFfWorkers) * 32;
 
 struct FirstFusedParams {
-  __nv_bfloat16* y;               // [n, hout, wout, 256] bf16 pairs (the lo half is written with direct stores)
+  __nv_bfloat16* y;               // [n, hout, wout, 256] bf16 pairs
   long long* dbg_times;           // NIC trace hook (tools/trace_first.py): [cta][32 tiles][16] clock64 stamps, null = off
   const float* bias;
   const float* beta;
@@ -692,7 +703,7 @@ struct FirstFusedParams {
 };
 
 struct __align__(8) FirstFusedBarriers {
-  uint64_t patch_full[2], a_full, a_empty, w_full, gamma_full, acc_full[2], acc_empty[2], sq1, sq2, g1, g2;
+  uint64_t patch_full[2], a_full, a_empty, w_full, gamma_full, acc_full[2], acc_empty[2], sq_full, gdn_done;
   uint32_t tmem_base;
   volatile int abort_flag;
 };
@@ -707,18 +718,18 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ FirstFusedBarriers sb;
-  __shared__ float s_bias[128];
+  __shared__ __align__(16) float s_bias[128];
   __shared__ __align__(16) float s_beta[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&sb.patch_full[i], 1); mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], kFfWorkers); }
     mbar_init(&sb.a_full, kFfProducers * 32); mbar_init(&sb.a_empty, 1); mbar_init(&sb.w_full, 1); mbar_init(&sb.gamma_full, 1);
-    mbar_init(&sb.sq1, kFfWorkers); mbar_init(&sb.sq2, kFfWorkers); mbar_init(&sb.g1, 1); mbar_init(&sb.g2, 1);
+    mbar_init(&sb.sq_full, kFfWorkers); mbar_init(&sb.gdn_done, 1);
     sb.abort_flag = 0;
     fence_barrier_init();
   }
-  if (warp == kFfProducers) { tmem_alloc(&sb.tmem_base, 512); tmem_relinquish(); }
+  if (warp == kFfIssuerWarp) { tmem_alloc(&sb.tmem_base, 512); tmem_relinquish(); }
   pdl_wait();
   if (tid < 128) { s_bias[tid] = f.bias[tid]; s_beta[tid] = f.beta[tid]; }
   tcgen05_fence_before();
@@ -732,28 +743,30 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     tx = tile % f.tiles_x; tile /= f.tiles_x; ty = tile % f.tiles_y; img = tile / f.tiles_y;
   };
 
-  if (warp < kFfProducers) {
-    // ===================== producers: 64 threads, two pixel rows each =====================
-    auto fetch_patch = [&](int tile, int bufi) {
-      int img, ty, tx;
-      tile_coords(tile, img, ty, tx);
-      mbar_expect_tx(&sb.patch_full[bufi], kPatchBytes);
-      tma_load_3d(patch + bufi * kPatchStride, &map_img, &sb.patch_full[bufi], 16 * tx - 4, 32 * ty - 2, img * 3);
-    };
-    if (tid == 0) { tma_prefetch_desc(&map_img); if (first_tile < f.total_tiles) fetch_patch(first_tile, 0); }
-    uint32_t it = 0;
-    for (int tile = first_tile; tile < f.total_tiles; tile += tile_step, ++it) {
-      const uint32_t st = it & 1;
-      asm volatile("bar.sync 3, %0;" ::"n"(kFfProducers * 32) : "memory");      // patch(it-1) is no longer read
-      if (tid == 0 && tile + tile_step < f.total_tiles) fetch_patch(tile + tile_step, st ^ 1);
-      if (!__all_sync(0xffffffffu, wait_abort(&sb.patch_full[st], (it >> 1) & 1, &sb.abort_flag, f.status))) break;
-      if (!__all_sync(0xffffffffu, wait_abort(&sb.a_empty, (it & 1) ^ 1, &sb.abort_flag, f.status))) break;
-#pragma unroll 1
-      for (int rr = 0; rr < 128 / (kFfProducers * 32); ++rr) {
-        const int r = tid + rr * (kFfProducers * 32), g = r >> 3, c8 = r & 7;
-        const uint32_t swz = static_cast<uint32_t>(r & 7);
+  if (warp < kFfFirstWorker) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp < kFfProducers) {
+      // ===================== producers: 128 threads, one pixel row each =====================
+      auto fetch_patch = [&](int tile, int bufi) {
+        int img, ty, tx;
+        tile_coords(tile, img, ty, tx);
+        mbar_expect_tx(&sb.patch_full[bufi], kPatchBytes);
+        tma_load_3d(patch + bufi * kPatchStride, &map_img, &sb.patch_full[bufi], 16 * tx - 4, 32 * ty - 2, img * 3);
+      };
+      if (tid == 0) { tma_prefetch_desc(&map_img); if (first_tile < f.total_tiles) fetch_patch(first_tile, 0); }
+      const int r = tid, g = r >> 3, c8 = r & 7;
+      const uint32_t swz = static_cast<uint32_t>(r & 7);
+      uint8_t* dst = smem + f.off_a + r * 128;
+      uint32_t it = 0;
+      for (int tile = first_tile; tile < f.total_tiles; tile += tile_step, ++it) {
+        const uint32_t st = it & 1;
+        asm volatile("bar.sync 3, %0;" ::"n"(kFfProducers * 32) : "memory");      // patch(it-1) is no longer read
+        if (tid == 0 && tile + tile_step < f.total_tiles) fetch_patch(tile + tile_step, st ^ 1);
+        if (!__all_sync(0xffffffffu, wait_abort(&sb.patch_full[st], (it >> 1) & 1, &sb.abort_flag, f.status))) break;
+        if (tid == 0) ftrace(f, it, 13);
+        if (!__all_sync(0xffffffffu, wait_abort(&sb.a_empty, (it & 1) ^ 1, &sb.abort_flag, f.status))) break;
+        if (tid == 0) ftrace(f, it, 15);
         const float* src = reinterpret_cast<const float*>(patch + st * kPatchStride) + (2 * g) * kPatchW + 2 * c8 + 2;
-        uint8_t* dst = smem + f.off_a + r * 128;
 #pragma unroll
         for (int ch = 0; ch < 10; ++ch) {
           uint32_t h[4], l[4];
@@ -778,14 +791,12 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             *reinterpret_cast<uint4*>(dst + 2 * kPanel + offl) = make_uint4(l[0], l[1], l[2], l[3]);
           }
         }
+        fence_proxy_async_smem();
+        mbar_arrive(&sb.a_full);
+        if (tid == 0) ftrace(f, it, 14);
       }
-      fence_proxy_async_smem();
-      mbar_arrive(&sb.a_full);
-      if (tid == 0) ftrace(f, it, 14);
-    }
-  } else if (warp == kFfProducers) {
-    // ===================== weight / gamma loader + MMA issuer =====================
-    if (lane == 0) {
+    } else if (warp == kFfIssuerWarp && lane == 0) {
+      // ===================== weight / gamma loader + MMA issuer =====================
       tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_g); tma_prefetch_desc(&map_o);
       mbar_expect_tx(&sb.w_full, 3 * kPanel);
       for (int k = 0; k < 3; ++k) tma_load_2d(smem + f.off_w + k * kPanel, &map_w, &sb.w_full, k * 64, 0);
@@ -794,11 +805,10 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       const uint32_t idesc = umma_idesc_bf16(128, 128);
       const uint32_t hi = umma_desc_hi(1024);
       const uint32_t ab = umma_desc_lo(smem_u32(smem + f.off_a)), w_lo = umma_desc_lo(smem_u32(smem + f.off_w));
-      const uint32_t sq_lo = umma_desc_lo(smem_u32(sq));
       const uint32_t gh = umma_desc_lo(smem_u32(smem + f.off_gamma)), gl = umma_desc_lo(smem_u32(smem + f.off_gamma + 2 * kPanel));
       constexpr uint32_t P = kPanel >> 4;
       bool ok = wait_abort(&sb.w_full, 0, &sb.abort_flag, f.status) && wait_abort(&sb.gamma_full, 0, &sb.abort_flag, f.status);
-      const uint32_t d2 = tmem + 256;
+      const uint32_t d2 = tmem + 256, s_hi = tmem + 384, s_lo = tmem + 448;
       auto conv_mmas = [&](uint32_t it) -> bool {
         const uint32_t g = it & 1;
         if (!wait_abort(&sb.acc_empty[g], ((it >> 1) & 1) ^ 1, &sb.abort_flag, f.status)) return false;
@@ -818,141 +828,153 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         umma_commit(&sb.acc_full[g]);
         return true;
       };
+      // Order per tile j: GDN(j) as soon as the workers have stored its squares, then the conv of tile j + 1 (tile 1 goes out
+      // with tile 0): its accumulator buffer is the one tile j - 1 is normalised from, which the workers do right after the
+      // squares that have just been consumed - a later conv would block this thread past sq_full(j + 1).
       uint32_t it = 0;
       int tile = first_tile;
       if (ok && tile < f.total_tiles) ok = conv_mmas(0);
+      if (ok && tile + tile_step < f.total_tiles) ok = conv_mmas(1);
       for (; tile < f.total_tiles && ok; tile += tile_step, ++it) {
-        if (tile + tile_step < f.total_tiles) { if (!conv_mmas(it + 1)) break; }       // conv of the next tile first: it overlaps the workers
-        ftrace(f, it, 11);
-        if (!wait_abort(&sb.sq1, it & 1, &sb.abort_flag, f.status)) break;
+        if (!wait_abort(&sb.sq_full, it & 1, &sb.abort_flag, f.status)) break;
         ftrace(f, it, 12);
         tcgen05_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const uint32_t o = (k >> 2) * P + (k & 3) * 2; umma_bf16_lohi(d2, sq_lo + o, hi, gh + o, hi, idesc, k); }
+        for (int k = 0; k < 8; ++k) umma_bf16_ts(d2, s_hi + 8 * k, gh + (k >> 2) * P + (k & 3) * 2, hi, idesc, k);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const uint32_t o = (k >> 2) * P + (k & 3) * 2; umma_bf16_lohi(d2, sq_lo + o, hi, gl + o, hi, idesc, 1); }
-        umma_commit(&sb.g1);
-        if (!wait_abort(&sb.sq2, it & 1, &sb.abort_flag, f.status)) break;
-        ftrace(f, it, 13);
-        tcgen05_fence_after();
+        for (int k = 0; k < 8; ++k) umma_bf16_ts(d2, s_hi + 8 * k, gl + (k >> 2) * P + (k & 3) * 2, hi, idesc, 1);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const uint32_t o = (k >> 2) * P + (k & 3) * 2; umma_bf16_lohi(d2, sq_lo + o, hi, gh + o, hi, idesc, 1); }
-        umma_commit(&sb.g2);
+        for (int k = 0; k < 8; ++k) umma_bf16_ts(d2, s_lo + 8 * k, gh + (k >> 2) * P + (k & 3) * 2, hi, idesc, 1);
+        umma_commit(&sb.gdn_done);
+        if (it >= 1 && tile + tile_step < f.total_tiles) { if (!conv_mmas(it + 1)) break; }
+        ftrace(f, it, 11);
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     // ===================== workers =====================
-    const int wi = warp - kFfProducers - 1;
+    const int wi = warp - kFfFirstWorker;
     const int q = warp & 3, hs = wi >> 2;
     const int row = q * 32 + lane;
     const bool leader = wi == 0 && lane == 0;
     const uint32_t swz = static_cast<uint32_t>(row & 7);
     uint8_t* mine = sq + hs * kPanel + row * 128;                // this thread's row of panel hs (64 channels)
-    auto sync_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kFfWorkers * 32) : "memory"); };
+    // Staging is per warp: the 32 rows x 128 B a warp writes are one 4 KB swizzle-aligned slice of panel hs, stored by the
+    // warp's own TMA box (64 channels x 8 x 4 pixels) - the eight worker warps never wait for each other.
+    uint8_t* slice = sq + hs * kPanel + q * 4096;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t t_x = tmem + lane_off + hs * 64, t_g = tmem + 256 + lane_off + hs * 64;
+    const uint32_t t_sh = tmem + 384 + lane_off + hs * 32, t_sl = tmem + 448 + lane_off + hs * 32;
+    const float4* bias4 = reinterpret_cast<const float4*>(s_bias + hs * 64);      // 16-byte broadcast loads: a quarter of the LDS count
+    const float4* beta4 = reinterpret_cast<const float4*>(s_beta + hs * 64);
+    // x is NOT kept in registers between its squares and its normalisation: it stays in its accumulator buffer and is read twice
+    auto squares_of = [&](uint32_t j) -> bool {
+      const uint32_t g = j & 1;
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.acc_full[g], (j >> 1) & 1, &sb.abort_flag, f.status))) return false;
+      tcgen05_fence_after();
+      float xv[64];
+      tmem_ld_32x32(t_x + g * 128, xv);
+      tmem_ld_32x32(t_x + g * 128 + 32, xv + 32);
+      tmem_ld_wait();
+#pragma unroll
+      for (int part = 0; part < 4; ++part) {
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+          const float4 b = bias4[part * 4 + e4];
+          const float a0 = xv[part * 16 + 4 * e4] + b.x, a1 = xv[part * 16 + 4 * e4 + 1] + b.y;
+          const float a2 = xv[part * 16 + 4 * e4 + 2] + b.z, a3 = xv[part * 16 + 4 * e4 + 3] + b.w;
+          split2(a0 * a0, a1 * a1, h[2 * e4], l[2 * e4]);
+          split2(a2 * a2, a3 * a3, h[2 * e4 + 1], l[2 * e4 + 1]);
+        }
+        tmem_st_32x8(t_sh + part * 8, h);
+        tmem_st_32x8(t_sl + part * 8, l);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb.sq_full);
+      return true;
+    };
+    auto stage_lo = [&](const uint32_t* lo_keep, int img, int ty, int tx) {
+      if (lane == 0) tma_store_wait_read();                         // the hi half has left the slice
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz) << 4)) =
+            make_uint4(lo_keep[j * 4], lo_keep[j * 4 + 1], lo_keep[j * 4 + 2], lo_keep[j * 4 + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&map_o, slice, 128 + hs * 64, tx * 8, ty * 16 + q * 4, img);
+        tma_store_commit();
+      }
+    };
     uint32_t it = 0;
-    for (int tile = first_tile; tile < f.total_tiles; tile += tile_step, ++it) {
+    int tile = first_tile;
+    bool ok = tile < f.total_tiles && squares_of(0);
+    uint32_t lo_keep[32];
+    int p_img = 0, p_ty = 0, p_tx = 0;
+    for (; ok && tile < f.total_tiles; tile += tile_step, ++it) {
       int img, ty, tx;
       tile_coords(tile, img, ty, tx);
       const uint32_t g = it & 1;
       if (leader) ftrace(f, it, 0);
-      if (!__all_sync(0xffffffffu, wait_abort(&sb.acc_full[g], (it >> 1) & 1, &sb.abort_flag, f.status))) break;
-      if (leader) ftrace(f, it, 1);
-      tcgen05_fence_after();
-      float xr[64];
-      tmem_ld_32x32(tmem + g * 128 + lane_off + hs * 64, xr);
-      tmem_ld_32x32(tmem + g * 128 + lane_off + hs * 64 + 32, xr + 32);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sb.acc_empty[g]);                // x is in registers: the accumulator buffer is free again
-#pragma unroll
-      for (int j = 0; j < 64; ++j) xr[j] += s_bias[hs * 64 + j];
-      if (leader) ftrace(f, it, 2);
-      if (leader) tma_store_wait_read();                           // previous tile's lo store has left the staging tile
-      sync_workers();
-      if (leader) ftrace(f, it, 3);
-      // squares, hi part
-      uint32_t lo_keep[32];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t h[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { const float a = xr[j * 8 + e * 2], b = xr[j * 8 + e * 2 + 1]; split2(a * a, b * b, h[e], lo_keep[j * 4 + e]); }
-        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sb.sq1);
-      if (leader) ftrace(f, it, 4);
-      if (!__all_sync(0xffffffffu, wait_abort(&sb.g1, it & 1, &sb.abort_flag, f.status))) break;
-      if (leader) ftrace(f, it, 5);
-      // squares, lo part (the MMAs over the hi part have completed)
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz) << 4)) =
-            make_uint4(lo_keep[j * 4], lo_keep[j * 4 + 1], lo_keep[j * 4 + 2], lo_keep[j * 4 + 3]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sb.sq2);
-      if (leader) ftrace(f, it, 6);
-      if (!__all_sync(0xffffffffu, wait_abort(&sb.g2, it & 1, &sb.abort_flag, f.status))) break;
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.gdn_done, it & 1, &sb.abort_flag, f.status))) { ok = false; break; }
       if (leader) ftrace(f, it, 7);
       tcgen05_fence_after();
-      float v0[32], v1[32];
-      tmem_ld_32x32(tmem + 256 + lane_off + hs * 64, v0);
-      tmem_ld_32x32(tmem + 256 + lane_off + hs * 64 + 32, v1);
+      float v[64];
+      tmem_ld_32x32(t_g, v);
+      tmem_ld_32x32(t_g + 32, v + 32);
       tmem_ld_wait();
       tcgen05_fence_before();
-      const float4* beta4 = reinterpret_cast<const float4*>(s_beta + hs * 64);
+      if (it > 0) stage_lo(lo_keep, p_img, p_ty, p_tx);
+      if (leader) ftrace(f, it, 10);
+      if (tile + tile_step < f.total_tiles) ok = squares_of(it + 1);      // the norm columns were read above: GDN(t + 1) may overwrite them
+      if (leader) ftrace(f, it, 4);
+      tcgen05_fence_after();
+      {
+        float xa[64];
+        tmem_ld_32x32(t_x + g * 128, xa);
+        tmem_ld_32x32(t_x + g * 128 + 32, xa + 32);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sb.acc_empty[g]);                // x has been read for the second and last time
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b0 = beta4[j], b1 = beta4[8 + j];
-        v0[j * 4] = xr[j * 4] * rsqrt_approx(v0[j * 4] + b0.x); v0[j * 4 + 1] = xr[j * 4 + 1] * rsqrt_approx(v0[j * 4 + 1] + b0.y);
-        v0[j * 4 + 2] = xr[j * 4 + 2] * rsqrt_approx(v0[j * 4 + 2] + b0.z); v0[j * 4 + 3] = xr[j * 4 + 3] * rsqrt_approx(v0[j * 4 + 3] + b0.w);
-        v1[j * 4] = xr[32 + j * 4] * rsqrt_approx(v1[j * 4] + b1.x); v1[j * 4 + 1] = xr[32 + j * 4 + 1] * rsqrt_approx(v1[j * 4 + 1] + b1.y);
-        v1[j * 4 + 2] = xr[32 + j * 4 + 2] * rsqrt_approx(v1[j * 4 + 2] + b1.z); v1[j * 4 + 3] = xr[32 + j * 4 + 3] * rsqrt_approx(v1[j * 4 + 3] + b1.w);
+        for (int j = 0; j < 16; ++j) {
+          const float4 bi = bias4[j], be = beta4[j];
+          v[4 * j] = (xa[4 * j] + bi.x) * rsqrt_approx(v[4 * j] + be.x);
+          v[4 * j + 1] = (xa[4 * j + 1] + bi.y) * rsqrt_approx(v[4 * j + 1] + be.y);
+          v[4 * j + 2] = (xa[4 * j + 2] + bi.z) * rsqrt_approx(v[4 * j + 2] + be.z);
+          v[4 * j + 3] = (xa[4 * j + 3] + bi.w) * rsqrt_approx(v[4 * j + 3] + be.w);
+        }
       }
-      // output hi tile (the MMAs over the lo squares have completed), TMA store, then the lo tile
+      if (leader) ftrace(f, it, 2);
+      if (lane == 0) tma_store_wait_read();                           // the previous tile's lo half has left the slice
+      __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         uint32_t h[4];
-        const float* src = (j < 4) ? (v0 + j * 8) : (v1 + (j - 4) * 8);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split2(src[e * 2], src[e * 2 + 1], h[e], lo_keep[j * 4 + e]);
+        for (int e = 0; e < 4; ++e) split2(v[j * 8 + e * 2], v[j * 8 + e * 2 + 1], h[e], lo_keep[j * 4 + e]);
         *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
       }
       fence_proxy_async_smem();
-      sync_workers();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&map_o, slice, hs * 64, tx * 8, ty * 16 + q * 4, img);
+        tma_store_commit();
+      }
       if (leader) ftrace(f, it, 8);
-      if (leader) {
-        tma_store_4d(&map_o, sq, 0, tx * 8, ty * 16, img);
-        tma_store_4d(&map_o, sq + kPanel, 64, tx * 8, ty * 16, img);
-        tma_store_commit();
-        tma_store_wait_read();
-      }
-      sync_workers();
-      if (leader) ftrace(f, it, 9);
-      // (the lo half through direct 16-byte global stores instead of a second staging round was tried in round 2: the eight
-      //  stores per thread take 1600 clk - L2-transaction bound - against 500 clk for staging + TMA; reverted)
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz) << 4)) =
-            make_uint4(lo_keep[j * 4], lo_keep[j * 4 + 1], lo_keep[j * 4 + 2], lo_keep[j * 4 + 3]);
-      fence_proxy_async_smem();
-      sync_workers();
-      if (leader) {
-        tma_store_4d(&map_o, sq, 128, tx * 8, ty * 16, img);
-        tma_store_4d(&map_o, sq + kPanel, 192, tx * 8, ty * 16, img);
-        tma_store_commit();
-        ftrace(f, it, 10);
-      }
+      p_img = img; p_ty = ty; p_tx = tx;
     }
-    if (leader) tma_store_wait_all();
+    if (ok && it > 0) stage_lo(lo_keep, p_img, p_ty, p_tx);
+    if (lane == 0) tma_store_wait_all();
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == kFfProducers) tmem_dealloc(tmem, 512);
+  if (warp == kFfIssuerWarp) tmem_dealloc(tmem, 512);
 }
 
 // reference [128, 3, 5, 5] -> bf16 [128][192]: [hi k<64 | lo k<64 | hi k 64..79 | lo k 64..79 | 0], k = (kh * 5 + kw) * 3 + c
@@ -1097,7 +1119,7 @@ int conv_first_gdn_x3(const nic_conv_desc* d, const void* x, const void* w_packe
   if (int rc = encode_2d(&map_w, w_packed, 192, 128, 64, 128)) return rc;
   if (int rc = encode_2d(&map_g, gamma_packed, 128, 256, 64, 128)) return rc;
   if (int rc = encode_image_patch(&map_img, x, d->n, 3, d->h_in, d->w_in, kPatchW, kPatchH)) return rc;
-  if (int rc = encode_nhwc(&map_o, y, d->n, d->h_out, d->w_out, 256, 8, 16, 1, 2)) return rc;
+  if (int rc = encode_nhwc(&map_o, y, d->n, d->h_out, d->w_out, 256, 8, 4, 1, 2)) return rc;      // one store box per worker warp
   static bool attr_set = false;
   if (!attr_set) {
     if (int rc = check_cuda(cudaFuncSetAttribute(first_fused_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;

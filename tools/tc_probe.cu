@@ -522,8 +522,114 @@ static void run_tma_patch(EncodeTiledFn enc, int pw, int ph, int stride, int dep
   cudaFree(d); cudaFree(dl); cudaFree(ds);
 }
 
+// -------------------------------------------------------------------------------------------------
+// T9: A operand in tensor memory (tcgen05.st of packed bf16x2, then the [a_tmem] form of tcgen05.mma), B from shared memory
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mma_ts_probe_kernel(const __nv_bfloat16* A, const __nv_bfloat16* B, float* D, int iters, long long* cycles,
+                                                           int* status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 128 * 64; i += 128) {
+    const int r = i / 64, k = i % 64;
+    *reinterpret_cast<__nv_bfloat16*>(sB + sw128_offset(r, k)) = B[i];
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_base, 256); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tm = tmem_base;
+  {
+    uint32_t r[32];
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(A + tid * 64);
+    for (int j = 0; j < 32; ++j) r[j] = row[j];          // K elements 2j (low half), 2j + 1 (high half)
+    tmem_st_32x32(tm + 128 + (static_cast<uint32_t>(warp * 32) << 16), r);
+    tmem_st_wait();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 1 && elect_one()) {
+    const uint32_t idesc = umma_idesc_bf16(128, 128);
+    const uint32_t b_lo = umma_desc_lo(smem_u32(sB)), b_hi = umma_desc_hi(1024);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_ts(tm, tm + 128 + k * 8, b_lo + 2 * k, b_hi, idesc, k > 0);
+    umma_commit(&bar);
+  }
+  __syncwarp();
+  bool ok = mbar_wait(&bar, 0, 1u << 22);
+  if (!ok) { if (tid == 0) *status = 1; }
+  tcgen05_fence_after();
+  if (ok) {
+    for (int c = 0; c < 128; c += 32) {
+      float v[32];
+      tmem_ld_32x32(tm + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+      tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) D[(warp * 32 + lane) * 128 + c + j] = v[j];
+    }
+  }
+  // rate: `iters` groups of 4 back-to-back TS MMAs
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (ok && warp == 1 && elect_one()) {
+    const uint32_t idesc = umma_idesc_bf16(128, 128);
+    const uint32_t b_lo = umma_desc_lo(smem_u32(sB)), b_hi = umma_desc_hi(1024);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16_ts(tm, tm + 128 + k * 8, b_lo + 2 * k, b_hi, idesc, 1);
+    }
+    umma_commit(&bar);
+    if (!mbar_wait(&bar, 1, 1u << 24)) *status = 2;
+    cycles[0] = clock64() - t0;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 256);
+}
+
+static int run_mma_ts_probe() {
+  std::vector<__nv_bfloat16> hA(128 * 64), hB(128 * 64);
+  srand(4321);
+  for (auto& v : hA) v = __float2bfloat16((rand() % 17 - 8) / 8.0f);
+  for (auto& v : hB) v = __float2bfloat16((rand() % 13 - 6) / 4.0f);
+  __nv_bfloat16 *dA, *dB; float* dD; int* dS; long long* dC;
+  CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dD, 128 * 128 * 4)); CK(cudaMalloc(&dS, 4));
+  CK(cudaMalloc(&dC, 8));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0, 128 * 128 * 4)); CK(cudaMemset(dS, 0, 4)); CK(cudaMemset(dC, 0, 8));
+  const int smem = 16 * 1024 + 1024, iters = 256;
+  mma_ts_probe_kernel<<<1, 128, smem>>>(dA, dB, dD, iters, dC, dS);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  TS probe: CUDA error %s\n", cudaGetErrorString(e)); exit(3); }
+  std::vector<float> hD(128 * 128); int st; long long cyc;
+  CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+  double maxerr = 0; int bad = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < 128; ++n) {
+      double ref = 0;
+      for (int k = 0; k < 64; ++k) ref += bf2f(hA[m * 64 + k]) * bf2f(hB[n * 64 + k]);
+      const double err = fabs(ref - hD[m * 128 + n]);
+      if (err > maxerr) maxerr = err;
+      if (err > 1e-3) ++bad;
+    }
+  printf("  A from TMEM (packed bf16x2 columns): status=%d bad=%d/16384 maxerr=%.4g  %s;  %.1f clk per M128 N128 K16 MMA\n", st, bad, maxerr,
+         (bad == 0 && st == 0) ? "OK" : "MISMATCH", (double)cyc / (iters * 4));
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dS); cudaFree(dC);
+  return bad == 0 && st == 0;
+}
+
 int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "t8")) { run_mma_walk(); return 0; }
+  if (argc > 1 && !strcmp(argv[1], "t9")) { printf("T9 A operand in tensor memory\n"); return run_mma_ts_probe() ? 0 : 1; }
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s sm_%d%d, %d SMs, smem/block optin %zu\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount, prop.sharedMemPerBlockOptin);
   EncodeTiledFn enc = get_encode();

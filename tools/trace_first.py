@@ -23,8 +23,8 @@ op.run(x, B, 512, 768, "bf16x3", in_layout=LAYOUT_NCHW)
 torch.cuda.synchronize()
 lib.nic_debug_set_trace(None)
 t = buf.cpu().reshape(148, 32, 16)
-names = ["w:top", "w:acc_full", "w:x_loaded", "w:stage_free", "w:sq1", "w:g1", "w:sq2", "w:g2", "w:hi_staged", "w:hi_read", "w:lo_stored",
-         "m:conv_next", "m:sq1_seen", "m:sq2_seen", "p:a_full"]
+names = ["w:top", "-", "w:normalised", "-", "w:squares_next", "-", "-", "w:gdn_done", "w:hi_stored", "-", "w:lo_prev_stored",
+         "m:conv_next", "m:sq_seen", "p:patch_ready", "p:a_full", "p:a_empty_seen"]
 for cta in (0, 77):
     base = int(t[cta, 0, 0])
     print(f"CTA {cta}")
