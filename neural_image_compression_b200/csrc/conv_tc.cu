@@ -147,6 +147,20 @@ int encode_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, int c, in
   return NIC_OK;
 }
 
+// NHWC bf16 tensor, boxes of 32 channels (64-byte rows, SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3) x box_w x box_h pixels
+int encode_nhwc_c32(CUtensorMap* m, const void* base, int n, int h, int w, int c, int box_w, int box_h) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled(nhwc %dx%dx%dx%d, 32-channel box %dx%d) failed: %d", n, h, w, c, box_w, box_h, (int)r);
+  return NIC_OK;
+}
+
 
 namespace {
 

@@ -54,6 +54,25 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// Packed fp32 pairs (FADD2 / FMUL2, sm_100): one issue slot for two IEEE round-to-nearest operations - the element-wise
+// stages of the first-layer kernel are bound by issue slots and dependent-instruction latency, not by FLOPs.
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tadd.rn.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void mul2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tmul.rn.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+// split2 with the subtraction as one packed operation
+__device__ __forceinline__ void split2p(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  add2(a, b, -__uint_as_float(hi << 16), -__uint_as_float(hi & 0xffff0000u));
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a, b);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // ---------------------------------------------------------------------------------------------
 // GDN / IGDN, c = 128, on a flat list of pixels: x [npix][128] f32 -> y [npix][256] bf16 = [hi(128) | lo(128)].
 // One persistent CTA per SM; tile = 128 pixels; worker thread <-> (pixel row, 64-channel half hs).
@@ -674,9 +693,10 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 // activation, one kernel.  The two-kernel form (conv_first_x3_kernel + gdn_x3_kernel) moves 2.4 GB through HBM per 16 images
 // (f32 scratch out and in, pairs out); this one writes the 0.8 GB of pairs only.
 //
-// 16 warps in four groups of four (the unit of setmaxnreg): 0-3 producers (patch by TMA, im2col with hi/lo split, one pixel row
-// per thread, one A stage), 4 MMA issuer (5-7 idle), 8-15 workers (thread <-> pixel row x 64-channel half).  The producers and
-// the issuer give registers back (64 each) so that the workers run with 192.
+// 24 warps in six groups of four (the unit of setmaxnreg): 0-3 producers (patch by TMA, im2col with hi/lo split, one pixel row
+// per thread, one A stage), 4 MMA issuer (5-7 idle), 8-23 workers (thread <-> pixel row x 32-channel quarter; four worker warps
+// per scheduler hide each other's TMEM / MUFU / shared-memory latencies - with eight the same chain took 5.7k clk per tile at 22 %
+// issue utilisation).  The producers and the issuer group give registers back (64) so that the workers run with 88 (the pool is what the CTA was launched with: 768 x 80).
 //
 // Tensor memory (512 columns): conv accumulators X0, X1 (2 x 128), GDN accumulator (128), SQUARES (128: 64 columns of packed
 // bf16x2 hi, 64 of lo).  The squares are the A operand of the 24 GDN MMAs straight from tensor memory (the [a_tmem] form of
@@ -689,7 +709,7 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 // History (16 images, 512 x 768): squares through shared memory, one tile in the worker stage at a time 383 us (a chain of
 // 8.2k clk per tile) -> squares in TMEM 291 -> per-warp staging / stores 260 -> this layout (see profiles/README.md).
 // ---------------------------------------------------------------------------------------------
-constexpr int kFfProducers = 4, kFfIssuerWarp = 4, kFfFirstWorker = 8, kFfWorkers = 8;
+constexpr int kFfProducers = 4, kFfIssuerWarp = 4, kFfFirstWorker = 8, kFfWorkers = 16;
 constexpr int kFfThreads = (kFfFirstWorker + kFfWorkers) * 32;
 
 struct FirstFusedParams {
@@ -851,41 +871,40 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
-    // ===================== workers =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    // ===================== workers: thread <-> pixel row x 32-channel quarter =====================
     const int wi = warp - kFfFirstWorker;
-    const int q = warp & 3, hs = wi >> 2;
-    const int row = q * 32 + lane;
+    const int q = warp & 3, cq = wi >> 2;
     const bool leader = wi == 0 && lane == 0;
-    const uint32_t swz = static_cast<uint32_t>(row & 7);
-    uint8_t* mine = sq + hs * kPanel + row * 128;                // this thread's row of panel hs (64 channels)
-    // Staging is per warp: the 32 rows x 128 B a warp writes are one 4 KB swizzle-aligned slice of panel hs, stored by the
-    // warp's own TMA box (64 channels x 8 x 4 pixels) - the eight worker warps never wait for each other.
-    uint8_t* slice = sq + hs * kPanel + q * 4096;
+    // Staging is per warp: 32 rows x 64 B (32 channels), a 2 KB slice in the 64-byte swizzle layout, stored by the warp's own TMA
+    // box (32 channels x 8 x 4 pixels) - the sixteen worker warps never wait for each other.
+    uint8_t* slice = sq + wi * 2048;
+    uint8_t* mine = slice + lane * 64;
+    const uint32_t swz = static_cast<uint32_t>(lane >> 1) & 3u;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t t_x = tmem + lane_off + hs * 64, t_g = tmem + 256 + lane_off + hs * 64;
-    const uint32_t t_sh = tmem + 384 + lane_off + hs * 32, t_sl = tmem + 448 + lane_off + hs * 32;
-    const float4* bias4 = reinterpret_cast<const float4*>(s_bias + hs * 64);      // 16-byte broadcast loads: a quarter of the LDS count
-    const float4* beta4 = reinterpret_cast<const float4*>(s_beta + hs * 64);
+    const uint32_t t_x = tmem + lane_off + cq * 32, t_g = tmem + 256 + lane_off + cq * 32;
+    const uint32_t t_sh = tmem + 384 + lane_off + cq * 16, t_sl = tmem + 448 + lane_off + cq * 16;
+    const float4* bias4 = reinterpret_cast<const float4*>(s_bias + cq * 32);      // 16-byte broadcast loads
+    const float4* beta4 = reinterpret_cast<const float4*>(s_beta + cq * 32);
     // x is NOT kept in registers between its squares and its normalisation: it stays in its accumulator buffer and is read twice
     auto squares_of = [&](uint32_t j) -> bool {
       const uint32_t g = j & 1;
       if (!__all_sync(0xffffffffu, wait_abort(&sb.acc_full[g], (j >> 1) & 1, &sb.abort_flag, f.status))) return false;
       tcgen05_fence_after();
-      float xv[64];
-      tmem_ld_32x32(t_x + g * 128, xv);
-      tmem_ld_32x32(t_x + g * 128 + 32, xv + 32);
-      tmem_ld_wait();
 #pragma unroll
-      for (int part = 0; part < 4; ++part) {
+      for (int part = 0; part < 2; ++part) {
+        float xv[16];
+        tmem_ld_32x16(t_x + g * 128 + part * 16, xv);
+        tmem_ld_wait();
         uint32_t h[8], l[8];
 #pragma unroll
         for (int e4 = 0; e4 < 4; ++e4) {
           const float4 b = bias4[part * 4 + e4];
-          const float a0 = xv[part * 16 + 4 * e4] + b.x, a1 = xv[part * 16 + 4 * e4 + 1] + b.y;
-          const float a2 = xv[part * 16 + 4 * e4 + 2] + b.z, a3 = xv[part * 16 + 4 * e4 + 3] + b.w;
-          split2(a0 * a0, a1 * a1, h[2 * e4], l[2 * e4]);
-          split2(a2 * a2, a3 * a3, h[2 * e4 + 1], l[2 * e4 + 1]);
+          float a0 = xv[4 * e4], a1 = xv[4 * e4 + 1], a2 = xv[4 * e4 + 2], a3 = xv[4 * e4 + 3];
+          add2(a0, a1, b.x, b.y); add2(a2, a3, b.z, b.w);
+          mul2(a0, a1, a0, a1); mul2(a2, a3, a2, a3);
+          split2p(a0, a1, h[2 * e4], l[2 * e4]);
+          split2p(a2, a3, h[2 * e4 + 1], l[2 * e4 + 1]);
         }
         tmem_st_32x8(t_sh + part * 8, h);
         tmem_st_32x8(t_sl + part * 8, l);
@@ -900,20 +919,20 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       if (lane == 0) tma_store_wait_read();                         // the hi half has left the slice
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz) << 4)) =
             make_uint4(lo_keep[j * 4], lo_keep[j * 4 + 1], lo_keep[j * 4 + 2], lo_keep[j * 4 + 3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_4d(&map_o, slice, 128 + hs * 64, tx * 8, ty * 16 + q * 4, img);
+        tma_store_4d(&map_o, slice, 128 + cq * 32, tx * 8, ty * 16 + q * 4, img);
         tma_store_commit();
       }
     };
     uint32_t it = 0;
     int tile = first_tile;
     bool ok = tile < f.total_tiles && squares_of(0);
-    uint32_t lo_keep[32];
+    uint32_t lo_keep[16];
     int p_img = 0, p_ty = 0, p_tx = 0;
     for (; ok && tile < f.total_tiles; tile += tile_step, ++it) {
       int img, ty, tx;
@@ -923,9 +942,8 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       if (!__all_sync(0xffffffffu, wait_abort(&sb.gdn_done, it & 1, &sb.abort_flag, f.status))) { ok = false; break; }
       if (leader) ftrace(f, it, 7);
       tcgen05_fence_after();
-      float v[64];
+      float v[32];
       tmem_ld_32x32(t_g, v);
-      tmem_ld_32x32(t_g + 32, v + 32);
       tmem_ld_wait();
       tcgen05_fence_before();
       if (it > 0) stage_lo(lo_keep, p_img, p_ty, p_tx);
@@ -933,37 +951,41 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       if (tile + tile_step < f.total_tiles) ok = squares_of(it + 1);      // the norm columns were read above: GDN(t + 1) may overwrite them
       if (leader) ftrace(f, it, 4);
       tcgen05_fence_after();
-      {
-        float xa[64];
-        tmem_ld_32x32(t_x + g * 128, xa);
-        tmem_ld_32x32(t_x + g * 128 + 32, xa + 32);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sb.acc_empty[g]);                // x has been read for the second and last time
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 bi = bias4[j], be = beta4[j];
-          v[4 * j] = (xa[4 * j] + bi.x) * rsqrt_approx(v[4 * j] + be.x);
-          v[4 * j + 1] = (xa[4 * j + 1] + bi.y) * rsqrt_approx(v[4 * j + 1] + be.y);
-          v[4 * j + 2] = (xa[4 * j + 2] + bi.z) * rsqrt_approx(v[4 * j + 2] + be.z);
-          v[4 * j + 3] = (xa[4 * j + 3] + bi.w) * rsqrt_approx(v[4 * j + 3] + be.w);
+      for (int part = 0; part < 2; ++part) {
+        float xa[16];
+        tmem_ld_32x16(t_x + g * 128 + part * 16, xa);
+        tmem_ld_wait();
+        if (part == 1) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sb.acc_empty[g]);              // x has been read for the second and last time
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 bi = bias4[part * 4 + j], be = beta4[part * 4 + j];
+          float* vv = v + part * 16 + 4 * j;
+          float x0 = xa[4 * j], x1 = xa[4 * j + 1], x2 = xa[4 * j + 2], x3 = xa[4 * j + 3];
+          add2(x0, x1, bi.x, bi.y); add2(x2, x3, bi.z, bi.w);
+          add2(vv[0], vv[1], be.x, be.y); add2(vv[2], vv[3], be.z, be.w);
+          mul2(x0, x1, rsqrt_approx(vv[0]), rsqrt_approx(vv[1])); mul2(x2, x3, rsqrt_approx(vv[2]), rsqrt_approx(vv[3]));
+          vv[0] = x0; vv[1] = x1; vv[2] = x2; vv[3] = x3;
         }
       }
       if (leader) ftrace(f, it, 2);
       if (lane == 0) tma_store_wait_read();                           // the previous tile's lo half has left the slice
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         uint32_t h[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split2(v[j * 8 + e * 2], v[j * 8 + e * 2 + 1], h[e], lo_keep[j * 4 + e]);
+        for (int e = 0; e < 4; ++e) split2p(v[j * 8 + e * 2], v[j * 8 + e * 2 + 1], h[e], lo_keep[j * 4 + e]);
         *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_4d(&map_o, slice, hs * 64, tx * 8, ty * 16 + q * 4, img);
+        tma_store_4d(&map_o, slice, cq * 32, tx * 8, ty * 16 + q * 4, img);
         tma_store_commit();
       }
       if (leader) ftrace(f, it, 8);
@@ -1119,7 +1141,7 @@ int conv_first_gdn_x3(const nic_conv_desc* d, const void* x, const void* w_packe
   if (int rc = encode_2d(&map_w, w_packed, 192, 128, 64, 128)) return rc;
   if (int rc = encode_2d(&map_g, gamma_packed, 128, 256, 64, 128)) return rc;
   if (int rc = encode_image_patch(&map_img, x, d->n, 3, d->h_in, d->w_in, kPatchW, kPatchH)) return rc;
-  if (int rc = encode_nhwc(&map_o, y, d->n, d->h_out, d->w_out, 256, 8, 4, 1, 2)) return rc;      // one store box per worker warp
+  if (int rc = encode_nhwc_c32(&map_o, y, d->n, d->h_out, d->w_out, 256, 8, 4)) return rc;      // one store box per worker warp
   static bool attr_set = false;
   if (!attr_set) {
     if (int rc = check_cuda(cudaFuncSetAttribute(first_fused_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
