@@ -723,7 +723,7 @@ struct FirstFusedParams {
 };
 
 struct __align__(8) FirstFusedBarriers {
-  uint64_t patch_full[2], a_full, a_empty, w_full, gamma_full, acc_full[2], acc_empty[2], sq_full, gdn_done;
+  uint64_t patch_full[2], a_full, a_empty, w_full, w_patched, gamma_full, acc_full[2], acc_empty[2], sq_full, gdn_done;
   uint32_t tmem_base;
   volatile int abort_flag;
 };
@@ -738,20 +738,19 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ FirstFusedBarriers sb;
-  __shared__ __align__(16) float s_bias[128];
   __shared__ __align__(16) float s_beta[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&sb.patch_full[i], 1); mbar_init(&sb.acc_full[i], 1); mbar_init(&sb.acc_empty[i], kFfWorkers); }
     mbar_init(&sb.a_full, kFfProducers * 32); mbar_init(&sb.a_empty, 1); mbar_init(&sb.w_full, 1); mbar_init(&sb.gamma_full, 1);
-    mbar_init(&sb.sq_full, kFfWorkers); mbar_init(&sb.gdn_done, 1);
+    mbar_init(&sb.sq_full, kFfWorkers); mbar_init(&sb.gdn_done, 1); mbar_init(&sb.w_patched, 128);
     sb.abort_flag = 0;
     fence_barrier_init();
   }
   if (warp == kFfIssuerWarp) { tmem_alloc(&sb.tmem_base, 512); tmem_relinquish(); }
   pdl_wait();
-  if (tid < 128) { s_bias[tid] = f.bias[tid]; s_beta[tid] = f.beta[tid]; }
+  if (tid < 128) s_beta[tid] = f.beta[tid];
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -763,6 +762,22 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     tx = tile % f.tiles_x; tile /= f.tiles_x; ty = tile % f.tiles_y; img = tile / f.tiles_y;
   };
 
+  if (warp >= kFfFirstWorker && warp < kFfFirstWorker + 4) {
+    // The bias rides in the conv: column k = 75 of the im2col operand is the constant 1 and column 75 of W holds bias hi / lo
+    // (tail panel: [hi k 64..79 | lo k 64..79]), so the accumulator already contains x + bias (to the same 2^-17 relative grade
+    // as every other product) and nobody adds it element by element.  128 threads patch the resident W tile once.
+    const int co = tid - kFfFirstWorker * 32;
+    if (wait_abort(&sb.w_full, 0, &sb.abort_flag, f.status)) {
+      uint8_t* wrow = smem + f.off_w + 2 * kPanel + co * 128;
+      const uint32_t sw = static_cast<uint32_t>(co & 7);
+      const float b = f.bias[co];
+      const __nv_bfloat16 bh = __float2bfloat16_rn(b), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+      *reinterpret_cast<__nv_bfloat16*>(wrow + ((1u ^ sw) << 4) + 6) = bh;       // hi part, column 75 - 64 = 11: chunk 1, byte 6
+      *reinterpret_cast<__nv_bfloat16*>(wrow + ((3u ^ sw) << 4) + 6) = bl;       // lo part, column 16 + 11 = 27: chunk 3, byte 6
+      fence_proxy_async_smem();
+    }
+    mbar_arrive(&sb.w_patched);
+  }
   if (warp < kFfFirstWorker) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp < kFfProducers) {
@@ -787,20 +802,14 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         if (!__all_sync(0xffffffffu, wait_abort(&sb.a_empty, (it & 1) ^ 1, &sb.abort_flag, f.status))) break;
         if (tid == 0) ftrace(f, it, 15);
         const float* src = reinterpret_cast<const float*>(patch + st * kPatchStride) + (2 * g) * kPatchW + 2 * c8 + 2;
-#pragma unroll
-        for (int ch = 0; ch < 10; ++ch) {
+        // k = kh * 15 + kw * 3 + c: the 15 values of one filter row come from three 5-float runs (8-byte aligned: two LDS.64 + one
+        // LDS.32 each, conflict-free - scalar loads at this stride-2 pattern are 2-way conflicted); column 75 is the constant 1 that
+        // multiplies the bias row of W (see the prologue), 76..79 are zero.  Chunks of 8 k are emitted as soon as they are complete.
+        float kv[80];
+        auto emit = [&](int ch) {
           uint32_t h[4], l[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float v2[2];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int k = ch * 8 + e * 2 + hh;
-              if (k < 75) { const int tap = k / 3, c = k % 3; v2[hh] = src[c * kPatchPlane + (tap / 5) * kPatchW + (tap % 5)]; }
-              else v2[hh] = 0.f;
-            }
-            split2(v2[0], v2[1], h[e], l[e]);
-          }
+          for (int e = 0; e < 4; ++e) split2(kv[ch * 8 + 2 * e], kv[ch * 8 + 2 * e + 1], h[e], l[e]);
           if (ch < 8) {
             const uint32_t off = (static_cast<uint32_t>(ch) ^ swz) << 4;
             *reinterpret_cast<uint4*>(dst + off) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -810,6 +819,19 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             *reinterpret_cast<uint4*>(dst + 2 * kPanel + offh) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(dst + 2 * kPanel + offl) = make_uint4(l[0], l[1], l[2], l[3]);
           }
+        };
+        kv[75] = 1.f; kv[76] = 0.f; kv[77] = 0.f; kv[78] = 0.f; kv[79] = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 5; ++kh) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float* pr = src + c * kPatchPlane + kh * kPatchW;
+            const float2 a = *reinterpret_cast<const float2*>(pr), b = *reinterpret_cast<const float2*>(pr + 2);
+            kv[kh * 15 + c] = a.x; kv[kh * 15 + 3 + c] = a.y; kv[kh * 15 + 6 + c] = b.x; kv[kh * 15 + 9 + c] = b.y; kv[kh * 15 + 12 + c] = pr[4];
+          }
+#pragma unroll
+          for (int ch = 0; ch < 10; ++ch)
+            if (ch * 8 + 8 <= (kh + 1) * 15 + (kh == 4 ? 5 : 0) && ch * 8 + 8 > kh * 15) emit(ch);
         }
         fence_proxy_async_smem();
         mbar_arrive(&sb.a_full);
@@ -827,7 +849,7 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
       const uint32_t ab = umma_desc_lo(smem_u32(smem + f.off_a)), w_lo = umma_desc_lo(smem_u32(smem + f.off_w));
       const uint32_t gh = umma_desc_lo(smem_u32(smem + f.off_gamma)), gl = umma_desc_lo(smem_u32(smem + f.off_gamma + 2 * kPanel));
       constexpr uint32_t P = kPanel >> 4;
-      bool ok = wait_abort(&sb.w_full, 0, &sb.abort_flag, f.status) && wait_abort(&sb.gamma_full, 0, &sb.abort_flag, f.status);
+      bool ok = wait_abort(&sb.w_patched, 0, &sb.abort_flag, f.status) && wait_abort(&sb.gamma_full, 0, &sb.abort_flag, f.status);
       const uint32_t d2 = tmem + 256, s_hi = tmem + 384, s_lo = tmem + 448;
       auto conv_mmas = [&](uint32_t it) -> bool {
         const uint32_t g = it & 1;
@@ -884,7 +906,6 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t t_x = tmem + lane_off + cq * 32, t_g = tmem + 256 + lane_off + cq * 32;
     const uint32_t t_sh = tmem + 384 + lane_off + cq * 16, t_sl = tmem + 448 + lane_off + cq * 16;
-    const float4* bias4 = reinterpret_cast<const float4*>(s_bias + cq * 32);      // 16-byte broadcast loads
     const float4* beta4 = reinterpret_cast<const float4*>(s_beta + cq * 32);
     // x is NOT kept in registers between its squares and its normalisation: it stays in its accumulator buffer and is read twice
     auto squares_of = [&](uint32_t j) -> bool {
@@ -899,9 +920,7 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         uint32_t h[8], l[8];
 #pragma unroll
         for (int e4 = 0; e4 < 4; ++e4) {
-          const float4 b = bias4[part * 4 + e4];
           float a0 = xv[4 * e4], a1 = xv[4 * e4 + 1], a2 = xv[4 * e4 + 2], a3 = xv[4 * e4 + 3];
-          add2(a0, a1, b.x, b.y); add2(a2, a3, b.z, b.w);
           mul2(a0, a1, a0, a1); mul2(a2, a3, a2, a3);
           split2p(a0, a1, h[2 * e4], l[2 * e4]);
           split2p(a2, a3, h[2 * e4 + 1], l[2 * e4 + 1]);
@@ -963,10 +982,9 @@ first_fused_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 bi = bias4[part * 4 + j], be = beta4[part * 4 + j];
+          const float4 be = beta4[part * 4 + j];
           float* vv = v + part * 16 + 4 * j;
           float x0 = xa[4 * j], x1 = xa[4 * j + 1], x2 = xa[4 * j + 2], x3 = xa[4 * j + 3];
-          add2(x0, x1, bi.x, bi.y); add2(x2, x3, bi.z, bi.w);
           add2(vv[0], vv[1], be.x, be.y); add2(vv[2], vv[3], be.z, be.w);
           mul2(x0, x1, rsqrt_approx(vv[0]), rsqrt_approx(vv[1])); mul2(x2, x3, rsqrt_approx(vv[2]), rsqrt_approx(vv[3]));
           vv[0] = x0; vv[1] = x1; vv[2] = x2; vv[3] = x3;
