@@ -147,6 +147,21 @@ int encode_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, int c, in
   return NIC_OK;
 }
 
+// 2-D row-major bf16 tensor, boxes of 32 elements (64-byte rows, SWIZZLE_64B) x box_rows
+int encode_2d_c32(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(NIC_E_CUDA, "cuTensorMapEncodeTiled(2d %llu x %llu, 32-column box x %u) failed: %d", (unsigned long long)inner,
+                                     (unsigned long long)rows, box_rows, (int)r);
+  return NIC_OK;
+}
+
 // NHWC bf16 tensor, boxes of 32 channels (64-byte rows, SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3) x box_w x box_h pixels
 int encode_nhwc_c32(CUtensorMap* m, const void* base, int n, int h, int w, int c, int box_w, int box_h) {
   EncodeTiledFn enc = get_encode();

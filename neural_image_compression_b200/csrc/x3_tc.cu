@@ -274,6 +274,220 @@ gdn_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------
+// GDN / IGDN, c = 128, bf16 hi/lo PAIR input (what the conv engine writes), second generation: the structure of the first-layer
+// kernel below, measured there first.
+//   * squares live in TENSOR MEMORY (128 columns of packed bf16x2: hi | lo) and are the A operand of the 24 MMAs ([a_tmem]
+//     form) - no shared-memory writes for them, the MMAs read only gamma through the shared-memory port;
+//   * 16 worker warps (thread <-> pixel row x 32-channel quarter), no barrier between them: per-warp 2 KB staging slices in the
+//     64-byte swizzle layout, each drained by the warp's own TMA store;
+//   * x is read from its shared-memory tile ONCE, into registers, so the tile buffer goes back to the loader a whole iteration
+//     before the next-but-one tile is needed (the first generation held it until its stores had been read: its loads were
+//     issued ~half an iteration ahead and their latency was exposed - 7.0k clk per tile against an HBM floor of 5.7k);
+//   * per tile t: lo half of t - 1 -> slice -> TMA store | norm(t) from TMEM | y = x * (r)sqrt(beta + norm) | hi half -> slice
+//     -> TMA store | x(t + 1) from its tile, squares -> TMEM, GDN(t + 1) starts.
+// Shared memory: gamma hi / lo 64 KB + two 64 KB x tiles + 32 KB staging.  20 warps: loader, MMA issuer (+ 2 idle), 16 workers;
+// the first group gives registers back (56) so that the workers run with 104.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGtFirstWorker = 4, kGtWorkers = 16;
+constexpr int kGtThreads = (kGtFirstWorker + kGtWorkers) * 32;
+
+struct __align__(8) GdnTsBarriers {
+  uint64_t x_full[2], x_empty[2], gamma_full, sq_full, gdn_done;
+  uint32_t tmem_base;
+  volatile int abort_flag;
+};
+
+__global__ void __launch_bounds__(kGtThreads, 1)
+gdn_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_o,
+              const __grid_constant__ GdnX3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* gam = smem;                             // g_hi panel 0, 1 | g_lo panel 0, 1   ([128 out][64 in] bf16 each)
+  uint8_t* bufs = smem + 4 * kPanel;               // two x tiles of 4 panels: [hi 0..63 | lo 0..63 | hi 64..127 | lo 64..127]
+  uint8_t* stg = smem + 12 * kPanel;               // 16 staging slices of 32 rows x 64 B
+  __shared__ GdnTsBarriers sb;
+  __shared__ __align__(16) float s_beta[128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&sb.x_full[i], 1); mbar_init(&sb.x_empty[i], kGtWorkers); }
+    mbar_init(&sb.gamma_full, 1); mbar_init(&sb.sq_full, kGtWorkers); mbar_init(&sb.gdn_done, 1);
+    sb.abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&sb.tmem_base, 256); tmem_relinquish(); }
+  pdl_wait();                                       // the conv that wrote x has completed
+  if (threadIdx.x < 128) s_beta[threadIdx.x] = p.beta[threadIdx.x];
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = sb.tmem_base;              // columns: squares hi 0..63, lo 64..127, norm 128..255
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+
+  if (warp < kGtFirstWorker) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0 && lane == 0) {
+      // ===================== loader =====================
+      tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_g); tma_prefetch_desc(&map_o);
+      mbar_expect_tx(&sb.gamma_full, 4 * kPanel);
+      tma_load_2d(gam, &map_g, &sb.gamma_full, 0, 0);
+      tma_load_2d(gam + kPanel, &map_g, &sb.gamma_full, 64, 0);
+      tma_load_2d(gam + 2 * kPanel, &map_g, &sb.gamma_full, 0, 128);
+      tma_load_2d(gam + 3 * kPanel, &map_g, &sb.gamma_full, 64, 128);
+      uint32_t it = 0;
+      for (int tile = first_tile; tile < p.ntiles; tile += tile_step, ++it) {
+        const uint32_t b = it & 1;
+        if (!wait_abort(&sb.x_empty[b], ((it >> 1) & 1) ^ 1, &sb.abort_flag, p.status)) break;
+        mbar_expect_tx(&sb.x_full[b], 4 * kPanel);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tma_load_2d(bufs + (b * 4 + k) * kPanel, &map_x, &sb.x_full[b], (k >> 1) * 64 + (k & 1) * 128, tile * 128);
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      const uint32_t hi = umma_desc_hi(1024);
+      const uint32_t gh = umma_desc_lo(smem_u32(gam)), gl = umma_desc_lo(smem_u32(gam + 2 * kPanel));
+      constexpr uint32_t P = kPanel >> 4;
+      const uint32_t s_hi = tmem, s_lo = tmem + 64, d = tmem + 128;
+      bool ok = wait_abort(&sb.gamma_full, 0, &sb.abort_flag, p.status);
+      uint32_t it = 0;
+      for (int tile = first_tile; tile < p.ntiles && ok; tile += tile_step, ++it) {
+        if (!wait_abort(&sb.sq_full, it & 1, &sb.abort_flag, p.status)) break;
+        gtrace(p, it, 5);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16_ts(d, s_hi + 8 * k, gh + (k >> 2) * P + (k & 3) * 2, hi, idesc, k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16_ts(d, s_hi + 8 * k, gl + (k >> 2) * P + (k & 3) * 2, hi, idesc, 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16_ts(d, s_lo + 8 * k, gh + (k >> 2) * P + (k & 3) * 2, hi, idesc, 1);
+        umma_commit(&sb.gdn_done);
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ===================== workers =====================
+    const int wi = warp - kGtFirstWorker;
+    const int q = warp & 3, cq = wi >> 2;
+    const int row = q * 32 + lane;
+    const bool leader = wi == 0 && lane == 0;
+    uint8_t* slice = stg + wi * 2048;
+    uint8_t* mine = slice + lane * 64;
+    const uint32_t swz64 = static_cast<uint32_t>(lane >> 1) & 3u;
+    const uint32_t swz = static_cast<uint32_t>(row & 7);
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t t_sh = tmem + lane_off + cq * 16, t_sl = tmem + 64 + lane_off + cq * 16, t_g = tmem + 128 + lane_off + cq * 32;
+    const float4* beta4 = reinterpret_cast<const float4*>(s_beta + cq * 32);
+    float xr[32];
+    // x(j) from its tile into registers (the tile goes back to the loader), squares -> tensor memory
+    auto squares_of = [&](uint32_t j) -> bool {
+      const uint32_t b = j & 1;
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.x_full[b], (j >> 1) & 1, &sb.abort_flag, p.status))) return false;
+      const uint8_t* xh = bufs + (b * 4 + 2 * (cq >> 1)) * kPanel + row * 128;
+      const uint8_t* xl = xh + kPanel;
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const uint32_t off = ((static_cast<uint32_t>(4 * (cq & 1) + j4)) ^ swz) << 4;
+        const uint4 h = *reinterpret_cast<const uint4*>(xh + off), l = *reinterpret_cast<const uint4*>(xl + off);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float a0 = __uint_as_float(hw[e] << 16), a1 = __uint_as_float(hw[e] & 0xffff0000u);
+          add2(a0, a1, __uint_as_float(lw[e] << 16), __uint_as_float(lw[e] & 0xffff0000u));
+          xr[j4 * 8 + e * 2] = a0; xr[j4 * 8 + e * 2 + 1] = a1;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb.x_empty[b]);
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float a0 = xr[part * 16 + 2 * e], a1 = xr[part * 16 + 2 * e + 1];
+          mul2(a0, a1, a0, a1);
+          split2p(a0, a1, h[e], l[e]);
+        }
+        tmem_st_32x8(t_sh + part * 8, h);
+        tmem_st_32x8(t_sl + part * 8, l);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb.sq_full);
+      return true;
+    };
+    auto stage_lo = [&](const uint32_t* lo_keep, int tile) {
+      if (lane == 0) tma_store_wait_read();                         // the hi half has left the slice
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz64) << 4)) =
+            make_uint4(lo_keep[j * 4], lo_keep[j * 4 + 1], lo_keep[j * 4 + 2], lo_keep[j * 4 + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&map_o, slice, 128 + cq * 32, tile * 128 + q * 32);
+        tma_store_commit();
+      }
+    };
+    uint32_t it = 0;
+    int tile = first_tile;
+    bool ok = tile < p.ntiles && squares_of(0);
+    uint32_t lo_keep[16];
+    int p_tile = 0;
+    for (; ok && tile < p.ntiles; tile += tile_step, ++it) {
+      if (leader) gtrace(p, it, 0);
+      if (it > 0) stage_lo(lo_keep, p_tile);
+      if (leader) gtrace(p, it, 1);
+      if (!__all_sync(0xffffffffu, wait_abort(&sb.gdn_done, it & 1, &sb.abort_flag, p.status))) { ok = false; break; }
+      if (leader) gtrace(p, it, 7);
+      tcgen05_fence_after();
+      float v[32];
+      tmem_ld_32x32(t_g, v);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 be = beta4[j];
+        float* vv = v + 4 * j;
+        add2(vv[0], vv[1], be.x, be.y); add2(vv[2], vv[3], be.z, be.w);
+        float x0 = xr[4 * j], x1 = xr[4 * j + 1], x2 = xr[4 * j + 2], x3 = xr[4 * j + 3];
+        if (p.inverse) { mul2(x0, x1, sqrt_approx(vv[0]), sqrt_approx(vv[1])); mul2(x2, x3, sqrt_approx(vv[2]), sqrt_approx(vv[3])); }
+        else { mul2(x0, x1, rsqrt_approx(vv[0]), rsqrt_approx(vv[1])); mul2(x2, x3, rsqrt_approx(vv[2]), rsqrt_approx(vv[3])); }
+        vv[0] = x0; vv[1] = x1; vv[2] = x2; vv[3] = x3;
+      }
+      if (leader) gtrace(p, it, 2);
+      if (lane == 0) tma_store_wait_read();                           // the previous tile's lo half has left the slice
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split2p(v[j * 8 + e * 2], v[j * 8 + e * 2 + 1], h[e], lo_keep[j * 4 + e]);
+        *reinterpret_cast<uint4*>(mine + ((static_cast<uint32_t>(j) ^ swz64) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&map_o, slice, cq * 32, tile * 128 + q * 32);
+        tma_store_commit();
+      }
+      if (leader) gtrace(p, it, 8);
+      p_tile = tile;
+      if (tile + tile_step < p.ntiles) ok = squares_of(it + 1);
+      if (leader) gtrace(p, it, 4);
+    }
+    if (ok && it > 0) stage_lo(lo_keep, p_tile);
+    if (lane == 0) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // The same GDN / IGDN for c = 64 NP channels where gamma hi / lo (4 c^2 bytes: 144 KB at c = 192) cannot stay in shared memory
 // next to the tile: gamma STREAMS through a ring in [64 out x 64 in] pieces (hi + lo = 16 KB per ring slot, all NP^2 piece pairs
 // once per 128-pixel tile - they live in L2), and the norm is accumulated per 64-channel output piece:
@@ -1091,6 +1305,20 @@ int gdn_fwd_tc_x3(const void* x, int pair_in, long npix, int c, int inverse, con
   else if (int rc = encode_2d_ex(&map_x, x, 4, 128, static_cast<uint64_t>(npix), 32, 128)) return rc;
   if (int rc = encode_2d(&map_g, gamma_packed, 128, 256, 64, 128)) return rc;
   if (int rc = encode_2d(&map_o, y, 256, static_cast<uint64_t>(npix), 64, 128)) return rc;
+  static const bool use_ts = !(getenv("NIC_GDN_TS") && atoi(getenv("NIC_GDN_TS")) == 0);
+  if (pair_in && use_ts) {
+    CUtensorMap map_o32;
+    if (int rc = encode_2d_c32(&map_o32, y, 256, static_cast<uint64_t>(npix), 32)) return rc;
+    const int smem_ts = 14 * kPanel + 1024;
+    static bool ts_attr_set = false;
+    if (!ts_attr_set) {
+      if (int rc = check_cuda(cudaFuncSetAttribute(gdn_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ts), "cudaFuncSetAttribute")) return rc;
+      ts_attr_set = true;
+    }
+    const int grid_ts = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
+    if (int rc = check_cuda(launch_pdl(gdn_ts_kernel, grid_ts, kGtThreads, smem_ts, st, map_x, map_g, map_o32, p), "gdn_ts_kernel launch")) return rc;
+    return check_launch("gdn_ts_kernel");
+  }
   const int smem_bytes = 12 * kPanel + 1024;
   static bool attr_set = false;
   if (!attr_set) {
