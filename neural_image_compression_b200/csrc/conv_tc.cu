@@ -206,6 +206,7 @@ struct TcParams {
   int blk_roff[2], blk_coff[2];                // position of block b inside the tile (pixels)
   int tile_h, tile_w;                          // output pixels per tile
   int tiles_x, tiles_y, n_ntiles, total_tiles;
+  int pos_per_wave, spatial_tiles;             // phase-interleaved tile order (decode_tile); pos_per_wave = 0: phase-major
   int nchunks;                                 // K chunks of 64 (cin / 64; 3 cin / 64 in the bf16x3 arm)
   int a_chunk_mod;                             // input channel chunk of K chunk c is c % a_chunk_mod (bf16x3: [hi | lo | hi again])
   const int* lo_flag;                          // bf16x3, optional device flag: 0 = the lo half of the input pair tensor is all zero
@@ -270,12 +271,29 @@ __device__ __forceinline__ void trace(const TcParams& p, uint32_t tile_iter, int
   }
 }
 
-__device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& ntile, int& phase, int& img, int& ty, int& tx) {
+// Tile order.  Default: x, y, image, phase, N tile (phase-major: consecutive tiles cost the same, the static round robin over
+// the CTAs is balanced).  Transposed convs on a full grid use the phase-interleaved order instead: wave w (one tile per CTA)
+// covers pos_per_wave = grid / nphases spatial tiles in ALL phases at once - CTA c takes position c / nphases in phase
+// (c + w) % nphases, so every CTA still cycles through the phases - and the input patch a phase reads is in L2 from its sibling
+// phases (phase-major re-read the whole input from DRAM once per phase: g_s layer 3, 809 MB for a 201 MB input).
+// Returns false for the unused slots of the last wave (always a CTA's last iteration).
+__device__ __forceinline__ bool decode_tile(const TcParams& p, int tile, int& ntile, int& phase, int& img, int& ty, int& tx) {
+  if (p.pos_per_wave) {
+    const int w = tile / static_cast<int>(gridDim.x), c = tile - w * static_cast<int>(gridDim.x);
+    int s = w * p.pos_per_wave + c / p.nphases;
+    if (s >= p.spatial_tiles) return false;
+    ntile = 0;
+    phase = (c + w) % p.nphases;
+    tx = s % p.tiles_x; s /= p.tiles_x;
+    ty = s % p.tiles_y; img = s / p.tiles_y;
+    return true;
+  }
   tx = tile % p.tiles_x; tile /= p.tiles_x;
   ty = tile % p.tiles_y; tile /= p.tiles_y;
   img = tile % p.n; tile /= p.n;
   phase = tile % p.nphases; tile /= p.nphases;
   ntile = tile;
+  return true;
 }
 
 // number of M blocks of the tile that contain at least one real output pixel
@@ -730,7 +748,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t bytes = p.ph_rows * p.pw_cols * 128;
       for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step) {
         int ntile, phase, img, ty, tx;
-        decode_tile(p, tile, ntile, phase, img, ty, tx);
+        if (!decode_tile(p, tile, ntile, phase, img, ty, tx)) break;
         const TcPhase& ph = p.phases[phase];
         for (int chunk = 0; chunk < nchunks_eff && ok; ++chunk) {
           const int kc = kchunk(chunk);
@@ -767,7 +785,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         bool ok = true;
         for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step) {
           int ntile, phase, img, ty, tx;
-          decode_tile(p, tile, ntile, phase, img, ty, tx);
+          if (!decode_tile(p, tile, ntile, phase, img, ty, tx)) break;
           const TcPhase& ph = p.phases[phase];
           const int t0 = ph.plane_tap_begin[0], t1 = ph.plane_tap_begin[ph.nplanes];
           for (int chunk = 0; chunk < nchunks_eff && ok; ++chunk) {
@@ -819,7 +837,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int i = 0; i < 9; ++i) { ao[i] = nine ? s_tap_aoff[i] : 0u; bo[i] = nine ? s_tap_brow[i] * nchunks * bb16 : 0u; }
         for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step, ++tcount) {
           int ntile, phase, img, ty, tx;
-          decode_tile(p, tile, ntile, phase, img, ty, tx);
+          if (!decode_tile(p, tile, ntile, phase, img, ty, tx)) break;
           const TcPhase& ph = p.phases[phase];
           const int nblk = live_blocks(p, ty, tx);
           const int nplanes = ph.nplanes;
@@ -894,7 +912,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (b_res) { ok = wait_or_abort(&sb.bres_full, 0, &sb, p.status); tcgen05_fence_after(); }
         for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step, ++tcount) {
           int ntile, phase, img, ty, tx;
-          decode_tile(p, tile, ntile, phase, img, ty, tx);
+          if (!decode_tile(p, tile, ntile, phase, img, ty, tx)) break;
           const TcPhase& ph = p.phases[phase];
           const int nblk = live_blocks(p, ty, tx);
           const int nplanes = ph.nplanes;
@@ -1025,7 +1043,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     bool ok = true;
     for (int tile = first_tile; tile < p.total_tiles && ok; tile += tile_step, ++tcount) {
       int ntile, phase, img, ty, tx;
-      decode_tile(p, tile, ntile, phase, img, ty, tx);
+      if (!decode_tile(p, tile, ntile, phase, img, ty, tx)) break;
       const TcPhase& ph = p.phases[phase];
       const int nblk = live_blocks(p, ty, tx);
       const uint32_t buf = tcount & 1;
@@ -1602,6 +1620,16 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   p.tiles_x = (p.wp + p.tile_w - 1) / p.tile_w;
   p.tiles_y = (p.hp + p.tile_h - 1) / p.tile_h;
   p.total_tiles = p.tiles_x * p.tiles_y * p.n * p.nphases * p.n_ntiles;
+  p.pos_per_wave = 0; p.spatial_tiles = p.tiles_x * p.tiles_y * p.n;
+  {
+    static const bool interleave = !(getenv("NIC_TC_PHASE_ORDER") && atoi(getenv("NIC_TC_PHASE_ORDER")) == 0);
+    // measured (bf16x3, 16 images): g_s layer 3 (6144 tiles) 1109 -> 1031 us; layer 2 (1536 tiles, input L2-resident either way)
+    // 272.7 -> 273.7, layer 1 (384 tiles) 85.5 -> 88.8 - so only where the input cannot stay in L2 across the phase passes
+    if (interleave && p.nphases > 1 && p.n_ntiles == 1 && kNumSMs % p.nphases == 0 && p.total_tiles >= 16 * kNumSMs) {
+      p.pos_per_wave = kNumSMs / p.nphases;
+      p.total_tiles = (p.spatial_tiles + p.pos_per_wave - 1) / p.pos_per_wave * kNumSMs;      // virtual slots: waves x grid
+    }
+  }
   p.nslabs = tt.ntaps;
 
   // shared memory: A slots | B ring (or resident weights) | gamma | squares
