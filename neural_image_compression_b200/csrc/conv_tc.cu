@@ -206,6 +206,7 @@ struct TcParams {
   int blk_roff[2], blk_coff[2];                // position of block b inside the tile (pixels)
   int tile_h, tile_w;                          // output pixels per tile
   int tiles_x, tiles_y, n_ntiles, total_tiles;
+  int chunk_perm;                              // bf16x3: K chunks c-slice by c-slice (kchunk in the kernel)
   int nt_inner;                                // N tile innermost in the tile order (decode_tile)
   int pos_per_wave, spatial_tiles;             // phase-interleaved tile order (decode_tile); pos_per_wave = 0: phase-major
   int nchunks;                                 // K chunks of 64 (cin / 64; 3 cin / 64 in the bf16x3 arm)
@@ -739,7 +740,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // half as all zero - without the middle third (every role derives the same list from the same device word)
   int nchunks_eff = p.nchunks, skip_from = 1 << 30, skip_add = 0;
   if (p.lo_flag && __ldg(p.lo_flag) == 0) { skip_add = p.a_chunk_mod / 2; skip_from = skip_add; nchunks_eff = p.nchunks - skip_add; }
-  auto kchunk = [&](int chunk) { return chunk + (chunk >= skip_from ? skip_add : 0); };
+  // bf16x3 with a weight ring: the K chunks are walked c-slice by c-slice - (A_hi c, W_hi c), (A_hi c, W_lo c), (A_lo c, W_hi c) -
+  // instead of in K-concatenation order, so that the second fetch of an A_hi patch follows the first within a sixth of the tile
+  // (it used to come four sixths later and a quarter of those re-reads had left L2: g_a layer 2 read 1048 MB for an 805 MB input)
+  const int nc = p.a_chunk_mod / 2, per = (skip_add ? 2 : 3);
+  const bool perm = p.chunk_perm != 0;
+  auto kchunk = [&](int chunk) {
+    if (perm) { const int c = chunk / per, r = chunk - c * per; return r == 0 ? c : (r == 1 ? 2 * nc + c : nc + c); }
+    return chunk + (chunk >= skip_from ? skip_add : 0);
+  };
 
   tcgen05_fence_before();
   __syncthreads();
@@ -1677,6 +1686,10 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   const int gdn_bytes = (gdn ? 2 * 128 * 128 : 0) + stage_bytes;
   const int bres_bytes = tt.ntaps * p.nchunks * p.nb * 128;
   p.b_resident = (p.n_ntiles == 1 && p.nb <= 16 && bres_bytes + 2 * p.slot_bytes + gdn_bytes + 1024 <= kMaxDynSmem) ? 1 : 0;
+  {
+    static const bool perm = !(getenv("NIC_TC_CHUNK_PERM") && atoi(getenv("NIC_TC_CHUNK_PERM")) == 0);
+    p.chunk_perm = (perm && x3 && !p.b_resident) ? 1 : 0;
+  }
   if (p.b_resident) p.lo_flag = nullptr;          // resident weights are indexed by chunk position: always the full list
   int b_bytes;
   if (p.b_resident) {
