@@ -206,6 +206,8 @@ struct TcParams {
   int blk_roff[2], blk_coff[2];                // position of block b inside the tile (pixels)
   int tile_h, tile_w;                          // output pixels per tile
   int tiles_x, tiles_y, n_ntiles, total_tiles;
+  int b_slot_bytes;                            // stride of the weight ring: 16 KB (a 128-row slab), 8 KB in pair mode (64 rows per CTA)
+  int pair;                                    // conv_tc_kernel<true>: clusters of two CTAs, cta_group::2 MMAs
   int chunk_perm;                              // bf16x3: K chunks c-slice by c-slice (kchunk in the kernel)
   int nt_inner;                                // N tile innermost in the tile order (decode_tile)
   int pos_per_wave, spatial_tiles;             // phase-interleaved tile order (decode_tile); pos_per_wave = 0: phase-major
@@ -280,6 +282,20 @@ __device__ __forceinline__ void trace(const TcParams& p, uint32_t tile_iter, int
 // phases (phase-major re-read the whole input from DRAM once per phase: g_s layer 3, 809 MB for a 201 MB input).
 // Returns false for the unused slots of the last wave (always a CTA's last iteration).
 __device__ __forceinline__ bool decode_tile(const TcParams& p, int tile, int& ntile, int& phase, int& img, int& ty, int& tx) {
+  if (p.pos_per_wave && p.pair) {
+    // CTA pairs: cluster k of wave w takes pair slot u = w * grid / 2 + k: the pair of adjacent spatial tiles u / nphases in phase
+    // (u + u / nphases) % nphases - four consecutive clusters cover the four phases of one pair of tiles
+    const int half = static_cast<int>(gridDim.x) >> 1;
+    const int w = tile / static_cast<int>(gridDim.x), c = tile - w * static_cast<int>(gridDim.x);
+    const int u = w * half + (c >> 1), pp = u / p.nphases;
+    int s = 2 * pp + (c & 1);
+    if (s >= p.spatial_tiles) return false;
+    ntile = 0;
+    phase = (u - pp * p.nphases + pp) % p.nphases;
+    tx = s % p.tiles_x; s /= p.tiles_x;
+    ty = s % p.tiles_y; img = s / p.tiles_y;
+    return true;
+  }
   if (p.pos_per_wave) {
     const int w = tile / static_cast<int>(gridDim.x), c = tile - w * static_cast<int>(gridDim.x);
     int s = w * p.pos_per_wave + c / p.nphases;
@@ -705,6 +721,13 @@ __device__ __forceinline__ bool epilogue_tile_swapped(const TcParams& p, const f
   return true;
 }
 
+// PAIR: the kernel runs as clusters of two CTAs (cta_group::2, see tc_primitives.cuh): CTA r of a cluster works on tile 2 j + r
+// (same phase, same N tile), loads its own input patches and HALF of every weight slab (rows [64 r, 64 r + 64) of the N = 128
+// slab); the leader's two issuing warps issue M = 256 MMAs over both CTAs' blocks and multicast the ring / accumulator commits;
+// both CTAs' loads signal the leader's "full" barriers, both CTAs' epilogues release the leader's accumulator barriers.  Per MMA
+// an SM then reads 4 KB of pixels + 2 KB of weights (96 B/clk) and fills half the weight bytes: the N = 128 mainloop stops being
+// bound by shared-memory bandwidth.  Normal orientation, weight ring, one N tile only.
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_o, const __grid_constant__ TcParams p) {
@@ -722,15 +745,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool gdn = p.epilogue == NIC_EPI_GDN || p.epilogue == NIC_EPI_IGDN;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&sb.a_full[i], 1); mbar_init(&sb.a_empty[i], kMmaWarps); }
     for (int i = 0; i < kMaxBSlots; ++i) { mbar_init(&sb.b_full[i], 1); mbar_init(&sb.b_empty[i], kMmaWarps); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], kMmaWarps); mbar_init(&sb.acc_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sb.acc_full[i], kMmaWarps); mbar_init(&sb.acc_empty[i], PAIR ? 2 * kEpiWarps : kEpiWarps); }
     mbar_init(&sb.gdn_full, 1); mbar_init(&sb.gamma_full, 1); mbar_init(&sb.bres_full, 1);
     sb.abort_flag = 0;
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(&sb.tmem_base, 512); tmem_relinquish(); }
+  if (warp == 2) {
+    if (PAIR) { tmem_alloc_pair(&sb.tmem_base, 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(&sb.tmem_base, 512); tmem_relinquish(); }
+  }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); if (gdn) tma_prefetch_desc(&map_g); if (p.tma_out) tma_prefetch_desc(&map_o); }
   // everything above is independent of the preceding kernel; from here on global memory it may have written is read
   pdl_wait();
@@ -752,6 +779,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();                      // the peer's barriers are initialised before anything arrives on them
   tcgen05_fence_after();
   const uint32_t tmem = sb.tmem_base;
 
@@ -774,10 +802,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (!wait_or_abort(&sb.a_empty[s], ((it / p.nsa) & 1) ^ 1, &sb, p.status)) { ok = false; break; }
             if (chunk == 0 && pl == 0) trace(p, (tile - first_tile) / tile_step, 5);
             if (chunk == nchunks_eff - 1 && pl == ph.nplanes - 1) trace(p, (tile - first_tile) / tile_step, 6);
-            mbar_expect_tx(&sb.a_full[s], bytes);
             const int w0 = p.in_stride * (tx * p.tile_w + ph.plane_dxmin[pl]) + ph.plane_pw[pl];
             const int h0 = p.in_stride * (ty * p.tile_h + ph.plane_dymin[pl]) + ph.plane_ph[pl];
-            tma_load_4d(smem + p.off_a + s * p.slot_bytes, &map_a, &sb.a_full[s], (kc % p.a_chunk_mod) * 64, w0, h0, img);
+            if (PAIR) {       // both CTAs' patches complete the LEADER's barrier
+              if (rank == 0) mbar_expect_tx(&sb.a_full[s], 2 * bytes);
+              tma_load_4d_pair(smem + p.off_a + s * p.slot_bytes, &map_a, mapa_u32(smem_u32(&sb.a_full[s]), 0), (kc % p.a_chunk_mod) * 64, w0, h0, img);
+            } else {
+              mbar_expect_tx(&sb.a_full[s], bytes);
+              tma_load_4d(smem + p.off_a + s * p.slot_bytes, &map_a, &sb.a_full[s], (kc % p.a_chunk_mod) * 64, w0, h0, img);
+            }
           }
         }
       }
@@ -810,8 +843,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int t = t0; t < t1; ++t, ++it) {
               const int s = it % p.nsb;
               if (!wait_or_abort(&sb.b_empty[s], ((it / p.nsb) & 1) ^ 1, &sb, p.status)) { ok = false; break; }
-              mbar_expect_tx(&sb.b_full[s], bytes);
-              tma_load_2d(smem + p.off_b + s * (128 * 128), &map_w, &sb.b_full[s], kc * 64, s_tap_brow[t] * p.cout_pad + ntile * p.nb);
+              if (PAIR) {     // this CTA's half of the slab (the tensor map's box is nb / 2 rows)
+                if (rank == 0) mbar_expect_tx(&sb.b_full[s], bytes);
+                tma_load_2d_pair(smem + p.off_b + s * p.b_slot_bytes, &map_w, mapa_u32(smem_u32(&sb.b_full[s]), 0), kc * 64,
+                                 s_tap_brow[t] * p.cout_pad + ntile * p.nb + static_cast<int>(rank) * (p.nb / 2));
+              } else {
+                mbar_expect_tx(&sb.b_full[s], bytes);
+                tma_load_2d(smem + p.off_b + s * p.b_slot_bytes, &map_w, &sb.b_full[s], kc * 64, s_tap_brow[t] * p.cout_pad + ntile * p.nb);
+              }
             }
           }
         }
@@ -834,10 +873,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int nsa = p.nsa, nsb = p.nsb, nchunks = nchunks_eff, b_res = p.b_resident;
       const bool swp = p.swap != 0;
       const uint32_t blk_off = (mw && !swp) ? static_cast<uint32_t>((p.blk_roff[1] * p.pw_cols + p.blk_coff[1]) * 128) >> 4 : 0u;
-      const uint32_t idesc_use = swp ? umma_idesc_bf16(128, 256) : idesc;
+      const uint32_t idesc_use = PAIR ? umma_idesc_bf16(256, p.nb) : (swp ? umma_idesc_bf16(128, 256) : idesc);
       const uint32_t f_hi = swp ? b_hi : a_hi, g_hi = swp ? a_hi : b_hi;
       const uint32_t a_base_lo = umma_desc_lo(a_base), b_base_lo = umma_desc_lo(b_base);
-      const uint32_t slot16 = static_cast<uint32_t>(p.slot_bytes) >> 4, bb16 = bbytes >> 4;
+      const uint32_t slot16 = static_cast<uint32_t>(p.slot_bytes) >> 4, bb16 = bbytes >> 4, bslot16 = static_cast<uint32_t>(p.b_slot_bytes) >> 4;
       // Resident weights (N = 16 layers): ONE thread per issuer walks the loop - no barrier polls inside a plane, so dropping the
       // per-tap elect / reconvergence / warp barrier matters (per-tap overhead, not the tensor pipe, bounds these layers).
       // Weight ring (everything else): the warp-uniform loop below is faster (mbarrier polls by the whole warp wake sooner).
@@ -902,7 +941,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   if (!mbar_try_wait(&sb.b_full[sbi], pb) && !wait_or_abort(&sb.b_full[sbi], pb, &sb, p.status)) { ok = false; break; }
                   tcgen05_fence_after();
                   if (live) {
-                    const uint32_t b_lo = b_base_lo + sbi * ((128 * 128) >> 4);
+                    const uint32_t b_lo = b_base_lo + sbi * bslot16;
                     const uint32_t a_lo0 = a_slot_lo + s_tap_aoff[t];
                     umma_bf16_lohi(d_tmem, a_lo0, a_hi, b_lo, b_hi, idesc, accumulate);
                     umma_bf16_lohi(d_tmem, a_lo0 + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
@@ -922,7 +961,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           umma_commit(&sb.acc_full[buf]);
         }
       }
-      if (!b_res) {
+      if (!b_res && !(PAIR && rank != 0)) {       // (pair: the leader CTA issues for both)
+        auto MMA = [&](uint32_t d, uint32_t f, uint32_t fh, uint32_t g, uint32_t gh, uint32_t id, uint32_t acc) {
+          if constexpr (PAIR) umma_bf16_lohi_pair(d, f, fh, g, gh, id, acc); else umma_bf16_lohi(d, f, fh, g, gh, id, acc);
+        };
+        auto COMMIT = [&](uint64_t* bar) { if constexpr (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
         uint32_t tcount = 0;
         uint32_t sa = 0, pa = 0, sbi = 0, pb = 0;      // ring slot + phase parity of the A and B rings
         bool ok = true;
@@ -931,7 +974,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           int ntile, phase, img, ty, tx;
           if (!decode_tile(p, tile, ntile, phase, img, ty, tx)) break;
           const TcPhase& ph = p.phases[phase];
-          const int nblk = live_blocks(p, ty, tx);
+          int nblk = live_blocks(p, ty, tx);
+          if (PAIR) {       // the M = 256 MMA covers block b of both tiles of the pair
+            int n2, ph2, img2, ty2, tx2;
+            if (decode_tile(p, tile + 1, n2, ph2, img2, ty2, tx2)) { const int nb2 = live_blocks(p, ty2, tx2); nblk = nb2 > nblk ? nb2 : nblk; }
+          }
           const int nplanes = ph.nplanes;
           const uint32_t buf = tcount & 1;
           if (!wait_or_abort(&sb.acc_empty[buf], ((tcount >> 1) & 1) ^ 1, &sb, p.status)) break;
@@ -969,26 +1016,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
               tcgen05_fence_after();
               const uint32_t a_lo0 = a_base_lo + sa0 * slot16 + aoff, a_lo1 = a_base_lo + sa1 * slot16 + aoff;
-              const uint32_t b_lo0 = b_base_lo + s0 * ((128 * 128) >> 4), b_lo1 = b_base_lo + s1 * ((128 * 128) >> 4);
+              const uint32_t b_lo0 = b_base_lo + s0 * bslot16, b_lo1 = b_base_lo + s1 * bslot16;
               const uint32_t f0 = swp ? b_lo0 : a_lo0, g0 = swp ? a_lo0 : b_lo0, f1 = swp ? b_lo1 : a_lo1, g1 = swp ? a_lo1 : b_lo1;
               if (elect_one()) {
                 if (live) {
-                  umma_bf16_lohi(d_tmem, f0, f_hi, g0, g_hi, idesc_use, accumulate);
-                  umma_bf16_lohi(d_tmem, f0 + 2, f_hi, g0 + 2, g_hi, idesc_use, 1);
-                  umma_bf16_lohi(d_tmem, f0 + 4, f_hi, g0 + 4, g_hi, idesc_use, 1);
-                  umma_bf16_lohi(d_tmem, f0 + 6, f_hi, g0 + 6, g_hi, idesc_use, 1);
+                  MMA(d_tmem, f0, f_hi, g0, g_hi, idesc_use, accumulate);
+                  MMA(d_tmem, f0 + 2, f_hi, g0 + 2, g_hi, idesc_use, 1);
+                  MMA(d_tmem, f0 + 4, f_hi, g0 + 4, g_hi, idesc_use, 1);
+                  MMA(d_tmem, f0 + 6, f_hi, g0 + 6, g_hi, idesc_use, 1);
                 }
-                umma_commit(&sb.b_empty[s0]);
-                umma_commit(&sb.a_empty[sa0]);
+                COMMIT(&sb.b_empty[s0]);
+                COMMIT(&sb.a_empty[sa0]);
                 if (two) {
                   if (live) {
-                    umma_bf16_lohi(d_tmem, f1, f_hi, g1, g_hi, idesc_use, 1);
-                    umma_bf16_lohi(d_tmem, f1 + 2, f_hi, g1 + 2, g_hi, idesc_use, 1);
-                    umma_bf16_lohi(d_tmem, f1 + 4, f_hi, g1 + 4, g_hi, idesc_use, 1);
-                    umma_bf16_lohi(d_tmem, f1 + 6, f_hi, g1 + 6, g_hi, idesc_use, 1);
+                    MMA(d_tmem, f1, f_hi, g1, g_hi, idesc_use, 1);
+                    MMA(d_tmem, f1 + 2, f_hi, g1 + 2, g_hi, idesc_use, 1);
+                    MMA(d_tmem, f1 + 4, f_hi, g1 + 4, g_hi, idesc_use, 1);
+                    MMA(d_tmem, f1 + 6, f_hi, g1 + 6, g_hi, idesc_use, 1);
                   }
-                  umma_commit(&sb.b_empty[s1]);
-                  umma_commit(&sb.a_empty[sa1]);
+                  COMMIT(&sb.b_empty[s1]);
+                  COMMIT(&sb.a_empty[sa1]);
                 }
               }
               __syncwarp();
@@ -1015,38 +1062,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   if (++sbi == static_cast<uint32_t>(nsb)) { sbi = 0; pb ^= 1; }
                 }
                 tcgen05_fence_after();
-                const uint32_t b_lo0 = b_base_lo + s0 * ((128 * 128) >> 4), b_lo1 = b_base_lo + s1 * ((128 * 128) >> 4);
+                const uint32_t b_lo0 = b_base_lo + s0 * bslot16, b_lo1 = b_base_lo + s1 * bslot16;
                 const uint32_t a_lo0 = a_slot_lo + s_tap_aoff[t] + blk_off, a_lo1 = a_slot_lo + s_tap_aoff[two ? t + 1 : t] + blk_off;
                 // first / second operand of the MMA: (pixels, weights), or (weights, pixels) in the swapped orientation
                 const uint32_t f0 = swp ? b_lo0 : a_lo0, g0 = swp ? a_lo0 : b_lo0, f1 = swp ? b_lo1 : a_lo1, g1 = swp ? a_lo1 : b_lo1;
                 if (elect_one()) {
                   if (live) {
-                    umma_bf16_lohi(d_tmem, f0, f_hi, g0, g_hi, idesc_use, accumulate);
-                    umma_bf16_lohi(d_tmem, f0 + 2, f_hi, g0 + 2, g_hi, idesc_use, 1);
-                    umma_bf16_lohi(d_tmem, f0 + 4, f_hi, g0 + 4, g_hi, idesc_use, 1);
-                    umma_bf16_lohi(d_tmem, f0 + 6, f_hi, g0 + 6, g_hi, idesc_use, 1);
+                    MMA(d_tmem, f0, f_hi, g0, g_hi, idesc_use, accumulate);
+                    MMA(d_tmem, f0 + 2, f_hi, g0 + 2, g_hi, idesc_use, 1);
+                    MMA(d_tmem, f0 + 4, f_hi, g0 + 4, g_hi, idesc_use, 1);
+                    MMA(d_tmem, f0 + 6, f_hi, g0 + 6, g_hi, idesc_use, 1);
                   }
-                  umma_commit(&sb.b_empty[s0]);
+                  COMMIT(&sb.b_empty[s0]);
                   if (two) {
                     if (live) {
-                      umma_bf16_lohi(d_tmem, f1, f_hi, g1, g_hi, idesc_use, 1);
-                      umma_bf16_lohi(d_tmem, f1 + 2, f_hi, g1 + 2, g_hi, idesc_use, 1);
-                      umma_bf16_lohi(d_tmem, f1 + 4, f_hi, g1 + 4, g_hi, idesc_use, 1);
-                      umma_bf16_lohi(d_tmem, f1 + 6, f_hi, g1 + 6, g_hi, idesc_use, 1);
+                      MMA(d_tmem, f1, f_hi, g1, g_hi, idesc_use, 1);
+                      MMA(d_tmem, f1 + 2, f_hi, g1 + 2, g_hi, idesc_use, 1);
+                      MMA(d_tmem, f1 + 4, f_hi, g1 + 4, g_hi, idesc_use, 1);
+                      MMA(d_tmem, f1 + 6, f_hi, g1 + 6, g_hi, idesc_use, 1);
                     }
-                    umma_commit(&sb.b_empty[s1]);
+                    COMMIT(&sb.b_empty[s1]);
                   }
                 }
                 __syncwarp();
                 accumulate = 1;
               }
-              if (elect_one()) umma_commit(&sb.a_empty[sa]);
+              if (elect_one()) COMMIT(&sb.a_empty[sa]);
               __syncwarp();
               if (++sa == static_cast<uint32_t>(nsa)) { sa = 0; pa ^= 1; }
             }
           }
           if (lane == 0 && mw == 0) trace(p, tcount, 2);
-          if (elect_one()) umma_commit(&sb.acc_full[buf]);
+          if (elect_one()) COMMIT(&sb.acc_full[buf]);
           __syncwarp();
         }
       }
@@ -1078,14 +1125,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (warp == kFirstEpiWarp && lane == 0) trace(p, tcount, 4);
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sb.acc_empty[buf]);
+      if (lane == 0) {
+        if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sb.acc_empty[buf]), 0));   // the leader's issuers wait for both CTAs
+        else mbar_arrive(&sb.acc_empty[buf]);
+      }
     }
     if (p.tma_out && warp == kFirstEpiWarp && lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (PAIR) cluster_sync();                      // no CTA leaves while its peer may still read its shared memory or signal its barriers
+  if (warp == 2) { if (PAIR) tmem_dealloc_pair(tmem, 512); else tmem_dealloc(tmem, 512); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1613,6 +1664,21 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   // (round 2, after the two-chunk issue loop: the stride-1 layers now gain too - entropy-parameter 1x1s 90 -> 74 / 97 -> 88 us, h_a
   // layer 1 38.6 -> 32.8, h_s layer 3 81 -> 74, context conv 72 -> 67 us; the stride-2 g_a layer 4 still loses, 65 -> 69 us)
   bool swap = swap_ok && (swap_env ? atoi(swap_env) != 0 : (tt.nphases > 1 || tt.in_stride == 1));
+  // CTA pairs (conv_tc_kernel<true>): normal orientation, side-by-side two-block tiles, one N tile of 128, an even number of tiles
+  // per phase (the two CTAs of a cluster take tiles 2 j and 2 j + 1 of the same phase) and at least two waves of them
+  bool pair = false;
+  {
+    const char* pair_env = getenv("NIC_TC_PAIR");
+    const int tx2 = (p.wp + 2 * kTileW - 1) / (2 * kTileW), ty2 = (p.hp + kTileH - 1) / kTileH;
+    const long per_phase = static_cast<long>(tx2) * ty2 * p.n;
+    // measured (bf16x3, 16 images, same box, results bit-identical): g_a layer 2 743.8 -> 709.3 us, layer 3 212.1 -> 201.6, g_s layer 3
+    // 1040.7 -> 1018.7 (against the swapped one-CTA form); g_s layer 2 (1536 tiles in four phases) 271.0 -> 278.4: stays unpaired
+    const bool worth = tt.nphases == 1 || per_phase * tt.nphases >= 16 * kNumSMs;
+    pair = (pair_env ? atoi(pair_env) != 0 : worth) && !flat && p.nb == 128 && p.n_ntiles == 1 && p.wp > kTileW && per_phase % 2 == 0 &&
+           per_phase * tt.nphases >= 2 * kNumSMs && !getenv("NIC_TC_MT");
+    if (pair) swap = false;
+  }
+  p.pair = pair ? 1 : 0;
   const bool stacked = flat || swap;
   // two M = 128 blocks per tile share every weight slab (halves the L2 -> shared-memory weight traffic, which is
   // what bounds M = 128 tiles: profiles/README.md); side by side for images, stacked for the flat 1x1 case
@@ -1649,7 +1715,10 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     // 272.7 -> 273.7, layer 1 (384 tiles) 85.5 -> 88.8 - so only where the input cannot stay in L2 across the phase passes
     if (interleave && p.nphases > 1 && p.n_ntiles == 1 && kNumSMs % p.nphases == 0 && p.total_tiles >= 16 * kNumSMs) {
       p.pos_per_wave = kNumSMs / p.nphases;
-      p.total_tiles = (p.spatial_tiles + p.pos_per_wave - 1) / p.pos_per_wave * kNumSMs;      // virtual slots: waves x grid
+      if (pair) {
+        const long slots = static_cast<long>(p.spatial_tiles / 2) * p.nphases, half = kNumSMs / 2;
+        p.total_tiles = static_cast<int>((slots + half - 1) / half) * kNumSMs;
+      } else p.total_tiles = (p.spatial_tiles + p.pos_per_wave - 1) / p.pos_per_wave * kNumSMs;      // virtual slots: waves x grid
     }
   }
   p.nslabs = tt.ntaps;
@@ -1690,6 +1759,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     static const bool perm = !(getenv("NIC_TC_CHUNK_PERM") && atoi(getenv("NIC_TC_CHUNK_PERM")) == 0);
     p.chunk_perm = (perm && x3 && !p.b_resident) ? 1 : 0;
   }
+  p.b_slot_bytes = p.pair ? 64 * 128 : 128 * 128;
   if (p.b_resident) p.lo_flag = nullptr;          // resident weights are indexed by chunk position: always the full list
   int b_bytes;
   if (p.b_resident) {
@@ -1697,9 +1767,10 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     p.nsa = 4;
     while (p.nsa > 2 && p.nsa * p.slot_bytes + b_bytes + gdn_bytes + 1024 > kMaxDynSmem) --p.nsa;
   } else {
+    const int bslot = p.pair ? 64 * 128 : 128 * 128;
     // prefer a deep weight ring (TMA latency ~1 us vs ~0.13 us of MMA per slab and block), then A slots
     p.nsa = 2; p.nsb = 4;
-    if (2 * p.slot_bytes + 4 * 128 * 128 + gdn_bytes + 1024 > kMaxDynSmem) {
+    if (2 * p.slot_bytes + 4 * bslot + gdn_bytes + 1024 > kMaxDynSmem) {
       if (p.stage2) return fail(NIC_E_UNSUPPORTED, "conv bf16x3: internal: staging tiles do not fit");   // cannot happen: slots of these layers are <= 42 KB
       return fail(NIC_E_UNSUPPORTED, "conv bf16: patch of %d x %d pixels does not fit shared memory", p.ph_rows, p.pw_cols);
     }
@@ -1707,15 +1778,15 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     if (one_tap) {
       p.nsa = 2; p.nsb = 2;
       for (;;) {
-        if (p.nsa <= p.nsb && p.nsa < kMaxSlots && (p.nsa + 1) * p.slot_bytes + p.nsb * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsa;
-        else if (p.nsb < kMaxBSlots && p.nsa * p.slot_bytes + (p.nsb + 1) * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsb;
+        if (p.nsa <= p.nsb && p.nsa < kMaxSlots && (p.nsa + 1) * p.slot_bytes + p.nsb * bslot + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsa;
+        else if (p.nsb < kMaxBSlots && p.nsa * p.slot_bytes + (p.nsb + 1) * bslot + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsb;
         else break;
       }
     } else
     for (;;) {
-      if (p.nsb < kMaxBSlots && p.nsa * p.slot_bytes + (p.nsb + 1) * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem && p.nsb < 2 * p.nsa + 2) ++p.nsb;
-      else if (p.nsa < kMaxSlots && (p.nsa + 1) * p.slot_bytes + p.nsb * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsa;
-      else if (p.nsb < kMaxBSlots && p.nsa * p.slot_bytes + (p.nsb + 1) * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsb;
+      if (p.nsb < kMaxBSlots && p.nsa * p.slot_bytes + (p.nsb + 1) * bslot + gdn_bytes + 1024 <= kMaxDynSmem && p.nsb < 2 * p.nsa + 2) ++p.nsb;
+      else if (p.nsa < kMaxSlots && (p.nsa + 1) * p.slot_bytes + p.nsb * bslot + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsa;
+      else if (p.nsb < kMaxBSlots && p.nsa * p.slot_bytes + (p.nsb + 1) * bslot + gdn_bytes + 1024 <= kMaxDynSmem) ++p.nsb;
       else break;
     }
     {   // timing experiments: NIC_TC_NSA / NIC_TC_NSB force the ring depths (checked against the shared-memory budget)
@@ -1723,10 +1794,10 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
       const int fa = ea ? atoi(ea) : 0, fb = eb ? atoi(eb) : 0;
       if (fa || fb) {
         const int na = fa ? fa : p.nsa, nb2 = fb ? fb : p.nsb;
-        if (na >= 2 && na <= kMaxSlots && nb2 >= 2 && nb2 <= kMaxBSlots && na * p.slot_bytes + nb2 * 128 * 128 + gdn_bytes + 1024 <= kMaxDynSmem) { p.nsa = na; p.nsb = nb2; }
+        if (na >= 2 && na <= kMaxSlots && nb2 >= 2 && nb2 <= kMaxBSlots && na * p.slot_bytes + nb2 * bslot + gdn_bytes + 1024 <= kMaxDynSmem) { p.nsa = na; p.nsb = nb2; }
       }
     }
-    b_bytes = p.nsb * 128 * 128;
+    b_bytes = p.nsb * bslot;
   }
   p.off_a = 0; p.off_b = p.nsa * p.slot_bytes; p.off_gamma = p.off_b + b_bytes; p.off_sq = p.off_gamma + (gdn ? 2 * 128 * 128 : 0);
   p.smem_bytes = p.off_sq + stage_bytes + 1024;
@@ -1734,7 +1805,8 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   CUtensorMap map_a, map_w, map_g, map_o;
   if (p.split_out && !p.tma_out) return fail(NIC_E_BADALIGN, "conv bf16x3: bf16-pair output must be 16-byte aligned");
   if (int rc = encode_nhwc(&map_a, x, gn, gh, gw, (x3 ? 2 : 1) * d->c_in, p.pw_cols, p.ph_rows, tt.in_stride, 2)) return rc;
-  if (int rc = encode_2d(&map_w, w_packed, static_cast<uint64_t>(x3 ? 3 : 1) * d->c_in, static_cast<uint64_t>(tt.ntaps) * p.cout_pad, 64, p.nb)) return rc;
+  if (int rc = encode_2d(&map_w, w_packed, static_cast<uint64_t>(x3 ? 3 : 1) * d->c_in, static_cast<uint64_t>(tt.ntaps) * p.cout_pad, 64,
+                         p.pair ? p.nb / 2 : p.nb)) return rc;
   if (gdn) { if (int rc = encode_2d(&map_g, gdn_gamma, 128, 128, 64, 128)) return rc; }
   else map_g = map_w;
   if (p.tma_out) {
@@ -1745,11 +1817,15 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
 
   static bool attr_set = false;
   if (!attr_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), "cudaFuncSetAttribute")) return rc;
+    if (int rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), "cudaFuncSetAttribute")) return rc;
+    if (int rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), "cudaFuncSetAttribute")) return rc;
     attr_set = true;
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  if (int rc = check_cuda(launch_pdl(conv_tc_kernel, grid, kThreads, p.smem_bytes, st, map_a, map_w, map_g, map_o, p), "conv_tc_kernel launch")) return rc;
+  if (p.pair) {
+    if (p.mt != 2 || p.swap || p.b_resident || grid % 2) return fail(NIC_E_UNSUPPORTED, "conv tc: CTA-pair launch with an unsupported tiling");
+    if (int rc = check_cuda(launch_pdl_cluster(conv_tc_kernel<true>, grid, kThreads, p.smem_bytes, st, 2, map_a, map_w, map_g, map_o, p), "conv_tc_kernel launch")) return rc;
+  } else if (int rc = check_cuda(launch_pdl(conv_tc_kernel<false>, grid, kThreads, p.smem_bytes, st, map_a, map_w, map_g, map_o, p), "conv_tc_kernel launch")) return rc;
   return check_launch("conv_tc_kernel");
 }
 

@@ -261,3 +261,30 @@ def test_x3_two_pass_on_integer_symbols(kind):
         ref = _ref(conv, v_in.cpu(), epi, gdn=g, mask=mask)
         print(kind, scale, _close(got, ref), float((got - full).abs().max() / full.abs().max()))
         assert float((got - full).abs().max() / full.abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("kind,precision", [("conv", "bf16x3"), ("convT", "bf16x3"), ("convT_big", "bf16x3"), ("conv", "bf16")])
+def test_cta_pair_form_is_bit_identical_to_the_one_cta_form(kind, precision, monkeypatch):
+    """conv_tc_kernel<true> (clusters of two CTAs, cta_group::2 MMAs of M = 256, half a weight slab per CTA, barriers across the pair)
+    accumulates exactly what two M = 128 MMAs do: the outputs must match bit for bit, at a shape large enough for the pair form
+    (>= 2 waves of two-block tiles) including ragged right / bottom edges."""
+    from neural_image_compression_b200 import engine, _lib
+    from neural_image_compression_b200._lib import EPI_BIAS, EPI_LRELU
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    if kind == "conv":
+        conv, h, w, b = nn.Conv2d(128, 128, 5, 2, 2).to(dev), 250, 382, 5
+    elif kind == "convT":
+        conv, h, w, b = nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1).to(dev), 63, 96, 6
+    else:       # enough tiles (>= 16 waves) for the phase-interleaved tile order of the pair form
+        conv, h, w, b = nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1).to(dev), 128, 192, 16
+    op = engine.ConvOp(conv, EPI_LRELU if kind == "conv" else EPI_BIAS)
+    x = torch.randn(b, h, w, 128, device=dev)
+    x = engine.to_pair(x) if precision == "bf16x3" else x.to(torch.bfloat16)
+    monkeypatch.setenv("NIC_TC_PAIR", "0")
+    ref = op.run(x, b, h, w, precision).clone()
+    monkeypatch.setenv("NIC_TC_PAIR", "1")
+    out = op.run(x, b, h, w, precision).clone()
+    torch.cuda.synchronize()
+    assert _lib.load().nic_pipeline_status() == 0
+    assert torch.equal(ref.view(torch.int16), out.view(torch.int16))

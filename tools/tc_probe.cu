@@ -627,8 +627,252 @@ static int run_mma_ts_probe() {
   return bad == 0 && st == 0;
 }
 
+// -------------------------------------------------------------------------------------------------
+// T10: cta_group::2 - a CTA pair computes D[256 x 128] = A[256 x 64] . B[128 x 64]^T: CTA r holds A rows [128 r, 128 r + 128) and
+// B rows (N) [64 r, 64 r + 64) in its own shared memory; the leader issues the MMAs; the commit is multicast to both CTAs.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) mma_pair_probe_kernel(const __nv_bfloat16* A, const __nv_bfloat16* B, float* D,
+                                                                                       int iters, long long* cycles, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                 // 128 rows x 128 B
+  uint8_t* sB = smem + 16 * 1024;     // 64 rows x 128 B
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank();
+  for (int i = tid; i < 128 * 64; i += 128) {
+    const int r = i / 64, k = i % 64;
+    *reinterpret_cast<__nv_bfloat16*>(sA + sw128_offset(r, k)) = A[(rank * 128 + r) * 64 + k];
+  }
+  for (int i = tid; i < 64 * 64; i += 128) {
+    const int r = i / 64, k = i % 64;
+    *reinterpret_cast<__nv_bfloat16*>(sB + sw128_offset(r, k)) = B[(rank * 64 + r) * 64 + k];
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tm = tmem_base;
+  const uint32_t idesc = umma_idesc_bf16(256, 128);
+  if (rank == 0 && warp == 1 && elect_one()) {
+    const uint32_t a_lo = umma_desc_lo(smem_u32(sA)), b_lo = umma_desc_lo(smem_u32(sB)), hi = umma_desc_hi(1024);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+          "setp.ne.b32 p, %6, 0;\n\t"
+          "mov.b64 da, {%1, %2};\n\t"
+          "mov.b64 db, {%3, %4};\n\t"
+          "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(tm),
+          "r"(a_lo + 2 * k), "r"(hi), "r"(b_lo + 2 * k), "r"(hi), "r"(idesc), "r"(k > 0 ? 1u : 0u)
+          : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar)),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+  }
+  __syncwarp();
+  bool ok = mbar_wait(&bar, 0, 1u << 22);
+  if (!ok) { if (tid == 0) atomicExch(status, 1 + rank); }
+  tcgen05_fence_after();
+  if (ok) {
+    for (int c = 0; c < 128; c += 32) {
+      float v[32];
+      tmem_ld_32x32(tm + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+      tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) D[(rank * 128 + warp * 32 + lane) * 128 + c + j] = v[j];
+    }
+  }
+  // rate: `iters` groups of 4 back-to-back pair MMAs
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  if (ok && rank == 0 && warp == 1 && elect_one()) {
+    const uint32_t a_lo = umma_desc_lo(smem_u32(sA)), b_lo = umma_desc_lo(smem_u32(sB)), hi = umma_desc_hi(1024);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(tm),
+            "r"(a_lo + 2 * k), "r"(hi), "r"(b_lo + 2 * k), "r"(hi), "r"(idesc), "r"(1u)
+            : "memory");
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar)),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+    if (!mbar_wait(&bar, 1, 1u << 24)) atomicExch(status, 3);
+    cycles[1] = clock64() - t0;
+  }
+  __syncwarp();
+  if (ok) {
+    if (!mbar_wait(&bar, 1, 1u << 24)) { if (tid == 0) atomicExch(status, 5 + rank); }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(128u) : "memory");
+}
+
+static int run_mma_pair_probe() {
+  std::vector<__nv_bfloat16> hA(256 * 64), hB(128 * 64);
+  srand(777);
+  for (auto& v : hA) v = __float2bfloat16((rand() % 17 - 8) / 8.0f);
+  for (auto& v : hB) v = __float2bfloat16((rand() % 13 - 6) / 4.0f);
+  __nv_bfloat16 *dA, *dB; float* dD; int* dS; long long* dC;
+  CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dD, 256 * 128 * 4)); CK(cudaMalloc(&dS, 4));
+  CK(cudaMalloc(&dC, 16));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0, 256 * 128 * 4)); CK(cudaMemset(dS, 0, 4)); CK(cudaMemset(dC, 0, 16));
+  const int smem = 24 * 1024 + 1024, iters = 256;
+  mma_pair_probe_kernel<<<2, 128, smem>>>(dA, dB, dD, iters, dC, dS);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  pair probe: CUDA error %s\n", cudaGetErrorString(e)); exit(3); }
+  std::vector<float> hD(256 * 128); int st; long long cyc[2];
+  CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cyc, dC, 16, cudaMemcpyDeviceToHost));
+  double maxerr = 0; int bad = 0;
+  for (int m = 0; m < 256; ++m)
+    for (int n = 0; n < 128; ++n) {
+      double ref = 0;
+      for (int k = 0; k < 64; ++k) ref += bf2f(hA[m * 64 + k]) * bf2f(hB[n * 64 + k]);
+      const double err = fabs(ref - hD[m * 128 + n]);
+      if (err > maxerr) maxerr = err;
+      if (err > 1e-3) ++bad;
+    }
+  printf("  CTA pair, M256 N128 K64 (B split along N): status=%d bad=%d/32768 maxerr=%.4g  %s;  ~%.1f clk per M256 N128 K16 MMA\n", st, bad, maxerr,
+         (bad == 0 && st == 0) ? "OK" : "MISMATCH", (double)cyc[1] / (iters * 4));
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dS); cudaFree(dC);
+  return bad == 0 && st == 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// T11: the barrier plumbing of a CTA pair: both CTAs TMA-load their operand halves and signal ONE barrier in the leader
+// (cp.async.bulk.tensor .cta_group::2 with a mapa'd barrier address); the peer reports "accumulator drained" with a remote
+// mbarrier.arrive on the leader's barrier.
+// -------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) pair_tma_probe_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                                       const __grid_constant__ CUtensorMap mapB, float* D, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                 // 128 rows x 128 B
+  uint8_t* sB = smem + 16 * 1024;     // 64 rows x 128 B
+  __shared__ uint64_t full, done, drained;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (tid == 0) { mbar_init(&full, 1); mbar_init(&done, 1); mbar_init(&drained, 2); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc_pair(&tmem_base, 128); tmem_relinquish_pair(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tcgen05_fence_after();
+  const uint32_t tm = tmem_base;
+  if (warp == 2 && lane == 0) {
+    const uint32_t full_leader = mapa_u32(smem_u32(&full), 0);
+    if (rank == 0) mbar_expect_tx(&full, 2 * (16384 + 8192));          // both CTAs' A and B halves
+    tma_load_2d_pair(sA, &mapA, full_leader, 0, rank * 128);
+    tma_load_2d_pair(sB, &mapB, full_leader, 0, rank * 64);
+  }
+  if (rank == 0 && warp == 1 && lane == 0) {
+    if (!mbar_wait(&full, 0, 1u << 22)) atomicExch(status, 1);
+    else {
+      tcgen05_fence_after();
+      const uint32_t idesc = umma_idesc_bf16(256, 128);
+      const uint32_t a_lo = umma_desc_lo(smem_u32(sA)), b_lo = umma_desc_lo(smem_u32(sB)), hi = umma_desc_hi(1024);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16_lohi_pair(tm, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc, k > 0);
+      umma_commit_pair(&done);
+    }
+  }
+  __syncwarp();
+  const bool ok = mbar_wait(&done, 0, 1u << 22);
+  if (!ok) { if (tid == 0) atomicExch(status, 2 + rank); }
+  tcgen05_fence_after();
+  if (ok) {
+    for (int c = 0; c < 128; c += 32) {
+      float v[32];
+      tmem_ld_32x32(tm + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+      tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) D[(rank * 128 + warp * 32 + lane) * 128 + c + j] = v[j];
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    if (rank == 0) mbar_arrive(&drained); else mbar_arrive_cluster(mapa_u32(smem_u32(&drained), 0));
+    if (rank == 0 && !mbar_wait(&drained, 0, 1u << 22)) atomicExch(status, 4);
+  }
+  __syncthreads();
+  cluster_sync();
+  if (warp == 0) tmem_dealloc_pair(tm, 128);
+}
+
+static int run_pair_tma_probe(EncodeTiledFn enc) {
+  std::vector<__nv_bfloat16> hA(256 * 64), hB(128 * 64);
+  srand(999);
+  for (auto& v : hA) v = __float2bfloat16((rand() % 17 - 8) / 8.0f);
+  for (auto& v : hB) v = __float2bfloat16((rand() % 13 - 6) / 4.0f);
+  __nv_bfloat16 *dA, *dB; float* dD; int* dS;
+  CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dD, 256 * 128 * 4)); CK(cudaMalloc(&dS, 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0, 256 * 128 * 4)); CK(cudaMemset(dS, 0, 4));
+  CUtensorMap mapA, mapB;
+  auto make2d = [&](CUtensorMap* m, void* base, int rows, int box_rows) {
+    cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); exit(2); }
+  };
+  make2d(&mapA, dA, 256, 128);
+  make2d(&mapB, dB, 128, 64);
+  const int smem = 24 * 1024 + 1024;
+  pair_tma_probe_kernel<<<2, 128, smem>>>(mapA, mapB, dD, dS);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  pair TMA probe: CUDA error %s\n", cudaGetErrorString(e)); exit(3); }
+  std::vector<float> hD(256 * 128); int st;
+  CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0; int bad = 0;
+  for (int m = 0; m < 256; ++m)
+    for (int n = 0; n < 128; ++n) {
+      double ref = 0;
+      for (int k = 0; k < 64; ++k) ref += bf2f(hA[m * 64 + k]) * bf2f(hB[n * 64 + k]);
+      const double err = fabs(ref - hD[m * 128 + n]);
+      if (err > maxerr) maxerr = err;
+      if (err > 1e-3) ++bad;
+    }
+  printf("  CTA pair fed by TMA, one barrier in the leader, remote arrive: status=%d bad=%d/32768 maxerr=%.4g  %s\n", st, bad, maxerr,
+         (bad == 0 && st == 0) ? "OK" : "MISMATCH");
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dS);
+  return bad == 0 && st == 0;
+}
+
 int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "t8")) { run_mma_walk(); return 0; }
+  if (argc > 1 && !strcmp(argv[1], "t11")) { printf("T11 CTA pair plumbing\n"); return run_pair_tma_probe(get_encode()) ? 0 : 1; }
+  if (argc > 1 && !strcmp(argv[1], "t10")) { printf("T10 cta_group::2\n"); return run_mma_pair_probe() ? 0 : 1; }
   if (argc > 1 && !strcmp(argv[1], "t9")) { printf("T9 A operand in tensor memory\n"); return run_mma_ts_probe() ? 0 : 1; }
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s sm_%d%d, %d SMs, smem/block optin %zu\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount, prop.sharedMemPerBlockOptin);
