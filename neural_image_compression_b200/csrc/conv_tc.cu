@@ -1815,12 +1815,8 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     if (int rc = encode_nhwc(&map_o, y, on, oh, ow, ctot, kTileW, kTileH, tt.out_stride, p.tma_out == 2 ? 4 : 2)) return rc;
   } else map_o = map_w;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), "cudaFuncSetAttribute")) return rc;
-    if (int rc = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem), "cudaFuncSetAttribute")) return rc;
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_kernel<false>), kMaxDynSmem)) return rc;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_kernel<true>), kMaxDynSmem)) return rc;
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
   if (p.pair) {
     if (p.mt != 2 || p.swap || p.b_resident || grid % 2) return fail(NIC_E_UNSUPPORTED, "conv tc: CTA-pair launch with an unsupported tiling");
@@ -1855,11 +1851,7 @@ static int launch_first(const nic_conv_desc* d, const void* x, const void* w_pac
   if (int rc = encode_2d(&map_w, w_packed, 128, 128, 64, 128)) return rc;
   if (int rc = encode_2d(&map_g, gdn_gamma, 128, 128, 64, 128)) return rc;
   if (int rc = encode_nhwc(&map_o, y, d->n, d->h_out, d->w_out, 128, kTileW, kTileH, 1, 2)) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048), "cudaFuncSetAttribute")) return rc;
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_first_tc_kernel), 232448 - 2048)) return rc;
   const int grid = f.total_tiles < kNumSMs ? f.total_tiles : kNumSMs;
   conv_first_tc_kernel<<<grid, kFirstThreads, smem_bytes, st>>>(map_w, map_g, map_o, p, f);
   return check_launch("conv_first_tc_kernel");

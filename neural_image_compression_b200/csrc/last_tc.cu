@@ -310,12 +310,8 @@ int conv_last_scatter_x3(const nic_conv_desc* d, const void* x, const void* w_pa
   CUtensorMap map_a, map_w;
   if (int rc = encode_nhwc(&map_a, x, d->n, d->h_in, d->w_in, 2 * d->c_in, kBW, kBH, 1, 2)) return rc;
   if (int rc = encode_2d(&map_w, w_packed, d->c_in, 2 * kN, 64, kN)) return rc;
-  static bool attr_set[2] = {false, false};
   auto kern = p.kc == 2 ? last_scatter_x3_kernel<2> : last_scatter_x3_kernel<3>;
-  if (!attr_set[p.kc - 2]) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
-    attr_set[p.kc - 2] = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem_bytes)) return rc;
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
   if (int rc = check_cuda(launch_pdl(kern, grid, kThreads, smem_bytes, st, map_a, map_w, p), "last_scatter_x3_kernel launch")) return rc;
   return check_launch("last_scatter_x3_kernel");

@@ -3,6 +3,10 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 
 namespace nic {
@@ -17,6 +21,20 @@ int encode_image_patch(CUtensorMap* m, const void* base, int n, int c, int h, in
 // one device int per process: the kernels' "a bounded wait expired" flag (nic_pipeline_status)
 int* status_word();
 extern void* g_trace_buffer;
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device): function attributes belong to a device's context, so a
+// process that drives several GPUs needs it on each of them (a plain `static bool` was right only for one process per GPU)
+inline int ensure_dyn_smem(const void* kernel, int bytes) {
+  static std::mutex m;
+  static std::vector<std::pair<const void*, int>> done;
+  int dev = 0;
+  if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  std::lock_guard<std::mutex> g(m);
+  for (const auto& e : done) if (e.first == kernel && e.second == dev) return 0;
+  if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute")) return rc;
+  done.emplace_back(kernel, dev);
+  return 0;
+}
 
 // Launch with the programmatic-stream-serialization attribute when NIC_PDL=1 (see tc_primitives.cuh: pdl_wait /
 // pdl_launch_dependents).  Measured inside the CUDA-graph replay of the forward pass: no difference beyond run-to-run noise

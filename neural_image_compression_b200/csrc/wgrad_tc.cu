@@ -261,11 +261,7 @@ int wgrad_tc_launch(const nic_conv_desc* d, const void* x_pair, const void* g_pa
   CUtensorMap map_big, map_small;
   if (int rc = encode_nhwc(&map_big, big, d->n, hb, wb, 2 * p.cb, p.pw, p.ph, d->stride, 2)) return rc;
   if (int rc = encode_nhwc(&map_small, small, d->n, p.hs, p.ws, 2 * p.cs, 8, 8, 1, 2)) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgMaxDynSmem), "cudaFuncSetAttribute")) return rc;
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(wgrad_tc_kernel), kWgMaxDynSmem)) return rc;
   wgrad_tc_kernel<<<pl.grid, kWgThreads, pl.smem_bytes, st>>>(map_big, map_small, p);
   *splits_out = p.splits;
   return check_launch("wgrad_tc_kernel");

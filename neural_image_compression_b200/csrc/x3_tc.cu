@@ -1275,12 +1275,8 @@ static int launch_gdn_c(const void* x, int pair_in, long npix, int inverse, cons
   if (int rc = encode_2d(&map_g, gamma_packed, c, 2 * c, 64, 64)) return rc;
   if (int rc = encode_2d(&map_o, y, 2 * c, static_cast<uint64_t>(npix), 64, 128)) return rc;
   const int smem_bytes = kGRing * 2 * kPiece + 2 * NP * kPanel + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(gdn_x3c_kernel<NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
-    if (int rc = check_cuda(cudaFuncSetAttribute(gdn_x3c_kernel<NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gdn_x3c_kernel<NP, false>), smem_bytes)) return rc;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gdn_x3c_kernel<NP, true>), smem_bytes)) return rc;
   const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
   if (int rc = check_cuda(pair_in ? launch_pdl(gdn_x3c_kernel<NP, true>, grid, (4 * NP + 2) * 32, smem_bytes, st, map_x, map_g, map_o, p)
                                   : launch_pdl(gdn_x3c_kernel<NP, false>, grid, (4 * NP + 2) * 32, smem_bytes, st, map_x, map_g, map_o, p),
@@ -1310,22 +1306,14 @@ int gdn_fwd_tc_x3(const void* x, int pair_in, long npix, int c, int inverse, con
     CUtensorMap map_o32;
     if (int rc = encode_2d_c32(&map_o32, y, 256, static_cast<uint64_t>(npix), 32)) return rc;
     const int smem_ts = 14 * kPanel + 1024;
-    static bool ts_attr_set = false;
-    if (!ts_attr_set) {
-      if (int rc = check_cuda(cudaFuncSetAttribute(gdn_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ts), "cudaFuncSetAttribute")) return rc;
-      ts_attr_set = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gdn_ts_kernel), smem_ts)) return rc;
     const int grid_ts = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
     if (int rc = check_cuda(launch_pdl(gdn_ts_kernel, grid_ts, kGtThreads, smem_ts, st, map_x, map_g, map_o32, p), "gdn_ts_kernel launch")) return rc;
     return check_launch("gdn_ts_kernel");
   }
   const int smem_bytes = 12 * kPanel + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(gdn_x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
-    if (int rc = check_cuda(cudaFuncSetAttribute(gdn_x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gdn_x3_kernel<false>), smem_bytes)) return rc;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gdn_x3_kernel<true>), smem_bytes)) return rc;
   const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
   if (int rc = check_cuda(pair_in ? launch_pdl(gdn_x3_kernel<true>, grid, kGdnThreads, smem_bytes, st, map_x, map_g, map_o, p)
                                   : launch_pdl(gdn_x3_kernel<false>, grid, kGdnThreads, smem_bytes, st, map_x, map_g, map_o, p),
@@ -1357,11 +1345,9 @@ int conv_first_x3(const nic_conv_desc* d, const void* x, const void* w_packed, c
   CUtensorMap map_w, map_img;
   if (int rc = encode_2d(&map_w, w_packed, 192, f.cout, 64, f.cout)) return rc;
   if (int rc = encode_image_patch(&map_img, x, d->n, 3, d->h_in, d->w_in, kPatchW, kPatchH)) return rc;
-  static int attr_bytes = 0;
-  if (attr_bytes < smem_bytes) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(conv_first_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
-    attr_bytes = smem_bytes;
-  }
+  // (the attribute is set once per device to the larger of the two layouts, c_out = 192)
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_first_x3_kernel),
+                               6 * kPanel + 3 * 192 * 128 + 8 * 32 * kScratchRow + 2 * kPatchStride + 1024 + 64)) return rc;
   const int grid = f.total_tiles < kNumSMs ? f.total_tiles : kNumSMs;
   conv_first_x3_kernel<<<grid, kF3Threads, smem_bytes, st>>>(map_w, map_img, f);
   return check_launch("conv_first_x3_kernel");
@@ -1388,11 +1374,7 @@ int conv_first_gdn_x3(const nic_conv_desc* d, const void* x, const void* w_packe
   if (int rc = encode_2d(&map_g, gamma_packed, 128, 256, 64, 128)) return rc;
   if (int rc = encode_image_patch(&map_img, x, d->n, 3, d->h_in, d->w_in, kPatchW, kPatchH)) return rc;
   if (int rc = encode_nhwc_c32(&map_o, y, d->n, d->h_out, d->w_out, 256, 8, 4)) return rc;      // one store box per worker warp
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(first_fused_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "cudaFuncSetAttribute")) return rc;
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(first_fused_x3_kernel), smem_bytes)) return rc;
   const int grid = f.total_tiles < kNumSMs ? f.total_tiles : kNumSMs;
   if (int rc = check_cuda(launch_pdl(first_fused_x3_kernel, grid, kFfThreads, smem_bytes, st, map_w, map_g, map_img, map_o, f), "first_fused_x3_kernel launch")) return rc;
   return check_launch("first_fused_x3_kernel");
