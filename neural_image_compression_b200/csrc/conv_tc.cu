@@ -1673,8 +1673,10 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     const long per_phase = static_cast<long>(tx2) * ty2 * p.n;
     // measured (bf16x3, 16 images, same box, results bit-identical): g_a layer 2 743.8 -> 709.3 us, layer 3 212.1 -> 201.6, g_s layer 3
     // 1040.7 -> 1018.7 (against the swapped one-CTA form); g_s layer 2 (1536 tiles in four phases) 271.0 -> 278.4: stays unpaired
-    const bool worth = tt.nphases == 1 || per_phase * tt.nphases >= 16 * kNumSMs;
-    pair = (pair_env ? atoi(pair_env) != 0 : worth) && !flat && p.nb == 128 && p.n_ntiles == 1 && p.wp > kTileW && per_phase % 2 == 0 &&
+    // bf16x3 only by default: the single-pass bf16 arm LOSES with it (whole step 1.79 -> 1.89 ms); never together with the fused GDN
+    // epilogue, whose own MMAs and commits are cta_group::1 (a kernel should not mix the two forms)
+    const bool worth = x3 && (tt.nphases == 1 || per_phase * tt.nphases >= 16 * kNumSMs);
+    pair = (pair_env ? atoi(pair_env) != 0 : worth) && !gdn && !flat && p.nb == 128 && p.n_ntiles == 1 && p.wp > kTileW && per_phase % 2 == 0 &&
            per_phase * tt.nphases >= 2 * kNumSMs && !getenv("NIC_TC_MT");
     if (pair) swap = false;
   }
@@ -1713,7 +1715,9 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     static const bool interleave = !(getenv("NIC_TC_PHASE_ORDER") && atoi(getenv("NIC_TC_PHASE_ORDER")) == 0);
     // measured (bf16x3, 16 images): g_s layer 3 (6144 tiles) 1109 -> 1031 us; layer 2 (1536 tiles, input L2-resident either way)
     // 272.7 -> 273.7, layer 1 (384 tiles) 85.5 -> 88.8 - so only where the input cannot stay in L2 across the phase passes
-    if (interleave && p.nphases > 1 && p.n_ntiles == 1 && kNumSMs % p.nphases == 0 && p.total_tiles >= 16 * kNumSMs) {
+    // (... i.e. the input does not fit L2: the single-pass bf16 arm's 100 MB input does, and loses 25 us of 1.85 ms to the order)
+    const double in_bytes = static_cast<double>(d->n) * d->h_in * d->w_in * d->c_in * (x3 ? 4 : 2);
+    if (interleave && in_bytes > 112e6 && p.nphases > 1 && p.n_ntiles == 1 && kNumSMs % p.nphases == 0 && p.total_tiles >= 16 * kNumSMs) {
       p.pos_per_wave = kNumSMs / p.nphases;
       if (pair) {
         const long slots = static_cast<long>(p.spatial_tiles / 2) * p.nphases, half = kNumSMs / 2;
