@@ -288,3 +288,14 @@ def test_cta_pair_form_is_bit_identical_to_the_one_cta_form(kind, precision, mon
     torch.cuda.synchronize()
     assert _lib.load().nic_pipeline_status() == 0
     assert torch.equal(ref.view(torch.int16), out.view(torch.int16))
+    if precision == "bf16x3":       # and both are the conv: torch's fp32 conv (TF32 off) of the same hi + lo input
+        xin = (x[..., :128].float() + x[..., 128:].float()).permute(0, 3, 1, 2).contiguous()
+        tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            want = conv(xin)
+        finally:
+            torch.backends.cudnn.allow_tf32 = tf32
+        want = F.leaky_relu(want, 0.01) if kind == "conv" else want
+        got = (out[..., :128].float() + out[..., 128:].float()).permute(0, 3, 1, 2)
+        assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()

@@ -1,5 +1,7 @@
+"""CTA-pair form of conv_tc_kernel against the one-CTA form, bit for bit, on the layer shapes of the M = 128 model (GPU box):
+    python tools/pair_check.py"""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn as nn
 from neural_image_compression_b200 import engine, _lib
 from neural_image_compression_b200._lib import EPI_BIAS, EPI_GDN, EPI_IGDN, EPI_LRELU
