@@ -209,6 +209,7 @@ struct TcParams {
   int b_slot_bytes;                            // stride of the weight ring: 16 KB (a 128-row slab), 8 KB in pair mode (64 rows per CTA)
   int pair;                                    // conv_tc_kernel<true>: clusters of two CTAs, cta_group::2 MMAs
   int chunk_perm;                              // bf16x3: K chunks c-slice by c-slice (kchunk in the kernel)
+  int tail_first, tail_n;                      // last wave in half tiles: first virtual slot, number of tiles split (0 = off)
   int nt_inner;                                // N tile innermost in the tile order (decode_tile)
   int pos_per_wave, spatial_tiles;             // phase-interleaved tile order (decode_tile); pos_per_wave = 0: phase-major
   int nchunks;                                 // K chunks of 64 (cin / 64; 3 cin / 64 in the bf16x3 arm)
@@ -306,6 +307,10 @@ __device__ __forceinline__ bool decode_tile(const TcParams& p, int tile, int& nt
     ty = s % p.tiles_y; img = s / p.tiles_y;
     return true;
   }
+  if (p.tail_n && tile >= p.tail_first) {   // last wave in half tiles (tail_block): slot k -> its tile
+    const int k = tile - p.tail_first;
+    tile = p.tail_first + (p.pair ? ((k >> 2) << 1) + (k & 1) : k >> 1);
+  }
   if (p.nt_inner) {                       // N tile innermost: the CTAs of one wave share their input tiles, not their weights
     ntile = tile % p.n_ntiles; tile /= p.n_ntiles;
     tx = tile % p.tiles_x; tile /= p.tiles_x;
@@ -319,6 +324,15 @@ __device__ __forceinline__ bool decode_tile(const TcParams& p, int tile, int& nt
   phase = tile % p.nphases; tile /= p.nphases;
   ntile = tile;
   return true;
+}
+
+// Last wave in half tiles: when the tiles left over after the full waves would occupy fewer than half of the CTAs (g_a layer 2:
+// 1536 tiles = 10 waves of 148 + 56), each of them is done as two one-block slots on two CTAs (pair form: on two clusters) - the
+// layer ends after 10.5 tile times instead of 11.  Returns the block a slot computes, or -1 for a whole tile.
+__device__ __forceinline__ int tail_block(const TcParams& p, int tile) {
+  if (!p.tail_n || tile < p.tail_first) return -1;
+  const int k = tile - p.tail_first;
+  return p.pair ? (k >> 1) & 1 : k & 1;
 }
 
 // number of M blocks of the tile that contain at least one real output pixel
@@ -987,7 +1001,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // swapped orientation: issuer 0 alone issues N = 256 MMAs (weights first, the pixels of both blocks second) into the
           // whole 256-column buffer; issuer 1 walks the rings and only commits
           const uint32_t d_tmem = tmem + buf * 256 + (swp ? 0 : mw * 128);
-          const bool live = swp ? mw == 0 : mw < nblk;
+          const int only = tail_block(p, tile);
+          const bool live = swp ? mw == 0 : (mw < nblk && (only < 0 || mw == only));
           uint32_t accumulate = 0;
           if (nplanes == 1 && ph.plane_tap_begin[1] - ph.plane_tap_begin[0] == 1) {
             // one tap per K chunk (1x1 convs): the per-chunk bookkeeping of the generic loop below (one ring wait, one elect / warp
@@ -1119,6 +1134,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                      warp == kFirstEpiWarp && lane == 0, img, ty, tx, ph.py, ph.px, ntile * p.nb, nblk);
       } else
       for (int b = 0; b < nblk && ok && !(p.dbg & 8); ++b)
+        if (const int only = tail_block(p, tile); only < 0 || b == only)
         ok = epilogue_block<kEpiWarps>(p, &sb, s_bias, s_beta, sq, smem + p.off_gamma, &map_o, tmem + buf * 256 + b * 128, q, lane,
                                        (warp - kFirstEpiWarp) >> 2, warp == kFirstEpiWarp && lane == 0, img, ty * p.tile_h + p.blk_roff[b],
                                        tx * p.tile_w + p.blk_coff[b], ph.py, ph.px, ntile * p.nb, gdn_count, b == 0 ? tcount : 0xffffffffu);
@@ -1723,6 +1739,16 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
         const long slots = static_cast<long>(p.spatial_tiles / 2) * p.nphases, half = kNumSMs / 2;
         p.total_tiles = static_cast<int>((slots + half - 1) / half) * kNumSMs;
       } else p.total_tiles = (p.spatial_tiles + p.pos_per_wave - 1) / p.pos_per_wave * kNumSMs;      // virtual slots: waves x grid
+    }
+  }
+  p.tail_first = 0; p.tail_n = 0;
+  {
+    static const bool tail = !(getenv("NIC_TC_TAIL") && atoi(getenv("NIC_TC_TAIL")) == 0);
+    const int rem = p.total_tiles % kNumSMs;
+    if (tail && !p.swap && p.mt == 2 && p.n_ntiles == 1 && p.nphases == 1 && !p.pos_per_wave && !p.nt_inner && p.nb == 128 &&
+        p.total_tiles > 4 * kNumSMs && rem > 0 && 2 * rem <= kNumSMs && rem % 2 == 0) {
+      p.tail_first = p.total_tiles - rem; p.tail_n = rem;
+      p.total_tiles = p.tail_first + 2 * rem;
     }
   }
   p.nslabs = tt.ntaps;
