@@ -277,11 +277,11 @@ __device__ __forceinline__ void trace(const TcParams& p, uint32_t tile_iter, int
 }
 
 // Tile order.  Default: x, y, image, phase, N tile (phase-major: consecutive tiles cost the same, the static round robin over
-// the CTAs is balanced).  Transposed convs on a full grid use the phase-interleaved order instead: wave w (one tile per CTA)
-// covers pos_per_wave = grid / nphases spatial tiles in ALL phases at once - CTA c takes position c / nphases in phase
-// (c + w) % nphases, so every CTA still cycles through the phases - and the input patch a phase reads is in L2 from its sibling
-// phases (phase-major re-read the whole input from DRAM once per phase: g_s layer 3, 809 MB for a 201 MB input).
-// Returns false for the unused slots of the last wave (always a CTA's last iteration).
+// the CTAs is balanced).  Transposed convs whose input does not fit L2 use a phase-interleaved order instead (pos_per_wave != 0):
+// consecutive slots are the phases (x N tiles) of ONE spatial tile, so the input patch a phase reads is in L2 from its sibling
+// phases (phase-major re-read the whole input from DRAM once per phase: g_s layer 3, 809 MB for a 201 MB input), and the phase of
+// a slot is rotated by its position so that every CTA still cycles through the cheap and the expensive phases.
+// Returns false for the unused slots of the last wave of the pair form (always a CTA's last iteration).
 __device__ __forceinline__ bool decode_tile(const TcParams& p, int tile, int& ntile, int& phase, int& img, int& ty, int& tx) {
   if (p.pos_per_wave && p.pair) {
     // CTA pairs: cluster k of wave w takes pair slot u = w * grid / 2 + k: the pair of adjacent spatial tiles u / nphases in phase
@@ -298,11 +298,13 @@ __device__ __forceinline__ bool decode_tile(const TcParams& p, int tile, int& nt
     return true;
   }
   if (p.pos_per_wave) {
-    const int w = tile / static_cast<int>(gridDim.x), c = tile - w * static_cast<int>(gridDim.x);
-    int s = w * p.pos_per_wave + c / p.nphases;
-    if (s >= p.spatial_tiles) return false;
-    ntile = 0;
-    phase = (c + w) % p.nphases;
+    // one-CTA form: slot u is variant u % V (V = phases x N tiles) of spatial tile u / V, the phase rotated by the position so that
+    // a CTA (u = c + wave x grid) keeps cycling through the phases; consecutive CTAs work on the V variants of one input region
+    const int V = p.nphases * p.n_ntiles;
+    int s = tile / V;
+    const int v = tile - s * V;
+    ntile = v % p.n_ntiles;
+    phase = (v / p.n_ntiles + s) % p.nphases;
     tx = s % p.tiles_x; s /= p.tiles_x;
     ty = s % p.tiles_y; img = s / p.tiles_y;
     return true;
@@ -1733,12 +1735,12 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     // 272.7 -> 273.7, layer 1 (384 tiles) 85.5 -> 88.8 - so only where the input cannot stay in L2 across the phase passes
     // (... i.e. the input does not fit L2: the single-pass bf16 arm's 100 MB input does, and loses 25 us of 1.85 ms to the order)
     const double in_bytes = static_cast<double>(d->n) * d->h_in * d->w_in * d->c_in * (x3 ? 4 : 2);
-    if (interleave && in_bytes > 112e6 && p.nphases > 1 && p.n_ntiles == 1 && kNumSMs % p.nphases == 0 && p.total_tiles >= 16 * kNumSMs) {
-      p.pos_per_wave = kNumSMs / p.nphases;
+    if (interleave && in_bytes > 112e6 && p.nphases > 1 && p.total_tiles >= 16 * kNumSMs) {
+      p.pos_per_wave = 1;                      // (a flag now: both interleaved orders are computed from the slot index)
       if (pair) {
         const long slots = static_cast<long>(p.spatial_tiles / 2) * p.nphases, half = kNumSMs / 2;
-        p.total_tiles = static_cast<int>((slots + half - 1) / half) * kNumSMs;
-      } else p.total_tiles = (p.spatial_tiles + p.pos_per_wave - 1) / p.pos_per_wave * kNumSMs;      // virtual slots: waves x grid
+        p.total_tiles = static_cast<int>((slots + half - 1) / half) * kNumSMs;      // virtual slots: waves x grid
+      }
     }
   }
   p.tail_first = 0; p.tail_n = 0;
@@ -1787,8 +1789,10 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
   p.b_resident = (p.n_ntiles == 1 && p.nb <= 16 && bres_bytes + 2 * p.slot_bytes + gdn_bytes + 1024 <= kMaxDynSmem) ? 1 : 0;
   {
     static const bool perm = !(getenv("NIC_TC_CHUNK_PERM") && atoi(getenv("NIC_TC_CHUNK_PERM")) == 0);
-    // only where the input cannot stay in L2 anyway (the 8 x 256 x 256 training step, whose inputs do, is 30 us faster without it)
-    p.chunk_perm = (perm && x3 && !p.b_resident && static_cast<double>(d->n) * d->h_in * d->w_in * d->c_in * 4 > 112e6) ? 1 : 0;
+    // For every size, although it only pays when the input cannot stay in L2 (the 8 x 256 x 256 training step, whose inputs do, is
+    // 30 us of 3.8 ms faster without it): the chunk order is the fp32 accumulation order, and a pixel's value must not depend on the
+    // size of the image or batch around it (tests/test_gpu_scalable.py compares a crop with the full image symbol for symbol)
+    p.chunk_perm = (perm && x3 && !p.b_resident) ? 1 : 0;
   }
   p.b_slot_bytes = p.pair ? 64 * 128 : 128 * 128;
   if (p.b_resident) p.lo_flag = nullptr;          // resident weights are indexed by chunk position: always the full list

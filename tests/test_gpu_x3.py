@@ -302,3 +302,23 @@ def test_cta_pair_form_is_bit_identical_to_the_one_cta_form(kind, precision, mon
         want = F.leaky_relu(want, 0.01) if not kind.startswith("convT") else want
         got = (out[..., :128].float() + out[..., 128:].float()).permute(0, 3, 1, 2)
         assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
+
+
+def test_phase_interleaved_tile_order_with_two_n_tiles(monkeypatch):
+    """Transposed conv to 192 channels (two N tiles) on an input larger than L2 - g_s of the M = 192 models at 2048 x 1536: the
+    phase-interleaved tile order (decode_tile) must give exactly what the phase-major order gives."""
+    from neural_image_compression_b200 import engine, _lib
+    from neural_image_compression_b200._lib import EPI_BIAS
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    conv = nn.ConvTranspose2d(192, 192, 5, 2, 2, output_padding=1).to(dev)
+    op = engine.ConvOp(conv, EPI_BIAS)
+    b, h, w = 1, 512, 768
+    x = engine.to_pair(torch.randn(b, h, w, 192, device=dev))
+    monkeypatch.setenv("NIC_TC_PHASE_ORDER", "0")
+    ref = op.run(x, b, h, w, "bf16x3").clone()
+    monkeypatch.setenv("NIC_TC_PHASE_ORDER", "1")
+    out = op.run(x, b, h, w, "bf16x3").clone()
+    torch.cuda.synchronize()
+    assert _lib.load().nic_pipeline_status() == 0
+    assert torch.equal(ref.view(torch.int16), out.view(torch.int16))
