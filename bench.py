@@ -452,10 +452,10 @@ def main():
     achieved = k2_flops * B / (k2_ms / 1e3) / 1e12
     peak = peaks["bf16_burst"]
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full captures
-    # (bf16x3: 882.2 MB + 181.4 MB, profiles/r2_ncu_full_k2.txt; algorithmic: 805.3 MB of pair input + 201.3 MB of output +
+    # (bf16x3: 908.2 MB + 179.4 MB, profiles/r2_ncu_full_k2.txt; algorithmic: 805.3 MB of pair input + 201.3 MB of output +
     #  2.5 MB of weights - the hi patches are fetched twice per tile, a tenth of the second fetches reach DRAM;
     #  bf16: 403.8 MB + 83.3 MB, profiles/r1_ncu_full_v6_k2_bf16.txt)
-    k2_traffic = {"bf16": 487.1e6, "bf16x3": 1063.6e6}.get(kern_prec) if B == 16 else None
+    k2_traffic = {"bf16": 487.1e6, "bf16x3": 1087.6e6}.get(kern_prec) if B == 16 else None
     passes = 3 if kern_prec == "bf16x3" else 1
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": k2_traffic,
                 "kernel": k2_kernel, "ms_per_launch": k2_ms, "mma_passes": passes, "tensor_pipe_frac": passes * achieved / peak,
