@@ -498,8 +498,10 @@ gdn_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 // was ring-latency bound (traced: 1600 clk for each of the 9 steps of a tile, 23.5k clk per tile); with 8 pairs in flight the MMA
 // loop runs at the tensor rate and the price is that a tile's load no longer overlaps the previous tile's arithmetic.
 // ---------------------------------------------------------------------------------------------
-constexpr int kGRing = 8;                       // ring slots of one (g_hi, g_lo) piece pair
-constexpr int kPiece = 64 * 128;                // [64 out rows][64 in] bf16, 128-byte swizzle
+constexpr int kGRing = 2;                       // ring slots of one (g_hi, g_lo) piece pair
+constexpr int kPiece = 64 * 128;                // [64 out rows][64 in] bf16, 128-byte swizzle; a ring piece is NP of them: ALL C output
+                                                // rows x 64 inputs, the B operand of an N = C MMA (N = 64 MMAs cost 67 clk each - as much
+                                                // as N = 128 - so the (n, k) pieces of the first version spent 108 x 67 clk per tile at C = 192)
 
 struct __align__(8) GdnCBarriers {
   uint64_t x_full, x_empty, sq_ready, g_full[kGRing], g_empty[kGRing], mma_done;
@@ -515,7 +517,7 @@ gdn_x3c_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;                            // kGRing x [g_hi piece | g_lo piece]
-  uint8_t* bufs = smem + kGRing * 2 * kPiece;      // the tile buffer, 2 NP panels: [hi 0 | lo 0 | hi 1 | lo 1 | ...] once squared
+  uint8_t* bufs = smem + kGRing * 2 * NP * kPiece; // the tile buffer, 2 NP panels: [hi 0 | lo 0 | hi 1 | lo 1 | ...] once squared
   __shared__ GdnCBarriers sb;
   __shared__ __align__(16) float s_beta[C];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -541,11 +543,11 @@ gdn_x3c_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     //  N = 64 MMA; this warp has nothing else to do)
     if (lane == 0) {
       tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_o);
-      const uint32_t idesc = umma_idesc_bf16(128, 64);
+      const uint32_t idesc = umma_idesc_bf16(128, C);
       const uint32_t hi = umma_desc_hi(1024);
       const uint32_t sq = umma_desc_lo(smem_u32(bufs));
       const uint32_t r0 = umma_desc_lo(smem_u32(ring));
-      constexpr uint32_t P = kPanel >> 4, PP = kPiece >> 4;
+      constexpr uint32_t P = kPanel >> 4, PP = (NP * kPiece) >> 4;
       uint32_t it = 0, step = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < p.ntiles && ok; tile += gridDim.x, ++it) {
@@ -558,41 +560,35 @@ gdn_x3c_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (!wait_abort(&sb.sq_ready, it & 1, &sb.abort_flag, p.status)) break;          // the workers have written the squares
         tcgen05_fence_after();
 #pragma unroll
-        for (int n = 0; n < NP; ++n) {
+        for (int k = 0; k < NP; ++k, ++step) {       // input-channel group k: squares panel k against the [C x 64] gamma piece k
+          const uint32_t s = step % kGRing;
+          if (!wait_abort(&sb.g_full[s], (step / kGRing) & 1, &sb.abort_flag, p.status)) { ok = false; break; }
+          tcgen05_fence_after();
+          const uint32_t gh = r0 + s * 2 * PP, gl = gh + PP, sh = sq + 2 * k * P, sl = sh + P;
 #pragma unroll
-          for (int k = 0; k < NP; ++k, ++step) {
-            const uint32_t s = step % kGRing;
-            if (!wait_abort(&sb.g_full[s], (step / kGRing) & 1, &sb.abort_flag, p.status)) { ok = false; break; }
-            tcgen05_fence_after();
-            const uint32_t gh = r0 + s * 2 * PP, gl = gh + PP, sh = sq + 2 * k * P, sl = sh + P;
-            const uint32_t d = tmem + n * 64;
+          for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(tmem, sh + kk * 2, hi, gh + kk * 2, hi, idesc, (k | kk) ? 1u : 0u);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(d, sh + kk * 2, hi, gh + kk * 2, hi, idesc, (k | kk) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(tmem, sh + kk * 2, hi, gl + kk * 2, hi, idesc, 1);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(d, sh + kk * 2, hi, gl + kk * 2, hi, idesc, 1);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(d, sl + kk * 2, hi, gh + kk * 2, hi, idesc, 1);
-            umma_commit(&sb.g_empty[s]);
-          }
-          if (!ok) break;
+          for (int kk = 0; kk < 4; ++kk) umma_bf16_lohi(tmem, sl + kk * 2, hi, gh + kk * 2, hi, idesc, 1);
+          umma_commit(&sb.g_empty[s]);
         }
         umma_commit(&sb.mma_done);
       }
     }
   } else if (warp == kWorkers + 1) {
-    // ===================== gamma ring: every (n, k) piece pair once per tile =====================
+    // ===================== gamma ring: the NP piece pairs once per tile =====================
     if (lane == 0) {
       tma_prefetch_desc(&map_g);
       uint32_t step = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < p.ntiles && ok; tile += gridDim.x) {
-        for (int nk = 0; nk < NP * NP; ++nk, ++step) {
+        for (int k = 0; k < NP; ++k, ++step) {
           const uint32_t s = step % kGRing;
           if (!wait_abort(&sb.g_empty[s], ((step / kGRing) & 1) ^ 1, &sb.abort_flag, p.status)) { ok = false; break; }
-          const int n = nk / NP, k = nk % NP;
-          mbar_expect_tx(&sb.g_full[s], 2 * kPiece);
-          tma_load_2d(ring + s * 2 * kPiece, &map_g, &sb.g_full[s], k * 64, n * 64);                 // g_hi[n][k]
-          tma_load_2d(ring + s * 2 * kPiece + kPiece, &map_g, &sb.g_full[s], k * 64, C + n * 64);     // g_lo[n][k]
+          mbar_expect_tx(&sb.g_full[s], 2 * NP * kPiece);
+          tma_load_2d(ring + s * 2 * NP * kPiece, &map_g, &sb.g_full[s], k * 64, 0);                     // g_hi[:, 64 k .. 64 k + 63]
+          tma_load_2d(ring + s * 2 * NP * kPiece + NP * kPiece, &map_g, &sb.g_full[s], k * 64, C);       // g_lo
         }
       }
     }
@@ -1272,9 +1268,9 @@ static int launch_gdn_c(const void* x, int pair_in, long npix, int inverse, cons
   CUtensorMap map_x, map_g, map_o;
   if (pair_in) { if (int rc = encode_2d(&map_x, x, 2 * c, static_cast<uint64_t>(npix), 64, 128)) return rc; }
   else if (int rc = encode_2d_ex(&map_x, x, 4, c, static_cast<uint64_t>(npix), 32, 128)) return rc;
-  if (int rc = encode_2d(&map_g, gamma_packed, c, 2 * c, 64, 64)) return rc;
+  if (int rc = encode_2d(&map_g, gamma_packed, c, 2 * c, 64, c)) return rc;
   if (int rc = encode_2d(&map_o, y, 2 * c, static_cast<uint64_t>(npix), 64, 128)) return rc;
-  const int smem_bytes = kGRing * 2 * kPiece + 2 * NP * kPanel + 1024;
+  const int smem_bytes = kGRing * 2 * NP * kPiece + 2 * NP * kPanel + 1024;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gdn_x3c_kernel<NP, false>), smem_bytes)) return rc;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gdn_x3c_kernel<NP, true>), smem_bytes)) return rc;
   const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
