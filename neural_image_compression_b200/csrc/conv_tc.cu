@@ -283,16 +283,16 @@ __device__ __forceinline__ void trace(const TcParams& p, uint32_t tile_iter, int
 // a slot is rotated by its position so that every CTA still cycles through the cheap and the expensive phases.
 // Returns false for the unused slots of the last wave of the pair form (always a CTA's last iteration).
 __device__ __forceinline__ bool decode_tile(const TcParams& p, int tile, int& ntile, int& phase, int& img, int& ty, int& tx) {
-  if (p.pos_per_wave && p.pair) {
-    // CTA pairs: cluster k of wave w takes pair slot u = w * grid / 2 + k: the pair of adjacent spatial tiles u / nphases in phase
-    // (u + u / nphases) % nphases - four consecutive clusters cover the four phases of one pair of tiles
-    const int half = static_cast<int>(gridDim.x) >> 1;
-    const int w = tile / static_cast<int>(gridDim.x), c = tile - w * static_cast<int>(gridDim.x);
-    const int u = w * half + (c >> 1), pp = u / p.nphases;
-    int s = 2 * pp + (c & 1);
+  if (p.pair && (p.pos_per_wave || p.n_ntiles > 1)) {
+    // CTA pairs: cluster slot u = tile / 2 is variant u % V (V = phases x N tiles) of the pair of adjacent spatial tiles u / V - the
+    // two CTAs of a cluster share phase and N tile (the weights), consecutive clusters cover the variants of one input region;
+    // in the interleaved order the phase is rotated by the position so that a cluster keeps cycling through the phases
+    const int V = p.nphases * p.n_ntiles;
+    const int u = tile >> 1, pp = u / V, v = u - pp * V;
+    int s = 2 * pp + (tile & 1);
     if (s >= p.spatial_tiles) return false;
-    ntile = 0;
-    phase = (u - pp * p.nphases + pp) % p.nphases;
+    ntile = v % p.n_ntiles;
+    phase = (v / p.n_ntiles + (p.pos_per_wave ? pp : 0)) % p.nphases;
     tx = s % p.tiles_x; s /= p.tiles_x;
     ty = s % p.tiles_y; img = s / p.tiles_y;
     return true;
@@ -742,7 +742,7 @@ __device__ __forceinline__ bool epilogue_tile_swapped(const TcParams& p, const f
 // slab); the leader's two issuing warps issue M = 256 MMAs over both CTAs' blocks and multicast the ring / accumulator commits;
 // both CTAs' loads signal the leader's "full" barriers, both CTAs' epilogues release the leader's accumulator barriers.  Per MMA
 // an SM then reads 4 KB of pixels + 2 KB of weights (96 B/clk) and fills half the weight bytes: the N = 128 mainloop stops being
-// bound by shared-memory bandwidth.  Normal orientation, weight ring, one N tile only.
+// bound by shared-memory bandwidth.  Normal orientation, weight ring, one or two N tiles.
 template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -1694,7 +1694,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     // bf16x3 only by default: the single-pass bf16 arm LOSES with it (whole step 1.79 -> 1.89 ms); never together with the fused GDN
     // epilogue, whose own MMAs and commits are cta_group::1 (a kernel should not mix the two forms)
     const bool worth = x3 && (tt.nphases == 1 || per_phase * tt.nphases >= 16 * kNumSMs);
-    pair = (pair_env ? atoi(pair_env) != 0 : worth) && !gdn && !flat && p.nb == 128 && p.n_ntiles == 1 && p.wp > kTileW && per_phase % 2 == 0 &&
+    pair = (pair_env ? atoi(pair_env) != 0 : worth) && !gdn && !flat && p.nb == 128 && p.n_ntiles <= 2 && p.wp > kTileW && per_phase % 2 == 0 &&
            per_phase * tt.nphases >= 2 * kNumSMs && !getenv("NIC_TC_MT");
     if (pair) swap = false;
   }
@@ -1736,11 +1736,7 @@ static int launch_tc(const nic_conv_desc* d, const TapTable& tt, const void* x, 
     // (... i.e. the input does not fit L2: the single-pass bf16 arm's 100 MB input does, and loses 25 us of 1.85 ms to the order)
     const double in_bytes = static_cast<double>(d->n) * d->h_in * d->w_in * d->c_in * (x3 ? 4 : 2);
     if (interleave && in_bytes > 112e6 && p.nphases > 1 && p.total_tiles >= 16 * kNumSMs) {
-      p.pos_per_wave = 1;                      // (a flag now: both interleaved orders are computed from the slot index)
-      if (pair) {
-        const long slots = static_cast<long>(p.spatial_tiles / 2) * p.nphases, half = kNumSMs / 2;
-        p.total_tiles = static_cast<int>((slots + half - 1) / half) * kNumSMs;      // virtual slots: waves x grid
-      }
+      p.pos_per_wave = 1;                      // (a flag: both interleaved orders are computed from the slot index)
     }
   }
   p.tail_first = 0; p.tail_n = 0;

@@ -263,7 +263,8 @@ def test_x3_two_pass_on_integer_symbols(kind):
         assert float((got - full).abs().max() / full.abs().max()) < 2e-6
 
 
-@pytest.mark.parametrize("kind,precision", [("conv", "bf16x3"), ("conv_big", "bf16x3"), ("convT", "bf16x3"), ("convT_big", "bf16x3"), ("conv", "bf16")])
+@pytest.mark.parametrize("kind,precision", [("conv", "bf16x3"), ("conv_big", "bf16x3"), ("conv_192", "bf16x3"), ("convT", "bf16x3"), ("convT_big", "bf16x3"),
+                                            ("conv", "bf16")])
 def test_cta_pair_form_is_bit_identical_to_the_one_cta_form(kind, precision, monkeypatch):
     """conv_tc_kernel<true> (clusters of two CTAs, cta_group::2 MMAs of M = 256, half a weight slab per CTA, barriers across the pair)
     accumulates exactly what two M = 128 MMAs do: the outputs must match bit for bit, at a shape large enough for the pair form
@@ -276,6 +277,8 @@ def test_cta_pair_form_is_bit_identical_to_the_one_cta_form(kind, precision, mon
         conv, h, w, b = nn.Conv2d(128, 128, 5, 2, 2).to(dev), 250, 382, 5
     elif kind == "conv_big":    # 1536 tiles = 10 full waves + 56: the last wave runs as half tiles (tail_block) in both forms
         conv, h, w, b = nn.Conv2d(128, 128, 5, 2, 2).to(dev), 256, 384, 16
+    elif kind == "conv_192":    # two N tiles (192 output channels): the two CTAs of a cluster share the N tile
+        conv, h, w, b = nn.Conv2d(128, 192, 5, 2, 2).to(dev), 250, 382, 5
     elif kind == "convT":
         conv, h, w, b = nn.ConvTranspose2d(128, 128, 5, 2, 2, output_padding=1).to(dev), 63, 96, 6
     else:       # enough tiles (>= 16 waves) for the phase-interleaved tile order of the pair form
@@ -300,7 +303,8 @@ def test_cta_pair_form_is_bit_identical_to_the_one_cta_form(kind, precision, mon
         finally:
             torch.backends.cudnn.allow_tf32 = tf32
         want = F.leaky_relu(want, 0.01) if not kind.startswith("convT") else want
-        got = (out[..., :128].float() + out[..., 128:].float()).permute(0, 3, 1, 2)
+        co = conv.out_channels
+        got = (out[..., :co].float() + out[..., co:].float()).permute(0, 3, 1, 2)
         assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
 
 
