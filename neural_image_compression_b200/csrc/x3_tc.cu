@@ -906,7 +906,9 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 // 24 warps in six groups of four (the unit of setmaxnreg): 0-3 producers (patch by TMA, im2col with hi/lo split, one pixel row
 // per thread, one A stage), 4 MMA issuer (5-7 idle), 8-23 workers (thread <-> pixel row x 32-channel quarter; four worker warps
 // per scheduler hide each other's TMEM / MUFU / shared-memory latencies - with eight the same chain took 5.7k clk per tile at 22 %
-// issue utilisation).  The producers and the issuer group give registers back (64) so that the workers run with 88 (the pool is what the CTA was launched with: 768 x 80).
+// issue utilisation).  The producers and the issuer group give registers back (64) so that the workers run with 88 - the pool is
+// what the CTA was launched with, 768 x 80: a setmaxnreg.inc that counts on the SM's unallocated registers waits for ever.
+// The bias rides in the conv (constant-1 column 75 of the im2col operand against a bias row patched into the resident W tile).
 //
 // Tensor memory (512 columns): conv accumulators X0, X1 (2 x 128), GDN accumulator (128), SQUARES (128: 64 columns of packed
 // bf16x2 hi, 64 of lo).  The squares are the A operand of the 24 GDN MMAs straight from tensor memory (the [a_tmem] form of
@@ -917,7 +919,8 @@ conv_first_x3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 // so that GDN(t + 1) is covered by the normalisation and the hi store, and the TMA read of a staged half by the work after it.
 // Shared memory: W 48 KB + gamma hi/lo 64 KB + A 48 KB + staging 32 KB + two patches.
 // History (16 images, 512 x 768): squares through shared memory, one tile in the worker stage at a time 383 us (a chain of
-// 8.2k clk per tile) -> squares in TMEM 291 -> per-warp staging / stores 260 -> this layout (see profiles/README.md).
+// 8.2k clk per tile) -> squares in TMEM 291 -> per-warp staging / stores 260 -> 16 worker warps + packed f32x2 245 -> bias in the
+// conv, 8-byte im2col loads 235 (see profiles/README.md).
 // ---------------------------------------------------------------------------------------------
 constexpr int kFfProducers = 4, kFfIssuerWarp = 4, kFfFirstWorker = 8, kFfWorkers = 16;
 constexpr int kFfThreads = (kFfFirstWorker + kFfWorkers) * 32;
