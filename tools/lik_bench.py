@@ -23,7 +23,7 @@ def run(lb, env, clean=False):
     y = 5 * torch.randn((lb, M, H, W), device=dev)
     raw = torch.randn((lb, 3 * K * M, H, W), device=dev)
     d = []
-    for i in range(12):
+    for i in range(24):
         flush.zero_()
         if clean:
             flush.view(torch.int32).max()       # read pass: the L2 now holds CLEAN lines of the flush buffer (nothing to write back)
@@ -32,11 +32,18 @@ def run(lb, env, clean=False):
         torch.cuda.synchronize()
         if i >= 4:
             d.append(a.elapsed_time(b))
-    ms = statistics.median(d)
+    ms = statistics.mean(d)
     return ms, y.numel() * 88 / (ms / 1e3) / 1e9 / PEAK
 
 
-for env in ({"NIC_LIK_FLAT": "0"}, {"NIC_LIK_STAGED": "0"}, {}, {"NIC_LIK_GRID": "296"}, {"NIC_LIK_GRID": "888"}):
-    r16, r256, c16 = run(16, env), run(256, env), run(16, env, clean=True)
-    print(env, f"batch16 {r16[0] * 1e3:.1f} us {r16[1]:.3f} | batch256 {r256[0] * 1e3:.1f} us {r256[1]:.3f} | batch16 after a clean flush "
-          f"{c16[0] * 1e3:.1f} us {c16[1]:.3f}", flush=True)
+envs = ({"NIC_LIK_FLAT": "0"}, {}, {"NIC_LIK_STAGED": "1"}, {"NIC_LIK_GRID": "296"}, {"NIC_LIK_GRID": "888"})
+acc = {i: ([], []) for i in range(len(envs))}
+for rnd in range(4):                                    # interleaved rounds: box drift hits every form alike
+    for i, env in enumerate(envs):
+        acc[i][0].append(run(16, env)[0])
+        acc[i][1].append(run(256, env)[0])
+for i, env in enumerate(envs):
+    m16, m256 = statistics.mean(acc[i][0]), statistics.mean(acc[i][1])
+    f = lambda ms, lb: lb * M * H * W * 88 / (ms / 1e3) / 1e9 / PEAK
+    print(env, f"batch16 {m16 * 1e3:.1f} us {f(m16, 16):.3f} (rounds {[round(v * 1e3, 1) for v in acc[i][0]]}) | "
+          f"batch256 {m256 * 1e3:.1f} us {f(m256, 256):.3f} (rounds {[round(v * 1e3) for v in acc[i][1]]})", flush=True)

@@ -1,0 +1,51 @@
+"""Stress check of the three gm_likelihood kernel forms (NIC_LIK_FLAT=0: (parts, B) grid with libdevice's erff; default: flat
+with the two-range erff; NIC_LIK_STAGED=1: flat with cp.async staging): element outputs must be bit-identical between the forms on random shapes; per-image sums agree to 1e-5."""
+import os
+import random
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from neural_image_compression_b200.EntropyModels import gm_likelihood  # noqa: E402
+from neural_image_compression_b200._lib import Q_NOISE, Q_ROUND  # noqa: E402
+
+dev = torch.device("cuda:0")
+random.seed(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+bad = 0
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+for it in range(N):
+    K = random.choice((1, 2, 3, 3, 3, 5))
+    b = random.choice((1, 2, 3, 7, 16, 33))
+    m = random.choice((8, 16, 128, 192))
+    h, w = random.choice(((8, 12), (3, 5), (32, 48), (4, 4), (17, 20), (64, 96)))
+    if b * m * h * w * (3 * K + 8) * 4 > 3e9:
+        continue
+    qm = random.choice((Q_ROUND, Q_ROUND, Q_NOISE))
+    full = random.random() < 0.7
+    y = 5 * torch.randn((b, m, h, w), device=dev)
+    raw = torch.randn((b, (2 if K == 1 else 3 * K) * m, h, w), device=dev)
+    noise = (torch.rand_like(y) - 0.5) if qm == Q_NOISE else None
+    outs = []
+    for env in ({"NIC_LIK_FLAT": "0"}, {}, {"NIC_LIK_STAGED": "1"}):
+        for k in ("NIC_LIK_FLAT", "NIC_LIK_STAGED"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        # poison the allocator's recycled blocks so that an element a kernel does not write shows up
+        r = gm_likelihood(y, raw, m, K, qm, noise=noise, full=full)
+        outs.append({k: v.clone() for k, v in r.items() if v is not None})
+        for v in r.values():
+            if v is not None:
+                v.fill_(float("nan"))
+    for name, ref in outs[0].items():
+        for j in range(1, len(outs)):
+            got = outs[j][name]
+            if name == "partials":
+                ok = torch.allclose(got.double().sum(1), ref.double().sum(1), rtol=1e-5, atol=1e-3)
+            else:
+                ok = torch.equal(got, ref)
+            if not ok:
+                bad += 1
+                print("MISMATCH", it, K, (b, m, h, w), qm, full, name, "form", j, flush=True)
+torch.cuda.synchronize()
+print("stress done:", N, "cases,", bad, "mismatches")
