@@ -470,13 +470,15 @@ def main():
         yl = 5 * torch.randn((lb, M, H_IMG // 16, W_IMG // 16), device=dev)
         rawl = torch.randn((lb, 3 * K * M, H_IMG // 16, W_IMG // 16), device=dev)
         ld = []
-        for i in range(8):
+        lout = gm_likelihood(yl, rawl, M, K, Q_ROUND, full=True)          # output tensors reused below: no allocator calls between
+        for i in range(23):                                               # the two events, only the C-ABI launch
             flush.zero_()
             ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ks.record(); gm_likelihood(yl, rawl, M, K, Q_ROUND, full=True); ke.record()
+            ks.record(); gm_likelihood(yl, rawl, M, K, Q_ROUND, full=True, out=lout); ke.record()
             torch.cuda.synchronize()
             if i >= 3:
                 ld.append(ks.elapsed_time(ke))
+        del lout
         lms = statistics.mean(ld)
         nbytes = yl.numel() * 88                                  # 52 B/elem + 36 B/elem for weights/mus/sigmas
         lik[f"batch{lb}"] = {"ms": lms, "GB/s": nbytes / (lms / 1e3) / 1e9, "frac_of_hbm_peak": nbytes / (lms / 1e3) / 1e9 / peaks["hbm"]}

@@ -20,10 +20,11 @@ _KERNEL_BOUND = 1e-9     # the bound compiled into the kernels (EntropyModels.py
 
 
 def gm_likelihood(y: Tensor, raw: Tensor, M: int, K: int, qmode: int, noise: Tensor = None, full: bool = True,
-                  want_y_in: bool = True):
+                  want_y_in: bool = True, out: dict = None):
     """nic_gm_likelihood_fwd on NCHW f32 tensors.
 
-    Returns dict(y_in, p, logp, partials[, weights, mus, sigmas | mu, sigma]).
+    Returns dict(y_in, p, logp, partials[, weights, mus, sigmas | mu, sigma]).  `out`: a dict returned by an earlier call with
+    the same arguments - its tensors are written again instead of fresh ones (timing loops: no allocator calls before the launch).
     """
     lib = _lib.load()
     engine.require_cuda(y, "y")
@@ -33,6 +34,18 @@ def gm_likelihood(y: Tensor, raw: Tensor, M: int, K: int, qmode: int, noise: Ten
     if m != M or raw.shape[1] != (2 * M if K == 1 else 3 * K * M):
         raise ValueError(f"entropy parameters {tuple(raw.shape)} do not match y {tuple(y.shape)} with M={M}, K={K}")
     dev = y.device
+    if noise is not None:
+        noise = noise.contiguous().float()
+    if out is not None:
+        y_in, p, logp, parts = out.get("y_in"), out["p"], out["logp"], out["partials"]
+        ws, mus, sgs = (None, out["mu"], out["sigma"]) if K == 1 and full else \
+            (out["weights"], out["mus"], out["sigmas"]) if full else (None, None, None)
+        if p.shape != y.shape or p.device != dev:
+            raise ValueError("gm_likelihood: `out` does not match y")
+        with torch.cuda.device(dev):
+            check(lib.nic_gm_likelihood_fwd(ptr(y), ptr(raw), ptr(noise), b, m, h * w, K, qmode, ptr(y_in), ptr(p), ptr(logp),
+                                            ptr(ws), ptr(mus), ptr(sgs), ptr(parts), current_stream()), "nic_gm_likelihood_fwd")
+        return out
     y_in = torch.empty_like(y) if want_y_in else None
     p, logp = torch.empty_like(y), torch.empty_like(y)
     parts = engine.partials(b, dev)
@@ -42,8 +55,6 @@ def gm_likelihood(y: Tensor, raw: Tensor, M: int, K: int, qmode: int, noise: Ten
         mus = torch.empty(shape, dtype=torch.float32, device=dev)
         sgs = torch.empty_like(mus)
         ws = torch.empty_like(mus) if K > 1 else None
-    if noise is not None:
-        noise = noise.contiguous().float()
     with torch.cuda.device(dev):
         check(lib.nic_gm_likelihood_fwd(ptr(y), ptr(raw), ptr(noise), b, m, h * w, K, qmode, ptr(y_in), ptr(p), ptr(logp),
                                         ptr(ws), ptr(mus), ptr(sgs), ptr(parts), current_stream()), "nic_gm_likelihood_fwd")

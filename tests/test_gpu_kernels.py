@@ -51,6 +51,44 @@ def test_gm_likelihood_matches_oracle(dev, K, shape):
     np.testing.assert_allclose(s.numpy(), ref_s.numpy(), rtol=1e-5)
 
 
+@pytest.mark.parametrize("K,shape,full", [(3, (5, 128, 8, 12), True), (3, (16, 128, 32, 48), True), (1, (3, 192, 17, 20), True),
+                                          (2, (7, 16, 3, 5), False), (5, (2, 8, 4, 4), True), (3, (33, 8, 4, 4), False)])
+def test_gm_likelihood_kernel_forms_agree(dev, K, shape, full, monkeypatch):
+    """The flat balanced form (default: one list of chunks cut into equal ranges, a block folds its sum at every image
+    boundary it crosses; erff with both ranges evaluated) against the (parts, B) grid with libdevice's erff, and the cp.async
+    staged form: element outputs bit-identical (ragged sizes, blocks spanning several images, more images than slots per block),
+    per-image sums equal to rounding, and p against the oracle."""
+    from neural_image_compression_b200.EntropyModels import gm_likelihood
+    from neural_image_compression_b200._lib import Q_NOISE, Q_ROUND
+    B, M, Hh, Ww = shape
+    g = torch.Generator().manual_seed(11)
+    y = 5 * torch.randn(shape, generator=g)
+    raw = torch.randn((B, (2 if K == 1 else 3 * K) * M, Hh, Ww), generator=g)
+    noise = torch.rand(shape, generator=g) - 0.5
+    for qmode, nz in ((Q_ROUND, None), (Q_NOISE, noise)):
+        outs = []
+        for env in ({"NIC_LIK_FLAT": "0"}, {}, {"NIC_LIK_STAGED": "1"}):
+            monkeypatch.delenv("NIC_LIK_FLAT", raising=False)
+            monkeypatch.delenv("NIC_LIK_STAGED", raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            r = gm_likelihood(y.to(dev), raw.to(dev), M, K, qmode, noise=None if nz is None else nz.to(dev), full=full)
+            outs.append({k: v.cpu() for k, v in r.items() if v is not None})
+        for form in outs[1:]:
+            for name, ref in outs[0].items():
+                if name == "partials":
+                    np.testing.assert_allclose(form[name].double().sum(1).numpy(), ref.double().sum(1).numpy(), rtol=1e-5, atol=1e-3)
+                else:
+                    assert torch.equal(form[name], ref), name
+        y_in = torch.round(y) if qmode == Q_ROUND else y + noise
+        assert torch.equal(outs[1]["y_in"], y_in)
+        p_ref = O.conditional_likelihood(y_in, O.split_parameters(raw, M, K), K)
+        bad, worst = H.likelihood_close(outs[1]["p"].numpy(), p_ref.numpy())
+        assert bad == 0, f"{bad} likelihoods outside tolerance (max abs err {worst:.3e})"
+        s = outs[1]["partials"].double().sum(dim=1)
+        np.testing.assert_allclose(s.numpy(), torch.log(outs[1]["p"]).double().sum(dim=(1, 2, 3)).numpy(), rtol=1e-5)
+
+
 def test_gm_likelihood_properties(dev):
     """p in [1e-9, 1]; mixture weights sum to 1; K = 1 mass is monotone in |y - mu|."""
     from neural_image_compression_b200.EntropyModels import gm_likelihood
