@@ -55,8 +55,7 @@ def test_gm_likelihood_matches_oracle(dev, K, shape):
                                           (2, (7, 16, 3, 5), False), (5, (2, 8, 4, 4), True), (3, (33, 8, 4, 4), False)])
 def test_gm_likelihood_kernel_forms_agree(dev, K, shape, full, monkeypatch):
     """The flat balanced form (default: one list of chunks cut into equal ranges, a block folds its sum at every image
-    boundary it crosses; erff with both ranges evaluated) against the (parts, B) grid with libdevice's erff, and the cp.async
-    staged form: element outputs bit-identical (ragged sizes, blocks spanning several images, more images than slots per block),
+    boundary it crosses; erff with both ranges evaluated) against the (parts, B) grid with libdevice's erff: element outputs bit-identical (ragged sizes, blocks spanning several images, more images than slots per block),
     per-image sums equal to rounding, and p against the oracle."""
     from neural_image_compression_b200.EntropyModels import gm_likelihood
     from neural_image_compression_b200._lib import Q_NOISE, Q_ROUND
@@ -67,7 +66,7 @@ def test_gm_likelihood_kernel_forms_agree(dev, K, shape, full, monkeypatch):
     noise = torch.rand(shape, generator=g) - 0.5
     for qmode, nz in ((Q_ROUND, None), (Q_NOISE, noise)):
         outs = []
-        for env in ({"NIC_LIK_FLAT": "0"}, {}, {"NIC_LIK_STAGED": "1"}):
+        for env in ({"NIC_LIK_FLAT": "0"}, {}):
             monkeypatch.delenv("NIC_LIK_FLAT", raising=False)
             monkeypatch.delenv("NIC_LIK_STAGED", raising=False)
             for k, v in env.items():

@@ -37,7 +37,7 @@ def run(lb, env, clean=False):
     return ms, y.numel() * 88 / (ms / 1e3) / 1e9 / PEAK
 
 
-envs = ({"NIC_LIK_FLAT": "0"}, {}, {"NIC_LIK_STAGED": "1"}, {"NIC_LIK_GRID": "296"}, {"NIC_LIK_GRID": "888"})
+envs = ({"NIC_LIK_FLAT": "0"}, {}, {"NIC_LIK_GRID": "296"}, {"NIC_LIK_GRID": "888"})
 acc = {i: ([], []) for i in range(len(envs))}
 for rnd in range(4):                                    # interleaved rounds: box drift hits every form alike
     for i, env in enumerate(envs):
