@@ -119,7 +119,9 @@ class _Chain(nn.Module):
     NHWC tensors: a conv followed by nn.LeakyReLU runs with the LeakyReLU epilogue fused."""
     precision = None
 
-    def run_nhwc(self, x, n, h, w, arm, in_layout=None):
+    def run_nhwc(self, x, n, h, w, arm, in_layout=None, tape=None, final_kw=None):
+        """tape: training.Tape that records every op for the backward (training forward); final_kw: `out=` window arguments of
+        the LAST conv (h_s writes psi straight into the concat buffer of the entropy-parameter stack)."""
         from . import Layers as L
         from ._lib import LAYOUT_NHWC
         layout = LAYOUT_NHWC if in_layout is None else in_layout
@@ -128,13 +130,14 @@ class _Chain(nn.Module):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             fuse = isinstance(nxt, nn.LeakyReLU)
+            kw = final_kw if (final_kw and i == len(mods) - 1) else {}
             if isinstance(m, L.TransposedDeconv3x3):
-                x, h, w = m.run_nhwc(x, n, h, w, arm, in_layout=layout, epilogue=EPI_LRELU if fuse else EPI_BIAS)
+                x, h, w = m.run_nhwc(x, n, h, w, arm, in_layout=layout, epilogue=EPI_LRELU if fuse else EPI_BIAS, tape=tape)
             elif isinstance(m, L._Block):
-                x, h, w = m.run_nhwc(x, n, h, w, arm, in_layout=layout)
+                x, h, w = m.run_nhwc(x, n, h, w, arm, in_layout=layout, tape=tape)
                 fuse = False
             elif isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
-                x, h, w = L._conv(arm, m, EPI_LRELU if fuse else EPI_BIAS, x, n, h, w, in_layout=layout)
+                x, h, w = L._conv(arm, m, EPI_LRELU if fuse else EPI_BIAS, x, n, h, w, in_layout=layout, tape=tape, **kw)
             else:
                 raise TypeError(f"unexpected module in a transform: {type(m).__name__}")
             layout = LAYOUT_NHWC

@@ -29,9 +29,13 @@ def _arm(precision: Optional[str], channels: int) -> str:
     return p if p in ("fp32", "bf16x3") else "bf16x3"
 
 
-def _conv(arm, conv, epi, x, n, h, w, in_layout=LAYOUT_NHWC, out_layout=LAYOUT_NHWC):
-    """One conv (+ bias / LeakyReLU) -> (f32 tensor, h_out, w_out)."""
+def _conv(arm, conv, epi, x, n, h, w, in_layout=LAYOUT_NHWC, out_layout=LAYOUT_NHWC, tape=None, **out_kw):
+    """One conv (+ bias / LeakyReLU) -> (f32 tensor, h_out, w_out).  tape: the training forward's record (training.Tape); the RGB
+    layer then stays NCHW (it is the transform's output and x_hat is NCHW)."""
     T = _T()
+    if tape is not None:
+        lay = LAYOUT_NCHW if (out_layout == LAYOUT_NHWC and conv.out_channels % 4) else out_layout
+        return (tape.conv(conv, epi, x, h, w, in_layout=in_layout, out_layout=lay, **out_kw),) + engine.conv_out_hw(conv, h, w)
     if out_layout == LAYOUT_NHWC and conv.out_channels % 4:
         # NHWC rows of e.g. 3 floats are not 16-byte aligned (the engine's NHWC stores are vectorised): such layers - the RGB
         # output of g_s - write NCHW, and the chain's NHWC convention is restored by a view permutation
@@ -42,17 +46,23 @@ def _conv(arm, conv, epi, x, n, h, w, in_layout=LAYOUT_NHWC, out_layout=LAYOUT_N
     return (y,) + engine.conv_out_hw(conv, h, w)
 
 
-def _gdn(arm, gdn, u, n, h, w):
+def _gdn(arm, gdn, u, n, h, w, tape=None):
     T = _T()
+    if tape is not None:
+        return tape.gdn(gdn, u, h, w)
     y = T.gdn_forward(arm, gdn, u, n, h, w)[0]
     T.forget_pairs()
     return y
 
 
+def _add(out, idn, tape=None):
+    return tape.add(out, idn) if tape is not None else _T().add_(out, idn)
+
+
 class _Block(nn.Module):
     precision = None      # None -> bf16x3 where the channel counts allow, else fp32; set by the owning model
 
-    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC):
+    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC, tape=None):
         raise NotImplementedError
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -74,8 +84,8 @@ class SubpelConv3x3(_Block):
         self.conv = nn.Conv2d(in_ch, out_ch * (upsample ** 2), kernel_size=3, stride=1, padding=1)
         self.shuffle = nn.PixelShuffle(upsample)
 
-    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC):
-        y, h, w = _conv(arm, self.conv, EPI_BIAS, x, n, h, w, in_layout=in_layout)
+    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC, tape=None):
+        y, h, w = _conv(arm, self.conv, EPI_BIAS, x, n, h, w, in_layout=in_layout, tape=tape)
         r = self.shuffle.upscale_factor
         c = y.shape[-1] // (r * r)
         y = y.reshape(n, h, w, c, r, r).permute(0, 1, 4, 2, 5, 3).reshape(n, h * r, w * r, c).contiguous()
@@ -89,8 +99,8 @@ class TransposedDeconv3x3(_Block):
         super().__init__()
         self.deconv = nn.ConvTranspose2d(in_ch, out_ch, kernel_size=3, stride=upsample, padding=1, output_padding=upsample - 1)
 
-    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC, epilogue=EPI_BIAS):
-        return _conv(arm, self.deconv, epilogue, x, n, h, w, in_layout=in_layout)
+    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC, epilogue=EPI_BIAS, tape=None):
+        return _conv(arm, self.deconv, epilogue, x, n, h, w, in_layout=in_layout, tape=tape)
 
 
 class ResidualBlockWithStride(_Block):
@@ -104,16 +114,16 @@ class ResidualBlockWithStride(_Block):
         self.gdn = GDN(out_ch, beta_min=1e-6, gamma_init=.1)
         self.skip = nn.Conv2d(in_ch, out_ch, kernel_size=1, stride=stride) if (stride != 1 or in_ch != out_ch) else None
 
-    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC):
+    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC, tape=None):
         T = _T()
-        u, ho, wo = _conv(arm, self.conv1, EPI_LRELU, x, n, h, w, in_layout=in_layout)
-        u, _, _ = _conv(arm, self.conv2, EPI_BIAS, u, n, ho, wo)
-        out = _gdn(arm, self.gdn, u, n, ho, wo)
+        u, ho, wo = _conv(arm, self.conv1, EPI_LRELU, x, n, h, w, in_layout=in_layout, tape=tape)
+        u, _, _ = _conv(arm, self.conv2, EPI_BIAS, u, n, ho, wo, tape=tape)
+        out = _gdn(arm, self.gdn, u, n, ho, wo, tape=tape)
         if self.skip is not None:
-            idn, _, _ = _conv(arm, self.skip, EPI_BIAS, x, n, h, w, in_layout=in_layout)
+            idn, _, _ = _conv(arm, self.skip, EPI_BIAS, x, n, h, w, in_layout=in_layout, tape=tape)
         else:
             idn = x if in_layout == LAYOUT_NHWC else x.permute(0, 2, 3, 1).contiguous()
-        return T.add_(out, idn), ho, wo
+        return _add(out, idn, tape), ho, wo
 
 
 class ResidualBlockUpsample(_Block):
@@ -127,13 +137,13 @@ class ResidualBlockUpsample(_Block):
         self.igdn = GDN(out_ch, inverse=True, beta_min=1e-6, gamma_init=.1)
         self.upsample = TransposedDeconv3x3(in_ch, out_ch, upsample)
 
-    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC):
+    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC, tape=None):
         T = _T()
-        u, ho, wo = self.subpel_conv.run_nhwc(x, n, h, w, arm, in_layout=in_layout, epilogue=EPI_LRELU)
-        u, _, _ = _conv(arm, self.conv, EPI_BIAS, u, n, ho, wo)
-        out = _gdn(arm, self.igdn, u, n, ho, wo)
-        idn, _, _ = self.upsample.run_nhwc(x, n, h, w, arm, in_layout=in_layout)
-        return T.add_(out, idn), ho, wo
+        u, ho, wo = self.subpel_conv.run_nhwc(x, n, h, w, arm, in_layout=in_layout, epilogue=EPI_LRELU, tape=tape)
+        u, _, _ = _conv(arm, self.conv, EPI_BIAS, u, n, ho, wo, tape=tape)
+        out = _gdn(arm, self.igdn, u, n, ho, wo, tape=tape)
+        idn, _, _ = self.upsample.run_nhwc(x, n, h, w, arm, in_layout=in_layout, tape=tape)
+        return _add(out, idn, tape), ho, wo
 
 
 class ResidualBlock(_Block):
@@ -146,12 +156,12 @@ class ResidualBlock(_Block):
         self.conv2 = nn.Conv2d(out_ch, out_ch, kernel_size=3, stride=1, padding=1)
         self.skip = nn.Conv2d(in_ch, out_ch, kernel_size=1, stride=1) if in_ch != out_ch else None
 
-    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC):
+    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC, tape=None):
         T = _T()
-        u, _, _ = _conv(arm, self.conv1, EPI_LRELU, x, n, h, w, in_layout=in_layout)
-        out, _, _ = _conv(arm, self.conv2, EPI_LRELU, u, n, h, w)
+        u, _, _ = _conv(arm, self.conv1, EPI_LRELU, x, n, h, w, in_layout=in_layout, tape=tape)
+        out, _, _ = _conv(arm, self.conv2, EPI_LRELU, u, n, h, w, tape=tape)
         if self.skip is not None:
-            idn, _, _ = _conv(arm, self.skip, EPI_BIAS, x, n, h, w, in_layout=in_layout)
+            idn, _, _ = _conv(arm, self.skip, EPI_BIAS, x, n, h, w, in_layout=in_layout, tape=tape)
         else:
             idn = x if in_layout == LAYOUT_NHWC else x.permute(0, 2, 3, 1).contiguous()
-        return T.add_(out, idn), h, w
+        return _add(out, idn, tape), h, w

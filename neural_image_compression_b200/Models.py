@@ -272,9 +272,10 @@ class HierarchicalMixtureResidual(nn.Module):
     JointAutoregressiveHierarchical with the 3x3 residual transforms (Encoder3x3 / Decoder3x3 / HyperEncoder3x3 / HyperDecoder3x3,
     Components.py:20-122, blocks of Layers.py).  Same constructor, attributes and ``state_dict`` keys.
 
-    Forward-only (evaluation, or training=True under torch.no_grad() with the noise relaxation): the transforms run layer by
-    layer on the conv engine (f32 NHWC tensors between layers; residual sums by nic_add_inplace), the entropy side on the same
-    kernels as the 5x5 model.  precision: "bf16x3" (default when latent_channels is a multiple of 64: tensor cores with hi/lo-
+    The transforms run layer by layer on the conv engine (f32 NHWC tensors between layers; residual sums by nic_add_inplace),
+    the entropy side on the same kernels as the 5x5 model.  With autograd enabled and training=True the call is the training
+    step's forward (training.train_forward: one autograd node; backward = training.Tape over the same C-ABI backward kernels
+    as the 5x5 model).  precision: "bf16x3" (default when latent_channels is a multiple of 64: tensor cores with hi/lo-
     split operands; the 3-channel first block on the fp32 CUDA-core kernels) or "fp32".  The training step (backward) of this
     family is not built: calling it with autograd enabled raises."""
 
@@ -311,10 +312,10 @@ class HierarchicalMixtureResidual(nn.Module):
         B, _, H, W = x.shape
         if H % 64 or W % 64:
             raise ValueError(f"H and W must be multiples of 64; got {H}x{W}")
-        if training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("HierarchicalMixtureResidual: the training step (backward kernels) of the 3x3 residual family is "
-                                      "not built; call under torch.no_grad() for the forward pass")
         from . import training as T
+        if training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # the training step: ONE autograd node over the hand-written backward (training.Tape walks the residual graphs)
+            return T.train_forward(self, x, noise=noise, lean=lean)
         arm, M, K = self.precision, self.M, self.K
         hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
         x = x.contiguous().float()

@@ -41,7 +41,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, engine
-from ._lib import (ConvDesc, DT_F32, EPI_BIAS, LAYOUT_NCHW, LAYOUT_NHWC, PREC_FP32, Q_NOISE, Q_PASSTHRU, Q_ROUND, check, current_stream, ptr)
+from ._lib import (ConvDesc, DT_F32, EPI_BIAS, EPI_LRELU, LAYOUT_NCHW, LAYOUT_NHWC, PREC_FP32, Q_NOISE, Q_PASSTHRU, Q_ROUND, check, current_stream, ptr)
 
 PREC = "fp32"
 WGRAD_TC = os.environ.get("NIC_WGRAD_TC", "1") != "0"      # tensor-core weight gradients in the bf16x3 arm (0: fp32 kernel everywhere)
@@ -261,6 +261,26 @@ def conv_dgrad(conv: nn.Module, g: torch.Tensor, n: int, h_in: int, w_in: int, g
     """Gradient w.r.t. the layer input (NHWC f32): the adjoint conv through nic_conv_fwd.
     (h_in, w_in) = forward input size.  `weight` / `c_in` select a slice of the layer's input channels
     (weight = the matching slice of conv.weight, contiguous)."""
+    if (not isinstance(conv, nn.ConvTranspose2d)) and conv.kernel_size == (1, 1) and conv.stride[0] > 1 and weight is None \
+            and g_layout == LAYOUT_NHWC:
+        # 1x1 strided conv (the skip of ResidualBlockWithStride, Layers.py:47): the input gradient is W^T g at the sampled positions
+        # and zero elsewhere - the contraction as a 1x1 stride-1 conv of the engine, the scatter as a strided view copy
+        st = conv.stride[0]
+        cache = conv.__dict__.setdefault("_nic_adjoint", {})
+        if "pointwise" not in cache:
+            with torch.device(conv.weight.device):
+                adj1 = nn.Conv2d(conv.out_channels, conv.in_channels, 1)
+            adj1.requires_grad_(False)
+            adj1.bias.data.zero_()
+            cache["pointwise"] = adj1
+        adj1 = cache["pointwise"]
+        adj1.weight = nn.Parameter(conv.weight.detach().transpose(0, 1).contiguous(), requires_grad=False)
+        adj1.__dict__.pop("_nic_train_ops", None)      # a fresh weight tensor every call
+        h_out, w_out = engine.conv_out_hw(conv, h_in, w_in)
+        t = conv_forward(arm, adj1, EPI_BIAS, g, n, h_out, w_out)
+        dx = torch.zeros((n, h_in, w_in, conv.in_channels), dtype=torch.float32, device=g.device)
+        dx[:, ::st, ::st, :] = t
+        return dx
     if arm == "bf16x3" and g_layout == LAYOUT_NCHW and weight is None and isinstance(conv, nn.ConvTranspose2d) and g.shape[-1] % 4 == 0:
         adj, op = _adjoint(conv, None, conv.in_channels, h_in, w_in)          # ConvTranspose2d(128, 3) backward = the 3 -> 128 conv
         if _is_first_layer_shape(adj):
@@ -370,6 +390,84 @@ def add_(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+class Tape:
+    """Record of a transform whose graph is not a plain chain (the 3x3 residual family, Layers.py / Components.py:20-122): every
+    conv (+ bias / LeakyReLU), GDN / IGDN and residual sum of the forward is appended with its input and output tensors;
+    `backward` walks the record in reverse, keeps one gradient per tensor (summed where a tensor feeds two consumers: the block
+    input of a residual block) and returns the gradient of the transform's input.  Kernels: the same C-ABI calls as the 5x5
+    chains (conv_wgrad, conv_dgrad, gdn_bwd, nic_lrelu_bwd, nic_add_inplace)."""
+
+    def __init__(self, arm: str, n: int):
+        self.arm, self.n, self.recs = arm, n, []
+
+    def conv(self, conv, epilogue, x, h, w, in_layout=LAYOUT_NHWC, out_layout=LAYOUT_NHWC, **out_kw):
+        y = conv_forward(self.arm, conv, epilogue, x, self.n, h, w, in_layout=in_layout, out_layout=out_layout, **out_kw)
+        self.recs.append(("conv", conv, epilogue, x, h, w, in_layout, out_layout, y))
+        return y
+
+    def gdn(self, gdn, u, h, w):
+        y, nrm = gdn_forward(self.arm, gdn, u, self.n, h, w)
+        self.recs.append(("gdn", gdn, u, nrm, h, w, y))
+        return y
+
+    def add(self, a, b):
+        y = add_(a.clone(), b)                      # out of place: `a` may be a LeakyReLU output whose signs the backward needs
+        self.recs.append(("add", a, b, y))
+        return y
+
+    @property
+    def output(self):
+        return self.recs[-1][-1]
+
+    def backward(self, g_out, g_layout, put, wgrad, root=None, side=None, keep=None):
+        """g_out: gradient of `output` (in g_layout).  root: the transform's input tensor; its gradient is returned (None when
+        root is None: the image needs none).  put(param, grad) collects parameter gradients, wgrad = conv_wgrad or its
+        side-stream form."""
+        n, arm = self.n, self.arm
+        grads = {id(self.output): (g_out, g_layout)}
+        internal = {id(r[-1]) for r in self.recs}
+
+        def give(t, g):
+            """Add g to the gradient of tensor t (a tensor made inside the transform, or its input when that is wanted)."""
+            if id(t) not in internal and (root is None or t is not root):
+                return
+            if id(t) in grads:
+                grads[id(t)] = (add_(grads[id(t)][0], g), LAYOUT_NHWC)
+            else:
+                grads[id(t)] = (g, LAYOUT_NHWC)
+
+        for rec in reversed(self.recs):
+            got = grads.pop(id(rec[-1]), None)
+            if got is None:
+                continue
+            g, gl = got
+            if rec[0] == "conv":
+                _, conv, epi, x, h, w, in_layout, out_layout, y = rec
+                if epi == EPI_LRELU:
+                    g = lrelu_bwd_(g, y)
+                dw, db = wgrad(conv, x, g, n, h, w, in_layout, gl, arm=arm)
+                put(conv.weight, dw); put(conv.bias, db)
+                if keep is not None:
+                    keep.append(g)
+                if id(x) in internal or (root is not None and x is root):
+                    give(x, conv_dgrad(conv, g, n, h, w, gl, arm=arm))
+            elif rec[0] == "gdn":
+                _, gdn, u, nrm, h, w, y = rec
+                du, dbeta, dgamma = gdn_bwd(gdn, u, g, n, h, w, norm=nrm, side=side, keep=keep)
+                put(gdn.beta, dbeta); put(gdn.gamma, dgamma)
+                give(u, du)
+            else:
+                _, a, b, y = rec
+                give(a, g)
+                give(b, g.clone())                                  # the two consumers may modify their gradient in place
+        return grads.pop(id(root), (None, None))[0] if root is not None else None
+
+
+def _is_chain(transform) -> bool:
+    """5x5 transforms expose `.ops` (a plain chain of conv [+ GDN]); the 3x3 residual family records a Tape."""
+    return hasattr(transform, "ops")
+
+
 _FACT_SLICES = (("matrices", 0, 0, 3), ("biases", 0, 3, 6), ("factors", 0, 6, 9), ("matrices", 1, 9, 18), ("biases", 1, 18, 21),
                 ("factors", 1, 21, 24), ("matrices", 2, 24, 33), ("biases", 2, 33, 36), ("factors", 2, 36, 39),
                 ("matrices", 3, 39, 42), ("biases", 3, 42, 43))
@@ -392,8 +490,11 @@ def _forward_impl(model, x, noise_z, noise_y, lean, qmode: int = Q_NOISE, arm: O
     with torch.cuda.device(dev):
         # g_a: conv (+ bias) -> u, kept for the GDN backward; GDN -> the next layer's input, kept for its weight gradient
         a, h, w, layout = x, H, W, LAYOUT_NCHW
-        enc = model.encoder.ops
+        enc = model.encoder.ops if _is_chain(model.encoder) else ()
         S["enc_in"], S["enc_u"] = [], []
+        if not _is_chain(model.encoder):
+            S["enc_tape"] = Tape(arm, B)
+            a, h, w = model.encoder.run_nhwc(x, B, H, W, arm, in_layout=LAYOUT_NCHW, tape=S["enc_tape"])
         for op in enc:
             S["enc_in"].append((a, h, w, layout))
             a = conv_forward(arm, op.conv, EPI_BIAS, a, B, h, w, in_layout=layout)
@@ -409,6 +510,9 @@ def _forward_impl(model, x, noise_z, noise_y, lean, qmode: int = Q_NOISE, arm: O
         y, y_in, y_in_nhwc, _ = engine.latent_handoff(y_nhwc, qmode, noise_y, torch.float32)
         def synthesis():
             a, h, w = y_in_nhwc, hy, wy
+            if not _is_chain(model.decoder):
+                S["dec_tape"] = Tape(arm, B)
+                return model.decoder.run_nhwc(a, B, h, w, arm, tape=S["dec_tape"])[0]        # the RGB layer writes NCHW
             dec = model.decoder.ops
             S["dec_in"], S["dec_u"] = [], []
             for i, op in enumerate(dec):
@@ -436,7 +540,10 @@ def _forward_impl(model, x, noise_z, noise_y, lean, qmode: int = Q_NOISE, arm: O
         # h_a (reads the unquantised y)
         a, h, w = y_nhwc, hy, wy
         S["ha_in"] = []
-        for op in model.hyper_encoder.ops:
+        if not _is_chain(model.hyper_encoder):
+            S["ha_tape"] = Tape(arm, B)
+            a, h, w = model.hyper_encoder.run_nhwc(a, B, h, w, arm, tape=S["ha_tape"])
+        for op in (model.hyper_encoder.ops if _is_chain(model.hyper_encoder) else ()):
             S["ha_in"].append((a, h, w))
             a = conv_forward(arm, op.conv, op.epilogue, a, B, h, w)
             h, w = engine.conv_out_hw(op.conv, h, w)
@@ -444,8 +551,11 @@ def _forward_impl(model, x, noise_z, noise_y, lean, qmode: int = Q_NOISE, arm: O
         # h_s -> psi, context -> phi, both windows of `combined`
         combined = _f32((B, hy, wy, 4 * M), dev)
         a, h, w = z_in_nhwc, hz, wz
-        hs = model.hyper_decoder.ops
+        hs = model.hyper_decoder.ops if _is_chain(model.hyper_decoder) else ()
         S["hs_in"] = []
+        if not _is_chain(model.hyper_decoder):
+            S["hs_tape"] = Tape(arm, B)
+            model.hyper_decoder.run_nhwc(a, B, h, w, arm, tape=S["hs_tape"], final_kw=dict(out=combined, out_c_total=4 * M, out_c_offset=2 * M))
         for i, op in enumerate(hs):
             S["hs_in"].append((a, h, w))
             if i == len(hs) - 1:
@@ -468,7 +578,7 @@ def _forward_impl(model, x, noise_z, noise_y, lean, qmode: int = Q_NOISE, arm: O
         else:
             x_hat = synthesis()
     S["arm"] = arm
-    S.update(combined=combined, e1=e1, e2=e2, raw=raw, y_in=y_in, y_in_nhwc=y_in_nhwc, z_in=z_in, z_in_nhwc=z_in_nhwc,
+    S.update(combined=combined, e1=e1, e2=e2, raw=raw, y_in=y_in, y_in_nhwc=y_in_nhwc, z_in=z_in, z_in_nhwc=z_in_nhwc, y_nhwc=y_nhwc,
              fparams=model.factorized_entropy_model.packed(), shape=(B, H, W))
     logp_y = ly["logp"]
     extra = [] if lean else ([ly["mu"], ly["sigma"]] if K == 1 else [ly["weights"], ly["mus"], ly["sigmas"]])
@@ -519,7 +629,9 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z, partial_hook=None) -> D
                 branch.wait_stream(main)
             with (torch.cuda.stream(branch) if branch is not None else contextlib.nullcontext()):
                 g, g_layout = g_xhat.contiguous().float(), LAYOUT_NCHW
-                dec = model.decoder.ops
+                dec = model.decoder.ops if _is_chain(model.decoder) else ()
+                if not _is_chain(model.decoder):
+                    g = S["dec_tape"].backward(g, g_layout, put, conv_wgrad_async, root=S["y_in_nhwc"], side=side, keep=keep)
                 for i in range(len(dec) - 1, -1, -1):
                     op = dec[i]
                     a, h, w = S["dec_in"][i]
@@ -557,7 +669,9 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z, partial_hook=None) -> D
             put(masked.weight, dw); put(masked.bias, db)
             d_yin = add_(d_yin, conv_dgrad(masked, d_phi, B, hy, wy, arm=arm))
             g = d_psi
-            hs = model.hyper_decoder.ops
+            hs = model.hyper_decoder.ops if _is_chain(model.hyper_decoder) else ()
+            if not _is_chain(model.hyper_decoder):
+                g = S["hs_tape"].backward(g, LAYOUT_NHWC, put, conv_wgrad_async, root=S["z_in_nhwc"], side=side, keep=keep)
             for i in range(len(hs) - 1, -1, -1):
                 op = hs[i]
                 a, h, w = S["hs_in"][i]
@@ -583,7 +697,9 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z, partial_hook=None) -> D
         dy = d_yin
         if d_zin is not None:
             g = d_zin
-            ha = model.hyper_encoder.ops
+            ha = model.hyper_encoder.ops if _is_chain(model.hyper_encoder) else ()
+            if not _is_chain(model.hyper_encoder):
+                g = S["ha_tape"].backward(g, LAYOUT_NHWC, put, conv_wgrad_async, root=S["y_nhwc"], side=side, keep=keep)
             for i in range(len(ha) - 1, -1, -1):
                 op = ha[i]
                 a, h, w = S["ha_in"][i]
@@ -603,7 +719,9 @@ def _backward_impl(model, S, g_xhat, g_logp_y, g_logp_z, partial_hook=None) -> D
         # ---- g_a (y_in = y + noise) ---------------------------------------------------------------------------------
         if dy is not None:
             g = dy
-            enc = model.encoder.ops
+            enc = model.encoder.ops if _is_chain(model.encoder) else ()
+            if not _is_chain(model.encoder):
+                S["enc_tape"].backward(g, LAYOUT_NHWC, put, conv_wgrad_async, root=None, side=side, keep=keep)
             for i in range(len(enc) - 1, -1, -1):
                 op = enc[i]
                 a, h, w, layout = S["enc_in"][i]

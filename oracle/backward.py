@@ -65,6 +65,26 @@ def loss_and_grads_scalable(sd, x, M: int, M1: int, K: int, noise_z: torch.Tenso
     return rd, grads
 
 
+def loss_and_grads_residual(sd, x, M: int, K: int, noise_z: torch.Tensor, noise_y: torch.Tensor, lambda_rd: float, dtype=torch.float32):
+    """The same for HierarchicalMixtureResidual (Models.py:109-205, the 3x3 residual transforms of Layers.py / Components.py:20-122):
+    autograd over forward_residual + rd_loss.  Pinned by tests/golden/c6_train_*.npz (``oracle/make_golden.py residual-train``:
+    the reference's own unmodified class, its rd_loss, loss.backward() and one Adam step).  Returns (rd dict, grads, forward dict)."""
+    keys = set(parameter_keys(sd))
+    leaves = {k: (v.detach().to("cpu", dtype).clone().requires_grad_(True) if k in keys else v.detach().clone()) for k, v in sd.items()}
+    prev = O.DIFFERENTIABLE
+    O.DIFFERENTIABLE = True
+    try:
+        out = O.forward_residual(leaves, x, M, K, training=True, noise_z=noise_z, noise_y=noise_y, dtype=dtype)
+        rd = O.rd_loss(out, x, lambda_rd)
+        rd["loss"].backward()
+    finally:
+        O.DIFFERENTIABLE = prev
+    grads = {k: leaves[k].grad.detach() for k in parameter_keys(sd) if leaves[k].grad is not None}
+    rd = dict(rd)
+    rd["loss"] = float(rd["loss"].detach())
+    return rd, grads, {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
+
+
 def kink_margin(sd, x, M: int, K: int, noise_z: torch.Tensor, noise_y: torch.Tensor) -> float:
     """Smallest |pre-activation| over the six LeakyReLU layers of the step (h_a 0/2, h_s 0/2, entropy-parameter 0/2), in float64.
     LeakyReLU's derivative jumps from 0.01 to 1 at 0, so an element whose pre-activation is below the fp32 accumulation noise

@@ -8,7 +8,7 @@ reference classes are imported unmodified with two stand-ins placed in
   * ``compressai.layers.gdn.GDN``: oracle/gdn.py (third-party arithmetic that
     is absent from /root/reference and from this image - parity unpinned there).
 
-Usage:  python -m oracle.make_golden [scalable | train | residual]  (from the repo root)
+Usage:  python -m oracle.make_golden [scalable | train | residual | residual-train]  (from the repo root)
 """
 from __future__ import annotations
 
@@ -316,9 +316,72 @@ def main_train():
               f"worst fp32-vs-fp64 relative gradient error {worst:.2e} -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+RESIDUAL_TRAIN_CASES = {
+    # name: (M, K, input shape, noise seed) - the training step of HierarchicalMixtureResidual at parity-test size
+    "c6_train_res3x3_k3_128_calib": (128, 3, (2, 3, 64, 128), 21),
+}
+
+
+def main_residual_train():
+    """The reference's training step (Trainer.py:81-86) on its own HierarchicalMixtureResidual: model(imgs) with its torch.rand_like
+    noise, rd_loss, loss.backward(), torch.optim.Adam(lr=1e-4).step().  Weights: the calib recipe of main_residual (gains from the
+    evaluation forward of the same input).  Gradients are kept as per-tensor L2 norms + sampled entries, as in main_train."""
+    Models, RDL = import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    from oracle import backward as OB
+    for name, (M, K, shape, nseed) in RESIDUAL_TRAIN_CASES.items():
+        torch.manual_seed(0)
+        model = Models.HierarchicalMixtureResidual(M, K=K)
+        sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+        torch.manual_seed(1)
+        x = torch.rand(*shape)
+        with torch.no_grad():
+            gy = float(np.float32(2.0 / float(model(x, training=False)["y"].std())))
+            model.load_state_dict(residual_init({k: v.clone() for k, v in sd0.items()}, gy, 1.0, 0.0))
+            gz = float(np.float32(3.0 / float(model(x, training=False)["z"].std())))
+        sd = residual_init({k: v.clone() for k, v in sd0.items()}, gy, gz)
+        model.load_state_dict(sd)
+        digest = state_digest(sd)
+        B, _, H, W = shape
+        torch.manual_seed(nseed)                         # the reference draws z's noise first, then y's (Models.py:158-159)
+        noise_z = torch.rand(B, M, H // 64, W // 64) - 0.5
+        noise_y = torch.rand(B, M, H // 16, W // 16) - 0.5
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        opt.zero_grad()
+        torch.manual_seed(nseed)
+        out = model(x)                                   # training=True is the default
+        assert torch.equal(out["z_in"] - out["z"], (out["z"] + noise_z) - out["z"]), "noise stream not reproduced"
+        assert torch.equal(out["y_in"] - out["y"], (out["y"] + noise_y) - out["y"]), "noise stream not reproduced"
+        rd = RDL.rd_loss(out, x, 0.005)
+        rd["loss"].backward()
+        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        opt.step()
+        after = {k: p.detach().clone() for k, p in model.named_parameters()}
+        _, g64, _ = OB.loss_and_grads_residual(sd, x, M, K, noise_z, noise_y, 0.005, dtype=torch.float64)
+        blob = {"x": x.numpy(), "noise_z": noise_z.numpy(), "noise_y": noise_y.numpy(), "state_digest": np.array(digest),
+                "M": np.array(M), "K": np.array(K), "gain_y": np.array(gy, np.float32), "gain_z": np.array(gz, np.float32),
+                "loss": np.array(float(rd["loss"].detach())), "bpp_total": np.array(rd["bpp_total"]), "mse": np.array(rd["mse"]),
+                "noise_seed": np.array(nseed)}
+        for k, g in grads.items():
+            idx = sample_index(g.numel())
+            blob["gnorm_" + k] = np.array(float(g.double().norm()))
+            blob["gnorm64_" + k] = np.array(float(g64[k].norm()))
+            blob["gerr64_" + k] = np.array(float((g.double() - g64[k]).norm()))
+            blob["gsamp_" + k] = g.reshape(-1)[idx].numpy()
+            blob["psamp_" + k] = after[k].reshape(-1)[idx].numpy()
+            blob["dnorm_" + k] = np.array(float((after[k].double() - sd[k].double()).norm()))
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **blob)
+        worst = max(float(blob["gerr64_" + k] / max(blob["gnorm64_" + k], 1e-30)) for k in grads)
+        print(f"{name}: gains {gy:.4f} / {gz:.4f}, loss {float(rd['loss'].detach()):.6f} bpp {rd['bpp_total']:.6f} mse {rd['mse']:.6f}; {len(grads)} gradients, "
+              f"worst fp32-vs-fp64 relative gradient error {worst:.2e} -> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "train":
         main_train()               # only the c4_train_* files
+    elif len(sys.argv) > 1 and sys.argv[1] == "residual-train":
+        main_residual_train()      # only the c6_train_* file
     elif len(sys.argv) > 1 and sys.argv[1] == "residual":
         main_residual()            # only the c6_* files
     elif len(sys.argv) > 1 and sys.argv[1] == "scalable":

@@ -60,7 +60,13 @@ def seeded_scalable_model(M, M1, K, init="calib", precision="fp32"):
 
 def residual_cases():
     """HierarchicalMixtureResidual cases (the 3x3 residual family; oracle/make_golden.py residual)."""
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "c6_*.npz")))
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "c6_res3x3_*.npz")))
+
+
+def residual_train_cases():
+    """Training step of HierarchicalMixtureResidual (the reference's own class: forward, rd_loss, backward, Adam;
+    oracle/make_golden.py residual-train)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "c6_train_*.npz")))
 
 
 def seeded_residual_model(M, K, gain_y, gain_z, precision="fp32", sigma_bias=3.0):
@@ -78,6 +84,11 @@ def seeded_residual_model(M, K, gain_y, gain_z, precision="fp32", sigma_bias=3.0
     sd["entropy_parameters.net.4.bias"] = b
     model.load_state_dict(sd)
     return model
+
+
+def residual_state_dict(M, K, gain_y, gain_z, sigma_bias=3.0):
+    m = seeded_residual_model(M, K, gain_y, gain_z, sigma_bias=sigma_bias)
+    return {k: v.clone() for k, v in m.state_dict().items()}
 
 
 def load_golden(name):

@@ -157,3 +157,104 @@ def test_graphed_forward_of_the_main_and_residual_models():
         torch.cuda.synchronize()
         for k in ("x_hat", "y_in", "z_in", "p_y", "p_z", "logp_y"):
             assert torch.equal(out[k], eager[k]), (type(model).__name__, k)
+
+
+# ---------------------------------------------------------------------------------------------------
+# training step of the residual family (training.Tape): forward with noise, rd_loss, backward, Adam
+# ---------------------------------------------------------------------------------------------------
+def _relnorm(a, b):
+    return float((a.double() - b.double()).norm() / max(float(b.double().norm()), 1e-30))
+
+
+def _res_grad_tol(arm, key):
+    """The reference's own fp32-vs-fp64 gradient spread on this case is 1.5e-4 of a tensor's norm (the model is 16 convs deep with a
+    LeakyReLU in every residual block: an element within rounding of a kink takes the other slope).  Measured against the oracle's
+    autograd: fp32 arm <= 4.1e-6 (allowed 2e-4), bf16x3 arm <= 2.7e-4 (allowed 5e-3: a kink flip moves the tensors upstream of it)."""
+    return 2e-4 if arm == "fp32" else 5e-3
+
+
+@pytest.mark.parametrize("arm", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("case", H.residual_train_cases())
+def test_residual_training_step_matches_reference_golden(case, arm):
+    """model(x) with autograd on -> rd_loss -> loss.backward() -> Adam.step() of HierarchicalMixtureResidual against the committed
+    vectors of the REAL reference class's step (sampled entries + norms of all 119 gradient tensors) and, tensor by tensor in full,
+    against the oracle's autograd on the same weights, input and noise."""
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    from neural_image_compression_b200.training import Adam
+    from oracle import backward as OB
+    g = H.load_golden(case)
+    M, K = int(g["M"]), int(g["K"])
+    model = H.seeded_residual_model(M, K, float(g["gain_y"]), float(g["gain_z"]), precision="fp32")
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x, nz, ny = (torch.from_numpy(g[k]) for k in ("x", "noise_z", "noise_y"))
+    ref_rd, ref_g, ref_out = OB.loss_and_grads_residual(sd, x, M, K, nz, ny, 0.005)
+    model = model.cuda()
+    model.train_precision = arm
+    opt = Adam(model.parameters(), lr=1e-4)
+    opt.zero_grad()
+    out = model(x.cuda(), noise=(nz.cuda(), ny.cuda()))              # training=True is the default, as in Trainer.py:82
+    rd = rd_loss(out, x.cuda(), 0.005)
+    ltol = 1e-5 if arm == "fp32" else 1e-4
+    assert abs(float(rd["loss"].detach()) - float(g["loss"])) <= ltol * abs(float(g["loss"]))
+    assert _relnorm(out["x_hat"].detach().cpu(), ref_out["x_hat"]) < (1e-5 if arm == "fp32" else 3e-4)
+    assert _relnorm(out["y"].detach().cpu(), ref_out["y"]) < (1e-5 if arm == "fp32" else 3e-4)
+    rd["loss"].backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    opt.step()
+    torch.cuda.synchronize()
+    assert len(grads) == 119 and set(grads) == set(ref_g)
+    worst = {k: float((grads[k].double().cpu() - ref_g[k].double()).norm() / max(float(ref_g[k].double().norm()), 1e-30)) for k in grads}
+    print(arm, "worst gradient errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:6])
+    bad = {k: v for k, v in worst.items() if v > _res_grad_tol(arm, k)}
+    assert not bad, bad
+    want, _ = OB.adam_step({k: v.cpu() for k, v in before.items()}, {k: v.cpu() for k, v in grads.items()})
+    for k, p in model.named_parameters():
+        gr = grads[k]
+        idx = H.sample_index(gr.numel())
+        gn = float(g["gnorm_" + k])
+        tol = _res_grad_tol(arm, k)
+        assert abs(float(gr.double().norm()) - gn) <= tol * gn + 1e-12, (k, float(gr.double().norm()), gn)
+        np.testing.assert_allclose(gr.reshape(-1)[idx].cpu().numpy(), g["gsamp_" + k], rtol=5 * tol, atol=10 * tol * gn / gr.numel() ** 0.5,
+                                   err_msg=k)
+        np.testing.assert_allclose(p.detach().cpu().numpy(), want[k].numpy(), rtol=1e-6, atol=1e-7, err_msg=k)      # the Adam kernel
+
+
+def test_residual_step_gradients_equals_autograd_backward():
+    """training.step_gradients (what parallel.ShardedTrainer runs and captures) on the residual model = the autograd route."""
+    from neural_image_compression_b200 import training as T
+    from neural_image_compression_b200.RateDistortionLoss import rd_loss
+    g = H.load_golden(H.residual_train_cases()[0])
+    model = H.seeded_residual_model(int(g["M"]), int(g["K"]), float(g["gain_y"]), float(g["gain_z"]), precision="fp32").cuda()
+    x, nz, ny = (torch.from_numpy(g[k]).cuda() for k in ("x", "noise_z", "noise_y"))
+    out = model(x, noise=(nz, ny))
+    rd_loss(out, x, 0.005)["loss"].backward()
+    ref = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    for p in model.parameters():
+        p.grad = None
+    res = T.step_gradients(model, x, 0.005, noise=(nz, ny))
+    torch.cuda.synchronize()
+    for k, p in model.named_parameters():
+        assert p.grad is not None and torch.allclose(p.grad, ref[k], rtol=1e-5, atol=1e-8 + 1e-6 * float(ref[k].abs().max())), k
+    assert res is not None
+
+
+def test_residual_graphed_trainer_steps_like_the_eager_one():
+    """parallel.ShardedTrainer on HierarchicalMixtureResidual: eager and CUDA-graph replays of forward + loss + backward + Adam
+    (fresh noise per step: statistical check, as tests/test_gpu_train.py does for the 5x5 model)."""
+    from neural_image_compression_b200 import parallel
+    g = H.load_golden(H.residual_train_cases()[0])
+    x = torch.from_numpy(g["x"]).cuda()
+    losses = {}
+    for mode in (False, True):
+        model = H.seeded_residual_model(int(g["M"]), int(g["K"]), float(g["gain_y"]), float(g["gain_z"]), precision="bf16x3").cuda()
+        w0 = model.decoder.net[6].conv1.weight.detach().clone()
+        tr = parallel.ShardedTrainer(model, 0.005, lr=1e-4, graph=mode)
+        ls = [float(tr.step(x)["loss"].detach()) for _ in range(20)]
+        torch.cuda.synchronize()
+        losses[mode] = ls
+        assert tr.optimizer.t == 20 and int(tr.optimizer._t_dev) == 20
+        moved = float((model.decoder.net[6].conv1.weight.detach() - w0).abs().max())
+        assert 3e-4 < moved <= 20 * 3.2e-4, moved
+    assert abs(losses[True][0] - losses[False][0]) < 0.02 * losses[False][0], (losses[True][0], losses[False][0])
+    assert losses[True][-1] < losses[True][0] and abs(losses[True][-1] - losses[False][-1]) < 0.05 * losses[False][-1], losses

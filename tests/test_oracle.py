@@ -127,6 +127,29 @@ def test_training_step_oracle_matches_reference_gradients(case):
     assert float(w[:, :, 3:].abs().sum()) > 0, "masked taps carry gradient in the reference"
 
 
+@pytest.mark.parametrize("case", H.residual_train_cases())
+def test_residual_training_step_oracle_matches_reference_gradients(case):
+    """The 3x3 residual family: autograd over oracle.forward_residual (+ restated Adam) against the REAL reference class's
+    loss.backward() / Adam.step() (119 parameter tensors)."""
+    g = H.load_golden(case)
+    M, K = int(g["M"]), int(g["K"])
+    sd = H.residual_state_dict(M, K, float(g["gain_y"]), float(g["gain_z"]))
+    assert H.state_digest(sd) == str(g["state_digest"])
+    x, nz, ny = (torch.from_numpy(g[k]) for k in ("x", "noise_z", "noise_y"))
+    rd, grads, _ = OB.loss_and_grads_residual(sd, x, M, K, nz, ny, 0.005)
+    assert abs(rd["loss"] - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    keys = [k[6:] for k in g.files if k.startswith("gnorm_")]
+    assert set(keys) == set(grads.keys()) == set(OB.parameter_keys(sd)) and len(keys) == 119
+    sd["context_model.masked.weight"] *= O.mask_a(sd["context_model.masked.weight"])     # the forward's in-place side effect
+    new, _ = OB.adam_step(sd, grads)
+    for k in keys:
+        idx = H.sample_index(grads[k].numel())
+        gn = float(g["gnorm_" + k])
+        assert abs(float(grads[k].double().norm()) - gn) <= 1e-4 * gn + 1e-12, k
+        np.testing.assert_allclose(grads[k].reshape(-1)[idx].numpy(), g["gsamp_" + k], rtol=1e-3, atol=1e-4 * gn / grads[k].numel() ** 0.5, err_msg=k)
+        np.testing.assert_allclose(new[k].reshape(-1)[idx].numpy(), g["psamp_" + k], rtol=1e-6, atol=2e-6, err_msg=k)
+
+
 def test_metrics_oracle_basic_properties():
     """oracle/metrics.py (Evaluator.py:26-53 + the restated pytorch_msssim): identity, symmetry, monotonicity, luma weights."""
     from oracle import metrics as OM
