@@ -582,10 +582,33 @@ def main():
                                     "768x512, batch 4 per GPU, layer-by-layer on the conv engine (random-init weights)",
                         "value": rb * world * nr / (float(rt_ms.item()) / 1e3), "unit": "images/s", "ms_per_step": float(rt_ms.item()) / nr,
                         "precision": "bf16x3", "bpp_total": float(rrd["bpp_total"]), "scaling": "weak"}
-            del rmodel, rfwd, rx
+            del rfwd, rx
+            torch.cuda.empty_cache()
+            if not args.no_train_step:
+                # its training step (training.Tape over the residual graphs): 8 crops of 256 x 256 per GPU, as configs[3]
+                rtr = parallel.ShardedTrainer(rmodel, LAMBDA, lr=1e-4, graph=use_graph)
+                rgen = torch.Generator(device="cpu"); rgen.manual_seed(3000 + rank)
+                rcrops = [torch.rand((8, 3, 256, 256), generator=rgen).to(dev) for _ in range(2)]
+                for i in range(3):
+                    rtr.step(rcrops[i % 2])
+                sync_all()
+                rs, re_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                rs.record()
+                for i in range(nr):
+                    rtl = rtr.step(rcrops[i % 2])
+                re_.record()
+                sync_all()
+                rtt = torch.tensor([rs.elapsed_time(re_)], device=dev)
+                if world > 1:
+                    dist.all_reduce(rtt, op=dist.ReduceOp.MAX)
+                residual["train_step"] = {"workload": "forward with noise + rd_loss + backward + gradient all-reduce + Adam, 8 x 3x256x256 crops per GPU",
+                                          "value": 8 * world * nr / (float(rtt.item()) / 1e3), "unit": "images/s",
+                                          "ms_per_step": float(rtt.item()) / nr, "loss_last": float(rtl["loss"].detach())}
+                del rtr, rcrops
+            del rmodel
             torch.cuda.empty_cache()
         except Exception as e:               # noqa: BLE001
-            residual = {"error": f"{type(e).__name__}: {e}"[:300]}
+            residual = dict(residual or {}, error=f"{type(e).__name__}: {e}"[:300])
 
     assert lib.nic_pipeline_status() == 0, "a tensor-core kernel aborted on an expired pipeline wait: numbers invalid"
     if rank == 0:

@@ -4,6 +4,7 @@ Same class names, constructor arguments and parameter names (``conv1 / conv2 / g
 upsample.deconv``, ``conv / shuffle``, ``deconv``) so that ``state_dict`` round-trips with the reference.  Each block executes as
 a short chain of C-ABI calls - ``nic_conv_fwd`` with the bias / LeakyReLU epilogue fused, the GDN / IGDN contraction, and
 ``nic_add_inplace`` for the residual sum - on f32 NHWC tensors (``run_nhwc``); ``forward`` wraps that for stand-alone NCHW calls.
+With a ``tape`` (training.Tape) the same chain is the TRAINING forward: every op is recorded for the hand-written backward.
 Arithmetic: "bf16x3" (tensor cores, hi/lo-split operands; layers whose input channel count is not a multiple of 64, e.g. the
 3-channel first block, run on the fp32 CUDA-core kernels) or "fp32".
 """
