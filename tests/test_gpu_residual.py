@@ -128,7 +128,7 @@ def test_residual_model_matches_reference_vectors(case, precision):
     assert set(out) == set(ref) | {"training"}
 
 
-def test_residual_model_rejects_autograd_training_call_and_bad_arguments():
+def test_residual_model_bad_arguments_and_training_calls():
     from neural_image_compression_b200.Models import HierarchicalMixtureResidual
     with pytest.raises(ValueError):
         HierarchicalMixtureResidual(0)
@@ -136,11 +136,12 @@ def test_residual_model_rejects_autograd_training_call_and_bad_arguments():
         HierarchicalMixtureResidual(128, K=0)
     m = HierarchicalMixtureResidual(128, K=1).cuda()
     x = torch.rand(1, 3, 64, 64).cuda()
-    with pytest.raises(NotImplementedError):
-        m(x)                                                  # training=True with autograd on: the backward is not built
+    out = m(x)                                                # training=True with autograd on: the differentiable training forward
+    assert out["training"] is True and out["x_hat"].requires_grad and out["logp_y"].requires_grad and not out["y_in"].requires_grad
+    assert float((out["y_in"] - out["y"]).abs().max()) <= 0.5
     with torch.no_grad():
         out = m(x, training=True)
-    assert out["training"] is True and float((out["y_in"] - out["y"]).abs().max()) <= 0.5
+    assert out["training"] is True and float((out["y_in"] - out["y"]).abs().max()) <= 0.5 and not out["x_hat"].requires_grad
 
 
 def test_graphed_forward_of_the_main_and_residual_models():
