@@ -9,6 +9,7 @@
 //
 // Reference ops served: Components.py:10-16, 39-45, 69-73, 99-103; ContextModels.py:18-20;
 // ParametersModels.py:29-35; GDN (compressai) as a 1x1 tap over x^2 with the x * rsqrt / sqrt epilogue.
+#include <stdlib.h>
 #include "conv_common.cuh"
 
 namespace nic {
@@ -332,6 +333,64 @@ conv_simt_kernel(const SimtParams p) {
   }
 }
 
+// Few-input-channel convs to 128 output channels (the RGB-input convs of the 3x3 residual family's first block: Conv2d(3, 128, 3, s2)
+// and its 1x1 stride-2 skip, Layers.py:38-47).  The register-tiled kernel above spends its time gathering K = 27 (or 3) operands per
+// pixel into 16-deep K slabs: 396 + 339 us for 4 x 512 x 768 images against an output-write floor of ~40 us each.  Here a warp owns
+// one output pixel at a time, lane l its channels 4 l .. 4 l + 3 with their KT x 4 weights in registers; the KT inputs of the pixel
+// are fetched by lanes 0 .. KT - 1 with one load instruction and handed round by shuffles, the result leaves as one 512-byte row.
+// fp32 FMAs in ascending k, bias last - the same sum.
+template <int KT>
+__global__ void __launch_bounds__(128)
+conv_smallcin_kernel(const SimtParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int cin = p.cin, kt = p.tt.ntaps * cin;
+  float4 w[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+    w[k] = k < kt ? __ldg(reinterpret_cast<const float4*>(p.w + static_cast<long>(k) * p.cout) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + lane);
+  // lane k fetches operand k = (tap, input channel) of the pixel: ONE load instruction per pixel and warp, issued a pixel ahead;
+  // the FMA loop takes the operands by shuffle
+  const int my_t = lane < kt ? lane / cin : 0, my_c = lane < kt ? lane - my_t * cin : 0;
+  const int my_dy = p.tt.dy[my_t], my_dx = p.tt.dx[my_t];
+  const long my_coff = my_c * p.xs_c;
+  const int is = p.tt.in_stride;
+  const int pixels = p.n * p.hout * p.wout, hw = p.wout * p.hout;       // host: < 2^31 (32-bit index arithmetic: no emulated divisions)
+  auto fetch = [&](int pix) -> float {
+    if (pix >= pixels || lane >= kt) return 0.f;
+    const int img = pix / hw, r = pix - img * hw, oy = r / p.wout, ox = r - oy * p.wout;
+    const int iy = oy * is + my_dy, ix = ox * is + my_dx;
+    return (iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) ? __ldg(p.x + img * p.xs_n + my_coff + iy * p.xs_h + ix * p.xs_w) : 0.f;
+  };
+  // PB consecutive pixels per warp and round: their PB loads are in flight together (one load a pixel ahead left every round
+  // waiting out a full memory latency: 271 us at K = 27; the arithmetic of a pixel is ~150 issue slots)
+  constexpr int PB = 8;
+  for (int base = warp * PB; base < pixels; base += nwarps * PB) {
+    float v[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) v[j] = fetch(base + j);
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int pix = base + j;
+      if (pix >= pixels) break;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        const float a = __shfl_sync(0xffffffffu, v[j], k);
+        acc.x = fmaf(a, w[k].x, acc.x); acc.y = fmaf(a, w[k].y, acc.y); acc.z = fmaf(a, w[k].z, acc.z); acc.w = fmaf(a, w[k].w, acc.w);
+      }
+      acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+      if (p.epilogue == NIC_EPI_LRELU) {
+        acc.x = acc.x > 0.f ? acc.x : acc.x * 0.01f; acc.y = acc.y > 0.f ? acc.y : acc.y * 0.01f;
+        acc.z = acc.z > 0.f ? acc.z : acc.z * 0.01f; acc.w = acc.w > 0.f ? acc.w : acc.w * 0.01f;
+      }
+      const int img = pix / hw, r = pix - img * hw, oy = r / p.wout, ox = r - oy * p.wout;
+      __stcs(reinterpret_cast<float4*>(p.y + img * p.ys_n + oy * p.ys_h + ox * p.ys_w + lane * 4), acc);
+    }
+  }
+}
+
 static int launch_simt(const SimtParams& p, cudaStream_t st);
 static void set_strides(int layout, long c, long h, long w, long* sn, long* sc, long* sh, long* sw) {
   if (layout == NIC_LAYOUT_NCHW) { *sn = c * h * w; *sc = h * w; *sh = w; *sw = 1; }
@@ -347,6 +406,21 @@ static int launch_simt(const SimtParams& p, cudaStream_t st) {
     if (P > maxP) maxP = P;
   }
   if (maxP == 0) return NIC_OK;
+  const int kt = p.tt.ntaps * p.cin;
+  const char* sc_env = getenv("NIC_SMALLCIN");                       // A/B switch: 0 = the register-tiled kernel for these layers too
+  if (p.tt.nphases == 1 && p.tt.out_stride == 1 && p.cin <= 4 && p.cout == 128 && kt <= 27 && !p.a_square && !p.out_bf16 &&
+      (p.epilogue == NIC_EPI_BIAS || p.epilogue == NIC_EPI_LRELU) && p.ys_c == 1 && p.ys_w % 4 == 0 && p.ys_h % 4 == 0 && p.ys_n % 4 == 0 &&
+      ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.bias)) & 15) == 0 &&
+      !(sc_env && atoi(sc_env) == 0)) {
+    const long pixels = static_cast<long>(p.n) * p.hout * p.wout;
+    if (pixels + kNumSMs * 12L * 4 >= 0x7fffffffL) return fail(NIC_E_BADSHAPE, "conv fp32: %ld output pixels", pixels);
+    long blocks = (pixels + 31) / 32;                                 // 4 warps per block (142 registers: 3 blocks per SM), one pixel per warp and iteration
+    if (blocks > kNumSMs * 12) blocks = kNumSMs * 12;
+    if (kt <= 3) conv_smallcin_kernel<3><<<static_cast<unsigned>(blocks), 128, 0, st>>>(p);
+    else if (kt <= 12) conv_smallcin_kernel<12><<<static_cast<unsigned>(blocks), 128, 0, st>>>(p);
+    else conv_smallcin_kernel<27><<<static_cast<unsigned>(blocks), 128, 0, st>>>(p);
+    return check_launch("conv_smallcin_kernel");
+  }
   const bool gather = (p.xs_c != 1) || (p.cin % BK != 0) || ((reinterpret_cast<uintptr_t>(p.x) & 15) != 0) ||
                       (p.xs_w % 4 != 0) || (p.xs_h % 4 != 0) || (p.xs_n % 4 != 0);
   const bool small_n = p.cout <= 16;
