@@ -131,13 +131,16 @@ class _Chain(nn.Module):
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             fuse = isinstance(nxt, nn.LeakyReLU)
             kw = final_kw if (final_kw and i == len(mods) - 1) else {}
+            after = mods[i + (2 if fuse else 1)] if i + (2 if fuse else 1) < len(mods) else None
+            # evaluation: a conv whose only consumer is the next conv hands its result over as a bf16 hi/lo pair (bf16x3 arm)
+            pair = tape is None and isinstance(after, (nn.Conv2d, nn.ConvTranspose2d, L.TransposedDeconv3x3))
             if isinstance(m, L.TransposedDeconv3x3):
-                x, h, w = m.run_nhwc(x, n, h, w, arm, in_layout=layout, epilogue=EPI_LRELU if fuse else EPI_BIAS, tape=tape)
+                x, h, w = m.run_nhwc(x, n, h, w, arm, in_layout=layout, epilogue=EPI_LRELU if fuse else EPI_BIAS, tape=tape, pair_out=pair)
             elif isinstance(m, L._Block):
                 x, h, w = m.run_nhwc(x, n, h, w, arm, in_layout=layout, tape=tape)
                 fuse = False
             elif isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
-                x, h, w = L._conv(arm, m, EPI_LRELU if fuse else EPI_BIAS, x, n, h, w, in_layout=layout, tape=tape, **kw)
+                x, h, w = L._conv(arm, m, EPI_LRELU if fuse else EPI_BIAS, x, n, h, w, in_layout=layout, tape=tape, pair_out=pair, **kw)
             else:
                 raise TypeError(f"unexpected module in a transform: {type(m).__name__}")
             layout = LAYOUT_NHWC

@@ -30,7 +30,7 @@ def _arm(precision: Optional[str], channels: int) -> str:
     return p if p in ("fp32", "bf16x3") else "bf16x3"
 
 
-def _conv(arm, conv, epi, x, n, h, w, in_layout=LAYOUT_NHWC, out_layout=LAYOUT_NHWC, tape=None, **out_kw):
+def _conv(arm, conv, epi, x, n, h, w, in_layout=LAYOUT_NHWC, out_layout=LAYOUT_NHWC, tape=None, pair_out=False, **out_kw):
     """One conv (+ bias / LeakyReLU) -> (f32 tensor, h_out, w_out).  tape: the training forward's record (training.Tape); the RGB
     layer then stays NCHW (it is the transform's output and x_hat is NCHW)."""
     T = _T()
@@ -42,7 +42,9 @@ def _conv(arm, conv, epi, x, n, h, w, in_layout=LAYOUT_NHWC, out_layout=LAYOUT_N
         # output of g_s - write NCHW, and the chain's NHWC convention is restored by a view permutation
         y = T.conv_forward(arm, conv, epi, x, n, h, w, in_layout=in_layout, out_layout=LAYOUT_NCHW).permute(0, 2, 3, 1).contiguous()
     else:
-        y = T.conv_forward(arm, conv, epi, x, n, h, w, in_layout=in_layout, out_layout=out_layout)
+        # pair_out: the only consumer is the next conv - in the bf16x3 arm the result stays a bf16 hi/lo pair (evaluation only:
+        # the training forward keeps f32 activations for the backward)
+        y = T.conv_forward(arm, conv, epi, x, n, h, w, in_layout=in_layout, out_layout=out_layout, pair_out=pair_out, **out_kw)
     T.forget_pairs()
     return (y,) + engine.conv_out_hw(conv, h, w)
 
@@ -100,8 +102,8 @@ class TransposedDeconv3x3(_Block):
         super().__init__()
         self.deconv = nn.ConvTranspose2d(in_ch, out_ch, kernel_size=3, stride=upsample, padding=1, output_padding=upsample - 1)
 
-    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC, epilogue=EPI_BIAS, tape=None):
-        return _conv(arm, self.deconv, epilogue, x, n, h, w, in_layout=in_layout, tape=tape)
+    def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC, epilogue=EPI_BIAS, tape=None, pair_out=False):
+        return _conv(arm, self.deconv, epilogue, x, n, h, w, in_layout=in_layout, tape=tape, pair_out=pair_out)
 
 
 class ResidualBlockWithStride(_Block):
@@ -117,7 +119,7 @@ class ResidualBlockWithStride(_Block):
 
     def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC, tape=None):
         T = _T()
-        u, ho, wo = _conv(arm, self.conv1, EPI_LRELU, x, n, h, w, in_layout=in_layout, tape=tape)
+        u, ho, wo = _conv(arm, self.conv1, EPI_LRELU, x, n, h, w, in_layout=in_layout, tape=tape, pair_out=True)
         u, _, _ = _conv(arm, self.conv2, EPI_BIAS, u, n, ho, wo, tape=tape)
         out = _gdn(arm, self.gdn, u, n, ho, wo, tape=tape)
         if self.skip is not None:
@@ -140,7 +142,7 @@ class ResidualBlockUpsample(_Block):
 
     def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC, tape=None):
         T = _T()
-        u, ho, wo = self.subpel_conv.run_nhwc(x, n, h, w, arm, in_layout=in_layout, epilogue=EPI_LRELU, tape=tape)
+        u, ho, wo = self.subpel_conv.run_nhwc(x, n, h, w, arm, in_layout=in_layout, epilogue=EPI_LRELU, tape=tape, pair_out=True)
         u, _, _ = _conv(arm, self.conv, EPI_BIAS, u, n, ho, wo, tape=tape)
         out = _gdn(arm, self.igdn, u, n, ho, wo, tape=tape)
         idn, _, _ = self.upsample.run_nhwc(x, n, h, w, arm, in_layout=in_layout, tape=tape)
@@ -159,7 +161,7 @@ class ResidualBlock(_Block):
 
     def run_nhwc(self, x, n, h, w, arm, in_layout=LAYOUT_NHWC, tape=None):
         T = _T()
-        u, _, _ = _conv(arm, self.conv1, EPI_LRELU, x, n, h, w, in_layout=in_layout, tape=tape)
+        u, _, _ = _conv(arm, self.conv1, EPI_LRELU, x, n, h, w, in_layout=in_layout, tape=tape, pair_out=True)
         out, _, _ = _conv(arm, self.conv2, EPI_LRELU, u, n, h, w, tape=tape)
         if self.skip is not None:
             idn, _, _ = _conv(arm, self.skip, EPI_BIAS, x, n, h, w, in_layout=in_layout, tape=tape)

@@ -160,15 +160,20 @@ def _is_first_layer_shape(conv: nn.Module) -> bool:
 
 def conv_forward(arm: str, conv: nn.Module, epilogue: int, x: torch.Tensor, n: int, h: int, w: int, in_layout: int = LAYOUT_NHWC,
                  out_layout: int = LAYOUT_NHWC, out: Optional[torch.Tensor] = None, out_c_total: int = 0, out_c_offset: int = 0,
-                 mask_a: bool = False) -> torch.Tensor:
-    """One conv (+ bias / LeakyReLU) with f32 tensors at both ends; the contraction on the tensor cores in the bf16x3 arm."""
+                 mask_a: bool = False, pair_out: bool = False) -> torch.Tensor:
+    """One conv (+ bias / LeakyReLU) with f32 tensors at both ends; the contraction on the tensor cores in the bf16x3 arm.
+    pair_out (evaluation chains of the residual family): where the tensor-core kernel runs, leave the result as the bf16 hi/lo
+    pair the next conv consumes (no f32 round trip, no nic_to_pair launch); x may itself be such a pair."""
     op = _train_op(conv, epilogue, mask_a)
     if arm == "bf16x3" and _is_first_layer_shape(conv) and in_layout == LAYOUT_NCHW and out_layout == LAYOUT_NHWC and out is None \
             and epilogue == EPI_BIAS and w % 4 == 0:
         return op.run(x, n, h, w, "bf16x3", in_layout=LAYOUT_NCHW, out_dtype=torch.float32)       # the dedicated 3 -> 128 kernel
     if arm == "bf16x3" and in_layout == LAYOUT_NHWC and conv.in_channels % 64 == 0 and conv.out_channels <= 1792:
-        return op.run(to_pair(x), n, h, w, "bf16x3", out_layout=out_layout, out=out, out_c_total=out_c_total,
-                      out_c_offset=out_c_offset, out_dtype=torch.float32)
+        as_pair = pair_out and out is None and out_layout == LAYOUT_NHWC and conv.out_channels % 64 == 0
+        return op.run(x if x.dtype == torch.bfloat16 else to_pair(x), n, h, w, "bf16x3", out_layout=out_layout, out=out,
+                      out_c_total=out_c_total, out_c_offset=out_c_offset, out_dtype=None if as_pair else torch.float32)
+    if x.dtype == torch.bfloat16:
+        raise ValueError("conv_forward: a bf16 pair input needs the tensor-core path of the bf16x3 arm")
     return op.run(x, n, h, w, PREC, in_layout=in_layout, out_layout=out_layout, out=out, out_c_total=out_c_total,
                   out_c_offset=out_c_offset)
 

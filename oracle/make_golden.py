@@ -319,6 +319,7 @@ def main_train():
 RESIDUAL_TRAIN_CASES = {
     # name: (M, K, input shape, noise seed) - the training step of HierarchicalMixtureResidual at parity-test size
     "c6_train_res3x3_k3_128_calib": (128, 3, (2, 3, 64, 128), 21),
+    "c6_train_res3x3_k1_128x64_calib": (128, 1, (1, 3, 128, 64), 22),
 }
 
 
