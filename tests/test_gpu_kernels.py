@@ -68,7 +68,6 @@ def test_gm_likelihood_kernel_forms_agree(dev, K, shape, full, monkeypatch):
         outs = []
         for env in ({"NIC_LIK_FLAT": "0"}, {}):
             monkeypatch.delenv("NIC_LIK_FLAT", raising=False)
-            monkeypatch.delenv("NIC_LIK_STAGED", raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             r = gm_likelihood(y.to(dev), raw.to(dev), M, K, qmode, noise=None if nz is None else nz.to(dev), full=full)

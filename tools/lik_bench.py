@@ -17,7 +17,7 @@ flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
 
 def run(lb, env, clean=False):
-    for k in ("NIC_LIK_FLAT", "NIC_LIK_GRID", "NIC_LIK_PARTS", "NIC_LIK_STAGED"):
+    for k in ("NIC_LIK_FLAT", "NIC_LIK_GRID", "NIC_LIK_PARTS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     y = 5 * torch.randn((lb, M, H, W), device=dev)

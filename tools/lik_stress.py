@@ -28,7 +28,7 @@ for it in range(N):
     noise = (torch.rand_like(y) - 0.5) if qm == Q_NOISE else None
     outs = []
     for env in ({"NIC_LIK_FLAT": "0"}, {}):
-        for k in ("NIC_LIK_FLAT", "NIC_LIK_STAGED"):
+        for k in ("NIC_LIK_FLAT",):
             os.environ.pop(k, None)
         os.environ.update(env)
         # poison the allocator's recycled blocks so that an element a kernel does not write shows up
