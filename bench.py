@@ -483,7 +483,7 @@ def main():
         nbytes = yl.numel() * 88                                  # 52 B/elem + 36 B/elem for weights/mus/sigmas
         lik[f"batch{lb}"] = {"ms": lms, "GB/s": nbytes / (lms / 1e3) / 1e9, "frac_of_hbm_peak": nbytes / (lms / 1e3) / 1e9 / peaks["hbm"]}
         del yl, rawl
-    roofline_lik = {"bound": "hbm", "kernel": "gm_likelihood_kernel<K=3, full>", "unit": "GB/s", "peak": peaks["hbm"],
+    roofline_lik = {"bound": "hbm", "kernel": "gm_likelihood_flat_kernel<K=3, full>", "unit": "GB/s", "peak": peaks["hbm"],
                     "bytes_per_y_element": 88, "peak_source": f"{peaks['src']} copy bandwidth", **lik}
 
     # ---- the training step (BASELINE.json configs[3]) - extra line item, every rank takes part (gradient all-reduce) ----------
