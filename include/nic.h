@@ -159,6 +159,49 @@ int nic_conv_fwd_ex(const nic_conv_desc* d, const void* x, const void* w_packed,
                     void* workspace, size_t workspace_bytes, const int32_t* in_lo_nonzero, void* stream);
 
 /*
+ * Context model + entropy-parameter stack (+ likelihoods) as ONE call (SURVEY.md section 8b `nic_ctx_ep_fwd`; replaces
+ * ContextModels.py:15-20 -> torch.cat (Models.py:73) -> ParametersModels.py:29-35 (-> ParametersModels.py:43-64 +
+ * EntropyModels.py:192-233, Models.py:86-87 when p is given)).  It is a host-side composite, NOT one kernel: it enqueues the masked
+ * 5x5 context conv (12 live taps), the three 1x1 layers and, optionally, the likelihood kernel on `stream`, with the intermediates
+ * in caller-owned buffers (they stay L2-resident between the launches; DESIGN.md section 4 explains why a single fused kernel
+ * does not fit at fp32 grade).  Results are bit-identical to the same five nic_* calls made one by one.
+ *   ctx:      descriptor of the context conv; writes phi into its channel window of `combined` (out_c_total / out_c_offset);
+ *             the caller has put psi (the h_s output) into the other window, so torch.cat never happens
+ *   ep[0..2]: descriptors of the 1x1 layers: combined -> e1 -> e2 -> raw (ep[2]: out_layout NCHW, out_dtype F32)
+ *   y_in_engine / y_in_lo_nonzero: the context conv's input in the engine layout and its optional nic_latent_handoff_ex flag
+ *   raw:      [n, (1 + 2) K M or 2 M, h, w] f32, always written (the likelihood kernel reads it)
+ *   p == NULL: stop after raw.  Otherwise y_in (NCHW f32), m, k, qmode and the outputs are nic_gm_likelihood_fwd's.
+ *   workspace: >= the largest nic_conv_workspace_bytes of the four descriptors (the launches are sequential).
+ */
+typedef struct nic_ctx_ep_args {
+  const nic_conv_desc* ctx;
+  const nic_conv_desc* ep[3];
+  const void* w_ctx;
+  const float* b_ctx;
+  const void* w_ep[3];
+  const float* b_ep[3];
+  const void* y_in_engine;
+  const int32_t* y_in_lo_nonzero;
+  void* combined;
+  void* e1;
+  void* e2;
+  float* raw;
+  const float* y_in;
+  const float* noise;
+  int32_t m, k, qmode, reserved;
+  float* y_in_out;
+  float* p;
+  float* logp;
+  float* weights;
+  float* mus;
+  float* sigmas;
+  float* logp_partials;
+  void* workspace;
+  size_t workspace_bytes;
+} nic_ctx_ep_args;
+int nic_ctx_ep_fwd(const nic_ctx_ep_args* a, void* stream);
+
+/*
  * Stand-alone GDN / IGDN (compressai.layers.gdn.GDN.forward; call sites Components.py:11-15, 40-44) for
  * callers that invoke the layer on its own: y = x * rsqrt(beta + gamma . x^2) (inverse: * sqrt).
  * x, y: f32 in `layout`; gamma_packed / beta_eff from nic_pack_gdn(NIC_PREC_FP32).

@@ -33,6 +33,15 @@ class ConvDesc(C.Structure):
         "in_dtype", "out_dtype", "out_c_total", "out_c_offset")]
 
 
+class CtxEpArgs(C.Structure):
+    """struct nic_ctx_ep_args (include/nic.h): one call for context conv + entropy-parameter stack (+ likelihoods)."""
+    _fields_ = [("ctx", C.POINTER(ConvDesc)), ("ep", C.POINTER(ConvDesc) * 3), ("w_ctx", _vp), ("b_ctx", _vp), ("w_ep", _vp * 3),
+                ("b_ep", _vp * 3), ("y_in_engine", _vp), ("y_in_lo_nonzero", _vp), ("combined", _vp), ("e1", _vp), ("e2", _vp),
+                ("raw", _vp), ("y_in", _vp), ("noise", _vp), ("m", _i32), ("k", _i32), ("qmode", _i32), ("reserved", _i32),
+                ("y_in_out", _vp), ("p", _vp), ("logp", _vp), ("weights", _vp), ("mus", _vp), ("sigmas", _vp), ("logp_partials", _vp),
+                ("workspace", _vp), ("workspace_bytes", _sz)]
+
+
 # name -> (restype, argtypes); must list every function include/nic.h declares (tests check this)
 SIGNATURES = {
     "nic_version": (C.c_int, []),
@@ -46,6 +55,7 @@ SIGNATURES = {
     "nic_conv_workspace_bytes": (_sz, [C.POINTER(ConvDesc)]),
     "nic_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nic_conv_fwd_ex": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "nic_ctx_ep_fwd": (C.c_int, [C.POINTER(CtxEpArgs), _vp]),
     "nic_gdn_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "nic_latent_handoff": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp]),
     "nic_latent_handoff_ex": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),

@@ -91,4 +91,33 @@ int nic_conv_fwd_ex(const nic_conv_desc* d, const void* x, const void* w_packed,
   }
 }
 
+int nic_ctx_ep_fwd(const nic_ctx_ep_args* a, void* stream) {
+  if (int rc = nic_check_device()) return rc;
+  if (!a || !a->ctx || !a->ep[0] || !a->ep[1] || !a->ep[2]) return fail(NIC_E_BADSHAPE, "ctx_ep: null descriptor");
+  if (!a->y_in_engine || !a->combined || !a->e1 || !a->e2 || !a->raw) return fail(NIC_E_BADSHAPE, "ctx_ep: null buffer");
+  const nic_conv_desc* ds[4] = {a->ctx, a->ep[0], a->ep[1], a->ep[2]};
+  size_t need = 0;
+  for (const nic_conv_desc* d : ds) {
+    if (int rc = validate_conv_desc(d)) return rc;
+    const size_t b = nic_conv_workspace_bytes(d);
+    need = b > need ? b : need;
+  }
+  if (need && (!a->workspace || a->workspace_bytes < need)) return fail(NIC_E_WORKSPACE, "ctx_ep: workspace %zu < %zu bytes", a->workspace_bytes, need);
+  if (a->ep[0]->n != a->ctx->n || a->ep[0]->h_in != a->ctx->h_out || a->ep[0]->w_in != a->ctx->w_out ||
+      a->ep[0]->c_in != (a->ctx->out_c_total ? a->ctx->out_c_total : a->ctx->c_out) || a->ep[1]->c_in != a->ep[0]->c_out ||
+      a->ep[2]->c_in != a->ep[1]->c_out)
+    return fail(NIC_E_BADSHAPE, "ctx_ep: the four descriptors do not chain");
+  // phi into its window of `combined` (psi is already in the other one), then the 1x1 stack
+  if (int rc = nic_conv_fwd_ex(a->ctx, a->y_in_engine, a->w_ctx, a->b_ctx, nullptr, nullptr, a->combined, a->workspace, a->workspace_bytes,
+                               a->y_in_lo_nonzero, stream)) return rc;
+  if (int rc = nic_conv_fwd(a->ep[0], a->combined, a->w_ep[0], a->b_ep[0], nullptr, nullptr, a->e1, a->workspace, a->workspace_bytes, stream)) return rc;
+  if (int rc = nic_conv_fwd(a->ep[1], a->e1, a->w_ep[1], a->b_ep[1], nullptr, nullptr, a->e2, a->workspace, a->workspace_bytes, stream)) return rc;
+  if (int rc = nic_conv_fwd(a->ep[2], a->e2, a->w_ep[2], a->b_ep[2], nullptr, nullptr, a->raw, a->workspace, a->workspace_bytes, stream)) return rc;
+  if (!a->p) return NIC_OK;
+  if (a->ep[2]->out_layout != NIC_LAYOUT_NCHW || a->ep[2]->out_dtype != NIC_DT_F32)
+    return fail(NIC_E_BADSHAPE, "ctx_ep: the likelihood kernel reads raw as NCHW f32");
+  return nic_gm_likelihood_fwd(a->y_in, a->raw, a->noise, a->ctx->n, a->m, a->ep[2]->h_out * a->ep[2]->w_out, a->k, a->qmode, a->y_in_out,
+                               a->p, a->logp, a->weights, a->mus, a->sigmas, a->logp_partials, stream);
+}
+
 }  // extern "C"

@@ -160,6 +160,68 @@ class ConvOp:
         return out
 
 
+class CtxEpPlan:
+    """The context conv + entropy-parameter stack (+ likelihood kernel) of one (batch, size, precision) as ONE C-ABI call
+    (nic_ctx_ep_fwd: ContextModels.py:15-20 -> Models.py:73 -> ParametersModels.py:29-64 -> EntropyModels.py:192-233).
+    Descriptors, packed weights and the intermediate buffers are set up once; `run` fills `combined[..., phi window]`, the raw
+    parameters and - with y_in - the likelihood outputs.  Results are bit-identical to the four ConvOp.run calls + gm_likelihood."""
+
+    def __init__(self, ctx_op: "ConvOp", ep_ops, n: int, h: int, w: int, precision: str, M: int, K: int, device, full: bool = True):
+        lib = _lib.load()
+        x3 = precision == "bf16x3"
+        adt = act_dtype(precision)
+        in_dt = (DT_BF16X2 if x3 else DT_BF16) if adt == torch.bfloat16 else DT_F32
+        cw = 2 if (x3 and adt == torch.bfloat16) else 1
+        self.n, self.h, self.w, self.M, self.K, self.precision, self.full = n, h, w, M, K, precision, full
+        self.descs = [ctx_op.desc(n, h, w, precision, LAYOUT_NHWC, LAYOUT_NHWC, in_dt, in_dt, 4 * M, 0),
+                      ep_ops[0].desc(n, h, w, precision, LAYOUT_NHWC, LAYOUT_NHWC, in_dt, in_dt),
+                      ep_ops[1].desc(n, h, w, precision, LAYOUT_NHWC, LAYOUT_NHWC, in_dt, in_dt),
+                      ep_ops[2].desc(n, h, w, precision, LAYOUT_NHWC, LAYOUT_NCHW, in_dt, DT_F32)]
+        self.ops = [ctx_op] + list(ep_ops)
+        self.e1 = torch.empty((n, h, w, cw * self.descs[1].c_out), dtype=adt, device=device)
+        self.e2 = torch.empty((n, h, w, cw * self.descs[2].c_out), dtype=adt, device=device)
+        ws = max(lib.nic_conv_workspace_bytes(C.byref(d)) for d in self.descs)
+        self.ws = torch.empty(max(ws, 256), dtype=torch.uint8, device=device)
+        self.device = device
+
+    def run(self, y_in_engine: torch.Tensor, combined: torch.Tensor, y_in: Optional[torch.Tensor] = None, qmode: int = 2,
+            in_lo_flag: Optional[torch.Tensor] = None):
+        """-> (raw [n, C, h, w] f32, likelihood dict | None).  qmode: _lib.Q_* (default Q_PASSTHRU: y_in is already quantised)."""
+        lib = _lib.load()
+        n, h, w, M, K = self.n, self.h, self.w, self.M, self.K
+        packed = [op.packed(self.precision) for op in self.ops]
+        raw = torch.empty((n, self.descs[3].c_out, h, w), dtype=torch.float32, device=self.device)
+        a = _lib.CtxEpArgs()
+        a.ctx = C.pointer(self.descs[0])
+        for i in range(3):
+            a.ep[i] = C.pointer(self.descs[1 + i])
+            a.w_ep[i], a.b_ep[i] = ptr(packed[1 + i][0]), ptr(packed[1 + i][1])
+        a.w_ctx, a.b_ctx = ptr(packed[0][0]), ptr(packed[0][1])
+        a.y_in_engine, a.y_in_lo_nonzero = ptr(y_in_engine), ptr(in_lo_flag)
+        a.combined, a.e1, a.e2, a.raw = ptr(combined), ptr(self.e1), ptr(self.e2), ptr(raw)
+        a.workspace, a.workspace_bytes = ptr(self.ws), self.ws.numel()
+        out = None
+        if y_in is not None:
+            p, logp = torch.empty_like(y_in), torch.empty_like(y_in)
+            parts = partials(n, self.device)
+            out = {"p": p, "logp": logp, "partials": parts}
+            a.y_in, a.m, a.k, a.qmode = ptr(y_in), M, K, qmode
+            a.p, a.logp, a.logp_partials = ptr(p), ptr(logp), ptr(parts)
+            if self.full:
+                shape = (n, M, h, w) if K == 1 else (n, K, M, h, w)
+                mus, sgs = torch.empty(shape, dtype=torch.float32, device=self.device), torch.empty(shape, dtype=torch.float32, device=self.device)
+                a.mus, a.sigmas = ptr(mus), ptr(sgs)
+                if K == 1:
+                    out["mu"], out["sigma"] = mus, sgs
+                else:
+                    ws_ = torch.empty(shape, dtype=torch.float32, device=self.device)
+                    a.weights = ptr(ws_)
+                    out["weights"], out["mus"], out["sigmas"] = ws_, mus, sgs
+        with torch.cuda.device(self.device):
+            check(lib.nic_ctx_ep_fwd(C.byref(a), current_stream()), "nic_ctx_ep_fwd")
+        return raw, out
+
+
 def to_pair(v: torch.Tensor) -> torch.Tensor:
     """f32 [..., c] -> bf16 [..., 2c] = [hi | lo], hi = bf16(v), lo = bf16(v - hi): the NIC_DT_BF16X2 activation format."""
     hi = v.to(torch.bfloat16)

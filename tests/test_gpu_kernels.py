@@ -304,3 +304,55 @@ def test_rd_loss_resums_when_logp_was_modified_in_place(dev):
     out["logp_y"].mul_(2.0)
     b = rd_loss(out, x, 0.005)["bpp_y"]
     assert abs(b - 2 * a) < 1e-5 * abs(a)
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16", "fp32"])
+@pytest.mark.parametrize("K", [3, 1])
+def test_ctx_ep_one_call_equals_the_separate_calls(dev, precision, K):
+    """nic_ctx_ep_fwd (context conv + entropy-parameter stack + likelihoods behind ONE C-ABI call) against the
+    same work as four nic_conv_fwd calls + nic_gm_likelihood_fwd: bit-identical raw parameters and likelihood outputs, and the raw
+    parameters against the oracle (ContextModels.py:15-20, Models.py:73, ParametersModels.py:29-35)."""
+    from neural_image_compression_b200 import _lib, engine
+    from neural_image_compression_b200.EntropyModels import gm_likelihood
+    M, B, hy, wy = 128, 2, 8, 12
+    model = H.seeded_model(M, K, "calib", precision=precision)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(dev)
+    torch.manual_seed(5)
+    yq = torch.round(4 * torch.randn(B, hy, wy, M))
+    psi = torch.randn(B, hy, wy, 2 * M)
+    pair, adt = precision == "bf16x3", engine.act_dtype(precision)
+    y_eng = (engine.to_pair(yq) if pair else yq.to(adt)).to(dev)
+    y_nchw = yq.permute(0, 3, 1, 2).contiguous().to(dev)
+
+    def fresh_combined():
+        c = torch.zeros((B, hy, wy, (2 if pair else 1) * 4 * M), dtype=adt, device=dev)
+        if pair:
+            pp = engine.to_pair(psi).to(dev)
+            c[..., 2 * M:4 * M] = pp[..., :2 * M]; c[..., 6 * M:8 * M] = pp[..., 2 * M:]
+        else:
+            c[..., 2 * M:] = psi.to(adt).to(dev)
+        return c
+    model.context_model.masked.apply_mask_()
+    ctx_op, ep = model.context_model.masked._op, model.entropy_parameters.ops
+    with torch.no_grad():
+        c1 = fresh_combined()
+        ctx_op.run(y_eng, B, hy, wy, precision, out=c1, out_c_total=4 * M, out_c_offset=0)
+        a = ep[0].run(c1, B, hy, wy, precision)
+        a = ep[1].run(a, B, hy, wy, precision)
+        raw1 = ep[2].run(a, B, hy, wy, precision, out_layout=_lib.LAYOUT_NCHW, out_dtype=torch.float32)
+        l1 = gm_likelihood(y_nchw, raw1, M, K, _lib.Q_PASSTHRU, full=True, want_y_in=False)
+        c2 = fresh_combined()
+        plan = engine.CtxEpPlan(ctx_op, ep, B, hy, wy, precision, M, K, dev, full=True)
+        raw2, l2 = plan.run(y_eng, c2, y_in=y_nchw, qmode=_lib.Q_PASSTHRU)
+        raw3, none = plan.run(y_eng, fresh_combined())                   # without the likelihood epilogue
+    torch.cuda.synchronize()
+    assert none is None and torch.equal(raw1, raw2) and torch.equal(raw1, raw3) and torch.equal(c1, c2)
+    for k in l1:
+        if l1[k] is not None:
+            assert torch.equal(l1[k], l2[k]), k
+    if precision != "bf16":
+        phi = O.context(sd, yq.permute(0, 3, 1, 2))
+        ref = O.entropy_parameters_raw(sd, torch.cat([phi, psi.permute(0, 3, 1, 2)], dim=1))
+        err = float((raw2.cpu() - ref).abs().max() / ref.abs().max())
+        assert err < (2e-5 if precision == "fp32" else 1e-4), err
