@@ -227,22 +227,34 @@ class JointAutoregressiveHierarchical(nn.Module):
             branch2 = _branch_stream(x.device, 1)
             if branch2 is not None:
                 branch2.wait_stream(main_stream)
-            with (torch.cuda.stream(branch2) if branch2 is not None else contextlib.nullcontext()):
-                self.context_model.masked._op.run(y_in_nhwc, B, hy, wy, prec, out=combined, out_c_total=4 * M, out_c_offset=0,
-                                                  in_lo_flag=getattr(y_in_nhwc, "_nic_lo_flag", None))
+            # eager launches (no graph branches): context conv + 1x1 stack + likelihood kernel go out through ONE C-ABI call after
+            # h_s (nic_ctx_ep_fwd; same kernels, same results).  While a graph is captured the context conv is its own branch instead.
+            one_call = branch2 is None and os.environ.get("NIC_CTX_EP_ONE_CALL", "1") != "0"
+            y_flag = getattr(y_in_nhwc, "_nic_lo_flag", None)
+            if not one_call:
+                with (torch.cuda.stream(branch2) if branch2 is not None else contextlib.nullcontext()):
+                    self.context_model.masked._op.run(y_in_nhwc, B, hy, wy, prec, out=combined, out_c_total=4 * M, out_c_offset=0,
+                                                      in_lo_flag=y_flag)
             z, z_in, z_in_nhwc = _pair_h_a(self, y_src, B, hy, wy, training, noise_z, prec_up, prec)
             _pair_h_s_into(self, z_in_nhwc, B, hz, wz, prec, combined, 4 * M, 2 * M)
             if branch2 is not None:
                 main_stream.wait_stream(branch2)
 
-            # ---- entropy parameters (1x1 stack) ---------------------------------------------------
             ep = self.entropy_parameters.ops
-            a = ep[0].run(combined, B, hy, wy, prec)
-            a = ep[1].run(a, B, hy, wy, prec)
-            raw = ep[2].run(a, B, hy, wy, prec, out_layout=LAYOUT_NCHW, out_dtype=torch.float32)
-
-            # ---- likelihoods -------------------------------------------------------------------------
-            ly = gm_likelihood(y_in, raw, M, K, Q_PASSTHRU, full=not lean, want_y_in=False)
+            if one_call:
+                key = (B, hy, wy, prec, bool(lean), str(x.device))
+                plans = self.__dict__.setdefault("_ctx_ep_plans", {})
+                if key not in plans:
+                    plans.clear()                                # one shape at a time: the plan owns the two hidden activations
+                    plans[key] = engine.CtxEpPlan(self.context_model.masked._op, ep, B, hy, wy, prec, M, K, x.device, full=not lean)
+                raw, ly = plans[key].run(y_in_nhwc, combined, y_in=y_in, qmode=Q_PASSTHRU, in_lo_flag=y_flag)
+            else:
+                # ---- entropy parameters (1x1 stack) ---------------------------------------------------
+                a = ep[0].run(combined, B, hy, wy, prec)
+                a = ep[1].run(a, B, hy, wy, prec)
+                raw = ep[2].run(a, B, hy, wy, prec, out_layout=LAYOUT_NCHW, out_dtype=torch.float32)
+                # ---- likelihoods -------------------------------------------------------------------------
+                ly = gm_likelihood(y_in, raw, M, K, Q_PASSTHRU, full=not lean, want_y_in=False)
             _, p_z, logp_z, parts_z = self.factorized_entropy_model.likelihood(z_in, Q_PASSTHRU)
             p_y, logp_y = ly["p"], ly["logp"]
 
