@@ -288,8 +288,7 @@ class HierarchicalMixtureResidual(nn.Module):
     the entropy side on the same kernels as the 5x5 model.  With autograd enabled and training=True the call is the training
     step's forward (training.train_forward: one autograd node; backward = training.Tape over the same C-ABI backward kernels
     as the 5x5 model).  precision: "bf16x3" (default when latent_channels is a multiple of 64: tensor cores with hi/lo-
-    split operands; the 3-channel first block on the fp32 CUDA-core kernels) or "fp32".  The training step (backward) of this
-    family is not built: calling it with autograd enabled raises."""
+    split operands; the RGB-input convs of the first block on conv_smallcin_kernel in fp32) or "fp32"."""
 
     def __init__(self, latent_channels: int = 192, K: int = 1, *, precision: Optional[str] = None):
         super().__init__()
