@@ -373,6 +373,9 @@ int nic_gdn_reparam_bwd(int32_t c, float beta_min, const float* beta_raw, const 
 int nic_gdn_reparam(int32_t c, float beta_min, const float* beta_raw, const float* gamma_raw, float* beta_eff, float* gamma_eff,
                     float* gamma_eff_t, void* stream);
 int nic_gdn_apply(const float* u, const float* norm, int64_t n, int32_t inverse, float* out, void* stream);
+/* out = nic_gdn_apply(u, norm) + addend in one pass (the residual sum after the GDN / IGDN of ResidualBlockWithStride /
+ * ResidualBlockUpsample, Layers.py:58-60, 85-87); bit-identical to nic_gdn_apply followed by nic_add_inplace */
+int nic_gdn_apply_add(const float* u, const float* norm, const float* addend, int64_t n, int32_t inverse, float* out, void* stream);
 int nic_gdn_bwd_prep(const float* u, const float* g, const float* norm, int64_t n, int32_t inverse, float* t, float* du, void* stream);
 size_t nic_gdn_bwd_finish_workspace_bytes(int64_t pixels, int32_t c);
 int nic_gdn_bwd_finish(const float* u, const float* t, const float* r, int64_t pixels, int32_t c, float beta_min,

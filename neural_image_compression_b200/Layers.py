@@ -49,11 +49,12 @@ def _conv(arm, conv, epi, x, n, h, w, in_layout=LAYOUT_NHWC, out_layout=LAYOUT_N
     return (y,) + engine.conv_out_hw(conv, h, w)
 
 
-def _gdn(arm, gdn, u, n, h, w, tape=None):
+def _gdn(arm, gdn, u, n, h, w, tape=None, addend=None):
+    """GDN / IGDN; addend (evaluation only): + the block's skip branch in the same pass."""
     T = _T()
     if tape is not None:
         return tape.gdn(gdn, u, h, w)
-    y = T.gdn_forward(arm, gdn, u, n, h, w)[0]
+    y = T.gdn_forward(arm, gdn, u, n, h, w, addend=addend)[0]
     T.forget_pairs()
     return y
 
@@ -121,11 +122,14 @@ class ResidualBlockWithStride(_Block):
         T = _T()
         u, ho, wo = _conv(arm, self.conv1, EPI_LRELU, x, n, h, w, in_layout=in_layout, tape=tape, pair_out=True)
         u, _, _ = _conv(arm, self.conv2, EPI_BIAS, u, n, ho, wo, tape=tape)
-        out = _gdn(arm, self.gdn, u, n, ho, wo, tape=tape)
+        if tape is not None:
+            out = _gdn(arm, self.gdn, u, n, ho, wo, tape=tape)
         if self.skip is not None:
             idn, _, _ = _conv(arm, self.skip, EPI_BIAS, x, n, h, w, in_layout=in_layout, tape=tape)
         else:
             idn = x if in_layout == LAYOUT_NHWC else x.permute(0, 2, 3, 1).contiguous()
+        if tape is None:
+            return _gdn(arm, self.gdn, u, n, ho, wo, addend=idn), ho, wo            # GDN and the residual sum in one pass
         return _add(out, idn, tape), ho, wo
 
 
@@ -144,8 +148,11 @@ class ResidualBlockUpsample(_Block):
         T = _T()
         u, ho, wo = self.subpel_conv.run_nhwc(x, n, h, w, arm, in_layout=in_layout, epilogue=EPI_LRELU, tape=tape, pair_out=True)
         u, _, _ = _conv(arm, self.conv, EPI_BIAS, u, n, ho, wo, tape=tape)
-        out = _gdn(arm, self.igdn, u, n, ho, wo, tape=tape)
+        if tape is not None:
+            out = _gdn(arm, self.igdn, u, n, ho, wo, tape=tape)
         idn, _, _ = self.upsample.run_nhwc(x, n, h, w, arm, in_layout=in_layout, tape=tape)
+        if tape is None:
+            return _gdn(arm, self.igdn, u, n, ho, wo, addend=idn), ho, wo           # IGDN and the residual sum in one pass
         return _add(out, idn, tape), ho, wo
 
 

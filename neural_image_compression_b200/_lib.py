@@ -92,6 +92,7 @@ SIGNATURES = {
     "nic_to_pair": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "nic_gdn_reparam": (C.c_int, [_i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nic_gdn_apply": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "nic_gdn_apply_add": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "nic_gdn_bwd_prep": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "nic_gdn_bwd_du": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "nic_gdn_reparam_bwd": (C.c_int, [_i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -263,6 +263,16 @@ __global__ void gdn_apply_kernel(const float* __restrict__ u, const float* __res
     out[i] = inverse ? u[i] * sqrtf(nv) : u[i] * (1.0f / sqrtf(nv));
   }
 }
+// the same followed by the residual sum of the 3x3 blocks (Layers.py:58-60, 85-87): out = gdn(u) + addend.  The product is rounded
+// before the sum (no FMA contraction): bit-identical to nic_gdn_apply followed by nic_add_inplace, one pass over memory instead of two
+__global__ void gdn_apply_add_kernel(const float* __restrict__ u, const float* __restrict__ nrm, const float* __restrict__ addend, int inverse,
+                                     float* __restrict__ out, long n) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float nv = nrm[i];
+    const float y = inverse ? __fmul_rn(u[i], sqrtf(nv)) : __fmul_rn(u[i], 1.0f / sqrtf(nv));
+    out[i] = __fadd_rn(y, addend[i]);
+  }
+}
 __global__ void gdn_bwd_finish_kernel(const float* __restrict__ u, const float* __restrict__ r, float* __restrict__ du, long n) {
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
     du[i] = fmaf(2.0f * u[i], r[i], du[i]);
@@ -694,6 +704,14 @@ int nic_gdn_apply(const float* u, const float* norm, int64_t n, int32_t inverse,
   if (n == 0) return NIC_OK;
   gdn_apply_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(u, norm, inverse, out, n);
   return check_launch("gdn_apply_kernel");
+}
+
+int nic_gdn_apply_add(const float* u, const float* norm, const float* addend, int64_t n, int32_t inverse, float* out, void* stream) {
+  if (int rc = nic_check_device()) return rc;
+  if (n < 0 || (n > 0 && (!u || !norm || !addend || !out))) return fail(NIC_E_BADSHAPE, "gdn_apply_add: bad arguments");
+  if (n == 0) return NIC_OK;
+  gdn_apply_add_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(u, norm, addend, inverse, out, n);
+  return check_launch("gdn_apply_add_kernel");
 }
 
 int nic_gdn_bwd_prep(const float* u, const float* g, const float* norm, int64_t n, int32_t inverse, float* t, float* du, void* stream) {

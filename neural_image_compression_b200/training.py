@@ -206,16 +206,21 @@ def _gdn_tc(gdn: nn.Module):
     return st
 
 
-def gdn_forward(arm: str, gdn: nn.Module, u: torch.Tensor, n: int, h: int, w: int):
+def gdn_forward(arm: str, gdn: nn.Module, u: torch.Tensor, n: int, h: int, w: int, addend: Optional[torch.Tensor] = None):
     """GDN / IGDN of an NHWC f32 tensor -> (out, norm | None).  bf16x3 arm: the norm is a tensor-core 1x1 conv over the split
-    squares and is kept for the backward; fp32 arm: nic_gdn_fwd (the backward recomputes the norm)."""
+    squares and is kept for the backward; fp32 arm: nic_gdn_fwd (the backward recomputes the norm).
+    addend (evaluation chains of the residual family): out = gdn(u) + addend - in the bf16x3 arm in the same pass (nic_gdn_apply_add)."""
     lib = _lib.load()
     c = gdn.in_channels
     if arm == "bf16x3" and c % 64 == 0:
         st = _gdn_tc(gdn)
         norm = st["norm_op"].run(to_pair(u, square=True), n, h, w, "bf16x3", out_dtype=torch.float32)
         out = torch.empty_like(u)
-        check(lib.nic_gdn_apply(ptr(u), ptr(norm), u.numel(), int(gdn.inverse), ptr(out), current_stream()), "nic_gdn_apply")
+        if addend is not None:
+            check(lib.nic_gdn_apply_add(ptr(u), ptr(norm), ptr(addend), u.numel(), int(gdn.inverse), ptr(out), current_stream()),
+                  "nic_gdn_apply_add")
+        else:
+            check(lib.nic_gdn_apply(ptr(u), ptr(norm), u.numel(), int(gdn.inverse), ptr(out), current_stream()), "nic_gdn_apply")
         return out, norm
     gamma = _f32(c * c, u.device)
     beta = _f32(c, u.device)
@@ -223,6 +228,8 @@ def gdn_forward(arm: str, gdn: nn.Module, u: torch.Tensor, n: int, h: int, w: in
                            ptr(beta), ptr(gamma), PREC_FP32, current_stream()), "nic_pack_gdn")
     y = torch.empty_like(u)
     check(lib.nic_gdn_fwd(ptr(u), n, c, h, w, LAYOUT_NHWC, int(gdn.inverse), ptr(gamma), ptr(beta), ptr(y), current_stream()), "nic_gdn_fwd")
+    if addend is not None:
+        add_(y, addend)
     return y, None
 
 
